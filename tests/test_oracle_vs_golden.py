@@ -1,0 +1,93 @@
+"""CPU: pins oracle/ppo_oracle.py against vectors produced by the unmodified reference
+(oracle/make_golden.py -> tests/golden/*.npz)."""
+import numpy as np
+import pytest
+
+from oracle import ppo_oracle as O
+from tests.golden_util import cfg_of, flat, load, meta_of, params_from, rel_err, stream_of
+
+
+def test_gae_scan_is_bit_exact_and_normalisation_1e6():
+    g = load("gae_cases")
+    names = sorted({k.rsplit(".", 1)[0] for k in g.files if k.endswith(".returns")})
+    assert len(names) >= 13
+    for n in names:
+        gamma, lam = (0.9, 0.8) if n.startswith("odd") else (0.99, 0.95)
+        ret, adv = O.compute_returns(g[n + ".rewards"], g[n + ".values"], g[n + ".dones"], g[n + ".last_values"],
+                                     gamma, lam, normalize_advantage=n.endswith("norm"))
+        assert np.array_equal(ret, g[n + ".returns"]), n  # same fp32 op order -> identical bits
+        if n.endswith("raw"):
+            assert np.array_equal(adv, g[n + ".advantages"]), n
+        else:
+            assert rel_err(adv, g[n + ".advantages"]) < 1e-6, n
+
+
+@pytest.mark.parametrize("tag", ["clipped", "unclipped"])
+def test_loss_values_and_hand_derived_gradients(tag):
+    g = load("loss_terms")
+    f = lambda k: g[f"{tag}.{k}"]
+    out = O.ppo_loss_fwd_bwd(f("mu"), f("sigma"), f("value"), f("actions"), f("old_logp"), f("advantages"),
+                             f("returns"), f("old_values"), 0.2, 1.0, 0.01, tag == "clipped")
+    assert abs(out["surrogate"] - float(f("surrogate"))) < 1e-6 * max(1, abs(float(f("surrogate"))))
+    assert abs(out["value_loss"] - float(f("value_loss"))) < 1e-5 * abs(float(f("value_loss")))
+    assert abs(out["entropy"] - float(f("entropy"))) < 1e-6 * abs(float(f("entropy")))
+    assert rel_err(out["logp"], f("logp")) < 1e-6
+    assert rel_err(out["dmu"], f("dmu")) < 1e-5
+    assert rel_err(out["dsigma"], f("dsigma")) < 1e-5
+    assert rel_err(out["dvalue"], f("dvalue")) < 1e-5
+    kl = O.kl_mean(f("mu"), f("sigma"), f("old_mu"), f("old_sigma"))
+    assert abs(kl - float(f("kl"))) < 1e-5 * abs(float(f("kl")))
+    # the ratio must leave the clip range on both sides for the test to mean anything
+    assert (out["ratio"] > 1.2).any() and (out["ratio"] < 0.8).any()
+
+
+@pytest.mark.parametrize("name", ["ppo_mlp_small", "ppo_mlp_groups"])
+def test_full_learn_iterations_match_reference(name):
+    g = load(name)
+    meta = meta_of(g)
+    cfg = cfg_of(meta)
+    names = meta["param_names"]
+    params = params_from(g, "init", names)
+    adam = O.adam_init(params)
+    lr = cfg["learning_rate"]
+    for it in range(meta["iterations"]):
+        p = f"it{it}."
+        st, last_values, loss_dict, lr, trace = O.learn_iteration(
+            params, adam, lr, stream_of(g, it, meta), g[p + "z_rollout"], g[p + "perm"], cfg)
+        # rollout products
+        assert rel_err(st["actions"], g[p + "storage.actions"]) < 1e-5
+        assert rel_err(st["values"], g[p + "storage.values"]) < 1e-5
+        assert rel_err(st["actions_log_prob"], g[p + "storage.actions_log_prob"]) < 1e-5
+        assert rel_err(st["mu"], g[p + "storage.mu"]) < 1e-5
+        assert rel_err(st["sigma"], g[p + "storage.sigma"]) < 1e-6
+        assert rel_err(st["rewards"], g[p + "storage.rewards"]) < 1e-6
+        assert np.array_equal(st["dones"], g[p + "storage.dones"])
+        assert rel_err(st["returns"], g[p + "storage.returns"]) < 1e-5
+        assert rel_err(st["advantages"], g[p + "storage.advantages"]) < 1e-5
+        # per-minibatch trace
+        n_mb = len(trace)
+        assert n_mb == g[p + "mb.lr"].shape[0]
+        assert np.allclose([t["lr"] for t in trace], g[p + "mb.lr"], rtol=1e-12), "KL-adaptive lr sequence"
+        assert rel_err(trace[0]["grads"], g[p + "mb.raw_grads"][0]) < 1e-5
+        for i in range(n_mb):
+            assert rel_err(trace[i]["grads"], g[p + "mb.raw_grads"][i]) < 2e-4, i
+            assert abs(trace[i]["total_norm"] - g[p + "mb.total_norm"][i]) < 2e-4 * g[p + "mb.total_norm"][i]
+        # post-update state
+        assert rel_err(flat(params), g[p + "mb.params_after"][-1]) < 1e-5
+        assert rel_err(np.concatenate([v.reshape(-1) for v in adam["exp_avg"].values()]), g[p + "adam.exp_avg"]) < 1e-4
+        assert rel_err(np.concatenate([v.reshape(-1) for v in adam["exp_avg_sq"].values()]), g[p + "adam.exp_avg_sq"]) < 1e-4
+        assert adam["step"] == int(g[p + "adam.step"])
+        assert abs(lr - float(g[p + "learning_rate"])) < 1e-15
+
+
+def test_trajectory_split_pad_unpad_bit_exact():
+    g = load("trajectory_cases")
+    for n in ("small", "none", "all", "c4like"):
+        padded, masks = O.split_and_pad_trajectories(g[n + ".x"], g[n + ".dones"])
+        assert np.array_equal(masks, g[n + ".masks"]), n
+        assert np.array_equal(padded, g[n + ".padded"]), n
+        assert np.array_equal(O.unpad_trajectories(padded, masks), g[n + ".unpadded"]), n
+        assert np.array_equal(O.last_was_done(g[n + ".dones"]), g[n + ".last_was_done"]), n
+        assert np.array_equal(O.hidden_at_trajectory_starts(g[n + ".saved_hidden"], g[n + ".dones"]),
+                              g[n + ".hidden_at_starts"]), n
+        assert masks.sum() == g[n + ".x"].shape[0] * g[n + ".x"].shape[1]
