@@ -1,0 +1,234 @@
+/*
+ * rslrl_b200.h -- C ABI of the B200-native PPO learning-iteration kernels.
+ *
+ * The reference (kaixi287/rsl_rl v3.1.0) is pure Python on PyTorch and has no FFI of its own; the
+ * drop-in boundary is its Python class API.  This header is the boundary one
+ * level below: what the Python mirror in rsl_rl_b200/ binds with ctypes.  Every entry point cites
+ * the reference code whose arithmetic it replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the parameter name ends in `_host`;
+ *   - all tensors are dense row-major fp32 unless stated; sizes are element counts;
+ *   - `stream` is a cudaStream_t passed as void*; every call only enqueues work (no sync, no alloc);
+ *   - return value 0 = ok, non-zero = error (message via rslrl_last_error());
+ *   - no function falls back to the host: without a CUDA device every launch returns an error.
+ */
+#ifndef RSLRL_B200_H_
+#define RSLRL_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSLRL_ABI_VERSION 1
+#define RSLRL_MAX_SEGMENTS 16 /* max obs groups / gather fields per launch */
+#define RSLRL_MAX_PROBLEMS 4  /* max GEMM problems grouped into one launch */
+
+typedef void* rslrl_stream_t;
+
+/* ---- library plumbing ------------------------------------------------------------------------ */
+int rslrl_abi_version(void);
+const char* rslrl_last_error(void);
+/* number of kernel launches enqueued through this library since load / last reset */
+unsigned long long rslrl_launch_count(void);
+void rslrl_reset_launch_count(void);
+/* adds `n` to the launch counter: used by the host when it replays a captured CUDA graph of n of
+ * this library's kernels */
+void rslrl_add_launch_count(unsigned long long n);
+
+/* dtype codes for integer/bool inputs coming from the environment (VecEnv.step, env/vec_env.py:56-98) */
+enum { RSLRL_U8 = 0, RSLRL_I32 = 1, RSLRL_I64 = 2, RSLRL_F32 = 3 };
+/* activation codes (rsl_rl/utils/utils.py:18-49 resolve_nn_activation) */
+enum {
+  RSLRL_ACT_IDENTITY = 0, RSLRL_ACT_ELU = 1, RSLRL_ACT_RELU = 2, RSLRL_ACT_TANH = 3, RSLRL_ACT_SIGMOID = 4,
+  RSLRL_ACT_LRELU = 5, RSLRL_ACT_SELU = 6, RSLRL_ACT_SOFTPLUS = 7
+};
+/* GEMM arithmetic: fp32 CUDA-core FMA (1e-5 parity class) or TF32 tcgen05 tensor cores (1e-3 class) */
+enum { RSLRL_PREC_FP32 = 0, RSLRL_PREC_TF32 = 1 };
+/* action-noise parameterisation (rsl_rl/modules/actor_critic.py:88-93,133-138) */
+enum { RSLRL_STD_SCALAR = 0, RSLRL_STD_LOG = 1 };
+
+/* ---- rollout side ---------------------------------------------------------------------------- */
+
+/* Gaussian head of PPO.act (rsl_rl/algorithms/ppo.py:133-137; modules/actor_critic.py:133-146,170-171;
+ * torch.distributions.Normal.sample/log_prob):
+ *   sigma[a]   = std[a]            (RSLRL_STD_SCALAR)  |  exp(log_std[a])  (RSLRL_STD_LOG)
+ *   actions    = z * sigma + mu    (two roundings, as normal_().mul_().add_())
+ *   log_prob   = sum_a( -(a-mu)^2/(2 sigma^2) - log sigma - log sqrt(2 pi) )
+ * mu,z,actions,sigma_out: [n,A]; log_prob: [n].  sigma_out may be NULL. */
+int rslrl_gaussian_act(const float* mu, const float* std_param, int std_type, const float* z, float* actions,
+                       float* log_prob, float* sigma_out, int64_t n, int A, rslrl_stream_t stream);
+
+/* RolloutStorage.add_transitions (rsl_rl/storage/rollout_storage.py:77-103) fused with the reward
+ * handling of PPO.process_env_step (rsl_rl/algorithms/ppo.py:150-164):
+ *   rewards_row = rewards (+ intrinsic) + gamma * (values * time_outs)
+ * One launch writes row `step` of every [T,N,.] buffer; the *_row pointers already address that row.
+ * obs_src_host/obs_dst_host/obs_dim_host: host arrays with one entry per observation group.
+ * sigma_stride: 0 -> sigma is [A] and is broadcast, A -> sigma is [N,A].
+ * dones / time_outs: dtype codes above; time_outs and intrinsic may be NULL. */
+int rslrl_store_transition(int n_groups, const float* const* obs_src_host, float* const* obs_dst_host,
+                           const int* obs_dim_host, const float* actions, const float* mu, const float* sigma,
+                           int sigma_stride, const float* values, const float* log_prob, const float* rewards,
+                           const void* dones, int dones_dtype, const void* time_outs, int time_outs_dtype,
+                           const float* intrinsic, double gamma, float* actions_row, float* mu_row,
+                           float* sigma_row, float* values_row, float* log_prob_row, float* rewards_row,
+                           uint8_t* dones_row, int N, int A, rslrl_stream_t stream);
+
+/* RolloutStorage.compute_returns (rsl_rl/storage/rollout_storage.py:127-149): reverse GAE scan over T
+ * with done masking, returns, advantages = returns - values, and (normalize != 0) the global
+ * (adv - mean) / (std_unbiased + 1e-8) normalisation, in ONE cooperative kernel.
+ * rewards/values/returns/advantages: [T,N] fp32, dones: [T,N] u8, last_values: [N].
+ * workspace: rslrl_gae_workspace_bytes(N) bytes of device scratch (need not be zeroed). */
+int64_t rslrl_gae_workspace_bytes(int N);
+int rslrl_gae_norm(const float* rewards, const float* values, const uint8_t* dones, const float* last_values,
+                   float* returns, float* advantages, void* workspace, int T, int N, double gamma, double lam,
+                   int normalize, rslrl_stream_t stream);
+
+/* ---- minibatch construction ------------------------------------------------------------------ */
+
+/* RolloutStorage.mini_batch_generator's `x.flatten(0,1)[batch_idx]` for several fields at once
+ * (rsl_rl/storage/rollout_storage.py:168-197).  For field f and output row j:
+ *   dst[f][j*dst_stride[f] + dst_col[f] + c] = src[f][idx[j]*row_floats[f] + c],  c < row_floats[f]
+ * (dst_stride/dst_col let several observation groups be concatenated into one matrix, which also
+ * absorbs the torch.cat of modules/actor_critic.py:158-168).  idx: int64 [n_rows]. */
+int rslrl_permute_gather(int n_fields, const float* const* src_host, float* const* dst_host,
+                         const int* row_floats_host, const int* dst_stride_host, const int* dst_col_host,
+                         const int64_t* idx, int64_t n_rows, rslrl_stream_t stream);
+
+/* ---- dense layers (rsl_rl/networks/mlp.py:106-114 forward; autograd backward of nn.Linear + activation) */
+
+typedef struct {
+  const float* x; /* [M,K], row stride ldx */
+  const float* w; /* [N,K] row-major (nn.Linear.weight), row stride K */
+  const float* b; /* [N] or NULL */
+  float* y;       /* [M,N], row stride ldy */
+  int M, N, K, ldx, ldy;
+  int act;        /* RSLRL_ACT_* applied to x W^T + b */
+} rslrl_linear_fwd_t;
+
+typedef struct {
+  const float* dy; /* [M,N], row stride ldy : gradient w.r.t. this layer's pre-activation output */
+  const float* w;  /* [N,K] */
+  const float* h;  /* [M,K], row stride ldh : this layer's INPUT (= previous layer's activation output) */
+  float* dx;       /* [M,K], row stride ldx : gradient w.r.t. previous layer's pre-activation */
+  int M, N, K, ldy, ldh, ldx;
+  int act;         /* activation of the PREVIOUS layer: dx = (dy W) * act'(.) evaluated from h */
+} rslrl_linear_bwd_data_t;
+
+typedef struct {
+  const float* dy; /* [M,N], row stride ldy */
+  const float* x;  /* [M,K], row stride ldx */
+  float* dw;       /* [N,K] accumulated:  dw += dy^T x */
+  float* db;       /* [N]   accumulated:  db += colsum(dy); may be NULL */
+  int M, N, K, ldy, ldx;
+} rslrl_linear_bwd_weight_t;
+
+/* Each call runs `n` independent problems (e.g. actor and critic) in one launch; *_host arrays live
+ * in host memory and are copied into the kernel parameters. */
+int rslrl_linear_forward(int n, const rslrl_linear_fwd_t* probs_host, int precision, rslrl_stream_t stream);
+int rslrl_linear_backward_data(int n, const rslrl_linear_bwd_data_t* probs_host, int precision,
+                               rslrl_stream_t stream);
+int rslrl_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* probs_host, int precision,
+                                 rslrl_stream_t stream);
+
+/* ---- PPO objective (rsl_rl/algorithms/ppo.py:255-315), forward + hand-derived backward ---------- */
+
+/* rows = num_aug * mb_orig samples (symmetry augmentation repeats the per-sample scalars,
+ * ppo.py:240-244: they are indexed i % mb_orig here instead of being materialised).
+ *   mu [rows,A], value [rows], actions [rows,A]
+ *   old_logp/advantages/returns/old_values [mb_orig], old_mu/old_sigma [mb_orig,A]
+ *   std_param [A] (std or log_std according to std_type)
+ *   adv_stats: NULL, or double[2] = {sum, sumsq} of `advantages` for the per-minibatch
+ *              normalisation of ppo.py:221-223
+ * outputs
+ *   dmu [rows,A], dvalue [rows]   (dL/dmu, dL/dvalue of loss = surr + c_v*vloss - c_e*entropy)
+ *   dstd [A]   += dL/dstd_param   (accumulated)
+ *   kl_out [1]  = mean KL(old||new) over the first mb_orig rows as fp32 (ppo.py:262-269); may alias
+ *                 the tail slot of the flat gradient buffer so that it rides the gradient all-reduce
+ *   loss_sums  double[3] += {surrogate_mean, value_loss_mean, entropy_mean} of this minibatch
+ *   workspace  rslrl_loss_workspace_bytes() bytes, zero-initialised once by the caller */
+int64_t rslrl_loss_workspace_bytes(void);
+int rslrl_ppo_loss_fwd_bwd(const float* mu, const float* std_param, int std_type, const float* value,
+                           const float* actions, const float* old_logp, const float* advantages,
+                           const float* returns, const float* old_values, const float* old_mu,
+                           const float* old_sigma, const double* adv_stats, float* dmu, float* dvalue,
+                           float* dstd, float* kl_out, double* loss_sums, void* workspace, int64_t rows,
+                           int64_t mb_orig, int A, double clip_param, double value_loss_coef,
+                           double entropy_coef, int use_clipped_value_loss, rslrl_stream_t stream);
+
+/* sum and sum of squares of x[0..n) into out[2] (double, overwritten): statistics for
+ * ppo.py:221-223 per-minibatch advantage normalisation. */
+int rslrl_sum_sumsq(const float* x, int64_t n, double* out, void* workspace, rslrl_stream_t stream);
+
+/* ---- optimiser (rsl_rl/algorithms/ppo.py:260-294 KL-adaptive LR, :380 clip_grad_norm_, :381 Adam) -- */
+
+/* Device-resident optimiser scalars, one per parameter group (policy / RND predictor). */
+typedef struct {
+  double lr;          /* learning rate used by the NEXT adam kernel */
+  double clip_scale;  /* clip_coef / world_size, applied to the (summed) gradient */
+  double total_norm;  /* L2 norm of the averaged gradient before clipping */
+  double step_size;   /* lr / (1 - beta1^t) */
+  double bc2_sqrt;    /* sqrt(1 - beta2^t) */
+  double kl_mean;     /* last averaged KL (diagnostic) */
+  long long step;     /* Adam step count t */
+  long long pad_;
+} rslrl_opt_state_t;
+
+/* Pass 1 over the flat gradient buffer g[0..P):  total_norm = ||g / world||_2,
+ * clip_scale = min(1, max_norm / (total_norm + 1e-6)) / world   (torch clip_grad_norm_ semantics;
+ * max_norm <= 0 disables clipping), then -- if adaptive != 0 -- the KL rule of ppo.py:280-284 on
+ * kl = *kl_sum / world (lr /= 1.5 if kl > 2 d, lr *= 1.5 if 0 < kl < d/2, clamped to [1e-5,1e-2];
+ * round_lr_fp32 != 0 reproduces the fp32 broadcast of ppo.py:288-290 in multi-GPU mode), then
+ * step += 1 and the bias corrections.  All scalars stay on the device in *state. */
+int64_t rslrl_optim_workspace_bytes(int64_t P);
+int rslrl_grad_norm_lr(const float* g, int64_t P, const float* kl_sum, rslrl_opt_state_t* state, void* workspace,
+                       int world_size, double max_grad_norm, int adaptive, double desired_kl, int round_lr_fp32,
+                       double beta1, double beta2, rslrl_stream_t stream);
+
+/* Pass 2: torch.optim.Adam (weight_decay=0, amsgrad=False) on the flat buffers with g' = g*clip_scale:
+ *   m += (g'-m)(1-beta1);  v = beta2 v + (1-beta2) g'^2;  p -= step_size * m / (sqrt(v)/bc2_sqrt + eps)
+ * zero_grad != 0 clears g afterwards (the backward kernels accumulate). */
+int rslrl_adam_step(float* p, float* g, float* m, float* v, int64_t P, const rslrl_opt_state_t* state,
+                    double beta1, double beta2, double eps, int zero_grad, rslrl_stream_t stream);
+
+/* ---- recurrent minibatches (rsl_rl/utils/utils.py:78-141; storage/rollout_storage.py:206-260) ---- */
+
+/* Segmented scan over dones[T,N] (u8).  Trajectories are enumerated env-major (all pieces of env 0,
+ * then env 1, ...); a piece ends at a done step and at t = T-1 (utils.py:97-98).  Outputs (int32):
+ *   traj_id [T,N], traj_pos [T,N]   trajectory index and position inside it for every (t, env)
+ *   traj_len / traj_env / traj_start [T*N capacity]  per trajectory: length, env, first time step
+ *   env_traj_offset [N+1]            exclusive scan of trajectories per env; [N] = n_traj
+ * workspace: rslrl_traj_workspace_bytes(T,N) bytes. */
+int64_t rslrl_traj_workspace_bytes(int T, int N);
+int rslrl_trajectory_index(const uint8_t* dones, int T, int N, int32_t* traj_id, int32_t* traj_pos,
+                           int32_t* traj_len, int32_t* traj_env, int32_t* traj_start, int32_t* env_traj_offset,
+                           void* workspace, rslrl_stream_t stream);
+/* masks[t*capacity + j] = (first_traj + j < n_traj_end && traj_len[first_traj + j] > t), u8, j < capacity
+ * (utils.py:129 trajectory_masks) */
+int rslrl_trajectory_masks(const int32_t* traj_len, uint8_t* masks, int T, int first_traj, int n_traj_end,
+                           int capacity, rslrl_stream_t stream);
+/* split_and_pad_trajectories (utils.py:106-127) for trajectories [first_traj, first_traj+capacity):
+ *   padded[p, j, :] = x[traj_start[J]+p, traj_env[J], :] if J = first_traj+j < n_traj_end and p < traj_len[J]
+ *                     else 0;   x: [T,N,D], padded: [T,capacity,D] (every element written once). */
+int rslrl_split_and_pad(const float* x, const int32_t* traj_len, const int32_t* traj_env,
+                        const int32_t* traj_start, float* padded, int T, int N, int D, int first_traj,
+                        int n_traj_end, int capacity, rslrl_stream_t stream);
+/* unpad_trajectories (utils.py:134-141): out[t, env-env0, :] = padded[traj_pos[t,env], traj_id[t,env]-first_traj, :]
+ * for env in [env0, env1); out: [T, env1-env0, D]. */
+int rslrl_unpad(const float* padded, const int32_t* traj_id, const int32_t* traj_pos, float* out, int T, int N,
+                int D, int env0, int env1, int first_traj, int capacity, rslrl_stream_t stream);
+/* hidden states at trajectory starts (rollout_storage.py:238-250): saved [T,L,N,H] ->
+ *   out[l, j, :] = saved[traj_start[J], l, traj_env[J], :],  J = first_traj + j < n_traj_end; out: [L,capacity,H] */
+int rslrl_hidden_at_starts(const float* saved, const int32_t* traj_env, const int32_t* traj_start, float* out,
+                           int T, int L, int N, int H, int first_traj, int n_traj_end, int capacity,
+                           rslrl_stream_t stream);
+
+/* ---- small utilities ------------------------------------------------------------------------- */
+int rslrl_fill_zero(void* p, int64_t bytes, rslrl_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSLRL_B200_H_ */

@@ -1,0 +1,175 @@
+"""ctypes binding of `include/rslrl_b200.h` (the C ABI of the sm_100a kernels).
+
+There is exactly one arithmetic back end.  If the shared library is missing, or a call is made with
+tensors that are not on a CUDA device, this module raises -- it never computes anything on the host.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import torch
+
+from . import _build
+
+c_void_p, c_int, c_i64, c_double = C.c_void_p, C.c_int, C.c_int64, C.c_double
+
+# enums of include/rslrl_b200.h
+U8, I32, I64, F32 = 0, 1, 2, 3
+ACT_CODES = {"identity": 0, "elu": 1, "relu": 2, "tanh": 3, "sigmoid": 4, "lrelu": 5, "selu": 6, "softplus": 7,
+             "crelu": 1}  # nn.CELU(alpha=1) == nn.ELU(alpha=1)
+PREC_FP32, PREC_TF32 = 0, 1
+PREC_CODES = {"fp32": PREC_FP32, "tf32": PREC_TF32}
+STD_SCALAR, STD_LOG = 0, 1
+MAX_SEGMENTS, MAX_PROBLEMS = 16, 4
+
+
+class LinearFwd(C.Structure):
+    _fields_ = [("x", c_void_p), ("w", c_void_p), ("b", c_void_p), ("y", c_void_p),
+                ("M", c_int), ("N", c_int), ("K", c_int), ("ldx", c_int), ("ldy", c_int), ("act", c_int)]
+
+
+class LinearBwdData(C.Structure):
+    _fields_ = [("dy", c_void_p), ("w", c_void_p), ("h", c_void_p), ("dx", c_void_p),
+                ("M", c_int), ("N", c_int), ("K", c_int), ("ldy", c_int), ("ldh", c_int), ("ldx", c_int),
+                ("act", c_int)]
+
+
+class LinearBwdWeight(C.Structure):
+    _fields_ = [("dy", c_void_p), ("x", c_void_p), ("dw", c_void_p), ("db", c_void_p),
+                ("M", c_int), ("N", c_int), ("K", c_int), ("ldy", c_int), ("ldx", c_int)]
+
+
+class OptState(C.Structure):
+    _fields_ = [("lr", c_double), ("clip_scale", c_double), ("total_norm", c_double), ("step_size", c_double),
+                ("bc2_sqrt", c_double), ("kl_mean", c_double), ("step", C.c_longlong), ("pad_", C.c_longlong)]
+
+
+OPT_STATE_DOUBLES = C.sizeof(OptState) // 8  # the struct is viewed as 8 x 8-byte words on the device
+
+_SIGNATURES = {
+    "rslrl_abi_version": (c_int, []),
+    "rslrl_last_error": (C.c_char_p, []),
+    "rslrl_launch_count": (C.c_ulonglong, []),
+    "rslrl_reset_launch_count": (None, []),
+    "rslrl_add_launch_count": (None, [C.c_ulonglong]),
+    "rslrl_gaussian_act": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int,
+                                   c_void_p]),
+    "rslrl_store_transition": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p,
+                                       c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_int, c_int, c_void_p]),
+    "rslrl_gae_workspace_bytes": (c_i64, [c_int]),
+    "rslrl_gae_norm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                               c_double, c_double, c_int, c_void_p]),
+    "rslrl_permute_gather": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64,
+                                     c_void_p]),
+    "rslrl_linear_forward": (c_int, [c_int, c_void_p, c_int, c_void_p]),
+    "rslrl_linear_backward_data": (c_int, [c_int, c_void_p, c_int, c_void_p]),
+    "rslrl_linear_backward_weight": (c_int, [c_int, c_void_p, c_int, c_void_p]),
+    "rslrl_loss_workspace_bytes": (c_i64, []),
+    "rslrl_sum_sumsq": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_void_p]),
+    "rslrl_optim_workspace_bytes": (c_i64, [c_i64]),
+    "rslrl_grad_norm_lr": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_int, c_double, c_int, c_double,
+                                   c_int, c_double, c_double, c_void_p]),
+    "rslrl_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_double, c_double, c_double,
+                                c_int, c_void_p]),
+    "rslrl_traj_workspace_bytes": (c_i64, [c_int, c_int]),
+    "rslrl_trajectory_index": (c_int, [c_void_p, c_int, c_int] + [c_void_p] * 8),
+    "rslrl_trajectory_masks": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "rslrl_split_and_pad": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_void_p]),
+    "rslrl_unpad": (c_int, [c_void_p] * 4 + [c_int] * 7 + [c_void_p]),
+    "rslrl_hidden_at_starts": (c_int, [c_void_p] * 4 + [c_int] * 7 + [c_void_p]),
+    "rslrl_fill_zero": (c_int, [c_void_p, c_i64, c_void_p]),
+}
+
+# the ppo_loss signature above is easier to read spelled out:
+_SIGNATURES["rslrl_ppo_loss_fwd_bwd"] = (c_int, [
+    c_void_p, c_void_p, c_int, c_void_p,            # mu, std_param, std_type, value
+    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,  # actions, old_logp, advantages, returns, old_values
+    c_void_p, c_void_p, c_void_p,                   # old_mu, old_sigma, adv_stats
+    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,  # dmu, dvalue, dstd, kl_out, loss_sums, workspace
+    c_i64, c_i64, c_int, c_double, c_double, c_double, c_int, c_void_p])
+
+_lib = None
+
+
+def library_path() -> str:
+    return _build.LIBPATH
+
+
+def lib():
+    """The loaded shared library; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise RuntimeError(
+                f"rsl_rl_b200: native library {path} is missing. Build it with "
+                "`python -c 'import __graft_entry__ as g; g.build()'` (or `python -m rsl_rl_b200._build`). "
+                "There is no PyTorch/CPU fallback for the PPO kernels.")
+        handle = C.CDLL(path)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError here == header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        if handle.rslrl_abi_version() != 1:
+            raise RuntimeError("rsl_rl_b200: ABI version mismatch between _native.py and the shared library")
+        _lib = handle
+    return _lib
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def check(rc: int):
+    if rc != 0:
+        raise RuntimeError("rsl_rl_b200 native call failed: " + lib().rslrl_last_error().decode())
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def require_cuda(*tensors: torch.Tensor):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("rsl_rl_b200 kernels need CUDA tensors (got a tensor on %s); there is no CPU path"
+                               % t.device)
+
+
+def f32c(t: torch.Tensor) -> torch.Tensor:
+    """fp32 + contiguous view of `t` (copies only when needed)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+_FLAG_DTYPES = {torch.uint8: U8, torch.bool: U8, torch.int32: I32, torch.int64: I64, torch.float32: F32}
+
+
+def flag_tensor(t: torch.Tensor):
+    """(tensor, dtype code) for dones / time_outs coming from the env in any integer/bool/float dtype."""
+    if t.dtype not in _FLAG_DTYPES:
+        t = t.to(torch.float32)
+    if not t.is_contiguous():
+        t = t.contiguous()
+    return t, _FLAG_DTYPES[t.dtype]
+
+
+def void_array(ptrs: Sequence[Optional[int]]):
+    return (c_void_p * len(ptrs))(*ptrs)
+
+
+def int_array(vals: Sequence[int]):
+    return (c_int * len(vals))(*vals)
+
+
+def launch_count() -> int:
+    return int(lib().rslrl_launch_count())

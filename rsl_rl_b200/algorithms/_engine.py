@@ -1,0 +1,146 @@
+"""Launch plans for the feed-forward PPO path: rollout step, last-value evaluation and update().
+
+`FeedForwardEngine` owns every scratch buffer (activations, gradients, permuted minibatch copy) and
+turns one PPO phase into a fixed sequence of C-ABI kernel launches with static pointers:
+
+  rollout step   L grouped Linear launches (actor + critic in one grid) -> gaussian head
+                 (outputs land directly in row `step` of the rollout buffer)
+  update()       1 gather launch for the WHOLE batch (the permutation is the same for every epoch,
+                 reference rollout_storage.py:165, so the buffer is permuted once and minibatch i is
+                 the contiguous row block i), then per minibatch:
+                 L forward launches -> fused loss fwd+bwd -> L wgrad + (L-1) dgrad launches ->
+                 [gradient all-reduce] -> grad-norm/KL/LR kernel -> Adam kernel
+                 with every scalar (KL, lr, Adam step, loss sums) resident on the device.
+
+Because pointers and shapes are static and nothing returns to the host, the whole update() is captured
+once into a CUDA graph and replayed (single-GPU); the host reads back 128 bytes per update().
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from .. import _native as nat
+from ..networks.mlp import MLP, linear_backward_data, linear_backward_weight, linear_forward
+from .flat_params import FlatParamGroup, FusedAdam
+
+
+class _Net:
+    """One MLP (actor or critic) seen as lists of (weight, bias, activation code)."""
+
+    def __init__(self, mlp: MLP):
+        self.layers: List[nn.Linear] = mlp.linear_layers()
+        self.acts = mlp.layer_activation_codes()
+        self.dims = [self.layers[0].in_features] + [l.out_features for l in self.layers]
+        self.L = len(self.layers)
+
+
+def supports(policy) -> Optional[str]:
+    """None if the fused feed-forward engine can drive `policy`, else the reason it cannot."""
+    from ..modules.actor_critic import ActorCritic
+
+    if type(policy) is not ActorCritic:
+        return f"policy class {type(policy).__name__} is not the feed-forward ActorCritic"
+    if policy.state_dependent_std:
+        return "state_dependent_std"
+    for mlp in (policy.actor, policy.critic):
+        if any(isinstance(m, nn.Unflatten) for m in mlp):
+            return "tuple-shaped MLP output"
+        if mlp.layer_activation_codes()[-1] != 0:
+            return "last_activation"
+    return None
+
+
+class FeedForwardEngine:
+    def __init__(self, policy, storage_rows: int, num_envs: int, minibatch_rows: int, device, precision: str):
+        self.policy = policy
+        self.device = torch.device(device)
+        self.prec = nat.PREC_CODES[precision]
+        self.actor, self.critic = _Net(policy.actor), _Net(policy.critic)
+        self.A = self.actor.dims[-1]
+        self.std_param = policy.std if policy.noise_std_type == "scalar" else policy.log_std
+        self.std_type = nat.STD_SCALAR if policy.noise_std_type == "scalar" else nat.STD_LOG
+        self.rows = max(num_envs, minibatch_rows)
+        f32 = dict(dtype=torch.float32, device=self.device)
+        R = self.rows
+        # activations (outputs of hidden layers) and ping-pong gradient buffers
+        self.h_a = [torch.empty(R, d, **f32) for d in self.actor.dims[1:-1]]
+        self.h_c = [torch.empty(R, d, **f32) for d in self.critic.dims[1:-1]]
+        wa, wc = max(self.actor.dims[1:-1] + [1]), max(self.critic.dims[1:-1] + [1])
+        self.g_a = [torch.empty(R * wa, **f32) for _ in range(2)]
+        self.g_c = [torch.empty(R * wc, **f32) for _ in range(2)]
+        self.mu = torch.empty(R, self.A, **f32)
+        self.value = torch.empty(R, 1, **f32)
+        self.dmu = torch.empty(R, self.A, **f32)
+        self.dvalue = torch.empty(R, 1, **f32)
+        self.loss_ws = torch.zeros(int(nat.lib().rslrl_loss_workspace_bytes()), dtype=torch.uint8, device=self.device)
+        self.sum_ws = torch.zeros(64, dtype=torch.uint8, device=self.device)
+        self.adv_stats = torch.zeros(2, dtype=torch.float64, device=self.device)
+
+    # ---------------------------------------------------------------------------------------------
+    def forward(self, x_a: torch.Tensor, x_c: torch.Tensor, mu_out: torch.Tensor, v_out: torch.Tensor,
+                actor: bool = True, critic: bool = True):
+        """Grouped forward of actor and critic on M = x.shape[0] rows; hidden activations stay in
+        self.h_a / self.h_c (rows [:M]) for the backward pass."""
+        M = (x_a if actor else x_c).shape[0]
+        La, Lc = self.actor.L if actor else 0, self.critic.L if critic else 0
+        in_a, in_c = x_a, x_c
+        for l in range(max(La, Lc)):
+            probs = []
+            if l < La:
+                lin = self.actor.layers[l]
+                out = mu_out if l == La - 1 else self.h_a[l][:M]
+                probs.append((in_a, lin.weight, lin.bias, out, self.actor.acts[l]))
+                in_a = out
+            if l < Lc:
+                lin = self.critic.layers[l]
+                out = v_out if l == Lc - 1 else self.h_c[l][:M]
+                probs.append((in_c, lin.weight, lin.bias, out, self.critic.acts[l]))
+                in_c = out
+            linear_forward(probs, self.prec)
+
+    def backward(self, x_a: torch.Tensor, x_c: torch.Tensor, dmu: torch.Tensor, dvalue: torch.Tensor):
+        """dL/dW, dL/db accumulated into the parameters' .grad views (flat gradient buffer)."""
+        M = x_a.shape[0]
+        nets = ((self.actor, self.h_a, self.g_a, x_a, dmu), (self.critic, self.h_c, self.g_c, x_c, dvalue))
+        dy = [dmu, dvalue]
+        for k in range(max(self.actor.L, self.critic.L)):
+            wprobs, dprobs, new_dy = [], [], list(dy)
+            for ni, (net, hs, gbuf, x_in, _) in enumerate(nets):
+                l = net.L - 1 - k
+                if l < 0:
+                    continue
+                lin = net.layers[l]
+                inp = x_in if l == 0 else hs[l - 1][:M]
+                wprobs.append((dy[ni], inp, lin.weight.grad, lin.bias.grad))
+                if l > 0:
+                    dx = gbuf[k % 2][:M * net.dims[l]].view(M, net.dims[l])
+                    dprobs.append((dy[ni], lin.weight, inp, dx, net.acts[l - 1]))
+                    new_dy[ni] = dx
+            linear_backward_weight(wprobs, self.prec)
+            if dprobs:
+                linear_backward_data(dprobs, self.prec)
+            dy = new_dy
+
+    def gaussian_head(self, mu, z, actions_out, logp_out, sigma_out):
+        nat.check(nat.lib().rslrl_gaussian_act(mu.data_ptr(), self.std_param.data_ptr(), self.std_type, z.data_ptr(),
+                                               actions_out.data_ptr(), logp_out.data_ptr(), nat.ptr(sigma_out),
+                                               mu.shape[0], self.A, nat.stream_ptr()))
+
+    def loss(self, rows: int, mb_orig: int, mu, value, actions, old_logp, adv, returns, old_values, old_mu, old_sigma,
+             kl_out, loss_sums, hp, per_mb_norm: bool):
+        L = nat.lib()
+        stats_ptr = None
+        if per_mb_norm:
+            nat.check(L.rslrl_sum_sumsq(adv.data_ptr(), mb_orig, self.adv_stats.data_ptr(), self.sum_ws.data_ptr(),
+                                        nat.stream_ptr()))
+            stats_ptr = self.adv_stats.data_ptr()
+        nat.check(L.rslrl_ppo_loss_fwd_bwd(
+            mu.data_ptr(), self.std_param.data_ptr(), self.std_type, value.data_ptr(), actions.data_ptr(),
+            old_logp.data_ptr(), adv.data_ptr(), returns.data_ptr(), old_values.data_ptr(), old_mu.data_ptr(),
+            old_sigma.data_ptr(), stats_ptr, self.dmu.data_ptr(), self.dvalue.data_ptr(),
+            self.std_param.grad.data_ptr(), nat.ptr(kl_out), nat.ptr(loss_sums), self.loss_ws.data_ptr(), rows,
+            mb_orig, self.A, hp["clip_param"], hp["value_loss_coef"], hp["entropy_coef"],
+            int(hp["use_clipped_value_loss"]), nat.stream_ptr()))

@@ -1,0 +1,179 @@
+"""Flat parameter / gradient / Adam-moment buffers with the parameters re-bound as views.
+
+The reference keeps 17 separate parameter tensors, concatenates their gradients for every all-reduce
+(`torch.cat` + 17 `copy_` back, rsl_rl/algorithms/ppo.py:441-469) and steps them with foreach-Adam.
+Here a parameter group owns four flat fp32 buffers in HBM -- values, gradients, exp_avg, exp_avg_sq --
+laid out in `module.parameters()` order (`[std, actor.0.weight, actor.0.bias, ...]`, the reference's
+own flattening order), each tensor starting on a 16-byte boundary.  `param.data` and `param.grad`
+are views, so state_dict()/load_state_dict()/checkpoints see ordinary tensors while the kernels see
+one contiguous span: the gradient all-reduce is in place, clip+Adam is two launches.
+
+One extra 16-byte tail after the gradients carries the minibatch KL so that it rides the same
+all-reduce (reference: a separate 4-byte all-reduce plus a broadcast per minibatch, ppo.py:272-290).
+"""
+from __future__ import annotations
+
+from typing import Iterable, List
+
+import torch
+import torch.nn as nn
+
+from .. import _native as nat
+
+ALIGN = 4  # floats (16 bytes): float4 accesses and TMA base alignment
+
+
+class FlatParamGroup:
+    def __init__(self, params: Iterable[nn.Parameter], device):
+        self.params: List[nn.Parameter] = [p for p in params]
+        if not self.params:
+            raise ValueError("FlatParamGroup needs at least one parameter")
+        self.device = torch.device(device)
+        self.offsets: List[int] = []
+        off = 0
+        for p in self.params:
+            if p.dtype != torch.float32:
+                raise TypeError("rsl_rl_b200 keeps parameters in fp32")
+            self.offsets.append(off)
+            off += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
+        self.numel = off  # padded element count P
+        f32 = dict(dtype=torch.float32, device=self.device)
+        self.values = torch.zeros(off, **f32)
+        self.grads_ext = torch.zeros(off + ALIGN, **f32)  # gradients + KL tail
+        self.grads = self.grads_ext[:off]
+        self.kl_slot = self.grads_ext[off:off + 1]
+        self.exp_avg = torch.zeros(off, **f32)
+        self.exp_avg_sq = torch.zeros(off, **f32)
+        self.bind()
+
+    def _view(self, flat: torch.Tensor, i: int) -> torch.Tensor:
+        p = self.params[i]
+        return flat[self.offsets[i]:self.offsets[i] + p.numel()].view(p.shape)
+
+    def bind(self):
+        """Copies the current parameter values into the flat buffer and re-points param.data/.grad."""
+        with torch.no_grad():
+            for i, p in enumerate(self.params):
+                v = self._view(self.values, i)
+                if p.data.data_ptr() != v.data_ptr():
+                    v.copy_(p.data)
+                    p.data = v
+                g = self._view(self.grads, i)
+                if p.grad is None or p.grad.data_ptr() != g.data_ptr():
+                    if p.grad is not None:
+                        g.copy_(p.grad)
+                    p.grad = g
+
+    def is_bound(self) -> bool:
+        base = self.values.data_ptr()
+        gbase = self.grads.data_ptr()
+        for off, p in zip(self.offsets, self.params):
+            if p.data.data_ptr() != base + 4 * off or p.grad is None or p.grad.data_ptr() != gbase + 4 * off:
+                return False
+        return True
+
+    def ensure_bound(self):
+        if not self.is_bound():
+            self.bind()
+
+    def moment_views(self, i: int):
+        return self._view(self.exp_avg, i), self._view(self.exp_avg_sq, i)
+
+    def zero_grad(self):
+        nat.check(nat.lib().rslrl_fill_zero(self.grads_ext.data_ptr(), self.grads_ext.numel() * 4, nat.stream_ptr()))
+
+
+class DeviceOptState:
+    """`rslrl_opt_state_t` in device memory followed by the loss accumulators, read back with ONE copy.
+
+    layout (8-byte words): [0] lr [1] clip_scale [2] total_norm [3] step_size [4] bc2_sqrt [5] kl_mean
+                           [6] step (int64) [7] pad | [8..10] loss sums (surrogate, value, entropy) [11..15] spare
+    """
+
+    WORDS = 16
+
+    def __init__(self, device, lr: float):
+        self.buf = torch.zeros(self.WORDS, dtype=torch.float64, device=device)
+        self.as_int = self.buf.view(torch.int64)
+        self.buf[0] = lr
+        self.loss_sums = self.buf[8:11]
+
+    def ptr(self) -> int:
+        return self.buf.data_ptr()
+
+    def set_lr(self, lr: float):
+        self.buf[0:1].fill_(lr)
+
+    def set_step(self, step: int):
+        self.as_int[6:7].fill_(int(step))
+
+    def read(self):
+        host = self.buf.cpu()
+        step = int(host.view(torch.int64)[6])
+        return dict(lr=float(host[0]), clip_scale=float(host[1]), total_norm=float(host[2]), kl_mean=float(host[5]),
+                    step=step, loss_sums=[float(host[8]), float(host[9]), float(host[10])])
+
+
+class FusedAdam(torch.optim.Adam):
+    """`torch.optim.Adam` whose state lives in a FlatParamGroup and whose step is the fused
+    clip + KL-adaptive-LR + Adam kernel pair.
+
+    It is a real `torch.optim.Adam` (default hyper-parameters; `state_dict()` has the usual `exp_avg`,
+    `exp_avg_sq`, `step` entries per parameter, so reference checkpoints load and save unchanged,
+    reference on_policy_runner.py:289-324).  `step()` without arguments behaves like the stock optimiser
+    (it runs on the same flat-buffer views); the PPO update calls `fused_step()`.
+    """
+
+    def __init__(self, group: FlatParamGroup, lr: float):
+        super().__init__(group.params, lr=lr, foreach=None, capturable=False, fused=None)
+        self.group = group
+        self.dev_state = DeviceOptState(group.device, lr)
+        self._opt_ws = torch.zeros(int(nat.lib().rslrl_optim_workspace_bytes(group.numel)), dtype=torch.uint8,
+                                   device=group.device)
+        self._host_step = 0
+        self._install_state()
+
+    def _install_state(self):
+        for i, p in enumerate(self.group.params):
+            m, v = self.group.moment_views(i)
+            self.state[p] = {"step": torch.tensor(float(self._host_step)), "exp_avg": m, "exp_avg_sq": v}
+
+    # ---- fused path
+    def fused_step(self, *, world_size: int = 1, max_grad_norm: float = 0.0, adaptive: bool = False,
+                   desired_kl: float = 0.0, round_lr_fp32: bool = False, use_kl: bool = True, zero_grad: bool = True):
+        g = self.group
+        pg = self.param_groups[0]
+        beta1, beta2 = pg["betas"]
+        L = nat.lib()
+        nat.check(L.rslrl_grad_norm_lr(g.grads.data_ptr(), g.numel, g.kl_slot.data_ptr() if use_kl else None,
+                                       self.dev_state.ptr(), self._opt_ws.data_ptr(), world_size, float(max_grad_norm),
+                                       int(adaptive), float(desired_kl or 0.0), int(round_lr_fp32), beta1, beta2,
+                                       nat.stream_ptr()))
+        nat.check(L.rslrl_adam_step(g.values.data_ptr(), g.grads.data_ptr(), g.exp_avg.data_ptr(),
+                                    g.exp_avg_sq.data_ptr(), g.numel, self.dev_state.ptr(), beta1, beta2, pg["eps"],
+                                    int(zero_grad), nat.stream_ptr()))
+        self._host_step += 1
+
+    def sync_host_state(self, lr: float):
+        """Mirrors the device scalars into the torch-visible optimiser state (once per update())."""
+        for pg in self.param_groups:
+            pg["lr"] = lr
+        for p in self.group.params:
+            self.state[p]["step"] = torch.tensor(float(self._host_step))
+
+    # ---- checkpoint compatibility
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        with torch.no_grad():
+            step = 0
+            for i, p in enumerate(self.group.params):
+                st = self.state.get(p, None)
+                m, v = self.group.moment_views(i)
+                if st:
+                    m.copy_(st["exp_avg"])
+                    v.copy_(st["exp_avg_sq"])
+                    step = int(float(st["step"]))
+            self._host_step = step
+            self._install_state()
+            self.dev_state.set_step(step)
+            self.dev_state.set_lr(self.param_groups[0]["lr"])

@@ -1,0 +1,399 @@
+"""Proximal Policy Optimization on fused sm_100a kernels.
+
+Mirror of `rsl_rl/algorithms/ppo.py` of the reference: same constructor arguments (plus three optional
+keyword arguments at the end), same public methods and attributes
+(`policy, optimizer, storage, transition, learning_rate, rnd, rnd_optimizer, symmetry, ...`), same
+loss dictionary.  Differences are under the hood:
+
+* the policy parameters live in one flat buffer (`FlatParamGroup`), `optimizer` is a `FusedAdam`
+  (a real `torch.optim.Adam` subclass) -- clip_grad_norm_ + KL-adaptive LR + Adam are two launches;
+* `act()` writes actions / mean / sigma / value / log-prob straight into row `step` of the rollout
+  buffer, `process_env_step()` adds observations, rewards (with the time-out bootstrap) and dones
+  with one launch;
+* `update()` runs forward, the PPO objective with its hand-derived backward, the MLP backward and
+  the optimiser step without autograd and without host synchronisation; the learning rate lives on
+  the device and is read back once per update (so `learning_rate` is still a Python float);
+* multi-GPU: ONE in-place all-reduce of the flat gradient buffer per minibatch; the minibatch KL
+  rides in its tail and every rank applies the LR rule identically (reference: 3 collectives and
+  2 host syncs per minibatch, ppo.py:272-290, 441-469).
+
+Feed-forward policies without RND / symmetry take the fused engine; recurrent policies, RND and
+symmetry augmentation take `_update_composite` (same kernels for GEMMs, storage, GAE, trajectories and
+the optimiser, with the surrounding algebra expressed through autograd).
+"""
+from __future__ import annotations
+
+from itertools import chain
+
+import torch
+import torch.nn as nn
+
+from .. import _native as nat
+from ..modules.rnd import RandomNetworkDistillation
+from ..storage import RolloutStorage
+from ..utils import string_to_callable
+from . import _engine
+from .flat_params import FlatParamGroup, FusedAdam
+
+
+class PPO:
+    """Proximal Policy Optimization algorithm (https://arxiv.org/abs/1707.06347)."""
+
+    def __init__(
+        self,
+        policy,
+        num_learning_epochs=5,
+        num_mini_batches=4,
+        clip_param=0.2,
+        gamma=0.99,
+        lam=0.95,
+        value_loss_coef=1.0,
+        entropy_coef=0.01,
+        learning_rate=0.001,
+        max_grad_norm=1.0,
+        use_clipped_value_loss=True,
+        schedule="adaptive",
+        desired_kl=0.01,
+        device="cpu",
+        normalize_advantage_per_mini_batch=False,
+        rnd_cfg: dict | None = None,
+        symmetry_cfg: dict | None = None,
+        multi_gpu_cfg: dict | None = None,
+        # --- rsl_rl_b200 extensions (all optional) ---
+        gemm_precision: str = "fp32",   # "fp32": CUDA-core FMA (1e-5 class) | "tf32": tcgen05 tensor cores (1e-3 class)
+        use_cuda_graph: bool = True,     # capture update() into one CUDA graph (single-GPU fused path)
+        rng_compat: bool = True,         # consume the RNG exactly like the reference (discarded draws in update())
+    ):
+        if torch.device(device).type != "cuda":
+            raise RuntimeError(f"rsl_rl_b200.PPO runs on a CUDA device only (got device={device!r}); "
+                               "there is no CPU fallback.")
+        nat.lib()
+        self.device = device
+        self.is_multi_gpu = multi_gpu_cfg is not None
+        if multi_gpu_cfg is not None:
+            self.gpu_global_rank = multi_gpu_cfg["global_rank"]
+            self.gpu_world_size = multi_gpu_cfg["world_size"]
+        else:
+            self.gpu_global_rank = 0
+            self.gpu_world_size = 1
+
+        # RND (reference ppo.py:60-71)
+        if rnd_cfg is not None:
+            rnd_lr = rnd_cfg.pop("learning_rate", 1e-3)
+            self.rnd = RandomNetworkDistillation(device=self.device, **rnd_cfg)
+            self._rnd_group = FlatParamGroup(self.rnd.predictor.parameters(), self.device)
+            self.rnd_optimizer = FusedAdam(self._rnd_group, lr=rnd_lr)
+        else:
+            self.rnd = None
+            self.rnd_optimizer = None
+            self._rnd_group = None
+
+        # symmetry (reference ppo.py:73-92)
+        if symmetry_cfg is not None:
+            if not (symmetry_cfg["use_data_augmentation"] or symmetry_cfg["use_mirror_loss"]):
+                print("Symmetry not used for learning. We will use it for logging instead.")
+            if isinstance(symmetry_cfg["data_augmentation_func"], str):
+                symmetry_cfg["data_augmentation_func"] = string_to_callable(symmetry_cfg["data_augmentation_func"])
+            if symmetry_cfg["use_data_augmentation"] and not callable(symmetry_cfg["data_augmentation_func"]):
+                raise ValueError("Data augmentation enabled but the function is not callable:"
+                                 f" {symmetry_cfg['data_augmentation_func']}")
+            self.symmetry = symmetry_cfg
+        else:
+            self.symmetry = None
+
+        self.policy = policy
+        self.policy.to(self.device)
+        self.policy.set_gemm_precision(gemm_precision)
+        if self.rnd is not None:
+            self.rnd.predictor.precision = gemm_precision
+            self.rnd.target.precision = gemm_precision
+        self._group = FlatParamGroup(self.policy.parameters(), self.device)
+        self.optimizer = FusedAdam(self._group, lr=learning_rate)
+        self.storage: RolloutStorage = None  # type: ignore
+        self.transition = RolloutStorage.Transition()
+
+        self.clip_param = clip_param
+        self.num_learning_epochs = num_learning_epochs
+        self.num_mini_batches = num_mini_batches
+        self.value_loss_coef = value_loss_coef
+        self.entropy_coef = entropy_coef
+        self.gamma = gamma
+        self.lam = lam
+        self.max_grad_norm = max_grad_norm
+        self.use_clipped_value_loss = use_clipped_value_loss
+        self.desired_kl = desired_kl
+        self.schedule = schedule
+        self.learning_rate = learning_rate
+        self.normalize_advantage_per_mini_batch = normalize_advantage_per_mini_batch
+        self.intrinsic_rewards = None
+
+        self.gemm_precision = gemm_precision
+        self.use_cuda_graph = use_cuda_graph
+        self.rng_compat = rng_compat
+        self._engine = None
+        self._engine_reason = _engine.supports(self.policy)
+        if self.rnd is not None:
+            self._engine_reason = self._engine_reason or "RND"
+        if self.symmetry is not None:
+            self._engine_reason = self._engine_reason or "symmetry"
+        self._graph = None
+        self._graph_key = None
+        self._graph_launches = 0
+        self._eager_updates = 0
+        self._mb_hook = None  # test hook: called after every minibatch backward in eager mode
+        self.last_update_info = {}
+
+    # ------------------------------------------------------------------------------------------
+    def init_storage(self, training_type, num_envs, num_transitions_per_env, obs, actions_shape):
+        self.storage = RolloutStorage(training_type, num_envs, num_transitions_per_env, obs, actions_shape, self.device)
+        if self._engine_reason is None:
+            B = num_envs * num_transitions_per_env
+            mb = B // self.num_mini_batches
+            self._engine = _engine.FeedForwardEngine(self.policy, B, num_envs, mb, self.device, self.gemm_precision)
+            self._alloc_update_buffers(num_envs, num_transitions_per_env)
+
+    @property
+    def fused(self) -> bool:
+        return self._engine is not None
+
+    # ------------------------------------------------------------------------------------------
+    # rollout
+    # ------------------------------------------------------------------------------------------
+    def _inputs(self, obs):
+        pol = self.policy
+        x_a = pol.actor_obs_normalizer(pol.get_actor_obs(obs))
+        if pol.critic_shares_actor_input:
+            return nat.f32c(x_a), nat.f32c(x_a)
+        x_c = pol.critic_obs_normalizer(pol.get_critic_obs(obs))
+        return nat.f32c(x_a), nat.f32c(x_c)
+
+    def act(self, obs):
+        """Reference ppo.py:129-140."""
+        if not self.fused:
+            return self._act_composite(obs)
+        st, eng, tr = self.storage, self._engine, self.transition
+        s = st.step
+        if s >= st.num_transitions_per_env:
+            raise OverflowError("Rollout buffer overflow! You should call clear() before adding new transitions.")
+        self._group.ensure_bound()
+        x_a, x_c = self._inputs(obs)
+        nat.require_cuda(x_a, x_c)
+        eng.forward(x_a, x_c, st.mu[s], st.values[s])
+        z = self.policy.draw_noise(st.mu[s])
+        eng.gaussian_head(st.mu[s], z, st.actions[s], st.actions_log_prob[s], st.sigma[s])
+        tr.actions, tr.values = st.actions[s], st.values[s]
+        tr.actions_log_prob = st.actions_log_prob[s].view(-1)
+        tr.action_mean, tr.action_sigma = st.mu[s], st.sigma[s]
+        tr.observations = obs
+        self.policy._mean, self.policy._std = tr.action_mean, tr.action_sigma
+        return tr.actions
+
+    def _act_composite(self, obs):
+        tr = self.transition
+        if self.policy.is_recurrent:
+            tr.hidden_states = self.policy.get_hidden_states()
+        tr.actions = self.policy.act(obs).detach()
+        tr.values = self.policy.evaluate(obs).detach()
+        tr.actions_log_prob = self.policy.get_actions_log_prob(tr.actions).detach()
+        tr.action_mean = self.policy.action_mean.detach()
+        tr.action_sigma = self.policy.action_std.detach()
+        tr.observations = obs
+        return tr.actions
+
+    def process_env_step(self, obs, rewards, dones, extras):
+        """Reference ppo.py:142-169; the reward bootstrap and the buffer write are one kernel."""
+        self.policy.update_normalization(obs)
+        if self.rnd:
+            self.rnd.update_normalization(obs)
+        tr = self.transition
+        tr.rewards = rewards
+        tr.dones = dones
+        intrinsic = None
+        if self.rnd:
+            self.intrinsic_rewards = self.rnd.get_intrinsic_reward(obs)
+            intrinsic = self.intrinsic_rewards
+        time_outs = extras["time_outs"] if "time_outs" in extras else None
+        self.storage._store(tr, time_outs=time_outs, intrinsic=intrinsic, gamma=self.gamma)
+        tr.clear()
+        self.policy.reset(dones)
+
+    def compute_returns(self, obs):
+        """Reference ppo.py:171-176."""
+        if self.fused:
+            _, x_c = self._inputs(obs)
+            last_values = self._last_values
+            self._engine.forward(x_c, x_c, None, last_values, actor=False)
+        else:
+            last_values = self.policy.evaluate(obs).detach()
+        self.storage.compute_returns(last_values, self.gamma, self.lam,
+                                     normalize_advantage=not self.normalize_advantage_per_mini_batch)
+
+    # ------------------------------------------------------------------------------------------
+    # update: fused feed-forward path
+    # ------------------------------------------------------------------------------------------
+    def _alloc_update_buffers(self, N, T):
+        pol, dev = self.policy, self.device
+        M = self.num_mini_batches
+        self._mb = (N * T) // M
+        Bp = self._mb * M
+        f32 = dict(dtype=torch.float32, device=dev)
+        pad4 = lambda d: (d + 3) // 4 * 4
+        self._Oa, self._Oc = pol.num_actor_obs, pol.num_critic_obs
+        self._xa_raw = torch.empty(Bp, pad4(self._Oa), **f32)
+        self._xc_raw = self._xa_raw if pol.critic_shares_actor_input else torch.empty(Bp, pad4(self._Oc), **f32)
+        A = self._engine.A
+        self._p_actions = torch.empty(Bp, A, **f32)
+        self._p_mu = torch.empty(Bp, A, **f32)
+        self._p_sigma = torch.empty(Bp, A, **f32)
+        self._p_values = torch.empty(Bp, **f32)
+        self._p_adv = torch.empty(Bp, **f32)
+        self._p_ret = torch.empty(Bp, **f32)
+        self._p_logp = torch.empty(Bp, **f32)
+        self._perm = torch.empty(Bp, dtype=torch.int64, device=dev)
+        self._last_values = torch.empty(N, 1, **f32)
+        self._discard = torch.empty(self._mb, A, **f32)
+
+    def _hyper(self):
+        return dict(clip_param=float(self.clip_param), value_loss_coef=float(self.value_loss_coef),
+                    entropy_coef=float(self.entropy_coef), use_clipped_value_loss=bool(self.use_clipped_value_loss))
+
+    def _gather_all(self):
+        """Permute the whole rollout once (all minibatches of all epochs reuse it)."""
+        st, pol = self.storage, self.policy
+        fields, widths, outs, strides, cols = [], [], [], [], []
+
+        def add_groups(groups, dst):
+            col = 0
+            for g in groups:
+                src = st.observations[g]
+                w = int(src[0, 0].numel())
+                fields.append(src); widths.append(w); outs.append(dst); strides.append(dst.stride(0)); cols.append(col)
+                col += w
+
+        add_groups(pol.obs_groups["policy"], self._xa_raw)
+        if not pol.critic_shares_actor_input:
+            add_groups(pol.obs_groups["critic"], self._xc_raw)
+        A = self._engine.A
+        for src, dst, w in ((st.actions, self._p_actions, A), (st.mu, self._p_mu, A), (st.sigma, self._p_sigma, A),
+                            (st.values, self._p_values, 1), (st.advantages, self._p_adv, 1),
+                            (st.returns, self._p_ret, 1), (st.actions_log_prob, self._p_logp, 1)):
+            fields.append(src); widths.append(w); outs.append(dst); strides.append(w); cols.append(0)
+        # the gather's dst base pointer is per field; column offsets handle the concatenation
+        st._gather(fields, widths, self._perm, outs, strides, cols)
+        xa = self._xa_raw[:, :self._Oa]
+        xc = self._xc_raw[:, :self._Oc]
+        if not isinstance(pol.actor_obs_normalizer, nn.Identity):
+            xa = nat.f32c(pol.actor_obs_normalizer(xa))
+        if pol.critic_shares_actor_input:
+            xc = xa
+        elif not isinstance(pol.critic_obs_normalizer, nn.Identity):
+            xc = nat.f32c(pol.critic_obs_normalizer(xc))
+        return xa, xc
+
+    def _update_kernels(self):
+        """Everything update() puts on the stream; capturable (static pointers, no host reads)."""
+        eng, opt, hp = self._engine, self.optimizer, self._hyper()
+        mb, M = self._mb, self.num_mini_batches
+        xa, xc = self._gather_all()
+        ds = opt.dev_state
+        nat.check(nat.lib().rslrl_fill_zero(ds.loss_sums.data_ptr(), 24, nat.stream_ptr()))
+        adaptive = self.desired_kl is not None and self.schedule == "adaptive"
+        for _ in range(self.num_learning_epochs):
+            for i in range(M):
+                r = slice(i * mb, (i + 1) * mb)
+                mu, value = eng.mu[:mb], eng.value[:mb]
+                eng.forward(xa[r], xc[r], mu, value)
+                eng.loss(mb, mb, mu, value, self._p_actions[r], self._p_logp[r], self._p_adv[r], self._p_ret[r],
+                         self._p_values[r], self._p_mu[r], self._p_sigma[r], self._group.kl_slot, ds.loss_sums, hp,
+                         self.normalize_advantage_per_mini_batch)
+                eng.backward(xa[r], xc[r], eng.dmu[:mb], eng.dvalue[:mb])
+                if self._mb_hook is not None:
+                    self._mb_hook(self)
+                if self.is_multi_gpu:
+                    torch.distributed.all_reduce(self._group.grads_ext, op=torch.distributed.ReduceOp.SUM)
+                opt.fused_step(world_size=self.gpu_world_size, max_grad_norm=self.max_grad_norm, adaptive=adaptive,
+                               desired_kl=self.desired_kl or 0.0, round_lr_fp32=self.is_multi_gpu)
+
+    def _update_fused(self):
+        st, eng, opt = self.storage, self._engine, self.optimizer
+        self._group.ensure_bound()
+        M, E = self.num_mini_batches, self.num_learning_epochs
+        perm = st._randperm(M * self._mb)
+        self._perm.copy_(perm)
+        if self.rng_compat:  # the reference's policy.act() inside update() draws (and discards) a sample per minibatch
+            for _ in range(M * E):
+                self._discard.normal_()
+        opt.dev_state.set_lr(self.learning_rate)
+
+        graph_ok = self.use_cuda_graph and not self.is_multi_gpu and self._mb_hook is None
+        if not graph_ok or self._eager_updates < 1:
+            # the first update always runs eagerly (module loading, lazy initialisation); later ones replay a graph
+            self._eager_updates += 1
+            self._update_kernels()
+            return self._finish_update()
+        key = (self._hyper_key(), st.actions.data_ptr(), self._group.values.data_ptr())
+        if self._graph is None or self._graph_key != key:
+            torch.cuda.synchronize()
+            before, host_step = nat.launch_count(), opt._host_step
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._update_kernels()
+            self._graph_launches = nat.launch_count() - before
+            nat.lib().rslrl_add_launch_count(-self._graph_launches & 0xFFFFFFFFFFFFFFFF)  # capture launched nothing
+            opt._host_step = host_step
+            self._graph, self._graph_key = g, key
+        self._graph.replay()
+        nat.lib().rslrl_add_launch_count(self._graph_launches)
+        opt._host_step += M * E
+        return self._finish_update()
+
+    def _hyper_key(self):
+        return (self.clip_param, self.value_loss_coef, self.entropy_coef, self.use_clipped_value_loss, self.desired_kl,
+                self.schedule, self.max_grad_norm, self.num_learning_epochs, self.num_mini_batches,
+                self.normalize_advantage_per_mini_batch, self.gemm_precision)
+
+    def _finish_update(self):
+        info = self.optimizer.dev_state.read()  # the one device->host read of update()
+        n = self.num_learning_epochs * self.num_mini_batches
+        self.learning_rate = info["lr"]
+        self.optimizer.sync_host_state(self.learning_rate)
+        self.last_update_info = info
+        self.storage.clear()
+        s = info["loss_sums"]
+        return {"value_function": s[1] / n, "surrogate": s[0] / n, "entropy": s[2] / n}
+
+    def update(self):
+        """Reference ppo.py:178-422."""
+        if self.fused:
+            return self._update_fused()
+        return self._update_composite()
+
+    # ------------------------------------------------------------------------------------------
+    # update: composite path (recurrent / RND / symmetry)
+    # ------------------------------------------------------------------------------------------
+    def _update_composite(self):
+        raise NotImplementedError(
+            f"PPO.update: the fused engine does not cover this configuration yet ({self._engine_reason}).")
+
+    # ------------------------------------------------------------------------------------------
+    # multi-GPU helpers (reference ppo.py:428-469)
+    # ------------------------------------------------------------------------------------------
+    def broadcast_parameters(self):
+        """Rank 0's parameters to every rank: one flat broadcast per parameter group (the reference
+        pickles the state dicts, ppo.py:428-439)."""
+        self._group.ensure_bound()
+        torch.distributed.broadcast(self._group.values, src=0)
+        buffers = [b for b in self.policy.buffers()]
+        for b in buffers:
+            torch.distributed.broadcast(b, src=0)
+        if self.rnd:
+            self._rnd_group.ensure_bound()
+            torch.distributed.broadcast(self._rnd_group.values, src=0)
+
+    def reduce_parameters(self):
+        """Averages the gradients over all ranks in place (reference ppo.py:441-469)."""
+        self._group.ensure_bound()
+        groups = [self._group] + ([self._rnd_group] if self.rnd else [])
+        for g in groups:
+            torch.distributed.all_reduce(g.grads, op=torch.distributed.ReduceOp.SUM)
+            g.grads /= self.gpu_world_size

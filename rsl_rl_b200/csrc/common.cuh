@@ -1,0 +1,96 @@
+// Shared helpers for the sm_100a kernels behind include/rslrl_b200.h.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/rslrl_b200.h"
+
+namespace rslrl {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+void set_error(const char* fmt, ...);
+void count_launch(unsigned long long n = 1);
+
+// Records the launch and converts launch errors into the library's error channel.
+inline int finish_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return 1;
+  }
+  count_launch();
+  return 0;
+}
+
+#define RSLRL_CHECK_ARG(cond, what)                      \
+  do {                                                   \
+    if (!(cond)) {                                       \
+      rslrl::set_error("%s: bad argument: %s", what, #cond); \
+      return 2;                                          \
+    }                                                    \
+  } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum of NV doubles per thread; result valid in thread 0.  smem: NV * 32 doubles.
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double* smem) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) smem[i * 32 + warp] = v[i];
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      double x = lane < nwarps ? smem[i * 32 + lane] : 0.0;
+      v[i] = warp_sum(x);
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ float act_forward(int act, float z) {
+  switch (act) {
+    case RSLRL_ACT_ELU: return z > 0.f ? z : expm1f(z);
+    case RSLRL_ACT_RELU: return fmaxf(z, 0.f);
+    case RSLRL_ACT_TANH: return tanhf(z);
+    case RSLRL_ACT_SIGMOID: return 1.f / (1.f + expf(-z));
+    case RSLRL_ACT_LRELU: return z > 0.f ? z : 0.01f * z;
+    case RSLRL_ACT_SELU: return 1.0507009873554804934f * (z > 0.f ? z : 1.6732632423543772848f * expm1f(z));
+    case RSLRL_ACT_SOFTPLUS: return z > 20.f ? z : log1pf(expf(z));
+    default: return z;
+  }
+}
+
+// d act(z)/dz expressed through the activation OUTPUT h = act(z) (no pre-activation is stored).
+__device__ __forceinline__ float act_grad_from_output(int act, float h) {
+  switch (act) {
+    case RSLRL_ACT_ELU: return h > 0.f ? 1.f : h + 1.f;  // exp(z) = h + 1 for z <= 0
+    case RSLRL_ACT_RELU: return h > 0.f ? 1.f : 0.f;
+    case RSLRL_ACT_TANH: return 1.f - h * h;
+    case RSLRL_ACT_SIGMOID: return h * (1.f - h);
+    case RSLRL_ACT_LRELU: return h > 0.f ? 1.f : 0.01f;
+    case RSLRL_ACT_SELU:
+      return h > 0.f ? 1.0507009873554804934f : h + 1.0507009873554804934f * 1.6732632423543772848f;
+    case RSLRL_ACT_SOFTPLUS: return 1.f - expf(-h);  // sigmoid(z) = 1 - exp(-softplus(z))
+    default: return 1.f;
+  }
+}
+
+}  // namespace rslrl

@@ -1,0 +1,215 @@
+// GAE reverse scan + returns + advantage normalisation in one cooperative kernel.
+// Replaces RolloutStorage.compute_returns (reference rsl_rl/storage/rollout_storage.py:127-149),
+// which issues ~400 elementwise launches over 24 [N,1] slices.
+//
+// Layout: rewards/values/returns/advantages are [T,N] fp32, dones [T,N] u8 (the reference's [T,N,1]
+// buffers, same bytes).  One thread owns one env: for fixed t a warp touches 32 consecutive floats
+// (one 128 B line), so every access is fully coalesced.  All 3*T loads of an env are issued before
+// the scan starts (T is a template bound), which is what hides the HBM latency: the scan itself is
+// only T dependent FMUL/FADD triples.  The fp32 operation order of the reference is kept with
+// explicit round-to-nearest intrinsics (no FMA contraction), so `returns` and the un-normalised
+// advantages are bit-identical to the reference.  The normalisation needs the global mean and
+// unbiased std of all T*N advantages: per-thread fp64 partials -> warp shuffles -> one fp64 pair per
+// block in a workspace -> grid.sync() -> every block reduces the per-block pairs in the same order
+// (deterministic, no atomics, nothing to zero) -> the advantages, still in registers, are written
+// once.  Algorithmic traffic: 17*T*N + 4*N bytes.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace rslrl {
+
+constexpr int kGaeThreads = 128;
+constexpr int kGaeMaxBlocks = 4096;  // workspace capacity (pairs of doubles)
+
+__device__ __forceinline__ void gae_finalize_stats(double s, double ss, double* partials, double* smem,
+                                                   cg::grid_group& grid, int64_t B, float& mean_f, float& denom_f) {
+  double v[2] = {s, ss};
+  block_sum<2>(v, smem);
+  if (threadIdx.x == 0) {
+    partials[2 * blockIdx.x] = v[0];
+    partials[2 * blockIdx.x + 1] = v[1];
+  }
+  grid.sync();
+  double t[2] = {0.0, 0.0};
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
+    t[0] += partials[2 * i];
+    t[1] += partials[2 * i + 1];
+  }
+  block_sum<2>(t, smem);
+  if (threadIdx.x == 0) {
+    const double n = (double)B;
+    const double mean = t[0] / n;
+    double var = (t[1] - t[0] * t[0] / n) / (n - 1.0);  // unbiased, as torch.Tensor.std()
+    var = var > 0.0 ? var : 0.0;
+    smem[0] = mean;
+    smem[1] = sqrt(var);
+  }
+  __syncthreads();
+  mean_f = (float)smem[0];
+  denom_f = __fadd_rn((float)smem[1], 1e-8f);
+}
+
+// One env per thread, whole trajectory in registers.
+template <int TMAX>
+__global__ void __launch_bounds__(kGaeThreads)
+gae_norm_reg_kernel(const float* __restrict__ rewards, const float* __restrict__ values,
+                    const uint8_t* __restrict__ dones, const float* __restrict__ last_values,
+                    float* __restrict__ returns, float* __restrict__ advantages, double* __restrict__ partials,
+                    int T, int N, float gamma, float lam, int normalize) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double smem[64];
+  const int n = blockIdx.x * kGaeThreads + threadIdx.x;
+  float a[TMAX];
+  double s = 0.0, ss = 0.0;
+  if (n < N) {
+    float r[TMAX], v[TMAX];
+    uint8_t d[TMAX];
+#pragma unroll
+    for (int i = 0; i < TMAX; ++i) {
+      if (i < T) {
+        const size_t o = (size_t)i * N + n;
+        r[i] = __ldg(rewards + o);
+        v[i] = __ldg(values + o);
+        d[i] = __ldg(dones + o);
+      }
+    }
+    float next_v = __ldg(last_values + n);
+    float adv = 0.f;
+#pragma unroll
+    for (int i = TMAX - 1; i >= 0; --i) {
+      if (i < T) {
+        const float nnt = __fsub_rn(1.0f, (float)d[i]);
+        const float ng = __fmul_rn(nnt, gamma);
+        const float delta = __fsub_rn(__fadd_rn(r[i], __fmul_rn(ng, next_v)), v[i]);
+        adv = __fadd_rn(delta, __fmul_rn(__fmul_rn(ng, lam), adv));
+        const float ret = __fadd_rn(adv, v[i]);
+        returns[(size_t)i * N + n] = ret;
+        const float x = __fsub_rn(ret, v[i]);
+        a[i] = x;
+        s += (double)x;
+        ss += (double)x * (double)x;
+        next_v = v[i];
+      }
+    }
+  }
+  float mean_f = 0.f, denom_f = 1.f;
+  if (normalize) gae_finalize_stats(s, ss, partials, smem, grid, (int64_t)T * N, mean_f, denom_f);
+  if (n < N) {
+#pragma unroll
+    for (int i = 0; i < TMAX; ++i) {
+      if (i < T) {
+        const float x = normalize ? __fdiv_rn(__fsub_rn(a[i], mean_f), denom_f) : a[i];
+        advantages[(size_t)i * N + n] = x;
+      }
+    }
+  }
+}
+
+// Any T, any N: grid-stride over envs, raw advantages staged through `advantages` itself.
+__global__ void __launch_bounds__(kGaeThreads)
+gae_norm_generic_kernel(const float* __restrict__ rewards, const float* __restrict__ values,
+                        const uint8_t* __restrict__ dones, const float* __restrict__ last_values,
+                        float* __restrict__ returns, float* advantages, double* __restrict__ partials, int T, int N,
+                        float gamma, float lam, int normalize) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double smem[64];
+  double s = 0.0, ss = 0.0;
+  const int stride = gridDim.x * kGaeThreads;
+  for (int n = blockIdx.x * kGaeThreads + threadIdx.x; n < N; n += stride) {
+    float next_v = __ldg(last_values + n);
+    float adv = 0.f;
+    for (int i = T - 1; i >= 0; --i) {
+      const size_t o = (size_t)i * N + n;
+      const float r = __ldg(rewards + o), v = __ldg(values + o);
+      const float nnt = __fsub_rn(1.0f, (float)__ldg(dones + o));
+      const float ng = __fmul_rn(nnt, gamma);
+      const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(ng, next_v)), v);
+      adv = __fadd_rn(delta, __fmul_rn(__fmul_rn(ng, lam), adv));
+      const float ret = __fadd_rn(adv, v);
+      returns[o] = ret;
+      const float x = __fsub_rn(ret, v);
+      advantages[o] = x;
+      s += (double)x;
+      ss += (double)x * (double)x;
+      next_v = v;
+    }
+  }
+  if (!normalize) return;
+  float mean_f, denom_f;
+  gae_finalize_stats(s, ss, partials, smem, grid, (int64_t)T * N, mean_f, denom_f);
+  for (int n = blockIdx.x * kGaeThreads + threadIdx.x; n < N; n += stride)
+    for (int i = 0; i < T; ++i) {
+      const size_t o = (size_t)i * N + n;
+      advantages[o] = __fdiv_rn(__fsub_rn(advantages[o], mean_f), denom_f);  // own writes: same thread
+    }
+}
+
+template <typename K>
+static int max_coop_blocks(K kernel) {
+  int dev = 0, sms = 0, per_sm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kGaeThreads, 0);
+  int cap = sms * per_sm;
+  return cap < kGaeMaxBlocks ? cap : kGaeMaxBlocks;
+}
+
+template <int TMAX>
+static int launch_reg(void** args, int blocks, cudaStream_t st) {
+  static int cap = -1;
+  if (cap < 0) cap = max_coop_blocks(gae_norm_reg_kernel<TMAX>);
+  if (blocks > cap) return -1;  // caller falls back to the generic kernel
+  cudaError_t e = cudaLaunchCooperativeKernel((void*)gae_norm_reg_kernel<TMAX>, dim3(blocks), dim3(kGaeThreads),
+                                              args, 0, st);
+  if (e != cudaSuccess) {
+    set_error("rslrl_gae_norm: %s", cudaGetErrorString(e));
+    return 1;
+  }
+  count_launch();
+  return 0;
+}
+
+}  // namespace rslrl
+
+extern "C" {
+
+int64_t rslrl_gae_workspace_bytes(int N) {
+  (void)N;
+  return (int64_t)rslrl::kGaeMaxBlocks * 2 * sizeof(double);
+}
+
+int rslrl_gae_norm(const float* rewards, const float* values, const uint8_t* dones, const float* last_values,
+                   float* returns, float* advantages, void* workspace, int T, int N, double gamma_d, double lam_d,
+                   int normalize, rslrl_stream_t stream) {
+  using namespace rslrl;
+  float gamma = (float)gamma_d, lam = (float)lam_d;  // python scalars are cast to fp32 at each tensor op
+  RSLRL_CHECK_ARG(rewards && values && dones && last_values && returns && advantages && workspace, "rslrl_gae_norm");
+  RSLRL_CHECK_ARG(T > 0 && N > 0 && (int64_t)T * N > 1, "rslrl_gae_norm");
+  cudaStream_t st = (cudaStream_t)stream;
+  double* partials = (double*)workspace;
+  void* args[] = {&rewards, &values, &dones, &last_values, &returns, &advantages, &partials,
+                  &T,       &N,      &gamma, &lam,         &normalize};
+  const int blocks = (N + kGaeThreads - 1) / kGaeThreads;
+  int rc = -1;
+  if (T <= 8) rc = launch_reg<8>(args, blocks, st);
+  else if (T <= 16) rc = launch_reg<16>(args, blocks, st);
+  else if (T <= 24) rc = launch_reg<24>(args, blocks, st);
+  else if (T <= 32) rc = launch_reg<32>(args, blocks, st);
+  if (rc >= 0) return rc;
+  static int cap = -1;
+  if (cap < 0) cap = max_coop_blocks(gae_norm_generic_kernel);
+  const int gblocks = blocks < cap ? blocks : cap;
+  cudaError_t e = cudaLaunchCooperativeKernel((void*)gae_norm_generic_kernel, dim3(gblocks), dim3(kGaeThreads), args,
+                                              0, st);
+  if (e != cudaSuccess) {
+    set_error("rslrl_gae_norm: %s", cudaGetErrorString(e));
+    return 1;
+  }
+  count_launch();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,285 @@
+// FP32 CUDA-core GEMMs for nn.Linear forward / data-gradient / weight-gradient with fused epilogues.
+//
+// This is the RSLRL_PREC_FP32 arithmetic (the reference's own default on a GPU is cuBLAS SGEMM with
+// TF32 off, so this is the mode that meets the 1e-5 parity class; tcgen05 has no fp32 MMA).  The
+// tensor-core path lives in gemm_tc.cu.
+//
+// One templated kernel: C[M,N] (+)= sum_k A(m,k) B(n,k), 128x128x16 tiles, 256 threads, 8x8 register
+// tile per thread, register-staged double buffering through shared memory.  Operands may be stored
+// with the reduction index contiguous ("KC": X[M,K], W[N,K]) or strided ("MC": reduction index is the
+// slow one), which covers all three products without materialising a transpose:
+//   forward   Y  = act(X W^T + b)        A = X (KC),   B = W (KC)          epilogue: bias + activation
+//   dgrad     dX = (dY W) * act'(H)      A = dY (KC),  B = W (MC)          epilogue: activation gradient
+//   wgrad     dW += dY^T X, db += 1^T dY A = dY (MC),  B = X (MC), split-K epilogue: vector atomics
+// Several problems (actor and critic) share one launch (blockIdx.y).
+#include "common.cuh"
+
+namespace rslrl {
+
+constexpr int BM = 128, BN = 128, BK = 16, GEMM_THREADS = 256, PADW = 4;
+
+enum { EPI_FWD = 0, EPI_DGRAD = 1, EPI_WGRAD = 2 };
+
+struct GemmProblem {
+  const float* A;
+  const float* B;
+  float* C;
+  const float* bias;  // EPI_FWD
+  const float* H;     // EPI_DGRAD
+  float* colsum;      // EPI_WGRAD (db)
+  int M, N, K, lda, ldb, ldc, ldh, act, splits, k_per_split;
+};
+
+struct GemmBatch {
+  GemmProblem p[RSLRL_MAX_PROBLEMS];
+};
+
+// Loads a [ROWS x BK] operand tile into registers (2 float4 per thread) ...
+template <bool KC>
+__device__ __forceinline__ void load_tile(const float* __restrict__ base, int ld, int row0, int rows, int k0, int k1,
+                                          bool vec_ok, float4 (&r)[2]) {
+  const int t = threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int f = t + i * GEMM_THREADS;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (KC) {
+      const int row = row0 + (f >> 2), k = k0 + ((f & 3) << 2);
+      if (row < rows) {
+        const float* src = base + (size_t)row * ld + k;
+        if (vec_ok && k + 3 < k1) {
+          v = __ldg((const float4*)src);
+        } else {
+          if (k < k1) v.x = __ldg(src);
+          if (k + 1 < k1) v.y = __ldg(src + 1);
+          if (k + 2 < k1) v.z = __ldg(src + 2);
+          if (k + 3 < k1) v.w = __ldg(src + 3);
+        }
+      }
+    } else {
+      const int k = k0 + (f >> 5), row = row0 + ((f & 31) << 2);
+      if (k < k1) {
+        const float* src = base + (size_t)k * ld + row;
+        if (vec_ok && row + 3 < rows) {
+          v = __ldg((const float4*)src);
+        } else {
+          if (row < rows) v.x = __ldg(src);
+          if (row + 1 < rows) v.y = __ldg(src + 1);
+          if (row + 2 < rows) v.z = __ldg(src + 2);
+          if (row + 3 < rows) v.w = __ldg(src + 3);
+        }
+      }
+    }
+    r[i] = v;
+  }
+}
+
+// ... and stores it k-major into shared memory: S[k][row].
+template <bool KC>
+__device__ __forceinline__ void store_tile(float (*S)[BM + PADW], const float4 (&r)[2]) {
+  const int t = threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int f = t + i * GEMM_THREADS;
+    if (KC) {
+      const int row = f >> 2, k = (f & 3) << 2;
+      S[k][row] = r[i].x;
+      S[k + 1][row] = r[i].y;
+      S[k + 2][row] = r[i].z;
+      S[k + 3][row] = r[i].w;
+    } else {
+      const int k = f >> 5, row = (f & 31) << 2;
+      *(float4*)&S[k][row] = r[i];
+    }
+  }
+}
+
+template <bool A_KC, bool B_KC, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 2) sgemm_kernel(const GemmBatch batch) {
+  const GemmProblem& P = batch.p[blockIdx.y];
+  const int tiles_m = (P.M + BM - 1) / BM, tiles_n = (P.N + BN - 1) / BN;
+  const int tiles = tiles_m * tiles_n;
+  if ((int)blockIdx.x >= tiles * P.splits) return;
+  const int split = blockIdx.x / tiles, rem = blockIdx.x - split * tiles;
+  const int tm = rem / tiles_n, tn = rem - tm * tiles_n;
+  const int m0 = tm * BM, n0 = tn * BN;
+  const int k_begin = split * P.k_per_split;
+  const int k_end = min(P.K, k_begin + P.k_per_split);
+
+  __shared__ __align__(16) float As[2][BK][BM + PADW];
+  __shared__ __align__(16) float Bs[2][BK][BN + PADW];
+
+  const bool a_vec = (P.lda & 3) == 0 && ((uintptr_t)P.A & 15) == 0 && (A_KC ? (k_begin & 3) == 0 : true);
+  const bool b_vec = (P.ldb & 3) == 0 && ((uintptr_t)P.B & 15) == 0 && (B_KC ? (k_begin & 3) == 0 : true);
+
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  float rowsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const bool do_rowsum = EPI == EPI_WGRAD && P.colsum != nullptr && tn == 0 && tx == 0;
+
+  float4 ra[2], rb[2];
+  if (k_begin < k_end) {
+    load_tile<A_KC>(P.A, P.lda, m0, P.M, k_begin, k_end, a_vec, ra);
+    load_tile<B_KC>(P.B, P.ldb, n0, P.N, k_begin, k_end, b_vec, rb);
+    store_tile<A_KC>(As[0], ra);
+    store_tile<B_KC>(Bs[0], rb);
+  }
+  __syncthreads();
+  int buf = 0;
+  for (int kk = k_begin; kk < k_end; kk += BK) {
+    const bool has_next = kk + BK < k_end;
+    if (has_next) {
+      load_tile<A_KC>(P.A, P.lda, m0, P.M, kk + BK, k_end, a_vec, ra);
+      load_tile<B_KC>(P.B, P.ldb, n0, P.N, kk + BK, k_end, b_vec, rb);
+    }
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a0 = *(const float4*)&As[buf][k][ty * 4];
+      const float4 a1 = *(const float4*)&As[buf][k][64 + ty * 4];
+      const float4 b0 = *(const float4*)&Bs[buf][k][tx * 4];
+      const float4 b1 = *(const float4*)&Bs[buf][k][64 + tx * 4];
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      if (EPI == EPI_WGRAD) {
+        if (do_rowsum) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) rowsum[i] += a[i];
+        }
+      }
+    }
+    if (has_next) {
+      store_tile<A_KC>(As[buf ^ 1], ra);
+      store_tile<B_KC>(Bs[buf ^ 1], rb);
+    }
+    __syncthreads();
+    buf ^= 1;
+  }
+
+  // ---- epilogue
+  const bool c_vec = (P.ldc & 3) == 0 && ((uintptr_t)P.C & 15) == 0;
+  const bool h_vec = EPI == EPI_DGRAD && (P.ldh & 3) == 0 && ((uintptr_t)P.H & 15) == 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (m >= P.M) continue;
+#pragma unroll
+    for (int jh = 0; jh < 2; ++jh) {
+      const int n = n0 + jh * 64 + tx * 4;
+      if (n >= P.N) continue;
+      float o[4] = {acc[i][jh * 4], acc[i][jh * 4 + 1], acc[i][jh * 4 + 2], acc[i][jh * 4 + 3]};
+      const int nv = min(4, P.N - n);
+      float* dst = P.C + (size_t)m * P.ldc + n;
+      if (EPI == EPI_FWD) {
+        for (int q = 0; q < nv; ++q) {
+          const float z = o[q] + (P.bias ? __ldg(P.bias + n + q) : 0.f);
+          o[q] = act_forward(P.act, z);
+        }
+      } else if (EPI == EPI_DGRAD) {
+        const float* hp = P.H + (size_t)m * P.ldh + n;
+        if (P.act != RSLRL_ACT_IDENTITY) {
+          if (h_vec && nv == 4) {
+            const float4 h4 = __ldg((const float4*)hp);
+            o[0] *= act_grad_from_output(P.act, h4.x);
+            o[1] *= act_grad_from_output(P.act, h4.y);
+            o[2] *= act_grad_from_output(P.act, h4.z);
+            o[3] *= act_grad_from_output(P.act, h4.w);
+          } else {
+            for (int q = 0; q < nv; ++q) o[q] *= act_grad_from_output(P.act, __ldg(hp + q));
+          }
+        }
+      }
+      if (EPI == EPI_WGRAD) {
+        if (c_vec && nv == 4) {
+          atomicAdd((float4*)dst, make_float4(o[0], o[1], o[2], o[3]));
+        } else {
+          for (int q = 0; q < nv; ++q) atomicAdd(dst + q, o[q]);
+        }
+      } else {
+        if (c_vec && nv == 4) {
+          *(float4*)dst = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+          for (int q = 0; q < nv; ++q) dst[q] = o[q];
+        }
+      }
+    }
+    if (EPI == EPI_WGRAD) {
+      if (do_rowsum) atomicAdd(P.colsum + m, rowsum[i]);
+    }
+  }
+}
+
+static int pick_splits(int total_tiles_all, int K) {
+  // aim at >= 2 CTAs per SM in flight; keep at least 8 k-tiles per split
+  int want = (2 * kNumSMs + total_tiles_all - 1) / total_tiles_all;
+  int max_s = K / (BK * 8);
+  if (max_s < 1) max_s = 1;
+  if (want > max_s) want = max_s;
+  return want < 1 ? 1 : want;
+}
+
+template <bool A_KC, bool B_KC, int EPI>
+static int launch(const GemmBatch& batch, int n, cudaStream_t st, const char* what) {
+  int max_ctas = 0;
+  for (int i = 0; i < n; ++i) {
+    const GemmProblem& P = batch.p[i];
+    const int t = ((P.M + BM - 1) / BM) * ((P.N + BN - 1) / BN) * P.splits;
+    if (t > max_ctas) max_ctas = t;
+  }
+  if (max_ctas == 0) return 0;
+  sgemm_kernel<A_KC, B_KC, EPI><<<dim3(max_ctas, n), GEMM_THREADS, 0, st>>>(batch);
+  return finish_launch(what);
+}
+
+int simt_linear_forward(int n, const rslrl_linear_fwd_t* pr, cudaStream_t st) {
+  GemmBatch b{};
+  for (int i = 0; i < n; ++i) {
+    GemmProblem& P = b.p[i];
+    P.A = pr[i].x; P.B = pr[i].w; P.C = pr[i].y; P.bias = pr[i].b;
+    P.M = pr[i].M; P.N = pr[i].N; P.K = pr[i].K;
+    P.lda = pr[i].ldx; P.ldb = pr[i].K; P.ldc = pr[i].ldy; P.act = pr[i].act;
+    P.splits = 1; P.k_per_split = pr[i].K;
+  }
+  return launch<true, true, EPI_FWD>(b, n, st, "rslrl_linear_forward");
+}
+
+int simt_linear_backward_data(int n, const rslrl_linear_bwd_data_t* pr, cudaStream_t st) {
+  GemmBatch b{};
+  for (int i = 0; i < n; ++i) {
+    GemmProblem& P = b.p[i];
+    // dX[M,K] = sum_n dY[m,n] W[n,k]  ->  C[M, K] with reduction length N
+    P.A = pr[i].dy; P.B = pr[i].w; P.C = pr[i].dx; P.H = pr[i].h;
+    P.M = pr[i].M; P.N = pr[i].K; P.K = pr[i].N;
+    P.lda = pr[i].ldy; P.ldb = pr[i].K; P.ldc = pr[i].ldx; P.ldh = pr[i].ldh; P.act = pr[i].act;
+    P.splits = 1; P.k_per_split = pr[i].N;
+  }
+  return launch<true, false, EPI_DGRAD>(b, n, st, "rslrl_linear_backward_data");
+}
+
+int simt_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* pr, cudaStream_t st) {
+  GemmBatch b{};
+  int tiles_all = 0;
+  for (int i = 0; i < n; ++i) tiles_all += ((pr[i].N + BM - 1) / BM) * ((pr[i].K + BN - 1) / BN);
+  for (int i = 0; i < n; ++i) {
+    GemmProblem& P = b.p[i];
+    // dW[N,K] += sum_m dY[m,n] X[m,k]  ->  C[N, K] with reduction length M
+    P.A = pr[i].dy; P.B = pr[i].x; P.C = pr[i].dw; P.colsum = pr[i].db;
+    P.M = pr[i].N; P.N = pr[i].K; P.K = pr[i].M;
+    P.lda = pr[i].ldy; P.ldb = pr[i].ldx; P.ldc = pr[i].K;
+    P.splits = pick_splits(tiles_all, pr[i].M);
+    int kps = (pr[i].M + P.splits - 1) / P.splits;
+    kps = ((kps + BK - 1) / BK) * BK;
+    P.k_per_split = kps;
+    P.splits = (pr[i].M + kps - 1) / kps;
+  }
+  return launch<false, false, EPI_WGRAD>(b, n, st, "rslrl_linear_backward_weight");
+}
+
+}  // namespace rslrl

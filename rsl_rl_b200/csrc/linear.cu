@@ -1,0 +1,61 @@
+// C-ABI entry points for the dense layers: dispatch on the arithmetic mode only (one device target,
+// no fallbacks).  fp32 -> gemm_simt.cu, tf32 -> gemm_tc.cu (tcgen05 / TMEM / TMA).
+#include "common.cuh"
+
+namespace rslrl {
+int simt_linear_forward(int n, const rslrl_linear_fwd_t* pr, cudaStream_t st);
+int simt_linear_backward_data(int n, const rslrl_linear_bwd_data_t* pr, cudaStream_t st);
+int simt_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* pr, cudaStream_t st);
+int tc_linear_forward(int n, const rslrl_linear_fwd_t* pr, cudaStream_t st);
+int tc_linear_backward_data(int n, const rslrl_linear_bwd_data_t* pr, cudaStream_t st);
+int tc_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* pr, cudaStream_t st);
+}  // namespace rslrl
+
+extern "C" {
+
+int rslrl_linear_forward(int n, const rslrl_linear_fwd_t* probs_host, int precision, rslrl_stream_t stream) {
+  using namespace rslrl;
+  const char* what = "rslrl_linear_forward";
+  RSLRL_CHECK_ARG(n > 0 && n <= RSLRL_MAX_PROBLEMS && probs_host, what);
+  for (int i = 0; i < n; ++i) {
+    const rslrl_linear_fwd_t& p = probs_host[i];
+    RSLRL_CHECK_ARG(p.x && p.w && p.y && p.M > 0 && p.N > 0 && p.K > 0 && p.ldx >= p.K && p.ldy >= p.N, what);
+  }
+  if (precision == RSLRL_PREC_FP32) return simt_linear_forward(n, probs_host, (cudaStream_t)stream);
+  if (precision == RSLRL_PREC_TF32) return tc_linear_forward(n, probs_host, (cudaStream_t)stream);
+  set_error("%s: unknown precision %d", what, precision);
+  return 2;
+}
+
+int rslrl_linear_backward_data(int n, const rslrl_linear_bwd_data_t* probs_host, int precision,
+                               rslrl_stream_t stream) {
+  using namespace rslrl;
+  const char* what = "rslrl_linear_backward_data";
+  RSLRL_CHECK_ARG(n > 0 && n <= RSLRL_MAX_PROBLEMS && probs_host, what);
+  for (int i = 0; i < n; ++i) {
+    const rslrl_linear_bwd_data_t& p = probs_host[i];
+    RSLRL_CHECK_ARG(p.dy && p.w && p.dx && p.M > 0 && p.N > 0 && p.K > 0 && p.ldy >= p.N && p.ldx >= p.K, what);
+    RSLRL_CHECK_ARG(p.act == RSLRL_ACT_IDENTITY || (p.h && p.ldh >= p.K), what);
+  }
+  if (precision == RSLRL_PREC_FP32) return simt_linear_backward_data(n, probs_host, (cudaStream_t)stream);
+  if (precision == RSLRL_PREC_TF32) return tc_linear_backward_data(n, probs_host, (cudaStream_t)stream);
+  set_error("%s: unknown precision %d", what, precision);
+  return 2;
+}
+
+int rslrl_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* probs_host, int precision,
+                                 rslrl_stream_t stream) {
+  using namespace rslrl;
+  const char* what = "rslrl_linear_backward_weight";
+  RSLRL_CHECK_ARG(n > 0 && n <= RSLRL_MAX_PROBLEMS && probs_host, what);
+  for (int i = 0; i < n; ++i) {
+    const rslrl_linear_bwd_weight_t& p = probs_host[i];
+    RSLRL_CHECK_ARG(p.dy && p.x && p.dw && p.M > 0 && p.N > 0 && p.K > 0 && p.ldy >= p.N && p.ldx >= p.K, what);
+  }
+  if (precision == RSLRL_PREC_FP32) return simt_linear_backward_weight(n, probs_host, (cudaStream_t)stream);
+  if (precision == RSLRL_PREC_TF32) return tc_linear_backward_weight(n, probs_host, (cudaStream_t)stream);
+  set_error("%s: unknown precision %d", what, precision);
+  return 2;
+}
+
+}  // extern "C"

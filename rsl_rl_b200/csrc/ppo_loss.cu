@@ -1,0 +1,329 @@
+// Gaussian policy head (rollout) and the fused PPO objective forward+backward (update).
+//
+// rslrl_ppo_loss_fwd_bwd replaces ~60 forward and ~100 autograd-backward elementwise/reduction
+// launches per minibatch of the reference (rsl_rl/algorithms/ppo.py:255-315 + loss.backward()) by one
+// kernel.  One thread owns one sample row: a warp reads 32 consecutive rows = one contiguous
+// 32*A*4-byte span of mu / actions / old_mu / old_sigma, so all sectors fetched are used (rows are
+// walked in 16-byte chunks when A % 4 == 0).  Reductions (KL, the three loss means, dL/dstd[A]) go
+// per-thread fp64 -> warp shuffle -> shared -> one fp64 atomicAdd per block into a workspace; the
+// last block to finish (threadfence + ticket) publishes the results and clears the workspace, so
+// there is no extra reduction launch, no host involvement and nothing to zero between launches.
+// Algorithmic traffic: (20*A + 24) bytes per sample.
+#include "common.cuh"
+
+namespace rslrl {
+
+constexpr int kLossThreads = 128;
+constexpr int kMaxActions = 64;
+constexpr float kLogSqrt2Pi = 0.91893853320467274178f;   // log(sqrt(2 pi))
+constexpr float kEntropyConst = 1.41893853320467274178f;  // 0.5 + 0.5 log(2 pi)
+
+struct LossWorkspace {
+  double acc[4 + kMaxActions];  // kl, surrogate, value loss, (unused), dstd[A]
+  unsigned int ticket;
+  unsigned int pad_;
+};
+
+struct SumWorkspace {
+  double acc[2];
+  unsigned int ticket;
+  unsigned int pad_;
+};
+
+__global__ void __launch_bounds__(kLossThreads)
+gaussian_act_kernel(const float* __restrict__ mu, const float* __restrict__ std_param, int std_type,
+                    const float* __restrict__ z, float* __restrict__ actions, float* __restrict__ log_prob,
+                    float* __restrict__ sigma_out, long long n, int A) {
+  __shared__ float s_sigma[kMaxActions], s_logs[kMaxActions], s_i2v[kMaxActions];
+  if (threadIdx.x < A) {
+    const float p = std_param[threadIdx.x];
+    const float s = std_type == RSLRL_STD_LOG ? expf(p) : p;
+    s_sigma[threadIdx.x] = s;
+    s_logs[threadIdx.x] = logf(s);
+    s_i2v[threadIdx.x] = 2.f * (s * s);
+  }
+  __syncthreads();
+  const long long i = (long long)blockIdx.x * kLossThreads + threadIdx.x;
+  if (i >= n) return;
+  const float* m = mu + i * A;
+  const float* zz = z + i * A;
+  float* out = actions + i * A;
+  float lp = 0.f;
+  for (int a = 0; a < A; ++a) {
+    const float mean = m[a], s = s_sigma[a];
+    const float act = __fadd_rn(__fmul_rn(zz[a], s), mean);  // normal_().mul_(std).add_(mean)
+    out[a] = act;
+    const float d = act - mean;
+    lp += -(d * d) / s_i2v[a] - s_logs[a] - kLogSqrt2Pi;
+    if (sigma_out) sigma_out[i * A + a] = s;
+  }
+  log_prob[i] = lp;
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(kLossThreads)
+ppo_loss_kernel(const float* __restrict__ mu, const float* __restrict__ std_param, int std_type,
+                const float* __restrict__ value, const float* __restrict__ actions,
+                const float* __restrict__ old_logp, const float* __restrict__ advantages,
+                const float* __restrict__ returns, const float* __restrict__ old_values,
+                const float* __restrict__ old_mu, const float* __restrict__ old_sigma,
+                const double* __restrict__ adv_stats, float* __restrict__ dmu, float* __restrict__ dvalue,
+                float* dstd, float* kl_out, double* loss_sums, LossWorkspace* ws, long long rows, long long mb_orig,
+                int A, float clip, float c_v, float c_e, int use_clipped) {
+  __shared__ float s_sigma[kMaxActions], s_logs[kMaxActions], s_2var[kMaxActions];
+  __shared__ double s_red[4 * 32];
+  __shared__ float s_dstd[kMaxActions];
+  __shared__ bool s_last;
+  if (threadIdx.x < A) {
+    const float p = std_param[threadIdx.x];
+    const float s = std_type == RSLRL_STD_LOG ? expf(p) : p;
+    s_sigma[threadIdx.x] = s;
+    s_logs[threadIdx.x] = logf(s);
+    s_2var[threadIdx.x] = 2.f * (s * s);
+    s_dstd[threadIdx.x] = 0.f;
+  }
+  __syncthreads();
+
+  const long long i = (long long)blockIdx.x * kLossThreads + threadIdx.x;
+  const bool valid = i < rows;
+  const long long j = valid ? i % mb_orig : 0;
+  const float lo = 1.0f - clip, hi = 1.0f + clip;
+  const float g = 1.0f / (float)rows;
+
+  float lp = 0.f, kl = 0.f;
+  if (valid) {
+    const float* m = mu + i * A;
+    const float* ac = actions + i * A;
+    const bool do_kl = i < mb_orig;
+    const float* om = old_mu + j * A;
+    const float* os = old_sigma + j * A;
+    if (VEC) {
+      for (int c = 0; c < A; c += 4) {
+        const float4 m4 = *(const float4*)(m + c), a4 = *(const float4*)(ac + c);
+        const float mm[4] = {m4.x, m4.y, m4.z, m4.w}, aa[4] = {a4.x, a4.y, a4.z, a4.w};
+        float omv[4] = {0, 0, 0, 0}, osv[4] = {1, 1, 1, 1};
+        if (do_kl) {
+          const float4 o4 = __ldg((const float4*)(om + c)), s4 = __ldg((const float4*)(os + c));
+          omv[0] = o4.x; omv[1] = o4.y; omv[2] = o4.z; omv[3] = o4.w;
+          osv[0] = s4.x; osv[1] = s4.y; osv[2] = s4.z; osv[3] = s4.w;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float d = aa[q] - mm[q];
+          lp += -(d * d) / s_2var[c + q] - s_logs[c + q] - kLogSqrt2Pi;
+          if (do_kl) {
+            const float dm = omv[q] - mm[q];
+            kl += logf(s_sigma[c + q] / osv[q] + 1.0e-5f) + (osv[q] * osv[q] + dm * dm) / s_2var[c + q] - 0.5f;
+          }
+        }
+      }
+    } else {
+      for (int a = 0; a < A; ++a) {
+        const float d = ac[a] - m[a];
+        lp += -(d * d) / s_2var[a] - s_logs[a] - kLogSqrt2Pi;
+        if (do_kl) {
+          const float dm = om[a] - m[a], so = os[a];
+          kl += logf(s_sigma[a] / so + 1.0e-5f) + (so * so + dm * dm) / s_2var[a] - 0.5f;
+        }
+      }
+    }
+  }
+
+  float g_lp = 0.f, surr = 0.f, vl = 0.f;
+  if (valid) {
+    float adv = __ldg(advantages + j);
+    if (adv_stats) {  // per-minibatch normalisation (ppo.py:221-223), unbiased std
+      const double n = (double)mb_orig;
+      const double mean = adv_stats[0] / n;
+      double var = (adv_stats[1] - adv_stats[0] * adv_stats[0] / n) / (n - 1.0);
+      var = var > 0.0 ? var : 0.0;
+      adv = (adv - (float)mean) / ((float)sqrt(var) + 1e-8f);
+    }
+    const float ratio = expf(lp - __ldg(old_logp + j));
+    const float s1 = -adv * ratio;
+    const float clamped = fminf(fmaxf(ratio, lo), hi);
+    const float s2 = -adv * clamped;
+    surr = fmaxf(s1, s2);
+    // aten maximum backward: grad to the larger input, grad/2 to both on ties
+    const float g1 = s1 > s2 ? g : (s1 == s2 ? 0.5f * g : 0.f);
+    const float g2 = s2 > s1 ? g : (s1 == s2 ? 0.5f * g : 0.f);
+    const float in_range = (ratio >= lo && ratio <= hi) ? 1.f : 0.f;  // clamp backward mask (inclusive)
+    const float g_ratio = g1 * (-adv) + g2 * (-adv) * in_range;
+    g_lp = g_ratio * ratio;
+
+    const float v = value[i], R = __ldg(returns + j);
+    float dv_out;
+    if (use_clipped) {
+      const float vo = __ldg(old_values + j);
+      const float dv = v - vo;
+      const float vclip = vo + fminf(fmaxf(dv, -clip), clip);
+      const float e1 = v - R, e2 = vclip - R;
+      const float l1 = e1 * e1, l2 = e2 * e2;
+      vl = fmaxf(l1, l2);
+      const float ga = l1 > l2 ? g : (l1 == l2 ? 0.5f * g : 0.f);
+      const float gb = l2 > l1 ? g : (l1 == l2 ? 0.5f * g : 0.f);
+      const float in_v = (dv >= -clip && dv <= clip) ? 1.f : 0.f;
+      dv_out = c_v * (ga * 2.f * e1 + gb * 2.f * e2 * in_v);
+    } else {
+      const float e = R - v;
+      vl = e * e;
+      dv_out = c_v * g * (-2.f) * e;
+    }
+    dvalue[i] = dv_out;
+  }
+
+  // second pass over the row: dL/dmu and the per-action dL/dsigma column sums
+  {
+    const float* m = mu + (valid ? i : 0) * A;
+    const float* ac = actions + (valid ? i : 0) * A;
+    float* dm = dmu + (valid ? i : 0) * A;
+    const int lane = threadIdx.x & 31;
+    for (int c = 0; c < A; c += 4) {
+      float d[4] = {0, 0, 0, 0};
+      const int nq = A - c < 4 ? A - c : 4;
+      if (valid) {
+        if (VEC) {
+          const float4 m4 = *(const float4*)(m + c), a4 = *(const float4*)(ac + c);
+          d[0] = a4.x - m4.x; d[1] = a4.y - m4.y; d[2] = a4.z - m4.z; d[3] = a4.w - m4.w;
+        } else {
+          for (int q = 0; q < nq; ++q) d[q] = ac[c + q] - m[c + q];
+        }
+      }
+      float o[4] = {0, 0, 0, 0};
+      for (int q = 0; q < nq; ++q) {
+        const float s = s_sigma[c + q];
+        const float var = s * s;
+        o[q] = g_lp * d[q] / var;
+        float ds = valid ? g_lp * (d[q] * d[q] / (var * s) - 1.f / s) : 0.f;
+        ds = warp_sum(ds);
+        if (lane == 0) atomicAdd(&s_dstd[c + q], ds);
+      }
+      if (valid) {
+        if (VEC) *(float4*)(dm + c) = make_float4(o[0], o[1], o[2], o[3]);
+        else for (int q = 0; q < nq; ++q) dm[c + q] = o[q];
+      }
+    }
+  }
+
+  double red[3] = {(double)kl, (double)surr, (double)vl};
+  block_sum<3>(red, s_red);
+  if (threadIdx.x == 0) {
+    atomicAdd(&ws->acc[0], red[0]);
+    atomicAdd(&ws->acc[1], red[1]);
+    atomicAdd(&ws->acc[2], red[2]);
+  }
+  __syncthreads();
+  if (threadIdx.x < A) atomicAdd(&ws->acc[4 + threadIdx.x], (double)s_dstd[threadIdx.x]);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&ws->ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // ---- last block: publish and clear
+  if (threadIdx.x < A) {
+    const int a = threadIdx.x;
+    const float s = s_sigma[a];
+    // entropy bonus -c_e * mean_i sum_a log sigma_a  ->  d/dsigma_a = -c_e / sigma_a (x sigma for log-std)
+    double gsum = *((volatile double*)&ws->acc[4 + a]);
+    if (std_type == RSLRL_STD_LOG) gsum = gsum * (double)s - (double)c_e;
+    else gsum = gsum - (double)c_e / (double)s;
+    dstd[a] += (float)gsum;
+    ws->acc[4 + a] = 0.0;
+  }
+  if (threadIdx.x == 0) {
+    const double klm = *((volatile double*)&ws->acc[0]) / (double)mb_orig;
+    if (kl_out) *kl_out = (float)klm;
+    float ent = 0.f;
+    for (int a = 0; a < A; ++a) ent += kEntropyConst + s_logs[a];
+    if (loss_sums) {
+      loss_sums[0] += *((volatile double*)&ws->acc[1]) / (double)rows;
+      loss_sums[1] += *((volatile double*)&ws->acc[2]) / (double)rows;
+      loss_sums[2] += (double)ent;
+    }
+    ws->acc[0] = ws->acc[1] = ws->acc[2] = ws->acc[3] = 0.0;
+    __threadfence();
+    ws->ticket = 0u;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+sum_sumsq_kernel(const float* __restrict__ x, long long n, double* out, SumWorkspace* ws) {
+  __shared__ double s_red[2 * 32];
+  __shared__ bool s_last;
+  double v[2] = {0.0, 0.0};
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const double a = (double)__ldg(x + i);
+    v[0] += a;
+    v[1] += a * a;
+  }
+  block_sum<2>(v, s_red);
+  if (threadIdx.x == 0) {
+    atomicAdd(&ws->acc[0], v[0]);
+    atomicAdd(&ws->acc[1], v[1]);
+    __threadfence();
+    s_last = atomicAdd(&ws->ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    out[0] = *((volatile double*)&ws->acc[0]);
+    out[1] = *((volatile double*)&ws->acc[1]);
+    ws->acc[0] = ws->acc[1] = 0.0;
+    __threadfence();
+    ws->ticket = 0u;
+  }
+}
+
+}  // namespace rslrl
+
+extern "C" {
+
+int rslrl_gaussian_act(const float* mu, const float* std_param, int std_type, const float* z, float* actions,
+                       float* log_prob, float* sigma_out, int64_t n, int A, rslrl_stream_t stream) {
+  using namespace rslrl;
+  const char* what = "rslrl_gaussian_act";
+  RSLRL_CHECK_ARG(mu && std_param && z && actions && log_prob, what);
+  RSLRL_CHECK_ARG(n > 0 && A > 0 && A <= kMaxActions, what);
+  const int blocks = (int)((n + kLossThreads - 1) / kLossThreads);
+  gaussian_act_kernel<<<blocks, kLossThreads, 0, (cudaStream_t)stream>>>(mu, std_param, std_type, z, actions,
+                                                                          log_prob, sigma_out, n, A);
+  return finish_launch(what);
+}
+
+int64_t rslrl_loss_workspace_bytes(void) { return (int64_t)sizeof(rslrl::LossWorkspace); }
+
+int rslrl_ppo_loss_fwd_bwd(const float* mu, const float* std_param, int std_type, const float* value,
+                           const float* actions, const float* old_logp, const float* advantages,
+                           const float* returns, const float* old_values, const float* old_mu,
+                           const float* old_sigma, const double* adv_stats, float* dmu, float* dvalue,
+                           float* dstd, float* kl_out, double* loss_sums, void* workspace, int64_t rows,
+                           int64_t mb_orig, int A, double clip_param, double value_loss_coef,
+                           double entropy_coef, int use_clipped_value_loss, rslrl_stream_t stream) {
+  using namespace rslrl;
+  const char* what = "rslrl_ppo_loss_fwd_bwd";
+  RSLRL_CHECK_ARG(mu && std_param && value && actions && old_logp && advantages && returns && old_values, what);
+  RSLRL_CHECK_ARG(old_mu && old_sigma && dmu && dvalue && dstd && workspace, what);
+  RSLRL_CHECK_ARG(rows > 0 && mb_orig > 0 && rows % mb_orig == 0 && A > 0 && A <= kMaxActions, what);
+  const int blocks = (int)((rows + kLossThreads - 1) / kLossThreads);
+  const bool vec = (A % 4 == 0) && ((((uintptr_t)mu | (uintptr_t)actions | (uintptr_t)old_mu | (uintptr_t)old_sigma |
+                                      (uintptr_t)dmu) & 15) == 0);
+  auto kern = vec ? ppo_loss_kernel<true> : ppo_loss_kernel<false>;
+  kern<<<blocks, kLossThreads, 0, (cudaStream_t)stream>>>(
+      mu, std_param, std_type, value, actions, old_logp, advantages, returns, old_values, old_mu, old_sigma, adv_stats,
+      dmu, dvalue, dstd, kl_out, loss_sums, (LossWorkspace*)workspace, rows, mb_orig, A, (float)clip_param,
+      (float)value_loss_coef, (float)entropy_coef, use_clipped_value_loss);
+  return finish_launch(what);
+}
+
+int rslrl_sum_sumsq(const float* x, int64_t n, double* out, void* workspace, rslrl_stream_t stream) {
+  using namespace rslrl;
+  const char* what = "rslrl_sum_sumsq";
+  RSLRL_CHECK_ARG(x && out && workspace && n > 0, what);
+  long long blocks = (n + 256 * 8 - 1) / (256 * 8);
+  if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
+  sum_sumsq_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, out, (SumWorkspace*)workspace);
+  return finish_launch(what);
+}
+
+}  // extern "C"

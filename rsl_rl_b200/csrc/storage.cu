@@ -1,0 +1,198 @@
+// Rollout buffer kernels: single-launch transition store and the permuted minibatch gather.
+//
+// The rollout buffer is a structure of arrays in HBM: one dense [T,N,d] fp32 array per field
+// (observation groups, actions, mu, sigma, values, log-probs, rewards, returns, advantages) and a
+// [T,N] u8 array for dones -- byte-identical to the reference's tensors
+// (rsl_rl/storage/rollout_storage.py:47-68).  Row `step` of every array is one contiguous span, so
+// add_transitions is a set of straight copies: here one launch (grid.y = segment) with 16-byte
+// vector accesses, fused with the reward bootstrap and the dones dtype conversion.
+#include "common.cuh"
+
+namespace rslrl {
+
+constexpr int kCopyThreads = 256;
+
+struct CopySeg {
+  const float* src;
+  float* dst;
+  long long count;  // floats
+};
+
+struct StoreParams {
+  int n_copy;
+  CopySeg copy[RSLRL_MAX_SEGMENTS + 6];
+  // sigma broadcast ([A] -> [N,A]); sigma == nullptr when sigma is copied as a plain segment
+  const float* sigma;
+  float* sigma_row;
+  // rewards / dones
+  const float* rewards;
+  const float* values;
+  const float* intrinsic;
+  const void* time_outs;
+  const void* dones;
+  float* rewards_row;
+  uint8_t* dones_row;
+  int time_outs_dtype, dones_dtype;
+  float gamma;
+  int N, A;
+};
+
+__device__ __forceinline__ float load_flag(const void* p, int dtype, int i) {
+  switch (dtype) {
+    case RSLRL_U8: return (float)((const uint8_t*)p)[i];
+    case RSLRL_I32: return (float)((const int32_t*)p)[i];
+    case RSLRL_I64: return (float)((const long long*)p)[i];
+    default: return ((const float*)p)[i];
+  }
+}
+
+__global__ void __launch_bounds__(kCopyThreads) store_transition_kernel(const StoreParams p) {
+  const int seg = blockIdx.y;
+  const long long tid = (long long)blockIdx.x * kCopyThreads + threadIdx.x;
+  const long long stride = (long long)gridDim.x * kCopyThreads;
+  if (seg < p.n_copy) {
+    const CopySeg s = p.copy[seg];
+    const bool vec = (((uintptr_t)s.src | (uintptr_t)s.dst) & 15) == 0 && (s.count & 3) == 0;
+    if (vec) {
+      const float4* src = (const float4*)s.src;
+      float4* dst = (float4*)s.dst;
+      for (long long i = tid; i < (s.count >> 2); i += stride) dst[i] = __ldg(src + i);
+    } else {
+      for (long long i = tid; i < s.count; i += stride) s.dst[i] = __ldg(s.src + i);
+    }
+  } else if (seg == p.n_copy) {
+    // rewards (+ intrinsic) + gamma * (values * time_outs)   [ppo.py:150-164], dones -> u8 [rollout_storage.py:86]
+    for (long long i = tid; i < p.N; i += stride) {
+      float r = __ldg(p.rewards + i);
+      if (p.intrinsic) r = __fadd_rn(r, __ldg(p.intrinsic + i));
+      if (p.time_outs) {
+        const float to = load_flag(p.time_outs, p.time_outs_dtype, (int)i);
+        r = __fadd_rn(r, __fmul_rn(p.gamma, __fmul_rn(__ldg(p.values + i), to)));
+      }
+      p.rewards_row[i] = r;
+      const float d = load_flag(p.dones, p.dones_dtype, (int)i);
+      p.dones_row[i] = (uint8_t)(int)d;  // Tensor.copy_ float/int -> uint8 truncation
+    }
+  } else if (p.sigma) {
+    const long long total = (long long)p.N * p.A;
+    for (long long i = tid; i < total; i += stride) p.sigma_row[i] = __ldg(p.sigma + (i % p.A));
+  }
+}
+
+struct GatherField {
+  const float* src;
+  float* dst;
+  int row_floats, dst_stride, dst_col;
+};
+
+struct GatherParams {
+  GatherField f[RSLRL_MAX_SEGMENTS];
+  const long long* idx;
+  long long n_rows;
+};
+
+__global__ void __launch_bounds__(kCopyThreads) permute_gather_kernel(const GatherParams p) {
+  const GatherField f = p.f[blockIdx.y];
+  const long long tid = (long long)blockIdx.x * kCopyThreads + threadIdx.x;
+  const long long stride = (long long)gridDim.x * kCopyThreads;
+  const bool vec = (f.row_floats & 3) == 0 && (f.dst_stride & 3) == 0 && (f.dst_col & 3) == 0 &&
+                   (((uintptr_t)f.src | (uintptr_t)f.dst) & 15) == 0;
+  if (vec) {
+    const int chunks = f.row_floats >> 2;
+    const long long units = p.n_rows * chunks;
+    for (long long u = tid; u < units; u += stride) {
+      const long long j = u / chunks;
+      const int c = (int)(u - j * chunks);
+      const long long s = __ldg(p.idx + j);
+      const float4 v = __ldg((const float4*)(f.src + s * f.row_floats) + c);
+      *((float4*)(f.dst + j * f.dst_stride + f.dst_col) + c) = v;
+    }
+  } else {
+    const long long units = p.n_rows * f.row_floats;
+    for (long long u = tid; u < units; u += stride) {
+      const long long j = u / f.row_floats;
+      const int c = (int)(u - j * f.row_floats);
+      const long long s = __ldg(p.idx + j);
+      f.dst[j * f.dst_stride + f.dst_col + c] = __ldg(f.src + s * f.row_floats + c);
+    }
+  }
+}
+
+static int grid_for(long long units) {
+  long long b = (units + kCopyThreads - 1) / kCopyThreads;
+  const long long cap = (long long)kNumSMs * 8;
+  if (b > cap) b = cap;
+  return b < 1 ? 1 : (int)b;
+}
+
+}  // namespace rslrl
+
+extern "C" {
+
+int rslrl_store_transition(int n_groups, const float* const* obs_src_host, float* const* obs_dst_host,
+                           const int* obs_dim_host, const float* actions, const float* mu, const float* sigma,
+                           int sigma_stride, const float* values, const float* log_prob, const float* rewards,
+                           const void* dones, int dones_dtype, const void* time_outs, int time_outs_dtype,
+                           const float* intrinsic, double gamma, float* actions_row, float* mu_row,
+                           float* sigma_row, float* values_row, float* log_prob_row, float* rewards_row,
+                           uint8_t* dones_row, int N, int A, rslrl_stream_t stream) {
+  using namespace rslrl;
+  const char* what = "rslrl_store_transition";
+  RSLRL_CHECK_ARG(n_groups >= 0 && n_groups <= RSLRL_MAX_SEGMENTS, what);
+  RSLRL_CHECK_ARG(N > 0 && A > 0 && rewards && dones && rewards_row && dones_row, what);
+  RSLRL_CHECK_ARG(sigma_stride == 0 || sigma_stride == A, what);
+  StoreParams p{};
+  long long max_units = N;
+  auto add = [&](const float* s, float* d, long long count) {
+    if (!s || !d) return;
+    p.copy[p.n_copy++] = CopySeg{s, d, count};
+    if (count > max_units) max_units = count;
+  };
+  for (int g = 0; g < n_groups; ++g) add(obs_src_host[g], obs_dst_host[g], (long long)N * obs_dim_host[g]);
+  add(actions, actions_row, (long long)N * A);
+  add(mu, mu_row, (long long)N * A);
+  add(values, values_row, N);
+  add(log_prob, log_prob_row, N);
+  if (sigma && sigma_row) {
+    if (sigma_stride == A) {
+      add(sigma, sigma_row, (long long)N * A);
+    } else {
+      p.sigma = sigma;
+      p.sigma_row = sigma_row;
+      if ((long long)N * A > max_units) max_units = (long long)N * A;
+    }
+  }
+  p.rewards = rewards; p.values = values; p.intrinsic = intrinsic; p.time_outs = time_outs; p.dones = dones;
+  p.rewards_row = rewards_row; p.dones_row = dones_row;
+  p.time_outs_dtype = time_outs_dtype; p.dones_dtype = dones_dtype;
+  p.gamma = (float)gamma; p.N = N; p.A = A;
+  RSLRL_CHECK_ARG(!time_outs || values, what);
+  dim3 grid(grid_for(max_units / 4 + 1), p.n_copy + 1 + (p.sigma ? 1 : 0));
+  store_transition_kernel<<<grid, kCopyThreads, 0, (cudaStream_t)stream>>>(p);
+  return finish_launch(what);
+}
+
+int rslrl_permute_gather(int n_fields, const float* const* src_host, float* const* dst_host,
+                         const int* row_floats_host, const int* dst_stride_host, const int* dst_col_host,
+                         const int64_t* idx, int64_t n_rows, rslrl_stream_t stream) {
+  using namespace rslrl;
+  const char* what = "rslrl_permute_gather";
+  RSLRL_CHECK_ARG(n_fields > 0 && n_fields <= RSLRL_MAX_SEGMENTS && idx && n_rows >= 0, what);
+  if (n_rows == 0) return 0;
+  GatherParams p{};
+  long long max_units = 1;
+  for (int i = 0; i < n_fields; ++i) {
+    RSLRL_CHECK_ARG(src_host[i] && dst_host[i] && row_floats_host[i] > 0, what);
+    RSLRL_CHECK_ARG(dst_stride_host[i] >= dst_col_host[i] + row_floats_host[i], what);
+    p.f[i] = GatherField{src_host[i], dst_host[i], row_floats_host[i], dst_stride_host[i], dst_col_host[i]};
+    const long long chunks = (row_floats_host[i] + 3) / 4;
+    if (n_rows * chunks > max_units) max_units = n_rows * chunks;
+  }
+  p.idx = (const long long*)idx;
+  p.n_rows = n_rows;
+  dim3 grid(grid_for(max_units), n_fields);
+  permute_gather_kernel<<<grid, kCopyThreads, 0, (cudaStream_t)stream>>>(p);
+  return finish_launch(what);
+}
+
+}  // extern "C"

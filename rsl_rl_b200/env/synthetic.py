@@ -1,0 +1,84 @@
+"""Seeded synthetic VecEnv used by the tests, the smoke test and bench.py.
+
+obs ~ N(0,1) per group, rewards ~ N(0,1), dones ~ Bernoulli(p_done) as int64, half of the dones are
+flagged as time-outs; actions are ignored.  Random numbers come from the env's own generator so the
+policy's RNG stream is untouched.  `ReplayVecEnv` replays a recorded stream (golden fixtures).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from ..utils.tensordict_lite import TensorDict
+from .vec_env import VecEnv
+
+
+class SynthVecEnv(VecEnv):
+    def __init__(self, num_envs: int, group_dims: Optional[Dict[str, int]] = None, num_actions: int = 12,
+                 device="cuda:0", seed: int = 0, p_done: float = 0.02, p_timeout: float = 0.5,
+                 pinned_host: bool = False):
+        self.num_envs, self.num_actions = num_envs, num_actions
+        self.group_dims = dict(group_dims or {"policy": 48})
+        self.device = device
+        self.max_episode_length = 1000
+        self.episode_length_buf = torch.zeros(num_envs, dtype=torch.long, device=device)
+        self.cfg = {}
+        self.step_dt = 0.02
+        self.unwrapped = self
+        self.p_done, self.p_timeout = p_done, p_timeout
+        self.gen = torch.Generator(device=device)
+        self.gen.manual_seed(seed)
+        self._pin = pinned_host and torch.device(device).type == "cpu" and torch.cuda.is_available()
+        self._obs = self._draw_obs()
+
+    def _maybe_pin(self, t):
+        return t.pin_memory() if self._pin else t
+
+    def _draw_obs(self):
+        obs = {k: self._maybe_pin(torch.randn(self.num_envs, d, generator=self.gen, device=self.device))
+               for k, d in self.group_dims.items()}
+        return TensorDict(obs, batch_size=[self.num_envs], device=self.device)
+
+    def get_observations(self):
+        return self._obs
+
+    def step(self, actions):
+        n, dev = self.num_envs, self.device
+        rewards = self._maybe_pin(torch.randn(n, generator=self.gen, device=dev))
+        dones = self._maybe_pin((torch.rand(n, generator=self.gen, device=dev) < self.p_done).long())
+        time_outs = self._maybe_pin((torch.rand(n, generator=self.gen, device=dev) < self.p_timeout) & (dones > 0))
+        self._obs = self._draw_obs()
+        return self._obs, rewards, dones, {"time_outs": time_outs}
+
+
+class ReplayVecEnv(VecEnv):
+    """Replays recorded tensors: obs[k]: [S+1, N, d], rewards/dones/time_outs: [S, N]."""
+
+    def __init__(self, obs: Dict[str, torch.Tensor], rewards, dones, time_outs, num_actions: int, device="cuda:0"):
+        self._obs = {k: v.to(device) for k, v in obs.items()}
+        self._rew, self._done = rewards.to(device), dones.to(device)
+        self._to = None if time_outs is None else time_outs.to(device)
+        first = next(iter(self._obs.values()))
+        self.num_envs, self.num_actions = first.shape[1], num_actions
+        self.device = device
+        self.max_episode_length = 1000
+        self.episode_length_buf = torch.zeros(self.num_envs, dtype=torch.long, device=device)
+        self.cfg = {}
+        self.step_dt = 0.02
+        self.unwrapped = self
+        self.t = 0
+        self.actions_seen = []
+
+    def _cur(self):
+        return TensorDict({k: v[self.t] for k, v in self._obs.items()}, batch_size=[self.num_envs], device=self.device)
+
+    def get_observations(self):
+        return self._cur()
+
+    def step(self, actions):
+        self.actions_seen.append(actions.clone())
+        r, d = self._rew[self.t], self._done[self.t]
+        extras = {} if self._to is None else {"time_outs": self._to[self.t]}
+        self.t += 1
+        return self._cur(), r, d, extras

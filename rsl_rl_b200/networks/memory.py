@@ -1,0 +1,56 @@
+"""Recurrent memory in front of the MLPs (mirror of `rsl_rl/networks/memory.py`).
+
+State-dict keys stay `rnn.weight_ih_l0`, ... (an `nn.LSTM` / `nn.GRU` owns the parameters).  The padded
+trajectory layout and its inverse come from the segmented-scan kernels (utils.TrajectoryIndex); the
+recurrence itself currently runs through the cuDNN RNN that `nn.LSTM` dispatches to (library call --
+a persistent sm_100a LSTM kernel is the open item of SURVEY.md section 8 row A14)."""
+from __future__ import annotations
+
+import torch.nn as nn
+
+from ..utils.utils import unpad_trajectories
+
+
+class Memory(nn.Module):
+    def __init__(self, input_size, type="lstm", num_layers=1, hidden_size=256):
+        super().__init__()
+        rnn_cls = nn.GRU if type.lower() == "gru" else nn.LSTM
+        self.rnn = rnn_cls(input_size=input_size, hidden_size=hidden_size, num_layers=num_layers)
+        self.hidden_states = None
+        self._unpad = None  # optional fast unpad (set by the recurrent generator): callable(out) -> [T, N_mb, H]
+
+    def forward(self, input, masks=None, hidden_states=None):
+        batch_mode = masks is not None
+        if batch_mode:
+            if hidden_states is None:
+                raise ValueError("Hidden states not passed to memory module during policy update")
+            out, _ = self.rnn(input, hidden_states)
+            out = unpad_trajectories(out, masks)
+        else:
+            out, self.hidden_states = self.rnn(input.unsqueeze(0), self.hidden_states)
+        return out
+
+    def reset(self, dones=None, hidden_states=None):
+        if dones is None:
+            self.hidden_states = hidden_states
+        elif self.hidden_states is not None:
+            if hidden_states is None:
+                states = self.hidden_states if isinstance(self.hidden_states, tuple) else (self.hidden_states,)
+                for h in states:
+                    h[..., dones == 1, :] = 0.0
+            else:
+                raise NotImplementedError(
+                    "Resetting hidden states of done environments with custom hidden states is not implemented")
+
+    def detach_hidden_states(self, dones=None):
+        if self.hidden_states is None:
+            return
+        if dones is None:
+            if isinstance(self.hidden_states, tuple):
+                self.hidden_states = tuple(h.detach() for h in self.hidden_states)
+            else:
+                self.hidden_states = self.hidden_states.detach()
+        else:
+            states = self.hidden_states if isinstance(self.hidden_states, tuple) else (self.hidden_states,)
+            for h in states:
+                h[..., dones == 1, :] = h[..., dones == 1, :].detach()

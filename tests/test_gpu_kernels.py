@@ -1,0 +1,434 @@
+"""GPU: every kernel behind include/rslrl_b200.h against the numpy oracle / the reference's golden
+vectors.  Bit-exact for integer, byte, index and copy work and for the GAE scan; fp tolerances are the
+north-star classes (1e-6 GAE, 1e-5 fp32 GEMM path) read as max-abs error / max-abs value."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ppo_oracle as O
+from tests.golden_util import load, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def cu(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to(DEV)
+
+
+def _nat():
+    from rsl_rl_b200 import _native as nat
+    return nat
+
+
+# ----------------------------------------------------------------------------------------------- GAE
+def _gae_cuda(rewards, values, dones, last_values, gamma, lam, normalize):
+    from rsl_rl_b200.storage import RolloutStorage
+    from rsl_rl_b200.utils import TensorDictLite
+    T, N = rewards.shape[:2]
+    st = RolloutStorage("rl", N, T, TensorDictLite({"policy": torch.zeros(N, 1, device=DEV)}, batch_size=[N]), [1], DEV)
+    st.rewards.copy_(cu(rewards)); st.values.copy_(cu(values)); st.dones.copy_(cu(dones))
+    st.compute_returns(cu(last_values), gamma, lam, normalize_advantage=normalize)
+    torch.cuda.synchronize()
+    return st.returns.cpu().numpy(), st.advantages.cpu().numpy()
+
+
+def test_gae_matches_reference_golden_vectors():
+    g = load("gae_cases")
+    names = sorted({k.rsplit(".", 1)[0] for k in g.files if k.endswith(".returns")})
+    for n in names:
+        gamma, lam = (0.9, 0.8) if n.startswith("odd") else (0.99, 0.95)
+        ret, adv = _gae_cuda(g[n + ".rewards"], g[n + ".values"], g[n + ".dones"], g[n + ".last_values"], gamma, lam,
+                             n.endswith("norm"))
+        assert np.array_equal(ret, g[n + ".returns"]), n          # scan keeps the reference's fp32 op order
+        if n.endswith("raw"):
+            assert np.array_equal(adv, g[n + ".advantages"]), n
+        else:
+            assert rel_err(adv, g[n + ".advantages"]) < 1e-6, n
+
+
+@pytest.mark.parametrize("T,N", [(24, 4096), (24, 65536), (40, 300), (7, 1), (24, 200000), (64, 5000)])
+def test_gae_vs_oracle_all_kernel_variants(T, N):
+    """Register kernels (T<=32), generic kernel (T>32 or more envs than resident threads)."""
+    rng = np.random.default_rng(T * 1000 + N)
+    rewards = rng.standard_normal((T, N, 1)).astype(np.float32)
+    values = (2 * rng.standard_normal((T, N, 1))).astype(np.float32)
+    dones = (rng.random((T, N, 1)) < 0.03).astype(np.uint8)
+    last = rng.standard_normal((N, 1)).astype(np.float32)
+    if T * N < 2:
+        pytest.skip("std of a single element is undefined")
+    ret_o, adv_o = O.compute_returns(rewards, values, dones, last, 0.99, 0.95, True)
+    ret, adv = _gae_cuda(rewards, values, dones, last, 0.99, 0.95, True)
+    assert np.array_equal(ret, ret_o)
+    assert rel_err(adv, adv_o) < 1e-6
+    # size-independent properties: normalised advantages have mean 0 / unbiased std 1
+    a64 = adv.astype(np.float64)
+    assert abs(a64.mean()) < 1e-5 and abs(a64.std(ddof=1) - 1) < 1e-5
+    _, adv_raw = _gae_cuda(rewards, values, dones, last, 0.99, 0.95, False)
+    assert np.array_equal(adv_raw, (ret_o - values))
+
+
+# ------------------------------------------------------------------------------------ storage / gather
+@pytest.mark.parametrize("dones_dtype", [torch.int64, torch.bool, torch.uint8, torch.float32, torch.int32])
+@pytest.mark.parametrize("sigma_broadcast", [True, False])
+def test_store_transition_bit_exact(dones_dtype, sigma_broadcast):
+    from rsl_rl_b200.storage import RolloutStorage
+    from rsl_rl_b200.utils import TensorDictLite
+    torch.manual_seed(1)
+    N, A, T = 1000, 12, 3
+    obs = TensorDictLite({"a": torch.randn(N, 48, device=DEV), "b": torch.randn(N, 7, device=DEV)}, batch_size=[N])
+    st = RolloutStorage("rl", N, T, obs, [A], DEV)
+    gamma = 0.99
+    for step in range(T):
+        tr = RolloutStorage.Transition()
+        tr.observations = TensorDictLite({"a": torch.randn(N, 48, device=DEV), "b": torch.randn(N, 7, device=DEV)},
+                                         batch_size=[N])
+        tr.actions, tr.action_mean = torch.randn(N, A, device=DEV), torch.randn(N, A, device=DEV)
+        std = torch.rand(A, device=DEV) + 0.5
+        tr.action_sigma = std.expand(N, A) if sigma_broadcast else torch.rand(N, A, device=DEV)
+        tr.values, tr.actions_log_prob = torch.randn(N, 1, device=DEV), torch.randn(N, device=DEV)
+        tr.rewards = torch.randn(N, device=DEV)
+        d = torch.rand(N, device=DEV) < 0.3
+        tr.dones = d.to(dones_dtype)
+        to = (torch.rand(N, device=DEV) < 0.5) & d if step != 1 else None
+        exp_r = tr.rewards.clone()
+        if to is not None:
+            exp_r += gamma * torch.squeeze(tr.values * to.unsqueeze(1), 1)   # the reference's expression
+        st._store(tr, time_outs=to, gamma=gamma)
+        torch.cuda.synchronize()
+        assert torch.equal(st.observations["a"][step], tr.observations["a"])
+        assert torch.equal(st.observations["b"][step], tr.observations["b"])
+        assert torch.equal(st.actions[step], tr.actions) and torch.equal(st.mu[step], tr.action_mean)
+        assert torch.equal(st.sigma[step], tr.action_sigma.contiguous())
+        assert torch.equal(st.values[step], tr.values)
+        assert torch.equal(st.actions_log_prob[step].view(-1), tr.actions_log_prob)
+        assert torch.equal(st.rewards[step].view(-1), exp_r)
+        assert torch.equal(st.dones[step].view(-1), d.to(torch.uint8))
+    with pytest.raises(OverflowError):
+        st._store(tr)
+
+
+@pytest.mark.parametrize("widths", [(48,), (235, 1, 12), (187, 48, 4, 3)])
+def test_permute_gather_bit_exact_with_concat(widths):
+    from rsl_rl_b200.storage import RolloutStorage
+    torch.manual_seed(2)
+    B, n = 5000, 1237
+    idx = torch.randperm(B, device=DEV)[:n]
+    srcs = [torch.randn(B, w, device=DEV) for w in widths]
+    total = sum(widths)
+    ld = (total + 3) // 4 * 4
+    dst = torch.zeros(n, ld, device=DEV)
+    st = RolloutStorage.__new__(RolloutStorage)
+    cols = list(np.cumsum([0] + list(widths[:-1])))
+    st._gather(srcs, list(widths), idx, [dst] * len(widths), [ld] * len(widths), [int(c) for c in cols])
+    torch.cuda.synchronize()
+    assert torch.equal(dst[:, :total], torch.cat([s[idx] for s in srcs], dim=1))
+
+
+def test_mini_batch_generator_matches_reference_protocol():
+    """Same 10-tuple, bit-equal tensors for the same permutation (reference rollout_storage.py:160-203)."""
+    from rsl_rl_b200.storage import RolloutStorage
+    from rsl_rl_b200.utils import TensorDictLite
+    torch.manual_seed(3)
+    N, T, A, M, E = 64, 8, 4, 4, 2
+    obs = TensorDictLite({"policy": torch.zeros(N, 12, device=DEV), "extra": torch.zeros(N, 5, device=DEV)}, batch_size=[N])
+    st = RolloutStorage("rl", N, T, obs, [A], DEV)
+    for t in (st.observations["policy"], st.observations["extra"], st.actions, st.values, st.advantages, st.returns,
+              st.actions_log_prob, st.mu, st.sigma):
+        t.normal_()
+    perm = torch.randperm(N * T, device=DEV)
+    st._randperm = lambda n: perm
+    batches = list(st.mini_batch_generator(M, E))
+    assert len(batches) == M * E
+    mb = N * T // M
+    for k, b in enumerate(batches):
+        idx = perm[(k % M) * mb:(k % M + 1) * mb]
+        obs_b, actions, values, adv, ret, logp, mu, sigma, hid, masks = b
+        assert hid == (None, None) and masks is None and obs_b.batch_size[0] == mb
+        assert torch.equal(obs_b["policy"], st.observations["policy"].flatten(0, 1)[idx])
+        assert torch.equal(obs_b["extra"], st.observations["extra"].flatten(0, 1)[idx])
+        for got, src in ((actions, st.actions), (values, st.values), (adv, st.advantages), (ret, st.returns),
+                         (logp, st.actions_log_prob), (mu, st.mu), (sigma, st.sigma)):
+            assert torch.equal(got, src.flatten(0, 1)[idx]) and got.is_contiguous()
+    # default path: torch.randperm on the device, every index exactly once
+    del st._randperm
+    st._randperm = lambda n: torch.randperm(n, device=DEV)
+    seen = torch.cat([b[1] for b in list(st.mini_batch_generator(M, 1))])
+    assert seen.shape[0] == N * T
+
+
+# -------------------------------------------------------------------------------------------- GEMMs
+def _lin_ref(x, w, b, act):
+    z = x.double() @ w.double().T + (0 if b is None else b.double())
+    return torch.from_numpy(O.act_forward(act, z.cpu().numpy().astype(np.float32)).astype(np.float64)).to(DEV) \
+        if act != "identity" else z
+
+
+@pytest.mark.parametrize("M,K,N,act", [(1000, 48, 512, "elu"), (4096, 235, 512, "elu"), (777, 512, 256, "relu"),
+                                        (2048, 128, 12, "identity"), (2048, 128, 1, "identity"), (130, 5, 3, "tanh"),
+                                        (24576, 256, 128, "elu"), (64, 16, 200, "selu"), (300, 33, 65, "sigmoid"),
+                                        (300, 33, 65, "lrelu"), (300, 33, 65, "softplus")])
+def test_linear_forward_fp32(M, K, N, act):
+    from rsl_rl_b200.networks.mlp import linear_forward
+    nat = _nat()
+    torch.manual_seed(M + K + N)
+    x = torch.randn(M, K, device=DEV); w = torch.randn(N, K, device=DEV) / K ** 0.5; b = torch.randn(N, device=DEV)
+    y = torch.empty(M, N, device=DEV)
+    linear_forward([(x, w, b, y, nat.ACT_CODES[act])], nat.PREC_FP32)
+    ref = _lin_ref(x, w, b, act)
+    assert rel_err(y.cpu().numpy(), ref.cpu().numpy()) < 1e-5
+
+
+def test_linear_forward_grouped_and_strided_input():
+    from rsl_rl_b200.networks.mlp import linear_forward
+    nat = _nat()
+    torch.manual_seed(5)
+    xa = torch.randn(3000, 52, device=DEV)[:, :50]          # row stride 52, K = 50 (padded minibatch buffer)
+    xc = torch.randn(3000, 48, device=DEV)
+    wa, ba = torch.randn(96, 50, device=DEV), torch.randn(96, device=DEV)
+    wc, bc = torch.randn(33, 48, device=DEV), None
+    ya, yc = torch.empty(3000, 96, device=DEV), torch.empty(3000, 33, device=DEV)
+    linear_forward([(xa, wa, ba, ya, nat.ACT_CODES["elu"]), (xc, wc, bc, yc, 0)], nat.PREC_FP32)
+    assert rel_err(ya.cpu().numpy(), _lin_ref(xa, wa, ba, "elu").cpu().numpy()) < 1e-5
+    assert rel_err(yc.cpu().numpy(), _lin_ref(xc, wc, bc, "identity").cpu().numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("M,K,N,act", [(1000, 512, 256, "elu"), (4096, 128, 12, "elu"), (3000, 128, 1, "relu"),
+                                        (24576, 256, 128, "elu"), (513, 37, 5, "tanh"), (600, 48, 512, "identity")])
+def test_linear_backward_fp32(M, K, N, act):
+    """dx = (dy W) * act'(h), dW += dy^T x, db += colsum(dy) against an fp64 restatement."""
+    from rsl_rl_b200.networks.mlp import linear_backward_data, linear_backward_weight
+    nat = _nat()
+    torch.manual_seed(M + N)
+    z_prev = torch.randn(M, K, device=DEV)
+    h = torch.from_numpy(O.act_forward(act, z_prev.cpu().numpy())).to(DEV)          # this layer's input
+    w = torch.randn(N, K, device=DEV) / K ** 0.5
+    dy = torch.randn(M, N, device=DEV)
+    dx = torch.empty(M, K, device=DEV)
+    linear_backward_data([(dy, w, h, dx, nat.ACT_CODES[act])], nat.PREC_FP32)
+    dh = (dy.double() @ w.double()).cpu().numpy()
+    ref_dx = O.act_backward(act, z_prev.cpu().numpy(), h.cpu().numpy(), dh.astype(np.float32)) if act != "identity" else dh
+    assert rel_err(dx.cpu().numpy(), ref_dx) < 1e-5
+    dw = torch.zeros(N, K, device=DEV); db = torch.zeros(N, device=DEV)
+    linear_backward_weight([(dy, h, dw, db)], nat.PREC_FP32)
+    assert rel_err(dw.cpu().numpy(), (dy.double().T @ h.double()).cpu().numpy()) < 1e-5
+    assert rel_err(db.cpu().numpy(), dy.double().sum(0).cpu().numpy()) < 1e-5
+    linear_backward_weight([(dy, h, dw, db)], nat.PREC_FP32)                        # accumulates
+    assert rel_err(dw.cpu().numpy(), 2 * (dy.double().T @ h.double()).cpu().numpy()) < 1e-5
+
+
+def test_mlp_autograd_function_matches_torch():
+    from rsl_rl_b200.networks import MLP
+    torch.manual_seed(7)
+    mlp = MLP(20, 3, [32, -1, 16], "elu").to(DEV)
+    ref = torch.nn.Sequential(*[torch.nn.Linear(l.in_features, l.out_features) if isinstance(l, torch.nn.Linear)
+                                else torch.nn.ELU() for l in mlp]).to(DEV).double()
+    ref.load_state_dict({k: v.double() for k, v in mlp.state_dict().items()})
+    x = torch.randn(257, 20, device=DEV, requires_grad=True)
+    xr = x.detach().double().requires_grad_(True)
+    y, yr = mlp(x), ref(xr)
+    assert rel_err(y.detach().cpu().numpy(), yr.detach().cpu().numpy()) < 1e-5
+    y.square().sum().backward(); yr.square().sum().backward()
+    assert rel_err(x.grad.cpu().numpy(), xr.grad.cpu().numpy()) < 1e-5
+    for p, pr in zip(mlp.parameters(), ref.parameters()):
+        assert rel_err(p.grad.cpu().numpy(), pr.grad.cpu().numpy()) < 1e-5
+    assert list(mlp.state_dict().keys()) == ["0.weight", "0.bias", "2.weight", "2.bias", "4.weight", "4.bias",
+                                             "6.weight", "6.bias"]
+
+
+# ------------------------------------------------------------------------------- gaussian head / loss
+@pytest.mark.parametrize("A,std_type", [(12, "scalar"), (5, "log"), (3, "scalar")])
+def test_gaussian_act(A, std_type):
+    nat = _nat()
+    torch.manual_seed(A)
+    n = 4096
+    mu, z = torch.randn(n, A, device=DEV), torch.randn(n, A, device=DEV)
+    param = (torch.rand(A, device=DEV) + 0.3) if std_type == "scalar" else torch.randn(A, device=DEV) * 0.3
+    sigma = param if std_type == "scalar" else torch.exp(param)
+    act, lp, sig = torch.empty(n, A, device=DEV), torch.empty(n, device=DEV), torch.empty(n, A, device=DEV)
+    nat.check(nat.lib().rslrl_gaussian_act(mu.data_ptr(), param.data_ptr(), 0 if std_type == "scalar" else 1, z.data_ptr(),
+                                           act.data_ptr(), lp.data_ptr(), sig.data_ptr(), n, A, nat.stream_ptr()))
+    sg = sigma.expand(n, A).contiguous()
+    if std_type == "scalar":
+        assert torch.equal(act, z * sg + mu)       # bit-exact: mul then add, like Normal.sample()
+        assert torch.equal(sig, sg)
+    else:
+        assert rel_err(act.cpu().numpy(), (z * sg + mu).cpu().numpy()) < 1e-6
+    lp_o = O.gaussian_log_prob(mu.cpu().numpy(), sig.cpu().numpy(), act.cpu().numpy())
+    assert rel_err(lp.cpu().numpy(), lp_o) < 2e-6
+
+
+def _run_loss(mu, std_param, std_type, value, actions, old_logp, adv, ret, old_v, old_mu, old_sigma, clipped,
+              mb_orig=None, per_mb_norm=False):
+    nat = _nat()
+    rows, A = mu.shape
+    mb_orig = rows if mb_orig is None else mb_orig
+    t = lambda a: cu(np.asarray(a, dtype=np.float32).reshape(a.shape))
+    d = dict(mu=t(mu), sp=t(std_param), value=t(value.reshape(-1)), actions=t(actions), old_logp=t(old_logp.reshape(-1)),
+             adv=t(adv.reshape(-1)), ret=t(ret.reshape(-1)), old_v=t(old_v.reshape(-1)), old_mu=t(old_mu), old_sigma=t(old_sigma))
+    dmu, dv = torch.empty(rows, A, device=DEV), torch.empty(rows, device=DEV)
+    dstd, kl = torch.zeros(A, device=DEV), torch.zeros(1, device=DEV)
+    sums = torch.zeros(3, dtype=torch.float64, device=DEV)
+    ws = torch.zeros(int(nat.lib().rslrl_loss_workspace_bytes()), dtype=torch.uint8, device=DEV)
+    stats = None
+    if per_mb_norm:
+        stats = torch.zeros(2, dtype=torch.float64, device=DEV)
+        sws = torch.zeros(64, dtype=torch.uint8, device=DEV)
+        nat.check(nat.lib().rslrl_sum_sumsq(d["adv"].data_ptr(), mb_orig, stats.data_ptr(), sws.data_ptr(), nat.stream_ptr()))
+    for _ in range(2):  # twice: the workspace must clean itself up
+        dstd.zero_(); sums.zero_()
+        nat.check(nat.lib().rslrl_ppo_loss_fwd_bwd(
+            d["mu"].data_ptr(), d["sp"].data_ptr(), std_type, d["value"].data_ptr(), d["actions"].data_ptr(),
+            d["old_logp"].data_ptr(), d["adv"].data_ptr(), d["ret"].data_ptr(), d["old_v"].data_ptr(), d["old_mu"].data_ptr(),
+            d["old_sigma"].data_ptr(), nat.ptr(stats), dmu.data_ptr(), dv.data_ptr(), dstd.data_ptr(), kl.data_ptr(),
+            sums.data_ptr(), ws.data_ptr(), rows, mb_orig, A, 0.2, 1.0, 0.01, int(clipped), nat.stream_ptr()))
+    torch.cuda.synchronize()
+    return dmu.cpu().numpy(), dv.cpu().numpy(), dstd.cpu().numpy(), float(kl), sums.cpu().numpy()
+
+
+@pytest.mark.parametrize("tag", ["clipped", "unclipped"])
+def test_ppo_loss_against_reference_autograd(tag):
+    g = load("loss_terms")
+    f = lambda k: g[f"{tag}.{k}"]
+    sigma = f("sigma")
+    dmu, dv, dstd, kl, sums = _run_loss(f("mu"), sigma[0], 0, f("value"), f("actions"), f("old_logp"), f("advantages"),
+                                        f("returns"), f("old_values"), f("old_mu"), f("old_sigma"), tag == "clipped")
+    assert rel_err(dmu, f("dmu")) < 1e-5
+    assert rel_err(dv, f("dvalue").reshape(-1)) < 1e-5
+    assert rel_err(dstd, f("dsigma").sum(0)) < 1e-5
+    assert abs(kl - float(f("kl"))) < 1e-5 * abs(float(f("kl")))
+    assert abs(sums[0] - float(f("surrogate"))) < 1e-5 * max(1.0, abs(float(f("surrogate"))))
+    assert abs(sums[1] - float(f("value_loss"))) < 1e-5 * abs(float(f("value_loss")))
+    assert abs(sums[2] - float(f("entropy"))) < 1e-5 * abs(float(f("entropy")))
+
+
+@pytest.mark.parametrize("A,std_type,rows,aug", [(12, 0, 24576, 1), (12, 1, 5000, 1), (7, 0, 999, 1), (12, 0, 4096, 2)])
+def test_ppo_loss_against_oracle(A, std_type, rows, aug):
+    rng = np.random.default_rng(rows + A)
+    mb = rows
+    R = rows * aug
+    f = lambda *s: rng.standard_normal(s).astype(np.float32)
+    mu, actions = f(R, A), f(R, A)
+    param = (rng.random(A).astype(np.float32) + 0.5) if std_type == 0 else (0.2 * f(A))
+    sigma_vec = param if std_type == 0 else np.exp(param)
+    sigma = np.broadcast_to(sigma_vec, (R, A)).copy()
+    value, old_v, ret, adv = f(R), f(mb), f(mb), f(mb)
+    old_mu, old_sigma = mu[:mb] + 0.1 * f(mb, A), np.abs(f(mb, A)) + 0.5
+    old_logp = O.gaussian_log_prob(mu[:mb], sigma[:mb], actions[:mb]) + 0.3 * f(mb)
+    rep = lambda x: np.concatenate([x] * aug)
+    o = O.ppo_loss_fwd_bwd(mu, sigma, value, actions, rep(old_logp), rep(adv), rep(ret), rep(old_v), 0.2, 1.0, 0.01, True,
+                           n_entropy=mb)
+    dmu, dv, dstd, kl, sums = _run_loss(mu, param, std_type, value, actions, old_logp, adv, ret, old_v, old_mu, old_sigma,
+                                        True, mb_orig=mb)
+    ds = o["dsigma"].sum(0, dtype=np.float64)
+    if std_type == 1:
+        ds = (o["dsigma"] * sigma).sum(0, dtype=np.float64)
+    assert rel_err(dmu, o["dmu"]) < 1e-5 and rel_err(dv, o["dvalue"].reshape(-1)) < 1e-5
+    assert rel_err(dstd, ds) < 1e-4
+    assert abs(kl - O.kl_mean(mu[:mb], sigma[:mb], old_mu, old_sigma)) < 1e-5 * abs(kl)
+    assert abs(sums[0] - o["surrogate"]) < 1e-5 * max(1, abs(o["surrogate"]))
+    assert abs(sums[1] - o["value_loss"]) < 1e-5 * abs(o["value_loss"])
+    assert abs(sums[2] - o["entropy"]) < 1e-5 * abs(o["entropy"])
+
+
+def test_ppo_loss_per_minibatch_advantage_normalisation():
+    rng = np.random.default_rng(11)
+    mb, A = 3000, 12
+    f = lambda *s: rng.standard_normal(s).astype(np.float32)
+    mu, actions, value, old_v, ret, adv = f(mb, A), f(mb, A), f(mb), f(mb), f(mb), 3 * f(mb) + 1
+    sig = np.ones(A, np.float32)
+    sigma = np.broadcast_to(sig, (mb, A)).copy()
+    old_logp = O.gaussian_log_prob(mu, sigma, actions) + 0.1 * f(mb)
+    a64 = adv.astype(np.float64)
+    adv_n = ((adv - np.float32(a64.mean())) / (np.float32(a64.std(ddof=1)) + np.float32(1e-8))).astype(np.float32)
+    o = O.ppo_loss_fwd_bwd(mu, sigma, value, actions, old_logp, adv_n, ret, old_v, 0.2, 1.0, 0.01, True)
+    dmu, dv, dstd, kl, sums = _run_loss(mu, sig, 0, value, actions, old_logp, adv, ret, old_v, mu, sigma, True,
+                                        per_mb_norm=True)
+    assert rel_err(dmu, o["dmu"]) < 1e-5 and abs(sums[0] - o["surrogate"]) < 1e-5 * max(1, abs(o["surrogate"]))
+
+
+# --------------------------------------------------------------------------------------- optimiser
+@pytest.mark.parametrize("world,adaptive", [(1, True), (2, True), (1, False)])
+def test_clip_adam_kl_lr_against_oracle(world, adaptive):
+    from collections import OrderedDict
+    from rsl_rl_b200.algorithms.flat_params import FlatParamGroup, FusedAdam
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(48, 64), torch.nn.ELU(), torch.nn.Linear(64, 7)).to(DEV)
+    names = [k for k, _ in net.named_parameters()]
+    params = OrderedDict((k, v.detach().cpu().numpy().copy()) for k, v in net.named_parameters())
+    group = FlatParamGroup(net.parameters(), DEV)
+    opt = FusedAdam(group, lr=1e-3)
+    adam = O.adam_init(params)
+    lr = 1e-3
+    rng = np.random.default_rng(1)
+    kls = [0.05, 0.001, 0.03, 0.011, 0.0, 0.004, 0.1, 0.0049]
+    for step, kl in enumerate(kls):
+        grads = OrderedDict((k, (rng.standard_normal(v.shape) * (3.0 if step % 2 else 0.01)).astype(np.float32))
+                            for k, v in params.items())
+        for p, k in zip(net.parameters(), names):
+            p.grad.copy_(cu(grads[k]) * world)                  # the buffer holds the SUM over ranks
+        group.kl_slot.fill_(np.float32(kl) * world)
+        opt.fused_step(world_size=world, max_grad_norm=1.0, adaptive=adaptive, desired_kl=0.01,
+                       round_lr_fp32=world > 1)
+        if adaptive:
+            lr = O.adaptive_lr(lr, kl, 0.01)
+            if world > 1:
+                lr = float(np.float32(lr))
+        total = O.clip_grad_norm(grads, 1.0)
+        O.adam_step(params, grads, adam, lr)
+        info = opt.dev_state.read()
+        assert abs(info["lr"] - lr) < 1e-18 + 1e-12 * lr, (step, info["lr"], lr)
+        assert abs(info["total_norm"] - total) < 1e-5 * total
+        assert info["step"] == step + 1
+        assert float(group.grads.abs().max()) == 0.0          # cleared for the next backward
+        flat = np.concatenate([params[k].reshape(-1) for k in names])
+        mine = np.concatenate([p.detach().cpu().numpy().reshape(-1) for p in net.parameters()])
+        assert rel_err(mine, flat) < 1e-6, step
+
+
+# ------------------------------------------------------------------------------------ trajectories
+def test_trajectory_kernels_bit_exact_vs_reference():
+    from rsl_rl_b200.utils import TrajectoryIndex, split_and_pad_trajectories, unpad_trajectories
+    g = load("trajectory_cases")
+    for n in ("small", "none", "all", "c4like"):
+        x, dones = cu(g[n + ".x"]), cu(g[n + ".dones"])
+        padded, masks = split_and_pad_trajectories(x, dones)
+        assert np.array_equal(masks.cpu().numpy(), g[n + ".masks"]), n
+        assert np.array_equal(padded.cpu().numpy(), g[n + ".padded"]), n
+        assert np.array_equal(unpad_trajectories(padded, masks).cpu().numpy(), g[n + ".unpadded"]), n
+        index = TrajectoryIndex(dones)
+        n_traj = index.n_traj
+        assert n_traj == g[n + ".masks"].shape[1]
+        hid = index.hidden_at_starts(cu(g[n + ".saved_hidden"]), 0, n_traj)
+        assert np.array_equal(hid.cpu().numpy(), g[n + ".hidden_at_starts"]), n
+        T, N = dones.shape[:2]
+        # minibatch-style slices: env columns [e0,e1) <-> trajectories [off[e0], off[e1])
+        offs = index.offsets_host()
+        e0, e1 = N // 4, N // 2 if N >= 4 else N
+        if e1 > e0:
+            sub = index.split_and_pad(x, offs[e0], offs[e1])
+            assert np.array_equal(sub.cpu().numpy(), g[n + ".padded"][:, offs[e0]:offs[e1]]), n
+            un = index.unpad(sub, e0, e1, offs[e0])
+            assert np.array_equal(un.cpu().numpy(), g[n + ".x"][:, e0:e1]), n
+
+
+def test_trajectory_index_at_c4_size_properties():
+    from rsl_rl_b200.utils import TrajectoryIndex
+    torch.manual_seed(4)
+    T, N = 24, 4096
+    dones = (torch.rand(T, N, 1, device=DEV) < 0.02).to(torch.uint8)
+    index = TrajectoryIndex(dones)
+    n_traj = index.n_traj
+    assert n_traj == N + int(dones[:-1].sum())
+    masks = index.masks(0, n_traj)
+    assert int(masks.sum()) == T * N                                 # every (t, env) appears exactly once
+    x = torch.randn(T, N, 48, device=DEV)
+    padded = index.split_and_pad(x, 0, n_traj)
+    assert torch.equal(index.unpad(padded, 0, N, 0), x)              # round trip
+    assert float(padded[~masks].abs().max()) == 0.0
+    pad_o, mask_o = O.split_and_pad_trajectories(x[:, :64].cpu().numpy(), dones[:, :64].cpu().numpy())
+    k = mask_o.shape[1]
+    assert np.array_equal(padded[:, :k].cpu().numpy(), pad_o) and np.array_equal(masks[:, :k].cpu().numpy(), mask_o)

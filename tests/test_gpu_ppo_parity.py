@@ -1,0 +1,181 @@
+"""GPU: whole learn() iterations of the CUDA path against (a) the golden traces recorded from the
+unmodified reference and (b) the numpy oracle on seeded synthetic rollouts at benchmark sizes."""
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ppo_oracle as O
+from tests.golden_util import cfg_of, flat, load, meta_of, params_from, rel_err, stream_of
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _train_cfg(meta, **alg_extra):
+    alg = dict(meta["alg"], class_name="PPO", **alg_extra)
+    return dict(num_steps_per_env=meta["num_steps"], save_interval=10 ** 9,
+                obs_groups={k: list(v) for k, v in meta["obs_groups"].items()},
+                policy=dict(class_name="ActorCritic", actor_hidden_dims=list(meta["hidden"]),
+                            critic_hidden_dims=list(meta["hidden"]), activation=meta["activation"],
+                            init_noise_std=1.0, noise_std_type=meta["noise_std_type"]),
+                algorithm=alg)
+
+
+def _make_runner(meta, obs_streams, rewards, dones, time_outs, init_params, **alg_extra):
+    from rsl_rl_b200.env import ReplayVecEnv
+    from rsl_rl_b200.runners import OnPolicyRunner
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    env = ReplayVecEnv({k: t(v) for k, v in obs_streams.items()}, t(rewards), t(dones), t(time_outs),
+                       meta["num_actions"], device=DEV)
+    runner = OnPolicyRunner(env, _train_cfg(meta, **alg_extra), log_dir=None, device=DEV)
+    runner.alg.policy.load_state_dict({k: t(v).to(DEV) for k, v in init_params.items()})
+    assert runner.alg.fused, runner.alg._engine_reason
+    return runner, env
+
+
+@pytest.mark.parametrize("name", ["ppo_mlp_small", "ppo_mlp_groups"])
+def test_learn_iterations_match_reference_golden(name):
+    g = load(name)
+    meta = meta_of(g)
+    names = meta["param_names"]
+    T, iters = meta["num_steps"], meta["iterations"]
+    # the env replays the concatenated recorded stream of all iterations
+    obs = {k: np.concatenate([g[f"it{i}.stream.obs.{k}"][:T + (i == iters - 1)] for i in range(iters)])
+           for k in meta["group_dims"]}
+    cat = lambda key: np.concatenate([g[f"it{i}.stream.{key}"] for i in range(iters)])
+    init = OrderedDict((k, g[f"init.{k}"]) for k in names)
+    runner, env = _make_runner(meta, obs, cat("rewards"), cat("dones"), cat("time_outs"), init, use_cuda_graph=False)
+    alg = runner.alg
+    for it in range(iters):
+        p = f"it{it}."
+        zq = [torch.from_numpy(z).to(DEV) for z in g[p + "z_rollout"]]
+        alg.policy._noise_fn = lambda like, q=zq: q.pop(0)
+        perm = torch.from_numpy(g[p + "perm"]).to(DEV)
+        alg.storage._randperm = lambda n, perm=perm: perm
+        raw = []
+        alg._mb_hook = lambda a: raw.append(a._group.grads.detach().clone())
+        st = alg.storage
+        snap = {}
+        orig_update = alg.update
+
+        def update_and_snapshot():
+            for k in ("actions", "values", "actions_log_prob", "mu", "sigma", "rewards", "dones", "returns", "advantages"):
+                snap[k] = getattr(st, k).cpu().numpy().copy()
+            for k in meta["group_dims"]:
+                snap["obs." + k] = st.observations[k].cpu().numpy().copy()
+            return orig_update()
+
+        alg.update = update_and_snapshot
+        runner.learn(1)
+        alg.update = orig_update
+        # ---- rollout products
+        for k in meta["group_dims"]:
+            assert np.array_equal(snap["obs." + k], g[p + "storage.obs." + k])
+        assert np.array_equal(snap["dones"], g[p + "storage.dones"])
+        assert rel_err(snap["mu"], g[p + "storage.mu"]) < 1e-5
+        assert rel_err(snap["actions"], g[p + "storage.actions"]) < 1e-5
+        assert rel_err(snap["values"], g[p + "storage.values"]) < 1e-5
+        assert rel_err(snap["actions_log_prob"], g[p + "storage.actions_log_prob"]) < 1e-5
+        assert rel_err(snap["sigma"], g[p + "storage.sigma"]) < 1e-6
+        assert rel_err(snap["rewards"], g[p + "storage.rewards"]) < 1e-5
+        assert rel_err(snap["returns"], g[p + "storage.returns"]) < 1e-5
+        assert rel_err(snap["advantages"], g[p + "storage.advantages"]) < 1e-5
+        # ---- per-minibatch gradients (padded flat layout -> reference order)
+        grp = alg._group
+        pick = torch.cat([torch.arange(o, o + q.numel()) for o, q in zip(grp.offsets, grp.params)]).to(DEV)
+        ref_raw = g[p + "mb.raw_grads"]
+        assert len(raw) == ref_raw.shape[0]
+        assert rel_err(raw[0][pick].cpu().numpy(), ref_raw[0]) < 1e-5
+        for i in range(len(raw)):
+            assert rel_err(raw[i][pick].cpu().numpy(), ref_raw[i]) < 5e-4, i
+        # ---- post-update parameters, Adam state, learning rate
+        mine = torch.cat([q.detach().reshape(-1) for q in alg.policy.parameters()]).cpu().numpy()
+        assert rel_err(mine, g[p + "mb.params_after"][-1]) < 1e-5
+        assert rel_err(grp.exp_avg[pick].cpu().numpy(), g[p + "adam.exp_avg"]) < 1e-4
+        assert rel_err(grp.exp_avg_sq[pick].cpu().numpy(), g[p + "adam.exp_avg_sq"]) < 1e-4
+        assert alg.last_update_info["step"] == int(g[p + "adam.step"])
+        assert abs(alg.learning_rate - float(g[p + "learning_rate"])) < 1e-15
+        sd = alg.optimizer.state_dict()
+        assert float(sd["state"][0]["step"]) == float(g[p + "adam.step"]) and sd["param_groups"][0]["lr"] == alg.learning_rate
+
+
+def _synthetic_problem(N, T, O_dim, A, hidden, iters, seed):
+    rng = np.random.default_rng(seed)
+    f = lambda *s: rng.standard_normal(s).astype(np.float32)
+    obs = f(iters * T + 1, N, O_dim)
+    rewards = f(iters * T, N)
+    dones = (rng.random((iters * T, N)) < 0.02).astype(np.int64)
+    time_outs = (rng.random((iters * T, N)) < 0.5) & (dones > 0)
+    z = f(iters, T, N, A)
+    B = N * T
+    perms = np.stack([rng.permutation(B) for _ in range(iters)]).astype(np.int64)
+    meta = dict(num_envs=N, num_steps=T, num_actions=A, hidden=hidden, activation="elu", noise_std_type="scalar",
+                obs_groups={"policy": ["policy"], "critic": ["policy"]}, group_dims={"policy": O_dim},
+                alg=dict(learning_rate=1e-3, num_learning_epochs=5, num_mini_batches=4, schedule="adaptive",
+                         value_loss_coef=1.0, clip_param=0.2, use_clipped_value_loss=True, desired_kl=0.01,
+                         entropy_coef=0.01, gamma=0.99, lam=0.95, max_grad_norm=1.0,
+                         normalize_advantage_per_mini_batch=False))
+    return meta, obs, rewards, dones, time_outs, z, perms
+
+
+def _init_params_like_torch(meta, seed):
+    """Random-init weights of the named architecture (torch default init), as numpy."""
+    from rsl_rl_b200.modules import ActorCritic
+    from rsl_rl_b200.utils import TensorDictLite
+    torch.manual_seed(seed)
+    N = 2
+    obs = TensorDictLite({k: torch.zeros(N, d) for k, d in meta["group_dims"].items()}, batch_size=[N])
+    pol = ActorCritic(obs, meta["obs_groups"], meta["num_actions"], actor_hidden_dims=meta["hidden"],
+                      critic_hidden_dims=meta["hidden"], activation=meta["activation"])
+    return OrderedDict((k, v.detach().numpy().copy()) for k, v in pol.named_parameters())
+
+
+def _run_both(meta, obs, rewards, dones, time_outs, z, perms, iters, **alg_extra):
+    init = _init_params_like_torch(meta, 0)
+    T = meta["num_steps"]
+    runner, env = _make_runner(meta, {"policy": obs}, rewards, dones, time_outs, init, **alg_extra)
+    alg = runner.alg
+    params = OrderedDict((k, v.copy()) for k, v in init.items())
+    adam, lr, cfg = O.adam_init(params), meta["alg"]["learning_rate"], cfg_of(meta)
+    out = []
+    for it in range(iters):
+        zq = [torch.from_numpy(zz).to(DEV) for zz in z[it]]
+        alg.policy._noise_fn = lambda like, q=zq: q.pop(0)
+        perm = torch.from_numpy(perms[it]).to(DEV)
+        alg.storage._randperm = lambda n, perm=perm: perm
+        runner.learn(1)
+        sl = slice(it * T, (it + 1) * T)
+        stream = dict(obs_actor=obs[it * T:(it + 1) * T + 1], obs_critic=obs[it * T:(it + 1) * T + 1],
+                      rewards=rewards[sl], dones=dones[sl], time_outs=time_outs[sl])
+        st, last_values, loss_dict, lr, trace = O.learn_iteration(params, adam, lr, stream, z[it], perms[it], cfg)
+        mine = torch.cat([q.detach().reshape(-1) for q in alg.policy.parameters()]).cpu().numpy()
+        out.append(dict(mine=mine, ref=flat(params), lr_mine=alg.learning_rate, lr_ref=lr, st=st, alg=alg))
+    return out
+
+
+def test_three_iterations_with_cuda_graph_replay_vs_oracle():
+    """Iteration 0 runs eagerly, iteration 1 captures the update() graph, iteration 2 replays it."""
+    meta, obs, rewards, dones, time_outs, z, perms = _synthetic_problem(256, 8, 20, 6, [64, 32], 3, seed=5)
+    res = _run_both(meta, obs, rewards, dones, time_outs, z, perms, 3, use_cuda_graph=True)
+    for it, r in enumerate(res):
+        assert abs(r["lr_mine"] - r["lr_ref"]) < 1e-15, it
+        assert rel_err(r["mine"], r["ref"]) < 2e-5, it
+    assert res[-1]["alg"]._graph is not None
+
+
+def test_c1_shape_full_iteration_vs_oracle():
+    """BASELINE config C1/C2 per GPU: 4096 envs x 24 steps, obs 48, act 12, MLP [512,256,128], 5x4 minibatches."""
+    meta, obs, rewards, dones, time_outs, z, perms = _synthetic_problem(4096, 24, 48, 12, [512, 256, 128], 1, seed=9)
+    r = _run_both(meta, obs, rewards, dones, time_outs, z, perms, 1, use_cuda_graph=False)[0]
+    st, alg = r["st"], r["alg"]
+    s = alg.storage
+    assert rel_err(s.mu.cpu().numpy(), st["mu"]) < 1e-5
+    assert rel_err(s.values.cpu().numpy(), st["values"]) < 1e-5
+    assert rel_err(s.actions_log_prob.cpu().numpy(), st["actions_log_prob"]) < 1e-5
+    assert np.array_equal(s.dones.cpu().numpy(), st["dones"])
+    assert rel_err(s.returns.cpu().numpy(), st["returns"]) < 1e-5
+    assert rel_err(s.advantages.cpu().numpy(), st["advantages"]) < 1e-5
+    assert abs(r["lr_mine"] - r["lr_ref"]) < 1e-15
+    assert rel_err(r["mine"], r["ref"]) < 1e-5

@@ -1,0 +1,107 @@
+"""CPU: host-side logic that needs no kernels -- obs container, config resolution, flat parameter
+groups and optimiser state compatibility."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from rsl_rl_b200.algorithms.flat_params import FlatParamGroup, FusedAdam
+from rsl_rl_b200.utils import TensorDictLite, resolve_nn_activation, resolve_obs_groups, string_to_callable
+
+
+def test_tensordict_lite_surface():
+    td = TensorDictLite({"a": torch.arange(24.).view(4, 3, 2), "b": torch.arange(12.).view(4, 3)}, batch_size=[4, 3])
+    assert td[1]["a"].shape == (3, 2) and td[1].batch_size == torch.Size([3])
+    assert td[:, 1:3].batch_size == torch.Size([4, 2])
+    assert td[:, torch.tensor(1):torch.tensor(3)]["b"].shape == (4, 2)
+    flat = td.flatten(0, 1)
+    assert flat.batch_size == torch.Size([12]) and flat["a"].shape == (12, 2)
+    idx = torch.tensor([5, 0, 7])
+    assert torch.equal(flat[idx]["b"], td["b"].flatten()[idx])
+    assert flat[idx].batch_size == torch.Size([3])
+    assert "a" in td and set(td.keys()) == {"a", "b"}
+    clone = td.clone()
+    clone["a"].zero_()
+    assert td["a"].sum() > 0
+    td[0].copy_(TensorDictLite({"a": torch.ones(3, 2), "b": torch.ones(3)}, batch_size=[3]))
+    assert td["a"][0].eq(1).all()
+
+
+def test_resolve_obs_groups_defaults_and_errors():
+    obs = TensorDictLite({"policy": torch.zeros(2, 3), "critic": torch.zeros(2, 4)}, batch_size=[2])
+    with pytest.warns(UserWarning):
+        out = resolve_obs_groups(obs, {"policy": ["policy"]}, ["critic"])
+    assert out["critic"] == ["critic"]
+    obs2 = TensorDictLite({"policy": torch.zeros(2, 3)}, batch_size=[2])
+    with pytest.warns(UserWarning):
+        out = resolve_obs_groups(obs2, {"policy": ["policy"]}, ["critic", "rnd_state"])
+    assert out["critic"] == ["policy"] and out["rnd_state"] == ["policy"]
+    with pytest.raises(ValueError):
+        resolve_obs_groups(obs2, {"policy": ["missing"]}, [])
+    with pytest.raises(ValueError):
+        resolve_obs_groups(obs2, {"policy": []}, [])
+    with pytest.raises(ValueError):
+        resolve_obs_groups(TensorDictLite({"x": torch.zeros(2, 1)}, batch_size=[2]), {}, [])
+
+
+def test_activation_resolution():
+    assert isinstance(resolve_nn_activation("ELU"), nn.ELU)
+    with pytest.raises(ValueError):
+        resolve_nn_activation("nope")
+    with pytest.raises(NotImplementedError):
+        resolve_nn_activation("gelu")
+    assert string_to_callable("math:sqrt")(4.0) == 2.0
+    with pytest.raises(ValueError):
+        string_to_callable("math:pi")
+
+
+def _toy():
+    torch.manual_seed(0)
+    return nn.Sequential(nn.Linear(5, 7), nn.ELU(), nn.Linear(7, 1))
+
+
+def test_flat_param_group_views_and_rebinding():
+    net = _toy()
+    before = [p.detach().clone() for p in net.parameters()]
+    g = FlatParamGroup(net.parameters(), "cpu")
+    assert g.numel % 4 == 0 and all(o % 4 == 0 for o in g.offsets)
+    for p, b in zip(net.parameters(), before):
+        assert torch.equal(p, b)
+    assert g.is_bound()
+    g.values.zero_()
+    assert all(float(p.abs().sum()) == 0 for p in net.parameters())      # params are views
+    g.grads.fill_(2.0)
+    assert all(float(p.grad.mean()) == 2.0 for p in net.parameters())    # grads are views
+    # load_state_dict copies in place -> stays bound; .to()/zero_grad(set_to_none) unbinds -> rebind works
+    net.load_state_dict({k: torch.ones_like(v) for k, v in net.state_dict().items()})
+    assert g.is_bound() and float(g.values[:35].min()) == 1.0
+    net.zero_grad(set_to_none=True)
+    assert not g.is_bound()
+    g.ensure_bound()
+    assert g.is_bound()
+
+
+def test_fused_adam_is_a_torch_adam_with_compatible_state_dict():
+    net = _toy()
+    g = FlatParamGroup(net.parameters(), "cpu")
+    opt = FusedAdam(g, lr=1e-3)
+    assert isinstance(opt, torch.optim.Adam)
+    sd = opt.state_dict()
+    assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"}
+    # a stock optimiser's checkpoint loads into the fused one and lands in the flat moment buffers
+    ref_net = _toy()
+    ref = torch.optim.Adam(ref_net.parameters(), lr=5e-4)
+    for _ in range(3):
+        ref.zero_grad()
+        ref_net(torch.randn(8, 5)).pow(2).mean().backward()
+        ref.step()
+    opt.load_state_dict(ref.state_dict())
+    assert opt._host_step == 3 and opt.param_groups[0]["lr"] == 5e-4
+    flat_m = torch.cat([ref.state[p]["exp_avg"].reshape(-1) for p in ref_net.parameters()])
+    mine = torch.cat([g.moment_views(i)[0].reshape(-1) for i in range(len(g.params))])
+    assert torch.equal(flat_m, mine)
+    # stock step() keeps working on the views
+    net.load_state_dict(ref_net.state_dict())
+    g.grads.normal_()
+    opt.step()
+    assert g.is_bound()
