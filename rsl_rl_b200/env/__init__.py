@@ -1,5 +1,5 @@
 """Environment definitions (mirror of `rsl_rl.env`)."""
-from .synthetic import ReplayVecEnv, SynthVecEnv
+from .synthetic import PinnedHostEnv, ReplayVecEnv, SynthVecEnv
 from .vec_env import VecEnv
 
-__all__ = ["VecEnv", "SynthVecEnv", "ReplayVecEnv"]
+__all__ = ["VecEnv", "SynthVecEnv", "ReplayVecEnv", "PinnedHostEnv"]

@@ -82,3 +82,44 @@ class ReplayVecEnv(VecEnv):
         extras = {} if self._to is None else {"time_outs": self._to[self.t]}
         self.t += 1
         return self._cur(), r, d, extras
+
+
+class PinnedHostEnv(VecEnv):
+    """Host-resident environment for end-to-end timing: `pool` pre-generated steps of observations /
+    rewards / dones / time-outs live in PINNED host memory and are cycled; every step() hands the runner
+    host tensors (so the runner's `.to(device)` is a real host->device copy) and receives the actions
+    on the host (a real device->host copy).  No host-side random number generation inside the loop."""
+
+    def __init__(self, num_envs: int, group_dims=None, num_actions: int = 12, pool: int = 32, seed: int = 0,
+                 p_done: float = 0.02, p_timeout: float = 0.5):
+        self.num_envs, self.num_actions = num_envs, num_actions
+        self.group_dims = dict(group_dims or {"policy": 48})
+        self.device = "cpu"
+        self.max_episode_length = 1000
+        self.episode_length_buf = torch.zeros(num_envs, dtype=torch.long)
+        self.cfg = {}
+        self.step_dt = 0.02
+        self.unwrapped = self
+        g = torch.Generator().manual_seed(seed)
+        pin = (lambda t: t.pin_memory()) if torch.cuda.is_available() else (lambda t: t)
+        self._obs = {k: pin(torch.randn(pool, num_envs, d, generator=g)) for k, d in self.group_dims.items()}
+        self._rew = pin(torch.randn(pool, num_envs, generator=g))
+        dones = torch.rand(pool, num_envs, generator=g) < p_done
+        self._done = pin(dones.long())
+        self._to = pin((torch.rand(pool, num_envs, generator=g) < p_timeout) & dones)
+        self.pool, self.t = pool, 0
+        self.h2d_bytes_per_step = (sum(self.group_dims.values()) * 4 + 4 + 8 + 1) * num_envs
+        self.d2h_bytes_per_step = num_actions * 4 * num_envs
+
+    def _cur(self):
+        i = self.t % self.pool
+        return TensorDict({k: v[i] for k, v in self._obs.items()}, batch_size=[self.num_envs], device="cpu")
+
+    def get_observations(self):
+        return self._cur()
+
+    def step(self, actions):
+        i = self.t % self.pool
+        r, d, to = self._rew[i], self._done[i], self._to[i]
+        self.t += 1
+        return self._cur(), r, d, {"time_outs": to}

@@ -132,11 +132,14 @@ def _init_params_like_torch(meta, seed):
     return OrderedDict((k, v.detach().numpy().copy()) for k, v in pol.named_parameters())
 
 
-def _run_both(meta, obs, rewards, dones, time_outs, z, perms, iters, **alg_extra):
+def _run_both(meta, obs, rewards, dones, time_outs, z, perms, iters, capture_grads=False, **alg_extra):
     init = _init_params_like_torch(meta, 0)
     T = meta["num_steps"]
     runner, env = _make_runner(meta, {"policy": obs}, rewards, dones, time_outs, init, **alg_extra)
     alg = runner.alg
+    raw = []
+    if capture_grads:
+        alg._mb_hook = lambda a: raw.append(a._group.grads.detach().clone())
     params = OrderedDict((k, v.copy()) for k, v in init.items())
     adam, lr, cfg = O.adam_init(params), meta["alg"]["learning_rate"], cfg_of(meta)
     out = []
@@ -151,7 +154,8 @@ def _run_both(meta, obs, rewards, dones, time_outs, z, perms, iters, **alg_extra
                       rewards=rewards[sl], dones=dones[sl], time_outs=time_outs[sl])
         st, last_values, loss_dict, lr, trace = O.learn_iteration(params, adam, lr, stream, z[it], perms[it], cfg)
         mine = torch.cat([q.detach().reshape(-1) for q in alg.policy.parameters()]).cpu().numpy()
-        out.append(dict(mine=mine, ref=flat(params), lr_mine=alg.learning_rate, lr_ref=lr, st=st, alg=alg))
+        out.append(dict(mine=mine, ref=flat(params), lr_mine=alg.learning_rate, lr_ref=lr, st=st, alg=alg, raw=raw,
+                        trace=trace))
     return out
 
 
@@ -166,9 +170,14 @@ def test_three_iterations_with_cuda_graph_replay_vs_oracle():
 
 
 def test_c1_shape_full_iteration_vs_oracle():
-    """BASELINE config C1/C2 per GPU: 4096 envs x 24 steps, obs 48, act 12, MLP [512,256,128], 5x4 minibatches."""
+    """BASELINE config C1/C2 per GPU: 4096 envs x 24 steps, obs 48, act 12, MLP [512,256,128], 5x4 minibatches.
+
+    Tolerances: everything up to and including the first minibatch's gradient is held to the fp32 class
+    (1e-5).  The parameters after all 20 Adam steps are held to 1e-4: Adam's m/sqrt(v) normalisation
+    amplifies summation-order noise of the 24576-row GEMMs -- the unmodified reference (torch CPU, MKL)
+    and the numpy oracle (OpenBLAS) themselves differ by 2.2e-5 on this config (parity notes)."""
     meta, obs, rewards, dones, time_outs, z, perms = _synthetic_problem(4096, 24, 48, 12, [512, 256, 128], 1, seed=9)
-    r = _run_both(meta, obs, rewards, dones, time_outs, z, perms, 1, use_cuda_graph=False)[0]
+    r = _run_both(meta, obs, rewards, dones, time_outs, z, perms, 1, capture_grads=True, use_cuda_graph=False)[0]
     st, alg = r["st"], r["alg"]
     s = alg.storage
     assert rel_err(s.mu.cpu().numpy(), st["mu"]) < 1e-5
@@ -177,5 +186,10 @@ def test_c1_shape_full_iteration_vs_oracle():
     assert np.array_equal(s.dones.cpu().numpy(), st["dones"])
     assert rel_err(s.returns.cpu().numpy(), st["returns"]) < 1e-5
     assert rel_err(s.advantages.cpu().numpy(), st["advantages"]) < 1e-5
+    grp = alg._group
+    pick = torch.cat([torch.arange(o, o + q.numel()) for o, q in zip(grp.offsets, grp.params)]).to(DEV)
+    assert len(r["raw"]) == 20
+    assert rel_err(r["raw"][0][pick].cpu().numpy(), r["trace"][0]["grads"]) < 1e-5
+    assert abs(alg.last_update_info["total_norm"] - r["trace"][-1]["total_norm"]) < 1e-3 * r["trace"][-1]["total_norm"]
     assert abs(r["lr_mine"] - r["lr_ref"]) < 1e-15
-    assert rel_err(r["mine"], r["ref"]) < 1e-5
+    assert rel_err(r["mine"], r["ref"]) < 1e-4

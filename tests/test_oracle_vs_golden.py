@@ -91,3 +91,29 @@ def test_trajectory_split_pad_unpad_bit_exact():
         assert np.array_equal(O.hidden_at_trajectory_starts(g[n + ".saved_hidden"], g[n + ".dones"]),
                               g[n + ".hidden_at_starts"]), n
         assert masks.sum() == g[n + ".x"].shape[0] * g[n + ".x"].shape[1]
+
+
+def test_torch_cpu_port_matches_numpy_oracle():
+    """oracle/torch_cpu_port.py (the CPU-baseline leg of bench.py) computes the same iteration as the
+    pinned numpy oracle."""
+    import torch
+    from collections import OrderedDict
+    from oracle import torch_cpu_port as P
+
+    params, stream, z, perm = P.random_problem(96, T=8, obs_dim=12, A=4, hidden=(32, 16), seed=3)
+    cfg = dict(P.DEFAULT_CFG, num_learning_epochs=2)
+    np_params = OrderedDict((k, v.numpy().copy()) for k, v in params.items())
+    np_stream = dict(obs_actor=stream["obs"].numpy(), obs_critic=stream["obs"].numpy(), rewards=stream["rewards"].numpy(),
+                     dones=stream["dones"].numpy(), time_outs=stream["time_outs"].numpy() > 0)
+    ocfg = dict(cfg, activation="elu", noise_std_type="scalar")
+    st, _, loss_o, lr_o, _ = O.learn_iteration(np_params, O.adam_init(np_params), 1e-3, np_stream, z.numpy(),
+                                               perm.numpy(), ocfg)
+    loss_t, lr_t, extra = P.learn_iteration(params, P.adam_init(params), 1e-3, stream, z, perm, cfg)
+    assert lr_t == lr_o
+    assert rel_err(extra["returns"].numpy(), st["returns"]) < 1e-6
+    assert rel_err(extra["advantages"].numpy(), st["advantages"]) < 1e-5
+    for k in ("value_function", "surrogate", "entropy"):
+        assert abs(loss_t[k] - loss_o[k]) < 1e-5 * max(1.0, abs(loss_o[k]))
+    a = np.concatenate([v.numpy().reshape(-1) for v in params.values()])
+    b = np.concatenate([v.reshape(-1) for v in np_params.values()])
+    assert rel_err(a, b) < 1e-5
