@@ -115,6 +115,8 @@ typedef struct {
   float* dx;       /* [M,K], row stride ldx : gradient w.r.t. previous layer's pre-activation */
   int M, N, K, ldy, ldh, ldx;
   int act;         /* activation of the PREVIOUS layer: dx = (dy W) * act'(.) evaluated from h */
+  float* db_prev;  /* [K] or NULL: += column sums of dx = bias gradient of the previous layer (fused into the
+                      epilogue that produces dx, so dx is not re-read for it) */
 } rslrl_linear_bwd_data_t;
 
 typedef struct {
@@ -143,8 +145,11 @@ int rslrl_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* probs_h
  *   adv_stats: NULL, or double[2] = {sum, sumsq} of `advantages` for the per-minibatch
  *              normalisation of ppo.py:221-223
  * outputs
- *   dmu [rows,A], dvalue [rows]   (dL/dmu, dL/dvalue of loss = surr + c_v*vloss - c_e*entropy)
+ *   dmu [rows,A] (row stride dmu_stride >= A), dvalue [rows] (element stride dvalue_stride >= 1):
+ *              dL/dmu, dL/dvalue of loss = surr + c_v*vloss - c_e*entropy; the strides let the caller keep
+ *              16-byte row pitches for TMA (e.g. dvalue_stride = 4)
  *   dstd [A]   += dL/dstd_param   (accumulated)
+ *   db_mu [A], db_value [1]: NULL or += column sums of dmu / dvalue (= bias gradients of the two output layers)
  *   kl_out [1]  = mean KL(old||new) over the first mb_orig rows as fp32 (ppo.py:262-269); may alias
  *                 the tail slot of the flat gradient buffer so that it rides the gradient all-reduce
  *   loss_sums  double[3] += {surrogate_mean, value_loss_mean, entropy_mean} of this minibatch
@@ -153,8 +158,9 @@ int64_t rslrl_loss_workspace_bytes(void);
 int rslrl_ppo_loss_fwd_bwd(const float* mu, const float* std_param, int std_type, const float* value,
                            const float* actions, const float* old_logp, const float* advantages,
                            const float* returns, const float* old_values, const float* old_mu,
-                           const float* old_sigma, const double* adv_stats, float* dmu, float* dvalue,
-                           float* dstd, float* kl_out, double* loss_sums, void* workspace, int64_t rows,
+                           const float* old_sigma, const double* adv_stats, float* dmu, int dmu_stride,
+                           float* dvalue, int dvalue_stride, float* dstd, float* db_mu, float* db_value,
+                           float* kl_out, double* loss_sums, void* workspace, int64_t rows,
                            int64_t mb_orig, int A, double clip_param, double value_loss_coef,
                            double entropy_coef, int use_clipped_value_loss, rslrl_stream_t stream);
 

@@ -64,7 +64,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
             print(out)
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
-    link = [nvcc, "-shared", "-o", LIBPATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcuda"]
+    link = [nvcc, "-shared", "-o", LIBPATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc link failed:\n{r.stdout}")

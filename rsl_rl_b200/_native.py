@@ -33,7 +33,7 @@ class LinearFwd(C.Structure):
 class LinearBwdData(C.Structure):
     _fields_ = [("dy", c_void_p), ("w", c_void_p), ("h", c_void_p), ("dx", c_void_p),
                 ("M", c_int), ("N", c_int), ("K", c_int), ("ldy", c_int), ("ldh", c_int), ("ldx", c_int),
-                ("act", c_int)]
+                ("act", c_int), ("db_prev", c_void_p)]
 
 
 class LinearBwdWeight(C.Structure):
@@ -89,7 +89,8 @@ _SIGNATURES["rslrl_ppo_loss_fwd_bwd"] = (c_int, [
     c_void_p, c_void_p, c_int, c_void_p,            # mu, std_param, std_type, value
     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,  # actions, old_logp, advantages, returns, old_values
     c_void_p, c_void_p, c_void_p,                   # old_mu, old_sigma, adv_stats
-    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,  # dmu, dvalue, dstd, kl_out, loss_sums, workspace
+    c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,  # dmu, dmu_stride, dvalue, dvalue_stride, dstd, db_mu, db_value
+    c_void_p, c_void_p, c_void_p,                   # kl_out, loss_sums, workspace
     c_i64, c_i64, c_int, c_double, c_double, c_double, c_int, c_void_p])
 
 _lib = None

@@ -73,8 +73,9 @@ class FeedForwardEngine:
         self.g_c = [torch.empty(R * wc, **f32) for _ in range(2)]
         self.mu = torch.empty(R, self.A, **f32)
         self.value = torch.empty(R, 1, **f32)
-        self.dmu = torch.empty(R, self.A, **f32)
-        self.dvalue = torch.empty(R, 1, **f32)
+        # gradient heads keep a 16-byte row pitch so that TMA can read them (dvalue: 1 used column of 4)
+        self.dmu = torch.zeros(R, (self.A + 3) // 4 * 4, **f32)[:, :self.A]
+        self.dvalue = torch.zeros(R, 4, **f32)[:, :1]
         self.loss_ws = torch.zeros(int(nat.lib().rslrl_loss_workspace_bytes()), dtype=torch.uint8, device=self.device)
         self.sum_ws = torch.zeros(64, dtype=torch.uint8, device=self.device)
         self.adv_stats = torch.zeros(2, dtype=torch.float64, device=self.device)
@@ -114,10 +115,11 @@ class FeedForwardEngine:
                     continue
                 lin = net.layers[l]
                 inp = x_in if l == 0 else hs[l - 1][:M]
-                wprobs.append((dy[ni], inp, lin.weight.grad, lin.bias.grad))
+                # bias gradients come from the kernel that produces dy (loss kernel / dgrad epilogue), not from wgrad
+                wprobs.append((dy[ni], inp, lin.weight.grad, None))
                 if l > 0:
                     dx = gbuf[k % 2][:M * net.dims[l]].view(M, net.dims[l])
-                    dprobs.append((dy[ni], lin.weight, inp, dx, net.acts[l - 1]))
+                    dprobs.append((dy[ni], lin.weight, inp, dx, net.acts[l - 1], net.layers[l - 1].bias.grad))
                     new_dy[ni] = dx
             linear_backward_weight(wprobs, self.prec)
             if dprobs:
@@ -140,7 +142,9 @@ class FeedForwardEngine:
         nat.check(L.rslrl_ppo_loss_fwd_bwd(
             mu.data_ptr(), self.std_param.data_ptr(), self.std_type, value.data_ptr(), actions.data_ptr(),
             old_logp.data_ptr(), adv.data_ptr(), returns.data_ptr(), old_values.data_ptr(), old_mu.data_ptr(),
-            old_sigma.data_ptr(), stats_ptr, self.dmu.data_ptr(), self.dvalue.data_ptr(),
-            self.std_param.grad.data_ptr(), nat.ptr(kl_out), nat.ptr(loss_sums), self.loss_ws.data_ptr(), rows,
+            old_sigma.data_ptr(), stats_ptr, self.dmu.data_ptr(), self.dmu.stride(0), self.dvalue.data_ptr(),
+            self.dvalue.stride(0), self.std_param.grad.data_ptr(), self.actor.layers[-1].bias.grad.data_ptr(),
+            self.critic.layers[-1].bias.grad.data_ptr(), nat.ptr(kl_out), nat.ptr(loss_sums),
+            self.loss_ws.data_ptr(), rows,
             mb_orig, self.A, hp["clip_param"], hp["value_loss_coef"], hp["entropy_coef"],
             int(hp["use_clipped_value_loss"]), nat.stream_ptr()))

@@ -26,7 +26,7 @@ struct GemmProblem {
   float* C;
   const float* bias;  // EPI_FWD
   const float* H;     // EPI_DGRAD
-  float* colsum;      // EPI_WGRAD (db)
+  float* colsum;      // EPI_WGRAD: db (row sums of A);  EPI_DGRAD: db_prev (column sums of C)
   int M, N, K, lda, ldb, ldc, ldh, act, splits, k_per_split;
 };
 
@@ -164,6 +164,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) sgemm_kernel(const GemmBatch 
   }
 
   // ---- epilogue
+  float dcol[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // EPI_DGRAD: per-thread column sums of its 8 rows
   const bool c_vec = (P.ldc & 3) == 0 && ((uintptr_t)P.C & 15) == 0;
   const bool h_vec = EPI == EPI_DGRAD && (P.ldh & 3) == 0 && ((uintptr_t)P.H & 15) == 0;
 #pragma unroll
@@ -195,6 +196,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) sgemm_kernel(const GemmBatch 
             for (int q = 0; q < nv; ++q) o[q] *= act_grad_from_output(P.act, __ldg(hp + q));
           }
         }
+        for (int q = 0; q < nv; ++q) dcol[jh * 4 + q] += o[q];
       }
       if (EPI == EPI_WGRAD) {
         if (c_vec && nv == 4) {
@@ -212,6 +214,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) sgemm_kernel(const GemmBatch 
     }
     if (EPI == EPI_WGRAD) {
       if (do_rowsum) atomicAdd(P.colsum + m, rowsum[i]);
+    }
+  }
+  if (EPI == EPI_DGRAD) {
+    if (P.colsum != nullptr) {
+      // reduce the 16 thread-rows (ty) that share a column inside the warp pair first: lanes l and l^16
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v = dcol[j] + __shfl_xor_sync(0xffffffffu, dcol[j], 16);
+        const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+        if ((threadIdx.x & 16) == 0 && n < P.N) atomicAdd(P.colsum + n, v);
+      }
     }
   }
 }
@@ -255,7 +268,7 @@ int simt_linear_backward_data(int n, const rslrl_linear_bwd_data_t* pr, cudaStre
   for (int i = 0; i < n; ++i) {
     GemmProblem& P = b.p[i];
     // dX[M,K] = sum_n dY[m,n] W[n,k]  ->  C[M, K] with reduction length N
-    P.A = pr[i].dy; P.B = pr[i].w; P.C = pr[i].dx; P.H = pr[i].h;
+    P.A = pr[i].dy; P.B = pr[i].w; P.C = pr[i].dx; P.H = pr[i].h; P.colsum = pr[i].db_prev;
     P.M = pr[i].M; P.N = pr[i].K; P.K = pr[i].N;
     P.lda = pr[i].ldy; P.ldb = pr[i].K; P.ldc = pr[i].ldx; P.ldh = pr[i].ldh; P.act = pr[i].act;
     P.splits = 1; P.k_per_split = pr[i].N;

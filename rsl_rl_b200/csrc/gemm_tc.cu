@@ -1,17 +1,531 @@
-// TF32 tensor-core GEMMs (tcgen05 + TMEM + TMA) -- placeholder until the kernels land.
+// TF32 tensor-core GEMMs for nn.Linear forward / data-gradient / weight-gradient on sm_100a:
+// tcgen05.mma (kind::tf32) with the accumulator in TMEM, operands staged in shared memory by TMA
+// (cp.async.bulk.tensor, 128-byte swizzle), mbarrier producer/consumer pipeline, warp-specialised CTA.
+//
+//   warp 0      TMA producer  (one elected lane issues the bulk tensor copies of a k-block)
+//   warp 1      MMA issuer    (allocates TMEM, one elected lane issues 4 x tcgen05.mma per k-block,
+//                              tcgen05.commit releases the smem stage / publishes the accumulator)
+//   warps 2..5  epilogue      (tcgen05.ld 32 lanes x 32 columns -> registers -> fused epilogue ->
+//                              smem transpose -> 128-byte coalesced global stores / vector atomics)
+//
+// One kernel covers the three products through the operand "major" bits of the instruction descriptor
+// and matching shared-memory descriptors, so no transposed copies of weights or activations exist:
+//   forward  Y  = act(X W^T + b)     A = X  [M,K]  K-major     B = W [N,K]  K-major
+//   dgrad    dX = (dY W) * act'(H)   A = dY [M,N]  K-major     B = W [N,K]  MN-major (N is the reduction)
+//   wgrad    dW += dY^T X            A = dY [M,N]  MN-major    B = X [M,K]  MN-major (M is the reduction, split-K)
+// K-major tiles use SWIZZLE_128B (rows of 32 tf32), MN-major tf32 tiles need the 32-byte-atom flavour
+// (UMMA layout SWIZZLE_128B_BASE32B <-> TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).
+// Out-of-range rows/columns (M, N or K tails, N = 12 or 1 heads) are zero-filled by TMA and masked in the
+// epilogue, so every shape of the MLP goes through the same tiles.  Operands whose row pitch is not a
+// multiple of 16 bytes cannot be described to TMA; those problems are reported back to the caller
+// (linear.cu runs them on the fp32 CUDA-core kernel, which is strictly more accurate).
+//
+// Inputs are fp32 in HBM; the tensor core consumes them as tf32.  The bias-gradient of a layer is the
+// column sum of the dY it receives, so it is accumulated by the kernel that PRODUCES that dY (the dgrad
+// epilogue here, the loss kernel for the output layers) instead of re-reading dY.
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+
 #include "common.cuh"
 
 namespace rslrl {
-int tc_linear_forward(int, const rslrl_linear_fwd_t*, cudaStream_t) {
-  set_error("rslrl_linear_forward: RSLRL_PREC_TF32 kernels are not built into this library yet");
-  return 3;
+
+constexpr int TC_BLOCK_M = 128;
+constexpr int TC_BLOCK_K = 32;  // tf32 elements = one 128-byte swizzle row
+constexpr int TC_UMMA_K = 8;    // tf32 MMA depth (32 bytes)
+constexpr int TC_THREADS = 192;
+constexpr int TC_MAX_STAGES = 6;
+constexpr int TC_SMEM_BUDGET = 200 * 1024;
+
+enum { TC_FWD = 0, TC_DGRAD = 1, TC_WGRAD = 2 };
+
+struct TcProblem {
+  CUtensorMap map_a, map_b;
+  float* C;
+  const float* bias;  // fwd
+  const float* H;     // dgrad: saved activation (same shape as C)
+  float* db_prev;     // dgrad: += column sums of C (bias gradient of the previous layer); may be null
+  int M, N, K;        // C is [M,N], reduction length K
+  int ldc, ldh, act;
+  int block_n, tiles_m, tiles_n, splits, kb_per_split, num_kb;
+};
+
+struct alignas(64) TcBatch {
+  TcProblem p[2];
+};
+
+// ---------------------------------------------------------------------------------------------- PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-int tc_linear_backward_data(int, const rslrl_linear_bwd_data_t*, cudaStream_t) {
-  set_error("rslrl_linear_backward_data: RSLRL_PREC_TF32 kernels are not built into this library yet");
-  return 3;
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-int tc_linear_backward_weight(int, const rslrl_linear_bwd_weight_t*, cudaStream_t) {
-  set_error("rslrl_linear_backward_weight: RSLRL_PREC_TF32 kernels are not built into this library yet");
-  return 3;
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
 }
+// Bounded wait: a broken pipeline traps (launch failure reported to the host) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("rslrl tc_gemm: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor layout, version 1)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)(layout_type & 7) << 61;
+  return d;
+}
+constexpr uint32_t kLayoutSw128 = 2;         // K-major operands
+constexpr uint32_t kLayoutSw128Base32 = 1;   // MN-major tf32 operands
+
+// UMMA instruction descriptor: tf32 x tf32 -> f32, M = 128
+__device__ __forceinline__ uint32_t make_idesc(int n, bool a_mn_major, bool b_mn_major) {
+  uint32_t d = 0;
+  d |= 1u << 4;                      // accumulator format F32
+  d |= 2u << 7;                      // A format TF32
+  d |= 2u << 10;                     // B format TF32
+  d |= (a_mn_major ? 1u : 0u) << 15;
+  d |= (b_mn_major ? 1u : 0u) << 16;
+  d |= (uint32_t)(n >> 3) << 17;
+  d |= (uint32_t)(TC_BLOCK_M >> 4) << 24;
+  return d;
+}
+
+#define TMEM_LD_32x32(taddr, v)                                                                                      \
+  asm volatile(                                                                                                      \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,"   \
+      "%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"                                                 \
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),  \
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),       \
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),      \
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                    \
+      : "r"(taddr))
+#define TMEM_LD_32x16(taddr, v)                                                                                      \
+  asm volatile(                                                                                                      \
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"       \
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),  \
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])                     \
+      : "r"(taddr))
+
+// ------------------------------------------------------------------------------------------- kernel
+template <int MODE>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcBatch batch) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const TcProblem& P = batch.p[blockIdx.y];
+  const int tiles = P.tiles_m * P.tiles_n;
+  if ((int)blockIdx.x >= tiles * P.splits) return;
+  const int split = blockIdx.x / tiles, rem = blockIdx.x - split * tiles;
+  const int tm = rem / P.tiles_n, tn = rem - tm * P.tiles_n;
+  const int m0 = tm * TC_BLOCK_M, n0 = tn * P.block_n;
+  const int kb_begin = split * P.kb_per_split;
+  const int kb_end = min(P.num_kb, kb_begin + P.kb_per_split);
+  const int num_kb = kb_end - kb_begin;
+
+  constexpr bool A_MN = MODE == TC_WGRAD;
+  constexpr bool B_MN = MODE != TC_FWD;
+  const int block_n = P.block_n;
+  const uint32_t a_bytes = TC_BLOCK_M * TC_BLOCK_K * 4, b_bytes = (uint32_t)block_n * TC_BLOCK_K * 4;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  int stages = TC_SMEM_BUDGET / stage_bytes;
+  stages = stages > TC_MAX_STAGES ? TC_MAX_STAGES : stages;
+
+  // carve shared memory (dynamic smem base is 1024-byte aligned by the launch: see host side)
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* tiles_base = smem;
+  uint64_t* full_bar = (uint64_t*)(smem + (size_t)stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + TC_MAX_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + TC_MAX_STAGES;
+  uint32_t* tmem_ptr_smem = (uint32_t*)(tmem_full_bar + 1);
+  float* s_bias = (float*)(tmem_ptr_smem + 2);           // block_n floats (<= 256)
+  float* s_stage = (float*)tiles_base;                   // epilogue transpose buffers reuse the idle tile ring
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < block_n) tmem_cols <<= 1;
+
+  if (warp == 0 && elect_one()) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&P.map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&P.map_b) : "memory");
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                 "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (MODE == TC_FWD && warp >= 2) {
+    for (int j = threadIdx.x - 64; j < block_n; j += 128)
+      s_bias[j] = (P.bias != nullptr && n0 + j < P.N) ? __ldg(P.bias + n0 + j) : 0.f;
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (elect_one()) {
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % stages;
+        const uint32_t ph = (i / stages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sa = tiles_base + (size_t)s * stage_bytes;
+        uint8_t* sb = sa + a_bytes;
+        mbar_expect_tx(&full_bar[s], stage_bytes);
+        const int k0 = (kb_begin + i) * TC_BLOCK_K;
+        if (!A_MN) {
+          tma_load_2d(sa, &P.map_a, &full_bar[s], k0, m0);  // box {32 k, 128 m}
+        } else {
+          for (int j = 0; j < TC_BLOCK_M / 32; ++j)         // boxes {32 m, 32 k}: one MN atom column each
+            tma_load_2d(sa + j * 4096, &P.map_a, &full_bar[s], m0 + j * 32, k0);
+        }
+        if (!B_MN) {
+          tma_load_2d(sb, &P.map_b, &full_bar[s], k0, n0);  // box {32 k, block_n n}
+        } else {
+          for (int j = 0; j < block_n / 32; ++j)
+            tma_load_2d(sb + j * 4096, &P.map_b, &full_bar[s], n0 + j * 32, k0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    const uint32_t idesc = make_idesc(block_n, A_MN, B_MN);
+    for (int i = 0; i < num_kb; ++i) {
+      const int s = i % stages;
+      const uint32_t ph = (i / stages) & 1;
+      mbar_wait(&full_bar[s], ph);
+      tcgen05_fence_after();
+      if (elect_one()) {
+        const uint32_t sa = smem_u32(tiles_base + (size_t)s * stage_bytes);
+        const uint32_t sb = sa + a_bytes;
+#pragma unroll
+        for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
+          // K-major: advance 32 bytes inside the 128-byte swizzle row; SBO = 8 rows x 128 B.
+          // MN-major: one MMA consumes 8 reduction rows = 1024 B; LBO = next 32-element MN atom (4096 B box),
+          //           SBO = next group of 4 reduction rows (512 B).
+          const uint64_t da = A_MN ? make_smem_desc(sa + k * 1024, 4096, 512, kLayoutSw128Base32)
+                                   : make_smem_desc(sa + k * 32, 16, 1024, kLayoutSw128);
+          const uint64_t db = B_MN ? make_smem_desc(sb + k * 1024, 4096, 512, kLayoutSw128Base32)
+                                   : make_smem_desc(sb + k * 32, 16, 1024, kLayoutSw128);
+          umma_tf32(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+        }
+      }
+      __syncwarp();
+      if (elect_one()) {
+        tcgen05_commit(&empty_bar[s]);                 // frees the smem stage when the MMAs retire
+        if (i == num_kb - 1) tcgen05_commit(tmem_full_bar);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================================================================== epilogue warps
+    const int q = warp & 3;  // TMEM sub-partition of this warp: lanes [32q, 32q+32)
+    float* st = s_stage + (size_t)(warp - 2) * (32 * 33);
+    if (num_kb > 0) {
+      mbar_wait(tmem_full_bar, 0);
+      tcgen05_fence_after();
+    }
+    const int row0 = m0 + q * 32;
+    for (int c0 = 0; c0 < block_n; c0 += 32) {
+      const int ncols = min(32, block_n - c0);
+      uint32_t v[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+      if (num_kb > 0) {
+        if (ncols == 32) TMEM_LD_32x32(taddr, v);
+        else TMEM_LD_32x16(taddr, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+      // registers (lane = row) -> smem, so that the global access below has lane = column
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (j < ncols) {
+          float x = __uint_as_float(v[j]);
+          if (MODE == TC_FWD) x = act_forward(P.act, x + s_bias[c0 + j]);
+          st[lane * 33 + j] = x;
+        }
+      }
+      __syncwarp();
+      const int col = n0 + c0 + lane;
+      const bool col_ok = lane < ncols && col < P.N;
+      float colsum = 0.f;
+      for (int r = 0; r < 32; ++r) {
+        const int row = row0 + r;
+        if (row >= P.M) break;
+        if (col_ok) {
+          float x = st[r * 33 + lane];
+          float* dst = P.C + (size_t)row * P.ldc + col;
+          if (MODE == TC_DGRAD) {
+            if (P.act != RSLRL_ACT_IDENTITY) x *= act_grad_from_output(P.act, __ldg(P.H + (size_t)row * P.ldh + col));
+            colsum += x;
+          }
+          if (MODE == TC_WGRAD) atomicAdd(dst, x);
+          else *dst = x;
+        }
+      }
+      if (MODE == TC_DGRAD && P.db_prev != nullptr && col_ok) atomicAdd(P.db_prev + col, colsum);
+      __syncwarp();
+    }
+    tcgen05_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// -------------------------------------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+// 2-D fp32 tensor [rows, cols] with row pitch ld (elements); box {box_cols, box_rows}.
+static bool make_map(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_cols,
+                     int box_rows, bool atom32) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+static bool tma_ok(const void* p, long long ld) { return ((uintptr_t)p & 15) == 0 && (ld % 4) == 0; }
+
+static int pick_block_n(int N) {
+  if (N >= 256) return 256;
+  int b = (N + 31) / 32 * 32;  // MN-major operands come in 32-element atoms; keep it simple for K-major too
+  if (N <= 16) b = 16;
+  return b;
+}
+
+static size_t smem_bytes_for(int block_n) {
+  const size_t stage = (size_t)(TC_BLOCK_M + block_n) * TC_BLOCK_K * 4;
+  size_t stages = TC_SMEM_BUDGET / stage;
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  size_t need = stages * stage + (2 * TC_MAX_STAGES + 1) * 8 + 16 + 256 * 4;
+  const size_t epi = 4 * 32 * 33 * 4;
+  if (need < epi) need = epi;
+  return need + 1024;  // slack for the manual 1024-byte alignment
+}
+
+template <int MODE>
+static int launch_tc(TcBatch& b, int n, cudaStream_t st, const char* what) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
+      return 1;
+    }
+    attr_set = true;
+  }
+  int max_ctas = 0;
+  size_t smem = 0;
+  for (int i = 0; i < n; ++i) {
+    const int t = b.p[i].tiles_m * b.p[i].tiles_n * b.p[i].splits;
+    if (t > max_ctas) max_ctas = t;
+    const size_t s = smem_bytes_for(b.p[i].block_n);
+    if (s > smem) smem = s;
+  }
+  if (max_ctas == 0) return 0;
+  tc_gemm_kernel<MODE><<<dim3(max_ctas, n), TC_THREADS, smem, st>>>(b);
+  return finish_launch(what);
+}
+
+// Each tc_* entry returns 0 on success, 1 on error, and -1 if a problem cannot be described to TMA
+// (caller falls back to the fp32 kernel for the whole group).
+int tc_linear_forward(int n, const rslrl_linear_fwd_t* pr, cudaStream_t st) {
+  const char* what = "rslrl_linear_forward(tf32)";
+  if (n > 2) return -1;
+  TcBatch b{};
+  for (int i = 0; i < n; ++i) {
+    const rslrl_linear_fwd_t& q = pr[i];
+    if (!tma_ok(q.x, q.ldx) || !tma_ok(q.w, q.K)) return -1;
+    TcProblem& P = b.p[i];
+    P.block_n = pick_block_n(q.N);
+    if (!make_map(&P.map_a, q.x, q.M, q.K, q.ldx, TC_BLOCK_K, TC_BLOCK_M, false) ||
+        !make_map(&P.map_b, q.w, q.N, q.K, q.K, TC_BLOCK_K, P.block_n, false)) {
+      set_error("%s: cuTensorMapEncodeTiled failed", what);
+      return 1;
+    }
+    P.C = q.y; P.bias = q.b; P.M = q.M; P.N = q.N; P.K = q.K; P.ldc = q.ldy; P.act = q.act;
+    P.tiles_m = (q.M + TC_BLOCK_M - 1) / TC_BLOCK_M;
+    P.tiles_n = (q.N + P.block_n - 1) / P.block_n;
+    P.num_kb = (q.K + TC_BLOCK_K - 1) / TC_BLOCK_K;
+    P.splits = 1; P.kb_per_split = P.num_kb;
+  }
+  return launch_tc<TC_FWD>(b, n, st, what);
+}
+
+int tc_linear_backward_data(int n, const rslrl_linear_bwd_data_t* pr, cudaStream_t st) {
+  const char* what = "rslrl_linear_backward_data(tf32)";
+  if (n > 2) return -1;
+  TcBatch b{};
+  for (int i = 0; i < n; ++i) {
+    const rslrl_linear_bwd_data_t& q = pr[i];
+    // dX[M,K] = dY[M,N] W[N,K]: reduction N; B = W is MN-major (K contiguous) -> K must be whole 32-atoms
+    if (!tma_ok(q.dy, q.ldy) || !tma_ok(q.w, q.K) || (q.K % 32) != 0) return -1;
+    TcProblem& P = b.p[i];
+    P.block_n = q.K >= 256 ? 256 : q.K;
+    if (q.K % P.block_n != 0) return -1;
+    if (!make_map(&P.map_a, q.dy, q.M, q.N, q.ldy, TC_BLOCK_K, TC_BLOCK_M, false) ||
+        !make_map(&P.map_b, q.w, q.N, q.K, q.K, 32, TC_BLOCK_K, true)) {
+      set_error("%s: cuTensorMapEncodeTiled failed", what);
+      return 1;
+    }
+    P.C = q.dx; P.H = q.h; P.db_prev = q.db_prev;
+    P.M = q.M; P.N = q.K; P.K = q.N; P.ldc = q.ldx; P.ldh = q.ldh; P.act = q.act;
+    P.tiles_m = (q.M + TC_BLOCK_M - 1) / TC_BLOCK_M;
+    P.tiles_n = q.K / P.block_n;
+    P.num_kb = (q.N + TC_BLOCK_K - 1) / TC_BLOCK_K;
+    P.splits = 1; P.kb_per_split = P.num_kb;
+  }
+  return launch_tc<TC_DGRAD>(b, n, st, what);
+}
+
+int tc_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* pr, cudaStream_t st) {
+  const char* what = "rslrl_linear_backward_weight(tf32)";
+  if (n > 2) return -1;
+  TcBatch b{};
+  int tiles_all = 0;
+  for (int i = 0; i < n; ++i) {
+    const rslrl_linear_bwd_weight_t& q = pr[i];
+    // dW[N,K] += dY[M,N]^T X[M,K]: reduction M; both operands MN-major
+    if (!tma_ok(q.dy, q.ldy) || !tma_ok(q.x, q.ldx)) return -1;
+    TcProblem& P = b.p[i];
+    P.block_n = pick_block_n(q.K);
+    if (P.block_n < 32) P.block_n = 32;
+    P.tiles_m = (q.N + TC_BLOCK_M - 1) / TC_BLOCK_M;
+    P.tiles_n = (q.K + P.block_n - 1) / P.block_n;
+    tiles_all += P.tiles_m * P.tiles_n;
+  }
+  for (int i = 0; i < n; ++i) {
+    const rslrl_linear_bwd_weight_t& q = pr[i];
+    TcProblem& P = b.p[i];
+    if (!make_map(&P.map_a, q.dy, q.M, q.N, q.ldy, 32, TC_BLOCK_K, true) ||
+        !make_map(&P.map_b, q.x, q.M, q.K, q.ldx, 32, TC_BLOCK_K, true)) {
+      set_error("%s: cuTensorMapEncodeTiled failed", what);
+      return 1;
+    }
+    P.C = q.dw; P.M = q.N; P.N = q.K; P.K = q.M; P.ldc = q.K;
+    P.num_kb = (q.M + TC_BLOCK_K - 1) / TC_BLOCK_K;
+    int want = (2 * kNumSMs + tiles_all - 1) / tiles_all;   // ~2 CTAs worth of work per SM
+    int max_s = P.num_kb / 8;                               // at least 8 k-blocks (256 rows) per split
+    if (max_s < 1) max_s = 1;
+    if (want > max_s) want = max_s;
+    if (want < 1) want = 1;
+    P.kb_per_split = (P.num_kb + want - 1) / want;
+    P.splits = (P.num_kb + P.kb_per_split - 1) / P.kb_per_split;
+  }
+  return launch_tc<TC_WGRAD>(b, n, st, what);
+}
+
+// out[n] += sum_m x[m, n]  (only used when a caller asks the tensor-core wgrad for db)
+__global__ void colsum_kernel(const float* __restrict__ x, int M, int N, int ld, float* __restrict__ out) {
+  const int n = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int rows_per = (M + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
+  float acc = 0.f;
+  if (n < N)
+    for (int r = r0 + (threadIdx.x >> 5); r < r1; r += 8) acc += __ldg(x + (size_t)r * ld + n);
+  __shared__ float s[8][33];
+  s[threadIdx.x >> 5][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32 && n < N) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += s[w][threadIdx.x];
+    atomicAdd(out + n, t);
+  }
+}
+
+int colsum_accumulate(const float* x, int M, int N, int ld, float* out, cudaStream_t st) {
+  int ysplit = (M + 1023) / 1024;
+  if (ysplit > 256) ysplit = 256;
+  colsum_kernel<<<dim3((N + 31) / 32, ysplit), 256, 0, st>>>(x, M, N, ld, out);
+  return finish_launch("rslrl_linear_backward_weight(tf32, db)");
+}
+
 }  // namespace rslrl

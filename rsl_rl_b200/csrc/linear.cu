@@ -8,6 +8,7 @@ int simt_linear_backward_data(int n, const rslrl_linear_bwd_data_t* pr, cudaStre
 int simt_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* pr, cudaStream_t st);
 int tc_linear_forward(int n, const rslrl_linear_fwd_t* pr, cudaStream_t st);
 int tc_linear_backward_data(int n, const rslrl_linear_bwd_data_t* pr, cudaStream_t st);
+int colsum_accumulate(const float* x, int M, int N, int ld, float* out, cudaStream_t st);
 int tc_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* pr, cudaStream_t st);
 }  // namespace rslrl
 
@@ -22,7 +23,11 @@ int rslrl_linear_forward(int n, const rslrl_linear_fwd_t* probs_host, int precis
     RSLRL_CHECK_ARG(p.x && p.w && p.y && p.M > 0 && p.N > 0 && p.K > 0 && p.ldx >= p.K && p.ldy >= p.N, what);
   }
   if (precision == RSLRL_PREC_FP32) return simt_linear_forward(n, probs_host, (cudaStream_t)stream);
-  if (precision == RSLRL_PREC_TF32) return tc_linear_forward(n, probs_host, (cudaStream_t)stream);
+  if (precision == RSLRL_PREC_TF32) {
+    const int rc = tc_linear_forward(n, probs_host, (cudaStream_t)stream);
+    // -1: an operand cannot be described to TMA (row pitch not a multiple of 16 bytes) -> exact fp32 kernel
+    return rc >= 0 ? rc : simt_linear_forward(n, probs_host, (cudaStream_t)stream);
+  }
   set_error("%s: unknown precision %d", what, precision);
   return 2;
 }
@@ -38,7 +43,10 @@ int rslrl_linear_backward_data(int n, const rslrl_linear_bwd_data_t* probs_host,
     RSLRL_CHECK_ARG(p.act == RSLRL_ACT_IDENTITY || (p.h && p.ldh >= p.K), what);
   }
   if (precision == RSLRL_PREC_FP32) return simt_linear_backward_data(n, probs_host, (cudaStream_t)stream);
-  if (precision == RSLRL_PREC_TF32) return tc_linear_backward_data(n, probs_host, (cudaStream_t)stream);
+  if (precision == RSLRL_PREC_TF32) {
+    const int rc = tc_linear_backward_data(n, probs_host, (cudaStream_t)stream);
+    return rc >= 0 ? rc : simt_linear_backward_data(n, probs_host, (cudaStream_t)stream);
+  }
   set_error("%s: unknown precision %d", what, precision);
   return 2;
 }
@@ -53,7 +61,18 @@ int rslrl_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* probs_h
     RSLRL_CHECK_ARG(p.dy && p.x && p.dw && p.M > 0 && p.N > 0 && p.K > 0 && p.ldy >= p.N && p.ldx >= p.K, what);
   }
   if (precision == RSLRL_PREC_FP32) return simt_linear_backward_weight(n, probs_host, (cudaStream_t)stream);
-  if (precision == RSLRL_PREC_TF32) return tc_linear_backward_weight(n, probs_host, (cudaStream_t)stream);
+  if (precision == RSLRL_PREC_TF32) {
+    const int rc = tc_linear_backward_weight(n, probs_host, (cudaStream_t)stream);
+    if (rc < 0) return simt_linear_backward_weight(n, probs_host, (cudaStream_t)stream);
+    if (rc > 0) return rc;
+    // the tensor-core wgrad does not touch db (the fused engine takes bias gradients from the kernels that
+    // produce dy); callers that ask for it here get a column-sum pass
+    for (int i = 0; i < n; ++i) {
+      const rslrl_linear_bwd_weight_t& p = probs_host[i];
+      if (p.db && colsum_accumulate(p.dy, p.M, p.N, p.ldy, p.db, (cudaStream_t)stream)) return 1;
+    }
+    return 0;
+  }
   set_error("%s: unknown precision %d", what, precision);
   return 2;
 }

@@ -19,7 +19,7 @@ constexpr float kLogSqrt2Pi = 0.91893853320467274178f;   // log(sqrt(2 pi))
 constexpr float kEntropyConst = 1.41893853320467274178f;  // 0.5 + 0.5 log(2 pi)
 
 struct LossWorkspace {
-  double acc[4 + kMaxActions];  // kl, surrogate, value loss, (unused), dstd[A]
+  double acc[4 + 2 * kMaxActions];  // kl, surrogate, value loss, sum(dvalue), dstd[A], sum_rows(dmu)[A]
   unsigned int ticket;
   unsigned int pad_;
 };
@@ -67,12 +67,13 @@ ppo_loss_kernel(const float* __restrict__ mu, const float* __restrict__ std_para
                 const float* __restrict__ old_logp, const float* __restrict__ advantages,
                 const float* __restrict__ returns, const float* __restrict__ old_values,
                 const float* __restrict__ old_mu, const float* __restrict__ old_sigma,
-                const double* __restrict__ adv_stats, float* __restrict__ dmu, float* __restrict__ dvalue,
-                float* dstd, float* kl_out, double* loss_sums, LossWorkspace* ws, long long rows, long long mb_orig,
+                const double* __restrict__ adv_stats, float* __restrict__ dmu, int dmu_stride,
+                float* __restrict__ dvalue, int dvalue_stride, float* dstd, float* db_mu, float* db_value,
+                float* kl_out, double* loss_sums, LossWorkspace* ws, long long rows, long long mb_orig,
                 int A, float clip, float c_v, float c_e, int use_clipped) {
   __shared__ float s_sigma[kMaxActions], s_logs[kMaxActions], s_2var[kMaxActions];
   __shared__ double s_red[4 * 32];
-  __shared__ float s_dstd[kMaxActions];
+  __shared__ float s_dstd[kMaxActions], s_dbmu[kMaxActions];
   __shared__ bool s_last;
   if (threadIdx.x < A) {
     const float p = std_param[threadIdx.x];
@@ -81,6 +82,7 @@ ppo_loss_kernel(const float* __restrict__ mu, const float* __restrict__ std_para
     s_logs[threadIdx.x] = logf(s);
     s_2var[threadIdx.x] = 2.f * (s * s);
     s_dstd[threadIdx.x] = 0.f;
+    s_dbmu[threadIdx.x] = 0.f;
   }
   __syncthreads();
 
@@ -129,7 +131,7 @@ ppo_loss_kernel(const float* __restrict__ mu, const float* __restrict__ std_para
     }
   }
 
-  float g_lp = 0.f, surr = 0.f, vl = 0.f;
+  float g_lp = 0.f, surr = 0.f, vl = 0.f, dv_sum = 0.f;
   if (valid) {
     float adv = __ldg(advantages + j);
     if (adv_stats) {  // per-minibatch normalisation (ppo.py:221-223), unbiased std
@@ -169,14 +171,15 @@ ppo_loss_kernel(const float* __restrict__ mu, const float* __restrict__ std_para
       vl = e * e;
       dv_out = c_v * g * (-2.f) * e;
     }
-    dvalue[i] = dv_out;
+    dvalue[i * dvalue_stride] = dv_out;
+    dv_sum = dv_out;
   }
 
   // second pass over the row: dL/dmu and the per-action dL/dsigma column sums
   {
     const float* m = mu + (valid ? i : 0) * A;
     const float* ac = actions + (valid ? i : 0) * A;
-    float* dm = dmu + (valid ? i : 0) * A;
+    float* dm = dmu + (valid ? i : 0) * dmu_stride;
     const int lane = threadIdx.x & 31;
     for (int c = 0; c < A; c += 4) {
       float d[4] = {0, 0, 0, 0};
@@ -197,6 +200,10 @@ ppo_loss_kernel(const float* __restrict__ mu, const float* __restrict__ std_para
         float ds = valid ? g_lp * (d[q] * d[q] / (var * s) - 1.f / s) : 0.f;
         ds = warp_sum(ds);
         if (lane == 0) atomicAdd(&s_dstd[c + q], ds);
+        if (db_mu != nullptr) {
+          const float sm = warp_sum(o[q]);
+          if (lane == 0) atomicAdd(&s_dbmu[c + q], sm);
+        }
       }
       if (valid) {
         if (VEC) *(float4*)(dm + c) = make_float4(o[0], o[1], o[2], o[3]);
@@ -205,15 +212,19 @@ ppo_loss_kernel(const float* __restrict__ mu, const float* __restrict__ std_para
     }
   }
 
-  double red[3] = {(double)kl, (double)surr, (double)vl};
-  block_sum<3>(red, s_red);
+  double red[4] = {(double)kl, (double)surr, (double)vl, (double)dv_sum};
+  block_sum<4>(red, s_red);
   if (threadIdx.x == 0) {
     atomicAdd(&ws->acc[0], red[0]);
     atomicAdd(&ws->acc[1], red[1]);
     atomicAdd(&ws->acc[2], red[2]);
+    atomicAdd(&ws->acc[3], red[3]);
   }
   __syncthreads();
-  if (threadIdx.x < A) atomicAdd(&ws->acc[4 + threadIdx.x], (double)s_dstd[threadIdx.x]);
+  if (threadIdx.x < A) {
+    atomicAdd(&ws->acc[4 + threadIdx.x], (double)s_dstd[threadIdx.x]);
+    if (db_mu != nullptr) atomicAdd(&ws->acc[4 + kMaxActions + threadIdx.x], (double)s_dbmu[threadIdx.x]);
+  }
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) s_last = atomicAdd(&ws->ticket, 1u) == gridDim.x - 1;
@@ -230,10 +241,15 @@ ppo_loss_kernel(const float* __restrict__ mu, const float* __restrict__ std_para
     else gsum = gsum - (double)c_e / (double)s;
     dstd[a] += (float)gsum;
     ws->acc[4 + a] = 0.0;
+    if (db_mu != nullptr) {
+      db_mu[a] += (float)*((volatile double*)&ws->acc[4 + kMaxActions + a]);
+      ws->acc[4 + kMaxActions + a] = 0.0;
+    }
   }
   if (threadIdx.x == 0) {
     const double klm = *((volatile double*)&ws->acc[0]) / (double)mb_orig;
     if (kl_out) *kl_out = (float)klm;
+    if (db_value) *db_value += (float)*((volatile double*)&ws->acc[3]);
     float ent = 0.f;
     for (int a = 0; a < A; ++a) ent += kEntropyConst + s_logs[a];
     if (loss_sums) {
@@ -296,8 +312,9 @@ int64_t rslrl_loss_workspace_bytes(void) { return (int64_t)sizeof(rslrl::LossWor
 int rslrl_ppo_loss_fwd_bwd(const float* mu, const float* std_param, int std_type, const float* value,
                            const float* actions, const float* old_logp, const float* advantages,
                            const float* returns, const float* old_values, const float* old_mu,
-                           const float* old_sigma, const double* adv_stats, float* dmu, float* dvalue,
-                           float* dstd, float* kl_out, double* loss_sums, void* workspace, int64_t rows,
+                           const float* old_sigma, const double* adv_stats, float* dmu, int dmu_stride,
+                           float* dvalue, int dvalue_stride, float* dstd, float* db_mu, float* db_value,
+                           float* kl_out, double* loss_sums, void* workspace, int64_t rows,
                            int64_t mb_orig, int A, double clip_param, double value_loss_coef,
                            double entropy_coef, int use_clipped_value_loss, rslrl_stream_t stream) {
   using namespace rslrl;
@@ -305,13 +322,16 @@ int rslrl_ppo_loss_fwd_bwd(const float* mu, const float* std_param, int std_type
   RSLRL_CHECK_ARG(mu && std_param && value && actions && old_logp && advantages && returns && old_values, what);
   RSLRL_CHECK_ARG(old_mu && old_sigma && dmu && dvalue && dstd && workspace, what);
   RSLRL_CHECK_ARG(rows > 0 && mb_orig > 0 && rows % mb_orig == 0 && A > 0 && A <= kMaxActions, what);
+  RSLRL_CHECK_ARG(dmu_stride >= A && dvalue_stride >= 1, what);
   const int blocks = (int)((rows + kLossThreads - 1) / kLossThreads);
-  const bool vec = (A % 4 == 0) && ((((uintptr_t)mu | (uintptr_t)actions | (uintptr_t)old_mu | (uintptr_t)old_sigma |
-                                      (uintptr_t)dmu) & 15) == 0);
+  const bool vec = (A % 4 == 0) && (dmu_stride % 4 == 0) &&
+                   ((((uintptr_t)mu | (uintptr_t)actions | (uintptr_t)old_mu | (uintptr_t)old_sigma |
+                      (uintptr_t)dmu) & 15) == 0);
   auto kern = vec ? ppo_loss_kernel<true> : ppo_loss_kernel<false>;
   kern<<<blocks, kLossThreads, 0, (cudaStream_t)stream>>>(
       mu, std_param, std_type, value, actions, old_logp, advantages, returns, old_values, old_mu, old_sigma, adv_stats,
-      dmu, dvalue, dstd, kl_out, loss_sums, (LossWorkspace*)workspace, rows, mb_orig, A, (float)clip_param,
+      dmu, dmu_stride, dvalue, dvalue_stride, dstd, db_mu, db_value, kl_out, loss_sums, (LossWorkspace*)workspace, rows,
+      mb_orig, A, (float)clip_param,
       (float)value_loss_coef, (float)entropy_coef, use_clipped_value_loss);
   return finish_launch(what);
 }

@@ -38,11 +38,14 @@ def linear_forward(problems: Sequence[Tuple], precision: int):
 
 
 def linear_backward_data(problems: Sequence[Tuple], precision: int):
-    """problems: (dy[M,N], weight[N,K], h[M,K]|None, dx[M,K], act_code_of_previous_layer)."""
+    """problems: (dy[M,N], weight[N,K], h[M,K]|None, dx[M,K], act_code_of_previous_layer[, db_prev[K]|None])."""
     arr = (nat.LinearBwdData * len(problems))()
-    for i, (dy, w, h, dx, act) in enumerate(problems):
+    for i, prob in enumerate(problems):
+        dy, w, h, dx, act = prob[:5]
+        db_prev = prob[5] if len(prob) > 5 else None
         arr[i] = nat.LinearBwdData(dy.data_ptr(), w.data_ptr(), nat.ptr(h), dx.data_ptr(), dy.shape[0], w.shape[0],
-                                   w.shape[1], dy.stride(0), 0 if h is None else h.stride(0), dx.stride(0), act)
+                                   w.shape[1], dy.stride(0), 0 if h is None else h.stride(0), dx.stride(0), act,
+                                   nat.ptr(db_prev))
     nat.check(nat.lib().rslrl_linear_backward_data(len(problems), arr, precision, nat.stream_ptr()))
 
 

@@ -171,18 +171,20 @@ def _lin_ref(x, w, b, act):
                                         (2048, 128, 12, "identity"), (2048, 128, 1, "identity"), (130, 5, 3, "tanh"),
                                         (24576, 256, 128, "elu"), (64, 16, 200, "selu"), (300, 33, 65, "sigmoid"),
                                         (300, 33, 65, "lrelu"), (300, 33, 65, "softplus")])
-def test_linear_forward_fp32(M, K, N, act):
+@pytest.mark.parametrize("prec,tol", [("fp32", 1e-5), ("tf32", 1e-3)])
+def test_linear_forward(M, K, N, act, prec, tol):
     from rsl_rl_b200.networks.mlp import linear_forward
     nat = _nat()
     torch.manual_seed(M + K + N)
     x = torch.randn(M, K, device=DEV); w = torch.randn(N, K, device=DEV) / K ** 0.5; b = torch.randn(N, device=DEV)
-    y = torch.empty(M, N, device=DEV)
-    linear_forward([(x, w, b, y, nat.ACT_CODES[act])], nat.PREC_FP32)
+    y = torch.full((M, N), float("nan"), device=DEV)
+    linear_forward([(x, w, b, y, nat.ACT_CODES[act])], nat.PREC_CODES[prec])
     ref = _lin_ref(x, w, b, act)
-    assert rel_err(y.cpu().numpy(), ref.cpu().numpy()) < 1e-5
+    assert rel_err(y.cpu().numpy(), ref.cpu().numpy()) < tol
 
 
-def test_linear_forward_grouped_and_strided_input():
+@pytest.mark.parametrize("prec,tol", [("fp32", 1e-5), ("tf32", 1e-3)])
+def test_linear_forward_grouped_and_strided_input(prec, tol):
     from rsl_rl_b200.networks.mlp import linear_forward
     nat = _nat()
     torch.manual_seed(5)
@@ -191,33 +193,40 @@ def test_linear_forward_grouped_and_strided_input():
     wa, ba = torch.randn(96, 50, device=DEV), torch.randn(96, device=DEV)
     wc, bc = torch.randn(33, 48, device=DEV), None
     ya, yc = torch.empty(3000, 96, device=DEV), torch.empty(3000, 33, device=DEV)
-    linear_forward([(xa, wa, ba, ya, nat.ACT_CODES["elu"]), (xc, wc, bc, yc, 0)], nat.PREC_FP32)
-    assert rel_err(ya.cpu().numpy(), _lin_ref(xa, wa, ba, "elu").cpu().numpy()) < 1e-5
-    assert rel_err(yc.cpu().numpy(), _lin_ref(xc, wc, bc, "identity").cpu().numpy()) < 1e-5
+    linear_forward([(xa, wa, ba, ya, nat.ACT_CODES["elu"]), (xc, wc, bc, yc, 0)], nat.PREC_CODES[prec])
+    assert rel_err(ya.cpu().numpy(), _lin_ref(xa, wa, ba, "elu").cpu().numpy()) < tol
+    assert rel_err(yc.cpu().numpy(), _lin_ref(xc, wc, bc, "identity").cpu().numpy()) < tol
 
 
 @pytest.mark.parametrize("M,K,N,act", [(1000, 512, 256, "elu"), (4096, 128, 12, "elu"), (3000, 128, 1, "relu"),
                                         (24576, 256, 128, "elu"), (513, 37, 5, "tanh"), (600, 48, 512, "identity")])
-def test_linear_backward_fp32(M, K, N, act):
-    """dx = (dy W) * act'(h), dW += dy^T x, db += colsum(dy) against an fp64 restatement."""
+@pytest.mark.parametrize("prec,tol", [("fp32", 1e-5), ("tf32", 1e-3)])
+def test_linear_backward(M, K, N, act, prec, tol):
+    """dx = (dy W) * act'(h) (+ fused bias gradient of the previous layer), dW += dy^T x, db += colsum(dy)
+    against an fp64 restatement."""
     from rsl_rl_b200.networks.mlp import linear_backward_data, linear_backward_weight
     nat = _nat()
+    P = nat.PREC_CODES[prec]
     torch.manual_seed(M + N)
     z_prev = torch.randn(M, K, device=DEV)
     h = torch.from_numpy(O.act_forward(act, z_prev.cpu().numpy())).to(DEV)          # this layer's input
     w = torch.randn(N, K, device=DEV) / K ** 0.5
-    dy = torch.randn(M, N, device=DEV)
-    dx = torch.empty(M, K, device=DEV)
-    linear_backward_data([(dy, w, h, dx, nat.ACT_CODES[act])], nat.PREC_FP32)
+    Np = (N + 3) // 4 * 4
+    dy = torch.zeros(M, Np, device=DEV)[:, :N]                                      # 16-byte row pitch (TMA)
+    dy.normal_()
+    dx = torch.full((M, K), float("nan"), device=DEV)
+    db_prev = torch.zeros(K, device=DEV)
+    linear_backward_data([(dy, w, h, dx, nat.ACT_CODES[act], db_prev)], P)
     dh = (dy.double() @ w.double()).cpu().numpy()
     ref_dx = O.act_backward(act, z_prev.cpu().numpy(), h.cpu().numpy(), dh.astype(np.float32)) if act != "identity" else dh
-    assert rel_err(dx.cpu().numpy(), ref_dx) < 1e-5
+    assert rel_err(dx.cpu().numpy(), ref_dx) < tol
+    assert rel_err(db_prev.cpu().numpy(), np.asarray(ref_dx, dtype=np.float64).sum(0)) < 10 * tol
     dw = torch.zeros(N, K, device=DEV); db = torch.zeros(N, device=DEV)
-    linear_backward_weight([(dy, h, dw, db)], nat.PREC_FP32)
-    assert rel_err(dw.cpu().numpy(), (dy.double().T @ h.double()).cpu().numpy()) < 1e-5
+    linear_backward_weight([(dy, h, dw, db)], P)
+    assert rel_err(dw.cpu().numpy(), (dy.double().T @ h.double()).cpu().numpy()) < tol
     assert rel_err(db.cpu().numpy(), dy.double().sum(0).cpu().numpy()) < 1e-5
-    linear_backward_weight([(dy, h, dw, db)], nat.PREC_FP32)                        # accumulates
-    assert rel_err(dw.cpu().numpy(), 2 * (dy.double().T @ h.double()).cpu().numpy()) < 1e-5
+    linear_backward_weight([(dy, h, dw, None)], P)                                  # accumulates; db optional
+    assert rel_err(dw.cpu().numpy(), 2 * (dy.double().T @ h.double()).cpu().numpy()) < tol
 
 
 def test_mlp_autograd_function_matches_torch():
@@ -269,8 +278,11 @@ def _run_loss(mu, std_param, std_type, value, actions, old_logp, adv, ret, old_v
     t = lambda a: cu(np.asarray(a, dtype=np.float32).reshape(a.shape))
     d = dict(mu=t(mu), sp=t(std_param), value=t(value.reshape(-1)), actions=t(actions), old_logp=t(old_logp.reshape(-1)),
              adv=t(adv.reshape(-1)), ret=t(ret.reshape(-1)), old_v=t(old_v.reshape(-1)), old_mu=t(old_mu), old_sigma=t(old_sigma))
-    dmu, dv = torch.empty(rows, A, device=DEV), torch.empty(rows, device=DEV)
+    A4 = (A + 3) // 4 * 4
+    dmu_buf, dv_buf = torch.zeros(rows, A4, device=DEV), torch.zeros(rows, 4, device=DEV)
+    dmu, dv = dmu_buf[:, :A], dv_buf[:, 0]
     dstd, kl = torch.zeros(A, device=DEV), torch.zeros(1, device=DEV)
+    db_mu, db_v = torch.zeros(A, device=DEV), torch.zeros(1, device=DEV)
     sums = torch.zeros(3, dtype=torch.float64, device=DEV)
     ws = torch.zeros(int(nat.lib().rslrl_loss_workspace_bytes()), dtype=torch.uint8, device=DEV)
     stats = None
@@ -279,13 +291,18 @@ def _run_loss(mu, std_param, std_type, value, actions, old_logp, adv, ret, old_v
         sws = torch.zeros(64, dtype=torch.uint8, device=DEV)
         nat.check(nat.lib().rslrl_sum_sumsq(d["adv"].data_ptr(), mb_orig, stats.data_ptr(), sws.data_ptr(), nat.stream_ptr()))
     for _ in range(2):  # twice: the workspace must clean itself up
-        dstd.zero_(); sums.zero_()
+        dstd.zero_(); sums.zero_(); db_mu.zero_(); db_v.zero_()
         nat.check(nat.lib().rslrl_ppo_loss_fwd_bwd(
             d["mu"].data_ptr(), d["sp"].data_ptr(), std_type, d["value"].data_ptr(), d["actions"].data_ptr(),
             d["old_logp"].data_ptr(), d["adv"].data_ptr(), d["ret"].data_ptr(), d["old_v"].data_ptr(), d["old_mu"].data_ptr(),
-            d["old_sigma"].data_ptr(), nat.ptr(stats), dmu.data_ptr(), dv.data_ptr(), dstd.data_ptr(), kl.data_ptr(),
-            sums.data_ptr(), ws.data_ptr(), rows, mb_orig, A, 0.2, 1.0, 0.01, int(clipped), nat.stream_ptr()))
+            d["old_sigma"].data_ptr(), nat.ptr(stats), dmu.data_ptr(), A4, dv.data_ptr(), 4, dstd.data_ptr(),
+            db_mu.data_ptr(), db_v.data_ptr(), kl.data_ptr(), sums.data_ptr(), ws.data_ptr(), rows, mb_orig, A, 0.2, 1.0,
+            0.01, int(clipped), nat.stream_ptr()))
     torch.cuda.synchronize()
+    # the fused bias gradients of the two output layers are the column sums of dmu / dvalue
+    assert rel_err(db_mu.cpu().numpy(), dmu.double().sum(0).cpu().numpy()) < 1e-5
+    assert abs(float(db_v) - float(dv.double().sum())) < 1e-5 * max(1e-6, float(dv.double().abs().sum()))
+    assert float(dmu_buf[:, A:].abs().sum()) == 0.0 and float(dv_buf[:, 1:].abs().sum()) == 0.0
     return dmu.cpu().numpy(), dv.cpu().numpy(), dstd.cpu().numpy(), float(kl), sums.cpu().numpy()
 
 
