@@ -25,6 +25,7 @@
 // epilogue here, the loss kernel for the output layers) instead of re-reading dY.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -365,7 +366,10 @@ static bool make_map(CUtensorMap* map, const float* base, long long rows, long l
   cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+  static const int dtype_sel = [] { const char* e = getenv("RSLRL_TMA_DTYPE"); return e ? atoi(e) : 1; }();  // default: TFLOAT32 = TMA rounds fp32 -> tf32 to nearest (measured: profiles/experiments)
+  const CUtensorMapDataType dt = dtype_sel == 1 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32
+                               : dtype_sel == 2 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32_FTZ : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUresult r = fn(map, dt, 2, (void*)base, dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE,
                   atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
