@@ -115,11 +115,10 @@ class FeedForwardEngine:
                     continue
                 lin = net.layers[l]
                 inp = x_in if l == 0 else hs[l - 1][:M]
-                # bias gradients come from the kernel that produces dy (loss kernel / dgrad epilogue), not from wgrad
-                wprobs.append((dy[ni], inp, lin.weight.grad, None))
+                wprobs.append((dy[ni], inp, lin.weight.grad, lin.bias.grad))
                 if l > 0:
                     dx = gbuf[k % 2][:M * net.dims[l]].view(M, net.dims[l])
-                    dprobs.append((dy[ni], lin.weight, inp, dx, net.acts[l - 1], net.layers[l - 1].bias.grad))
+                    dprobs.append((dy[ni], lin.weight, inp, dx, net.acts[l - 1]))
                     new_dy[ni] = dx
             linear_backward_weight(wprobs, self.prec)
             if dprobs:
@@ -143,8 +142,7 @@ class FeedForwardEngine:
             mu.data_ptr(), self.std_param.data_ptr(), self.std_type, value.data_ptr(), actions.data_ptr(),
             old_logp.data_ptr(), adv.data_ptr(), returns.data_ptr(), old_values.data_ptr(), old_mu.data_ptr(),
             old_sigma.data_ptr(), stats_ptr, self.dmu.data_ptr(), self.dmu.stride(0), self.dvalue.data_ptr(),
-            self.dvalue.stride(0), self.std_param.grad.data_ptr(), self.actor.layers[-1].bias.grad.data_ptr(),
-            self.critic.layers[-1].bias.grad.data_ptr(), nat.ptr(kl_out), nat.ptr(loss_sums),
+            self.dvalue.stride(0), self.std_param.grad.data_ptr(), None, None, nat.ptr(kl_out), nat.ptr(loss_sums),
             self.loss_ws.data_ptr(), rows,
             mb_orig, self.A, hp["clip_param"], hp["value_loss_coef"], hp["entropy_coef"],
             int(hp["use_clipped_value_loss"]), nat.stream_ptr()))

@@ -36,20 +36,23 @@ namespace rslrl {
 constexpr int TC_BLOCK_M = 128;
 constexpr int TC_BLOCK_K = 32;  // tf32 elements = one 128-byte swizzle row
 constexpr int TC_UMMA_K = 8;    // tf32 MMA depth (32 bytes)
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_THREADS = (2 + TC_EPI_WARPS) * 32;
 constexpr int TC_MAX_STAGES = 6;
-constexpr int TC_SMEM_BUDGET = 200 * 1024;
+constexpr int TC_SMEM_BUDGET = 100 * 1024;  // per CTA: two CTAs per SM so that one's epilogue overlaps the other's mainloop
+constexpr int TC_MAX_BLOCK_N = 128;
 
 enum { TC_FWD = 0, TC_DGRAD = 1, TC_WGRAD = 2 };
 
 struct TcProblem {
   CUtensorMap map_a, map_b;
+  CUtensorMap map_c;  // output, box {32 cols, 32 rows} (store, or reduce-add for split-K wgrad)
+  CUtensorMap map_h;  // dgrad: saved activation H, same geometry as C
   float* C;
   const float* bias;  // fwd
-  const float* H;     // dgrad: saved activation (same shape as C)
-  float* db_prev;     // dgrad: += column sums of C (bias gradient of the previous layer); may be null
+  float* db;          // wgrad: += sum over the batch of dY (bias gradient); may be null
   int M, N, K;        // C is [M,N], reduction length K
-  int ldc, ldh, act;
+  int ldc, act, tma_out;
   int block_n, tiles_m, tiles_n, splits, kb_per_split, num_kb;
 };
 
@@ -163,49 +166,79 @@ __device__ __forceinline__ uint32_t make_idesc(int n, bool a_mn_major, bool b_mn
       : "r"(taddr))
 
 // ------------------------------------------------------------------------------------------- kernel
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"((uint64_t)map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   (uint64_t)map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+
+// fast activations for the tf32 path (errors << tf32 rounding)
+__device__ __forceinline__ float elu_fast(float z) { return z > 0.f ? z : __expf(z) - 1.f; }
+
 template <int MODE>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcBatch batch) {
+__global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_kernel(const __grid_constant__ TcBatch batch) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const TcProblem& P = batch.p[blockIdx.y];
-  const int tiles = P.tiles_m * P.tiles_n;
+  // Scalars are copied out of the parameter block once: reading them through the (dynamically indexed)
+  // reference inside the epilogue loops costs a dependent load per iteration.
+  const int tiles_n = P.tiles_n, tiles = P.tiles_m * tiles_n;
   if ((int)blockIdx.x >= tiles * P.splits) return;
+  const int pM = P.M, pN = P.N, ldc = P.ldc, act = P.act;
+  float* const __restrict__ Cptr = P.C;
+  const float* const __restrict__ bias_ptr = P.bias;
+  float* const __restrict__ db_ptr = P.db;
+  const bool tma_out = P.tma_out != 0;
+  const CUtensorMap* const map_a = &P.map_a;
+  const CUtensorMap* const map_b = &P.map_b;
+  const CUtensorMap* const map_c = &P.map_c;
+  const CUtensorMap* const map_h = &P.map_h;
   const int split = blockIdx.x / tiles, rem = blockIdx.x - split * tiles;
-  const int tm = rem / P.tiles_n, tn = rem - tm * P.tiles_n;
-  const int m0 = tm * TC_BLOCK_M, n0 = tn * P.block_n;
+  const int tm = rem / tiles_n, tn = rem - tm * tiles_n;
+  const int block_n = P.block_n;
+  const int m0 = tm * TC_BLOCK_M, n0 = tn * block_n;
   const int kb_begin = split * P.kb_per_split;
   const int kb_end = min(P.num_kb, kb_begin + P.kb_per_split);
   const int num_kb = kb_end - kb_begin;
 
   constexpr bool A_MN = MODE == TC_WGRAD;
   constexpr bool B_MN = MODE != TC_FWD;
-  const int block_n = P.block_n;
   const uint32_t a_bytes = TC_BLOCK_M * TC_BLOCK_K * 4, b_bytes = (uint32_t)block_n * TC_BLOCK_K * 4;
   const uint32_t stage_bytes = a_bytes + b_bytes;
   int stages = TC_SMEM_BUDGET / stage_bytes;
   stages = stages > TC_MAX_STAGES ? TC_MAX_STAGES : stages;
 
-  // carve shared memory (dynamic smem base is 1024-byte aligned by the launch: see host side)
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* tiles_base = smem;
-  uint64_t* full_bar = (uint64_t*)(smem + (size_t)stages * stage_bytes);
-  uint64_t* empty_bar = full_bar + TC_MAX_STAGES;
-  uint64_t* tmem_full_bar = empty_bar + TC_MAX_STAGES;
-  uint32_t* tmem_ptr_smem = (uint32_t*)(tmem_full_bar + 1);
-  float* s_bias = (float*)(tmem_ptr_smem + 2);           // block_n floats (<= 256)
-  float* s_stage = (float*)tiles_base;                   // epilogue transpose buffers reuse the idle tile ring
+  // carve shared memory; pointer arithmetic stays on the __shared__ symbol so accesses compile to LDS/STS
+  const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  uint8_t* const ring = smem_raw + pad;                        // tile ring, 1024-byte aligned
+  uint64_t* const full_bar = (uint64_t*)(ring + (size_t)stages * stage_bytes);
+  uint64_t* const empty_bar = full_bar + TC_MAX_STAGES;
+  uint64_t* const tmem_full_bar = empty_bar + TC_MAX_STAGES;
+  uint64_t* const h_bar = tmem_full_bar + 1;                   // one per epilogue warp
+  uint32_t* const tmem_ptr_smem = (uint32_t*)(h_bar + TC_EPI_WARPS);
+  float* const s_bias = (float*)(tmem_ptr_smem + 2);           // block_n floats (<= 256)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < block_n) tmem_cols <<= 1;
+  // wgrad: the 4 epilogue warps of the first half also reduce the dY tiles over the batch (bias gradient)
+  const bool do_db = MODE == TC_WGRAD && db_ptr != nullptr && tn == 0;
 
   if (warp == 0 && elect_one()) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&P.map_a) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&P.map_b) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map_b) : "memory");
+    if (tma_out) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map_c) : "memory");
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], do_db ? 5 : 1);
     }
     mbar_init(tmem_full_bar, 1);
+    for (int w = 0; w < TC_EPI_WARPS; ++w) mbar_init(&h_bar[w], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -215,8 +248,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (MODE == TC_FWD && warp >= 2) {
-    for (int j = threadIdx.x - 64; j < block_n; j += 128)
-      s_bias[j] = (P.bias != nullptr && n0 + j < P.N) ? __ldg(P.bias + n0 + j) : 0.f;
+    for (int j = threadIdx.x - 64; j < block_n; j += TC_EPI_WARPS * 32)
+      s_bias[j] = (bias_ptr != nullptr && n0 + j < pN) ? __ldg(bias_ptr + n0 + j) : 0.f;
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -230,21 +263,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         const int s = i % stages;
         const uint32_t ph = (i / stages) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* sa = tiles_base + (size_t)s * stage_bytes;
+        uint8_t* sa = ring + (size_t)s * stage_bytes;
         uint8_t* sb = sa + a_bytes;
         mbar_expect_tx(&full_bar[s], stage_bytes);
         const int k0 = (kb_begin + i) * TC_BLOCK_K;
         if (!A_MN) {
-          tma_load_2d(sa, &P.map_a, &full_bar[s], k0, m0);  // box {32 k, 128 m}
+          tma_load_2d(sa, map_a, &full_bar[s], k0, m0);  // box {32 k, 128 m}
         } else {
-          for (int j = 0; j < TC_BLOCK_M / 32; ++j)         // boxes {32 m, 32 k}: one MN atom column each
-            tma_load_2d(sa + j * 4096, &P.map_a, &full_bar[s], m0 + j * 32, k0);
+          for (int j = 0; j < TC_BLOCK_M / 32; ++j)      // boxes {32 m, 32 k}: one MN atom column each
+            tma_load_2d(sa + j * 4096, map_a, &full_bar[s], m0 + j * 32, k0);
         }
         if (!B_MN) {
-          tma_load_2d(sb, &P.map_b, &full_bar[s], k0, n0);  // box {32 k, block_n n}
+          tma_load_2d(sb, map_b, &full_bar[s], k0, n0);  // box {32 k, block_n n}
         } else {
-          for (int j = 0; j < block_n / 32; ++j)
-            tma_load_2d(sb + j * 4096, &P.map_b, &full_bar[s], n0 + j * 32, k0);
+          for (int j = 0; j < block_n / 32; ++j) tma_load_2d(sb + j * 4096, map_b, &full_bar[s], n0 + j * 32, k0);
         }
       }
     }
@@ -257,7 +289,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       mbar_wait(&full_bar[s], ph);
       tcgen05_fence_after();
       if (elect_one()) {
-        const uint32_t sa = smem_u32(tiles_base + (size_t)s * stage_bytes);
+        const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
         const uint32_t sb = sa + a_bytes;
 #pragma unroll
         for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
@@ -273,21 +305,63 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       }
       __syncwarp();
       if (elect_one()) {
-        tcgen05_commit(&empty_bar[s]);                 // frees the smem stage when the MMAs retire
+        tcgen05_commit(&empty_bar[s]);  // frees the smem stage when the MMAs retire
         if (i == num_kb - 1) tcgen05_commit(tmem_full_bar);
       }
       __syncwarp();
     }
   } else {
-    // ===================================================================== epilogue warps
-    const int q = warp & 3;  // TMEM sub-partition of this warp: lanes [32q, 32q+32)
-    float* st = s_stage + (size_t)(warp - 2) * (32 * 33);
+    // ===================================================================== epilogue warps (8)
+    const int ew = warp - 2;          // 0..7
+    const int q = warp & 3;           // TMEM sub-partition of this warp: lanes [32q, 32q+32)
+    const int half = ew >> 2;         // chunk parity handled by this warp
+    const int nchunks = (block_n + 31) / 32;
+    const int row0 = m0 + q * 32;
+
+    if (MODE == TC_WGRAD && do_db && half == 0) {
+      // bias gradient: db[f] += sum over the batch rows of dY[:, f]; thread <-> feature f of the A tile.
+      // A tile (MN-major, 32-byte-atom swizzle): box j = f/32 at +j*4096, row r at +r*128,
+      // 32-byte chunk ((f%32)/8) ^ (r&3), element f%8.
+      const int f = (ew & 3) * 32 + lane;   // 0..127
+      const uint32_t foff = (uint32_t)(f >> 5) * 4096u + (uint32_t)(f & 7) * 4u;
+      const uint32_t fchunk = (uint32_t)((f & 31) >> 3);
+      float acc = 0.f;
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % stages;
+        const uint32_t ph = (i / stages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        const uint8_t* sa = ring + (size_t)s * stage_bytes;
+#pragma unroll
+        for (int r = 0; r < TC_BLOCK_K; ++r)
+          acc += *(const float*)(sa + foff + (uint32_t)r * 128u + ((fchunk ^ (uint32_t)(r & 3)) << 5));
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty_bar[s])) : "memory");
+      }
+      if (m0 + f < pM) atomicAdd(db_ptr + m0 + f, acc);
+    }
+
     if (num_kb > 0) {
       mbar_wait(tmem_full_bar, 0);
       tcgen05_fence_after();
     }
-    const int row0 = m0 + q * 32;
-    for (int c0 = 0; c0 < block_n; c0 += 32) {
+    // The tile ring is idle now; slot(c, q) = 4 KB staging buffer of (column chunk c, row group q).
+    if (MODE == TC_DGRAD && act != RSLRL_ACT_IDENTITY && row0 < pM) {
+      // fetch this warp's H sub-tiles (saved activations) with TMA into their slots
+      if (lane == 0) {
+        int nmine = 0;
+        for (int c = half; c < nchunks; c += 2) ++nmine;
+        if (nmine > 0) {
+          mbar_expect_tx(&h_bar[ew], (uint32_t)nmine * 4096u);
+          for (int c = half; c < nchunks; c += 2)
+            tma_load_2d(ring + (size_t)(c * 4 + q) * 4096, map_h, &h_bar[ew], n0 + c * 32, row0);
+        }
+      }
+      __syncwarp();
+      if (half < nchunks) mbar_wait(&h_bar[ew], 0);
+    }
+
+    for (int c = half; c < nchunks; c += 2) {
+      const int c0 = c * 32;
       const int ncols = min(32, block_n - c0);
       uint32_t v[32];
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
@@ -299,36 +373,77 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0u;
       }
-      // registers (lane = row) -> smem, so that the global access below has lane = column
+      if (ncols < 32) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        if (j < ncols) {
-          float x = __uint_as_float(v[j]);
-          if (MODE == TC_FWD) x = act_forward(P.act, x + s_bias[c0 + j]);
-          st[lane * 33 + j] = x;
-        }
+        for (int j = 16; j < 32; ++j) v[j] = 0u;
       }
-      __syncwarp();
-      const int col = n0 + c0 + lane;
-      const bool col_ok = lane < ncols && col < P.N;
-      float colsum = 0.f;
-      for (int r = 0; r < 32; ++r) {
-        const int row = row0 + r;
-        if (row >= P.M) break;
-        if (col_ok) {
-          float x = st[r * 33 + lane];
-          float* dst = P.C + (size_t)row * P.ldc + col;
-          if (MODE == TC_DGRAD) {
-            if (P.act != RSLRL_ACT_IDENTITY) x *= act_grad_from_output(P.act, __ldg(P.H + (size_t)row * P.ldh + col));
-            colsum += x;
+      float x[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+
+      uint8_t* slot = ring + (size_t)(c * 4 + q) * 4096;
+      uint8_t* my_row = slot + lane * 128;
+      const uint32_t sw = (uint32_t)(lane & 7);  // 128-byte swizzle: 16-byte unit u lives at u ^ (row & 7)
+
+      if (MODE == TC_FWD) {
+        if (act == RSLRL_ACT_ELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = elu_fast(x[j] + s_bias[c0 + j]);
+        } else if (act == RSLRL_ACT_IDENTITY) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = x[j] + s_bias[c0 + j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = act_forward(act, x[j] + s_bias[c0 + j]);
+        }
+      } else if (MODE == TC_DGRAD) {
+        if (act != RSLRL_ACT_IDENTITY && row0 + lane < pM) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float4 h = *(const float4*)(my_row + ((u ^ sw) << 4));
+            if (act == RSLRL_ACT_ELU) {
+              x[4 * u + 0] *= h.x > 0.f ? 1.f : h.x + 1.f;
+              x[4 * u + 1] *= h.y > 0.f ? 1.f : h.y + 1.f;
+              x[4 * u + 2] *= h.z > 0.f ? 1.f : h.z + 1.f;
+              x[4 * u + 3] *= h.w > 0.f ? 1.f : h.w + 1.f;
+            } else {
+              x[4 * u + 0] *= act_grad_from_output(act, h.x);
+              x[4 * u + 1] *= act_grad_from_output(act, h.y);
+              x[4 * u + 2] *= act_grad_from_output(act, h.z);
+              x[4 * u + 3] *= act_grad_from_output(act, h.w);
+            }
           }
-          if (MODE == TC_WGRAD) atomicAdd(dst, x);
-          else *dst = x;
         }
       }
-      if (MODE == TC_DGRAD && P.db_prev != nullptr && col_ok) atomicAdd(P.db_prev + col, colsum);
-      __syncwarp();
+
+      if (tma_out) {
+        // registers -> swizzled staging slot (conflict-free 16-byte stores) -> one bulk tensor store per 32x32 block
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          *(float4*)(my_row + ((u ^ sw) << 4)) = make_float4(x[4 * u], x[4 * u + 1], x[4 * u + 2], x[4 * u + 3]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0 && row0 < pM) {
+          if (MODE == TC_WGRAD) tma_reduce_add_2d(map_c, slot, n0 + c0, row0);
+          else tma_store_2d(map_c, slot, n0 + c0, row0);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      } else {
+        // outputs whose row pitch TMA cannot describe (e.g. the [M,1] value head): direct stores
+        const int row = row0 + lane;
+        if (row < pM) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = n0 + c0 + j;
+            if (j < ncols && col < pN) {
+              if (MODE == TC_WGRAD) atomicAdd(Cptr + (size_t)row * ldc + col, x[j]);
+              else Cptr[(size_t)row * ldc + col] = x[j];
+            }
+          }
+        }
+      }
     }
+    if (tma_out && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem may be released
     tcgen05_fence_before();
   }
 
@@ -338,6 +453,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
 }
+
+int colsum_accumulate(const float* x, int M, int N, int ld, float* out, cudaStream_t st);
 
 // -------------------------------------------------------------------------------------------- host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -358,8 +475,10 @@ static EncodeTiledFn encode_fn() {
 }
 
 // 2-D fp32 tensor [rows, cols] with row pitch ld (elements); box {box_cols, box_rows}.
+// operand = true : MMA operand, encoded as TFLOAT32 so that TMA rounds fp32 -> tf32 to nearest on the way in
+// operand = false: plain fp32 tile (epilogue output / saved activation), no conversion
 static bool make_map(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_cols,
-                     int box_rows, bool atom32) {
+                     int box_rows, bool atom32, bool operand = true) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -367,8 +486,10 @@ static bool make_map(CUtensorMap* map, const float* base, long long rows, long l
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   static const int dtype_sel = [] { const char* e = getenv("RSLRL_TMA_DTYPE"); return e ? atoi(e) : 1; }();  // default: TFLOAT32 = TMA rounds fp32 -> tf32 to nearest (measured: profiles/experiments)
-  const CUtensorMapDataType dt = dtype_sel == 1 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32
-                               : dtype_sel == 2 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32_FTZ : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const CUtensorMapDataType dt = !operand          ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : dtype_sel == 1 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32
+                                 : dtype_sel == 2 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32_FTZ
+                                                  : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   CUresult r = fn(map, dt, 2, (void*)base, dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE,
                   atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
@@ -379,7 +500,7 @@ static bool make_map(CUtensorMap* map, const float* base, long long rows, long l
 static bool tma_ok(const void* p, long long ld) { return ((uintptr_t)p & 15) == 0 && (ld % 4) == 0; }
 
 static int pick_block_n(int N) {
-  if (N >= 256) return 256;
+  if (N >= TC_MAX_BLOCK_N) return TC_MAX_BLOCK_N;
   int b = (N + 31) / 32 * 32;  // MN-major operands come in 32-element atoms; keep it simple for K-major too
   if (N <= 16) b = 16;
   return b;
@@ -389,9 +510,7 @@ static size_t smem_bytes_for(int block_n) {
   const size_t stage = (size_t)(TC_BLOCK_M + block_n) * TC_BLOCK_K * 4;
   size_t stages = TC_SMEM_BUDGET / stage;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
-  size_t need = stages * stage + (2 * TC_MAX_STAGES + 1) * 8 + 16 + 256 * 4;
-  const size_t epi = 4 * 32 * 33 * 4;
-  if (need < epi) need = epi;
+  const size_t need = stages * stage + (2 * TC_MAX_STAGES + 1 + TC_EPI_WARPS) * 8 + 16 + 256 * 4;
   return need + 1024;  // slack for the manual 1024-byte alignment
 }
 
@@ -436,6 +555,7 @@ int tc_linear_forward(int n, const rslrl_linear_fwd_t* pr, cudaStream_t st) {
       return 1;
     }
     P.C = q.y; P.bias = q.b; P.M = q.M; P.N = q.N; P.K = q.K; P.ldc = q.ldy; P.act = q.act;
+    P.tma_out = tma_ok(q.y, q.ldy) && make_map(&P.map_c, q.y, q.M, q.N, q.ldy, 32, 32, false, false);
     P.tiles_m = (q.M + TC_BLOCK_M - 1) / TC_BLOCK_M;
     P.tiles_n = (q.N + P.block_n - 1) / P.block_n;
     P.num_kb = (q.K + TC_BLOCK_K - 1) / TC_BLOCK_K;
@@ -453,21 +573,32 @@ int tc_linear_backward_data(int n, const rslrl_linear_bwd_data_t* pr, cudaStream
     // dX[M,K] = dY[M,N] W[N,K]: reduction N; B = W is MN-major (K contiguous) -> K must be whole 32-atoms
     if (!tma_ok(q.dy, q.ldy) || !tma_ok(q.w, q.K) || (q.K % 32) != 0) return -1;
     TcProblem& P = b.p[i];
-    P.block_n = q.K >= 256 ? 256 : q.K;
+    P.block_n = q.K >= TC_MAX_BLOCK_N ? TC_MAX_BLOCK_N : q.K;
     if (q.K % P.block_n != 0) return -1;
     if (!make_map(&P.map_a, q.dy, q.M, q.N, q.ldy, TC_BLOCK_K, TC_BLOCK_M, false) ||
         !make_map(&P.map_b, q.w, q.N, q.K, q.K, 32, TC_BLOCK_K, true)) {
       set_error("%s: cuTensorMapEncodeTiled failed", what);
       return 1;
     }
-    P.C = q.dx; P.H = q.h; P.db_prev = q.db_prev;
-    P.M = q.M; P.N = q.K; P.K = q.N; P.ldc = q.ldx; P.ldh = q.ldh; P.act = q.act;
+    P.C = q.dx; P.M = q.M; P.N = q.K; P.K = q.N; P.ldc = q.ldx; P.act = q.act;
+    if (!tma_ok(q.dx, q.ldx)) return -1;
+    if (q.act != RSLRL_ACT_IDENTITY && !tma_ok(q.h, q.ldh)) return -1;
+    if (!make_map(&P.map_c, q.dx, q.M, q.K, q.ldx, 32, 32, false, false) ||
+        (q.act != RSLRL_ACT_IDENTITY && !make_map(&P.map_h, q.h, q.M, q.K, q.ldh, 32, 32, false, false))) {
+      set_error("%s: cuTensorMapEncodeTiled failed", what);
+      return 1;
+    }
+    P.tma_out = 1;
     P.tiles_m = (q.M + TC_BLOCK_M - 1) / TC_BLOCK_M;
     P.tiles_n = q.K / P.block_n;
     P.num_kb = (q.N + TC_BLOCK_K - 1) / TC_BLOCK_K;
     P.splits = 1; P.kb_per_split = P.num_kb;
   }
-  return launch_tc<TC_DGRAD>(b, n, st, what);
+  const int rc = launch_tc<TC_DGRAD>(b, n, st, what);
+  if (rc) return rc;
+  for (int i = 0; i < n; ++i)  // optional fused-API output: bias gradient of the previous layer
+    if (pr[i].db_prev && colsum_accumulate(pr[i].dx, pr[i].M, pr[i].K, pr[i].ldx, pr[i].db_prev, st)) return 1;
+  return 0;
 }
 
 int tc_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* pr, cudaStream_t st) {
@@ -494,7 +625,8 @@ int tc_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* pr, cudaSt
       set_error("%s: cuTensorMapEncodeTiled failed", what);
       return 1;
     }
-    P.C = q.dw; P.M = q.N; P.N = q.K; P.K = q.M; P.ldc = q.K;
+    P.C = q.dw; P.db = q.db; P.M = q.N; P.N = q.K; P.K = q.M; P.ldc = q.K;
+    P.tma_out = tma_ok(q.dw, q.K) && make_map(&P.map_c, q.dw, q.N, q.K, q.K, 32, 32, false, false);
     P.num_kb = (q.M + TC_BLOCK_K - 1) / TC_BLOCK_K;
     int want = (2 * kNumSMs + tiles_all - 1) / tiles_all;   // ~2 CTAs worth of work per SM
     int max_s = P.num_kb / 8;                               // at least 8 k-blocks (256 rows) per split

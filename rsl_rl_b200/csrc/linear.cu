@@ -8,7 +8,6 @@ int simt_linear_backward_data(int n, const rslrl_linear_bwd_data_t* pr, cudaStre
 int simt_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* pr, cudaStream_t st);
 int tc_linear_forward(int n, const rslrl_linear_fwd_t* pr, cudaStream_t st);
 int tc_linear_backward_data(int n, const rslrl_linear_bwd_data_t* pr, cudaStream_t st);
-int colsum_accumulate(const float* x, int M, int N, int ld, float* out, cudaStream_t st);
 int tc_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* pr, cudaStream_t st);
 }  // namespace rslrl
 
@@ -64,14 +63,7 @@ int rslrl_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* probs_h
   if (precision == RSLRL_PREC_TF32) {
     const int rc = tc_linear_backward_weight(n, probs_host, (cudaStream_t)stream);
     if (rc < 0) return simt_linear_backward_weight(n, probs_host, (cudaStream_t)stream);
-    if (rc > 0) return rc;
-    // the tensor-core wgrad does not touch db (the fused engine takes bias gradients from the kernels that
-    // produce dy); callers that ask for it here get a column-sum pass
-    for (int i = 0; i < n; ++i) {
-      const rslrl_linear_bwd_weight_t& p = probs_host[i];
-      if (p.db && colsum_accumulate(p.dy, p.M, p.N, p.ldy, p.db, (cudaStream_t)stream)) return 1;
-    }
-    return 0;
+    return rc;
   }
   set_error("%s: unknown precision %d", what, precision);
   return 2;

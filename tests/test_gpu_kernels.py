@@ -224,7 +224,7 @@ def test_linear_backward(M, K, N, act, prec, tol):
     dw = torch.zeros(N, K, device=DEV); db = torch.zeros(N, device=DEV)
     linear_backward_weight([(dy, h, dw, db)], P)
     assert rel_err(dw.cpu().numpy(), (dy.double().T @ h.double()).cpu().numpy()) < tol
-    assert rel_err(db.cpu().numpy(), dy.double().sum(0).cpu().numpy()) < 1e-5
+    assert rel_err(db.cpu().numpy(), dy.double().sum(0).cpu().numpy()) < tol   # tf32: sums the rounded dY tiles
     linear_backward_weight([(dy, h, dw, None)], P)                                  # accumulates; db optional
     assert rel_err(dw.cpu().numpy(), 2 * (dy.double().T @ h.double()).cpu().numpy()) < tol
 
