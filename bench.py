@@ -235,9 +235,18 @@ def run_ours(args):
     device = f"cuda:{local}"
     torch.cuda.set_device(local)
     K, W = args.steps, max(args.warmup, 3)
-    quiet = open(os.devnull, "w")
+    # the modules print their architecture and NCCL prints its version banner on fd 1: keep stdout for the JSON line
+    sys.stdout.flush()
+    saved_fd = os.dup(1)
+    devnull_fd = os.open(os.devnull, os.O_WRONLY)
+    os.dup2(devnull_fd, 1)
     stdout = sys.stdout
-    sys.stdout = quiet  # the modules print their architecture; keep stdout for the JSON line
+    sys.stdout = open(os.devnull, "w")
+
+    def restore_stdout():
+        sys.stdout.flush()
+        sys.stdout = stdout
+        os.dup2(saved_fd, 1)
 
     def barrier():
         torch.cuda.synchronize()
@@ -273,7 +282,7 @@ def run_ours(args):
     value = NUM_ENVS * NUM_STEPS * world * K / (ms * 1e-3)
 
     if args.only_timed:
-        sys.stdout = stdout
+        restore_stdout()
         if rank == 0:
             print(json.dumps(dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W,
                                   ms_per_step=ms / K, gpu_launches=int(launches), clocks=clocks,
@@ -341,9 +350,9 @@ def run_ours(args):
                     phases_ms=dict(phases, iteration=ms / K))
         if cpu is not None:
             line["cpu_baseline"] = cpu
-    sys.stdout = stdout
+    restore_stdout()
     if line is not None:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1 and torch.distributed.is_initialized():
         torch.distributed.destroy_process_group()
 
