@@ -130,7 +130,13 @@ def check(rc: int):
         raise RuntimeError("rsl_rl_b200 native call failed: " + lib().rslrl_last_error().decode())
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream_ptr() -> int:
+    """cudaStream_t of torch's current stream on the current device (the fast C accessor when available)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 

@@ -102,6 +102,46 @@ class FeedForwardEngine:
                 in_c = out
             linear_forward(probs, self.prec)
 
+    # ---- prebuilt launch plans for the rollout: everything static except the observation pointers ---------
+    def build_forward_plan(self, M: int, ld_a: int, ld_c: int, mu_out: torch.Tensor, v_out: torch.Tensor,
+                           actor: bool = True, critic: bool = True):
+        """ctypes launch arrays for `forward` on M rows with outputs fixed; returns a callable(xa_ptr, xc_ptr)."""
+        La, Lc = self.actor.L if actor else 0, self.critic.L if critic else 0
+        launches = []
+        in_a = in_c = None  # layer-0 inputs are patched per call
+        for l in range(max(La, Lc)):
+            specs = []
+            if l < La:
+                lin = self.actor.layers[l]
+                out = mu_out if l == La - 1 else self.h_a[l][:M]
+                specs.append(("a", in_a, lin, out, self.actor.acts[l], ld_a))
+                in_a = out
+            if l < Lc:
+                lin = self.critic.layers[l]
+                out = v_out if l == Lc - 1 else self.h_c[l][:M]
+                specs.append(("c", in_c, lin, out, self.critic.acts[l], ld_c))
+                in_c = out
+            arr = (nat.LinearFwd * len(specs))()
+            patch = []
+            for i, (tag, inp, lin, out, act, ld0) in enumerate(specs):
+                xptr = 0 if inp is None else inp.data_ptr()
+                ldx = ld0 if inp is None else inp.stride(0)
+                arr[i] = nat.LinearFwd(xptr, lin.weight.data_ptr(), lin.bias.data_ptr(), out.data_ptr(), M,
+                                       lin.weight.shape[0], lin.weight.shape[1], ldx, out.stride(0), act)
+                if inp is None:
+                    patch.append((i, tag))
+            launches.append((arr, len(specs), patch))
+        fn, prec, check = nat.lib().rslrl_linear_forward, self.prec, nat.check
+
+        def run(xa_ptr: int, xc_ptr: int):
+            st = nat.stream_ptr()
+            for arr, n, patch in launches:
+                for i, tag in patch:
+                    arr[i].x = xa_ptr if tag == "a" else xc_ptr
+                check(fn(n, arr, prec, st))
+
+        return run
+
     def backward(self, x_a: torch.Tensor, x_c: torch.Tensor, dmu: torch.Tensor, dvalue: torch.Tensor):
         """dL/dW, dL/db accumulated into the parameters' .grad views (flat gradient buffer)."""
         M = x_a.shape[0]

@@ -140,6 +140,7 @@ class PPO:
         self._graph_key = None
         self._graph_launches = 0
         self._eager_updates = 0
+        self._act_plans = {}
         self._mb_hook = None  # test hook: called after every minibatch backward in eager mode
         self.last_update_info = {}
 
@@ -175,15 +176,22 @@ class PPO:
         s = st.step
         if s >= st.num_transitions_per_env:
             raise OverflowError("Rollout buffer overflow! You should call clear() before adding new transitions.")
-        self._group.ensure_bound()
         x_a, x_c = self._inputs(obs)
-        nat.require_cuda(x_a, x_c)
-        eng.forward(x_a, x_c, st.mu[s], st.values[s])
-        z = self.policy.draw_noise(st.mu[s])
-        eng.gaussian_head(st.mu[s], z, st.actions[s], st.actions_log_prob[s], st.sigma[s])
-        tr.actions, tr.values = st.actions[s], st.values[s]
-        tr.actions_log_prob = st.actions_log_prob[s].view(-1)
-        tr.action_mean, tr.action_sigma = st.mu[s], st.sigma[s]
+        plan = self._act_plans.get(s)
+        if plan is None or plan[0] != (x_a.stride(0), x_c.stride(0), self._group.values.data_ptr()):
+            self._group.ensure_bound()
+            nat.require_cuda(x_a, x_c)
+            views = (st.mu[s], st.values[s], st.actions[s], st.actions_log_prob[s], st.sigma[s])
+            fwd = eng.build_forward_plan(st.num_envs, x_a.stride(0), x_c.stride(0), views[0], views[1])
+            plan = ((x_a.stride(0), x_c.stride(0), self._group.values.data_ptr()), fwd, views)
+            self._act_plans[s] = plan
+        _, fwd, (mu_s, val_s, act_s, logp_s, sig_s) = plan
+        fwd(x_a.data_ptr(), x_c.data_ptr())
+        z = self.policy.draw_noise(mu_s)
+        eng.gaussian_head(mu_s, z, act_s, logp_s, sig_s)
+        tr.actions, tr.values = act_s, val_s
+        tr.actions_log_prob = logp_s.view(-1)
+        tr.action_mean, tr.action_sigma = mu_s, sig_s
         tr.observations = obs
         self.policy._mean, self.policy._std = tr.action_mean, tr.action_sigma
         return tr.actions
@@ -213,7 +221,10 @@ class PPO:
             self.intrinsic_rewards = self.rnd.get_intrinsic_reward(obs)
             intrinsic = self.intrinsic_rewards
         time_outs = extras["time_outs"] if "time_outs" in extras else None
-        self.storage._store(tr, time_outs=time_outs, intrinsic=intrinsic, gamma=self.gamma)
+        if self.fused and tr.actions is not None and tr.actions.data_ptr() == self.storage.actions[self.storage.step].data_ptr():
+            self.storage._store_in_place(tr.observations, rewards, dones, time_outs, intrinsic, self.gamma)
+        else:
+            self.storage._store(tr, time_outs=time_outs, intrinsic=intrinsic, gamma=self.gamma)
         tr.clear()
         self.policy.reset(dones)
 

@@ -76,6 +76,7 @@ class RolloutStorage:
         self.saved_hidden_states_c = None
         self.step = 0
 
+        self._store_plans = {}
         self._gae_ws = torch.empty(int(nat.lib().rslrl_gae_workspace_bytes(N)), dtype=torch.uint8, device=device)
         # hooks used by the parity tests to inject a recorded permutation
         self._randperm = lambda n: torch.randperm(n, requires_grad=False, device=self.device)
@@ -131,6 +132,38 @@ class RolloutStorage:
             self.actions_log_prob[s].data_ptr(), self.rewards[s].data_ptr(), self.dones[s].data_ptr(), N, A,
             nat.stream_ptr()))
         self._save_hidden_states(tr.hidden_states)
+        self.step += 1
+
+    def _store_in_place(self, obs, rewards, dones, time_outs=None, intrinsic=None, gamma: float = 0.0):
+        """Fast path of `_store` for PPO's fused rollout: actions / mean / sigma / value / log-prob of this step
+        were already written into row `step` by `PPO.act`, so only observations, rewards (with the bootstrap)
+        and dones move.  Argument arrays are built once per step index and patched with the source pointers."""
+        s = self.step
+        if s >= self.num_transitions_per_env:
+            raise OverflowError("Rollout buffer overflow! You should call clear() before adding new transitions.")
+        plan = self._store_plans.get(s)
+        if plan is None:
+            dsts = [self.observations[k][s] for k in self._obs_keys]
+            plan = (nat.void_array([0] * len(dsts)), nat.void_array([d.data_ptr() for d in dsts]),
+                    nat.int_array([int(d[0].numel()) for d in dsts]), self.values[s].data_ptr(),
+                    self.rewards[s].data_ptr(), self.dones[s].data_ptr())
+            self._store_plans[s] = plan
+        src_arr, dst_arr, dim_arr, values_ptr, rew_row, done_row = plan
+        for i, k in enumerate(self._obs_keys):
+            src_arr[i] = nat.f32c(obs[k]).data_ptr()
+        rewards = nat.f32c(rewards)
+        dones, dcode = nat.flag_tensor(dones)
+        to_ptr, tcode = None, 0
+        if time_outs is not None:
+            if time_outs.device != rewards.device:
+                time_outs = time_outs.to(rewards.device)
+            time_outs, tcode = nat.flag_tensor(time_outs)
+            to_ptr = time_outs.data_ptr()
+        intr = None if intrinsic is None else nat.f32c(intrinsic).data_ptr()
+        nat.check(nat.lib().rslrl_store_transition(
+            len(self._obs_keys), src_arr, dst_arr, dim_arr, None, None, None, 0, values_ptr, None,
+            rewards.data_ptr(), dones.data_ptr(), dcode, to_ptr, tcode, intr, float(gamma), None, None, None, None, None,
+            rew_row, done_row, self.num_envs, self._A, nat.stream_ptr()))
         self.step += 1
 
     def _save_hidden_states(self, hidden_states):
