@@ -166,7 +166,8 @@ def _storage_arrays(storage):
 # ---------------------------------------------------------------------------------------------
 
 def scenario_ppo_mlp(out_dir, name, *, num_envs, num_steps, group_dims, obs_groups, num_actions, hidden,
-                     activation, noise_std_type, alg_overrides, iterations, seed=0, p_done=0.1):
+                     activation, noise_std_type, alg_overrides, iterations, seed=0, p_done=0.1,
+                     policy_class="ActorCritic", policy_extra=None, rnd_cfg=None, symmetry=False):
     import torch
     from rsl_rl.runners import OnPolicyRunner
 
@@ -178,21 +179,35 @@ def scenario_ppo_mlp(out_dir, name, *, num_envs, num_steps, group_dims, obs_grou
                desired_kl=0.01, entropy_coef=0.01, gamma=0.99, lam=0.95, max_grad_norm=1.0,
                normalize_advantage_per_mini_batch=False)
     alg.update(alg_overrides)
+    alg_run = dict(alg)
+    if rnd_cfg is not None:
+        alg_run["rnd_cfg"] = dict(rnd_cfg)
+    if symmetry:
+        sys.path.insert(0, os.path.join(HERE, ".."))
+        from oracle.symmetry_example import mirror_augmentation
+        alg_run["symmetry_cfg"] = dict(use_data_augmentation=True, use_mirror_loss=True, mirror_loss_coeff=0.5,
+                                       data_augmentation_func=mirror_augmentation)
     cfg = dict(num_steps_per_env=num_steps, save_interval=10 ** 9, obs_groups={k: list(v) for k, v in obs_groups.items()},
-               policy=dict(class_name="ActorCritic", actor_hidden_dims=list(hidden), critic_hidden_dims=list(hidden),
-                           activation=activation, init_noise_std=1.0, noise_std_type=noise_std_type),
-               algorithm=dict(alg))
+               policy=dict(class_name=policy_class, actor_hidden_dims=list(hidden), critic_hidden_dims=list(hidden),
+                           activation=activation, init_noise_std=1.0, noise_std_type=noise_std_type,
+                           **(policy_extra or {})),
+               algorithm=alg_run)
     data = {}
     meta = dict(num_envs=num_envs, num_steps=num_steps, num_actions=num_actions, hidden=list(hidden),
                 activation=activation, noise_std_type=noise_std_type, iterations=iterations,
                 obs_groups={k: list(v) for k, v in obs_groups.items()}, group_dims=dict(group_dims),
-                alg={k: v for k, v in alg.items() if k != "class_name"})
+                alg={k: v for k, v in alg.items() if k != "class_name"}, policy_class=policy_class,
+                policy_extra=dict(policy_extra or {}), rnd_cfg=None if rnd_cfg is None else dict(rnd_cfg),
+                symmetry=bool(symmetry))
     with Recorder() as rec:
         runner = OnPolicyRunner(env, cfg, log_dir=tempfile.mkdtemp(prefix="golden_"), device="cpu")
         rec.watch_optimizer(runner.alg.optimizer, runner.alg.policy)
         for k, v in _state_arrays(runner.alg.policy).items():
             data[f"init.{k}"] = v
         meta["param_names"] = [k for k, _ in runner.alg.policy.named_parameters()]
+        if runner.alg.rnd:
+            for k, v in _state_arrays(runner.alg.rnd).items():
+                data[f"init_rnd.{k}"] = v
         for it in range(iterations):
             n_norm, n_perm, n_clip, n_step = len(rec.normal_z), len(rec.perms), len(rec.clip_calls), len(rec.step_calls)
             first_obs = len(env.obs_log) - 1
@@ -208,9 +223,10 @@ def scenario_ppo_mlp(out_dir, name, *, num_envs, num_steps, group_dims, obs_grou
             data[p + "stream.time_outs"] = np.stack(env.to_log[first_step:first_step + T])
             zs = rec.normal_z[n_norm:]
             data[p + "z_rollout"] = np.stack(zs[:T])                 # [T,N,A]
-            data[p + "z_update_shapes"] = np.array([z.shape for z in zs[T:]])  # discarded draws (ppo.py:249)
-            assert len(rec.perms) == n_perm + 1
-            data[p + "perm"] = rec.perms[-1]
+            data[p + "z_update_count"] = np.array(len(zs[T:]))        # discarded draws (ppo.py:249)
+            if policy_class == "ActorCritic":
+                assert len(rec.perms) == n_perm + 1
+                data[p + "perm"] = rec.perms[-1]
             for k, v in _storage_arrays(runner.alg.storage).items():
                 data[p + "storage." + k] = v
             clips = rec.clip_calls[n_clip:]
@@ -221,6 +237,14 @@ def scenario_ppo_mlp(out_dir, name, *, num_envs, num_steps, group_dims, obs_grou
             data[p + "mb.params_after"] = np.stack([s[1] for s in steps])
             for k, v in _state_arrays(runner.alg.policy).items():
                 data[p + f"final.{k}"] = v
+            if runner.alg.rnd:
+                for k, v in _state_arrays(runner.alg.rnd).items():
+                    data[p + f"final_rnd.{k}"] = v
+            if runner.alg.storage.saved_hidden_states_a is not None:
+                for i, h in enumerate(runner.alg.storage.saved_hidden_states_a):
+                    data[p + f"storage.hidden_a{i}"] = h.numpy().copy()
+                for i, h in enumerate(runner.alg.storage.saved_hidden_states_c):
+                    data[p + f"storage.hidden_c{i}"] = h.numpy().copy()
             ost = runner.alg.optimizer.state_dict()["state"]
             data[p + "adam.exp_avg"] = np.concatenate([ost[i]["exp_avg"].numpy().reshape(-1) for i in range(len(ost))])
             data[p + "adam.exp_avg_sq"] = np.concatenate([ost[i]["exp_avg_sq"].numpy().reshape(-1) for i in range(len(ost))])
@@ -415,6 +439,19 @@ def main():
             alg_overrides=dict(use_clipped_value_loss=False, num_learning_epochs=3, num_mini_batches=2,
                                learning_rate=3e-4, max_grad_norm=0.5), iterations=1, seed=4),
     }
+    todo["ppo_lstm_small"] = lambda: scenario_ppo_mlp(
+        args.out, "ppo_lstm_small", num_envs=32, num_steps=8, group_dims={"policy": 10},
+        obs_groups={"policy": ["policy"], "critic": ["policy"]}, num_actions=3, hidden=[24, 12],
+        activation="elu", noise_std_type="scalar", alg_overrides=dict(num_learning_epochs=2), iterations=2, seed=7,
+        p_done=0.15, policy_class="ActorCriticRecurrent",
+        policy_extra=dict(rnn_type="lstm", rnn_hidden_dim=16, rnn_num_layers=1))
+    todo["ppo_rnd_sym_small"] = lambda: scenario_ppo_mlp(
+        args.out, "ppo_rnd_sym_small", num_envs=48, num_steps=6, group_dims={"policy": 11},
+        obs_groups={"policy": ["policy"], "critic": ["policy"]}, num_actions=4, hidden=[24, 12],
+        activation="elu", noise_std_type="scalar", alg_overrides=dict(num_learning_epochs=2), iterations=2, seed=8,
+        rnd_cfg=dict(weight=1.0, weight_schedule=None, reward_normalization=False, state_normalization=False,
+                     learning_rate=1e-3, num_outputs=1, predictor_hidden_dims=[-1], target_hidden_dims=[-1]),
+        symmetry=True)
     for name, fn in todo.items():
         if args.only in (None, name):
             fn()

@@ -383,8 +383,125 @@ class PPO:
     # update: composite path (recurrent / RND / symmetry)
     # ------------------------------------------------------------------------------------------
     def _update_composite(self):
-        raise NotImplementedError(
-            f"PPO.update: the fused engine does not cover this configuration yet ({self._engine_reason}).")
+        """PPO.update for recurrent policies, RND and symmetry augmentation (reference ppo.py:178-422).
+
+        Same kernels for the dense layers (through autograd), the rollout buffer, GAE, the trajectory
+        split/pad/unpad and the flat-buffer clip + KL-adaptive LR + Adam; the objective itself is expressed with
+        tensor algebra under autograd.  The KL goes to the device-side LR rule through the gradient tail slot, so
+        this path has no per-minibatch host synchronisation either."""
+        pol, st, opt = self.policy, self.storage, self.optimizer
+        M, E = self.num_mini_batches, self.num_learning_epochs
+        gen = (st.recurrent_mini_batch_generator(M, E) if pol.is_recurrent else st.mini_batch_generator(M, E))
+        sums = torch.zeros(5, dtype=torch.float64, device=self.device)  # value, surrogate, entropy, rnd, symmetry
+        self._group.ensure_bound()
+        self._group.zero_grad()
+        if self.rnd:
+            self._rnd_group.ensure_bound()
+            self._rnd_group.zero_grad()
+            self.rnd_optimizer.dev_state.set_lr(self.rnd_optimizer.param_groups[0]["lr"])
+        opt.dev_state.set_lr(self.learning_rate)
+        adaptive = self.desired_kl is not None and self.schedule == "adaptive"
+        clip = self.clip_param
+
+        for (obs_b, actions_b, target_values_b, adv_b, returns_b, old_logp_b, old_mu_b, old_sigma_b, hid_b,
+             masks_b) in gen:
+            num_aug = 1
+            original_batch_size = obs_b.batch_size[0]
+            if self.normalize_advantage_per_mini_batch:
+                with torch.no_grad():
+                    adv_b = (adv_b - adv_b.mean()) / (adv_b.std() + 1e-8)
+            if self.symmetry and self.symmetry["use_data_augmentation"]:
+                aug = self.symmetry["data_augmentation_func"]
+                obs_b, actions_b = aug(obs=obs_b, actions=actions_b, env=self.symmetry["_env"])
+                num_aug = int(obs_b.batch_size[0] / original_batch_size)
+                old_logp_b = old_logp_b.repeat(num_aug, 1)
+                target_values_b = target_values_b.repeat(num_aug, 1)
+                adv_b = adv_b.repeat(num_aug, 1)
+                returns_b = returns_b.repeat(num_aug, 1)
+
+            pol.act(obs_b, masks=masks_b, hidden_states=hid_b[0])  # also draws the sample the reference discards
+            logp = pol.get_actions_log_prob(actions_b)
+            value = pol.evaluate(obs_b, masks=masks_b, hidden_states=hid_b[1])
+            mu_b = pol.action_mean[:original_batch_size]
+            sigma_b = pol.action_std[:original_batch_size]
+            entropy_b = pol.entropy[:original_batch_size]
+
+            if adaptive:
+                with torch.no_grad():
+                    kl = torch.sum(torch.log(sigma_b / old_sigma_b + 1.0e-5)
+                                   + (torch.square(old_sigma_b) + torch.square(old_mu_b - mu_b))
+                                   / (2.0 * torch.square(sigma_b)) - 0.5, dim=-1)
+                    self._group.kl_slot.copy_(kl.mean().reshape(1))
+
+            adv = torch.squeeze(adv_b)
+            ratio = torch.exp(logp - torch.squeeze(old_logp_b))
+            surrogate_loss = torch.max(-adv * ratio, -adv * torch.clamp(ratio, 1.0 - clip, 1.0 + clip)).mean()
+            if self.use_clipped_value_loss:
+                value_clipped = target_values_b + (value - target_values_b).clamp(-clip, clip)
+                value_loss = torch.max((value - returns_b).pow(2), (value_clipped - returns_b).pow(2)).mean()
+            else:
+                value_loss = (returns_b - value).pow(2).mean()
+            entropy_mean = entropy_b.mean()
+            loss = surrogate_loss + self.value_loss_coef * value_loss - self.entropy_coef * entropy_mean
+
+            symmetry_loss = None
+            if self.symmetry:
+                aug = self.symmetry["data_augmentation_func"]
+                if not self.symmetry["use_data_augmentation"]:
+                    obs_b, _ = aug(obs=obs_b, actions=None, env=self.symmetry["_env"])
+                    num_aug = int(obs_b.shape[0] / original_batch_size)
+                mean_actions = pol.act_inference(obs_b.detach().clone())
+                _, actions_mean_symm = aug(obs=None, actions=mean_actions[:original_batch_size],
+                                           env=self.symmetry["_env"])
+                symmetry_loss = torch.nn.functional.mse_loss(mean_actions[original_batch_size:],
+                                                             actions_mean_symm.detach()[original_batch_size:])
+                if self.symmetry["use_mirror_loss"]:
+                    loss = loss + self.symmetry["mirror_loss_coeff"] * symmetry_loss
+                else:
+                    symmetry_loss = symmetry_loss.detach()
+
+            rnd_loss = None
+            if self.rnd:
+                with torch.no_grad():
+                    rnd_state = self.rnd.state_normalizer(self.rnd.get_rnd_state(obs_b[:original_batch_size]))
+                rnd_loss = torch.nn.functional.mse_loss(self.rnd.predictor(rnd_state), self.rnd.target(rnd_state).detach())
+
+            loss.backward()           # accumulates into the (zeroed) flat gradient views
+            if self.rnd:
+                rnd_loss.backward()
+            if self.is_multi_gpu:
+                torch.distributed.all_reduce(self._group.grads_ext, op=torch.distributed.ReduceOp.SUM)
+                if self.rnd:
+                    torch.distributed.all_reduce(self._rnd_group.grads_ext, op=torch.distributed.ReduceOp.SUM)
+            opt.fused_step(world_size=self.gpu_world_size, max_grad_norm=self.max_grad_norm, adaptive=adaptive,
+                           desired_kl=self.desired_kl or 0.0, round_lr_fp32=self.is_multi_gpu, use_kl=adaptive)
+            if self.rnd:  # the reference neither clips the RND gradients nor adapts their learning rate
+                self.rnd_optimizer.fused_step(world_size=self.gpu_world_size, max_grad_norm=0.0, use_kl=False)
+
+            with torch.no_grad():
+                sums[0] += value_loss.detach()
+                sums[1] += surrogate_loss.detach()
+                sums[2] += entropy_mean.detach()
+                if rnd_loss is not None:
+                    sums[3] += rnd_loss.detach()
+                if symmetry_loss is not None:
+                    sums[4] += symmetry_loss.detach()
+
+        n = E * M
+        info = opt.dev_state.read()
+        host = (sums / n).cpu().tolist()
+        self.learning_rate = info["lr"]
+        opt.sync_host_state(self.learning_rate)
+        if self.rnd:
+            self.rnd_optimizer.sync_host_state(self.rnd_optimizer.param_groups[0]["lr"])
+        self.last_update_info = info
+        st.clear()
+        loss_dict = {"value_function": host[0], "surrogate": host[1], "entropy": host[2]}
+        if self.rnd:
+            loss_dict["rnd"] = host[3]
+        if self.symmetry:
+            loss_dict["symmetry"] = host[4]
+        return loss_dict
 
     # ------------------------------------------------------------------------------------------
     # multi-GPU helpers (reference ppo.py:428-469)

@@ -36,8 +36,9 @@ class Memory(nn.Module):
         elif self.hidden_states is not None:
             if hidden_states is None:
                 states = self.hidden_states if isinstance(self.hidden_states, tuple) else (self.hidden_states,)
-                for h in states:
-                    h[..., dones == 1, :] = 0.0
+                done = (dones == 1).view(1, -1, 1)  # masked_fill_: same result as h[..., dones == 1, :] = 0 without
+                for h in states:                     # the host synchronisation of boolean-mask indexing
+                    h.masked_fill_(done, 0.0)
             else:
                 raise NotImplementedError(
                     "Resetting hidden states of done environments with custom hidden states is not implemented")

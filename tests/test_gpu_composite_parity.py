@@ -1,0 +1,86 @@
+"""GPU: the configurations that go through PPO._update_composite -- recurrent policy (LSTM memory,
+recurrent_mini_batch_generator, split/pad/unpad) and RND + symmetry augmentation + mirror loss (C5) -- against
+golden traces recorded from the unmodified reference (oracle/make_golden.py)."""
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+from tests.golden_util import load, meta_of, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _runner_from_golden(g, meta):
+    from oracle.symmetry_example import mirror_augmentation
+    from rsl_rl_b200.env import ReplayVecEnv
+    from rsl_rl_b200.runners import OnPolicyRunner
+    T, iters = meta["num_steps"], meta["iterations"]
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    obs = {k: t(np.concatenate([g[f"it{i}.stream.obs.{k}"][:T + (i == iters - 1)] for i in range(iters)]))
+           for k in meta["group_dims"]}
+    cat = lambda key: t(np.concatenate([g[f"it{i}.stream.{key}"] for i in range(iters)]))
+    env = ReplayVecEnv(obs, cat("rewards"), cat("dones"), cat("time_outs"), meta["num_actions"], device=DEV)
+    alg = dict(meta["alg"], class_name="PPO", use_cuda_graph=False)
+    if meta["rnd_cfg"] is not None:
+        alg["rnd_cfg"] = dict(meta["rnd_cfg"])
+    if meta["symmetry"]:
+        alg["symmetry_cfg"] = dict(use_data_augmentation=True, use_mirror_loss=True, mirror_loss_coeff=0.5,
+                                   data_augmentation_func=mirror_augmentation)
+    cfg = dict(num_steps_per_env=T, save_interval=10 ** 9, obs_groups={k: list(v) for k, v in meta["obs_groups"].items()},
+               policy=dict(class_name=meta["policy_class"], actor_hidden_dims=list(meta["hidden"]),
+                           critic_hidden_dims=list(meta["hidden"]), activation=meta["activation"], init_noise_std=1.0,
+                           noise_std_type=meta["noise_std_type"], **meta["policy_extra"]),
+               algorithm=alg)
+    runner = OnPolicyRunner(env, cfg, log_dir=None, device=DEV)
+    sd = {k[len("init."):]: t(g[k]).to(DEV) for k in g.files if k.startswith("init.")}
+    runner.alg.policy.load_state_dict(sd)
+    if runner.alg.rnd:
+        runner.alg.rnd.load_state_dict({k[len("init_rnd."):]: t(g[k]).to(DEV) for k in g.files if k.startswith("init_rnd.")})
+    assert not runner.alg.fused
+    return runner
+
+
+@pytest.mark.parametrize("name", ["ppo_lstm_small", "ppo_rnd_sym_small"])
+def test_composite_learn_iterations_match_reference_golden(name):
+    torch.backends.cudnn.allow_tf32 = False   # the fp32 parity class
+    g = load(name)
+    meta = meta_of(g)
+    runner = _runner_from_golden(g, meta)
+    alg, st = runner.alg, runner.alg.storage
+    for it in range(meta["iterations"]):
+        p = f"it{it}."
+        zq = [torch.from_numpy(z).to(DEV) for z in g[p + "z_rollout"]]
+        alg.policy._noise_fn = lambda like, q=zq: q.pop(0) if q else torch.zeros_like(like)
+        if p + "perm" in g.files:
+            perm = torch.from_numpy(g[p + "perm"]).to(DEV)
+            st._randperm = lambda n, perm=perm: perm
+        snap = {}
+        orig_update = alg.update
+
+        def update_and_snapshot():
+            for k in ("actions", "values", "actions_log_prob", "mu", "sigma", "rewards", "dones", "returns", "advantages"):
+                snap[k] = getattr(st, k).cpu().numpy().copy()
+            if st.saved_hidden_states_a is not None:
+                snap["hidden_a0"] = st.saved_hidden_states_a[0].cpu().numpy().copy()
+                snap["hidden_c1"] = st.saved_hidden_states_c[1].cpu().numpy().copy()
+            return orig_update()
+
+        alg.update = update_and_snapshot
+        runner.learn(1)
+        alg.update = orig_update
+        assert np.array_equal(snap["dones"], g[p + "storage.dones"])
+        for k in ("mu", "actions", "values", "actions_log_prob", "rewards", "returns", "advantages"):
+            assert rel_err(snap[k], g[p + "storage." + k]) < 2e-5, (it, k)
+        if "hidden_a0" in snap:
+            assert rel_err(snap["hidden_a0"], g[p + "storage.hidden_a0"]) < 2e-5
+            assert rel_err(snap["hidden_c1"], g[p + "storage.hidden_c1"]) < 2e-5
+        mine = torch.cat([q.detach().reshape(-1) for q in alg.policy.parameters()]).cpu().numpy()
+        assert abs(alg.learning_rate - float(g[p + "learning_rate"])) < 1e-15, it
+        assert rel_err(mine, g[p + "mb.params_after"][-1]) < 5e-5, it
+        if alg.rnd:
+            for k, v in alg.rnd.state_dict().items():
+                assert rel_err(v.cpu().numpy(), g[p + "final_rnd." + k]) < 5e-5, k
+        assert alg.last_update_info["step"] == int(g[p + "adam.step"])
