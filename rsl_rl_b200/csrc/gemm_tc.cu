@@ -179,7 +179,13 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const 
 }
 
 // fast activations for the tf32 path (errors << tf32 rounding)
-__device__ __forceinline__ float elu_fast(float z) { return z > 0.f ? z : __expf(z) - 1.f; }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// ELU(z) = z > 0 ? z : exp(z) - 1 with one MUFU.EX2 (abs. error ~1e-7, far below tf32 rounding)
+__device__ __forceinline__ float elu_fast(float z) { return z > 0.f ? z : ex2_approx(z * 1.4426950408889634f) - 1.f; }
 
 template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_kernel(const __grid_constant__ TcBatch batch) {
@@ -454,6 +460,371 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_kernel(const __grid_con
   }
 }
 
+// ------------------------------------------------------------------------------- persistent kernel
+// One CTA per SM loops over the tiles of all grouped problems (static round-robin schedule).  Compared
+// with the one-tile-per-CTA kernel above, the prologue (barrier init, TMEM allocation, descriptor prefetch)
+// is paid once, the TMA producer runs ahead into the next tile while the current one is still in its
+// epilogue, and the accumulator is double buffered in TMEM (2 x 256 columns) so that the epilogue of
+// tile i overlaps the MMAs of tile i+1.  Tiles are 128 x block_n with block_n up to 256.
+//   warp 0       TMA producer          warp 1        MMA issuer / TMEM owner
+//   warps 2..9   epilogue (8)          warps 10..13  wgrad only: bias-gradient reducers over the dY tiles
+constexpr int TCP_EPI_WARPS = 8;
+constexpr int TCP_THREADS = (2 + TCP_EPI_WARPS + 4) * 32;
+constexpr int TCP_MAX_STAGES = 6;
+constexpr int TCP_RING_BUDGET = 150 * 1024;
+constexpr int TCP_STAGING = TCP_EPI_WARPS * 2 * 4096;  // two 32x32 fp32 slots per epilogue warp
+constexpr int TCP_MAX_BLOCK_N = 256;
+
+struct TcpScalars {  // per-problem scalars mirrored into shared memory once per CTA
+  float* C;
+  const float* bias;
+  float* db;
+  int M, N, ldc, act, tma_out, block_n, tiles_m, tiles_n, splits, kb_per_split, num_kb, tile_count;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(const __grid_constant__ TcBatch batch,
+                                                                            const int n_problems) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr bool A_MN = MODE == TC_WGRAD;
+  constexpr bool B_MN = MODE != TC_FWD;
+
+  const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  uint8_t* const ring = smem_raw + pad;
+  // the ring is sized for the widest problem of the batch; every problem uses the same stage pitch
+  int max_bn = 16;
+  for (int i = 0; i < n_problems; ++i) max_bn = max(max_bn, batch.p[i].block_n);
+  const uint32_t a_bytes = TC_BLOCK_M * TC_BLOCK_K * 4;
+  const uint32_t stage_bytes = a_bytes + (uint32_t)max_bn * TC_BLOCK_K * 4;
+  int stages = TCP_RING_BUDGET / stage_bytes;
+  stages = stages > TCP_MAX_STAGES ? TCP_MAX_STAGES : stages;
+  uint8_t* const staging = ring + (size_t)stages * stage_bytes;  // 1024-byte aligned (stage_bytes is a multiple of 2048)
+  uint64_t* const full_bar = (uint64_t*)(staging + TCP_STAGING);
+  uint64_t* const empty_bar = full_bar + TCP_MAX_STAGES;
+  uint64_t* const tmem_full = empty_bar + TCP_MAX_STAGES;   // [2]
+  uint64_t* const tmem_empty = tmem_full + 2;               // [2]
+  uint64_t* const h_bar = tmem_empty + 2;                   // [TCP_EPI_WARPS][2]
+  uint32_t* const tmem_ptr_smem = (uint32_t*)(h_bar + 2 * TCP_EPI_WARPS);
+  TcpScalars* const sp = (TcpScalars*)(tmem_ptr_smem + 4);  // [2]
+  float* const bias_stage = (float*)(sp + 2);               // [TCP_EPI_WARPS][32], 16-byte aligned
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x < n_problems) {
+    const TcProblem& P = batch.p[threadIdx.x];
+    TcpScalars q;
+    q.C = P.C; q.bias = P.bias; q.db = P.db; q.M = P.M; q.N = P.N; q.ldc = P.ldc; q.act = P.act;
+    q.tma_out = P.tma_out; q.block_n = P.block_n; q.tiles_m = P.tiles_m; q.tiles_n = P.tiles_n; q.splits = P.splits;
+    q.kb_per_split = P.kb_per_split; q.num_kb = P.num_kb; q.tile_count = P.tiles_m * P.tiles_n * P.splits;
+    sp[threadIdx.x] = q;
+  }
+  if (warp == 0 && elect_one()) {
+    for (int i = 0; i < n_problems; ++i) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&batch.p[i].map_a) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&batch.p[i].map_b) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&batch.p[i].map_c) : "memory");
+    }
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], MODE == TC_WGRAD ? 5 : 1);  // MMA commit (+ the 4 reducer warps in wgrad)
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], TCP_EPI_WARPS);
+    }
+    for (int w = 0; w < 2 * TCP_EPI_WARPS; ++w) mbar_init(&h_bar[w], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  int total_tiles = 0;
+  for (int i = 0; i < n_problems; ++i) total_tiles += sp[i].tile_count;
+
+  // tile id -> (problem, split, tile_m, tile_n); tile_n fastest so that concurrently running CTAs share A rows
+  auto decode = [&](int t, int& pi, int& split, int& tm, int& tn) {
+    pi = 0;
+    while (t >= sp[pi].tile_count) { t -= sp[pi].tile_count; ++pi; }
+    const int tiles = sp[pi].tiles_m * sp[pi].tiles_n;
+    split = t / tiles;
+    const int rem = t - split * tiles;
+    tm = rem / sp[pi].tiles_n;
+    tn = rem - tm * sp[pi].tiles_n;
+  };
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (elect_one()) {
+      int it = 0;  // running k-block counter over all tiles of this CTA
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int pi, split, tm, tn;
+        decode(t, pi, split, tm, tn);
+        const CUtensorMap* map_a = &batch.p[pi].map_a;
+        const CUtensorMap* map_b = &batch.p[pi].map_b;
+        const int block_n = sp[pi].block_n;
+        const int m0 = tm * TC_BLOCK_M, n0 = tn * block_n;
+        const int kb0 = split * sp[pi].kb_per_split;
+        const int kb1 = min(sp[pi].num_kb, kb0 + sp[pi].kb_per_split);
+        const uint32_t tx_bytes = a_bytes + (uint32_t)block_n * TC_BLOCK_K * 4;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % stages;
+          mbar_wait(&empty_bar[s], ((it / stages) & 1) ^ 1);
+          uint8_t* sa = ring + (size_t)s * stage_bytes;
+          uint8_t* sb = sa + a_bytes;
+          mbar_expect_tx(&full_bar[s], tx_bytes);
+          const int k0 = kb * TC_BLOCK_K;
+          if (!A_MN) {
+            tma_load_2d(sa, map_a, &full_bar[s], k0, m0);
+          } else {
+            for (int j = 0; j < TC_BLOCK_M / 32; ++j) tma_load_2d(sa + j * 4096, map_a, &full_bar[s], m0 + j * 32, k0);
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, map_b, &full_bar[s], k0, n0);
+          } else {
+            for (int j = 0; j < block_n / 32; ++j) tma_load_2d(sb + j * 4096, map_b, &full_bar[s], n0 + j * 32, k0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    int it = 0, j = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
+      int pi, split, tm, tn;
+      decode(t, pi, split, tm, tn);
+      const int block_n = sp[pi].block_n;
+      const int kb0 = split * sp[pi].kb_per_split;
+      const int kb1 = min(sp[pi].num_kb, kb0 + sp[pi].kb_per_split);
+      const uint32_t idesc = make_idesc(block_n, A_MN, B_MN);
+      const int as = j & 1;
+      const uint32_t d_tmem = tmem_base + (uint32_t)as * 256u;
+      mbar_wait(&tmem_empty[as], ((j >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+      tcgen05_fence_after();
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const int s = it % stages;
+        mbar_wait(&full_bar[s], (it / stages) & 1);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
+          const uint32_t sb = sa + a_bytes;
+#pragma unroll
+          for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
+            const uint64_t da = A_MN ? make_smem_desc(sa + k * 1024, 4096, 512, kLayoutSw128Base32)
+                                     : make_smem_desc(sa + k * 32, 16, 1024, kLayoutSw128);
+            const uint64_t db = B_MN ? make_smem_desc(sb + k * 1024, 4096, 512, kLayoutSw128Base32)
+                                     : make_smem_desc(sb + k * 32, 16, 1024, kLayoutSw128);
+            umma_tf32(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+        }
+        __syncwarp();
+        if (elect_one()) {
+          tcgen05_commit(&empty_bar[s]);
+          if (kb == kb1 - 1) tcgen05_commit(&tmem_full[as]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < 2 + TCP_EPI_WARPS) {
+    // ===================================================================== epilogue warps
+    const int ew = warp - 2;
+    const int q = warp & 3;      // TMEM sub-partition
+    const int half = ew >> 2;    // chunk parity handled by this warp
+    uint8_t* const slot_base = staging + (size_t)ew * 8192;
+    uint64_t* const hb = h_bar + 2 * ew;
+    const uint32_t sw = (uint32_t)(lane & 7);
+    int j = 0;
+    uint32_t n_issued = 0;       // chunks processed by this warp so far (selects the staging slot)
+    uint32_t h_uses[2] = {0u, 0u};  // H loads issued per slot (phase of that slot's mbarrier)
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
+      int pi, split, tm, tn;
+      decode(t, pi, split, tm, tn);
+      const TcpScalars P = sp[pi];
+      const CUtensorMap* map_c = &batch.p[pi].map_c;
+      const CUtensorMap* map_h = &batch.p[pi].map_h;
+      const int block_n = P.block_n;
+      const int m0 = tm * TC_BLOCK_M, n0 = tn * block_n;
+      const int nchunks = (block_n + 31) / 32;
+      const int row0 = m0 + q * 32;
+      const int as = j & 1;
+      const bool rows_live = row0 < P.M;
+      const bool need_h = MODE == TC_DGRAD && P.act != RSLRL_ACT_IDENTITY && rows_live && P.tma_out;
+
+      // H sub-tile of the first chunk goes in flight before we wait for the accumulator
+      if (need_h && half < nchunks) {
+        const uint32_t slot = n_issued & 1;
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // earlier stores have left the slots
+          mbar_expect_tx(&hb[slot], 4096u);
+          tma_load_2d(slot_base + slot * 4096, map_h, &hb[slot], n0 + half * 32, row0);
+        }
+        ++h_uses[slot];
+      }
+      mbar_wait(&tmem_full[as], (j >> 1) & 1);
+      tcgen05_fence_after();
+
+      for (int c = half; c < nchunks; c += 2) {
+        const int c0 = c * 32;
+        const int ncols = min(32, block_n - c0);
+        const uint32_t slot = n_issued & 1;
+        uint8_t* const slot_ptr = slot_base + slot * 4096;
+        uint8_t* const my_row = slot_ptr + lane * 128;
+        // prefetch the next chunk's H into the other slot (its previous store must have drained)
+        if (need_h && c + 2 < nchunks) {
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            mbar_expect_tx(&hb[slot ^ 1], 4096u);
+            tma_load_2d(slot_base + (slot ^ 1) * 4096, map_h, &hb[slot ^ 1], n0 + (c + 2) * 32, row0);
+          }
+          ++h_uses[slot ^ 1];
+        }
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + (uint32_t)as * 256u + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+        if (ncols == 32) TMEM_LD_32x32(taddr, v);
+        else TMEM_LD_32x16(taddr, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (c + 2 >= nchunks) {  // last TMEM read of this tile by this warp: hand the accumulator back
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[as])) : "memory");
+        }
+        float x[32];
+        if (ncols == 32) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = (i < 16) ? __uint_as_float(v[i]) : 0.f;
+        }
+
+        if (MODE == TC_FWD) {
+          // bias of this 32-column chunk: one coalesced load, staged in 128 B of warp-private smem, read back
+          // as 8 broadcast 16-byte loads (instead of 32 shuffles)
+          float* const bs = bias_stage + ew * 32;
+          bs[lane] = (P.bias != nullptr && n0 + c0 + lane < P.N && lane < ncols) ? __ldg(P.bias + n0 + c0 + lane) : 0.f;
+          __syncwarp();
+          float b[32];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float4 b4 = *(const float4*)(bs + 4 * u);
+            b[4 * u] = b4.x; b[4 * u + 1] = b4.y; b[4 * u + 2] = b4.z; b[4 * u + 3] = b4.w;
+          }
+          __syncwarp();
+          if (P.act == RSLRL_ACT_ELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) x[i] = elu_fast(x[i] + b[i]);
+          } else if (P.act == RSLRL_ACT_IDENTITY) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) x[i] = x[i] + b[i];
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) x[i] = act_forward(P.act, x[i] + b[i]);
+          }
+        } else if (MODE == TC_DGRAD) {
+          if (need_h) {
+            mbar_wait(&hb[slot], (h_uses[slot] - 1u) & 1u);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const float4 h = *(const float4*)(my_row + ((u ^ sw) << 4));
+              if (P.act == RSLRL_ACT_ELU) {
+                x[4 * u + 0] *= h.x > 0.f ? 1.f : h.x + 1.f;
+                x[4 * u + 1] *= h.y > 0.f ? 1.f : h.y + 1.f;
+                x[4 * u + 2] *= h.z > 0.f ? 1.f : h.z + 1.f;
+                x[4 * u + 3] *= h.w > 0.f ? 1.f : h.w + 1.f;
+              } else {
+                x[4 * u + 0] *= act_grad_from_output(P.act, h.x);
+                x[4 * u + 1] *= act_grad_from_output(P.act, h.y);
+                x[4 * u + 2] *= act_grad_from_output(P.act, h.z);
+                x[4 * u + 3] *= act_grad_from_output(P.act, h.w);
+              }
+            }
+          }
+        }
+
+        if (P.tma_out) {
+          if (!need_h && lane == 0)  // the slot's previous store (two chunks ago) must have been read
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          __syncwarp();
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            *(float4*)(my_row + ((u ^ sw) << 4)) = make_float4(x[4 * u], x[4 * u + 1], x[4 * u + 2], x[4 * u + 3]);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            if (rows_live) {
+              if (MODE == TC_WGRAD) tma_reduce_add_2d(map_c, slot_ptr, n0 + c0, row0);
+              else tma_store_2d(map_c, slot_ptr, n0 + c0, row0);
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        } else {
+          const int row = row0 + lane;
+          if (row < P.M) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int col = n0 + c0 + i;
+              if (i < ncols && col < P.N) {
+                if (MODE == TC_WGRAD) atomicAdd(P.C + (size_t)row * P.ldc + col, x[i]);
+                else P.C[(size_t)row * P.ldc + col] = x[i];
+              }
+            }
+          }
+        }
+        ++n_issued;
+      }
+      if (half >= nchunks) {  // this warp has no chunk in this tile but still owes its arrival
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[as])) : "memory");
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    tcgen05_fence_before();
+  } else if (MODE == TC_WGRAD) {
+    // ===================================================================== bias-gradient reducers (wgrad)
+    const int f = (warp - 2 - TCP_EPI_WARPS) * 32 + lane;  // feature 0..127 of the A (dY) tile
+    const uint32_t foff = (uint32_t)(f >> 5) * 4096u + (uint32_t)(f & 7) * 4u;
+    const uint32_t fchunk = (uint32_t)((f & 31) >> 3);
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int pi, split, tm, tn;
+      decode(t, pi, split, tm, tn);
+      const int kb0 = split * sp[pi].kb_per_split;
+      const int kb1 = min(sp[pi].num_kb, kb0 + sp[pi].kb_per_split);
+      float* const db_ptr = sp[pi].db;
+      const bool active = db_ptr != nullptr && tn == 0;
+      float acc = 0.f;
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const int s = it % stages;
+        mbar_wait(&full_bar[s], (it / stages) & 1);
+        if (active) {
+          const uint8_t* sa = ring + (size_t)s * stage_bytes;
+#pragma unroll
+          for (int r = 0; r < TC_BLOCK_K; ++r)
+            acc += *(const float*)(sa + foff + (uint32_t)r * 128u + ((fchunk ^ (uint32_t)(r & 3)) << 5));
+        }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty_bar[s])) : "memory");
+      }
+      const int feat = tm * TC_BLOCK_M + f;
+      if (active && feat < sp[pi].M) atomicAdd(db_ptr + feat, acc);
+    }
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 int colsum_accumulate(const float* x, int M, int N, int ld, float* out, cudaStream_t st);
 
 // -------------------------------------------------------------------------------------------- host
@@ -497,10 +868,17 @@ static bool make_map(CUtensorMap* map, const float* base, long long rows, long l
   return r == CUDA_SUCCESS;
 }
 
+static bool use_persistent() {
+  static const int v = [] { const char* e = getenv("RSLRL_TC_PERSISTENT"); return e ? atoi(e) : 1; }();
+  return v != 0;
+}
+
 static bool tma_ok(const void* p, long long ld) { return ((uintptr_t)p & 15) == 0 && (ld % 4) == 0; }
 
+static int max_block_n() { return use_persistent() ? TCP_MAX_BLOCK_N : TC_MAX_BLOCK_N; }
+
 static int pick_block_n(int N) {
-  if (N >= TC_MAX_BLOCK_N) return TC_MAX_BLOCK_N;
+  if (N >= max_block_n()) return max_block_n();
   int b = (N + 31) / 32 * 32;  // MN-major operands come in 32-element atoms; keep it simple for K-major too
   if (N <= 16) b = 16;
   return b;
@@ -514,8 +892,48 @@ static size_t smem_bytes_for(int block_n) {
   return need + 1024;  // slack for the manual 1024-byte alignment
 }
 
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = kNumSMs;
+  }
+  return n;
+}
+
+template <int MODE>
+static int launch_tc_persistent(TcBatch& b, int n, cudaStream_t st, const char* what) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_persistent_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         227 * 1024);
+    if (e != cudaSuccess) {
+      set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
+      return 1;
+    }
+    attr_set = true;
+  }
+  int total = 0, max_bn = 16;
+  for (int i = 0; i < n; ++i) {
+    total += b.p[i].tiles_m * b.p[i].tiles_n * b.p[i].splits;
+    if (b.p[i].block_n > max_bn) max_bn = b.p[i].block_n;
+  }
+  if (total == 0) return 0;
+  const size_t stage = (size_t)(TC_BLOCK_M + max_bn) * TC_BLOCK_K * 4;
+  size_t stages = TCP_RING_BUDGET / stage;
+  if (stages > TCP_MAX_STAGES) stages = TCP_MAX_STAGES;
+  const size_t smem = stages * stage + TCP_STAGING + (2 * TCP_MAX_STAGES + 4 + 2 * TCP_EPI_WARPS) * 8 + 16 +
+                      2 * sizeof(TcpScalars) + TCP_EPI_WARPS * 128 + 1024;
+  const int grid = total < num_sms() ? total : num_sms();
+  tc_gemm_persistent_kernel<MODE><<<grid, TCP_THREADS, smem, st>>>(b, n);
+  return finish_launch(what);
+}
+
 template <int MODE>
 static int launch_tc(TcBatch& b, int n, cudaStream_t st, const char* what) {
+  if (use_persistent()) return launch_tc_persistent<MODE>(b, n, st, what);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -573,7 +991,7 @@ int tc_linear_backward_data(int n, const rslrl_linear_bwd_data_t* pr, cudaStream
     // dX[M,K] = dY[M,N] W[N,K]: reduction N; B = W is MN-major (K contiguous) -> K must be whole 32-atoms
     if (!tma_ok(q.dy, q.ldy) || !tma_ok(q.w, q.K) || (q.K % 32) != 0) return -1;
     TcProblem& P = b.p[i];
-    P.block_n = q.K >= TC_MAX_BLOCK_N ? TC_MAX_BLOCK_N : q.K;
+    P.block_n = q.K >= max_block_n() ? max_block_n() : q.K;
     if (q.K % P.block_n != 0) return -1;
     if (!make_map(&P.map_a, q.dy, q.M, q.N, q.ldy, TC_BLOCK_K, TC_BLOCK_M, false) ||
         !make_map(&P.map_b, q.w, q.N, q.K, q.K, 32, TC_BLOCK_K, true)) {
