@@ -127,6 +127,17 @@ typedef struct {
   int M, N, K, ldy, ldx;
 } rslrl_linear_bwd_weight_t;
 
+typedef struct {
+  const float* dy; /* [M,N], row stride ldy */
+  const float* w;  /* [N,K] */
+  const float* h;  /* [M,K], row stride ldh : the layer's input (previous activation output) */
+  float* dx;       /* [M,K], row stride ldx, or NULL : (dy W) * act'(h) */
+  float* dw;       /* [N,K] accumulated */
+  float* db;       /* [N] accumulated, or NULL */
+  int M, N, K, ldy, ldh, ldx;
+  int act;         /* activation of the previous layer */
+} rslrl_linear_bwd_head_t;
+
 /* Each call runs `n` independent problems (e.g. actor and critic) in one launch; *_host arrays live
  * in host memory and are copied into the kernel parameters. */
 int rslrl_linear_forward(int n, const rslrl_linear_fwd_t* probs_host, int precision, rslrl_stream_t stream);
@@ -134,6 +145,10 @@ int rslrl_linear_backward_data(int n, const rslrl_linear_bwd_data_t* probs_host,
                                rslrl_stream_t stream);
 int rslrl_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* probs_host, int precision,
                                  rslrl_stream_t stream);
+/* Backward of a NARROW layer (N <= 12: the action and value heads), data- and weight-gradient fused in one fp32
+ * launch that reads h and writes dx exactly once.  Returns a non-zero code (message via rslrl_last_error) if a
+ * problem does not qualify (N > 12, K % 4 != 0, unaligned rows); callers then use the two general calls. */
+int rslrl_linear_backward_head(int n, const rslrl_linear_bwd_head_t* probs_host, rslrl_stream_t stream);
 
 /* ---- PPO objective (rsl_rl/algorithms/ppo.py:255-315), forward + hand-derived backward ---------- */
 

@@ -4,7 +4,7 @@ import os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 import torch
 from rsl_rl_b200 import _native as nat
-from rsl_rl_b200.networks.mlp import linear_forward, linear_backward_data, linear_backward_weight
+from rsl_rl_b200.networks.mlp import linear_forward, linear_backward_data, linear_backward_weight, linear_backward_head
 
 prec = nat.PREC_CODES[sys.argv[1] if len(sys.argv) > 1 else "tf32"]
 M = int(sys.argv[2]) if len(sys.argv) > 2 else 24576
@@ -27,7 +27,7 @@ def timeit(fn, reps=10):
 pad4 = lambda n: (n + 3) // 4 * 4
 tot_us, tot_flop = 0.0, 0.0
 for l in range(4):
-    probs_f, probs_d, probs_w = [], [], []
+    probs_f, probs_d, probs_w, probs_h = [], [], [], []
     flop = 0
     for dims in (dims_a, dims_c):
         K, N = dims[l], dims[l + 1]
@@ -38,10 +38,14 @@ for l in range(4):
         probs_f.append((x, w, b, y, ELU if l < 3 else 0))
         probs_d.append((dy, w, x, dx, ELU, dbp))
         probs_w.append((dy, x, dw, None))
+        probs_h.append((dy, w, x, dx, dw, dbp[:N].contiguous() if N <= K else None, ELU))
         flop += 2 * M * N * K
     tf = timeit(lambda: linear_forward(probs_f, prec))
     tw = timeit(lambda: linear_backward_weight(probs_w, prec))
     td = timeit(lambda: linear_backward_data(probs_d, prec)) if l > 0 else 0.0
+    if l == 3:
+        th = timeit(lambda: linear_backward_head(probs_h))
+        print(f"layer 3 fused head backward (dgrad+wgrad+db): {th:.1f} us")
     print(f"layer {l} K={dims_a[l]:4d} N={dims_a[l+1]:4d}  fwd {tf:8.1f} us {flop/tf/1e6:7.1f} TF | wgrad {tw:8.1f} us {flop/tw/1e6:7.1f} TF"
           f" | dgrad {td:8.1f} us {(flop/td/1e6 if td else 0):7.1f} TF")
     tot_us += tf + tw + td; tot_flop += flop * (3 if l > 0 else 2)

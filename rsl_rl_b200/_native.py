@@ -41,6 +41,12 @@ class LinearBwdWeight(C.Structure):
                 ("M", c_int), ("N", c_int), ("K", c_int), ("ldy", c_int), ("ldx", c_int)]
 
 
+class LinearBwdHead(C.Structure):
+    _fields_ = [("dy", c_void_p), ("w", c_void_p), ("h", c_void_p), ("dx", c_void_p), ("dw", c_void_p),
+                ("db", c_void_p), ("M", c_int), ("N", c_int), ("K", c_int), ("ldy", c_int), ("ldh", c_int),
+                ("ldx", c_int), ("act", c_int)]
+
+
 class OptState(C.Structure):
     _fields_ = [("lr", c_double), ("clip_scale", c_double), ("total_norm", c_double), ("step_size", c_double),
                 ("bc2_sqrt", c_double), ("kl_mean", c_double), ("step", C.c_longlong), ("pad_", C.c_longlong)]
@@ -68,6 +74,7 @@ _SIGNATURES = {
     "rslrl_linear_forward": (c_int, [c_int, c_void_p, c_int, c_void_p]),
     "rslrl_linear_backward_data": (c_int, [c_int, c_void_p, c_int, c_void_p]),
     "rslrl_linear_backward_weight": (c_int, [c_int, c_void_p, c_int, c_void_p]),
+    "rslrl_linear_backward_head": (c_int, [c_int, c_void_p, c_void_p]),
     "rslrl_loss_workspace_bytes": (c_i64, []),
     "rslrl_sum_sumsq": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_void_p]),
     "rslrl_optim_workspace_bytes": (c_i64, [c_i64]),

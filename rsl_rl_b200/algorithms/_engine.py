@@ -23,7 +23,8 @@ import torch
 import torch.nn as nn
 
 from .. import _native as nat
-from ..networks.mlp import MLP, linear_backward_data, linear_backward_weight, linear_forward
+from ..networks.mlp import (MLP, head_backward_ok, linear_backward_data, linear_backward_head,
+                            linear_backward_weight, linear_forward)
 from .flat_params import FlatParamGroup, FusedAdam
 
 
@@ -148,19 +149,28 @@ class FeedForwardEngine:
         nets = ((self.actor, self.h_a, self.g_a, x_a, dmu), (self.critic, self.h_c, self.g_c, x_c, dvalue))
         dy = [dmu, dvalue]
         for k in range(max(self.actor.L, self.critic.L)):
-            wprobs, dprobs, new_dy = [], [], list(dy)
+            wprobs, dprobs, hprobs, new_dy = [], [], [], list(dy)
             for ni, (net, hs, gbuf, x_in, _) in enumerate(nets):
                 l = net.L - 1 - k
                 if l < 0:
                     continue
                 lin = net.layers[l]
                 inp = x_in if l == 0 else hs[l - 1][:M]
+                if k == 0 and l > 0 and head_backward_ok(lin.out_features, lin.in_features, inp):
+                    # narrow output layer: one fused fp32 launch for dgrad + wgrad + bias gradient
+                    dx = gbuf[0][:M * net.dims[l]].view(M, net.dims[l])
+                    hprobs.append((dy[ni], lin.weight, inp, dx, lin.weight.grad, lin.bias.grad, net.acts[l - 1]))
+                    new_dy[ni] = dx
+                    continue
                 wprobs.append((dy[ni], inp, lin.weight.grad, lin.bias.grad))
                 if l > 0:
                     dx = gbuf[k % 2][:M * net.dims[l]].view(M, net.dims[l])
                     dprobs.append((dy[ni], lin.weight, inp, dx, net.acts[l - 1]))
                     new_dy[ni] = dx
-            linear_backward_weight(wprobs, self.prec)
+            if hprobs:
+                linear_backward_head(hprobs)
+            if wprobs:
+                linear_backward_weight(wprobs, self.prec)
             if dprobs:
                 linear_backward_data(dprobs, self.prec)
             dy = new_dy

@@ -296,3 +296,185 @@ int simt_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* pr, cuda
 }
 
 }  // namespace rslrl
+
+// ======================================================================================================
+// Narrow output layers (the 12-wide action head and the 1-wide value head).
+// A 128-wide MMA tile is >90 % padding for them and a launch costs more than their arithmetic, so they get
+// fp32 CUDA-core kernels shaped after their memory traffic instead:
+//   head_forward   y = act(x W^T + b)                                    thread per row, W broadcast from smem
+//   head_backward  dx = (dy W) * act'(h), dW += dy^T h, db += 1^T dy     warp per row, lane <-> 4 input columns
+// The backward fuses what would be one dgrad and one wgrad launch and reads h / writes dx exactly once
+// (2*M*K*4 bytes).  Used by both arithmetic modes (they are exact fp32).
+// ======================================================================================================
+namespace rslrl {
+
+constexpr int HEAD_MAX_N = 16;
+constexpr int HEAD_THREADS = 128;
+
+struct HeadFwdProblem {
+  const float* x; const float* w; const float* b; float* y;
+  int M, N, K, ldx, ldy, act;
+};
+struct HeadFwdBatch { HeadFwdProblem p[RSLRL_MAX_PROBLEMS]; };
+
+__global__ void __launch_bounds__(HEAD_THREADS) head_forward_kernel(const HeadFwdBatch batch) {
+  extern __shared__ __align__(16) float s_w[];  // [N][K] then bias[N]
+  const HeadFwdProblem P = batch.p[blockIdx.y];
+  const int N = P.N, K = P.K;
+  for (int i = threadIdx.x; i < N * K; i += HEAD_THREADS) s_w[i] = __ldg(P.w + i);
+  float* s_b = s_w + N * K;
+  if (threadIdx.x < N) s_b[threadIdx.x] = P.b ? __ldg(P.b + threadIdx.x) : 0.f;
+  __syncthreads();
+  const bool vec = (K & 3) == 0 && (P.ldx & 3) == 0 && ((uintptr_t)P.x & 15) == 0;
+  for (int row = blockIdx.x * HEAD_THREADS + threadIdx.x; row < P.M; row += gridDim.x * HEAD_THREADS) {
+    float acc[HEAD_MAX_N];
+#pragma unroll
+    for (int a = 0; a < HEAD_MAX_N; ++a) acc[a] = 0.f;
+    const float* xr = P.x + (size_t)row * P.ldx;
+    if (vec) {
+      for (int k = 0; k < K; k += 4) {
+        const float4 xv = __ldg((const float4*)(xr + k));
+#pragma unroll
+        for (int a = 0; a < HEAD_MAX_N; ++a) {
+          if (a < N) {
+            const float4 wv = *(const float4*)(s_w + a * K + k);
+            acc[a] = fmaf(xv.x, wv.x, acc[a]);
+            acc[a] = fmaf(xv.y, wv.y, acc[a]);
+            acc[a] = fmaf(xv.z, wv.z, acc[a]);
+            acc[a] = fmaf(xv.w, wv.w, acc[a]);
+          }
+        }
+      }
+    } else {
+      for (int k = 0; k < K; ++k) {
+        const float xv = __ldg(xr + k);
+#pragma unroll
+        for (int a = 0; a < HEAD_MAX_N; ++a)
+          if (a < N) acc[a] = fmaf(xv, s_w[a * K + k], acc[a]);
+      }
+    }
+    float* yr = P.y + (size_t)row * P.ldy;
+#pragma unroll
+    for (int a = 0; a < HEAD_MAX_N; ++a)
+      if (a < N) yr[a] = act_forward(P.act, acc[a] + s_b[a]);
+  }
+}
+
+struct HeadBwdProblem {
+  const float* dy; const float* w; const float* h; float* dx; float* dw; float* db;
+  int M, N, K, ldy, ldh, ldx, act;
+};
+struct HeadBwdBatch { HeadBwdProblem p[RSLRL_MAX_PROBLEMS]; };
+
+constexpr int HEADB_WARPS = 8;
+constexpr int HEADB_MAX_N = 12;
+
+// K <= 128 per pass (lane <-> 4 consecutive input columns); wider inputs loop over 128-column panels.
+__global__ void __launch_bounds__(HEADB_WARPS * 32) head_backward_kernel(const HeadBwdBatch batch) {
+  __shared__ float s_dw[HEADB_MAX_N][128];
+  __shared__ float s_db[HEADB_MAX_N];
+  const HeadBwdProblem P = batch.p[blockIdx.y];
+  const int N = P.N, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gwarp = blockIdx.x * HEADB_WARPS + warp, nwarps = gridDim.x * HEADB_WARPS;
+  for (int k0 = 0; k0 < P.K; k0 += 128) {
+    const int col = k0 + lane * 4;
+    const bool col_ok = col < P.K;  // K % 4 == 0 is required by the dispatcher
+    float w[HEADB_MAX_N][4], dw[HEADB_MAX_N][4];
+#pragma unroll
+    for (int a = 0; a < HEADB_MAX_N; ++a) {
+      float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a < N && col_ok) wv = __ldg((const float4*)(P.w + (size_t)a * P.K + col));
+      w[a][0] = wv.x; w[a][1] = wv.y; w[a][2] = wv.z; w[a][3] = wv.w;
+      dw[a][0] = dw[a][1] = dw[a][2] = dw[a][3] = 0.f;
+    }
+    float db_acc = 0.f;
+    for (int i = threadIdx.x; i < HEADB_MAX_N * 128; i += HEADB_WARPS * 32) (&s_dw[0][0])[i] = 0.f;
+    if (threadIdx.x < HEADB_MAX_N) s_db[threadIdx.x] = 0.f;
+    __syncthreads();
+    for (int row = gwarp; row < P.M; row += 2 * nwarps) {
+      // two rows per iteration: both rows' loads are in flight before either is consumed
+      const int row2 = row + nwarps;
+      const bool has2 = row2 < P.M;
+      const float dyl_a = lane < N ? __ldg(P.dy + (size_t)row * P.ldy + lane) : 0.f;
+      const float dyl_b = (has2 && lane < N) ? __ldg(P.dy + (size_t)row2 * P.ldy + lane) : 0.f;
+      float4 hv_a = make_float4(0.f, 0.f, 0.f, 0.f), hv_b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (col_ok) {
+        hv_a = __ldg((const float4*)(P.h + (size_t)row * P.ldh + col));
+        if (has2) hv_b = __ldg((const float4*)(P.h + (size_t)row2 * P.ldh + col));
+      }
+      db_acc += dyl_a + dyl_b;
+      float4 dxa = make_float4(0.f, 0.f, 0.f, 0.f), dxb = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int a = 0; a < HEADB_MAX_N; ++a) {
+        if (a < N) {
+          const float da = __shfl_sync(0xffffffffu, dyl_a, a), dbv = __shfl_sync(0xffffffffu, dyl_b, a);
+          dxa.x = fmaf(da, w[a][0], dxa.x); dxa.y = fmaf(da, w[a][1], dxa.y);
+          dxa.z = fmaf(da, w[a][2], dxa.z); dxa.w = fmaf(da, w[a][3], dxa.w);
+          dxb.x = fmaf(dbv, w[a][0], dxb.x); dxb.y = fmaf(dbv, w[a][1], dxb.y);
+          dxb.z = fmaf(dbv, w[a][2], dxb.z); dxb.w = fmaf(dbv, w[a][3], dxb.w);
+          dw[a][0] = fmaf(da, hv_a.x, fmaf(dbv, hv_b.x, dw[a][0])); dw[a][1] = fmaf(da, hv_a.y, fmaf(dbv, hv_b.y, dw[a][1]));
+          dw[a][2] = fmaf(da, hv_a.z, fmaf(dbv, hv_b.z, dw[a][2])); dw[a][3] = fmaf(da, hv_a.w, fmaf(dbv, hv_b.w, dw[a][3]));
+        }
+      }
+      if (P.dx != nullptr && col_ok) {
+        if (P.act != RSLRL_ACT_IDENTITY) {
+          dxa.x *= act_grad_from_output(P.act, hv_a.x); dxa.y *= act_grad_from_output(P.act, hv_a.y);
+          dxa.z *= act_grad_from_output(P.act, hv_a.z); dxa.w *= act_grad_from_output(P.act, hv_a.w);
+          dxb.x *= act_grad_from_output(P.act, hv_b.x); dxb.y *= act_grad_from_output(P.act, hv_b.y);
+          dxb.z *= act_grad_from_output(P.act, hv_b.z); dxb.w *= act_grad_from_output(P.act, hv_b.w);
+        }
+        *(float4*)(P.dx + (size_t)row * P.ldx + col) = dxa;
+        if (has2) *(float4*)(P.dx + (size_t)row2 * P.ldx + col) = dxb;
+      }
+    }
+    // block-level reduction of the weight / bias gradient partials, then one atomic per element per block
+#pragma unroll
+    for (int a = 0; a < HEADB_MAX_N; ++a) {
+      if (a < N) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) atomicAdd(&s_dw[a][lane * 4 + j], dw[a][j]);
+      }
+    }
+    if (k0 == 0 && lane < N) atomicAdd(&s_db[lane], db_acc);
+    __syncthreads();
+    for (int i = threadIdx.x; i < N * 128; i += HEADB_WARPS * 32) {
+      const int a = i >> 7, c = k0 + (i & 127);
+      if (c < P.K) atomicAdd(P.dw + (size_t)a * P.K + c, s_dw[a][i & 127]);
+    }
+    if (k0 == 0 && P.db != nullptr && threadIdx.x < N) atomicAdd(P.db + threadIdx.x, s_db[threadIdx.x]);
+    __syncthreads();
+  }
+}
+
+// returns -1 when the problems do not fit the head kernels (caller uses the general GEMM path)
+int head_linear_forward(int n, const rslrl_linear_fwd_t* pr, cudaStream_t st) {
+  HeadFwdBatch b{};
+  size_t smem = 0;
+  int max_m = 0;
+  for (int i = 0; i < n; ++i) {
+    if (pr[i].N > HEAD_MAX_N || pr[i].K > 1024 || pr[i].M < 1024 || pr[i].M > 8192) return -1;  // rollout-sized batches only
+    b.p[i] = HeadFwdProblem{pr[i].x, pr[i].w, pr[i].b, pr[i].y, pr[i].M, pr[i].N, pr[i].K, pr[i].ldx, pr[i].ldy, pr[i].act};
+    const size_t s = ((size_t)pr[i].N * pr[i].K + pr[i].N + 4) * sizeof(float);
+    if (s > smem) smem = s;
+    if (pr[i].M > max_m) max_m = pr[i].M;
+  }
+  if (smem > 48 * 1024) return -1;
+  int blocks = (max_m + HEAD_THREADS - 1) / HEAD_THREADS;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  head_forward_kernel<<<dim3(blocks, n), HEAD_THREADS, smem, st>>>(b);
+  return finish_launch("rslrl_linear_forward(head)");
+}
+
+int head_linear_backward(int n, const rslrl_linear_bwd_head_t* pr, cudaStream_t st) {
+  HeadBwdBatch b{};
+  for (int i = 0; i < n; ++i) {
+    const rslrl_linear_bwd_head_t& q = pr[i];
+    if (q.N > HEADB_MAX_N || (q.K & 3) || (q.ldh & 3) || ((uintptr_t)q.h & 15) || ((uintptr_t)q.w & 15)) return -1;
+    if (q.dx && ((q.ldx & 3) || ((uintptr_t)q.dx & 15))) return -1;
+    b.p[i] = HeadBwdProblem{q.dy, q.w, q.h, q.dx, q.dw, q.db, q.M, q.N, q.K, q.ldy, q.ldh, q.ldx, q.act};
+  }
+  head_backward_kernel<<<dim3(kNumSMs * 2, n), HEADB_WARPS * 32, 0, st>>>(b);
+  return finish_launch("rslrl_linear_backward_head");
+}
+
+}  // namespace rslrl

@@ -36,11 +36,6 @@ namespace rslrl {
 constexpr int TC_BLOCK_M = 128;
 constexpr int TC_BLOCK_K = 32;  // tf32 elements = one 128-byte swizzle row
 constexpr int TC_UMMA_K = 8;    // tf32 MMA depth (32 bytes)
-constexpr int TC_EPI_WARPS = 8;
-constexpr int TC_THREADS = (2 + TC_EPI_WARPS) * 32;
-constexpr int TC_MAX_STAGES = 6;
-constexpr int TC_SMEM_BUDGET = 100 * 1024;  // per CTA: two CTAs per SM so that one's epilogue overlaps the other's mainloop
-constexpr int TC_MAX_BLOCK_N = 128;
 
 enum { TC_FWD = 0, TC_DGRAD = 1, TC_WGRAD = 2 };
 
@@ -187,292 +182,24 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // ELU(z) = z > 0 ? z : exp(z) - 1 with one MUFU.EX2 (abs. error ~1e-7, far below tf32 rounding)
 __device__ __forceinline__ float elu_fast(float z) { return z > 0.f ? z : ex2_approx(z * 1.4426950408889634f) - 1.f; }
 
-template <int MODE>
-__global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_kernel(const __grid_constant__ TcBatch batch) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  const TcProblem& P = batch.p[blockIdx.y];
-  // Scalars are copied out of the parameter block once: reading them through the (dynamically indexed)
-  // reference inside the epilogue loops costs a dependent load per iteration.
-  const int tiles_n = P.tiles_n, tiles = P.tiles_m * tiles_n;
-  if ((int)blockIdx.x >= tiles * P.splits) return;
-  const int pM = P.M, pN = P.N, ldc = P.ldc, act = P.act;
-  float* const __restrict__ Cptr = P.C;
-  const float* const __restrict__ bias_ptr = P.bias;
-  float* const __restrict__ db_ptr = P.db;
-  const bool tma_out = P.tma_out != 0;
-  const CUtensorMap* const map_a = &P.map_a;
-  const CUtensorMap* const map_b = &P.map_b;
-  const CUtensorMap* const map_c = &P.map_c;
-  const CUtensorMap* const map_h = &P.map_h;
-  const int split = blockIdx.x / tiles, rem = blockIdx.x - split * tiles;
-  const int tm = rem / tiles_n, tn = rem - tm * tiles_n;
-  const int block_n = P.block_n;
-  const int m0 = tm * TC_BLOCK_M, n0 = tn * block_n;
-  const int kb_begin = split * P.kb_per_split;
-  const int kb_end = min(P.num_kb, kb_begin + P.kb_per_split);
-  const int num_kb = kb_end - kb_begin;
-
-  constexpr bool A_MN = MODE == TC_WGRAD;
-  constexpr bool B_MN = MODE != TC_FWD;
-  const uint32_t a_bytes = TC_BLOCK_M * TC_BLOCK_K * 4, b_bytes = (uint32_t)block_n * TC_BLOCK_K * 4;
-  const uint32_t stage_bytes = a_bytes + b_bytes;
-  int stages = TC_SMEM_BUDGET / stage_bytes;
-  stages = stages > TC_MAX_STAGES ? TC_MAX_STAGES : stages;
-
-  // carve shared memory; pointer arithmetic stays on the __shared__ symbol so accesses compile to LDS/STS
-  const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
-  uint8_t* const ring = smem_raw + pad;                        // tile ring, 1024-byte aligned
-  uint64_t* const full_bar = (uint64_t*)(ring + (size_t)stages * stage_bytes);
-  uint64_t* const empty_bar = full_bar + TC_MAX_STAGES;
-  uint64_t* const tmem_full_bar = empty_bar + TC_MAX_STAGES;
-  uint64_t* const h_bar = tmem_full_bar + 1;                   // one per epilogue warp
-  uint32_t* const tmem_ptr_smem = (uint32_t*)(h_bar + TC_EPI_WARPS);
-  float* const s_bias = (float*)(tmem_ptr_smem + 2);           // block_n floats (<= 256)
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < block_n) tmem_cols <<= 1;
-  // wgrad: the 4 epilogue warps of the first half also reduce the dY tiles over the batch (bias gradient)
-  const bool do_db = MODE == TC_WGRAD && db_ptr != nullptr && tn == 0;
-
-  if (warp == 0 && elect_one()) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map_a) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map_b) : "memory");
-    if (tma_out) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map_c) : "memory");
-    for (int s = 0; s < stages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], do_db ? 5 : 1);
-    }
-    mbar_init(tmem_full_bar, 1);
-    for (int w = 0; w < TC_EPI_WARPS; ++w) mbar_init(&h_bar[w], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
-                 "r"(tmem_cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  if (MODE == TC_FWD && warp >= 2) {
-    for (int j = threadIdx.x - 64; j < block_n; j += TC_EPI_WARPS * 32)
-      s_bias[j] = (bias_ptr != nullptr && n0 + j < pN) ? __ldg(bias_ptr + n0 + j) : 0.f;
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
-
-  if (warp == 0) {
-    // ===================================================================== TMA producer
-    if (elect_one()) {
-      for (int i = 0; i < num_kb; ++i) {
-        const int s = i % stages;
-        const uint32_t ph = (i / stages) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* sa = ring + (size_t)s * stage_bytes;
-        uint8_t* sb = sa + a_bytes;
-        mbar_expect_tx(&full_bar[s], stage_bytes);
-        const int k0 = (kb_begin + i) * TC_BLOCK_K;
-        if (!A_MN) {
-          tma_load_2d(sa, map_a, &full_bar[s], k0, m0);  // box {32 k, 128 m}
-        } else {
-          for (int j = 0; j < TC_BLOCK_M / 32; ++j)      // boxes {32 m, 32 k}: one MN atom column each
-            tma_load_2d(sa + j * 4096, map_a, &full_bar[s], m0 + j * 32, k0);
-        }
-        if (!B_MN) {
-          tma_load_2d(sb, map_b, &full_bar[s], k0, n0);  // box {32 k, block_n n}
-        } else {
-          for (int j = 0; j < block_n / 32; ++j) tma_load_2d(sb + j * 4096, map_b, &full_bar[s], n0 + j * 32, k0);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    const uint32_t idesc = make_idesc(block_n, A_MN, B_MN);
-    for (int i = 0; i < num_kb; ++i) {
-      const int s = i % stages;
-      const uint32_t ph = (i / stages) & 1;
-      mbar_wait(&full_bar[s], ph);
-      tcgen05_fence_after();
-      if (elect_one()) {
-        const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
-        const uint32_t sb = sa + a_bytes;
-#pragma unroll
-        for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
-          // K-major: advance 32 bytes inside the 128-byte swizzle row; SBO = 8 rows x 128 B.
-          // MN-major: one MMA consumes 8 reduction rows = 1024 B; LBO = next 32-element MN atom (4096 B box),
-          //           SBO = next group of 4 reduction rows (512 B).
-          const uint64_t da = A_MN ? make_smem_desc(sa + k * 1024, 4096, 512, kLayoutSw128Base32)
-                                   : make_smem_desc(sa + k * 32, 16, 1024, kLayoutSw128);
-          const uint64_t db = B_MN ? make_smem_desc(sb + k * 1024, 4096, 512, kLayoutSw128Base32)
-                                   : make_smem_desc(sb + k * 32, 16, 1024, kLayoutSw128);
-          umma_tf32(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
-        }
-      }
-      __syncwarp();
-      if (elect_one()) {
-        tcgen05_commit(&empty_bar[s]);  // frees the smem stage when the MMAs retire
-        if (i == num_kb - 1) tcgen05_commit(tmem_full_bar);
-      }
-      __syncwarp();
-    }
-  } else {
-    // ===================================================================== epilogue warps (8)
-    const int ew = warp - 2;          // 0..7
-    const int q = warp & 3;           // TMEM sub-partition of this warp: lanes [32q, 32q+32)
-    const int half = ew >> 2;         // chunk parity handled by this warp
-    const int nchunks = (block_n + 31) / 32;
-    const int row0 = m0 + q * 32;
-
-    if (MODE == TC_WGRAD && do_db && half == 0) {
-      // bias gradient: db[f] += sum over the batch rows of dY[:, f]; thread <-> feature f of the A tile.
-      // A tile (MN-major, 32-byte-atom swizzle): box j = f/32 at +j*4096, row r at +r*128,
-      // 32-byte chunk ((f%32)/8) ^ (r&3), element f%8.
-      const int f = (ew & 3) * 32 + lane;   // 0..127
-      const uint32_t foff = (uint32_t)(f >> 5) * 4096u + (uint32_t)(f & 7) * 4u;
-      const uint32_t fchunk = (uint32_t)((f & 31) >> 3);
-      float acc = 0.f;
-      for (int i = 0; i < num_kb; ++i) {
-        const int s = i % stages;
-        const uint32_t ph = (i / stages) & 1;
-        mbar_wait(&full_bar[s], ph);
-        const uint8_t* sa = ring + (size_t)s * stage_bytes;
-#pragma unroll
-        for (int r = 0; r < TC_BLOCK_K; ++r)
-          acc += *(const float*)(sa + foff + (uint32_t)r * 128u + ((fchunk ^ (uint32_t)(r & 3)) << 5));
-        __syncwarp();
-        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty_bar[s])) : "memory");
-      }
-      if (m0 + f < pM) atomicAdd(db_ptr + m0 + f, acc);
-    }
-
-    if (num_kb > 0) {
-      mbar_wait(tmem_full_bar, 0);
-      tcgen05_fence_after();
-    }
-    // The tile ring is idle now; slot(c, q) = 4 KB staging buffer of (column chunk c, row group q).
-    if (MODE == TC_DGRAD && act != RSLRL_ACT_IDENTITY && row0 < pM) {
-      // fetch this warp's H sub-tiles (saved activations) with TMA into their slots
-      if (lane == 0) {
-        int nmine = 0;
-        for (int c = half; c < nchunks; c += 2) ++nmine;
-        if (nmine > 0) {
-          mbar_expect_tx(&h_bar[ew], (uint32_t)nmine * 4096u);
-          for (int c = half; c < nchunks; c += 2)
-            tma_load_2d(ring + (size_t)(c * 4 + q) * 4096, map_h, &h_bar[ew], n0 + c * 32, row0);
-        }
-      }
-      __syncwarp();
-      if (half < nchunks) mbar_wait(&h_bar[ew], 0);
-    }
-
-    for (int c = half; c < nchunks; c += 2) {
-      const int c0 = c * 32;
-      const int ncols = min(32, block_n - c0);
-      uint32_t v[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-      if (num_kb > 0) {
-        if (ncols == 32) TMEM_LD_32x32(taddr, v);
-        else TMEM_LD_32x16(taddr, v);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0u;
-      }
-      if (ncols < 32) {
-#pragma unroll
-        for (int j = 16; j < 32; ++j) v[j] = 0u;
-      }
-      float x[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
-
-      uint8_t* slot = ring + (size_t)(c * 4 + q) * 4096;
-      uint8_t* my_row = slot + lane * 128;
-      const uint32_t sw = (uint32_t)(lane & 7);  // 128-byte swizzle: 16-byte unit u lives at u ^ (row & 7)
-
-      if (MODE == TC_FWD) {
-        if (act == RSLRL_ACT_ELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = elu_fast(x[j] + s_bias[c0 + j]);
-        } else if (act == RSLRL_ACT_IDENTITY) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = x[j] + s_bias[c0 + j];
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = act_forward(act, x[j] + s_bias[c0 + j]);
-        }
-      } else if (MODE == TC_DGRAD) {
-        if (act != RSLRL_ACT_IDENTITY && row0 + lane < pM) {
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const float4 h = *(const float4*)(my_row + ((u ^ sw) << 4));
-            if (act == RSLRL_ACT_ELU) {
-              x[4 * u + 0] *= h.x > 0.f ? 1.f : h.x + 1.f;
-              x[4 * u + 1] *= h.y > 0.f ? 1.f : h.y + 1.f;
-              x[4 * u + 2] *= h.z > 0.f ? 1.f : h.z + 1.f;
-              x[4 * u + 3] *= h.w > 0.f ? 1.f : h.w + 1.f;
-            } else {
-              x[4 * u + 0] *= act_grad_from_output(act, h.x);
-              x[4 * u + 1] *= act_grad_from_output(act, h.y);
-              x[4 * u + 2] *= act_grad_from_output(act, h.z);
-              x[4 * u + 3] *= act_grad_from_output(act, h.w);
-            }
-          }
-        }
-      }
-
-      if (tma_out) {
-        // registers -> swizzled staging slot (conflict-free 16-byte stores) -> one bulk tensor store per 32x32 block
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-          *(float4*)(my_row + ((u ^ sw) << 4)) = make_float4(x[4 * u], x[4 * u + 1], x[4 * u + 2], x[4 * u + 3]);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0 && row0 < pM) {
-          if (MODE == TC_WGRAD) tma_reduce_add_2d(map_c, slot, n0 + c0, row0);
-          else tma_store_2d(map_c, slot, n0 + c0, row0);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
-      } else {
-        // outputs whose row pitch TMA cannot describe (e.g. the [M,1] value head): direct stores
-        const int row = row0 + lane;
-        if (row < pM) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = n0 + c0 + j;
-            if (j < ncols && col < pN) {
-              if (MODE == TC_WGRAD) atomicAdd(Cptr + (size_t)row * ldc + col, x[j]);
-              else Cptr[(size_t)row * ldc + col] = x[j];
-            }
-          }
-        }
-      }
-    }
-    if (tma_out && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem may be released
-    tcgen05_fence_before();
-  }
-
-  __syncthreads();
-  if (warp == 1) {
-    tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
-  }
-}
-
 // ------------------------------------------------------------------------------- persistent kernel
-// One CTA per SM loops over the tiles of all grouped problems (static round-robin schedule).  Compared
-// with the one-tile-per-CTA kernel above, the prologue (barrier init, TMEM allocation, descriptor prefetch)
-// is paid once, the TMA producer runs ahead into the next tile while the current one is still in its
-// epilogue, and the accumulator is double buffered in TMEM (2 x 256 columns) so that the epilogue of
-// tile i overlaps the MMAs of tile i+1.  Tiles are 128 x block_n with block_n up to 256.
-//   warp 0       TMA producer          warp 1        MMA issuer / TMEM owner
-//   warps 2..9   epilogue (8)          warps 10..13  wgrad only: bias-gradient reducers over the dY tiles
+// One CTA per SM loops over the tiles of all grouped problems (static round-robin schedule): the prologue
+// (barrier init, TMEM allocation, descriptor prefetch) is paid once, the TMA producer runs ahead into the
+// next tile while the current one is still in its epilogue, and the accumulator is double buffered in TMEM
+// (2 x 256 columns) so that the epilogue of tile i overlaps the MMAs of tile i+1.  Tiles are 128 x block_n
+// with block_n up to 256.
+//   warp 0       TMA producer (operands)     warp 1   MMA issuer / TMEM owner      warps 2..9  epilogue (8)
+//   warps 10..13 wgrad: bias-gradient reducers over the dY tiles; dgrad: warp 10 streams the saved
+//                activations H through a ring of 8 chunk buffers (128 rows x 32 columns each) ahead of the
+//                epilogue, which multiplies in place and bulk-stores from the same buffer.
 constexpr int TCP_EPI_WARPS = 8;
 constexpr int TCP_THREADS = (2 + TCP_EPI_WARPS + 4) * 32;
 constexpr int TCP_MAX_STAGES = 6;
 constexpr int TCP_RING_BUDGET = 150 * 1024;
-constexpr int TCP_STAGING = TCP_EPI_WARPS * 2 * 4096;  // two 32x32 fp32 slots per epilogue warp
+constexpr int TCP_STAGING = TCP_EPI_WARPS * 2 * 4096;  // fwd / wgrad: two 32x32 fp32 slots per epilogue warp
+constexpr int TCP_H_CHUNKS = 8;                        // dgrad: ring of H chunk buffers, 16 KB each
+constexpr int TCP_H_BYTES = TCP_H_CHUNKS * 16384;
+constexpr int TCP_RING_BUDGET_DGRAD = 96 * 1024;
 constexpr int TCP_MAX_BLOCK_N = 256;
 
 struct TcpScalars {  // per-problem scalars mirrored into shared memory once per CTA
@@ -496,15 +223,16 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
   for (int i = 0; i < n_problems; ++i) max_bn = max(max_bn, batch.p[i].block_n);
   const uint32_t a_bytes = TC_BLOCK_M * TC_BLOCK_K * 4;
   const uint32_t stage_bytes = a_bytes + (uint32_t)max_bn * TC_BLOCK_K * 4;
-  int stages = TCP_RING_BUDGET / stage_bytes;
+  int stages = (MODE == TC_DGRAD ? TCP_RING_BUDGET_DGRAD : TCP_RING_BUDGET) / stage_bytes;
   stages = stages > TCP_MAX_STAGES ? TCP_MAX_STAGES : stages;
   uint8_t* const staging = ring + (size_t)stages * stage_bytes;  // 1024-byte aligned (stage_bytes is a multiple of 2048)
-  uint64_t* const full_bar = (uint64_t*)(staging + TCP_STAGING);
+  uint64_t* const full_bar = (uint64_t*)(staging + (MODE == TC_DGRAD ? TCP_H_BYTES : TCP_STAGING));
   uint64_t* const empty_bar = full_bar + TCP_MAX_STAGES;
   uint64_t* const tmem_full = empty_bar + TCP_MAX_STAGES;   // [2]
   uint64_t* const tmem_empty = tmem_full + 2;               // [2]
-  uint64_t* const h_bar = tmem_empty + 2;                   // [TCP_EPI_WARPS][2]
-  uint32_t* const tmem_ptr_smem = (uint32_t*)(h_bar + 2 * TCP_EPI_WARPS);
+  uint64_t* const h_full = tmem_empty + 2;                  // [TCP_H_CHUNKS]  (dgrad)
+  uint64_t* const h_empty = h_full + TCP_H_CHUNKS;          // [TCP_H_CHUNKS]
+  uint32_t* const tmem_ptr_smem = (uint32_t*)(h_empty + TCP_H_CHUNKS);
   TcpScalars* const sp = (TcpScalars*)(tmem_ptr_smem + 4);  // [2]
   float* const bias_stage = (float*)(sp + 2);               // [TCP_EPI_WARPS][32], 16-byte aligned
 
@@ -532,7 +260,10 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], TCP_EPI_WARPS);
     }
-    for (int w = 0; w < 2 * TCP_EPI_WARPS; ++w) mbar_init(&h_bar[w], 1);
+    for (int w = 0; w < TCP_H_CHUNKS; ++w) {
+      mbar_init(&h_full[w], 1);
+      mbar_init(&h_empty[w], 4);  // the four row-group warps that consume a chunk
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -637,54 +368,30 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
     const int ew = warp - 2;
     const int q = warp & 3;      // TMEM sub-partition
     const int half = ew >> 2;    // chunk parity handled by this warp
-    uint8_t* const slot_base = staging + (size_t)ew * 8192;
-    uint64_t* const hb = h_bar + 2 * ew;
+    uint8_t* const slot_base = staging + (size_t)ew * 8192;   // fwd / wgrad staging slots of this warp
     const uint32_t sw = (uint32_t)(lane & 7);
     int j = 0;
     uint32_t n_issued = 0;       // chunks processed by this warp so far (selects the staging slot)
-    uint32_t h_uses[2] = {0u, 0u};  // H loads issued per slot (phase of that slot's mbarrier)
+    int gbase = 0;               // dgrad: running chunk index of this CTA (H ring position)
+    int prev_h_slot = -1;        // dgrad: H buffer whose store is still being read
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
       int pi, split, tm, tn;
       decode(t, pi, split, tm, tn);
       const TcpScalars P = sp[pi];
       const CUtensorMap* map_c = &batch.p[pi].map_c;
-      const CUtensorMap* map_h = &batch.p[pi].map_h;
       const int block_n = P.block_n;
       const int m0 = tm * TC_BLOCK_M, n0 = tn * block_n;
       const int nchunks = (block_n + 31) / 32;
       const int row0 = m0 + q * 32;
       const int as = j & 1;
       const bool rows_live = row0 < P.M;
-      const bool need_h = MODE == TC_DGRAD && P.act != RSLRL_ACT_IDENTITY && rows_live && P.tma_out;
 
-      // H sub-tile of the first chunk goes in flight before we wait for the accumulator
-      if (need_h && half < nchunks) {
-        const uint32_t slot = n_issued & 1;
-        if (lane == 0) {
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // earlier stores have left the slots
-          mbar_expect_tx(&hb[slot], 4096u);
-          tma_load_2d(slot_base + slot * 4096, map_h, &hb[slot], n0 + half * 32, row0);
-        }
-        ++h_uses[slot];
-      }
       mbar_wait(&tmem_full[as], (j >> 1) & 1);
       tcgen05_fence_after();
 
       for (int c = half; c < nchunks; c += 2) {
         const int c0 = c * 32;
         const int ncols = min(32, block_n - c0);
-        const uint32_t slot = n_issued & 1;
-        uint8_t* const slot_ptr = slot_base + slot * 4096;
-        uint8_t* const my_row = slot_ptr + lane * 128;
-        // prefetch the next chunk's H into the other slot (its previous store must have drained)
-        if (need_h && c + 2 < nchunks) {
-          if (lane == 0) {
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            mbar_expect_tx(&hb[slot ^ 1], 4096u);
-            tma_load_2d(slot_base + (slot ^ 1) * 4096, map_h, &hb[slot ^ 1], n0 + (c + 2) * 32, row0);
-          }
-          ++h_uses[slot ^ 1];
-        }
         uint32_t v[32];
         const uint32_t taddr = tmem_base + (uint32_t)as * 256u + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
         if (ncols == 32) TMEM_LD_32x32(taddr, v);
@@ -704,6 +411,48 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
           for (int i = 0; i < 32; ++i) x[i] = (i < 16) ? __uint_as_float(v[i]) : 0.f;
         }
 
+        if (MODE == TC_DGRAD) {
+          // H chunk (128 rows x 32 cols, 128-byte swizzle) streamed in by warp 10; this warp owns rows [32q, 32q+32)
+          const int g = gbase + c;
+          const int hs = g % TCP_H_CHUNKS;
+          uint8_t* const blk = staging + (size_t)hs * 16384 + q * 4096;
+          uint8_t* const my_row = blk + lane * 128;
+          mbar_wait(&h_full[hs], (uint32_t)(g / TCP_H_CHUNKS) & 1u);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            float4* const hp = (float4*)(my_row + ((u ^ sw) << 4));
+            const float4 h = *hp;
+            float4 o;
+            if (P.act == RSLRL_ACT_ELU) {
+              o.x = x[4 * u + 0] * (h.x > 0.f ? 1.f : h.x + 1.f);
+              o.y = x[4 * u + 1] * (h.y > 0.f ? 1.f : h.y + 1.f);
+              o.z = x[4 * u + 2] * (h.z > 0.f ? 1.f : h.z + 1.f);
+              o.w = x[4 * u + 3] * (h.w > 0.f ? 1.f : h.w + 1.f);
+            } else {
+              o.x = x[4 * u + 0] * act_grad_from_output(P.act, h.x);
+              o.y = x[4 * u + 1] * act_grad_from_output(P.act, h.y);
+              o.z = x[4 * u + 2] * act_grad_from_output(P.act, h.z);
+              o.w = x[4 * u + 3] * act_grad_from_output(P.act, h.w);
+            }
+            *hp = o;  // in place: the buffer becomes the staging tile of the bulk store
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            if (rows_live) tma_store_2d(map_c, blk, n0 + c0, row0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            if (prev_h_slot >= 0) {  // the previous chunk's store has read its buffer: give it back to the H producer
+              asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+              asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&h_empty[prev_h_slot])) : "memory");
+            }
+          }
+          prev_h_slot = hs;
+          continue;
+        }
+
+        const uint32_t slot = n_issued & 1;
+        uint8_t* const slot_ptr = slot_base + slot * 4096;
+        uint8_t* const my_row = slot_ptr + lane * 128;
         if (MODE == TC_FWD) {
           // bias of this 32-column chunk: one coalesced load, staged in 128 B of warp-private smem, read back
           // as 8 broadcast 16-byte loads (instead of 32 shuffles)
@@ -727,29 +476,10 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
 #pragma unroll
             for (int i = 0; i < 32; ++i) x[i] = act_forward(P.act, x[i] + b[i]);
           }
-        } else if (MODE == TC_DGRAD) {
-          if (need_h) {
-            mbar_wait(&hb[slot], (h_uses[slot] - 1u) & 1u);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const float4 h = *(const float4*)(my_row + ((u ^ sw) << 4));
-              if (P.act == RSLRL_ACT_ELU) {
-                x[4 * u + 0] *= h.x > 0.f ? 1.f : h.x + 1.f;
-                x[4 * u + 1] *= h.y > 0.f ? 1.f : h.y + 1.f;
-                x[4 * u + 2] *= h.z > 0.f ? 1.f : h.z + 1.f;
-                x[4 * u + 3] *= h.w > 0.f ? 1.f : h.w + 1.f;
-              } else {
-                x[4 * u + 0] *= act_grad_from_output(P.act, h.x);
-                x[4 * u + 1] *= act_grad_from_output(P.act, h.y);
-                x[4 * u + 2] *= act_grad_from_output(P.act, h.z);
-                x[4 * u + 3] *= act_grad_from_output(P.act, h.w);
-              }
-            }
-          }
         }
 
         if (P.tma_out) {
-          if (!need_h && lane == 0)  // the slot's previous store (two chunks ago) must have been read
+          if (lane == 0)  // the slot's previous store (two chunks ago) must have been read
             asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           __syncwarp();
 #pragma unroll
@@ -784,9 +514,29 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[as])) : "memory");
       }
+      gbase += nchunks;
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     tcgen05_fence_before();
+  } else if (MODE == TC_DGRAD) {
+    // ===================================================================== H producer (dgrad), warp 10
+    if (warp == 2 + TCP_EPI_WARPS && elect_one()) {
+      int g = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int pi, split, tm, tn;
+        decode(t, pi, split, tm, tn);
+        const CUtensorMap* map_h = &batch.p[pi].map_h;
+        const int block_n = sp[pi].block_n;
+        const int m0 = tm * TC_BLOCK_M, n0 = tn * block_n;
+        const int nchunks = (block_n + 31) / 32;
+        for (int c = 0; c < nchunks; ++c, ++g) {
+          const int hs = g % TCP_H_CHUNKS;
+          mbar_wait(&h_empty[hs], ((uint32_t)(g / TCP_H_CHUNKS) & 1u) ^ 1u);
+          mbar_expect_tx(&h_full[hs], 16384u);
+          tma_load_2d(staging + (size_t)hs * 16384, map_h, &h_full[hs], n0 + c * 32, m0);  // box {32 cols, 128 rows}
+        }
+      }
+    }
   } else if (MODE == TC_WGRAD) {
     // ===================================================================== bias-gradient reducers (wgrad)
     const int f = (warp - 2 - TCP_EPI_WARPS) * 32 + lane;  // feature 0..127 of the A (dY) tile
@@ -868,28 +618,15 @@ static bool make_map(CUtensorMap* map, const float* base, long long rows, long l
   return r == CUDA_SUCCESS;
 }
 
-static bool use_persistent() {
-  static const int v = [] { const char* e = getenv("RSLRL_TC_PERSISTENT"); return e ? atoi(e) : 1; }();
-  return v != 0;
-}
-
 static bool tma_ok(const void* p, long long ld) { return ((uintptr_t)p & 15) == 0 && (ld % 4) == 0; }
 
-static int max_block_n() { return use_persistent() ? TCP_MAX_BLOCK_N : TC_MAX_BLOCK_N; }
+static int max_block_n() { return TCP_MAX_BLOCK_N; }
 
 static int pick_block_n(int N) {
   if (N >= max_block_n()) return max_block_n();
   int b = (N + 31) / 32 * 32;  // MN-major operands come in 32-element atoms; keep it simple for K-major too
   if (N <= 16) b = 16;
   return b;
-}
-
-static size_t smem_bytes_for(int block_n) {
-  const size_t stage = (size_t)(TC_BLOCK_M + block_n) * TC_BLOCK_K * 4;
-  size_t stages = TC_SMEM_BUDGET / stage;
-  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
-  const size_t need = stages * stage + (2 * TC_MAX_STAGES + 1 + TC_EPI_WARPS) * 8 + 16 + 256 * 4;
-  return need + 1024;  // slack for the manual 1024-byte alignment
 }
 
 static int num_sms() {
@@ -922,10 +659,11 @@ static int launch_tc_persistent(TcBatch& b, int n, cudaStream_t st, const char* 
   }
   if (total == 0) return 0;
   const size_t stage = (size_t)(TC_BLOCK_M + max_bn) * TC_BLOCK_K * 4;
-  size_t stages = TCP_RING_BUDGET / stage;
+  size_t stages = (MODE == TC_DGRAD ? TCP_RING_BUDGET_DGRAD : TCP_RING_BUDGET) / stage;
   if (stages > TCP_MAX_STAGES) stages = TCP_MAX_STAGES;
-  const size_t smem = stages * stage + TCP_STAGING + (2 * TCP_MAX_STAGES + 4 + 2 * TCP_EPI_WARPS) * 8 + 16 +
-                      2 * sizeof(TcpScalars) + TCP_EPI_WARPS * 128 + 1024;
+  const size_t smem = stages * stage + (MODE == TC_DGRAD ? TCP_H_BYTES : TCP_STAGING) +
+                      (2 * TCP_MAX_STAGES + 4 + 2 * TCP_H_CHUNKS) * 8 + 16 + 2 * sizeof(TcpScalars) +
+                      TCP_EPI_WARPS * 128 + 1024;
   const int grid = total < num_sms() ? total : num_sms();
   tc_gemm_persistent_kernel<MODE><<<grid, TCP_THREADS, smem, st>>>(b, n);
   return finish_launch(what);
@@ -933,27 +671,7 @@ static int launch_tc_persistent(TcBatch& b, int n, cudaStream_t st, const char* 
 
 template <int MODE>
 static int launch_tc(TcBatch& b, int n, cudaStream_t st, const char* what) {
-  if (use_persistent()) return launch_tc_persistent<MODE>(b, n, st, what);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) {
-      set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
-      return 1;
-    }
-    attr_set = true;
-  }
-  int max_ctas = 0;
-  size_t smem = 0;
-  for (int i = 0; i < n; ++i) {
-    const int t = b.p[i].tiles_m * b.p[i].tiles_n * b.p[i].splits;
-    if (t > max_ctas) max_ctas = t;
-    const size_t s = smem_bytes_for(b.p[i].block_n);
-    if (s > smem) smem = s;
-  }
-  if (max_ctas == 0) return 0;
-  tc_gemm_kernel<MODE><<<dim3(max_ctas, n), TC_THREADS, smem, st>>>(b);
-  return finish_launch(what);
+  return launch_tc_persistent<MODE>(b, n, st, what);
 }
 
 // Each tc_* entry returns 0 on success, 1 on error, and -1 if a problem cannot be described to TMA
@@ -1000,9 +718,9 @@ int tc_linear_backward_data(int n, const rslrl_linear_bwd_data_t* pr, cudaStream
     }
     P.C = q.dx; P.M = q.M; P.N = q.K; P.K = q.N; P.ldc = q.ldx; P.act = q.act;
     if (!tma_ok(q.dx, q.ldx)) return -1;
-    if (q.act != RSLRL_ACT_IDENTITY && !tma_ok(q.h, q.ldh)) return -1;
+    if (q.act == RSLRL_ACT_IDENTITY || !tma_ok(q.h, q.ldh)) return -1;  // (no saved activation: exact fp32 kernel)
     if (!make_map(&P.map_c, q.dx, q.M, q.K, q.ldx, 32, 32, false, false) ||
-        (q.act != RSLRL_ACT_IDENTITY && !make_map(&P.map_h, q.h, q.M, q.K, q.ldh, 32, 32, false, false))) {
+        !make_map(&P.map_h, q.h, q.M, q.K, q.ldh, 32, TC_BLOCK_M, false, false)) {
       set_error("%s: cuTensorMapEncodeTiled failed", what);
       return 1;
     }

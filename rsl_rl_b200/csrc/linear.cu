@@ -7,6 +7,8 @@ int simt_linear_forward(int n, const rslrl_linear_fwd_t* pr, cudaStream_t st);
 int simt_linear_backward_data(int n, const rslrl_linear_bwd_data_t* pr, cudaStream_t st);
 int simt_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* pr, cudaStream_t st);
 int tc_linear_forward(int n, const rslrl_linear_fwd_t* pr, cudaStream_t st);
+int head_linear_forward(int n, const rslrl_linear_fwd_t* pr, cudaStream_t st);
+int head_linear_backward(int n, const rslrl_linear_bwd_head_t* pr, cudaStream_t st);
 int tc_linear_backward_data(int n, const rslrl_linear_bwd_data_t* pr, cudaStream_t st);
 int tc_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* pr, cudaStream_t st);
 }  // namespace rslrl
@@ -20,6 +22,11 @@ int rslrl_linear_forward(int n, const rslrl_linear_fwd_t* probs_host, int precis
   for (int i = 0; i < n; ++i) {
     const rslrl_linear_fwd_t& p = probs_host[i];
     RSLRL_CHECK_ARG(p.x && p.w && p.y && p.M > 0 && p.N > 0 && p.K > 0 && p.ldx >= p.K && p.ldy >= p.N, what);
+  }
+  if (precision == RSLRL_PREC_FP32 || precision == RSLRL_PREC_TF32) {
+    // narrow heads (N <= 16) on many rows: dedicated exact-fp32 kernel in both arithmetic modes
+    const int rc = head_linear_forward(n, probs_host, (cudaStream_t)stream);
+    if (rc >= 0) return rc;
   }
   if (precision == RSLRL_PREC_FP32) return simt_linear_forward(n, probs_host, (cudaStream_t)stream);
   if (precision == RSLRL_PREC_TF32) {
@@ -67,6 +74,22 @@ int rslrl_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* probs_h
   }
   set_error("%s: unknown precision %d", what, precision);
   return 2;
+}
+
+int rslrl_linear_backward_head(int n, const rslrl_linear_bwd_head_t* probs_host, rslrl_stream_t stream) {
+  using namespace rslrl;
+  const char* what = "rslrl_linear_backward_head";
+  RSLRL_CHECK_ARG(n > 0 && n <= RSLRL_MAX_PROBLEMS && probs_host, what);
+  for (int i = 0; i < n; ++i) {
+    const rslrl_linear_bwd_head_t& p = probs_host[i];
+    RSLRL_CHECK_ARG(p.dy && p.w && p.h && p.dw && p.M > 0 && p.N > 0 && p.K > 0 && p.ldy >= p.N && p.ldh >= p.K, what);
+  }
+  const int rc = head_linear_backward(n, probs_host, (cudaStream_t)stream);
+  if (rc < 0) {
+    set_error("%s: problem does not qualify (needs N <= 12, K %% 4 == 0, 16-byte aligned rows)", what);
+    return 4;
+  }
+  return rc;
 }
 
 }  // extern "C"

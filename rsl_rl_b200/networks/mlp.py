@@ -58,6 +58,25 @@ def linear_backward_weight(problems: Sequence[Tuple], precision: int):
     nat.check(nat.lib().rslrl_linear_backward_weight(len(problems), arr, precision, nat.stream_ptr()))
 
 
+HEAD_MAX_N = 12
+
+
+def head_backward_ok(N: int, K: int, *tensors) -> bool:
+    return N <= HEAD_MAX_N and K % 4 == 0 and all(t is None or (t.data_ptr() % 16 == 0 and t.stride(0) % 4 == 0)
+                                                  for t in tensors)
+
+
+def linear_backward_head(problems: Sequence[Tuple]):
+    """Fused dgrad + wgrad + bias gradient of a narrow layer.
+    problems: (dy[M,N], weight[N,K], h[M,K], dx[M,K]|None, dw[N,K], db[N]|None, act_code_of_previous_layer)."""
+    arr = (nat.LinearBwdHead * len(problems))()
+    for i, (dy, w, h, dx, dw, db, act) in enumerate(problems):
+        arr[i] = nat.LinearBwdHead(dy.data_ptr(), w.data_ptr(), h.data_ptr(), nat.ptr(dx), dw.data_ptr(), nat.ptr(db),
+                                   dy.shape[0], w.shape[0], w.shape[1], dy.stride(0), h.stride(0),
+                                   0 if dx is None else dx.stride(0), act)
+    nat.check(nat.lib().rslrl_linear_backward_head(len(problems), arr, nat.stream_ptr()))
+
+
 class _MLPFunction(torch.autograd.Function):
     """Differentiable wrapper: forward = chain of fused Linear+activation launches, backward = fused
     dgrad (+activation derivative) and split-K wgrad launches.  Used whenever an MLP is called under

@@ -449,3 +449,26 @@ def test_trajectory_index_at_c4_size_properties():
     pad_o, mask_o = O.split_and_pad_trajectories(x[:, :64].cpu().numpy(), dones[:, :64].cpu().numpy())
     k = mask_o.shape[1]
     assert np.array_equal(padded[:, :k].cpu().numpy(), pad_o) and np.array_equal(masks[:, :k].cpu().numpy(), mask_o)
+
+
+@pytest.mark.parametrize("M,K,N,act", [(24576, 128, 12, "elu"), (4096, 128, 1, "elu"), (3001, 256, 5, "tanh"),
+                                        (2000, 48, 12, "identity")])
+def test_linear_backward_head_fused(M, K, N, act):
+    """Fused narrow-layer backward: dx, dW (accumulated), db (accumulated) against fp64."""
+    from rsl_rl_b200.networks.mlp import head_backward_ok, linear_backward_head
+    nat = _nat()
+    torch.manual_seed(M + N)
+    z_prev = torch.randn(M, K, device=DEV)
+    h = torch.from_numpy(O.act_forward(act, z_prev.cpu().numpy())).to(DEV)
+    w = torch.randn(N, K, device=DEV) / K ** 0.5
+    dy = torch.zeros(M, (N + 3) // 4 * 4, device=DEV)[:, :N]
+    dy.normal_()
+    dx = torch.full((M, K), float("nan"), device=DEV)
+    dw, db = torch.ones(N, K, device=DEV), torch.ones(N, device=DEV)
+    assert head_backward_ok(N, K, h, dx)
+    linear_backward_head([(dy, w, h, dx, dw, db, nat.ACT_CODES[act])])
+    dh = (dy.double() @ w.double()).cpu().numpy()
+    ref_dx = O.act_backward(act, z_prev.cpu().numpy(), h.cpu().numpy(), dh.astype(np.float32)) if act != "identity" else dh
+    assert rel_err(dx.cpu().numpy(), ref_dx) < 1e-5
+    assert rel_err(dw.cpu().numpy(), 1 + (dy.double().T @ h.double()).cpu().numpy()) < 1e-5
+    assert rel_err(db.cpu().numpy(), 1 + dy.double().sum(0).cpu().numpy()) < 1e-5
