@@ -141,6 +141,7 @@ class PPO:
         self._graph_launches = 0
         self._eager_updates = 0
         self._act_plans = {}
+        self._act_in = None
         self._mb_hook = None  # test hook: called after every minibatch backward in eager mode
         self.last_update_info = {}
 
@@ -177,18 +178,55 @@ class PPO:
         if s >= st.num_transitions_per_env:
             raise OverflowError("Rollout buffer overflow! You should call clear() before adding new transitions.")
         x_a, x_c = self._inputs(obs)
+        key = (x_a.stride(0), x_c.stride(0), x_a.shape[1], x_c.shape[1], self._group.values.data_ptr())
         plan = self._act_plans.get(s)
-        if plan is None or plan[0] != (x_a.stride(0), x_c.stride(0), self._group.values.data_ptr()):
+        if plan is None or plan["key"] != key:
             self._group.ensure_bound()
             nat.require_cuda(x_a, x_c)
             views = (st.mu[s], st.values[s], st.actions[s], st.actions_log_prob[s], st.sigma[s])
-            fwd = eng.build_forward_plan(st.num_envs, x_a.stride(0), x_c.stride(0), views[0], views[1])
-            plan = ((x_a.stride(0), x_c.stride(0), self._group.values.data_ptr()), fwd, views)
+            if self._act_in is None or self._act_in[0].shape != x_a.shape or self._act_in[1].shape != x_c.shape:
+                with torch.inference_mode(False):  # plain tensors: act() may also be called outside inference mode
+                    sa = torch.empty(x_a.shape, dtype=torch.float32, device=x_a.device)
+                    sc = sa if x_c.data_ptr() == x_a.data_ptr() else torch.empty(x_c.shape, dtype=torch.float32,
+                                                                                 device=x_c.device)
+                    self._act_in = (sa, sc, torch.empty(views[0].shape, dtype=torch.float32, device=x_a.device))
+            sa, sc, _ = self._act_in
+            plan = dict(key=key, views=views, graph=None, launches=0, visits=0,
+                        fwd=eng.build_forward_plan(st.num_envs, x_a.stride(0), x_c.stride(0), views[0], views[1]),
+                        fwd_static=eng.build_forward_plan(st.num_envs, sa.stride(0), sc.stride(0), views[0], views[1]))
             self._act_plans[s] = plan
-        _, fwd, (mu_s, val_s, act_s, logp_s, sig_s) = plan
-        fwd(x_a.data_ptr(), x_c.data_ptr())
-        z = self.policy.draw_noise(mu_s)
-        eng.gaussian_head(mu_s, z, act_s, logp_s, sig_s)
+        mu_s, val_s, act_s, logp_s, sig_s = plan["views"]
+        sa, sc, zbuf = self._act_in
+        if self.policy._noise_fn is not None:
+            zbuf.copy_(self.policy._noise_fn(mu_s))
+        else:
+            zbuf.normal_()  # same draw as torch.normal(mean, std): normal_(0,1) on a tensor of mu's shape
+        if not self.use_cuda_graph:
+            plan["fwd"](x_a.data_ptr(), x_c.data_ptr())
+            eng.gaussian_head(mu_s, zbuf, act_s, logp_s, sig_s)
+        else:
+            # forward + Gaussian head of step s replayed from a CUDA graph reading static input buffers
+            sa.copy_(x_a)
+            if sc is not sa:
+                sc.copy_(x_c)
+            if plan["graph"] is None:
+                plan["visits"] += 1
+                if plan["visits"] < 2:   # first visit runs eagerly (lazy initialisation), the second one captures
+                    plan["fwd_static"](sa.data_ptr(), sc.data_ptr())
+                    eng.gaussian_head(mu_s, zbuf, act_s, logp_s, sig_s)
+                else:
+                    torch.cuda.synchronize()
+                    before = nat.launch_count()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        plan["fwd_static"](sa.data_ptr(), sc.data_ptr())
+                        eng.gaussian_head(mu_s, zbuf, act_s, logp_s, sig_s)
+                    plan["launches"] = nat.launch_count() - before
+                    nat.lib().rslrl_add_launch_count(-plan["launches"] & 0xFFFFFFFFFFFFFFFF)
+                    plan["graph"] = g
+            if plan["graph"] is not None:
+                plan["graph"].replay()
+                nat.lib().rslrl_add_launch_count(plan["launches"])
         tr.actions, tr.values = act_s, val_s
         tr.actions_log_prob = logp_s.view(-1)
         tr.action_mean, tr.action_sigma = mu_s, sig_s

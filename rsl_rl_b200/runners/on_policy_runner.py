@@ -133,7 +133,9 @@ class OnPolicyRunner:
                 for _ in range(self.num_steps_per_env):
                     actions = self.alg.act(obs)
                     obs, rewards, dones, extras = self.env.step(actions.to(self.env.device))
-                    obs, rewards, dones = obs.to(self.device), rewards.to(self.device), dones.to(self.device)
+                    # host-resident envs: pinned buffers are copied asynchronously (stream ordered; the blocking
+                    # device->host copy of the next actions is the synchronisation point the env relies on)
+                    obs, rewards, dones = self._to_device(obs), self._to_device(rewards), self._to_device(dones)
                     self.alg.process_env_step(obs, rewards, dones, extras)
                     if logging:
                         if "episode" in extras:
@@ -177,6 +179,14 @@ class OnPolicyRunner:
             self.phase_times = {k: v / num_learning_iterations for k, v in acc.items()}
         if logging and not self.disable_logs:
             self.save(os.path.join(self.log_dir, f"model_{self.current_learning_iteration}.pt"))
+
+    def _to_device(self, x):
+        if isinstance(x, torch.Tensor):
+            return x.to(self.device, non_blocking=(not x.is_cuda) and x.is_pinned())
+        try:
+            return x.to(self.device, non_blocking=True)
+        except TypeError:
+            return x.to(self.device)
 
     # ------------------------------------------------------------------------------------------
     def log(self, locs: dict, width: int = 80, pad: int = 35):

@@ -90,7 +90,11 @@ class TensorDictLite:
                               device=self.device if device is None else device)
 
     def to(self, device, non_blocking: bool = False):
-        return self._map(lambda v: v.to(device, non_blocking=non_blocking), device=device)
+        """non_blocking is honoured only for pinned host sources (the only case where it is safe and useful)."""
+        dev = torch.device(device)
+        if all(v.device == dev for v in self._t.values()):
+            return self
+        return self._map(lambda v: v.to(dev, non_blocking=non_blocking and (v.is_cuda or v.is_pinned())), device=device)
 
     def detach(self):
         return self._map(lambda v: v.detach())
