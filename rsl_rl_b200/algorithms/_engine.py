@@ -77,11 +77,38 @@ class FeedForwardEngine:
         # gradient heads keep a 16-byte row pitch so that TMA can read them (dvalue: 1 used column of 4)
         self.dmu = torch.zeros(R, (self.A + 3) // 4 * 4, **f32)[:, :self.A]
         self.dvalue = torch.zeros(R, 4, **f32)[:, :1]
+        # First-layer weights whose row pitch is not a multiple of 16 bytes (e.g. 235 inputs) cannot be described to
+        # TMA: keep a zero-padded shadow [N, pad4(K)] that the tensor-core forward reads (refreshed after every
+        # optimiser step); inputs are then read at their padded width (pad columns are kept at zero).
+        self.w0_pad = {}
+        if precision != "fp32":
+            for tag, net in (("a", self.actor), ("c", self.critic)):
+                K = net.dims[0]
+                if K % 4:
+                    self.w0_pad[tag] = torch.zeros(net.dims[1], (K + 3) // 4 * 4, **f32)
+        self.refresh_padded()
         self.loss_ws = torch.zeros(int(nat.lib().rslrl_loss_workspace_bytes()), dtype=torch.uint8, device=self.device)
         self.sum_ws = torch.zeros(64, dtype=torch.uint8, device=self.device)
         self.adv_stats = torch.zeros(2, dtype=torch.float64, device=self.device)
 
     # ---------------------------------------------------------------------------------------------
+    def refresh_padded(self):
+        with torch.no_grad():
+            for tag, buf in self.w0_pad.items():
+                net = self.actor if tag == "a" else self.critic
+                buf[:, :net.dims[0]].copy_(net.layers[0].weight)
+
+    def _layer0(self, tag: str, x: torch.Tensor, ld: int = None):
+        """(input, weight) of the first layer: the padded pair when a shadow exists and x has the padded pitch."""
+        net = self.actor if tag == "a" else self.critic
+        buf = self.w0_pad.get(tag)
+        ld = x.stride(0) if ld is None else ld
+        if buf is not None and ld == buf.shape[1]:
+            if x is None:
+                return None, buf
+            return x.as_strided((x.shape[0], buf.shape[1]), (ld, 1), x.storage_offset()), buf
+        return x, net.layers[0].weight
+
     def forward(self, x_a: torch.Tensor, x_c: torch.Tensor, mu_out: torch.Tensor, v_out: torch.Tensor,
                 actor: bool = True, critic: bool = True):
         """Grouped forward of actor and critic on M = x.shape[0] rows; hidden activations stay in
@@ -94,12 +121,14 @@ class FeedForwardEngine:
             if l < La:
                 lin = self.actor.layers[l]
                 out = mu_out if l == La - 1 else self.h_a[l][:M]
-                probs.append((in_a, lin.weight, lin.bias, out, self.actor.acts[l]))
+                xin, w = self._layer0("a", in_a) if l == 0 else (in_a, lin.weight)
+                probs.append((xin, w, lin.bias, out, self.actor.acts[l]))
                 in_a = out
             if l < Lc:
                 lin = self.critic.layers[l]
                 out = v_out if l == Lc - 1 else self.h_c[l][:M]
-                probs.append((in_c, lin.weight, lin.bias, out, self.critic.acts[l]))
+                xin, w = self._layer0("c", in_c) if l == 0 else (in_c, lin.weight)
+                probs.append((xin, w, lin.bias, out, self.critic.acts[l]))
                 in_c = out
             linear_forward(probs, self.prec)
 
@@ -127,8 +156,9 @@ class FeedForwardEngine:
             for i, (tag, inp, lin, out, act, ld0) in enumerate(specs):
                 xptr = 0 if inp is None else inp.data_ptr()
                 ldx = ld0 if inp is None else inp.stride(0)
-                arr[i] = nat.LinearFwd(xptr, lin.weight.data_ptr(), lin.bias.data_ptr(), out.data_ptr(), M,
-                                       lin.weight.shape[0], lin.weight.shape[1], ldx, out.stride(0), act)
+                w = self._layer0(tag, None, ld0)[1] if inp is None else lin.weight
+                arr[i] = nat.LinearFwd(xptr, w.data_ptr(), lin.bias.data_ptr(), out.data_ptr(), M,
+                                       w.shape[0], w.shape[1], ldx, out.stride(0), act)
                 if inp is None:
                     patch.append((i, tag))
             launches.append((arr, len(specs), patch))

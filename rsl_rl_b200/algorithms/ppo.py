@@ -177,6 +177,8 @@ class PPO:
         s = st.step
         if s >= st.num_transitions_per_env:
             raise OverflowError("Rollout buffer overflow! You should call clear() before adding new transitions.")
+        if s == 0 and eng.w0_pad:
+            eng.refresh_padded()  # parameters may have been loaded / modified since the last optimiser step
         x_a, x_c = self._inputs(obs)
         key = (x_a.stride(0), x_c.stride(0), x_a.shape[1], x_c.shape[1], self._group.values.data_ptr())
         plan = self._act_plans.get(s)
@@ -186,9 +188,11 @@ class PPO:
             views = (st.mu[s], st.values[s], st.actions[s], st.actions_log_prob[s], st.sigma[s])
             if self._act_in is None or self._act_in[0].shape != x_a.shape or self._act_in[1].shape != x_c.shape:
                 with torch.inference_mode(False):  # plain tensors: act() may also be called outside inference mode
-                    sa = torch.empty(x_a.shape, dtype=torch.float32, device=x_a.device)
-                    sc = sa if x_c.data_ptr() == x_a.data_ptr() else torch.empty(x_c.shape, dtype=torch.float32,
-                                                                                 device=x_c.device)
+                    pad4 = lambda d: (d + 3) // 4 * 4
+                    z = lambda t: torch.zeros(t.shape[0], pad4(t.shape[1]), dtype=torch.float32,
+                                              device=t.device)[:, :t.shape[1]]      # 16-byte row pitch, zero pad
+                    sa = z(x_a)
+                    sc = sa if x_c.data_ptr() == x_a.data_ptr() else z(x_c)
                     self._act_in = (sa, sc, torch.empty(views[0].shape, dtype=torch.float32, device=x_a.device))
             sa, sc, _ = self._act_in
             plan = dict(key=key, views=views, graph=None, launches=0, visits=0,
@@ -288,8 +292,8 @@ class PPO:
         f32 = dict(dtype=torch.float32, device=dev)
         pad4 = lambda d: (d + 3) // 4 * 4
         self._Oa, self._Oc = pol.num_actor_obs, pol.num_critic_obs
-        self._xa_raw = torch.empty(Bp, pad4(self._Oa), **f32)
-        self._xc_raw = self._xa_raw if pol.critic_shares_actor_input else torch.empty(Bp, pad4(self._Oc), **f32)
+        self._xa_raw = torch.zeros(Bp, pad4(self._Oa), **f32)   # pad columns stay zero (padded first-layer weights)
+        self._xc_raw = self._xa_raw if pol.critic_shares_actor_input else torch.zeros(Bp, pad4(self._Oc), **f32)
         A = self._engine.A
         self._p_actions = torch.empty(Bp, A, **f32)
         self._p_mu = torch.empty(Bp, A, **f32)
@@ -362,6 +366,7 @@ class PPO:
                     torch.distributed.all_reduce(self._group.grads_ext, op=torch.distributed.ReduceOp.SUM)
                 opt.fused_step(world_size=self.gpu_world_size, max_grad_norm=self.max_grad_norm, adaptive=adaptive,
                                desired_kl=self.desired_kl or 0.0, round_lr_fp32=self.is_multi_gpu)
+                eng.refresh_padded()
 
     def _update_fused(self):
         st, eng, opt = self.storage, self._engine, self.optimizer

@@ -226,3 +226,30 @@ def test_tf32_tensor_core_iteration_vs_oracle():
     else:
         ratio = r["lr_mine"] / r["lr_ref"]
         assert min(abs(ratio - 1.5 ** k) for k in range(-3, 4)) < 1e-6, "lr trajectories differ by more than threshold flips"
+
+
+def test_tf32_unaligned_observation_width_vs_oracle():
+    """Observation width 10 (row pitch not a multiple of 16 bytes): the tensor-core path reads a zero-padded shadow
+    of the first-layer weights and padded inputs."""
+    meta, obs, rewards, dones, time_outs, z, perms = _synthetic_problem(512, 8, 10, 6, [64, 32], 3, seed=11)
+    # one iteration, eager: forward parity of the padded path and the first update
+    r = _run_both(meta, obs, rewards, dones, time_outs, z, perms, 1, use_cuda_graph=False, gemm_precision="tf32")[0]
+    s, st = r["alg"].storage, r["st"]
+    assert r["alg"]._engine.w0_pad, "the padded shadow weights were expected to be in use"
+    assert rel_err(s.mu.cpu().numpy(), st["mu"]) < 1e-3
+    assert rel_err(s.values.cpu().numpy(), st["values"]) < 1e-3
+    init = np.concatenate([v.reshape(-1) for v in _init_params_like_torch(meta, 0).values()]).astype(np.float64)
+    upd, upd_ref = r["mine"].astype(np.float64) - init, r["ref"].astype(np.float64) - init
+    if abs(r["lr_mine"] - r["lr_ref"]) < 1e-12:
+        assert np.linalg.norm(upd - upd_ref) / np.linalg.norm(upd_ref) < 5e-2
+    # three iterations with the rollout / update CUDA graphs active: the shadow must follow the parameters
+    res = _run_both(meta, obs, rewards, dones, time_outs, z, perms, 3, use_cuda_graph=True, gemm_precision="tf32")
+    alg = res[-1]["alg"]
+    w = alg.policy.actor[0].weight
+    assert torch.equal(alg._engine.w0_pad["a"][:, :w.shape[1]], w.detach())
+    assert float(alg._engine.w0_pad["a"][:, w.shape[1]:].abs().max()) == 0.0
+    ratio = res[-1]["lr_mine"] / res[-1]["lr_ref"]
+    assert min(abs(ratio - 1.5 ** k) for k in range(-6, 7)) < 1e-6
+    if abs(ratio - 1.0) < 1e-9:
+        u, ur = res[-1]["mine"].astype(np.float64) - init, res[-1]["ref"].astype(np.float64) - init
+        assert np.linalg.norm(u - ur) / np.linalg.norm(ur) < 0.15
