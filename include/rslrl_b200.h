@@ -78,9 +78,10 @@ int rslrl_store_transition(int n_groups, const float* const* obs_src_host, float
 
 /* RolloutStorage.compute_returns (rsl_rl/storage/rollout_storage.py:127-149): reverse GAE scan over T
  * with done masking, returns, advantages = returns - values, and (normalize != 0) the global
- * (adv - mean) / (std_unbiased + 1e-8) normalisation, in ONE cooperative kernel.
  * rewards/values/returns/advantages: [T,N] fp32, dones: [T,N] u8, last_values: [N].
- * workspace: rslrl_gae_workspace_bytes(N) bytes of device scratch (need not be zeroed). */
+ * (adv - mean) / (std_unbiased + 1e-8) normalisation, in ONE kernel (grid barrier inside).
+ * workspace: rslrl_gae_workspace_bytes(N) bytes of device scratch, zero-initialised ONCE by the caller
+ * (the kernel re-arms it); one workspace must not be shared by launches that may run concurrently. */
 int64_t rslrl_gae_workspace_bytes(int N);
 int rslrl_gae_norm(const float* rewards, const float* values, const uint8_t* dones, const float* last_values,
                    float* returns, float* advantages, void* workspace, int T, int N, double gamma, double lam,

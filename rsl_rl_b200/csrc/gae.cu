@@ -1,4 +1,4 @@
-// GAE reverse scan + returns + advantage normalisation in one cooperative kernel.
+// GAE reverse scan + returns + advantage normalisation in one kernel (grid-wide barrier inside).
 // Replaces RolloutStorage.compute_returns (reference rsl_rl/storage/rollout_storage.py:127-149),
 // which issues ~400 elementwise launches over 24 [N,1] slices.
 //
@@ -10,35 +10,70 @@
 // explicit round-to-nearest intrinsics (no FMA contraction), so `returns` and the un-normalised
 // advantages are bit-identical to the reference.  The normalisation needs the global mean and
 // unbiased std of all T*N advantages: per-thread fp64 partials -> warp shuffles -> one fp64 pair per
-// block in a workspace -> grid.sync() -> every block reduces the per-block pairs in the same order
-// (deterministic, no atomics, nothing to zero) -> the advantages, still in registers, are written
-// once.  Algorithmic traffic: 17*T*N + 4*N bytes.
-#include <cooperative_groups.h>
-
+// block in a workspace -> grid barrier -> every block reduces the per-block pairs in the same order
+// (deterministic) -> the advantages, still in registers, are written once.
+// Algorithmic traffic: 17*T*N + 4*N bytes.
+// The barrier is a ticket counter in the workspace (all blocks are co-resident: the grid never exceeds what
+// the occupancy API reports as simultaneously resident, and the wait is bounded); it costs ~1 us for <=592
+// blocks and, unlike a cooperative launch, lets consecutive launches overlap their ramp-up.  The last block
+// to leave re-arms the counters, so the workspace only has to be zero ONCE (at allocation).
 #include "common.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace rslrl {
 
 constexpr int kGaeThreads = 128;
 constexpr int kGaeMaxBlocks = 4096;  // workspace capacity (pairs of doubles)
 
+struct GaeBarrier {
+  unsigned int arrived;
+  unsigned int departed;
+};
+
+__device__ __forceinline__ void gae_grid_barrier(GaeBarrier* bar) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(&bar->arrived, 1u);
+    const long long t0 = clock64();
+    while (*((volatile unsigned int*)&bar->arrived) < gridDim.x) {
+      if (clock64() - t0 > 4000000000LL) {
+        printf("rslrl gae: grid barrier timeout (block %d)\n", blockIdx.x);
+        __trap();
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void gae_grid_barrier_release(GaeBarrier* bar) {
+  // called after the post-barrier reads: the last block out re-arms the barrier for the next launch
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(&bar->departed, 1u) == gridDim.x - 1) {
+      bar->arrived = 0u;
+      bar->departed = 0u;
+      __threadfence();
+    }
+  }
+}
+
 __device__ __forceinline__ void gae_finalize_stats(double s, double ss, double* partials, double* smem,
-                                                   cg::grid_group& grid, int64_t B, float& mean_f, float& denom_f) {
+                                                   GaeBarrier* bar, int64_t B, float& mean_f, float& denom_f) {
   double v[2] = {s, ss};
   block_sum<2>(v, smem);
   if (threadIdx.x == 0) {
     partials[2 * blockIdx.x] = v[0];
     partials[2 * blockIdx.x + 1] = v[1];
   }
-  grid.sync();
+  gae_grid_barrier(bar);
   double t[2] = {0.0, 0.0};
   for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
     t[0] += partials[2 * i];
     t[1] += partials[2 * i + 1];
   }
   block_sum<2>(t, smem);
+  gae_grid_barrier_release(bar);
   if (threadIdx.x == 0) {
     const double n = (double)B;
     const double mean = t[0] / n;
@@ -58,8 +93,7 @@ __global__ void __launch_bounds__(kGaeThreads)
 gae_norm_reg_kernel(const float* __restrict__ rewards, const float* __restrict__ values,
                     const uint8_t* __restrict__ dones, const float* __restrict__ last_values,
                     float* __restrict__ returns, float* __restrict__ advantages, double* __restrict__ partials,
-                    int T, int N, float gamma, float lam, int normalize) {
-  cg::grid_group grid = cg::this_grid();
+                    GaeBarrier* bar, int T, int N, float gamma, float lam, int normalize) {
   __shared__ double smem[64];
   const int n = blockIdx.x * kGaeThreads + threadIdx.x;
   float a[TMAX];
@@ -96,7 +130,7 @@ gae_norm_reg_kernel(const float* __restrict__ rewards, const float* __restrict__
     }
   }
   float mean_f = 0.f, denom_f = 1.f;
-  if (normalize) gae_finalize_stats(s, ss, partials, smem, grid, (int64_t)T * N, mean_f, denom_f);
+  if (normalize) gae_finalize_stats(s, ss, partials, smem, bar, (int64_t)T * N, mean_f, denom_f);
   if (n < N) {
 #pragma unroll
     for (int i = 0; i < TMAX; ++i) {
@@ -112,9 +146,8 @@ gae_norm_reg_kernel(const float* __restrict__ rewards, const float* __restrict__
 __global__ void __launch_bounds__(kGaeThreads)
 gae_norm_generic_kernel(const float* __restrict__ rewards, const float* __restrict__ values,
                         const uint8_t* __restrict__ dones, const float* __restrict__ last_values,
-                        float* __restrict__ returns, float* advantages, double* __restrict__ partials, int T, int N,
-                        float gamma, float lam, int normalize) {
-  cg::grid_group grid = cg::this_grid();
+                        float* __restrict__ returns, float* advantages, double* __restrict__ partials, GaeBarrier* bar,
+                        int T, int N, float gamma, float lam, int normalize) {
   __shared__ double smem[64];
   double s = 0.0, ss = 0.0;
   const int stride = gridDim.x * kGaeThreads;
@@ -139,7 +172,7 @@ gae_norm_generic_kernel(const float* __restrict__ rewards, const float* __restri
   }
   if (!normalize) return;
   float mean_f, denom_f;
-  gae_finalize_stats(s, ss, partials, smem, grid, (int64_t)T * N, mean_f, denom_f);
+  gae_finalize_stats(s, ss, partials, smem, bar, (int64_t)T * N, mean_f, denom_f);
   for (int n = blockIdx.x * kGaeThreads + threadIdx.x; n < N; n += stride)
     for (int i = 0; i < T; ++i) {
       const size_t o = (size_t)i * N + n;
@@ -161,9 +194,8 @@ template <int TMAX>
 static int launch_reg(void** args, int blocks, cudaStream_t st) {
   static int cap = -1;
   if (cap < 0) cap = max_coop_blocks(gae_norm_reg_kernel<TMAX>);
-  if (blocks > cap) return -1;  // caller falls back to the generic kernel
-  cudaError_t e = cudaLaunchCooperativeKernel((void*)gae_norm_reg_kernel<TMAX>, dim3(blocks), dim3(kGaeThreads),
-                                              args, 0, st);
+  if (blocks > cap) return -1;  // more envs than resident threads: caller uses the grid-stride kernel
+  cudaError_t e = cudaLaunchKernel((void*)gae_norm_reg_kernel<TMAX>, dim3(blocks), dim3(kGaeThreads), args, 0, st);
   if (e != cudaSuccess) {
     set_error("rslrl_gae_norm: %s", cudaGetErrorString(e));
     return 1;
@@ -178,7 +210,7 @@ extern "C" {
 
 int64_t rslrl_gae_workspace_bytes(int N) {
   (void)N;
-  return (int64_t)rslrl::kGaeMaxBlocks * 2 * sizeof(double);
+  return (int64_t)rslrl::kGaeMaxBlocks * 2 * sizeof(double) + (int64_t)sizeof(rslrl::GaeBarrier) + 8;
 }
 
 int rslrl_gae_norm(const float* rewards, const float* values, const uint8_t* dones, const float* last_values,
@@ -190,7 +222,8 @@ int rslrl_gae_norm(const float* rewards, const float* values, const uint8_t* don
   RSLRL_CHECK_ARG(T > 0 && N > 0 && (int64_t)T * N > 1, "rslrl_gae_norm");
   cudaStream_t st = (cudaStream_t)stream;
   double* partials = (double*)workspace;
-  void* args[] = {&rewards, &values, &dones, &last_values, &returns, &advantages, &partials,
+  GaeBarrier* bar = (GaeBarrier*)(partials + 2 * kGaeMaxBlocks);
+  void* args[] = {&rewards, &values, &dones, &last_values, &returns, &advantages, &partials, &bar,
                   &T,       &N,      &gamma, &lam,         &normalize};
   const int blocks = (N + kGaeThreads - 1) / kGaeThreads;
   int rc = -1;
@@ -202,8 +235,7 @@ int rslrl_gae_norm(const float* rewards, const float* values, const uint8_t* don
   static int cap = -1;
   if (cap < 0) cap = max_coop_blocks(gae_norm_generic_kernel);
   const int gblocks = blocks < cap ? blocks : cap;
-  cudaError_t e = cudaLaunchCooperativeKernel((void*)gae_norm_generic_kernel, dim3(gblocks), dim3(kGaeThreads), args,
-                                              0, st);
+  cudaError_t e = cudaLaunchKernel((void*)gae_norm_generic_kernel, dim3(gblocks), dim3(kGaeThreads), args, 0, st);
   if (e != cudaSuccess) {
     set_error("rslrl_gae_norm: %s", cudaGetErrorString(e));
     return 1;

@@ -300,65 +300,12 @@ int simt_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* pr, cuda
 // ======================================================================================================
 // Narrow output layers (the 12-wide action head and the 1-wide value head).
 // A 128-wide MMA tile is >90 % padding for them and a launch costs more than their arithmetic, so they get
-// fp32 CUDA-core kernels shaped after their memory traffic instead:
-//   head_forward   y = act(x W^T + b)                                    thread per row, W broadcast from smem
+// fp32 CUDA-core kernel shaped after its memory traffic for the BACKWARD pass (the forward stays on the GEMM path):
 //   head_backward  dx = (dy W) * act'(h), dW += dy^T h, db += 1^T dy     warp per row, lane <-> 4 input columns
-// The backward fuses what would be one dgrad and one wgrad launch and reads h / writes dx exactly once
-// (2*M*K*4 bytes).  Used by both arithmetic modes (they are exact fp32).
+// It fuses what would be one dgrad and one wgrad launch and reads h / writes dx exactly once (2*M*K*4 bytes).
+// Used by both arithmetic modes (it is exact fp32).
 // ======================================================================================================
 namespace rslrl {
-
-constexpr int HEAD_MAX_N = 16;
-constexpr int HEAD_THREADS = 128;
-
-struct HeadFwdProblem {
-  const float* x; const float* w; const float* b; float* y;
-  int M, N, K, ldx, ldy, act;
-};
-struct HeadFwdBatch { HeadFwdProblem p[RSLRL_MAX_PROBLEMS]; };
-
-__global__ void __launch_bounds__(HEAD_THREADS) head_forward_kernel(const HeadFwdBatch batch) {
-  extern __shared__ __align__(16) float s_w[];  // [N][K] then bias[N]
-  const HeadFwdProblem P = batch.p[blockIdx.y];
-  const int N = P.N, K = P.K;
-  for (int i = threadIdx.x; i < N * K; i += HEAD_THREADS) s_w[i] = __ldg(P.w + i);
-  float* s_b = s_w + N * K;
-  if (threadIdx.x < N) s_b[threadIdx.x] = P.b ? __ldg(P.b + threadIdx.x) : 0.f;
-  __syncthreads();
-  const bool vec = (K & 3) == 0 && (P.ldx & 3) == 0 && ((uintptr_t)P.x & 15) == 0;
-  for (int row = blockIdx.x * HEAD_THREADS + threadIdx.x; row < P.M; row += gridDim.x * HEAD_THREADS) {
-    float acc[HEAD_MAX_N];
-#pragma unroll
-    for (int a = 0; a < HEAD_MAX_N; ++a) acc[a] = 0.f;
-    const float* xr = P.x + (size_t)row * P.ldx;
-    if (vec) {
-      for (int k = 0; k < K; k += 4) {
-        const float4 xv = __ldg((const float4*)(xr + k));
-#pragma unroll
-        for (int a = 0; a < HEAD_MAX_N; ++a) {
-          if (a < N) {
-            const float4 wv = *(const float4*)(s_w + a * K + k);
-            acc[a] = fmaf(xv.x, wv.x, acc[a]);
-            acc[a] = fmaf(xv.y, wv.y, acc[a]);
-            acc[a] = fmaf(xv.z, wv.z, acc[a]);
-            acc[a] = fmaf(xv.w, wv.w, acc[a]);
-          }
-        }
-      }
-    } else {
-      for (int k = 0; k < K; ++k) {
-        const float xv = __ldg(xr + k);
-#pragma unroll
-        for (int a = 0; a < HEAD_MAX_N; ++a)
-          if (a < N) acc[a] = fmaf(xv, s_w[a * K + k], acc[a]);
-      }
-    }
-    float* yr = P.y + (size_t)row * P.ldy;
-#pragma unroll
-    for (int a = 0; a < HEAD_MAX_N; ++a)
-      if (a < N) yr[a] = act_forward(P.act, acc[a] + s_b[a]);
-  }
-}
 
 struct HeadBwdProblem {
   const float* dy; const float* w; const float* h; float* dx; float* dw; float* db;
@@ -446,25 +393,7 @@ __global__ void __launch_bounds__(HEADB_WARPS * 32) head_backward_kernel(const H
   }
 }
 
-// returns -1 when the problems do not fit the head kernels (caller uses the general GEMM path)
-int head_linear_forward(int n, const rslrl_linear_fwd_t* pr, cudaStream_t st) {
-  HeadFwdBatch b{};
-  size_t smem = 0;
-  int max_m = 0;
-  for (int i = 0; i < n; ++i) {
-    if (pr[i].N > HEAD_MAX_N || pr[i].K > 1024 || pr[i].M < 1024 || pr[i].M > 8192) return -1;  // rollout-sized batches only
-    b.p[i] = HeadFwdProblem{pr[i].x, pr[i].w, pr[i].b, pr[i].y, pr[i].M, pr[i].N, pr[i].K, pr[i].ldx, pr[i].ldy, pr[i].act};
-    const size_t s = ((size_t)pr[i].N * pr[i].K + pr[i].N + 4) * sizeof(float);
-    if (s > smem) smem = s;
-    if (pr[i].M > max_m) max_m = pr[i].M;
-  }
-  if (smem > 48 * 1024) return -1;
-  int blocks = (max_m + HEAD_THREADS - 1) / HEAD_THREADS;
-  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-  head_forward_kernel<<<dim3(blocks, n), HEAD_THREADS, smem, st>>>(b);
-  return finish_launch("rslrl_linear_forward(head)");
-}
-
+// returns -1 when the problems do not fit the head kernel (caller uses the general GEMM path)
 int head_linear_backward(int n, const rslrl_linear_bwd_head_t* pr, cudaStream_t st) {
   HeadBwdBatch b{};
   for (int i = 0; i < n; ++i) {

@@ -179,8 +179,11 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// ELU(z) = z > 0 ? z : exp(z) - 1 with one MUFU.EX2 (abs. error ~1e-7, far below tf32 rounding)
-__device__ __forceinline__ float elu_fast(float z) { return z > 0.f ? z : ex2_approx(z * 1.4426950408889634f) - 1.f; }
+// ELU(z) = max(z,0) + (exp(min(z,0)) - 1): branch- and predicate-free so that the 32 independent chains of a
+// chunk interleave (one MUFU.EX2 each; abs. error ~1e-7, far below tf32 rounding)
+__device__ __forceinline__ float elu_fast(float z) {
+  return fmaxf(z, 0.f) + (ex2_approx(fminf(z, 0.f) * 1.4426950408889634f) - 1.f);
+}
 
 // ------------------------------------------------------------------------------- persistent kernel
 // One CTA per SM loops over the tiles of all grouped problems (static round-robin schedule): the prologue
@@ -423,11 +426,11 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
             float4* const hp = (float4*)(my_row + ((u ^ sw) << 4));
             const float4 h = *hp;
             float4 o;
-            if (P.act == RSLRL_ACT_ELU) {
-              o.x = x[4 * u + 0] * (h.x > 0.f ? 1.f : h.x + 1.f);
-              o.y = x[4 * u + 1] * (h.y > 0.f ? 1.f : h.y + 1.f);
-              o.z = x[4 * u + 2] * (h.z > 0.f ? 1.f : h.z + 1.f);
-              o.w = x[4 * u + 3] * (h.w > 0.f ? 1.f : h.w + 1.f);
+            if (P.act == RSLRL_ACT_ELU) {  // ELU'(z) from the output: 1 for h > 0, h + 1 otherwise = min(h,0) + 1
+              o.x = x[4 * u + 0] * (fminf(h.x, 0.f) + 1.f);
+              o.y = x[4 * u + 1] * (fminf(h.y, 0.f) + 1.f);
+              o.z = x[4 * u + 2] * (fminf(h.z, 0.f) + 1.f);
+              o.w = x[4 * u + 3] * (fminf(h.w, 0.f) + 1.f);
             } else {
               o.x = x[4 * u + 0] * act_grad_from_output(P.act, h.x);
               o.y = x[4 * u + 1] * act_grad_from_output(P.act, h.y);

@@ -7,7 +7,6 @@ int simt_linear_forward(int n, const rslrl_linear_fwd_t* pr, cudaStream_t st);
 int simt_linear_backward_data(int n, const rslrl_linear_bwd_data_t* pr, cudaStream_t st);
 int simt_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* pr, cudaStream_t st);
 int tc_linear_forward(int n, const rslrl_linear_fwd_t* pr, cudaStream_t st);
-int head_linear_forward(int n, const rslrl_linear_fwd_t* pr, cudaStream_t st);
 int head_linear_backward(int n, const rslrl_linear_bwd_head_t* pr, cudaStream_t st);
 int tc_linear_backward_data(int n, const rslrl_linear_bwd_data_t* pr, cudaStream_t st);
 int tc_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* pr, cudaStream_t st);
@@ -22,11 +21,6 @@ int rslrl_linear_forward(int n, const rslrl_linear_fwd_t* probs_host, int precis
   for (int i = 0; i < n; ++i) {
     const rslrl_linear_fwd_t& p = probs_host[i];
     RSLRL_CHECK_ARG(p.x && p.w && p.y && p.M > 0 && p.N > 0 && p.K > 0 && p.ldx >= p.K && p.ldy >= p.N, what);
-  }
-  if (precision == RSLRL_PREC_FP32 || precision == RSLRL_PREC_TF32) {
-    // narrow heads (N <= 16) on many rows: dedicated exact-fp32 kernel in both arithmetic modes
-    const int rc = head_linear_forward(n, probs_host, (cudaStream_t)stream);
-    if (rc >= 0) return rc;
   }
   if (precision == RSLRL_PREC_FP32) return simt_linear_forward(n, probs_host, (cudaStream_t)stream);
   if (precision == RSLRL_PREC_TF32) {

@@ -77,7 +77,7 @@ class RolloutStorage:
         self.step = 0
 
         self._store_plans = {}
-        self._gae_ws = torch.empty(int(nat.lib().rslrl_gae_workspace_bytes(N)), dtype=torch.uint8, device=device)
+        self._gae_ws = torch.zeros(int(nat.lib().rslrl_gae_workspace_bytes(N)), dtype=torch.uint8, device=device)
         # hooks used by the parity tests to inject a recorded permutation
         self._randperm = lambda n: torch.randperm(n, requires_grad=False, device=self.device)
 
