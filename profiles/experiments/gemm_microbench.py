@@ -9,6 +9,7 @@ from rsl_rl_b200.networks.mlp import linear_forward, linear_backward_data, linea
 prec = nat.PREC_CODES[sys.argv[1] if len(sys.argv) > 1 else "tf32"]
 M = int(sys.argv[2]) if len(sys.argv) > 2 else 24576
 dev = "cuda"
+KINDS = os.environ.get("MB_KINDS", "f,w,d,h").split(",")  # restrict the kinds timed (kernel experiments)
 dims_a, dims_c = [48, 512, 256, 128, 12], [48, 512, 256, 128, 1]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 ELU = nat.ACT_CODES["elu"]
@@ -40,13 +41,13 @@ for l in range(4):
         probs_w.append((dy, x, dw, None))
         probs_h.append((dy, w, x, dx, dw, dbp[:N].contiguous() if N <= K else None, ELU))
         flop += 2 * M * N * K
-    tf = timeit(lambda: linear_forward(probs_f, prec))
-    tw = timeit(lambda: linear_backward_weight(probs_w, prec))
-    td = timeit(lambda: linear_backward_data(probs_d, prec)) if l > 0 else 0.0
-    if l == 3:
+    tf = timeit(lambda: linear_forward(probs_f, prec)) if 'f' in KINDS else 0.0
+    tw = timeit(lambda: linear_backward_weight(probs_w, prec)) if 'w' in KINDS else 0.0
+    td = timeit(lambda: linear_backward_data(probs_d, prec)) if l > 0 and 'd' in KINDS else 0.0
+    if l == 3 and 'h' in KINDS:
         th = timeit(lambda: linear_backward_head(probs_h))
         print(f"layer 3 fused head backward (dgrad+wgrad+db): {th:.1f} us")
-    print(f"layer {l} K={dims_a[l]:4d} N={dims_a[l+1]:4d}  fwd {tf:8.1f} us {flop/tf/1e6:7.1f} TF | wgrad {tw:8.1f} us {flop/tw/1e6:7.1f} TF"
+    print(f"layer {l} K={dims_a[l]:4d} N={dims_a[l+1]:4d}  fwd {tf:8.1f} us {(flop/tf/1e6 if tf else 0):7.1f} TF | wgrad {tw:8.1f} us {(flop/tw/1e6 if tw else 0):7.1f} TF"
           f" | dgrad {td:8.1f} us {(flop/td/1e6 if td else 0):7.1f} TF")
     tot_us += tf + tw + td; tot_flop += flop * (3 if l > 0 else 2)
 print(f"minibatch GEMM total {tot_us:.1f} us, {tot_flop/tot_us/1e6:.1f} TFLOP/s, x20 = {tot_us*20/1e3:.2f} ms/update")

@@ -40,15 +40,18 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    """Compile every .cu under csrc/ into one shared library (object files in build/, parallel)."""
-    if not force and not is_stale():
+def build_library(force: bool = False, verbose: bool = False, out: str = None, extra_flags=()) -> str:
+    """Compile every .cu under csrc/ into one shared library (object files in build/, parallel).
+    `out` / `extra_flags` build an experimental variant next to the product library (kernel A/B runs, tracing)."""
+    variant = out is not None or bool(extra_flags)
+    out = out or LIBPATH
+    if not force and not variant and not is_stale():
         return LIBPATH
-    os.makedirs(LIBDIR, exist_ok=True)
-    objdir = os.path.join(PKG, "..", "build", "obj")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    objdir = os.path.join(PKG, "..", "build", "obj_variant" if variant else "obj")
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
-    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + list(extra_flags)
     procs = []
     objs = []
     for src in sources():
@@ -59,19 +62,23 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, p in procs:
-        out, _ = p.communicate()
-        if verbose and out:
-            print(out)
+        log, _ = p.communicate()
+        if verbose and log:
+            print(log)
         if p.returncode != 0:
-            raise RuntimeError(f"nvcc failed on {src}:\n{out}")
-    link = [nvcc, "-shared", "-o", LIBPATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+            raise RuntimeError(f"nvcc failed on {src}:\n{log}")
+    link = [nvcc, "-shared", "-o", out, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc link failed:\n{r.stdout}")
-    return LIBPATH
+    return out
 
 
 if __name__ == "__main__":
     import sys
 
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    # python -m rsl_rl_b200._build [--force] [-v] [--out PATH] [-DFLAG ...]
+    argv = sys.argv[1:]
+    out_path = argv[argv.index("--out") + 1] if "--out" in argv else None
+    print(build_library(force="--force" in argv, verbose="-v" in argv, out=out_path,
+                        extra_flags=[a for a in argv if a.startswith("-D")]))

@@ -104,7 +104,8 @@ _lib = None
 
 
 def library_path() -> str:
-    return _build.LIBPATH
+    # RSLRL_B200_LIB: load another build of the same ABI (A/B kernel experiments); never a fallback
+    return os.environ.get("RSLRL_B200_LIB") or _build.LIBPATH
 
 
 def lib():

@@ -212,6 +212,23 @@ struct TcpScalars {  // per-problem scalars mirrored into shared memory once per
   int M, N, ldc, act, tma_out, block_n, tiles_m, tiles_n, splits, kb_per_split, num_kb, tile_count;
 };
 
+// Optional in-kernel timeline (build with -DRSLRL_TC_TRACE, read with profiles/experiments/gemm_trace.py):
+// per CTA 32 globaltimer slots: 0 entry, 1 prologue done, 2 first TMA, 3 first full barrier, 4+2j mainloop of the
+// CTA's j-th tile issued, 5+2j its epilogue issued (epilogue warp 0), 31 exit.
+#ifdef RSLRL_TC_TRACE
+__device__ unsigned long long g_tc_trace[148 * 32];
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define TRACE(slot) do { if ((slot) < 31 || (slot) == 31) g_tc_trace[blockIdx.x * 32 + ((slot) < 31 ? (slot) : 31)] = gtime(); } while (0)
+#define TRACE_TILE(slot) do { if ((slot) < 31) g_tc_trace[blockIdx.x * 32 + (slot)] = gtime(); } while (0)
+#else
+#define TRACE(slot) do { } while (0)
+#define TRACE_TILE(slot) do { } while (0)
+#endif
+
 template <int MODE>
 __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(const __grid_constant__ TcBatch batch,
                                                                             const int n_problems) {
@@ -240,6 +257,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
   float* const bias_stage = (float*)(sp + 2);               // [TCP_EPI_WARPS][32], 16-byte aligned
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) TRACE(0);
 
   if (threadIdx.x < n_problems) {
     const TcProblem& P = batch.p[threadIdx.x];
@@ -279,6 +297,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (threadIdx.x == 0) TRACE(1);
 
   int total_tiles = 0;
   for (int i = 0; i < n_problems; ++i) total_tiles += sp[i].tile_count;
@@ -313,6 +332,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
           mbar_wait(&empty_bar[s], ((it / stages) & 1) ^ 1);
           uint8_t* sa = ring + (size_t)s * stage_bytes;
           uint8_t* sb = sa + a_bytes;
+          if (it == 0) TRACE(2);
           mbar_expect_tx(&full_bar[s], tx_bytes);
           const int k0 = kb * TC_BLOCK_K;
           if (!A_MN) {
@@ -345,6 +365,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int s = it % stages;
         mbar_wait(&full_bar[s], (it / stages) & 1);
+        if (it == 0 && lane == 0) TRACE(3);
         tcgen05_fence_after();
         if (elect_one()) {
           const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
@@ -365,6 +386,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
         }
         __syncwarp();
       }
+      if (lane == 0) TRACE_TILE(4 + 2 * j);
     }
   } else if (warp < 2 + TCP_EPI_WARPS) {
     // ===================================================================== epilogue warps
@@ -518,6 +540,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[as])) : "memory");
       }
       gbase += nchunks;
+      if (ew == 0 && lane == 0) TRACE_TILE(5 + 2 * j);
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     tcgen05_fence_before();
@@ -572,6 +595,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
   }
 
   __syncthreads();
+  if (threadIdx.x == 0) TRACE(31);
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -804,3 +828,9 @@ int colsum_accumulate(const float* x, int M, int N, int ld, float* out, cudaStre
 }
 
 }  // namespace rslrl
+
+#ifdef RSLRL_TC_TRACE
+extern "C" int rslrl_debug_read_trace(unsigned long long* host) {
+  return (int)cudaMemcpyFromSymbol(host, rslrl::g_tc_trace, sizeof(unsigned long long) * 148 * 32);
+}
+#endif

@@ -471,4 +471,6 @@ def test_linear_backward_head_fused(M, K, N, act):
     ref_dx = O.act_backward(act, z_prev.cpu().numpy(), h.cpu().numpy(), dh.astype(np.float32)) if act != "identity" else dh
     assert rel_err(dx.cpu().numpy(), ref_dx) < 1e-5
     assert rel_err(dw.cpu().numpy(), 1 + (dy.double().T @ h.double()).cpu().numpy()) < 1e-5
-    assert rel_err(db.cpu().numpy(), 1 + dy.double().sum(0).cpu().numpy()) < 1e-5
+    # a column sum of M zero-mean values cancels: measure the error against the sum of magnitudes
+    db_err = (db.double() - 1 - dy.double().sum(0)).abs().max() / dy.double().abs().sum(0).max()
+    assert float(db_err) < 1e-6
