@@ -365,7 +365,16 @@ def run_ours(args):
     if line is not None:
         print(json.dumps(line), flush=True)
     if world > 1 and torch.distributed.is_initialized():
+        # the captured update() graphs hold NCCL work: release them before the communicator goes away, and never let
+        # the teardown of the process group keep a finished benchmark alive
+        for r in (runner, hrunner):
+            r.alg.release_graphs()
+        torch.cuda.synchronize()
+        torch.distributed.barrier()
+        sys.stdout.flush()
+        threading.Timer(20.0, lambda: os._exit(0)).start()
         torch.distributed.destroy_process_group()
+        os._exit(0)
 
 
 def main():

@@ -23,6 +23,7 @@ the optimiser, with the surrounding algebra expressed through autograd).
 """
 from __future__ import annotations
 
+import os
 from itertools import chain
 
 import torch
@@ -34,6 +35,9 @@ from ..storage import RolloutStorage
 from ..utils import string_to_callable
 from . import _engine
 from .flat_params import FlatParamGroup, FusedAdam
+
+
+_GRAPH_COLLECTIVES = os.environ.get("RSLRL_GRAPH_COLLECTIVES", "1") != "0"
 
 
 class PPO:
@@ -137,6 +141,7 @@ class PPO:
         if self.symmetry is not None:
             self._engine_reason = self._engine_reason or "symmetry"
         self._graph = None
+        self._graph_failed = False
         self._graph_key = None
         self._graph_launches = 0
         self._eager_updates = 0
@@ -379,8 +384,11 @@ class PPO:
                 self._discard.normal_()
         opt.dev_state.set_lr(self.learning_rate)
 
-        graph_ok = self.use_cuda_graph and not self.is_multi_gpu and self._mb_hook is None
-        if not graph_ok or self._eager_updates < 1:
+        # multi-GPU: the per-minibatch NCCL all-reduce is captured with the kernels (NCCL collectives are graph
+        # capturable); RSLRL_GRAPH_COLLECTIVES=0 keeps the multi-GPU update eager
+        graph_ok = (self.use_cuda_graph and self._mb_hook is None and not self._graph_failed
+                    and (not self.is_multi_gpu or _GRAPH_COLLECTIVES))
+        if not graph_ok or self._eager_updates < (2 if self.is_multi_gpu else 1):
             # the first update always runs eagerly (module loading, lazy initialisation); later ones replay a graph
             self._eager_updates += 1
             self._update_kernels()
@@ -390,8 +398,19 @@ class PPO:
             torch.cuda.synchronize()
             before, host_step = nat.launch_count(), opt._host_step
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            try:
+                with torch.cuda.graph(g):
+                    self._update_kernels()
+            except Exception as exc:  # e.g. a communicator that cannot be captured: stay eager from now on
+                if not self.is_multi_gpu:
+                    raise
+                print(f"[rsl_rl_b200] update() graph capture with the all-reduce failed ({exc}); running eagerly")
+                self._graph_failed = True
+                nat.lib().rslrl_add_launch_count(-(nat.launch_count() - before) & 0xFFFFFFFFFFFFFFFF)
+                opt._host_step = host_step
+                torch.cuda.synchronize()
                 self._update_kernels()
+                return self._finish_update()
             self._graph_launches = nat.launch_count() - before
             nat.lib().rslrl_add_launch_count(-self._graph_launches & 0xFFFFFFFFFFFFFFFF)  # capture launched nothing
             opt._host_step = host_step
@@ -400,6 +419,15 @@ class PPO:
         nat.lib().rslrl_add_launch_count(self._graph_launches)
         opt._host_step += M * E
         return self._finish_update()
+
+    def release_graphs(self):
+        """Drops the captured CUDA graphs (update() and the per-step act() graphs).  Call it before
+        `torch.distributed.destroy_process_group()`: the multi-GPU update graph holds NCCL work."""
+        torch.cuda.synchronize()
+        self._graph, self._graph_key = None, None
+        for plan in self._act_plans.values():
+            plan["graph"] = None
+            plan["visits"] = 0
 
     def _hyper_key(self):
         return (self.clip_param, self.value_loss_coef, self.entropy_coef, self.use_clipped_value_loss, self.desired_kl,
