@@ -114,9 +114,10 @@ def time_dominant_kernel(alg, reps: int = 2):
 
     eng, mb, M = alg._engine, alg._mb, alg.num_mini_batches
     xa, xc = alg._xa_raw[:, :alg._Oa], alg._xc_raw[:, :alg._Oc]
-    L = eng.actor.L
-    launches_per_mb = L + L + (L - 1)
+    from rsl_rl_b200 import _native as nat
+
     total_ms, n_mb = 0.0, 0
+    launches0 = nat.launch_count()
     for _ in range(reps):
         for i in range(M * alg.num_learning_epochs):
             r = slice((i % M) * mb, (i % M + 1) * mb)
@@ -128,6 +129,7 @@ def time_dominant_kernel(alg, reps: int = 2):
             e1.synchronize()
             total_ms += e0.elapsed_time(e1)
             n_mb += 1
+    launches_per_mb = (nat.launch_count() - launches0) / n_mb
     alg._group.zero_grad()
     flops = gemm_flops_per_minibatch(mb)
     return dict(ms_per_minibatch=total_ms / n_mb, launches_per_minibatch=launches_per_mb,
@@ -331,7 +333,8 @@ def run_ours(args):
         roofline = dict(bound="tensor", achieved=dom["tflops"], peak=peaks["tf_sustained"], unit="TFLOP/s",
                         frac=dom["tflops"] / peaks["tf_sustained"], traffic=None,
                         kernel=("sgemm_kernel (fp32 CUDA-core FMA)" if args.precision == "fp32"
-                                else "tc_gemm_kernel (tf32 tcgen05)"),
+                                else "mlp3_forward_kernel + tc_gemm_persistent_kernel<dgrad|wgrad> (tf32 tcgen05): "
+                                     "all dense launches of one minibatch forward + backward"),
                         avg_launch_us=dom["avg_launch_us"], flops_per_launch=dom["flops_per_launch"],
                         peak_source=peaks["source"] + ", bf16 dense sustained")
         gae_c1, gae_c3 = time_gae(device, NUM_ENVS), time_gae(device, 65536)

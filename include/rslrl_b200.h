@@ -139,6 +139,21 @@ typedef struct {
   int act;         /* activation of the previous layer */
 } rslrl_linear_bwd_head_t;
 
+/* Whole 3-hidden-layer MLP forward in ONE launch (rsl_rl/networks/mlp.py:106-114 for actor and critic):
+ *   y = W4 act(W3 act(W2 act(W1 x + b1) + b2) + b3) + b4
+ * on tcgen05 (tf32) with the activations kept in shared / tensor memory between the layers.  h[0..2] (all three or
+ * none) receive the hidden activations for the backward pass; NULL (rollout, inference) stores nothing but y. */
+typedef struct {
+  const float* x;    /* [M,K0], row stride ldx */
+  const float* w[4]; /* nn.Linear weights: [N1,K0] (row stride ldw0), [N2,N1], [N3,N2], [N4,N3] row-major */
+  const float* b[4]; /* biases (entries may be NULL) */
+  float* h[3];       /* [M,N1], [M,N2], [M,N3] with row strides ldh[i], or all NULL */
+  float* y;          /* [M,N4], row stride ldy */
+  int M, K0, N1, N2, N3, N4;
+  int ldx, ldw0, ldh[3], ldy;
+  int act;           /* RSLRL_ACT_* of the three hidden layers */
+} rslrl_mlp3_fwd_t;
+
 /* Each call runs `n` independent problems (e.g. actor and critic) in one launch; *_host arrays live
  * in host memory and are copied into the kernel parameters. */
 int rslrl_linear_forward(int n, const rslrl_linear_fwd_t* probs_host, int precision, rslrl_stream_t stream);
@@ -150,6 +165,9 @@ int rslrl_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* probs_h
  * launch that reads h and writes dx exactly once.  Returns a non-zero code (message via rslrl_last_error) if a
  * problem does not qualify (N > 12, K % 4 != 0, unaligned rows); callers then use the two general calls. */
 int rslrl_linear_backward_head(int n, const rslrl_linear_bwd_head_t* probs_host, rslrl_stream_t stream);
+/* Returns 4 when a net's shape is not eligible (N1 in 128..512 step 128, N2 in {128,256}, N3 <= 128 step 32,
+ * N4 <= 16, 16-byte aligned rows, same M for all nets): the caller then runs the layers one by one. */
+int rslrl_mlp3_forward(int n, const rslrl_mlp3_fwd_t* nets_host, rslrl_stream_t stream);
 
 /* ---- PPO objective (rsl_rl/algorithms/ppo.py:255-315), forward + hand-derived backward ---------- */
 

@@ -47,6 +47,12 @@ class LinearBwdHead(C.Structure):
                 ("ldx", c_int), ("act", c_int)]
 
 
+class Mlp3Fwd(C.Structure):
+    _fields_ = [("x", c_void_p), ("w", c_void_p * 4), ("b", c_void_p * 4), ("h", c_void_p * 3), ("y", c_void_p),
+                ("M", c_int), ("K0", c_int), ("N1", c_int), ("N2", c_int), ("N3", c_int), ("N4", c_int),
+                ("ldx", c_int), ("ldw0", c_int), ("ldh", c_int * 3), ("ldy", c_int), ("act", c_int)]
+
+
 class OptState(C.Structure):
     _fields_ = [("lr", c_double), ("clip_scale", c_double), ("total_norm", c_double), ("step_size", c_double),
                 ("bc2_sqrt", c_double), ("kl_mean", c_double), ("step", C.c_longlong), ("pad_", C.c_longlong)]
@@ -75,6 +81,7 @@ _SIGNATURES = {
     "rslrl_linear_backward_data": (c_int, [c_int, c_void_p, c_int, c_void_p]),
     "rslrl_linear_backward_weight": (c_int, [c_int, c_void_p, c_int, c_void_p]),
     "rslrl_linear_backward_head": (c_int, [c_int, c_void_p, c_void_p]),
+    "rslrl_mlp3_forward": (c_int, [c_int, c_void_p, c_void_p]),
     "rslrl_loss_workspace_bytes": (c_i64, []),
     "rslrl_sum_sumsq": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_void_p]),
     "rslrl_optim_workspace_bytes": (c_i64, [c_i64]),

@@ -19,12 +19,14 @@ from __future__ import annotations
 
 from typing import List, Optional
 
+import os
+
 import torch
 import torch.nn as nn
 
 from .. import _native as nat
 from ..networks.mlp import (MLP, head_backward_ok, linear_backward_data, linear_backward_head,
-                            linear_backward_weight, linear_forward)
+                            linear_backward_weight, linear_forward, mlp3_eligible, mlp3_forward, mlp3_struct)
 from .flat_params import FlatParamGroup, FusedAdam
 
 
@@ -87,6 +89,9 @@ class FeedForwardEngine:
                 if K % 4:
                     self.w0_pad[tag] = torch.zeros(net.dims[1], (K + 3) // 4 * 4, **f32)
         self.refresh_padded()
+        # whole-MLP forward in one launch (activations stay on chip between the layers): tf32 mode, eligible shapes
+        self.fused_fwd = (precision == "tf32" and os.environ.get("RSLRL_FUSED_MLP", "1") != "0"
+                          and all(mlp3_eligible(n.dims, n.acts) for n in (self.actor, self.critic)))
         self.loss_ws = torch.zeros(int(nat.lib().rslrl_loss_workspace_bytes()), dtype=torch.uint8, device=self.device)
         self.sum_ws = torch.zeros(64, dtype=torch.uint8, device=self.device)
         self.adv_stats = torch.zeros(2, dtype=torch.float64, device=self.device)
@@ -114,6 +119,14 @@ class FeedForwardEngine:
         """Grouped forward of actor and critic on M = x.shape[0] rows; hidden activations stay in
         self.h_a / self.h_c (rows [:M]) for the backward pass."""
         M = (x_a if actor else x_c).shape[0]
+        if self.fused_fwd and self._fused_inputs_ok(x_a if actor else None, x_c if critic else None):
+            nets = []
+            if actor:
+                nets.append(self._mlp3("a", x_a.data_ptr(), x_a.stride(0), M, mu_out, store=True))
+            if critic:
+                nets.append(self._mlp3("c", x_c.data_ptr(), x_c.stride(0), M, v_out, store=True))
+            mlp3_forward(nets)
+            return
         La, Lc = self.actor.L if actor else 0, self.critic.L if critic else 0
         in_a, in_c = x_a, x_c
         for l in range(max(La, Lc)):
@@ -132,10 +145,36 @@ class FeedForwardEngine:
                 in_c = out
             linear_forward(probs, self.prec)
 
+    def _fused_inputs_ok(self, x_a, x_c) -> bool:
+        return all(x is None or (x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0 and x.stride(1) == 1)
+                   for x in (x_a, x_c))
+
+    def _mlp3(self, tag: str, x_ptr: int, ldx: int, M: int, out: torch.Tensor, store: bool):
+        net, hs = (self.actor, self.h_a) if tag == "a" else (self.critic, self.h_c)
+        w0 = self._layer0(tag, None, ldx)[1]
+        weights = [w0] + [l.weight for l in net.layers[1:]]
+        return mlp3_struct(x_ptr, ldx, M, weights, [l.bias for l in net.layers],
+                           [h[:M] for h in hs] if store else None, out, net.acts[0])
+
     # ---- prebuilt launch plans for the rollout: everything static except the observation pointers ---------
     def build_forward_plan(self, M: int, ld_a: int, ld_c: int, mu_out: torch.Tensor, v_out: torch.Tensor,
                            actor: bool = True, critic: bool = True):
         """ctypes launch arrays for `forward` on M rows with outputs fixed; returns a callable(xa_ptr, xc_ptr)."""
+        if self.fused_fwd and ld_a % 4 == 0 and ld_c % 4 == 0:
+            # rollout: nothing is stored but the outputs (the update recomputes the activations of its minibatches)
+            tags = (["a"] if actor else []) + (["c"] if critic else [])
+            outs = {"a": mu_out, "c": v_out}
+            lds = {"a": ld_a, "c": ld_c}
+            structs = [self._mlp3(t, 0, lds[t], M, outs[t], store=False) for t in tags]
+            arr = (nat.Mlp3Fwd * len(structs))(*structs)
+            fn3, check3, n3 = nat.lib().rslrl_mlp3_forward, nat.check, len(structs)
+
+            def run_fused(xa_ptr: int, xc_ptr: int):
+                for i, t in enumerate(tags):
+                    arr[i].x = xa_ptr if t == "a" else xc_ptr
+                check3(fn3(n3, arr, nat.stream_ptr()))
+
+            return run_fused
         La, Lc = self.actor.L if actor else 0, self.critic.L if critic else 0
         launches = []
         in_a = in_c = None  # layer-0 inputs are patched per call

@@ -30,12 +30,9 @@
 #include <unordered_map>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace rslrl {
-
-constexpr int TC_BLOCK_M = 128;
-constexpr int TC_BLOCK_K = 32;  // tf32 elements = one 128-byte swizzle row
-constexpr int TC_UMMA_K = 8;    // tf32 MMA depth (32 bytes)
 
 enum { TC_FWD = 0, TC_DGRAD = 1, TC_WGRAD = 2 };
 
@@ -54,136 +51,6 @@ struct TcProblem {
 struct alignas(64) TcBatch {
   TcProblem p[2];
 };
-
-// ---------------------------------------------------------------------------------------------- PTX
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a broken pipeline traps (launch failure reported to the host) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("rslrl tc_gemm: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-
-// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor layout, version 1)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
-                                                   uint32_t layout_type) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
-  d |= (uint64_t)(layout_type & 7) << 61;
-  return d;
-}
-constexpr uint32_t kLayoutSw128 = 2;         // K-major operands
-constexpr uint32_t kLayoutSw128Base32 = 1;   // MN-major tf32 operands
-
-// UMMA instruction descriptor: tf32 x tf32 -> f32, M = 128
-__device__ __forceinline__ uint32_t make_idesc(int n, bool a_mn_major, bool b_mn_major) {
-  uint32_t d = 0;
-  d |= 1u << 4;                      // accumulator format F32
-  d |= 2u << 7;                      // A format TF32
-  d |= 2u << 10;                     // B format TF32
-  d |= (a_mn_major ? 1u : 0u) << 15;
-  d |= (b_mn_major ? 1u : 0u) << 16;
-  d |= (uint32_t)(n >> 3) << 17;
-  d |= (uint32_t)(TC_BLOCK_M >> 4) << 24;
-  return d;
-}
-
-#define TMEM_LD_32x32(taddr, v)                                                                                      \
-  asm volatile(                                                                                                      \
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,"   \
-      "%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"                                                 \
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),  \
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),       \
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),      \
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                    \
-      : "r"(taddr))
-#define TMEM_LD_32x16(taddr, v)                                                                                      \
-  asm volatile(                                                                                                      \
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"       \
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),  \
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])                     \
-      : "r"(taddr))
-
-// ------------------------------------------------------------------------------------------- kernel
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"((uint64_t)map),
-               "r"(smem_u32(src)), "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
-  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                   (uint64_t)map),
-               "r"(smem_u32(src)), "r"(c0), "r"(c1)
-               : "memory");
-}
-
-// fast activations for the tf32 path (errors << tf32 rounding)
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// ELU(z) = max(z,0) + (exp(min(z,0)) - 1): branch- and predicate-free so that the 32 independent chains of a
-// chunk interleave (one MUFU.EX2 each; abs. error ~1e-7, far below tf32 rounding)
-__device__ __forceinline__ float elu_fast(float z) {
-  return fmaxf(z, 0.f) + (ex2_approx(fminf(z, 0.f) * 1.4426950408889634f) - 1.f);
-}
 
 // ------------------------------------------------------------------------------- persistent kernel
 // One CTA per SM loops over the tiles of all grouped problems (static round-robin schedule): the prologue
@@ -645,6 +512,12 @@ static bool make_map(CUtensorMap* map, const float* base, long long rows, long l
   return r == CUDA_SUCCESS;
 }
 
+// exported to the other tcgen05 translation units (mlp_fused.cu)
+bool tc_make_map(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_cols,
+                 int box_rows, bool operand) {
+  return make_map(map, base, rows, cols, ld, box_cols, box_rows, false, operand);
+}
+
 static bool tma_ok(const void* p, long long ld) { return ((uintptr_t)p & 15) == 0 && (ld % 4) == 0; }
 
 static int max_block_n() { return TCP_MAX_BLOCK_N; }
@@ -656,7 +529,9 @@ static int pick_block_n(int N) {
   return b;
 }
 
-static int num_sms() {
+int tc_num_sms();
+static int num_sms() { return tc_num_sms(); }
+int tc_num_sms() {
   static int n = 0;
   if (n == 0) {
     int dev = 0;

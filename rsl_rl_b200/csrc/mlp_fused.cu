@@ -1,0 +1,548 @@
+// Fused forward of a 3-hidden-layer MLP (x -> N1 -> N2 -> N3 -> N4) on sm_100a: one persistent kernel, one CTA
+// per SM, each work item = (net, 128-row tile).  All four layers run on tcgen05 (kind::tf32) with the
+// accumulators in TMEM; the activations h1, h2, h3 never leave the SM between layers:
+//
+//   L1   acc1[c&1] (128 TMEM columns, double buffered) = x_tile W1[c*128:(c+1)*128,:]^T   per 128-column chunk c
+//        epilogue: + bias, activation, round to tf32 (rna) -> "granules" (128 rows x 32 columns, 16 KB, K-major
+//        128-byte swizzle) in shared memory = the A operand of the next layer, read in place by the MMA
+//   L2   acc2 (N2 <= 256 columns) += granule x W2[:, k-block]^T  while the epilogue produces the next chunk
+//   L3   acc3 (aliases acc1[0])   likewise from the h2 granules;  L4  acc4 (aliases acc1[1], 16 columns) from h3
+//   update mode: a store warp copies every granule to h1/h2/h3 in HBM with TMA (they are the saved activations of
+//   the backward pass); rollout mode stores nothing but the N4 outputs.
+//
+// Warps: 0 TMA producer (weight ring: x and weight k-blocks in MMA consumption order), 1 MMA issuer + TMEM owner,
+// 2 granule store warp, 3.. epilogue warps (E = 16: one (row-quarter, 32-column block) unit each per 128-column
+// chunk).  Shared memory: weight ring (32 KB stages), granule ring (16 KB each), biases of both nets, barriers.
+//
+// Numerics are those of the layer-by-layer tcgen05 path (gemm_tc.cu): operands rounded fp32 -> tf32 to nearest
+// (TMA does it for x and the weights, the epilogue for the activations), fp32 accumulation in the same k order.
+// Replaces rsl_rl/networks/mlp.py:106-114 (MLP.forward) for actor and critic in one launch.
+#include "tc_ptx.cuh"
+
+namespace rslrl {
+
+bool tc_make_map(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_cols,
+                 int box_rows, bool operand);
+int tc_num_sms();
+
+constexpr int MF_EPI_WARPS = 16;
+constexpr int MF_FIRST_EPI_WARP = 3;
+constexpr int MF_THREADS = (MF_FIRST_EPI_WARP + MF_EPI_WARPS) * 32;
+#ifndef RSLRL_MF_W_STAGES
+#define RSLRL_MF_W_STAGES 3
+#endif
+#ifndef RSLRL_MF_GRANULES
+#define RSLRL_MF_GRANULES 7
+#endif
+constexpr int MF_W_STAGES = RSLRL_MF_W_STAGES;
+constexpr int MF_W_STAGE_BYTES = 32768;
+constexpr int MF_GRANULES = RSLRL_MF_GRANULES;
+constexpr int MF_GRANULE_BYTES = 16384;
+constexpr int MF_MAX_BIAS = 512 + 256 + 128 + 16;
+
+struct MfNet {
+  CUtensorMap map_x, map_w1, map_w2, map_w3, map_w4;
+  CUtensorMap map_h1, map_h2, map_h3;  // stores (valid when store_h)
+  const float* b[4];
+  float* y;
+  int M, K0, N1, N2, N3, N4, ldy, act, store_h;
+};
+
+struct alignas(64) MfBatch {
+  MfNet net[2];
+};
+
+// Optional in-kernel timeline (build with -DRSLRL_TC_TRACE; read with profiles/experiments/mlp3_trace.py): per CTA,
+// slot 0 entry, 1 prologue done, then 9 slots per tile j (first three tiles): L1(0) issued, E1(0) done, last L1
+// chunk's epilogue done, acc2 published, E2 done, acc3 published, E3 done, acc4 published, E4 done.
+#ifdef RSLRL_TC_TRACE
+__device__ unsigned long long g_mf_trace[148 * 32];
+__device__ __forceinline__ void mf_trace(int slot) {
+  if (slot < 32) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    g_mf_trace[blockIdx.x * 32 + slot] = t;
+  }
+}
+#define MF_TRACE(cond, slot) do { if (cond) mf_trace(slot); } while (0)
+#else
+#define MF_TRACE(cond, slot) do { } while (0)
+#endif
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+// round-to-nearest (ties away) to tf32 with two integer ops: add half an ulp of the 10-bit mantissa, clear the 13
+// low bits (same result as cvt.rna.tf32.f32 for finite inputs; activations are finite)
+__device__ __forceinline__ float tf32_round_bits(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+// ELU(z) = max(z, exp(min(z, 0)) - 1): exp(z) - 1 >= z everywhere and is 0 for z >= 0 (5 instructions, one MUFU)
+__device__ __forceinline__ float elu_max_form(float z) {
+  return fmaxf(z, ex2_approx(fminf(z, 0.f) * 1.4426950408889634f) - 1.f);
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(MF_THREADS, 1) mlp3_forward_kernel(const __grid_constant__ MfBatch batch,
+                                                                     const int n_nets) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  uint8_t* const wring = smem_raw + pad;
+  uint8_t* const gring = wring + MF_W_STAGES * MF_W_STAGE_BYTES;
+  float* const bias_s = (float*)(gring + MF_GRANULES * MF_GRANULE_BYTES);  // [2][MF_MAX_BIAS]
+  uint64_t* const w_full = (uint64_t*)(bias_s + 2 * MF_MAX_BIAS);
+  uint64_t* const w_empty = w_full + MF_W_STAGES;
+  uint64_t* const g_full = w_empty + MF_W_STAGES;
+  uint64_t* const g_empty = g_full + MF_GRANULES;
+  uint64_t* const a_full = g_empty + MF_GRANULES;  // [3]: TMEM buffer 0, buffer 1, acc2
+  uint64_t* const a_empty = a_full + 3;            // [3]
+  uint32_t* const tmem_ptr_smem = (uint32_t*)(a_empty + 3);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  MF_TRACE(threadIdx.x == 0, 0);
+
+  // biases of every layer of every net -> shared memory (read by the epilogues as broadcast 16-byte loads)
+  for (int i = threadIdx.x; i < n_nets * MF_MAX_BIAS; i += MF_THREADS) {
+    const int ni = i / MF_MAX_BIAS, o = i - ni * MF_MAX_BIAS;
+    const MfNet& P = batch.net[ni];
+    float v = 0.f;
+    if (o < 512) { if (o < P.N1 && P.b[0]) v = __ldg(P.b[0] + o); }
+    else if (o < 768) { if (o - 512 < P.N2 && P.b[1]) v = __ldg(P.b[1] + o - 512); }
+    else if (o < 896) { if (o - 768 < P.N3 && P.b[2]) v = __ldg(P.b[2] + o - 768); }
+    else { if (o - 896 < P.N4 && P.b[3]) v = __ldg(P.b[3] + o - 896); }
+    bias_s[i] = v;
+  }
+  if (warp == 0 && elect_one()) {
+    for (int i = 0; i < n_nets; ++i) {
+      const MfNet& P = batch.net[i];
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&P.map_x) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&P.map_w1) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&P.map_w2) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&P.map_w3) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&P.map_w4) : "memory");
+    }
+    for (int s = 0; s < MF_W_STAGES; ++s) {
+      mbar_init(&w_full[s], 1);
+      mbar_init(&w_empty[s], 1);
+    }
+    for (int g = 0; g < MF_GRANULES; ++g) {
+      mbar_init(&g_full[g], 4);   // the four row-quarter warps that write a granule
+      mbar_init(&g_empty[g], 2);  // MMA commit + store warp
+    }
+    for (int a = 0; a < 3; ++a) {
+      mbar_init(&a_full[a], 1);
+      mbar_init(&a_empty[a], MF_EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  MF_TRACE(threadIdx.x == 0, 1);
+
+  const int tiles_m = (batch.net[0].M + TC_BLOCK_M - 1) / TC_BLOCK_M;
+  const int total = tiles_m * n_nets;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer (weight ring)
+    if (elect_one()) {
+      int it = 0;
+      auto stage = [&](int& s) -> uint8_t* {
+        s = it % MF_W_STAGES;
+        mbar_wait(&w_empty[s], ((it / MF_W_STAGES) & 1) ^ 1);
+        ++it;
+        return wring + (size_t)s * MF_W_STAGE_BYTES;
+      };
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const MfNet& P = batch.net[t % n_nets];
+        const int m0 = (t / n_nets) * TC_BLOCK_M;
+        const int kb0 = (P.K0 + TC_BLOCK_K - 1) / TC_BLOCK_K, C1 = P.N1 / 128;
+        auto l1 = [&](int c) {  // x k-block + the chunk's W1 k-block per stage
+          for (int kb = 0; kb < kb0; ++kb) {
+            int s;
+            uint8_t* dst = stage(s);
+            mbar_expect_tx(&w_full[s], 2u * 16384u);
+            tma_load_2d(dst, &P.map_x, &w_full[s], kb * TC_BLOCK_K, m0);
+            tma_load_2d(dst + 16384, &P.map_w1, &w_full[s], kb * TC_BLOCK_K, c * 128);
+          }
+        };
+        auto l2p = [&](int c) {
+          for (int kb = 0; kb < 4; ++kb) {
+            int s;
+            uint8_t* dst = stage(s);
+            mbar_expect_tx(&w_full[s], (uint32_t)P.N2 * 128u);
+            tma_load_2d(dst, &P.map_w2, &w_full[s], (c * 4 + kb) * TC_BLOCK_K, 0);
+          }
+        };
+        l1(0);
+        for (int c = 0; c < C1; ++c) {
+          if (c + 1 < C1) l1(c + 1);
+          l2p(c);
+        }
+        // the narrow layers pack several k-blocks into one 32 KB stage (bytes in flight, not stage count, is what
+        // the weight stream needs)
+        const int nkb3 = P.N2 / 32, pack3 = min(MF_W_STAGE_BYTES / (P.N3 * 128), nkb3);
+        for (int kb = 0; kb < nkb3; kb += pack3) {
+          int s;
+          uint8_t* dst = stage(s);
+          mbar_expect_tx(&w_full[s], (uint32_t)(pack3 * P.N3) * 128u);
+          for (int i = 0; i < pack3; ++i)
+            tma_load_2d(dst + (size_t)i * P.N3 * 128, &P.map_w3, &w_full[s], (kb + i) * TC_BLOCK_K, 0);
+        }
+        {
+          const int nkb4 = P.N3 / 32;
+          int s;
+          uint8_t* dst = stage(s);
+          mbar_expect_tx(&w_full[s], (uint32_t)nkb4 * 16u * 128u);
+          for (int i = 0; i < nkb4; ++i) tma_load_2d(dst + i * 2048, &P.map_w4, &w_full[s], i * TC_BLOCK_K, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    int it = 0;          // weight ring position
+    int gn = 0;          // granule counter
+    uint32_t use[3] = {0, 0, 0};  // uses of TMEM buffer 0 / buffer 1 / acc2 so far
+    // one k-block (32 tf32 columns) of MMAs: A at `sa`, B at `sb` (both K-major, 128-byte swizzle)
+    auto kblock = [&](uint32_t d_tmem, uint32_t sa, uint32_t sb, uint32_t idesc, bool first) {
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
+          const uint64_t da = make_smem_desc(sa + k * 32, 16, 1024, kLayoutSw128);
+          const uint64_t db = make_smem_desc(sb + k * 32, 16, 1024, kLayoutSw128);
+          umma_tf32(d_tmem, da, db, idesc, (first && k == 0) ? 0u : 1u);
+        }
+      }
+      __syncwarp();
+    };
+    auto wait_w = [&](int& s) -> uint32_t {
+      s = it % MF_W_STAGES;
+      mbar_wait(&w_full[s], (it / MF_W_STAGES) & 1);
+      ++it;
+      return smem_u32(wring + (size_t)s * MF_W_STAGE_BYTES);
+    };
+    auto wait_g = [&](int& g) -> uint32_t {
+      g = gn % MF_GRANULES;
+      mbar_wait(&g_full[g], (gn / MF_GRANULES) & 1);
+      ++gn;
+      return smem_u32(gring + (size_t)g * MF_GRANULE_BYTES);
+    };
+    auto acquire_acc = [&](int a) {
+      mbar_wait(&a_empty[a], (use[a] & 1) ^ 1);
+      tcgen05_fence_after();
+    };
+    auto publish_acc = [&](int a) {
+      if (elect_one()) tcgen05_commit(&a_full[a]);
+      __syncwarp();
+      ++use[a];
+    };
+    int tj = -1;
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+      ++tj;
+      const MfNet& P = batch.net[t % n_nets];
+      const int kb0 = (P.K0 + TC_BLOCK_K - 1) / TC_BLOCK_K, C1 = P.N1 / 128;
+      const uint32_t idesc1 = make_idesc(128, false, false), idesc2 = make_idesc(P.N2, false, false);
+      const uint32_t idesc3 = make_idesc(P.N3, false, false), idesc4 = make_idesc(16, false, false);
+      auto l1 = [&](int c) {
+        const int a = c & 1;
+        acquire_acc(a);
+        for (int kb = 0; kb < kb0; ++kb) {
+          int s;
+          const uint32_t base = wait_w(s);
+          tcgen05_fence_after();
+          kblock(tmem_base + (uint32_t)a * 128u, base, base + 16384u, idesc1, kb == 0);
+          if (elect_one()) tcgen05_commit(&w_empty[s]);
+          __syncwarp();
+        }
+        publish_acc(a);
+      };
+      // consume `n` granules against weight k-blocks into the accumulator at column `col`
+      // `pack` k-blocks of `kb_bytes` each share one weight stage
+      auto from_granules = [&](int n, uint32_t col, uint32_t idesc, bool first_overall, int pack, uint32_t kb_bytes) {
+        for (int kb = 0; kb < n; kb += pack) {
+          int s;
+          const uint32_t wb = wait_w(s);
+          for (int i = 0; i < pack; ++i) {
+            int g;
+            const uint32_t ga = wait_g(g);
+            tcgen05_fence_after();
+            kblock(tmem_base + col, ga, wb + (uint32_t)i * kb_bytes, idesc, first_overall && kb + i == 0);
+            if (elect_one()) tcgen05_commit(&g_empty[g]);
+            __syncwarp();
+          }
+          if (elect_one()) tcgen05_commit(&w_empty[s]);
+          __syncwarp();
+        }
+      };
+      l1(0);
+      MF_TRACE(lane == 0, 2 + 9 * tj);
+      acquire_acc(2);
+      for (int c = 0; c < C1; ++c) {
+        if (c + 1 < C1) l1(c + 1);
+        from_granules(4, 256u, idesc2, c == 0, 1, 0u);
+      }
+      publish_acc(2);
+      MF_TRACE(lane == 0, 2 + 9 * tj + 3);
+      acquire_acc(0);
+      from_granules(P.N2 / 32, 0u, idesc3, true, min(MF_W_STAGE_BYTES / (P.N3 * 128), P.N2 / 32), (uint32_t)P.N3 * 128u);
+      publish_acc(0);
+      MF_TRACE(lane == 0, 2 + 9 * tj + 5);
+      acquire_acc(1);
+      from_granules(P.N3 / 32, 128u, idesc4, true, P.N3 / 32, 2048u);
+      publish_acc(1);
+      MF_TRACE(lane == 0, 2 + 9 * tj + 7);
+    }
+  } else if (warp == 2) {
+    // ===================================================================== granule store warp
+    int gn = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+      const MfNet& P = batch.net[t % n_nets];
+      const int m0 = (t / n_nets) * TC_BLOCK_M;
+      const int n1 = P.N1 / 32, n2 = P.N2 / 32, n3 = P.N3 / 32;
+      for (int i = 0; i < n1 + n2 + n3; ++i, ++gn) {
+        const int g = gn % MF_GRANULES;
+        mbar_wait(&g_full[g], (gn / MF_GRANULES) & 1);
+        if (lane == 0) {
+          if (P.store_h) {
+            const CUtensorMap* map = i < n1 ? &P.map_h1 : (i < n1 + n2 ? &P.map_h2 : &P.map_h3);
+            const int col = (i < n1 ? i : (i < n1 + n2 ? i - n1 : i - n1 - n2)) * 32;
+            tma_store_2d(map, gring + (size_t)g * MF_GRANULE_BYTES, col, m0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          }
+          mbar_arrive(&g_empty[g]);
+        }
+        __syncwarp();
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  } else {
+    // ===================================================================== epilogue warps
+    const int ew = warp - MF_FIRST_EPI_WARP;
+    const int q = warp & 3;    // TMEM sub-partition = row quarter of the tile
+    const int j = ew >> 2;     // column-block slot 0..3
+    const uint32_t sw = (uint32_t)(lane & 7);
+    int gbase = 0;
+    uint32_t use[3] = {0, 0, 0};
+    int tj = -1;
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+      ++tj;
+      const int ni = t % n_nets;
+      const MfNet& P = batch.net[ni];
+      const int m0 = (t / n_nets) * TC_BLOCK_M;
+      const int C1 = P.N1 / 128;
+      const float* const bias_net = bias_s + ni * MF_MAX_BIAS;
+      const int act = P.act;
+
+      // one unit: TMEM columns [col, col+32) of this warp's 32 rows -> bias + activation -> granule `gidx`
+      auto unit = [&](uint32_t col, const float* bias, int gidx, int acc, bool last_read) {
+        uint32_t v[32];
+        TMEM_LD_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + col, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (last_read) {  // hand the accumulator back to the MMA warp
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_empty[acc]);
+        }
+        const int g = gidx % MF_GRANULES;
+        mbar_wait(&g_empty[g], ((gidx / MF_GRANULES) & 1) ^ 1);
+        uint8_t* const my_row = gring + (size_t)g * MF_GRANULE_BYTES + q * 4096 + lane * 128;
+        if (act == RSLRL_ACT_ELU) {
+          // branch-free fast path, two halves of 16 columns: 16 independent chains per lane (ILP hides the MUFU and
+          // shared-memory latencies; only four epilogue warps share a scheduler)
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            float z[16];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float4 b4 = *(const float4*)(bias + 16 * hh + 4 * u);
+              z[4 * u + 0] = __uint_as_float(v[16 * hh + 4 * u + 0]) + b4.x;
+              z[4 * u + 1] = __uint_as_float(v[16 * hh + 4 * u + 1]) + b4.y;
+              z[4 * u + 2] = __uint_as_float(v[16 * hh + 4 * u + 2]) + b4.z;
+              z[4 * u + 3] = __uint_as_float(v[16 * hh + 4 * u + 3]) + b4.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) z[i] = tf32_round_bits(elu_max_form(z[i]));
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              *(float4*)(my_row + (((4 * hh + u) ^ sw) << 4)) = make_float4(z[4 * u], z[4 * u + 1], z[4 * u + 2], z[4 * u + 3]);
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float4 b4 = *(const float4*)(bias + 4 * u);
+            float4 o;
+            o.x = tf32_rna(act_forward(act, __uint_as_float(v[4 * u + 0]) + b4.x));
+            o.y = tf32_rna(act_forward(act, __uint_as_float(v[4 * u + 1]) + b4.y));
+            o.z = tf32_rna(act_forward(act, __uint_as_float(v[4 * u + 2]) + b4.z));
+            o.w = tf32_rna(act_forward(act, __uint_as_float(v[4 * u + 3]) + b4.w));
+            *(float4*)(my_row + ((u ^ sw) << 4)) = o;
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&g_full[g]);
+      };
+      auto wait_acc = [&](int a) {
+        mbar_wait(&a_full[a], use[a] & 1);
+        tcgen05_fence_after();
+        ++use[a];
+      };
+      auto release_only = [&](int a) {  // a warp without a unit in this accumulator still owes its arrival
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_empty[a]);
+      };
+
+      // L1: chunk c lives in TMEM buffer c & 1, columns [ (c&1)*128 + 32 j, +32 )
+      for (int c = 0; c < C1; ++c) {
+        const int a = c & 1;
+        wait_acc(a);
+        unit((uint32_t)a * 128u + 32u * j, bias_net + c * 128 + 32 * j, gbase + j, a, true);
+        gbase += 4;
+        MF_TRACE(ew == 0 && lane == 0 && c == 0, 2 + 9 * tj + 1);
+        MF_TRACE(ew == 0 && lane == 0 && c == C1 - 1, 2 + 9 * tj + 2);
+      }
+      // L2: acc2 at columns 256.., N2 / 32 column blocks, this warp takes j, j + 4
+      {
+        const int ncb = P.N2 / 32;
+        wait_acc(2);
+        if (j >= ncb) release_only(2);
+        for (int cb = j; cb < ncb; cb += 4)
+          unit(256u + 32u * cb, bias_net + 512 + 32 * cb, gbase + cb, 2, cb + 4 >= ncb);
+        gbase += ncb;
+        MF_TRACE(ew == 0 && lane == 0, 2 + 9 * tj + 4);
+      }
+      // L3: acc3 in buffer 0
+      {
+        const int ncb = P.N3 / 32;
+        wait_acc(0);
+        if (j >= ncb) release_only(0);
+        else unit(32u * j, bias_net + 768 + 32 * j, gbase + j, 0, true);
+        gbase += ncb;
+        MF_TRACE(ew == 0 && lane == 0, 2 + 9 * tj + 6);
+      }
+      // L4: acc4 in buffer 1 (16 columns): the four j == 0 warps write the N4 outputs
+      {
+        wait_acc(1);
+        if (j == 0) {
+          uint32_t v[16];
+          TMEM_LD_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + 128u, v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          release_only(1);
+          const int row = m0 + q * 32 + lane;
+          if (row < P.M) {
+            float* const yr = P.y + (size_t)row * P.ldy;
+            const float* const b4 = bias_net + 896;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (i < P.N4) yr[i] = __uint_as_float(v[i]) + b4[i];
+          }
+        } else {
+          release_only(1);
+        }
+        MF_TRACE(ew == 0 && lane == 0, 2 + 9 * tj + 8);
+      }
+    }
+    tcgen05_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+static bool ok16(const void* p, long long ld) { return ((uintptr_t)p & 15) == 0 && (ld % 4) == 0; }
+
+// 0 ok, 1 error, -1 not eligible (caller runs the layers one by one)
+int mlp3_forward_fused(int n, const rslrl_mlp3_fwd_t* nets, cudaStream_t st) {
+  const char* what = "rslrl_mlp3_forward";
+  if (n < 1 || n > 2) return -1;
+  MfBatch b{};
+  for (int i = 0; i < n; ++i) {
+    const rslrl_mlp3_fwd_t& q = nets[i];
+    if (q.M != nets[0].M) return -1;
+    if (q.N1 % 128 || q.N1 < 128 || q.N1 > 512 || q.N2 % 128 || q.N2 < 128 || q.N2 > 256 || q.N3 % 32 || q.N3 < 32 ||
+        q.N3 > 128 || q.N4 < 1 || q.N4 > 16 || q.K0 < 1)
+      return -1;
+    if (!ok16(q.x, q.ldx) || !ok16(q.w[0], q.ldw0) || !ok16(q.w[1], q.N1) || !ok16(q.w[2], q.N2) || !ok16(q.w[3], q.N3))
+      return -1;
+    const bool store = q.h[0] != nullptr;
+    if (store && (!q.h[1] || !q.h[2] || !ok16(q.h[0], q.ldh[0]) || !ok16(q.h[1], q.ldh[1]) || !ok16(q.h[2], q.ldh[2])))
+      return -1;
+    MfNet& P = b.net[i];
+    bool ok = tc_make_map(&P.map_x, q.x, q.M, q.K0, q.ldx, 32, 128, true) &&
+              tc_make_map(&P.map_w1, q.w[0], q.N1, q.K0, q.ldw0, 32, 128, true) &&
+              tc_make_map(&P.map_w2, q.w[1], q.N2, q.N1, q.N1, 32, q.N2, true) &&
+              tc_make_map(&P.map_w3, q.w[2], q.N3, q.N2, q.N2, 32, q.N3, true) &&
+              tc_make_map(&P.map_w4, q.w[3], q.N4, q.N3, q.N3, 32, 16, true);
+    if (ok && store)
+      ok = tc_make_map(&P.map_h1, q.h[0], q.M, q.N1, q.ldh[0], 32, 128, false) &&
+           tc_make_map(&P.map_h2, q.h[1], q.M, q.N2, q.ldh[1], 32, 128, false) &&
+           tc_make_map(&P.map_h3, q.h[2], q.M, q.N3, q.ldh[2], 32, 128, false);
+    if (!ok) {
+      set_error("%s: cuTensorMapEncodeTiled failed", what);
+      return 1;
+    }
+    for (int l = 0; l < 4; ++l) P.b[l] = q.b[l];
+    P.y = q.y; P.M = q.M; P.K0 = q.K0; P.N1 = q.N1; P.N2 = q.N2; P.N3 = q.N3; P.N4 = q.N4; P.ldy = q.ldy;
+    P.act = q.act; P.store_h = store ? 1 : 0;
+  }
+  static bool attr_set = false;
+  const size_t smem = MF_W_STAGES * MF_W_STAGE_BYTES + MF_GRANULES * MF_GRANULE_BYTES + 2 * MF_MAX_BIAS * 4 +
+                      (2 * MF_W_STAGES + 2 * MF_GRANULES + 6) * 8 + 16 + 1024;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(mlp3_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
+      return 1;
+    }
+    attr_set = true;
+  }
+  const int total = (nets[0].M + TC_BLOCK_M - 1) / TC_BLOCK_M * n;
+  const int grid = total < tc_num_sms() ? total : tc_num_sms();
+  mlp3_forward_kernel<<<grid, MF_THREADS, smem, st>>>(b, n);
+  return finish_launch(what);
+}
+
+}  // namespace rslrl
+
+extern "C" int rslrl_mlp3_forward(int n, const rslrl_mlp3_fwd_t* nets_host, rslrl_stream_t stream) {
+  using namespace rslrl;
+  const char* what = "rslrl_mlp3_forward";
+  RSLRL_CHECK_ARG(n > 0 && n <= RSLRL_MAX_PROBLEMS && nets_host, what);
+  for (int i = 0; i < n; ++i) {
+    const rslrl_mlp3_fwd_t& p = nets_host[i];
+    RSLRL_CHECK_ARG(p.x && p.y && p.w[0] && p.w[1] && p.w[2] && p.w[3] && p.M > 0 && p.ldx >= p.K0 && p.ldw0 >= p.K0 &&
+                        p.ldy >= p.N4,
+                    what);
+  }
+  const int rc = mlp3_forward_fused(n, nets_host, (cudaStream_t)stream);
+  if (rc < 0) {
+    set_error("%s: shape not eligible (needs N1 in {128..512} %% 128, N2 in {128,256}, N3 <= 128 %% 32, N4 <= 16, "
+              "16-byte aligned rows, equal M)", what);
+    return 4;
+  }
+  return rc;
+}
+
+#ifdef RSLRL_TC_TRACE
+extern "C" int rslrl_debug_read_trace_mlp3(unsigned long long* host) {
+  return (int)cudaMemcpyFromSymbol(host, rslrl::g_mf_trace, sizeof(unsigned long long) * 148 * 32);
+}
+#endif

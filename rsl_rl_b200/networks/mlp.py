@@ -37,6 +37,40 @@ def linear_forward(problems: Sequence[Tuple], precision: int):
     nat.check(nat.lib().rslrl_linear_forward(len(problems), arr, precision, nat.stream_ptr()))
 
 
+def mlp3_eligible(dims: Sequence[int], acts: Sequence[int]) -> bool:
+    """Shapes the one-launch fused forward (csrc/mlp_fused.cu) covers: 3 hidden layers with one activation,
+    N1 in 128..512 (step 128), N2 in {128, 256}, N3 <= 128 (step 32), N4 <= 16, linear output."""
+    if len(dims) != 5 or len(acts) != 4:
+        return False
+    _, n1, n2, n3, n4 = dims
+    return (n1 % 128 == 0 and 128 <= n1 <= 512 and n2 in (128, 256) and n3 % 32 == 0 and 32 <= n3 <= 128
+            and 1 <= n4 <= 16 and acts[0] == acts[1] == acts[2] and acts[3] == 0)
+
+
+def mlp3_struct(x_ptr: int, ldx: int, M: int, weights, biases, hs, y, act: int) -> "nat.Mlp3Fwd":
+    """weights: 4 tensors [N_l, K_l] (weights[0] may be the zero-padded first-layer shadow); hs: 3 activation
+    buffers [>=M, N_l] or None (nothing but y is stored)."""
+    p = nat.Mlp3Fwd()
+    p.x = x_ptr
+    for l in range(4):
+        p.w[l] = weights[l].data_ptr()
+        p.b[l] = nat.ptr(biases[l])
+    for l in range(3):
+        p.h[l] = None if hs is None else hs[l].data_ptr()
+        p.ldh[l] = 0 if hs is None else hs[l].stride(0)
+    p.y = y.data_ptr()
+    p.M, p.K0 = M, weights[0].shape[1]
+    p.N1, p.N2, p.N3, p.N4 = (w.shape[0] for w in weights)
+    p.ldx, p.ldw0, p.ldy, p.act = ldx, weights[0].stride(0), y.stride(0), act
+    return p
+
+
+def mlp3_forward(structs: Sequence["nat.Mlp3Fwd"]):
+    """One launch for all nets (actor and critic)."""
+    arr = (nat.Mlp3Fwd * len(structs))(*structs)
+    nat.check(nat.lib().rslrl_mlp3_forward(len(structs), arr, nat.stream_ptr()))
+
+
 def linear_backward_data(problems: Sequence[Tuple], precision: int):
     """problems: (dy[M,N], weight[N,K], h[M,K]|None, dx[M,K], act_code_of_previous_layer[, db_prev[K]|None])."""
     arr = (nat.LinearBwdData * len(problems))()

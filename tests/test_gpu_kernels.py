@@ -474,3 +474,77 @@ def test_linear_backward_head_fused(M, K, N, act):
     # a column sum of M zero-mean values cancels: measure the error against the sum of magnitudes
     db_err = (db.double() - 1 - dy.double().sum(0)).abs().max() / dy.double().abs().sum(0).max()
     assert float(db_err) < 1e-6
+
+
+# ---------------------------------------------------------------------------------- fused MLP forward
+def _mlp3_case(M, dims, act, seed, store, pad_k0=False):
+    """Runs rslrl_mlp3_forward on one or two nets; returns (outputs, saved activations, fp64 references)."""
+    from rsl_rl_b200.networks.mlp import mlp3_forward, mlp3_struct
+    nat = _nat()
+    torch.manual_seed(seed)
+    structs, keep, refs = [], [], []
+    for d in dims:
+        K0 = d[0]
+        ld = (K0 + 3) // 4 * 4 if pad_k0 else K0
+        xbuf = torch.zeros(M, ld, device=DEV)
+        xbuf[:, :K0] = torch.randn(M, K0, device=DEV)
+        ws = [torch.randn(d[l + 1], d[l], device=DEV) / d[l] ** 0.5 for l in range(4)]
+        bs = [torch.randn(d[l + 1], device=DEV) * 0.3 for l in range(4)]
+        w0 = ws[0]
+        if ld != K0:  # zero-padded first-layer shadow, as the engine keeps it
+            w0 = torch.zeros(d[1], ld, device=DEV)
+            w0[:, :K0] = ws[0]
+        hs = [torch.full((M, d[l + 1]), float("nan"), device=DEV) for l in range(3)] if store else None
+        y = torch.full((M, d[4]), float("nan"), device=DEV)
+        structs.append(mlp3_struct(xbuf.data_ptr(), ld, M, [w0] + ws[1:], bs, hs, y, nat.ACT_CODES[act]))
+        keep.append((xbuf, w0, ws, bs, hs, y))
+        h = xbuf[:, :K0]
+        ref_h = []
+        for l in range(4):
+            h = _lin_ref(h.float(), ws[l], bs[l], act if l < 3 else "identity").float()
+            ref_h.append(h)
+        refs.append(ref_h)
+    mlp3_forward(structs)
+    torch.cuda.synchronize()
+    return keep, refs
+
+
+@pytest.mark.parametrize("M", [24576, 4096, 1000, 77])
+@pytest.mark.parametrize("store", [True, False])
+def test_mlp3_fused_forward_c2_shape(M, store):
+    """Actor + critic of the C2 config in one launch vs an fp64-accumulated reference (tf32 class: 1e-3)."""
+    keep, refs = _mlp3_case(M, [[48, 512, 256, 128, 12], [48, 512, 256, 128, 1]], "elu", M, store)
+    for (xbuf, w0, ws, bs, hs, y), ref_h in zip(keep, refs):
+        assert rel_err(y.cpu().numpy(), ref_h[3].cpu().numpy()) < 1e-3
+        if store:
+            for l in range(3):
+                assert rel_err(hs[l].cpu().numpy(), ref_h[l].cpu().numpy()) < 1e-3, l
+
+
+@pytest.mark.parametrize("dims,act,pad", [([235, 512, 256, 128, 12], "elu", True), ([48, 128, 128, 32, 16], "relu", False),
+                                          ([64, 384, 256, 96, 3], "tanh", False), ([20, 256, 128, 64, 1], "elu", False)])
+def test_mlp3_fused_forward_other_shapes(dims, act, pad):
+    keep, refs = _mlp3_case(3000, [dims], act, sum(dims), True, pad_k0=pad)
+    (xbuf, w0, ws, bs, hs, y), ref_h = keep[0], refs[0]
+    assert rel_err(y.cpu().numpy(), ref_h[3].cpu().numpy()) < 1e-3
+    # a saturating activation bounds max|h| by 1, so the max-norm relative error of the 1.1M tf32 dot products is
+    # larger than for ELU / ReLU layers (whose max|h| grows with the input scale)
+    tol = 3e-3 if act == "tanh" else 1e-3
+    for l in range(3):
+        assert rel_err(hs[l].cpu().numpy(), ref_h[l].cpu().numpy()) < tol, l
+
+
+def test_mlp3_fused_forward_matches_layerwise_tf32_path():
+    """The fused kernel and the layer-by-layer tcgen05 path agree to tf32 noise (they differ in where the hidden
+    activations are rounded to tf32: epilogue, ties away from zero, vs TMA on the next layer's load)."""
+    from rsl_rl_b200.networks.mlp import linear_forward
+    nat = _nat()
+    M, d = 4096, [48, 512, 256, 128, 12]
+    keep, _ = _mlp3_case(M, [d], "elu", 11, True)
+    xbuf, w0, ws, bs, hs, y = keep[0]
+    h = xbuf
+    for l in range(4):
+        out = torch.empty(M, d[l + 1], device=DEV)
+        linear_forward([(h, ws[l], bs[l], out, nat.ACT_CODES["elu"] if l < 3 else 0)], nat.PREC_TF32)
+        h = out
+    assert rel_err(y.cpu().numpy(), h.cpu().numpy()) < 5e-4
