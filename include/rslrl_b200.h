@@ -233,6 +233,24 @@ int rslrl_grad_norm_lr(const float* g, int64_t P, const float* kl_sum, rslrl_opt
 int rslrl_adam_step(float* p, float* g, float* m, float* v, int64_t P, const rslrl_opt_state_t* state,
                     double beta1, double beta2, double eps, int zero_grad, rslrl_stream_t stream);
 
+/* ---- data-parallel optimiser step in ONE launch (rsl_rl/algorithms/ppo.py:441-469 reduce_parameters, :272-290 KL
+ * all-reduce + lr broadcast, :380 clip_grad_norm_, :381 Adam.step).
+ * Every rank keeps its gradient buffer [P floats | 4-float tail whose first float is the minibatch KL] in memory that
+ * its peers can address (NVLink peer / symmetric memory); peer_grads_host[k] is rank k's buffer as seen from this
+ * rank (entry `rank` = the local buffer), peer_flags_host[k] rank k's zero-initialised flag buffer of
+ * rslrl_allreduce_adam_flag_bytes() bytes (unused when world == 1).  The kernel sums the gradients of all ranks
+ * (fixed rank order: bit-identical on every rank), derives ||mean g||, the clip scale and the KL-adaptive learning
+ * rate exactly like rslrl_grad_norm_lr, applies Adam like rslrl_adam_step and clears the local gradients once the
+ * peers have read them.  Must be launched by every rank the same number of times (flags are epoch stamped); the
+ * grid (<= 148 blocks) has to be co-resident.  workspace: rslrl_allreduce_adam_workspace_bytes(), zero-initialised. */
+int64_t rslrl_allreduce_adam_workspace_bytes(void);
+int64_t rslrl_allreduce_adam_flag_bytes(void);
+int rslrl_allreduce_clip_adam(int world, int rank, const float* const* peer_grads_host,
+                              unsigned int* const* peer_flags_host, float* p, float* m, float* v, int64_t P,
+                              rslrl_opt_state_t* state, void* workspace, double max_grad_norm, int adaptive,
+                              double desired_kl, int round_lr_fp32, int use_kl, double beta1, double beta2, double eps,
+                              int zero_grad, rslrl_stream_t stream);
+
 /* ---- recurrent minibatches (rsl_rl/utils/utils.py:78-141; storage/rollout_storage.py:206-260) ---- */
 
 /* Segmented scan over dones[T,N] (u8).  Trajectories are enumerated env-major (all pieces of env 0,

@@ -13,6 +13,7 @@ all-reduce (reference: a separate 4-byte all-reduce plus a broadcast per minibat
 """
 from __future__ import annotations
 
+import os
 from typing import Iterable, List
 
 import torch
@@ -79,6 +80,37 @@ class FlatParamGroup:
     def moment_views(self, i: int):
         return self._view(self.exp_avg, i), self._view(self.exp_avg_sq, i)
 
+    def make_symmetric(self, group=None):
+        """Moves the gradient buffer into symmetric (peer-mapped) memory so that every rank can read every other
+        rank's gradients over NVLink (collective call).  Returns (peer gradient pointers, peer flag pointers)."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        group = group or dist.group.WORLD
+        try:
+            symm_mem.enable_symm_mem_for_group(group.group_name)
+        except Exception:
+            pass
+        n = self.numel + ALIGN
+        g = symm_mem.empty(n, dtype=torch.float32, device=self.device)
+        g.zero_()
+        flags = symm_mem.empty(int(nat.lib().rslrl_allreduce_adam_flag_bytes()) // 4, dtype=torch.int32,
+                               device=self.device)
+        flags.zero_()
+        torch.cuda.synchronize()
+        hg = symm_mem.rendezvous(g, group)
+        hf = symm_mem.rendezvous(flags, group)
+        with torch.no_grad():
+            g.copy_(self.grads_ext)
+        self.grads_ext = g
+        self.grads = g[:self.numel]
+        self.kl_slot = g[self.numel:self.numel + 1]
+        self._symm = (hg, hf, flags)  # keep the handles (and the mappings) alive
+        self.bind()
+        torch.cuda.synchronize()
+        dist.barrier(group)
+        return [int(p) for p in hg.buffer_ptrs], [int(p) for p in hf.buffer_ptrs]
+
     def zero_grad(self):
         nat.check(nat.lib().rslrl_fill_zero(self.grads_ext.data_ptr(), self.grads_ext.numel() * 4, nat.stream_ptr()))
 
@@ -132,6 +164,25 @@ class FusedAdam(torch.optim.Adam):
                                    device=group.device)
         self._host_step = 0
         self._install_state()
+        # one-launch step (csrc/allreduce_adam.cu): world 1 = the local buffer only; enable_peer_allreduce() adds the
+        # peers' buffers (then the gradient all-reduce happens inside the same kernel)
+        self._ar_ws = torch.zeros(int(nat.lib().rslrl_allreduce_adam_workspace_bytes()), dtype=torch.uint8,
+                                  device=group.device)
+        self.peer_world, self.peer_rank = 1, 0
+        self._peer_grads = self._peer_flags = None
+        self.one_launch = os.environ.get("RSLRL_ONE_LAUNCH_STEP", "1") != "0"
+
+    def enable_peer_allreduce(self, rank: int, world: int, group=None):
+        """Gradients move to symmetric memory; from now on fused_step() all-reduces them itself (collective call)."""
+        grads, flags = self.group.make_symmetric(group)
+        if len(grads) != world:
+            raise RuntimeError("symmetric-memory rendezvous returned %d peers for world size %d" % (len(grads), world))
+        self.peer_world, self.peer_rank = world, rank
+        self._peer_grads, self._peer_flags = nat.void_array(grads), nat.void_array(flags)
+
+    @property
+    def peer_allreduce(self) -> bool:
+        return self.peer_world > 1
 
     def _install_state(self):
         for i, p in enumerate(self.group.params):
@@ -145,6 +196,17 @@ class FusedAdam(torch.optim.Adam):
         pg = self.param_groups[0]
         beta1, beta2 = pg["betas"]
         L = nat.lib()
+        if self.peer_allreduce or (self.one_launch and world_size == 1):
+            if self.peer_allreduce and world_size != self.peer_world:
+                raise RuntimeError("fused_step: world_size does not match the peer group")
+            peers = self._peer_grads if self.peer_allreduce else nat.void_array([g.grads_ext.data_ptr()])
+            nat.check(L.rslrl_allreduce_clip_adam(
+                self.peer_world, self.peer_rank, peers, self._peer_flags, g.values.data_ptr(), g.exp_avg.data_ptr(),
+                g.exp_avg_sq.data_ptr(), g.numel, self.dev_state.ptr(), self._ar_ws.data_ptr(), float(max_grad_norm),
+                int(adaptive), float(desired_kl or 0.0), int(round_lr_fp32), int(use_kl), beta1, beta2, pg["eps"],
+                int(zero_grad), nat.stream_ptr()))
+            self._host_step += 1
+            return
         nat.check(L.rslrl_grad_norm_lr(g.grads.data_ptr(), g.numel, g.kl_slot.data_ptr() if use_kl else None,
                                        self.dev_state.ptr(), self._opt_ws.data_ptr(), world_size, float(max_grad_norm),
                                        int(adaptive), float(desired_kl or 0.0), int(round_lr_fp32), beta1, beta2,

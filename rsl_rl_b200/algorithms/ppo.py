@@ -113,6 +113,8 @@ class PPO:
             self.rnd.target.precision = gemm_precision
         self._group = FlatParamGroup(self.policy.parameters(), self.device)
         self.optimizer = FusedAdam(self._group, lr=learning_rate)
+        if self.is_multi_gpu and os.environ.get("RSLRL_ALLREDUCE", "p2p") == "p2p":
+            self._enable_peer_allreduce()
         self.storage: RolloutStorage = None  # type: ignore
         self.transition = RolloutStorage.Transition()
 
@@ -149,6 +151,22 @@ class PPO:
         self._act_in = None
         self._mb_hook = None  # test hook: called after every minibatch backward in eager mode
         self.last_update_info = {}
+
+    def _enable_peer_allreduce(self):
+        """Gradient buffer into symmetric memory: the per-minibatch all-reduce then runs inside the optimiser kernel
+        over NVLink peer loads (csrc/allreduce_adam.cu).  Every rank must take the same path, so the outcome of the
+        set-up is agreed on with one NCCL all-reduce; on failure all ranks keep the NCCL all-reduce."""
+        ok = 1
+        try:
+            self.optimizer.enable_peer_allreduce(self.gpu_global_rank, self.gpu_world_size)
+        except Exception as exc:
+            print(f"[rsl_rl_b200] peer-memory all-reduce unavailable ({type(exc).__name__}: {exc}); using NCCL")
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+        torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
+        if int(flag.item()) == 0 and self.optimizer.peer_allreduce:
+            self.optimizer.peer_world, self.optimizer.peer_rank = 1, 0
+            self.optimizer.one_launch = False
 
     # ------------------------------------------------------------------------------------------
     def init_storage(self, training_type, num_envs, num_transitions_per_env, obs, actions_shape):
@@ -367,7 +385,7 @@ class PPO:
                 eng.backward(xa[r], xc[r], eng.dmu[:mb], eng.dvalue[:mb])
                 if self._mb_hook is not None:
                     self._mb_hook(self)
-                if self.is_multi_gpu:
+                if self.is_multi_gpu and not opt.peer_allreduce:
                     torch.distributed.all_reduce(self._group.grads_ext, op=torch.distributed.ReduceOp.SUM)
                 opt.fused_step(world_size=self.gpu_world_size, max_grad_norm=self.max_grad_norm, adaptive=adaptive,
                                desired_kl=self.desired_kl or 0.0, round_lr_fp32=self.is_multi_gpu)
@@ -541,7 +559,8 @@ class PPO:
             if self.rnd:
                 rnd_loss.backward()
             if self.is_multi_gpu:
-                torch.distributed.all_reduce(self._group.grads_ext, op=torch.distributed.ReduceOp.SUM)
+                if not opt.peer_allreduce:
+                    torch.distributed.all_reduce(self._group.grads_ext, op=torch.distributed.ReduceOp.SUM)
                 if self.rnd:
                     torch.distributed.all_reduce(self._rnd_group.grads_ext, op=torch.distributed.ReduceOp.SUM)
             opt.fused_step(world_size=self.gpu_world_size, max_grad_norm=self.max_grad_norm, adaptive=adaptive,
