@@ -18,11 +18,14 @@ with contextlib.redirect_stdout(io.StringIO()):
     runner.learn(3)
 torch.cuda.synchronize()
 runner.profile_phases = True
+K = int(sys.argv[3]) if len(sys.argv) > 3 else 5
+torch.cuda.profiler.start()   # ncu --profile-from-start off captures the K timed iterations only
 t0 = time.perf_counter()
 with contextlib.redirect_stdout(io.StringIO()):
-    runner.learn(5)
+    runner.learn(K)
 torch.cuda.synchronize()
-dt = (time.perf_counter() - t0) / 5
+torch.cuda.profiler.stop()
+dt = (time.perf_counter() - t0) / K
 p = torch.cat([q.detach().reshape(-1) for q in runner.alg.policy.parameters()])
 print(f"C3 {prec} envs={N}: {dt*1e3:.1f} ms/iter, {N*24/dt/1e6:.2f} M env-steps/s, phases {runner.phase_times}, "
       f"lr {runner.alg.learning_rate:.3e}, params finite {bool(torch.isfinite(p).all())}, "

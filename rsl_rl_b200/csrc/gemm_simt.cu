@@ -317,8 +317,11 @@ constexpr int HEADB_WARPS = 8;
 constexpr int HEADB_MAX_N = 12;
 
 // K <= 128 per pass (lane <-> 4 consecutive input columns); wider inputs loop over 128-column panels.
-__global__ void __launch_bounds__(HEADB_WARPS * 32) head_backward_kernel(const HeadBwdBatch batch) {
+constexpr int HEADB_ROWS = 4;  // rows per warp iteration: all their loads are issued before any is consumed
+
+__global__ void __launch_bounds__(HEADB_WARPS * 32, 2) head_backward_kernel(const HeadBwdBatch batch) {
   __shared__ float s_dw[HEADB_MAX_N][128];
+  __shared__ __align__(16) float s_w[HEADB_MAX_N][128];
   __shared__ float s_db[HEADB_MAX_N];
   const HeadBwdProblem P = batch.p[blockIdx.y];
   const int N = P.N, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -326,52 +329,62 @@ __global__ void __launch_bounds__(HEADB_WARPS * 32) head_backward_kernel(const H
   for (int k0 = 0; k0 < P.K; k0 += 128) {
     const int col = k0 + lane * 4;
     const bool col_ok = col < P.K;  // K % 4 == 0 is required by the dispatcher
-    float w[HEADB_MAX_N][4], dw[HEADB_MAX_N][4];
-#pragma unroll
-    for (int a = 0; a < HEADB_MAX_N; ++a) {
-      float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (a < N && col_ok) wv = __ldg((const float4*)(P.w + (size_t)a * P.K + col));
-      w[a][0] = wv.x; w[a][1] = wv.y; w[a][2] = wv.z; w[a][3] = wv.w;
-      dw[a][0] = dw[a][1] = dw[a][2] = dw[a][3] = 0.f;
+    // the weight panel lives in shared memory (one conflict-free 16-byte load per output per iteration), which
+    // leaves the registers to the rows in flight
+    for (int i = threadIdx.x; i < HEADB_MAX_N * 128; i += HEADB_WARPS * 32) {
+      const int a = i >> 7, c = k0 + (i & 127);
+      (&s_w[0][0])[i] = (a < N && c < P.K) ? __ldg(P.w + (size_t)a * P.K + c) : 0.f;
+      (&s_dw[0][0])[i] = 0.f;
     }
-    float db_acc = 0.f;
-    for (int i = threadIdx.x; i < HEADB_MAX_N * 128; i += HEADB_WARPS * 32) (&s_dw[0][0])[i] = 0.f;
     if (threadIdx.x < HEADB_MAX_N) s_db[threadIdx.x] = 0.f;
+    float dw[HEADB_MAX_N][4];
+#pragma unroll
+    for (int a = 0; a < HEADB_MAX_N; ++a) dw[a][0] = dw[a][1] = dw[a][2] = dw[a][3] = 0.f;
+    float db_acc = 0.f;
     __syncthreads();
-    for (int row = gwarp; row < P.M; row += 2 * nwarps) {
-      // two rows per iteration: both rows' loads are in flight before either is consumed
-      const int row2 = row + nwarps;
-      const bool has2 = row2 < P.M;
-      const float dyl_a = lane < N ? __ldg(P.dy + (size_t)row * P.ldy + lane) : 0.f;
-      const float dyl_b = (has2 && lane < N) ? __ldg(P.dy + (size_t)row2 * P.ldy + lane) : 0.f;
-      float4 hv_a = make_float4(0.f, 0.f, 0.f, 0.f), hv_b = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (col_ok) {
-        hv_a = __ldg((const float4*)(P.h + (size_t)row * P.ldh + col));
-        if (has2) hv_b = __ldg((const float4*)(P.h + (size_t)row2 * P.ldh + col));
+    for (int row = gwarp; row < P.M; row += HEADB_ROWS * nwarps) {
+      float dyl[HEADB_ROWS];
+      float4 hv[HEADB_ROWS], dx[HEADB_ROWS];
+#pragma unroll
+      for (int j = 0; j < HEADB_ROWS; ++j) {
+        const int r = row + j * nwarps;
+        const bool ok = r < P.M;
+        dyl[j] = (ok && lane < N) ? __ldg(P.dy + (size_t)r * P.ldy + lane) : 0.f;
+        hv[j] = (ok && col_ok) ? __ldg((const float4*)(P.h + (size_t)r * P.ldh + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        dx[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      db_acc += dyl_a + dyl_b;
-      float4 dxa = make_float4(0.f, 0.f, 0.f, 0.f), dxb = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < HEADB_ROWS; ++j) db_acc += dyl[j];
 #pragma unroll
       for (int a = 0; a < HEADB_MAX_N; ++a) {
         if (a < N) {
-          const float da = __shfl_sync(0xffffffffu, dyl_a, a), dbv = __shfl_sync(0xffffffffu, dyl_b, a);
-          dxa.x = fmaf(da, w[a][0], dxa.x); dxa.y = fmaf(da, w[a][1], dxa.y);
-          dxa.z = fmaf(da, w[a][2], dxa.z); dxa.w = fmaf(da, w[a][3], dxa.w);
-          dxb.x = fmaf(dbv, w[a][0], dxb.x); dxb.y = fmaf(dbv, w[a][1], dxb.y);
-          dxb.z = fmaf(dbv, w[a][2], dxb.z); dxb.w = fmaf(dbv, w[a][3], dxb.w);
-          dw[a][0] = fmaf(da, hv_a.x, fmaf(dbv, hv_b.x, dw[a][0])); dw[a][1] = fmaf(da, hv_a.y, fmaf(dbv, hv_b.y, dw[a][1]));
-          dw[a][2] = fmaf(da, hv_a.z, fmaf(dbv, hv_b.z, dw[a][2])); dw[a][3] = fmaf(da, hv_a.w, fmaf(dbv, hv_b.w, dw[a][3]));
+          const float4 w4 = *(const float4*)&s_w[a][lane * 4];
+#pragma unroll
+          for (int j = 0; j < HEADB_ROWS; ++j) {
+            const float d = __shfl_sync(0xffffffffu, dyl[j], a);
+            dx[j].x = fmaf(d, w4.x, dx[j].x); dx[j].y = fmaf(d, w4.y, dx[j].y);
+            dx[j].z = fmaf(d, w4.z, dx[j].z); dx[j].w = fmaf(d, w4.w, dx[j].w);
+            dw[a][0] = fmaf(d, hv[j].x, dw[a][0]); dw[a][1] = fmaf(d, hv[j].y, dw[a][1]);
+            dw[a][2] = fmaf(d, hv[j].z, dw[a][2]); dw[a][3] = fmaf(d, hv[j].w, dw[a][3]);
+          }
         }
       }
       if (P.dx != nullptr && col_ok) {
-        if (P.act != RSLRL_ACT_IDENTITY) {
-          dxa.x *= act_grad_from_output(P.act, hv_a.x); dxa.y *= act_grad_from_output(P.act, hv_a.y);
-          dxa.z *= act_grad_from_output(P.act, hv_a.z); dxa.w *= act_grad_from_output(P.act, hv_a.w);
-          dxb.x *= act_grad_from_output(P.act, hv_b.x); dxb.y *= act_grad_from_output(P.act, hv_b.y);
-          dxb.z *= act_grad_from_output(P.act, hv_b.z); dxb.w *= act_grad_from_output(P.act, hv_b.w);
+#pragma unroll
+        for (int j = 0; j < HEADB_ROWS; ++j) {
+          const int r = row + j * nwarps;
+          if (r < P.M) {
+            float4 o = dx[j];
+            if (P.act == RSLRL_ACT_ELU) {  // ELU'(z) from the output h: 1 for h > 0, h + 1 otherwise
+              o.x *= fminf(hv[j].x, 0.f) + 1.f; o.y *= fminf(hv[j].y, 0.f) + 1.f;
+              o.z *= fminf(hv[j].z, 0.f) + 1.f; o.w *= fminf(hv[j].w, 0.f) + 1.f;
+            } else if (P.act != RSLRL_ACT_IDENTITY) {
+              o.x *= act_grad_from_output(P.act, hv[j].x); o.y *= act_grad_from_output(P.act, hv[j].y);
+              o.z *= act_grad_from_output(P.act, hv[j].z); o.w *= act_grad_from_output(P.act, hv[j].w);
+            }
+            *(float4*)(P.dx + (size_t)r * P.ldx + col) = o;
+          }
         }
-        *(float4*)(P.dx + (size_t)row * P.ldx + col) = dxa;
-        if (has2) *(float4*)(P.dx + (size_t)row2 * P.ldx + col) = dxb;
       }
     }
     // block-level reduction of the weight / bias gradient partials, then one atomic per element per block
@@ -402,7 +415,9 @@ int head_linear_backward(int n, const rslrl_linear_bwd_head_t* pr, cudaStream_t 
     if (q.dx && ((q.ldx & 3) || ((uintptr_t)q.dx & 15))) return -1;
     b.p[i] = HeadBwdProblem{q.dy, q.w, q.h, q.dx, q.dw, q.db, q.M, q.N, q.K, q.ldy, q.ldh, q.ldx, q.act};
   }
-  head_backward_kernel<<<dim3(kNumSMs * 2, n), HEADB_WARPS * 32, 0, st>>>(b);
+  // one block per SM per problem: the weight-gradient partials end in global atomics (N x K per block), so fewer,
+  // longer-running blocks keep the per-address contention at 148
+  head_backward_kernel<<<dim3(kNumSMs, n), HEADB_WARPS * 32, 0, st>>>(b);
   return finish_launch("rslrl_linear_backward_head");
 }
 

@@ -91,29 +91,82 @@ struct GatherParams {
   long long n_rows;
 };
 
-__global__ void __launch_bounds__(kCopyThreads) permute_gather_kernel(const GatherParams p) {
-  const GatherField f = p.f[blockIdx.y];
-  const long long tid = (long long)blockIdx.x * kCopyThreads + threadIdx.x;
-  const long long stride = (long long)gridDim.x * kCopyThreads;
+// Permuted row gather, all fields in one launch.  blockIdx.y < n_wide: one WARP per row of a wide field (>= 32 floats
+// per row): the lanes stride the row, so every request is a coalesced 128/512-byte span of one source row, and each
+// warp keeps kGatherRows rows in flight (their indices and first loads are issued before any store).  The last
+// blockIdx.y: one THREAD per row for all narrow fields together (the index is read once per row).  No integer
+// division anywhere: rows are enumerated by warp / thread id.
+constexpr int kGatherRows = 4;
+
+__device__ __forceinline__ void gather_wide(const GatherField f, const long long* __restrict__ idx, long long n_rows,
+                                            long long warp_id, long long n_warps, int lane) {
   const bool vec = (f.row_floats & 3) == 0 && (f.dst_stride & 3) == 0 && (f.dst_col & 3) == 0 &&
                    (((uintptr_t)f.src | (uintptr_t)f.dst) & 15) == 0;
   if (vec) {
+    // 16-byte chunks; a warp takes 8 rows at a time and walks their chunks as one flat range, so short rows (48 floats
+    // = 12 chunks) still keep all 32 lanes busy; 4 loads in flight per lane
+    constexpr int R = 8, U = 4;
     const int chunks = f.row_floats >> 2;
-    const long long units = p.n_rows * chunks;
-    for (long long u = tid; u < units; u += stride) {
-      const long long j = u / chunks;
-      const int c = (int)(u - j * chunks);
-      const long long s = __ldg(p.idx + j);
-      const float4 v = __ldg((const float4*)(f.src + s * f.row_floats) + c);
-      *((float4*)(f.dst + j * f.dst_stride + f.dst_col) + c) = v;
+    for (long long j0 = warp_id * R; j0 < n_rows; j0 += n_warps * R) {
+      const int nr = (int)((n_rows - j0 < R) ? n_rows - j0 : R);
+      const long long s_lane = (lane < nr) ? __ldg(idx + j0 + lane) : 0;
+      const int units = nr * chunks;
+      for (int u0 = 0; u0 < units; u0 += 32 * U) {
+        float4 v[U];
+        int rr[U], cc[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+          const int u = u0 + k * 32 + lane;
+          rr[k] = u / chunks;
+          cc[k] = u - rr[k] * chunks;
+          const long long srow = __shfl_sync(0xffffffffu, s_lane, rr[k] & 7);
+          if (u < units) v[k] = __ldg((const float4*)(f.src + (size_t)srow * f.row_floats) + cc[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+          const int u = u0 + k * 32 + lane;
+          if (u < units) *((float4*)(f.dst + (size_t)(j0 + rr[k]) * f.dst_stride + f.dst_col) + cc[k]) = v[k];
+        }
+      }
     }
-  } else {
-    const long long units = p.n_rows * f.row_floats;
-    for (long long u = tid; u < units; u += stride) {
-      const long long j = u / f.row_floats;
-      const int c = (int)(u - j * f.row_floats);
-      const long long s = __ldg(p.idx + j);
-      f.dst[j * f.dst_stride + f.dst_col + c] = __ldg(f.src + s * f.row_floats + c);
+    return;
+  }
+  for (long long j0 = warp_id * kGatherRows; j0 < n_rows; j0 += n_warps * kGatherRows) {
+    long long s[kGatherRows];
+#pragma unroll
+    for (int r = 0; r < kGatherRows; ++r) s[r] = (j0 + r < n_rows) ? __ldg(idx + j0 + r) : 0;
+    for (int c0 = 0; c0 < f.row_floats; c0 += 32) {
+      const int c = c0 + lane;
+      float v[kGatherRows];
+#pragma unroll
+      for (int r = 0; r < kGatherRows; ++r)
+        if (c < f.row_floats && j0 + r < n_rows) v[r] = __ldg(f.src + (size_t)s[r] * f.row_floats + c);
+#pragma unroll
+      for (int r = 0; r < kGatherRows; ++r)
+        if (c < f.row_floats && j0 + r < n_rows) f.dst[(size_t)(j0 + r) * f.dst_stride + f.dst_col + c] = v[r];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kCopyThreads) permute_gather_kernel(const GatherParams p, const int n_wide,
+                                                                      const int n_fields) {
+  const long long tid = (long long)blockIdx.x * kCopyThreads + threadIdx.x;
+  const long long stride = (long long)gridDim.x * kCopyThreads;
+  if ((int)blockIdx.y < n_wide) {
+    gather_wide(p.f[blockIdx.y], p.idx, p.n_rows, tid >> 5, stride >> 5, threadIdx.x & 31);
+    return;
+  }
+  for (long long j = tid; j < p.n_rows; j += stride) {
+    const long long s = __ldg(p.idx + j);
+    for (int i = n_wide; i < n_fields; ++i) {
+      const GatherField f = p.f[i];
+      const float* src = f.src + (size_t)s * f.row_floats;
+      float* dst = f.dst + (size_t)j * f.dst_stride + f.dst_col;
+      if ((f.row_floats & 3) == 0 && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
+        for (int c = 0; c < f.row_floats; c += 4) *(float4*)(dst + c) = __ldg((const float4*)(src + c));
+      } else {
+        for (int c = 0; c < f.row_floats; ++c) dst[c] = __ldg(src + c);
+      }
     }
   }
 }
@@ -180,18 +233,26 @@ int rslrl_permute_gather(int n_fields, const float* const* src_host, float* cons
   RSLRL_CHECK_ARG(n_fields > 0 && n_fields <= RSLRL_MAX_SEGMENTS && idx && n_rows >= 0, what);
   if (n_rows == 0) return 0;
   GatherParams p{};
-  long long max_units = 1;
   for (int i = 0; i < n_fields; ++i) {
     RSLRL_CHECK_ARG(src_host[i] && dst_host[i] && row_floats_host[i] > 0, what);
     RSLRL_CHECK_ARG(dst_stride_host[i] >= dst_col_host[i] + row_floats_host[i], what);
-    p.f[i] = GatherField{src_host[i], dst_host[i], row_floats_host[i], dst_stride_host[i], dst_col_host[i]};
-    const long long chunks = (row_floats_host[i] + 3) / 4;
-    if (n_rows * chunks > max_units) max_units = n_rows * chunks;
   }
+  // wide fields first (one warp per row), narrow ones after (one thread per row, all of them together)
+  int n_wide = 0, k = 0;
+  for (int pass = 0; pass < 2; ++pass)
+    for (int i = 0; i < n_fields; ++i) {
+      const bool wide = row_floats_host[i] >= 32;
+      if (wide != (pass == 0)) continue;
+      p.f[k++] = GatherField{src_host[i], dst_host[i], row_floats_host[i], dst_stride_host[i], dst_col_host[i]};
+      if (wide) ++n_wide;
+    }
   p.idx = (const long long*)idx;
   p.n_rows = n_rows;
-  dim3 grid(grid_for(max_units), n_fields);
-  permute_gather_kernel<<<grid, kCopyThreads, 0, (cudaStream_t)stream>>>(p);
+  const bool has_narrow = n_wide < n_fields;
+  // wide: n_rows / kGatherRows warps; narrow: n_rows threads
+  const long long units = n_wide ? (n_rows + kGatherRows - 1) / kGatherRows * 32 : n_rows;
+  dim3 grid(grid_for(units > n_rows ? units : n_rows), n_wide + (has_narrow ? 1 : 0));
+  permute_gather_kernel<<<grid, kCopyThreads, 0, (cudaStream_t)stream>>>(p, n_wide, n_fields);
   return finish_launch(what);
 }
 
