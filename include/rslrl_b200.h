@@ -46,7 +46,14 @@ enum {
   RSLRL_ACT_LRELU = 5, RSLRL_ACT_SELU = 6, RSLRL_ACT_SOFTPLUS = 7
 };
 /* GEMM arithmetic: fp32 CUDA-core FMA (1e-5 parity class) or TF32 tcgen05 tensor cores (1e-3 class) */
-enum { RSLRL_PREC_FP32 = 0, RSLRL_PREC_TF32 = 1 };
+enum { RSLRL_PREC_FP32 = 0, RSLRL_PREC_TF32 = 1, RSLRL_PREC_FP16 = 2 };
+/* RSLRL_PREC_FP16 ("16-bit activation storage"): the saved activations h, the layer gradients dy / dx, the
+ * minibatch observations x and a shadow copy of the weights are IEEE fp16 in HBM (10-bit mantissa = the precision
+ * tf32 gives the same operands) and the MMAs are tcgen05 kind::f16 with fp32 accumulation.  Master weights, weight /
+ * bias gradients, biases and the network outputs stay fp32.  Layer gradients carry a power-of-two scale (set where
+ * the chain starts, rslrl_linear_bwd_head_t.dx_scale, undone by rslrl_linear_bwd_weight_t.scale) so that they stay
+ * in fp16's normal range.  In this mode the pointers documented "fp32, or fp16 with RSLRL_PREC_FP16" below are
+ * `const __half*`; row strides are always in elements. */
 /* action-noise parameterisation (rsl_rl/modules/actor_critic.py:88-93,133-138) */
 enum { RSLRL_STD_SCALAR = 0, RSLRL_STD_LOG = 1 };
 
@@ -110,10 +117,11 @@ typedef struct {
 } rslrl_linear_fwd_t;
 
 typedef struct {
-  const float* dy; /* [M,N], row stride ldy : gradient w.r.t. this layer's pre-activation output */
-  const float* w;  /* [N,K] */
-  const float* h;  /* [M,K], row stride ldh : this layer's INPUT (= previous layer's activation output) */
-  float* dx;       /* [M,K], row stride ldx : gradient w.r.t. previous layer's pre-activation */
+  const void* dy; /* [M,N], row stride ldy : gradient w.r.t. this layer's pre-activation output (fp32, or fp16 with
+                     RSLRL_PREC_FP16 -- as are w, h and dx) */
+  const void* w;  /* [N,K] */
+  const void* h;  /* [M,K], row stride ldh : this layer's INPUT (= previous layer's activation output) */
+  void* dx;       /* [M,K], row stride ldx : gradient w.r.t. previous layer's pre-activation */
   int M, N, K, ldy, ldh, ldx;
   int act;         /* activation of the PREVIOUS layer: dx = (dy W) * act'(.) evaluated from h */
   float* db_prev;  /* [K] or NULL: += column sums of dx = bias gradient of the previous layer (fused into the
@@ -121,22 +129,25 @@ typedef struct {
 } rslrl_linear_bwd_data_t;
 
 typedef struct {
-  const float* dy; /* [M,N], row stride ldy */
-  const float* x;  /* [M,K], row stride ldx */
-  float* dw;       /* [N,K] accumulated:  dw += dy^T x */
-  float* db;       /* [N]   accumulated:  db += colsum(dy); may be NULL */
+  const void* dy; /* [M,N], row stride ldy (fp32, or fp16 with RSLRL_PREC_FP16 -- as is x) */
+  const void* x;  /* [M,K], row stride ldx */
+  float* dw;      /* [N,K] accumulated:  dw += scale * dy^T x */
+  float* db;      /* [N]   accumulated:  db += scale * colsum(dy); may be NULL */
   int M, N, K, ldy, ldx;
+  float scale;    /* 0 is read as 1; the fp16 path passes 1 / dx_scale of the chain's head */
 } rslrl_linear_bwd_weight_t;
 
 typedef struct {
   const float* dy; /* [M,N], row stride ldy */
   const float* w;  /* [N,K] */
-  const float* h;  /* [M,K], row stride ldh : the layer's input (previous activation output) */
-  float* dx;       /* [M,K], row stride ldx, or NULL : (dy W) * act'(h) */
-  float* dw;       /* [N,K] accumulated */
+  const void* h;   /* [M,K], row stride ldh : the layer's input (previous activation output); fp16 if f16 != 0 */
+  void* dx;        /* [M,K], row stride ldx, or NULL : dx_scale * (dy W) * act'(h); fp16 if f16 != 0 */
+  float* dw;       /* [N,K] accumulated (never scaled) */
   float* db;       /* [N] accumulated, or NULL */
   int M, N, K, ldy, ldh, ldx;
   int act;         /* activation of the previous layer */
+  int f16;         /* h and dx are fp16 */
+  float dx_scale;  /* 0 is read as 1 */
 } rslrl_linear_bwd_head_t;
 
 /* Whole 3-hidden-layer MLP forward in ONE launch (rsl_rl/networks/mlp.py:106-114 for actor and critic):
@@ -145,13 +156,16 @@ typedef struct {
  * none) receive the hidden activations for the backward pass; NULL (rollout, inference) stores nothing but y. */
 typedef struct {
   const float* x;    /* [M,K0], row stride ldx */
-  const float* w[4]; /* nn.Linear weights: [N1,K0] (row stride ldw0), [N2,N1], [N3,N2], [N4,N3] row-major */
+  const void* w[4];  /* nn.Linear weights: [N1,K0] (row stride ldw0), [N2,N1], [N3,N2], [N4,N3] row-major; w[0] is
+                        always fp32, w[1..3] are the fp16 shadows when precision == RSLRL_PREC_FP16 */
   const float* b[4]; /* biases (entries may be NULL) */
-  float* h[3];       /* [M,N1], [M,N2], [M,N3] with row strides ldh[i], or all NULL */
+  void* h[3];        /* [M,N1], [M,N2], [M,N3] with row strides ldh[i], or all NULL (fp16 with RSLRL_PREC_FP16) */
   float* y;          /* [M,N4], row stride ldy */
   int M, K0, N1, N2, N3, N4;
   int ldx, ldw0, ldh[3], ldy;
   int act;           /* RSLRL_ACT_* of the three hidden layers */
+  int precision;     /* RSLRL_PREC_TF32 (0 is read as TF32) or RSLRL_PREC_FP16: layer 1 always runs in tf32 on the
+                        fp32 x / w[0]; layers 2-4 consume the on-chip activations as tf32 or fp16 */
 } rslrl_mlp3_fwd_t;
 
 /* Each call runs `n` independent problems (e.g. actor and critic) in one launch; *_host arrays live
@@ -285,6 +299,11 @@ int rslrl_hidden_at_starts(const float* saved, const int32_t* traj_env, const in
 
 /* ---- small utilities ------------------------------------------------------------------------- */
 int rslrl_fill_zero(void* p, int64_t bytes, rslrl_stream_t stream);
+/* dst[r, c] = (fp16, round to nearest even, saturating) src[r, c] for r < rows, c < cols; columns [cols, cols_pad) of
+ * dst are written as zero.  Row strides in elements.  Used for the fp16 shadow of the flat parameter buffer
+ * (rows = 1) and of the permuted minibatch observations (RSLRL_PREC_FP16). */
+int rslrl_convert_f32_f16(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int64_t rows, int cols,
+                          int cols_pad, rslrl_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -19,8 +19,8 @@ c_void_p, c_int, c_i64, c_double = C.c_void_p, C.c_int, C.c_int64, C.c_double
 U8, I32, I64, F32 = 0, 1, 2, 3
 ACT_CODES = {"identity": 0, "elu": 1, "relu": 2, "tanh": 3, "sigmoid": 4, "lrelu": 5, "selu": 6, "softplus": 7,
              "crelu": 1}  # nn.CELU(alpha=1) == nn.ELU(alpha=1)
-PREC_FP32, PREC_TF32 = 0, 1
-PREC_CODES = {"fp32": PREC_FP32, "tf32": PREC_TF32}
+PREC_FP32, PREC_TF32, PREC_FP16 = 0, 1, 2
+PREC_CODES = {"fp32": PREC_FP32, "tf32": PREC_TF32, "fp16": PREC_FP16}
 STD_SCALAR, STD_LOG = 0, 1
 MAX_SEGMENTS, MAX_PROBLEMS = 16, 4
 
@@ -38,19 +38,19 @@ class LinearBwdData(C.Structure):
 
 class LinearBwdWeight(C.Structure):
     _fields_ = [("dy", c_void_p), ("x", c_void_p), ("dw", c_void_p), ("db", c_void_p),
-                ("M", c_int), ("N", c_int), ("K", c_int), ("ldy", c_int), ("ldx", c_int)]
+                ("M", c_int), ("N", c_int), ("K", c_int), ("ldy", c_int), ("ldx", c_int), ("scale", C.c_float)]
 
 
 class LinearBwdHead(C.Structure):
     _fields_ = [("dy", c_void_p), ("w", c_void_p), ("h", c_void_p), ("dx", c_void_p), ("dw", c_void_p),
                 ("db", c_void_p), ("M", c_int), ("N", c_int), ("K", c_int), ("ldy", c_int), ("ldh", c_int),
-                ("ldx", c_int), ("act", c_int)]
+                ("ldx", c_int), ("act", c_int), ("f16", c_int), ("dx_scale", C.c_float)]
 
 
 class Mlp3Fwd(C.Structure):
     _fields_ = [("x", c_void_p), ("w", c_void_p * 4), ("b", c_void_p * 4), ("h", c_void_p * 3), ("y", c_void_p),
                 ("M", c_int), ("K0", c_int), ("N1", c_int), ("N2", c_int), ("N3", c_int), ("N4", c_int),
-                ("ldx", c_int), ("ldw0", c_int), ("ldh", c_int * 3), ("ldy", c_int), ("act", c_int)]
+                ("ldx", c_int), ("ldw0", c_int), ("ldh", c_int * 3), ("ldy", c_int), ("act", c_int), ("precision", c_int)]
 
 
 class OptState(C.Structure):
@@ -101,6 +101,7 @@ _SIGNATURES = {
     "rslrl_unpad": (c_int, [c_void_p] * 4 + [c_int] * 7 + [c_void_p]),
     "rslrl_hidden_at_starts": (c_int, [c_void_p] * 4 + [c_int] * 7 + [c_void_p]),
     "rslrl_fill_zero": (c_int, [c_void_p, c_i64, c_void_p]),
+    "rslrl_convert_f32_f16": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_i64, c_int, c_int, c_void_p]),
 }
 
 # the ppo_loss signature above is easier to read spelled out:

@@ -19,6 +19,7 @@ from __future__ import annotations
 
 from typing import List, Optional
 
+import math
 import os
 
 import torch
@@ -57,10 +58,13 @@ def supports(policy) -> Optional[str]:
 
 
 class FeedForwardEngine:
-    def __init__(self, policy, storage_rows: int, num_envs: int, minibatch_rows: int, device, precision: str):
+    def __init__(self, policy, storage_rows: int, num_envs: int, minibatch_rows: int, device, precision: str,
+                 param_group: Optional[FlatParamGroup] = None):
         self.policy = policy
         self.device = torch.device(device)
         self.prec = nat.PREC_CODES[precision]
+        self.f16 = precision == "fp16"
+        self.group = param_group
         self.actor, self.critic = _Net(policy.actor), _Net(policy.critic)
         self.A = self.actor.dims[-1]
         self.std_param = policy.std if policy.noise_std_type == "scalar" else policy.log_std
@@ -68,12 +72,26 @@ class FeedForwardEngine:
         self.rows = max(num_envs, minibatch_rows)
         f32 = dict(dtype=torch.float32, device=self.device)
         R = self.rows
+        if self.f16:
+            # 16-bit storage: saved activations and layer gradients are fp16 in HBM (half the bytes of the update's
+            # dominant streams), the kind::f16 MMAs read fp16 weight shadows; layer gradients carry a power-of-two
+            # scale (~ minibatch size, undoing the 1/mb of the mean losses) so that they sit in fp16's normal range
+            why = self._fp16_ineligible()
+            if why:
+                raise ValueError(f"gemm_precision='fp16' is not available for this policy: {why}")
+            if param_group is None:
+                raise ValueError("gemm_precision='fp16' needs the flat parameter group (fp16 weight shadow)")
+            param_group.enable_shadow16()
+            self.grad_scale = float(2 ** round(math.log2(max(minibatch_rows, 1))))
+        else:
+            self.grad_scale = 1.0
+        adt = dict(dtype=torch.float16 if self.f16 else torch.float32, device=self.device)
         # activations (outputs of hidden layers) and ping-pong gradient buffers
-        self.h_a = [torch.empty(R, d, **f32) for d in self.actor.dims[1:-1]]
-        self.h_c = [torch.empty(R, d, **f32) for d in self.critic.dims[1:-1]]
+        self.h_a = [torch.empty(R, d, **adt) for d in self.actor.dims[1:-1]]
+        self.h_c = [torch.empty(R, d, **adt) for d in self.critic.dims[1:-1]]
         wa, wc = max(self.actor.dims[1:-1] + [1]), max(self.critic.dims[1:-1] + [1])
-        self.g_a = [torch.empty(R * wa, **f32) for _ in range(2)]
-        self.g_c = [torch.empty(R * wc, **f32) for _ in range(2)]
+        self.g_a = [torch.empty(R * wa, **adt) for _ in range(2)]
+        self.g_c = [torch.empty(R * wc, **adt) for _ in range(2)]
         self.mu = torch.empty(R, self.A, **f32)
         self.value = torch.empty(R, 1, **f32)
         # gradient heads keep a 16-byte row pitch so that TMA can read them (dvalue: 1 used column of 4)
@@ -90,14 +108,28 @@ class FeedForwardEngine:
                     self.w0_pad[tag] = torch.zeros(net.dims[1], (K + 3) // 4 * 4, **f32)
         self.refresh_padded()
         # whole-MLP forward in one launch (activations stay on chip between the layers): tf32 mode, eligible shapes
-        self.fused_fwd = (precision == "tf32" and os.environ.get("RSLRL_FUSED_MLP", "1") != "0"
-                          and all(mlp3_eligible(n.dims, n.acts) for n in (self.actor, self.critic)))
+        self.fused_fwd = self.f16 or (precision == "tf32" and os.environ.get("RSLRL_FUSED_MLP", "1") != "0"
+                                      and all(mlp3_eligible(n.dims, n.acts) for n in (self.actor, self.critic)))
+        self.needs_refresh = bool(self.w0_pad) or self.f16
         self.loss_ws = torch.zeros(int(nat.lib().rslrl_loss_workspace_bytes()), dtype=torch.uint8, device=self.device)
         self.sum_ws = torch.zeros(64, dtype=torch.uint8, device=self.device)
         self.adv_stats = torch.zeros(2, dtype=torch.float64, device=self.device)
 
     # ---------------------------------------------------------------------------------------------
+    def _fp16_ineligible(self) -> Optional[str]:
+        for name, net in (("actor", self.actor), ("critic", self.critic)):
+            if not mlp3_eligible(net.dims, net.acts):
+                return f"{name} {net.dims} is not a 3-hidden-layer MLP the fused forward covers"
+            if any(d % 64 for d in net.dims[1:-1]):
+                return f"{name} hidden widths {net.dims[1:-1]} must be multiples of 64"
+            if net.dims[-1] > 12:
+                return f"{name} output width {net.dims[-1]} > 12 (the output layer's backward is the narrow-head kernel)"
+        return None
+
     def refresh_padded(self):
+        """Derived copies of the parameters: zero-padded first-layer weights, fp16 weight shadow."""
+        if self.f16:
+            self.group.refresh_shadow16()
         with torch.no_grad():
             for tag, buf in self.w0_pad.items():
                 net = self.actor if tag == "a" else self.critic
@@ -152,9 +184,10 @@ class FeedForwardEngine:
     def _mlp3(self, tag: str, x_ptr: int, ldx: int, M: int, out: torch.Tensor, store: bool):
         net, hs = (self.actor, self.h_a) if tag == "a" else (self.critic, self.h_c)
         w0 = self._layer0(tag, None, ldx)[1]
-        weights = [w0] + [l.weight for l in net.layers[1:]]
+        weights = [w0] + [self.group.shadow16(l.weight) if self.f16 else l.weight for l in net.layers[1:]]
         return mlp3_struct(x_ptr, ldx, M, weights, [l.bias for l in net.layers],
-                           [h[:M] for h in hs] if store else None, out, net.acts[0])
+                           [h[:M] for h in hs] if store else None, out, net.acts[0],
+                           nat.PREC_FP16 if self.f16 else nat.PREC_TF32)
 
     # ---- prebuilt launch plans for the rollout: everything static except the observation pointers ---------
     def build_forward_plan(self, M: int, ld_a: int, ld_c: int, mu_out: torch.Tensor, v_out: torch.Tensor,
@@ -213,7 +246,10 @@ class FeedForwardEngine:
         return run
 
     def backward(self, x_a: torch.Tensor, x_c: torch.Tensor, dmu: torch.Tensor, dvalue: torch.Tensor):
-        """dL/dW, dL/db accumulated into the parameters' .grad views (flat gradient buffer)."""
+        """dL/dW, dL/db accumulated into the parameters' .grad views (flat gradient buffer).  fp16 mode: x_a / x_c are
+        the fp16 copies of the minibatch observations."""
+        if self.f16:
+            return self._backward16(x_a, x_c, dmu, dvalue)
         M = x_a.shape[0]
         nets = ((self.actor, self.h_a, self.g_a, x_a, dmu), (self.critic, self.h_c, self.g_c, x_c, dvalue))
         dy = [dmu, dvalue]
@@ -242,6 +278,35 @@ class FeedForwardEngine:
                 linear_backward_weight(wprobs, self.prec)
             if dprobs:
                 linear_backward_data(dprobs, self.prec)
+            dy = new_dy
+
+    def _backward16(self, x_a: torch.Tensor, x_c: torch.Tensor, dmu: torch.Tensor, dvalue: torch.Tensor):
+        """fp16-storage backward: narrow-head kernel (fp32 math, writes S * dZ3 as fp16), then per layer one grouped
+        wgrad launch (dW += dZ^T H / S, bias gradient from the same tiles) and one grouped dgrad launch."""
+        M = x_a.shape[0]
+        S, prec = self.grad_scale, nat.PREC_FP16
+        nets = ((self.actor, self.h_a, self.g_a, x_a, dmu), (self.critic, self.h_c, self.g_c, x_c, dvalue))
+        hprobs, dy = [], []
+        for net, hs, gbuf, _, d_out in nets:
+            lin, l = net.layers[-1], net.L - 1
+            dx = gbuf[0][:M * net.dims[l]].view(M, net.dims[l])
+            hprobs.append((d_out, lin.weight, hs[l - 1][:M], dx, lin.weight.grad, lin.bias.grad, net.acts[l - 1], S))
+            dy.append(dx)
+        linear_backward_head(hprobs)
+        for k in range(1, self.actor.L):
+            wprobs, dprobs, new_dy = [], [], list(dy)
+            for ni, (net, hs, gbuf, x_in, _) in enumerate(nets):
+                l = net.L - 1 - k
+                lin = net.layers[l]
+                inp = x_in if l == 0 else hs[l - 1][:M]
+                wprobs.append((dy[ni], inp, lin.weight.grad, lin.bias.grad, 1.0 / S))
+                if l > 0:
+                    dx = gbuf[k % 2][:M * net.dims[l]].view(M, net.dims[l])
+                    dprobs.append((dy[ni], self.group.shadow16(lin.weight), inp, dx, net.acts[l - 1]))
+                    new_dy[ni] = dx
+            linear_backward_weight(wprobs, prec)
+            if dprobs:
+                linear_backward_data(dprobs, prec)
             dy = new_dy
 
     def gaussian_head(self, mu, z, actions_out, logp_out, sigma_out):

@@ -4,7 +4,7 @@ The reference keeps 17 separate parameter tensors, concatenates their gradients 
 (`torch.cat` + 17 `copy_` back, rsl_rl/algorithms/ppo.py:441-469) and steps them with foreach-Adam.
 Here a parameter group owns four flat fp32 buffers in HBM -- values, gradients, exp_avg, exp_avg_sq --
 laid out in `module.parameters()` order (`[std, actor.0.weight, actor.0.bias, ...]`, the reference's
-own flattening order), each tensor starting on a 16-byte boundary.  `param.data` and `param.grad`
+own flattening order), each tensor starting on a 32-byte boundary.  `param.data` and `param.grad`
 are views, so state_dict()/load_state_dict()/checkpoints see ordinary tensors while the kernels see
 one contiguous span: the gradient all-reduce is in place, clip+Adam is two launches.
 
@@ -21,7 +21,7 @@ import torch.nn as nn
 
 from .. import _native as nat
 
-ALIGN = 4  # floats (16 bytes): float4 accesses and TMA base alignment
+ALIGN = 8  # elements: 32 bytes in fp32 (float4 accesses, TMA base alignment) = 16 bytes in the fp16 weight shadow
 
 
 class FlatParamGroup:
@@ -45,6 +45,7 @@ class FlatParamGroup:
         self.kl_slot = self.grads_ext[off:off + 1]
         self.exp_avg = torch.zeros(off, **f32)
         self.exp_avg_sq = torch.zeros(off, **f32)
+        self.values16 = None  # fp16 shadow of `values` (same element offsets), see enable_shadow16()
         self.bind()
 
     def _view(self, flat: torch.Tensor, i: int) -> torch.Tensor:
@@ -64,6 +65,25 @@ class FlatParamGroup:
                     if p.grad is not None:
                         g.copy_(p.grad)
                     p.grad = g
+
+    # ---- fp16 weight shadow (gemm_precision="fp16"): the kind::f16 MMAs read the weights from here
+    def enable_shadow16(self):
+        if self.values16 is None:
+            self.values16 = torch.zeros(self.numel, dtype=torch.float16, device=self.device)
+        self.refresh_shadow16()
+
+    def refresh_shadow16(self):
+        """values16 = fp16(values): one launch over the flat buffer (after every optimiser step / parameter load)."""
+        if self.values16 is not None:
+            nat.check(nat.lib().rslrl_convert_f32_f16(self.values.data_ptr(), self.numel, self.values16.data_ptr(),
+                                                      self.numel, 1, self.numel, self.numel, nat.stream_ptr()))
+
+    def shadow16(self, p: nn.Parameter) -> torch.Tensor:
+        """The fp16 shadow view of parameter `p` (same shape)."""
+        for off, q in zip(self.offsets, self.params):
+            if q is p:
+                return self.values16[off:off + p.numel()].view(p.shape)
+        raise KeyError("parameter is not part of this group")
 
     def is_bound(self) -> bool:
         base = self.values.data_ptr()

@@ -65,6 +65,7 @@ class PPO:
         multi_gpu_cfg: dict | None = None,
         # --- rsl_rl_b200 extensions (all optional) ---
         gemm_precision: str = "fp32",   # "fp32": CUDA-core FMA (1e-5 class) | "tf32": tcgen05 tensor cores (1e-3 class)
+                                         # | "fp16": tcgen05 kind::f16 on fp16-stored activations/gradients (1e-3 class)
         use_cuda_graph: bool = True,     # capture update() into one CUDA graph (single-GPU fused path)
         rng_compat: bool = True,         # consume the RNG exactly like the reference (discarded draws in update())
     ):
@@ -174,7 +175,8 @@ class PPO:
         if self._engine_reason is None:
             B = num_envs * num_transitions_per_env
             mb = B // self.num_mini_batches
-            self._engine = _engine.FeedForwardEngine(self.policy, B, num_envs, mb, self.device, self.gemm_precision)
+            self._engine = _engine.FeedForwardEngine(self.policy, B, num_envs, mb, self.device, self.gemm_precision,
+                                                     self._group)
             self._alloc_update_buffers(num_envs, num_transitions_per_env)
 
     @property
@@ -200,7 +202,7 @@ class PPO:
         s = st.step
         if s >= st.num_transitions_per_env:
             raise OverflowError("Rollout buffer overflow! You should call clear() before adding new transitions.")
-        if s == 0 and eng.w0_pad:
+        if s == 0 and eng.needs_refresh:
             eng.refresh_padded()  # parameters may have been loaded / modified since the last optimiser step
         x_a, x_c = self._inputs(obs)
         key = (x_a.stride(0), x_c.stride(0), x_a.shape[1], x_c.shape[1], self._group.values.data_ptr())
@@ -328,6 +330,11 @@ class PPO:
         self._perm = torch.empty(Bp, dtype=torch.int64, device=dev)
         self._last_values = torch.empty(N, 1, **f32)
         self._discard = torch.empty(self._mb, A, **f32)
+        if self._engine.f16:   # fp16 copies of the permuted observations: the B operand of the first layer's wgrad
+            pad8 = lambda d: (d + 7) // 8 * 8
+            f16 = dict(dtype=torch.float16, device=dev)
+            self._xa16 = torch.zeros(Bp, pad8(self._Oa), **f16)
+            self._xc16 = self._xa16 if pol.critic_shares_actor_input else torch.zeros(Bp, pad8(self._Oc), **f16)
 
     def _hyper(self):
         return dict(clip_param=float(self.clip_param), value_loss_coef=float(self.value_loss_coef),
@@ -366,11 +373,20 @@ class PPO:
             xc = nat.f32c(pol.critic_obs_normalizer(xc))
         return xa, xc
 
+    def _to_f16(self, x: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+        nat.check(nat.lib().rslrl_convert_f32_f16(x.data_ptr(), x.stride(0), dst.data_ptr(), dst.stride(0), x.shape[0],
+                                                  x.shape[1], dst.shape[1], nat.stream_ptr()))
+        return dst[:, :x.shape[1]]
+
     def _update_kernels(self):
         """Everything update() puts on the stream; capturable (static pointers, no host reads)."""
         eng, opt, hp = self._engine, self.optimizer, self._hyper()
         mb, M = self._mb, self.num_mini_batches
         xa, xc = self._gather_all()
+        xa16 = xc16 = None
+        if eng.f16:
+            xa16, xc16 = self._to_f16(xa, self._xa16), None
+            xc16 = xa16 if xc is xa else self._to_f16(xc, self._xc16)
         ds = opt.dev_state
         nat.check(nat.lib().rslrl_fill_zero(ds.loss_sums.data_ptr(), 24, nat.stream_ptr()))
         adaptive = self.desired_kl is not None and self.schedule == "adaptive"
@@ -382,7 +398,10 @@ class PPO:
                 eng.loss(mb, mb, mu, value, self._p_actions[r], self._p_logp[r], self._p_adv[r], self._p_ret[r],
                          self._p_values[r], self._p_mu[r], self._p_sigma[r], self._group.kl_slot, ds.loss_sums, hp,
                          self.normalize_advantage_per_mini_batch)
-                eng.backward(xa[r], xc[r], eng.dmu[:mb], eng.dvalue[:mb])
+                if eng.f16:
+                    eng.backward(xa16[r], xc16[r], eng.dmu[:mb], eng.dvalue[:mb])
+                else:
+                    eng.backward(xa[r], xc[r], eng.dmu[:mb], eng.dvalue[:mb])
                 if self._mb_hook is not None:
                     self._mb_hook(self)
                 if self.is_multi_gpu and not opt.peer_allreduce:

@@ -12,6 +12,8 @@
 //   dgrad     dX = (dY W) * act'(H)      A = dY (KC),  B = W (MC)          epilogue: activation gradient
 //   wgrad     dW += dY^T X, db += 1^T dY A = dY (MC),  B = X (MC), split-K epilogue: vector atomics
 // Several problems (actor and critic) share one launch (blockIdx.y).
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace rslrl {
@@ -268,7 +270,8 @@ int simt_linear_backward_data(int n, const rslrl_linear_bwd_data_t* pr, cudaStre
   for (int i = 0; i < n; ++i) {
     GemmProblem& P = b.p[i];
     // dX[M,K] = sum_n dY[m,n] W[n,k]  ->  C[M, K] with reduction length N
-    P.A = pr[i].dy; P.B = pr[i].w; P.C = pr[i].dx; P.H = pr[i].h; P.colsum = pr[i].db_prev;
+    P.A = (const float*)pr[i].dy; P.B = (const float*)pr[i].w; P.C = (float*)pr[i].dx; P.H = (const float*)pr[i].h;
+    P.colsum = pr[i].db_prev;
     P.M = pr[i].M; P.N = pr[i].K; P.K = pr[i].N;
     P.lda = pr[i].ldy; P.ldb = pr[i].K; P.ldc = pr[i].ldx; P.ldh = pr[i].ldh; P.act = pr[i].act;
     P.splits = 1; P.k_per_split = pr[i].N;
@@ -283,7 +286,7 @@ int simt_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* pr, cuda
   for (int i = 0; i < n; ++i) {
     GemmProblem& P = b.p[i];
     // dW[N,K] += sum_m dY[m,n] X[m,k]  ->  C[N, K] with reduction length M
-    P.A = pr[i].dy; P.B = pr[i].x; P.C = pr[i].dw; P.colsum = pr[i].db;
+    P.A = (const float*)pr[i].dy; P.B = (const float*)pr[i].x; P.C = pr[i].dw; P.colsum = pr[i].db;
     P.M = pr[i].N; P.N = pr[i].K; P.K = pr[i].M;
     P.lda = pr[i].ldy; P.ldb = pr[i].ldx; P.ldc = pr[i].K;
     P.splits = pick_splits(tiles_all, pr[i].M);
@@ -308,8 +311,9 @@ int simt_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* pr, cuda
 namespace rslrl {
 
 struct HeadBwdProblem {
-  const float* dy; const float* w; const float* h; float* dx; float* dw; float* db;
+  const float* dy; const float* w; const void* h; void* dx; float* dw; float* db;
   int M, N, K, ldy, ldh, ldx, act;
+  float dx_scale;
 };
 struct HeadBwdBatch { HeadBwdProblem p[RSLRL_MAX_PROBLEMS]; };
 
@@ -319,6 +323,30 @@ constexpr int HEADB_MAX_N = 12;
 // K <= 128 per pass (lane <-> 4 consecutive input columns); wider inputs loop over 128-column panels.
 constexpr int HEADB_ROWS = 4;  // rows per warp iteration: all their loads are issued before any is consumed
 
+// 4 consecutive elements of a row of h / dx, fp32 or fp16 storage
+template <bool F16>
+__device__ __forceinline__ float4 headb_load4(const void* base, size_t elem) {
+  if constexpr (F16) {
+    const uint2 raw = __ldg((const uint2*)((const __half*)base + elem));
+    const float2 a = __half22float2(*(const __half2*)&raw.x), b = __half22float2(*(const __half2*)&raw.y);
+    return make_float4(a.x, a.y, b.x, b.y);
+  } else {
+    return __ldg((const float4*)((const float*)base + elem));
+  }
+}
+template <bool F16>
+__device__ __forceinline__ void headb_store4(void* base, size_t elem, float4 o) {
+  if constexpr (F16) {
+    uint2 raw;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(raw.x) : "f"(o.y), "f"(o.x));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(raw.y) : "f"(o.w), "f"(o.z));
+    *(uint2*)((__half*)base + elem) = raw;
+  } else {
+    *(float4*)((float*)base + elem) = o;
+  }
+}
+
+template <bool F16>
 __global__ void __launch_bounds__(HEADB_WARPS * 32, 2) head_backward_kernel(const HeadBwdBatch batch) {
   __shared__ float s_dw[HEADB_MAX_N][128];
   __shared__ __align__(16) float s_w[HEADB_MAX_N][128];
@@ -350,7 +378,7 @@ __global__ void __launch_bounds__(HEADB_WARPS * 32, 2) head_backward_kernel(cons
         const int r = row + j * nwarps;
         const bool ok = r < P.M;
         dyl[j] = (ok && lane < N) ? __ldg(P.dy + (size_t)r * P.ldy + lane) : 0.f;
-        hv[j] = (ok && col_ok) ? __ldg((const float4*)(P.h + (size_t)r * P.ldh + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        hv[j] = (ok && col_ok) ? headb_load4<F16>(P.h, (size_t)r * P.ldh + col) : make_float4(0.f, 0.f, 0.f, 0.f);
         dx[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
@@ -382,7 +410,8 @@ __global__ void __launch_bounds__(HEADB_WARPS * 32, 2) head_backward_kernel(cons
               o.x *= act_grad_from_output(P.act, hv[j].x); o.y *= act_grad_from_output(P.act, hv[j].y);
               o.z *= act_grad_from_output(P.act, hv[j].z); o.w *= act_grad_from_output(P.act, hv[j].w);
             }
-            *(float4*)(P.dx + (size_t)r * P.ldx + col) = o;
+            o.x *= P.dx_scale; o.y *= P.dx_scale; o.z *= P.dx_scale; o.w *= P.dx_scale;
+            headb_store4<F16>(P.dx, (size_t)r * P.ldx + col, o);
           }
         }
       }
@@ -411,13 +440,17 @@ int head_linear_backward(int n, const rslrl_linear_bwd_head_t* pr, cudaStream_t 
   HeadBwdBatch b{};
   for (int i = 0; i < n; ++i) {
     const rslrl_linear_bwd_head_t& q = pr[i];
-    if (q.N > HEADB_MAX_N || (q.K & 3) || (q.ldh & 3) || ((uintptr_t)q.h & 15) || ((uintptr_t)q.w & 15)) return -1;
-    if (q.dx && ((q.ldx & 3) || ((uintptr_t)q.dx & 15))) return -1;
-    b.p[i] = HeadBwdProblem{q.dy, q.w, q.h, q.dx, q.dw, q.db, q.M, q.N, q.K, q.ldy, q.ldh, q.ldx, q.act};
+    if (q.N > HEADB_MAX_N || (q.K & 3) || (q.ldh & 3) || ((uintptr_t)q.h & 7) || ((uintptr_t)q.w & 15)) return -1;
+    if (!q.f16 && ((uintptr_t)q.h & 15)) return -1;
+    if (q.dx && ((q.ldx & 3) || ((uintptr_t)q.dx & (q.f16 ? 7 : 15)))) return -1;
+    if ((q.f16 != 0) != (pr[0].f16 != 0)) return -1;
+    b.p[i] = HeadBwdProblem{q.dy, q.w, q.h, q.dx, q.dw, q.db, q.M, q.N, q.K, q.ldy, q.ldh, q.ldx, q.act,
+                            q.dx_scale == 0.f ? 1.f : q.dx_scale};
   }
   // one block per SM per problem: the weight-gradient partials end in global atomics (N x K per block), so fewer,
   // longer-running blocks keep the per-address contention at 148
-  head_backward_kernel<<<dim3(kNumSMs, n), HEADB_WARPS * 32, 0, st>>>(b);
+  if (pr[0].f16) head_backward_kernel<true><<<dim3(kNumSMs, n), HEADB_WARPS * 32, 0, st>>>(b);
+  else head_backward_kernel<false><<<dim3(kNumSMs, n), HEADB_WARPS * 32, 0, st>>>(b);
   return finish_launch("rslrl_linear_backward_head");
 }
 

@@ -24,6 +24,7 @@
 // column sum of the dY it receives, so it is accumulated by the kernel that PRODUCES that dY (the dgrad
 // epilogue here, the loss kernel for the output layers) instead of re-reading dY.
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include <cstdlib>
 #include <mutex>
@@ -45,6 +46,7 @@ struct TcProblem {
   float* db;          // wgrad: += sum over the batch of dY (bias gradient); may be null
   int M, N, K;        // C is [M,N], reduction length K
   int ldc, act, tma_out;
+  float out_scale;    // wgrad: dW, db += out_scale * (...)  (undoes the power-of-two gradient scaling of the fp16 path)
   int block_n, tiles_m, tiles_n, splits, kb_per_split, num_kb;
 };
 
@@ -76,6 +78,7 @@ struct TcpScalars {  // per-problem scalars mirrored into shared memory once per
   float* C;
   const float* bias;
   float* db;
+  float out_scale;
   int M, N, ldc, act, tma_out, block_n, tiles_m, tiles_n, splits, kb_per_split, num_kb, tile_count;
 };
 
@@ -96,12 +99,21 @@ __device__ __forceinline__ unsigned long long gtime() {
 #define TRACE_TILE(slot) do { } while (0)
 #endif
 
-template <int MODE>
+// F16 = operands (and the dgrad's H input / dX output) are fp16 in HBM: kind::f16 MMAs, k-blocks of 64 elements (the
+// same 128-byte rows), MN-major operands in the plain 128-byte swizzle (64-element atoms, 8 KB TMA boxes).
+template <int MODE, bool F16>
 __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(const __grid_constant__ TcBatch batch,
                                                                             const int n_problems) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr bool A_MN = MODE == TC_WGRAD;
   constexpr bool B_MN = MODE != TC_FWD;
+  constexpr int BK = F16 ? 64 : 32;            // elements per k-block (one 128-byte row)
+  constexpr int MNB = F16 ? 64 : 32;           // MN-major operands: elements per TMA box along MN
+  constexpr uint32_t MN_BOX = F16 ? 8192u : 4096u;    // bytes per MN-major box (MNB x BK elements)
+  constexpr uint32_t MN_KADV = F16 ? 2048u : 1024u;   // MN-major: bytes per MMA k-step (16 / 8 rows of 128 bytes)
+  constexpr uint32_t MN_SBO = F16 ? 1024u : 512u;
+  constexpr uint32_t MN_LAYOUT = F16 ? kLayoutSw128 : kLayoutSw128Base32;
+  constexpr int CH = (MODE == TC_DGRAD && F16) ? 64 : 32;  // epilogue chunk width in output columns
 
   const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
   uint8_t* const ring = smem_raw + pad;
@@ -129,7 +141,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
   if (threadIdx.x < n_problems) {
     const TcProblem& P = batch.p[threadIdx.x];
     TcpScalars q;
-    q.C = P.C; q.bias = P.bias; q.db = P.db; q.M = P.M; q.N = P.N; q.ldc = P.ldc; q.act = P.act;
+    q.C = P.C; q.bias = P.bias; q.db = P.db; q.out_scale = P.out_scale; q.M = P.M; q.N = P.N; q.ldc = P.ldc; q.act = P.act;
     q.tma_out = P.tma_out; q.block_n = P.block_n; q.tiles_m = P.tiles_m; q.tiles_n = P.tiles_n; q.splits = P.splits;
     q.kb_per_split = P.kb_per_split; q.num_kb = P.num_kb; q.tile_count = P.tiles_m * P.tiles_n * P.splits;
     sp[threadIdx.x] = q;
@@ -201,16 +213,16 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
           uint8_t* sb = sa + a_bytes;
           if (it == 0) TRACE(2);
           mbar_expect_tx(&full_bar[s], tx_bytes);
-          const int k0 = kb * TC_BLOCK_K;
+          const int k0 = kb * BK;
           if (!A_MN) {
             tma_load_2d(sa, map_a, &full_bar[s], k0, m0);
           } else {
-            for (int j = 0; j < TC_BLOCK_M / 32; ++j) tma_load_2d(sa + j * 4096, map_a, &full_bar[s], m0 + j * 32, k0);
+            for (int j = 0; j < TC_BLOCK_M / MNB; ++j) tma_load_2d(sa + j * MN_BOX, map_a, &full_bar[s], m0 + j * MNB, k0);
           }
           if (!B_MN) {
             tma_load_2d(sb, map_b, &full_bar[s], k0, n0);
           } else {
-            for (int j = 0; j < block_n / 32; ++j) tma_load_2d(sb + j * 4096, map_b, &full_bar[s], n0 + j * 32, k0);
+            for (int j = 0; j < block_n / MNB; ++j) tma_load_2d(sb + j * MN_BOX, map_b, &full_bar[s], n0 + j * MNB, k0);
           }
         }
       }
@@ -224,7 +236,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
       const int block_n = sp[pi].block_n;
       const int kb0 = split * sp[pi].kb_per_split;
       const int kb1 = min(sp[pi].num_kb, kb0 + sp[pi].kb_per_split);
-      const uint32_t idesc = make_idesc(block_n, A_MN, B_MN);
+      const uint32_t idesc = F16 ? make_idesc_f16(block_n, A_MN, B_MN) : make_idesc(block_n, A_MN, B_MN);
       const int as = j & 1;
       const uint32_t d_tmem = tmem_base + (uint32_t)as * 256u;
       mbar_wait(&tmem_empty[as], ((j >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
@@ -239,11 +251,12 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
           const uint32_t sb = sa + a_bytes;
 #pragma unroll
           for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
-            const uint64_t da = A_MN ? make_smem_desc(sa + k * 1024, 4096, 512, kLayoutSw128Base32)
+            const uint64_t da = A_MN ? make_smem_desc(sa + k * MN_KADV, MN_BOX, MN_SBO, MN_LAYOUT)
                                      : make_smem_desc(sa + k * 32, 16, 1024, kLayoutSw128);
-            const uint64_t db = B_MN ? make_smem_desc(sb + k * 1024, 4096, 512, kLayoutSw128Base32)
+            const uint64_t db = B_MN ? make_smem_desc(sb + k * MN_KADV, MN_BOX, MN_SBO, MN_LAYOUT)
                                      : make_smem_desc(sb + k * 32, 16, 1024, kLayoutSw128);
-            umma_tf32(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (F16) umma_f16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_tf32(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
         }
         __syncwarp();
@@ -273,7 +286,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
       const CUtensorMap* map_c = &batch.p[pi].map_c;
       const int block_n = P.block_n;
       const int m0 = tm * TC_BLOCK_M, n0 = tn * block_n;
-      const int nchunks = (block_n + 31) / 32;
+      const int nchunks = (block_n + CH - 1) / CH;
       const int row0 = m0 + q * 32;
       const int as = j & 1;
       const bool rows_live = row0 < P.M;
@@ -282,6 +295,61 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
       tcgen05_fence_after();
 
       for (int c = half; c < nchunks; c += 2) {
+        if constexpr (MODE == TC_DGRAD && F16) {
+          // 64 output columns per chunk: the fp16 H chunk (128 rows x 128 bytes, streamed in by warp 10) is multiplied
+          // in place by the accumulator and becomes the staging tile of the fp16 dX bulk store
+          const int c0 = c * 64;
+          uint32_t v0[32], v1[32];
+          const uint32_t taddr = tmem_base + (uint32_t)as * 256u + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+          TMEM_LD_32x32(taddr, v0);
+          TMEM_LD_32x32(taddr + 32u, v1);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (c + 2 >= nchunks) {
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[as])) : "memory");
+          }
+          const int g = gbase + c;
+          const int hs = g % TCP_H_CHUNKS;
+          uint8_t* const blk = staging + (size_t)hs * 16384 + q * 4096;
+          uint8_t* const my_row = blk + lane * 128;
+          mbar_wait(&h_full[hs], (uint32_t)(g / TCP_H_CHUNKS) & 1u);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            uint4* const hp = (uint4*)(my_row + ((u ^ sw) << 4));
+            const uint4 h = *hp;
+            const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+            uint32_t ow[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 hf = unpack_f16x2(hw[e]);
+              const float xa = __uint_as_float(u < 4 ? v0[8 * u + 2 * e] : v1[8 * (u - 4) + 2 * e]);
+              const float xb = __uint_as_float(u < 4 ? v0[8 * u + 2 * e + 1] : v1[8 * (u - 4) + 2 * e + 1]);
+              float ga, gb;
+              if (P.act == RSLRL_ACT_ELU) {
+                ga = fminf(hf.x, 0.f) + 1.f;
+                gb = fminf(hf.y, 0.f) + 1.f;
+              } else {
+                ga = act_grad_from_output(P.act, hf.x);
+                gb = act_grad_from_output(P.act, hf.y);
+              }
+              ow[e] = pack_f16x2(xa * ga, xb * gb);
+            }
+            *hp = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            if (rows_live) tma_store_2d(map_c, blk, n0 + c0, row0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            if (prev_h_slot >= 0) {
+              asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+              asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&h_empty[prev_h_slot])) : "memory");
+            }
+          }
+          prev_h_slot = hs;
+          continue;
+        }
         const int c0 = c * 32;
         const int ncols = min(32, block_n - c0);
         uint32_t v[32];
@@ -370,6 +438,10 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
           }
         }
 
+        if (MODE == TC_WGRAD && P.out_scale != 1.f) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] *= P.out_scale;
+        }
         if (P.tma_out) {
           if (lane == 0)  // the slot's previous store (two chunks ago) must have been read
             asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -421,12 +493,12 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
         const CUtensorMap* map_h = &batch.p[pi].map_h;
         const int block_n = sp[pi].block_n;
         const int m0 = tm * TC_BLOCK_M, n0 = tn * block_n;
-        const int nchunks = (block_n + 31) / 32;
+        const int nchunks = (block_n + CH - 1) / CH;
         for (int c = 0; c < nchunks; ++c, ++g) {
           const int hs = g % TCP_H_CHUNKS;
           mbar_wait(&h_empty[hs], ((uint32_t)(g / TCP_H_CHUNKS) & 1u) ^ 1u);
           mbar_expect_tx(&h_full[hs], 16384u);
-          tma_load_2d(staging + (size_t)hs * 16384, map_h, &h_full[hs], n0 + c * 32, m0);  // box {32 cols, 128 rows}
+          tma_load_2d(staging + (size_t)hs * 16384, map_h, &h_full[hs], n0 + c * CH, m0);  // box {CH cols, 128 rows}
         }
       }
     }
@@ -449,15 +521,22 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
         mbar_wait(&full_bar[s], (it / stages) & 1);
         if (active) {
           const uint8_t* sa = ring + (size_t)s * stage_bytes;
+          if constexpr (F16) {  // 64-feature boxes of 64 rows x 128 bytes, 16-byte chunks XORed with (row & 7)
+            const uint32_t fo = (uint32_t)(f >> 6) * 8192u + (uint32_t)(f & 7) * 2u, fc = (uint32_t)((f & 63) >> 3);
+#pragma unroll 16
+            for (int r = 0; r < 64; ++r)
+              acc += __half2float(*(const __half*)(sa + fo + (uint32_t)r * 128u + ((fc ^ (uint32_t)(r & 7)) << 4)));
+          } else {
 #pragma unroll
-          for (int r = 0; r < TC_BLOCK_K; ++r)
-            acc += *(const float*)(sa + foff + (uint32_t)r * 128u + ((fchunk ^ (uint32_t)(r & 3)) << 5));
+            for (int r = 0; r < TC_BLOCK_K; ++r)
+              acc += *(const float*)(sa + foff + (uint32_t)r * 128u + ((fchunk ^ (uint32_t)(r & 3)) << 5));
+          }
         }
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty_bar[s])) : "memory");
       }
       const int feat = tm * TC_BLOCK_M + f;
-      if (active && feat < sp[pi].M) atomicAdd(db_ptr + feat, acc);
+      if (active && feat < sp[pi].M) atomicAdd(db_ptr + feat, acc * sp[pi].out_scale);
     }
   }
 
@@ -512,6 +591,26 @@ static bool make_map(CUtensorMap* map, const float* base, long long rows, long l
   return r == CUDA_SUCCESS;
 }
 
+// 2-D fp16 tensor [rows, cols] with row pitch ld (elements); box {box_cols <= 64, box_rows}, 128-byte swizzle.
+static bool make_map16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_cols,
+                       int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+bool tc_make_map16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_cols,
+                   int box_rows) {
+  return make_map16(map, base, rows, cols, ld, box_cols, box_rows);
+}
+static bool tma_ok16(const void* p, long long ld) { return ((uintptr_t)p & 15) == 0 && (ld % 8) == 0; }
+
 // exported to the other tcgen05 translation units (mlp_fused.cu)
 bool tc_make_map(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_cols,
                  int box_rows, bool operand) {
@@ -542,11 +641,11 @@ int tc_num_sms() {
   return n;
 }
 
-template <int MODE>
+template <int MODE, bool F16 = false>
 static int launch_tc_persistent(TcBatch& b, int n, cudaStream_t st, const char* what) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_gemm_persistent_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_persistent_kernel<MODE, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          227 * 1024);
     if (e != cudaSuccess) {
       set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
@@ -567,13 +666,15 @@ static int launch_tc_persistent(TcBatch& b, int n, cudaStream_t st, const char* 
                       (2 * TCP_MAX_STAGES + 4 + 2 * TCP_H_CHUNKS) * 8 + 16 + 2 * sizeof(TcpScalars) +
                       TCP_EPI_WARPS * 128 + 1024;
   const int grid = total < num_sms() ? total : num_sms();
-  tc_gemm_persistent_kernel<MODE><<<grid, TCP_THREADS, smem, st>>>(b, n);
+  tc_gemm_persistent_kernel<MODE, F16><<<grid, TCP_THREADS, smem, st>>>(b, n);
   return finish_launch(what);
 }
 
-template <int MODE>
+template <int MODE, bool F16 = false>
 static int launch_tc(TcBatch& b, int n, cudaStream_t st, const char* what) {
-  return launch_tc_persistent<MODE>(b, n, st, what);
+  for (int i = 0; i < n; ++i)
+    if (b.p[i].out_scale == 0.f) b.p[i].out_scale = 1.f;
+  return launch_tc_persistent<MODE, F16>(b, n, st, what);
 }
 
 // Each tc_* entry returns 0 on success, 1 on error, and -1 if a problem cannot be described to TMA
@@ -613,16 +714,16 @@ int tc_linear_backward_data(int n, const rslrl_linear_bwd_data_t* pr, cudaStream
     TcProblem& P = b.p[i];
     P.block_n = q.K >= max_block_n() ? max_block_n() : q.K;
     if (q.K % P.block_n != 0) return -1;
-    if (!make_map(&P.map_a, q.dy, q.M, q.N, q.ldy, TC_BLOCK_K, TC_BLOCK_M, false) ||
-        !make_map(&P.map_b, q.w, q.N, q.K, q.K, 32, TC_BLOCK_K, true)) {
+    if (!make_map(&P.map_a, (const float*)q.dy, q.M, q.N, q.ldy, TC_BLOCK_K, TC_BLOCK_M, false) ||
+        !make_map(&P.map_b, (const float*)q.w, q.N, q.K, q.K, 32, TC_BLOCK_K, true)) {
       set_error("%s: cuTensorMapEncodeTiled failed", what);
       return 1;
     }
-    P.C = q.dx; P.M = q.M; P.N = q.K; P.K = q.N; P.ldc = q.ldx; P.act = q.act;
+    P.C = (float*)q.dx; P.M = q.M; P.N = q.K; P.K = q.N; P.ldc = q.ldx; P.act = q.act;
     if (!tma_ok(q.dx, q.ldx)) return -1;
     if (q.act == RSLRL_ACT_IDENTITY || !tma_ok(q.h, q.ldh)) return -1;  // (no saved activation: exact fp32 kernel)
-    if (!make_map(&P.map_c, q.dx, q.M, q.K, q.ldx, 32, 32, false, false) ||
-        !make_map(&P.map_h, q.h, q.M, q.K, q.ldh, 32, TC_BLOCK_M, false, false)) {
+    if (!make_map(&P.map_c, (const float*)q.dx, q.M, q.K, q.ldx, 32, 32, false, false) ||
+        !make_map(&P.map_h, (const float*)q.h, q.M, q.K, q.ldh, 32, TC_BLOCK_M, false, false)) {
       set_error("%s: cuTensorMapEncodeTiled failed", what);
       return 1;
     }
@@ -635,7 +736,7 @@ int tc_linear_backward_data(int n, const rslrl_linear_bwd_data_t* pr, cudaStream
   const int rc = launch_tc<TC_DGRAD>(b, n, st, what);
   if (rc) return rc;
   for (int i = 0; i < n; ++i)  // optional fused-API output: bias gradient of the previous layer
-    if (pr[i].db_prev && colsum_accumulate(pr[i].dx, pr[i].M, pr[i].K, pr[i].ldx, pr[i].db_prev, st)) return 1;
+    if (pr[i].db_prev && colsum_accumulate((const float*)pr[i].dx, pr[i].M, pr[i].K, pr[i].ldx, pr[i].db_prev, st)) return 1;
   return 0;
 }
 
@@ -658,12 +759,12 @@ int tc_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* pr, cudaSt
   for (int i = 0; i < n; ++i) {
     const rslrl_linear_bwd_weight_t& q = pr[i];
     TcProblem& P = b.p[i];
-    if (!make_map(&P.map_a, q.dy, q.M, q.N, q.ldy, 32, TC_BLOCK_K, true) ||
-        !make_map(&P.map_b, q.x, q.M, q.K, q.ldx, 32, TC_BLOCK_K, true)) {
+    if (!make_map(&P.map_a, (const float*)q.dy, q.M, q.N, q.ldy, 32, TC_BLOCK_K, true) ||
+        !make_map(&P.map_b, (const float*)q.x, q.M, q.K, q.ldx, 32, TC_BLOCK_K, true)) {
       set_error("%s: cuTensorMapEncodeTiled failed", what);
       return 1;
     }
-    P.C = q.dw; P.db = q.db; P.M = q.N; P.N = q.K; P.K = q.M; P.ldc = q.K;
+    P.C = q.dw; P.db = q.db; P.M = q.N; P.N = q.K; P.K = q.M; P.ldc = q.K; P.out_scale = q.scale;
     P.tma_out = tma_ok(q.dw, q.K) && make_map(&P.map_c, q.dw, q.N, q.K, q.K, 32, 32, false, false);
     P.num_kb = (q.M + TC_BLOCK_K - 1) / TC_BLOCK_K;
     int want = (2 * kNumSMs + tiles_all - 1) / tiles_all;   // ~2 CTAs worth of work per SM
@@ -675,6 +776,72 @@ int tc_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* pr, cudaSt
     P.splits = (P.num_kb + P.kb_per_split - 1) / P.kb_per_split;
   }
   return launch_tc<TC_WGRAD>(b, n, st, what);
+}
+
+// ---- fp16-storage variants (RSLRL_PREC_FP16): same kernel, F16 = true.  -1 = shape not eligible (no fallback: the
+// caller reports it, the operands are fp16 and no other kernel reads them).
+int tc16_linear_backward_data(int n, const rslrl_linear_bwd_data_t* pr, cudaStream_t st) {
+  const char* what = "rslrl_linear_backward_data(fp16)";
+  if (n > 2) return -1;
+  TcBatch b{};
+  for (int i = 0; i < n; ++i) {
+    const rslrl_linear_bwd_data_t& q = pr[i];
+    // dX[M,K] = dY[M,N] W[N,K]: A = dY K-major (k-blocks of 64 of N), B = W16 MN-major in 64x64 boxes
+    if (!tma_ok16(q.dy, q.ldy) || !tma_ok16(q.w, q.K) || !tma_ok16(q.dx, q.ldx) || !tma_ok16(q.h, q.ldh)) return -1;
+    if ((q.K % 64) != 0 || q.act == RSLRL_ACT_IDENTITY || q.h == nullptr || q.db_prev != nullptr) return -1;
+    TcProblem& P = b.p[i];
+    P.block_n = q.K >= max_block_n() ? max_block_n() : q.K;
+    if (q.K % P.block_n != 0) return -1;
+    if (!make_map16(&P.map_a, q.dy, q.M, q.N, q.ldy, 64, TC_BLOCK_M) ||
+        !make_map16(&P.map_b, q.w, q.N, q.K, q.K, 64, 64) ||
+        !make_map16(&P.map_c, q.dx, q.M, q.K, q.ldx, 64, 32) ||
+        !make_map16(&P.map_h, q.h, q.M, q.K, q.ldh, 64, TC_BLOCK_M)) {
+      set_error("%s: cuTensorMapEncodeTiled failed", what);
+      return 1;
+    }
+    P.C = nullptr; P.M = q.M; P.N = q.K; P.K = q.N; P.ldc = q.ldx; P.act = q.act; P.tma_out = 1;
+    P.tiles_m = (q.M + TC_BLOCK_M - 1) / TC_BLOCK_M;
+    P.tiles_n = q.K / P.block_n;
+    P.num_kb = (q.N + 63) / 64;
+    P.splits = 1; P.kb_per_split = P.num_kb;
+  }
+  return launch_tc<TC_DGRAD, true>(b, n, st, what);
+}
+
+int tc16_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* pr, cudaStream_t st) {
+  const char* what = "rslrl_linear_backward_weight(fp16)";
+  if (n > 2) return -1;
+  TcBatch b{};
+  int tiles_all = 0;
+  for (int i = 0; i < n; ++i) {
+    const rslrl_linear_bwd_weight_t& q = pr[i];
+    // dW[N,K] += scale * dY[M,N]^T X[M,K]: reduction M in k-blocks of 64 rows; both operands MN-major 64x64 boxes
+    if (!tma_ok16(q.dy, q.ldy) || !tma_ok16(q.x, q.ldx) || !tma_ok(q.dw, q.K)) return -1;
+    TcProblem& P = b.p[i];
+    P.block_n = q.K >= max_block_n() ? max_block_n() : (q.K + 63) / 64 * 64;
+    P.tiles_m = (q.N + TC_BLOCK_M - 1) / TC_BLOCK_M;
+    P.tiles_n = (q.K + P.block_n - 1) / P.block_n;
+    tiles_all += P.tiles_m * P.tiles_n;
+  }
+  for (int i = 0; i < n; ++i) {
+    const rslrl_linear_bwd_weight_t& q = pr[i];
+    TcProblem& P = b.p[i];
+    if (!make_map16(&P.map_a, q.dy, q.M, q.N, q.ldy, 64, 64) || !make_map16(&P.map_b, q.x, q.M, q.K, q.ldx, 64, 64) ||
+        !make_map(&P.map_c, q.dw, q.N, q.K, q.K, 32, 32, false, false)) {
+      set_error("%s: cuTensorMapEncodeTiled failed", what);
+      return 1;
+    }
+    P.C = q.dw; P.db = q.db; P.M = q.N; P.N = q.K; P.K = q.M; P.ldc = q.K; P.out_scale = q.scale; P.tma_out = 1;
+    P.num_kb = (q.M + 63) / 64;
+    int want = (2 * kNumSMs + tiles_all - 1) / tiles_all;   // ~2 CTAs worth of work per SM
+    int max_s = P.num_kb / 4;                               // at least 4 k-blocks (256 rows) per split
+    if (max_s < 1) max_s = 1;
+    if (want > max_s) want = max_s;
+    if (want < 1) want = 1;
+    P.kb_per_split = (P.num_kb + want - 1) / want;
+    P.splits = (P.num_kb + P.kb_per_split - 1) / P.kb_per_split;
+  }
+  return launch_tc<TC_WGRAD, true>(b, n, st, what);
 }
 
 // out[n] += sum_m x[m, n]  (only used when a caller asks the tensor-core wgrad for db)

@@ -10,6 +10,8 @@ int tc_linear_forward(int n, const rslrl_linear_fwd_t* pr, cudaStream_t st);
 int head_linear_backward(int n, const rslrl_linear_bwd_head_t* pr, cudaStream_t st);
 int tc_linear_backward_data(int n, const rslrl_linear_bwd_data_t* pr, cudaStream_t st);
 int tc_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* pr, cudaStream_t st);
+int tc16_linear_backward_data(int n, const rslrl_linear_bwd_data_t* pr, cudaStream_t st);
+int tc16_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* pr, cudaStream_t st);
 }  // namespace rslrl
 
 extern "C" {
@@ -47,6 +49,15 @@ int rslrl_linear_backward_data(int n, const rslrl_linear_bwd_data_t* probs_host,
     const int rc = tc_linear_backward_data(n, probs_host, (cudaStream_t)stream);
     return rc >= 0 ? rc : simt_linear_backward_data(n, probs_host, (cudaStream_t)stream);
   }
+  if (precision == RSLRL_PREC_FP16) {
+    const int rc = tc16_linear_backward_data(n, probs_host, (cudaStream_t)stream);
+    if (rc < 0) {
+      set_error("%s(fp16): shape not eligible (needs K %% 64 == 0, an activation with saved fp16 h, 16-byte aligned "
+                "rows, at most 2 problems)", what);
+      return 4;
+    }
+    return rc;
+  }
   set_error("%s: unknown precision %d", what, precision);
   return 2;
 }
@@ -64,6 +75,14 @@ int rslrl_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* probs_h
   if (precision == RSLRL_PREC_TF32) {
     const int rc = tc_linear_backward_weight(n, probs_host, (cudaStream_t)stream);
     if (rc < 0) return simt_linear_backward_weight(n, probs_host, (cudaStream_t)stream);
+    return rc;
+  }
+  if (precision == RSLRL_PREC_FP16) {
+    const int rc = tc16_linear_backward_weight(n, probs_host, (cudaStream_t)stream);
+    if (rc < 0) {
+      set_error("%s(fp16): shape not eligible (needs 16-byte aligned rows of dy, x and dw, at most 2 problems)", what);
+      return 4;
+    }
     return rc;
   }
   set_error("%s: unknown precision %d", what, precision);

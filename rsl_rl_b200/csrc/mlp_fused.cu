@@ -23,6 +23,8 @@ namespace rslrl {
 
 bool tc_make_map(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_cols,
                  int box_rows, bool operand);
+bool tc_make_map16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_cols,
+                   int box_rows);
 int tc_num_sms();
 
 constexpr int MF_EPI_WARPS = 16;
@@ -89,8 +91,14 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// F16: the activations leave the epilogue as fp16 (granules of 128 rows x 64 columns, still 128-byte rows), layers 2-4
+// run as kind::f16 MMAs against the fp16 weight shadows and the saved activations are stored as fp16.  Layer 1 is
+// tf32 in both modes (x and W1 are fp32 in HBM).
+template <bool F16>
 __global__ void __launch_bounds__(MF_THREADS, 1) mlp3_forward_kernel(const __grid_constant__ MfBatch batch,
                                                                      const int n_nets) {
+  constexpr int GK = F16 ? 64 : 32;    // activation columns per granule = k-block of layers 2-4
+  constexpr int KB2 = 128 / GK;        // granules per 128-column chunk of layer 1
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
   uint8_t* const wring = smem_raw + pad;
@@ -132,7 +140,7 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp3_forward_kernel(const __gri
       mbar_init(&w_empty[s], 1);
     }
     for (int g = 0; g < MF_GRANULES; ++g) {
-      mbar_init(&g_full[g], 4);   // the four row-quarter warps that write a granule
+      mbar_init(&g_full[g], F16 ? 8 : 4);   // the row-quarter warps (x 2 column halves in fp16) that write a granule
       mbar_init(&g_empty[g], 2);  // MMA commit + store warp
     }
     for (int a = 0; a < 3; ++a) {
@@ -180,11 +188,11 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp3_forward_kernel(const __gri
           }
         };
         auto l2p = [&](int c) {
-          for (int kb = 0; kb < 4; ++kb) {
+          for (int kb = 0; kb < KB2; ++kb) {
             int s;
             uint8_t* dst = stage(s);
             mbar_expect_tx(&w_full[s], (uint32_t)P.N2 * 128u);
-            tma_load_2d(dst, &P.map_w2, &w_full[s], (c * 4 + kb) * TC_BLOCK_K, 0);
+            tma_load_2d(dst, &P.map_w2, &w_full[s], (c * KB2 + kb) * GK, 0);
           }
         };
         l1(0);
@@ -194,20 +202,20 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp3_forward_kernel(const __gri
         }
         // the narrow layers pack several k-blocks into one 32 KB stage (bytes in flight, not stage count, is what
         // the weight stream needs)
-        const int nkb3 = P.N2 / 32, pack3 = min(MF_W_STAGE_BYTES / (P.N3 * 128), nkb3);
+        const int nkb3 = P.N2 / GK, pack3 = min(MF_W_STAGE_BYTES / (P.N3 * 128), nkb3);
         for (int kb = 0; kb < nkb3; kb += pack3) {
           int s;
           uint8_t* dst = stage(s);
           mbar_expect_tx(&w_full[s], (uint32_t)(pack3 * P.N3) * 128u);
           for (int i = 0; i < pack3; ++i)
-            tma_load_2d(dst + (size_t)i * P.N3 * 128, &P.map_w3, &w_full[s], (kb + i) * TC_BLOCK_K, 0);
+            tma_load_2d(dst + (size_t)i * P.N3 * 128, &P.map_w3, &w_full[s], (kb + i) * GK, 0);
         }
         {
-          const int nkb4 = P.N3 / 32;
+          const int nkb4 = P.N3 / GK;
           int s;
           uint8_t* dst = stage(s);
           mbar_expect_tx(&w_full[s], (uint32_t)nkb4 * 16u * 128u);
-          for (int i = 0; i < nkb4; ++i) tma_load_2d(dst + i * 2048, &P.map_w4, &w_full[s], i * TC_BLOCK_K, 0);
+          for (int i = 0; i < nkb4; ++i) tma_load_2d(dst + i * 2048, &P.map_w4, &w_full[s], i * GK, 0);
         }
       }
     }
@@ -217,13 +225,15 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp3_forward_kernel(const __gri
     int gn = 0;          // granule counter
     uint32_t use[3] = {0, 0, 0};  // uses of TMEM buffer 0 / buffer 1 / acc2 so far
     // one k-block (32 tf32 columns) of MMAs: A at `sa`, B at `sb` (both K-major, 128-byte swizzle)
-    auto kblock = [&](uint32_t d_tmem, uint32_t sa, uint32_t sb, uint32_t idesc, bool first) {
+    // (a 128-byte k-block is 4 MMAs in both element types: 4 x 8 tf32 or 4 x 16 fp16)
+    auto kblock = [&](uint32_t d_tmem, uint32_t sa, uint32_t sb, uint32_t idesc, bool first, bool f16) {
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
           const uint64_t da = make_smem_desc(sa + k * 32, 16, 1024, kLayoutSw128);
           const uint64_t db = make_smem_desc(sb + k * 32, 16, 1024, kLayoutSw128);
-          umma_tf32(d_tmem, da, db, idesc, (first && k == 0) ? 0u : 1u);
+          if (f16) umma_f16(d_tmem, da, db, idesc, (first && k == 0) ? 0u : 1u);
+          else umma_tf32(d_tmem, da, db, idesc, (first && k == 0) ? 0u : 1u);
         }
       }
       __syncwarp();
@@ -254,8 +264,10 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp3_forward_kernel(const __gri
       ++tj;
       const MfNet& P = batch.net[t % n_nets];
       const int kb0 = (P.K0 + TC_BLOCK_K - 1) / TC_BLOCK_K, C1 = P.N1 / 128;
-      const uint32_t idesc1 = make_idesc(128, false, false), idesc2 = make_idesc(P.N2, false, false);
-      const uint32_t idesc3 = make_idesc(P.N3, false, false), idesc4 = make_idesc(16, false, false);
+      const uint32_t idesc1 = make_idesc(128, false, false);
+      const uint32_t idesc2 = F16 ? make_idesc_f16(P.N2, false, false) : make_idesc(P.N2, false, false);
+      const uint32_t idesc3 = F16 ? make_idesc_f16(P.N3, false, false) : make_idesc(P.N3, false, false);
+      const uint32_t idesc4 = F16 ? make_idesc_f16(16, false, false) : make_idesc(16, false, false);
       auto l1 = [&](int c) {
         const int a = c & 1;
         acquire_acc(a);
@@ -263,7 +275,7 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp3_forward_kernel(const __gri
           int s;
           const uint32_t base = wait_w(s);
           tcgen05_fence_after();
-          kblock(tmem_base + (uint32_t)a * 128u, base, base + 16384u, idesc1, kb == 0);
+          kblock(tmem_base + (uint32_t)a * 128u, base, base + 16384u, idesc1, kb == 0, false);
           if (elect_one()) tcgen05_commit(&w_empty[s]);
           __syncwarp();
         }
@@ -279,7 +291,7 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp3_forward_kernel(const __gri
             int g;
             const uint32_t ga = wait_g(g);
             tcgen05_fence_after();
-            kblock(tmem_base + col, ga, wb + (uint32_t)i * kb_bytes, idesc, first_overall && kb + i == 0);
+            kblock(tmem_base + col, ga, wb + (uint32_t)i * kb_bytes, idesc, first_overall && kb + i == 0, F16);
             if (elect_one()) tcgen05_commit(&g_empty[g]);
             __syncwarp();
           }
@@ -292,16 +304,16 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp3_forward_kernel(const __gri
       acquire_acc(2);
       for (int c = 0; c < C1; ++c) {
         if (c + 1 < C1) l1(c + 1);
-        from_granules(4, 256u, idesc2, c == 0, 1, 0u);
+        from_granules(KB2, 256u, idesc2, c == 0, 1, 0u);
       }
       publish_acc(2);
       MF_TRACE(lane == 0, 2 + 9 * tj + 3);
       acquire_acc(0);
-      from_granules(P.N2 / 32, 0u, idesc3, true, min(MF_W_STAGE_BYTES / (P.N3 * 128), P.N2 / 32), (uint32_t)P.N3 * 128u);
+      from_granules(P.N2 / GK, 0u, idesc3, true, min(MF_W_STAGE_BYTES / (P.N3 * 128), P.N2 / GK), (uint32_t)P.N3 * 128u);
       publish_acc(0);
       MF_TRACE(lane == 0, 2 + 9 * tj + 5);
       acquire_acc(1);
-      from_granules(P.N3 / 32, 128u, idesc4, true, P.N3 / 32, 2048u);
+      from_granules(P.N3 / GK, 128u, idesc4, true, P.N3 / GK, 2048u);
       publish_acc(1);
       MF_TRACE(lane == 0, 2 + 9 * tj + 7);
     }
@@ -311,14 +323,14 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp3_forward_kernel(const __gri
     for (int t = blockIdx.x; t < total; t += gridDim.x) {
       const MfNet& P = batch.net[t % n_nets];
       const int m0 = (t / n_nets) * TC_BLOCK_M;
-      const int n1 = P.N1 / 32, n2 = P.N2 / 32, n3 = P.N3 / 32;
+      const int n1 = P.N1 / GK, n2 = P.N2 / GK, n3 = P.N3 / GK;
       for (int i = 0; i < n1 + n2 + n3; ++i, ++gn) {
         const int g = gn % MF_GRANULES;
         mbar_wait(&g_full[g], (gn / MF_GRANULES) & 1);
         if (lane == 0) {
           if (P.store_h) {
             const CUtensorMap* map = i < n1 ? &P.map_h1 : (i < n1 + n2 ? &P.map_h2 : &P.map_h3);
-            const int col = (i < n1 ? i : (i < n1 + n2 ? i - n1 : i - n1 - n2)) * 32;
+            const int col = (i < n1 ? i : (i < n1 + n2 ? i - n1 : i - n1 - n2)) * GK;
             tma_store_2d(map, gring + (size_t)g * MF_GRANULE_BYTES, col, m0);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -348,7 +360,8 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp3_forward_kernel(const __gri
       const int act = P.act;
 
       // one unit: TMEM columns [col, col+32) of this warp's 32 rows -> bias + activation -> granule `gidx`
-      auto unit = [&](uint32_t col, const float* bias, int gidx, int acc, bool last_read) {
+      // (fp16: two units share a granule; `hsel` picks the 64-byte half of the 128-byte rows)
+      auto unit = [&](uint32_t col, const float* bias, int gidx, int hsel, int acc, bool last_read) {
         uint32_t v[32];
         TMEM_LD_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + col, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -360,7 +373,32 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp3_forward_kernel(const __gri
         const int g = gidx % MF_GRANULES;
         mbar_wait(&g_empty[g], ((gidx / MF_GRANULES) & 1) ^ 1);
         uint8_t* const my_row = gring + (size_t)g * MF_GRANULE_BYTES + q * 4096 + lane * 128;
-        if (act == RSLRL_ACT_ELU) {
+        if constexpr (F16) {
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            float z[16];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float4 b4 = *(const float4*)(bias + 16 * hh + 4 * u);
+              z[4 * u + 0] = __uint_as_float(v[16 * hh + 4 * u + 0]) + b4.x;
+              z[4 * u + 1] = __uint_as_float(v[16 * hh + 4 * u + 1]) + b4.y;
+              z[4 * u + 2] = __uint_as_float(v[16 * hh + 4 * u + 2]) + b4.z;
+              z[4 * u + 3] = __uint_as_float(v[16 * hh + 4 * u + 3]) + b4.w;
+            }
+            if (act == RSLRL_ACT_ELU) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) z[i] = elu_max_form(z[i]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) z[i] = act_forward(act, z[i]);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u)  // 16-byte chunk = 8 fp16 columns
+              *(uint4*)(my_row + (((uint32_t)(4 * hsel + 2 * hh + u) ^ sw) << 4)) =
+                  make_uint4(pack_f16x2(z[8 * u], z[8 * u + 1]), pack_f16x2(z[8 * u + 2], z[8 * u + 3]),
+                             pack_f16x2(z[8 * u + 4], z[8 * u + 5]), pack_f16x2(z[8 * u + 6], z[8 * u + 7]));
+          }
+        } else if (act == RSLRL_ACT_ELU) {
           // branch-free fast path, two halves of 16 columns: 16 independent chains per lane (ILP hides the MUFU and
           // shared-memory latencies; only four epilogue warps share a scheduler)
 #pragma unroll
@@ -411,8 +449,8 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp3_forward_kernel(const __gri
       for (int c = 0; c < C1; ++c) {
         const int a = c & 1;
         wait_acc(a);
-        unit((uint32_t)a * 128u + 32u * j, bias_net + c * 128 + 32 * j, gbase + j, a, true);
-        gbase += 4;
+        unit((uint32_t)a * 128u + 32u * j, bias_net + c * 128 + 32 * j, gbase + (F16 ? j >> 1 : j), j & 1, a, true);
+        gbase += KB2;
         MF_TRACE(ew == 0 && lane == 0 && c == 0, 2 + 9 * tj + 1);
         MF_TRACE(ew == 0 && lane == 0 && c == C1 - 1, 2 + 9 * tj + 2);
       }
@@ -422,8 +460,8 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp3_forward_kernel(const __gri
         wait_acc(2);
         if (j >= ncb) release_only(2);
         for (int cb = j; cb < ncb; cb += 4)
-          unit(256u + 32u * cb, bias_net + 512 + 32 * cb, gbase + cb, 2, cb + 4 >= ncb);
-        gbase += ncb;
+          unit(256u + 32u * cb, bias_net + 512 + 32 * cb, gbase + (F16 ? cb >> 1 : cb), cb & 1, 2, cb + 4 >= ncb);
+        gbase += F16 ? ncb / 2 : ncb;
         MF_TRACE(ew == 0 && lane == 0, 2 + 9 * tj + 4);
       }
       // L3: acc3 in buffer 0
@@ -431,8 +469,8 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp3_forward_kernel(const __gri
         const int ncb = P.N3 / 32;
         wait_acc(0);
         if (j >= ncb) release_only(0);
-        else unit(32u * j, bias_net + 768 + 32 * j, gbase + j, 0, true);
-        gbase += ncb;
+        else unit(32u * j, bias_net + 768 + 32 * j, gbase + (F16 ? j >> 1 : j), j & 1, 0, true);
+        gbase += F16 ? ncb / 2 : ncb;
         MF_TRACE(ew == 0 && lane == 0, 2 + 9 * tj + 6);
       }
       // L4: acc4 in buffer 1 (16 columns): the four j == 0 warps write the N4 outputs
@@ -473,6 +511,7 @@ static bool ok16(const void* p, long long ld) { return ((uintptr_t)p & 15) == 0 
 int mlp3_forward_fused(int n, const rslrl_mlp3_fwd_t* nets, cudaStream_t st) {
   const char* what = "rslrl_mlp3_forward";
   if (n < 1 || n > 2) return -1;
+  const bool f16 = nets[0].precision == RSLRL_PREC_FP16;
   MfBatch b{};
   for (int i = 0; i < n; ++i) {
     const rslrl_mlp3_fwd_t& q = nets[i];
@@ -480,21 +519,38 @@ int mlp3_forward_fused(int n, const rslrl_mlp3_fwd_t* nets, cudaStream_t st) {
     if (q.N1 % 128 || q.N1 < 128 || q.N1 > 512 || q.N2 % 128 || q.N2 < 128 || q.N2 > 256 || q.N3 % 32 || q.N3 < 32 ||
         q.N3 > 128 || q.N4 < 1 || q.N4 > 16 || q.K0 < 1)
       return -1;
-    if (!ok16(q.x, q.ldx) || !ok16(q.w[0], q.ldw0) || !ok16(q.w[1], q.N1) || !ok16(q.w[2], q.N2) || !ok16(q.w[3], q.N3))
-      return -1;
+    if (!ok16(q.x, q.ldx) || !ok16(q.w[0], q.ldw0)) return -1;
+    if (!f16 && (!ok16(q.w[1], q.N1) || !ok16(q.w[2], q.N2) || !ok16(q.w[3], q.N3))) return -1;
     const bool store = q.h[0] != nullptr;
-    if (store && (!q.h[1] || !q.h[2] || !ok16(q.h[0], q.ldh[0]) || !ok16(q.h[1], q.ldh[1]) || !ok16(q.h[2], q.ldh[2])))
-      return -1;
+    if (store && (!q.h[1] || !q.h[2])) return -1;
+    if ((q.precision == RSLRL_PREC_FP16) != f16) return -1;
     MfNet& P = b.net[i];
     bool ok = tc_make_map(&P.map_x, q.x, q.M, q.K0, q.ldx, 32, 128, true) &&
-              tc_make_map(&P.map_w1, q.w[0], q.N1, q.K0, q.ldw0, 32, 128, true) &&
-              tc_make_map(&P.map_w2, q.w[1], q.N2, q.N1, q.N1, 32, q.N2, true) &&
-              tc_make_map(&P.map_w3, q.w[2], q.N3, q.N2, q.N2, 32, q.N3, true) &&
-              tc_make_map(&P.map_w4, q.w[3], q.N4, q.N3, q.N3, 32, 16, true);
-    if (ok && store)
-      ok = tc_make_map(&P.map_h1, q.h[0], q.M, q.N1, q.ldh[0], 32, 128, false) &&
-           tc_make_map(&P.map_h2, q.h[1], q.M, q.N2, q.ldh[1], 32, 128, false) &&
-           tc_make_map(&P.map_h3, q.h[2], q.M, q.N3, q.ldh[2], 32, 128, false);
+              tc_make_map(&P.map_w1, (const float*)q.w[0], q.N1, q.K0, q.ldw0, 32, 128, true);
+    if (f16) {
+      // fp16 rows: 16-byte alignment = pitch % 8; N3 must fill whole 64-column granules
+      if (q.N3 % 64 || q.N1 % 8 || q.N2 % 8 || ((uintptr_t)q.w[1] & 15) || ((uintptr_t)q.w[2] & 15) || ((uintptr_t)q.w[3] & 15))
+        return -1;
+      if (store)
+        for (int l = 0; l < 3; ++l)
+          if (((uintptr_t)q.h[l] & 15) || q.ldh[l] % 8) return -1;
+      ok = ok && tc_make_map16(&P.map_w2, q.w[1], q.N2, q.N1, q.N1, 64, q.N2) &&
+           tc_make_map16(&P.map_w3, q.w[2], q.N3, q.N2, q.N2, 64, q.N3) &&
+           tc_make_map16(&P.map_w4, q.w[3], q.N4, q.N3, q.N3, 64, 16);
+      if (ok && store)
+        ok = tc_make_map16(&P.map_h1, q.h[0], q.M, q.N1, q.ldh[0], 64, 128) &&
+             tc_make_map16(&P.map_h2, q.h[1], q.M, q.N2, q.ldh[1], 64, 128) &&
+             tc_make_map16(&P.map_h3, q.h[2], q.M, q.N3, q.ldh[2], 64, 128);
+    } else {
+      if (store && (!ok16(q.h[0], q.ldh[0]) || !ok16(q.h[1], q.ldh[1]) || !ok16(q.h[2], q.ldh[2]))) return -1;
+      ok = ok && tc_make_map(&P.map_w2, (const float*)q.w[1], q.N2, q.N1, q.N1, 32, q.N2, true) &&
+           tc_make_map(&P.map_w3, (const float*)q.w[2], q.N3, q.N2, q.N2, 32, q.N3, true) &&
+           tc_make_map(&P.map_w4, (const float*)q.w[3], q.N4, q.N3, q.N3, 32, 16, true);
+      if (ok && store)
+        ok = tc_make_map(&P.map_h1, (const float*)q.h[0], q.M, q.N1, q.ldh[0], 32, 128, false) &&
+             tc_make_map(&P.map_h2, (const float*)q.h[1], q.M, q.N2, q.ldh[1], 32, 128, false) &&
+             tc_make_map(&P.map_h3, (const float*)q.h[2], q.M, q.N3, q.ldh[2], 32, 128, false);
+    }
     if (!ok) {
       set_error("%s: cuTensorMapEncodeTiled failed", what);
       return 1;
@@ -503,20 +559,22 @@ int mlp3_forward_fused(int n, const rslrl_mlp3_fwd_t* nets, cudaStream_t st) {
     P.y = q.y; P.M = q.M; P.K0 = q.K0; P.N1 = q.N1; P.N2 = q.N2; P.N3 = q.N3; P.N4 = q.N4; P.ldy = q.ldy;
     P.act = q.act; P.store_h = store ? 1 : 0;
   }
-  static bool attr_set = false;
+  static bool attr_set[2] = {false, false};
   const size_t smem = MF_W_STAGES * MF_W_STAGE_BYTES + MF_GRANULES * MF_GRANULE_BYTES + 2 * MF_MAX_BIAS * 4 +
                       (2 * MF_W_STAGES + 2 * MF_GRANULES + 6) * 8 + 16 + 1024;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(mlp3_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (!attr_set[f16]) {
+    cudaError_t e = f16 ? cudaFuncSetAttribute(mlp3_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                        : cudaFuncSetAttribute(mlp3_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
       return 1;
     }
-    attr_set = true;
+    attr_set[f16] = true;
   }
   const int total = (nets[0].M + TC_BLOCK_M - 1) / TC_BLOCK_M * n;
   const int grid = total < tc_num_sms() ? total : tc_num_sms();
-  mlp3_forward_kernel<<<grid, MF_THREADS, smem, st>>>(b, n);
+  if (f16) mlp3_forward_kernel<true><<<grid, MF_THREADS, smem, st>>>(b, n);
+  else mlp3_forward_kernel<false><<<grid, MF_THREADS, smem, st>>>(b, n);
   return finish_launch(what);
 }
 
@@ -534,8 +592,8 @@ extern "C" int rslrl_mlp3_forward(int n, const rslrl_mlp3_fwd_t* nets_host, rslr
   }
   const int rc = mlp3_forward_fused(n, nets_host, (cudaStream_t)stream);
   if (rc < 0) {
-    set_error("%s: shape not eligible (needs N1 in {128..512} %% 128, N2 in {128,256}, N3 <= 128 %% 32, N4 <= 16, "
-              "16-byte aligned rows, equal M)", what);
+    set_error("%s: shape not eligible (needs N1 in {128..512} %% 128, N2 in {128,256}, N3 <= 128 %% 32 (%% 64 in fp16), "
+              "N4 <= 16, 16-byte aligned rows, equal M and precision)", what);
     return 4;
   }
   return rc;

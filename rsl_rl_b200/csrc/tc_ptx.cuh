@@ -64,6 +64,16 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// fp16 x fp16 -> f32 (kind::f16): same shared-memory byte geometry as tf32 (128-byte rows), K = 16 per instruction
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
@@ -99,6 +109,30 @@ __device__ __forceinline__ uint32_t make_idesc(int n, bool a_mn_major, bool b_mn
   d |= (uint32_t)(n >> 3) << 17;
   d |= (uint32_t)(TC_BLOCK_M >> 4) << 24;
   return d;
+}
+
+// UMMA instruction descriptor: f16 x f16 -> f32, M = 128 (A/B format code 0 = F16)
+__device__ __forceinline__ uint32_t make_idesc_f16(int n, bool a_mn_major, bool b_mn_major) {
+  uint32_t d = 0;
+  d |= 1u << 4;                      // accumulator format F32
+  d |= (a_mn_major ? 1u : 0u) << 15;
+  d |= (b_mn_major ? 1u : 0u) << 16;
+  d |= (uint32_t)(n >> 3) << 17;
+  d |= (uint32_t)(TC_BLOCK_M >> 4) << 24;
+  return d;
+}
+// two fp32 -> packed fp16x2 (round to nearest even, saturating to +-65504 instead of inf); `lo` lands in the low half
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t v) {
+  float2 r;
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}"
+      : "=f"(r.x), "=f"(r.y)
+      : "r"(v));
+  return r;
 }
 
 #define TMEM_LD_32x32(taddr, v)                                                                                      \

@@ -104,7 +104,8 @@ class GaussianHeadMixin:
     def set_gemm_precision(self, precision: str):
         for m in self.modules():
             if isinstance(m, MLP):
-                m.precision = precision
+                # (the autograd path of an MLP has no fp16-storage variant: tensor cores there mean tf32)
+                m.precision = "tf32" if precision == "fp16" else precision
 
 
 class ActorCritic(GaussianHeadMixin, nn.Module):

@@ -47,9 +47,11 @@ def mlp3_eligible(dims: Sequence[int], acts: Sequence[int]) -> bool:
             and 1 <= n4 <= 16 and acts[0] == acts[1] == acts[2] and acts[3] == 0)
 
 
-def mlp3_struct(x_ptr: int, ldx: int, M: int, weights, biases, hs, y, act: int) -> "nat.Mlp3Fwd":
+def mlp3_struct(x_ptr: int, ldx: int, M: int, weights, biases, hs, y, act: int,
+                precision: int = nat.PREC_TF32) -> "nat.Mlp3Fwd":
     """weights: 4 tensors [N_l, K_l] (weights[0] may be the zero-padded first-layer shadow); hs: 3 activation
-    buffers [>=M, N_l] or None (nothing but y is stored)."""
+    buffers [>=M, N_l] or None (nothing but y is stored).  precision = PREC_FP16: weights[1:] are the fp16 shadows
+    and hs are fp16 buffers."""
     p = nat.Mlp3Fwd()
     p.x = x_ptr
     for l in range(4):
@@ -62,6 +64,7 @@ def mlp3_struct(x_ptr: int, ldx: int, M: int, weights, biases, hs, y, act: int) 
     p.M, p.K0 = M, weights[0].shape[1]
     p.N1, p.N2, p.N3, p.N4 = (w.shape[0] for w in weights)
     p.ldx, p.ldw0, p.ldy, p.act = ldx, weights[0].stride(0), y.stride(0), act
+    p.precision = precision
     return p
 
 
@@ -84,11 +87,13 @@ def linear_backward_data(problems: Sequence[Tuple], precision: int):
 
 
 def linear_backward_weight(problems: Sequence[Tuple], precision: int):
-    """problems: (dy[M,N], x[M,K], dw[N,K] (accumulated), db[N]|None (accumulated))."""
+    """problems: (dy[M,N], x[M,K], dw[N,K] (accumulated), db[N]|None (accumulated)[, scale])."""
     arr = (nat.LinearBwdWeight * len(problems))()
-    for i, (dy, x, dw, db) in enumerate(problems):
+    for i, prob in enumerate(problems):
+        dy, x, dw, db = prob[:4]
         arr[i] = nat.LinearBwdWeight(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), nat.ptr(db), dy.shape[0],
-                                     dw.shape[0], dw.shape[1], dy.stride(0), x.stride(0))
+                                     dw.shape[0], dw.shape[1], dy.stride(0), x.stride(0),
+                                     prob[4] if len(prob) > 4 else 1.0)
     nat.check(nat.lib().rslrl_linear_backward_weight(len(problems), arr, precision, nat.stream_ptr()))
 
 
@@ -96,18 +101,24 @@ HEAD_MAX_N = 12
 
 
 def head_backward_ok(N: int, K: int, *tensors) -> bool:
-    return N <= HEAD_MAX_N and K % 4 == 0 and all(t is None or (t.data_ptr() % 16 == 0 and t.stride(0) % 4 == 0)
+    return N <= HEAD_MAX_N and K % 4 == 0 and all(t is None or (t.data_ptr() % (8 if t.dtype == torch.float16 else 16) == 0 and t.stride(0) % 4 == 0)
                                                   for t in tensors)
 
 
 def linear_backward_head(problems: Sequence[Tuple]):
     """Fused dgrad + wgrad + bias gradient of a narrow layer.
-    problems: (dy[M,N], weight[N,K], h[M,K], dx[M,K]|None, dw[N,K], db[N]|None, act_code_of_previous_layer)."""
+    problems: (dy[M,N], weight[N,K], h[M,K], dx[M,K]|None, dw[N,K], db[N]|None, act_code_of_previous_layer[, dx_scale]).
+    h / dx may be fp16 tensors (the fp16-storage path); dx is then written as dx_scale * gradient."""
     arr = (nat.LinearBwdHead * len(problems))()
-    for i, (dy, w, h, dx, dw, db, act) in enumerate(problems):
+    for i, prob in enumerate(problems):
+        dy, w, h, dx, dw, db, act = prob[:7]
+        f16 = h.dtype == torch.float16
+        if dx is not None and (dx.dtype == torch.float16) != f16:
+            raise TypeError("linear_backward_head: h and dx must have the same dtype")
         arr[i] = nat.LinearBwdHead(dy.data_ptr(), w.data_ptr(), h.data_ptr(), nat.ptr(dx), dw.data_ptr(), nat.ptr(db),
                                    dy.shape[0], w.shape[0], w.shape[1], dy.stride(0), h.stride(0),
-                                   0 if dx is None else dx.stride(0), act)
+                                   0 if dx is None else dx.stride(0), act, int(f16),
+                                   prob[7] if len(prob) > 7 else 1.0)
     nat.check(nat.lib().rslrl_linear_backward_head(len(problems), arr, nat.stream_ptr()))
 
 

@@ -195,15 +195,17 @@ def test_c1_shape_full_iteration_vs_oracle():
     assert rel_err(r["mine"], r["ref"]) < 1e-4
 
 
-def test_tf32_tensor_core_iteration_vs_oracle():
-    """gemm_precision='tf32' (tcgen05) at the C1 shape: policy outputs and losses within the 1e-3 class.
+@pytest.mark.parametrize("prec", ["tf32", "fp16"])
+def test_tf32_tensor_core_iteration_vs_oracle(prec):
+    """gemm_precision='tf32' / 'fp16' (tcgen05) at the C1 shape: policy outputs and losses within the 1e-3 class.
     Post-update parameters are compared in relative L2 norm of the UPDATE (theta_new - theta_old): Adam's
     sign-like normalisation makes a max-norm comparison of 20 accumulated steps meaningless at tf32 noise."""
     meta, obs, rewards, dones, time_outs, z, perms = _synthetic_problem(4096, 24, 48, 12, [512, 256, 128], 1, seed=9)
     r = _run_both(meta, obs, rewards, dones, time_outs, z, perms, 1, capture_grads=True, use_cuda_graph=False,
-                  gemm_precision="tf32")[0]
+                  gemm_precision=prec)[0]
     st, alg = r["st"], r["alg"]
     s = alg.storage
+    assert alg._engine.f16 == (prec == "fp16")
     assert rel_err(s.mu.cpu().numpy(), st["mu"]) < 1e-3
     assert rel_err(s.values.cpu().numpy(), st["values"]) < 1e-3
     assert rel_err(s.actions_log_prob.cpu().numpy(), st["actions_log_prob"]) < 1e-3
@@ -214,7 +216,7 @@ def test_tf32_tensor_core_iteration_vs_oracle():
     assert np.linalg.norm(g0 - g0_ref) / np.linalg.norm(g0_ref) < 2e-3
     init = np.concatenate([v.reshape(-1) for v in _init_params_like_torch(meta, 0).values()]).astype(np.float64)
     upd, upd_ref = r["mine"].astype(np.float64) - init, r["ref"].astype(np.float64) - init
-    print("tf32 update rel L2 err", np.linalg.norm(upd - upd_ref) / np.linalg.norm(upd_ref),
+    print(prec, "update rel L2 err", np.linalg.norm(upd - upd_ref) / np.linalg.norm(upd_ref),
           "max-norm param err", rel_err(r["mine"], r["ref"]), "lr", r["lr_mine"], r["lr_ref"])
     # The KL-adaptive rule is a threshold decision per minibatch: tf32 rounding (and the summation order of the
     # split-K reductions) may legitimately flip one of the 20 decisions when a KL lands within ~1e-3 of a
@@ -250,6 +252,26 @@ def test_tf32_unaligned_observation_width_vs_oracle():
     assert float(alg._engine.w0_pad["a"][:, w.shape[1]:].abs().max()) == 0.0
     ratio = res[-1]["lr_mine"] / res[-1]["lr_ref"]
     assert min(abs(ratio - 1.5 ** k) for k in range(-6, 7)) < 1e-6
+    if abs(ratio - 1.0) < 1e-9:
+        u, ur = res[-1]["mine"].astype(np.float64) - init, res[-1]["ref"].astype(np.float64) - init
+        assert np.linalg.norm(u - ur) / np.linalg.norm(ur) < 0.15
+
+
+def test_fp16_three_iterations_with_cuda_graphs_shadow_follows_parameters():
+    """gemm_precision='fp16' with the rollout / update CUDA graphs active over three iterations: the fp16 weight
+    shadow must equal fp16(parameters) after every update and the LR trajectory may differ from the oracle's only by
+    threshold flips of the KL rule."""
+    meta, obs, rewards, dones, time_outs, z, perms = _synthetic_problem(1024, 8, 48, 12, [128, 128, 64], 3, seed=21)
+    res = _run_both(meta, obs, rewards, dones, time_outs, z, perms, 3, use_cuda_graph=True, gemm_precision="fp16")
+    alg = res[-1]["alg"]
+    assert alg._engine.f16 and alg._graph is not None
+    alg._engine.refresh_padded()
+    grp = alg._group
+    assert torch.equal(grp.values16, grp.values.half())
+    s, st = alg.storage, res[-1]["st"]
+    ratio = res[-1]["lr_mine"] / res[-1]["lr_ref"]
+    assert min(abs(ratio - 1.5 ** k) for k in range(-6, 7)) < 1e-6
+    init = np.concatenate([v.reshape(-1) for v in _init_params_like_torch(meta, 0).values()]).astype(np.float64)
     if abs(ratio - 1.0) < 1e-9:
         u, ur = res[-1]["mine"].astype(np.float64) - init, res[-1]["ref"].astype(np.float64) - init
         assert np.linalg.norm(u - ur) / np.linalg.norm(ur) < 0.15
