@@ -124,7 +124,10 @@ def time_dominant_kernel(alg, reps: int = 2):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             eng.forward(xa[r], xc[r], eng.mu[:mb], eng.value[:mb])
-            eng.backward(xa[r], xc[r], eng.dmu[:mb], eng.dvalue[:mb])
+            if eng.f16:  # the backward reads the fp16 copies of the minibatch observations
+                eng.backward(alg._xa16[r, :alg._Oa], alg._xc16[r, :alg._Oc], eng.dmu[:mb], eng.dvalue[:mb])
+            else:
+                eng.backward(xa[r], xc[r], eng.dmu[:mb], eng.dvalue[:mb])
             e1.record()
             e1.synchronize()
             total_ms += e0.elapsed_time(e1)
@@ -333,7 +336,7 @@ def run_ours(args):
         roofline = dict(bound="tensor", achieved=dom["tflops"], peak=peaks["tf_sustained"], unit="TFLOP/s",
                         frac=dom["tflops"] / peaks["tf_sustained"], traffic=None,
                         kernel=("sgemm_kernel (fp32 CUDA-core FMA)" if args.precision == "fp32"
-                                else "mlp3_forward_kernel + tc_gemm_persistent_kernel<dgrad|wgrad> (tf32 tcgen05): "
+                                else f"mlp3_forward_kernel + tc_gemm_persistent_kernel<dgrad|wgrad> ({args.precision} tcgen05): "
                                      "all dense launches of one minibatch forward + backward"),
                         avg_launch_us=dom["avg_launch_us"], flops_per_launch=dom["flops_per_launch"],
                         peak_source=peaks["source"] + ", bf16 dense sustained")
@@ -348,7 +351,7 @@ def run_ours(args):
                        sample=f"1 full C2 iteration ({NUM_ENVS} envs x {NUM_STEPS} steps, 5x4 minibatches) of "
                               f"oracle/torch_cpu_port.py in {dt:.1f} s on {os.cpu_count()} host cpus")
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms / K,
-                    higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32" if args.precision == "fp32" else "tf32",
+                    higher_is_better=True, scaling="weak", vs_baseline=None, dtype={"fp32": "f32", "tf32": "tf32", "fp16": "fp16 operands, fp32 accumulate"}[args.precision],
                     data="synthetic",
                     config=dict(workload=WORKLOAD, envs_per_gpu=NUM_ENVS, global_envs=NUM_ENVS * world,
                                 parallelism=f"dp{world}", gemm_precision=args.precision,
@@ -386,7 +389,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("RSLRL_PRECISION", "tf32"), choices=["fp32", "tf32"])
+    ap.add_argument("--precision", default=os.environ.get("RSLRL_PRECISION", "tf32"), choices=["fp32", "tf32", "fp16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--only-timed", action="store_true", help="profiling aid: warm-up + timed region only")
     args = ap.parse_args()

@@ -314,29 +314,26 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
           uint8_t* const blk = staging + (size_t)hs * 16384 + q * 4096;
           uint8_t* const my_row = blk + lane * 128;
           mbar_wait(&h_full[hs], (uint32_t)(g / TCP_H_CHUNKS) & 1u);
+          // branch-free inner loop per activation (the act code is uniform: hoisted out of the 64-element loop)
+          auto scale_chunk = [&](auto grad) {
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            uint4* const hp = (uint4*)(my_row + ((u ^ sw) << 4));
-            const uint4 h = *hp;
-            const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
-            uint32_t ow[4];
+            for (int u = 0; u < 8; ++u) {
+              uint4* const hp = (uint4*)(my_row + ((u ^ sw) << 4));
+              const uint4 h = *hp;
+              const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+              uint32_t ow[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 hf = unpack_f16x2(hw[e]);
-              const float xa = __uint_as_float(u < 4 ? v0[8 * u + 2 * e] : v1[8 * (u - 4) + 2 * e]);
-              const float xb = __uint_as_float(u < 4 ? v0[8 * u + 2 * e + 1] : v1[8 * (u - 4) + 2 * e + 1]);
-              float ga, gb;
-              if (P.act == RSLRL_ACT_ELU) {
-                ga = fminf(hf.x, 0.f) + 1.f;
-                gb = fminf(hf.y, 0.f) + 1.f;
-              } else {
-                ga = act_grad_from_output(P.act, hf.x);
-                gb = act_grad_from_output(P.act, hf.y);
+              for (int e = 0; e < 4; ++e) {
+                const float2 hf = unpack_f16x2(hw[e]);
+                const float xa = __uint_as_float(u < 4 ? v0[(8 * u + 2 * e) & 31] : v1[(8 * u + 2 * e) & 31]);
+                const float xb = __uint_as_float(u < 4 ? v0[(8 * u + 2 * e + 1) & 31] : v1[(8 * u + 2 * e + 1) & 31]);
+                ow[e] = pack_f16x2(xa * grad(hf.x), xb * grad(hf.y));
               }
-              ow[e] = pack_f16x2(xa * ga, xb * gb);
+              *hp = make_uint4(ow[0], ow[1], ow[2], ow[3]);
             }
-            *hp = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-          }
+          };
+          if (P.act == RSLRL_ACT_ELU) scale_chunk([](float hv) { return fminf(hv, 0.f) + 1.f; });
+          else scale_chunk([act = P.act](float hv) { return act_grad_from_output(act, hv); });
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) {
@@ -378,24 +375,22 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
           uint8_t* const blk = staging + (size_t)hs * 16384 + q * 4096;
           uint8_t* const my_row = blk + lane * 128;
           mbar_wait(&h_full[hs], (uint32_t)(g / TCP_H_CHUNKS) & 1u);
+          auto scale_chunk = [&](auto grad) {  // act code is uniform: one branch per chunk, none per element
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            float4* const hp = (float4*)(my_row + ((u ^ sw) << 4));
-            const float4 h = *hp;
-            float4 o;
-            if (P.act == RSLRL_ACT_ELU) {  // ELU'(z) from the output: 1 for h > 0, h + 1 otherwise = min(h,0) + 1
-              o.x = x[4 * u + 0] * (fminf(h.x, 0.f) + 1.f);
-              o.y = x[4 * u + 1] * (fminf(h.y, 0.f) + 1.f);
-              o.z = x[4 * u + 2] * (fminf(h.z, 0.f) + 1.f);
-              o.w = x[4 * u + 3] * (fminf(h.w, 0.f) + 1.f);
-            } else {
-              o.x = x[4 * u + 0] * act_grad_from_output(P.act, h.x);
-              o.y = x[4 * u + 1] * act_grad_from_output(P.act, h.y);
-              o.z = x[4 * u + 2] * act_grad_from_output(P.act, h.z);
-              o.w = x[4 * u + 3] * act_grad_from_output(P.act, h.w);
+            for (int u = 0; u < 8; ++u) {
+              float4* const hp = (float4*)(my_row + ((u ^ sw) << 4));
+              const float4 h = *hp;
+              float4 o;
+              o.x = x[4 * u + 0] * grad(h.x);
+              o.y = x[4 * u + 1] * grad(h.y);
+              o.z = x[4 * u + 2] * grad(h.z);
+              o.w = x[4 * u + 3] * grad(h.w);
+              *hp = o;  // in place: the buffer becomes the staging tile of the bulk store
             }
-            *hp = o;  // in place: the buffer becomes the staging tile of the bulk store
-          }
+          };
+          // ELU'(z) from the output: 1 for h > 0, h + 1 otherwise = min(h,0) + 1
+          if (P.act == RSLRL_ACT_ELU) scale_chunk([](float hv) { return fminf(hv, 0.f) + 1.f; });
+          else scale_chunk([act = P.act](float hv) { return act_grad_from_output(act, hv); });
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) {
