@@ -24,7 +24,7 @@ extern "C" {
 
 #define RSLRL_ABI_VERSION 1
 #define RSLRL_MAX_SEGMENTS 16 /* max obs groups / gather fields per launch */
-#define RSLRL_MAX_PROBLEMS 4  /* max GEMM problems grouped into one launch */
+#define RSLRL_MAX_PROBLEMS 6  /* max GEMM problems grouped into one launch (fp16 wgrad: 3 layers x actor, critic) */
 
 typedef void* rslrl_stream_t;
 
@@ -256,14 +256,15 @@ int rslrl_adam_step(float* p, float* g, float* m, float* v, int64_t P, const rsl
  * (fixed rank order: bit-identical on every rank), derives ||mean g||, the clip scale and the KL-adaptive learning
  * rate exactly like rslrl_grad_norm_lr, applies Adam like rslrl_adam_step and clears the local gradients once the
  * peers have read them.  Must be launched by every rank the same number of times (flags are epoch stamped); the
- * grid (<= 148 blocks) has to be co-resident.  workspace: rslrl_allreduce_adam_workspace_bytes(), zero-initialised. */
+ * grid (<= 148 blocks) has to be co-resident.  workspace: rslrl_allreduce_adam_workspace_bytes(), zero-initialised.
+ * p16_shadow (may be NULL): fp16 copy of p, same element offsets, rewritten by the Adam phase (RSLRL_PREC_FP16). */
 int64_t rslrl_allreduce_adam_workspace_bytes(void);
 int64_t rslrl_allreduce_adam_flag_bytes(void);
 int rslrl_allreduce_clip_adam(int world, int rank, const float* const* peer_grads_host,
                               unsigned int* const* peer_flags_host, float* p, float* m, float* v, int64_t P,
                               rslrl_opt_state_t* state, void* workspace, double max_grad_norm, int adaptive,
                               double desired_kl, int round_lr_fp32, int use_kl, double beta1, double beta2, double eps,
-                              int zero_grad, rslrl_stream_t stream);
+                              int zero_grad, void* p16_shadow, rslrl_stream_t stream);
 
 /* ---- recurrent minibatches (rsl_rl/utils/utils.py:78-141; storage/rollout_storage.py:206-260) ---- */
 

@@ -13,6 +13,7 @@ ELU = nat.ACT_CODES["elu"]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 handle = ctypes.CDLL(nat.library_path())
 h16 = lambda *s: torch.randn(*s, device=dev).half()
+merged = []
 for l in range(3):
     probs = []
     for dims in (dims_a, dims_c):
@@ -20,9 +21,13 @@ for l in range(3):
         x = h16(M, K); w = (torch.randn(N, K, device=dev) / K ** 0.5).half()
         dy = h16(M, N); dx = torch.empty(M, K, device=dev, dtype=torch.float16); dw = torch.zeros(N, K, device=dev)
         db = torch.zeros(N, device=dev)
-        probs.append({"d": (dy, w, x, dx, ELU), "w": (dy, x, dw, db, 1.0)}[kind])
+        probs.append({"d": (dy, w, x, dx, ELU), "w": (dy, x, dw, db, 1.0), "m": (dy, x, dw, db, 1.0)}[kind])
     if kind == "d" and l == 0: continue
-    fn = {"d": linear_backward_data, "w": linear_backward_weight}[kind]
+    if kind == "m":
+        merged += [(dy, x, dw, db, 1.0) for (dy, x, dw, db, _) in [(p[0], p[1], p[2], p[3], 0) for p in probs]]
+        if l < 2: continue
+        probs = sorted(merged, key=lambda p: -(p[2].shape[0] * p[2].shape[1]))
+    fn = {"d": linear_backward_data, "w": linear_backward_weight, "m": linear_backward_weight}[kind]
     for _ in range(3): fn(probs, prec)
     flush.fill_(0); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -36,7 +41,7 @@ for l in range(3):
     t0 = t[:, 0].min()
     rel = lambda a: (a - t0) / 1e3
     print(f"--- fp16 {kind} layer {l}: event time {e0.elapsed_time(e1)*1e3:.1f} us; CTA start spread {rel(t[:,0]).max():.2f} us, end min/max {rel(t[:,31]).min():.2f}/{rel(t[:,31]).max():.2f} us")
-    for cta in (0, 73, 147):
+    for cta in (0, 1, 73, 146, 147):
         r = t[cta]
         ev = [f"start {rel(r[0]):.2f}", f"prologue {rel(r[1]):.2f}", f"tma0 {rel(r[2]):.2f}", f"full0 {rel(r[3]):.2f}"]
         for j in range(13):

@@ -22,7 +22,7 @@ ACT_CODES = {"identity": 0, "elu": 1, "relu": 2, "tanh": 3, "sigmoid": 4, "lrelu
 PREC_FP32, PREC_TF32, PREC_FP16 = 0, 1, 2
 PREC_CODES = {"fp32": PREC_FP32, "tf32": PREC_TF32, "fp16": PREC_FP16}
 STD_SCALAR, STD_LOG = 0, 1
-MAX_SEGMENTS, MAX_PROBLEMS = 16, 4
+MAX_SEGMENTS, MAX_PROBLEMS = 16, 6
 
 
 class LinearFwd(C.Structure):
@@ -93,7 +93,7 @@ _SIGNATURES = {
     "rslrl_allreduce_adam_flag_bytes": (c_i64, []),
     "rslrl_allreduce_clip_adam": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64,
                                           c_void_p, c_void_p, c_double, c_int, c_double, c_int, c_int, c_double,
-                                          c_double, c_double, c_int, c_void_p]),
+                                          c_double, c_double, c_int, c_void_p, c_void_p]),
     "rslrl_traj_workspace_bytes": (c_i64, [c_int, c_int]),
     "rslrl_trajectory_index": (c_int, [c_void_p, c_int, c_int] + [c_void_p] * 8),
     "rslrl_trajectory_masks": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

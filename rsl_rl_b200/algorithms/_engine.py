@@ -90,8 +90,12 @@ class FeedForwardEngine:
         self.h_a = [torch.empty(R, d, **adt) for d in self.actor.dims[1:-1]]
         self.h_c = [torch.empty(R, d, **adt) for d in self.critic.dims[1:-1]]
         wa, wc = max(self.actor.dims[1:-1] + [1]), max(self.critic.dims[1:-1] + [1])
-        self.g_a = [torch.empty(R * wa, **adt) for _ in range(2)]
-        self.g_c = [torch.empty(R * wc, **adt) for _ in range(2)]
+        if self.f16:   # one gradient buffer per hidden layer: the weight gradients of all layers run as ONE launch at the end
+            self.g_a = [torch.empty(R * d, **adt) for d in self.actor.dims[1:-1]]
+            self.g_c = [torch.empty(R * d, **adt) for d in self.critic.dims[1:-1]]
+        else:
+            self.g_a = [torch.empty(R * wa, **adt) for _ in range(2)]
+            self.g_c = [torch.empty(R * wc, **adt) for _ in range(2)]
         self.mu = torch.empty(R, self.A, **f32)
         self.value = torch.empty(R, 1, **f32)
         # gradient heads keep a 16-byte row pitch so that TMA can read them (dvalue: 1 used column of 4)
@@ -126,10 +130,11 @@ class FeedForwardEngine:
                 return f"{name} output width {net.dims[-1]} > 12 (the output layer's backward is the narrow-head kernel)"
         return None
 
-    def refresh_padded(self):
-        """Derived copies of the parameters: zero-padded first-layer weights, fp16 weight shadow."""
+    def refresh_padded(self, after_step: bool = False):
+        """Derived copies of the parameters: zero-padded first-layer weights, fp16 weight shadow.
+        after_step: called right after an optimiser step (which may have refreshed the shadow itself)."""
         if self.f16:
-            self.group.refresh_shadow16()
+            self.group.refresh_shadow16(force=not after_step)
         with torch.no_grad():
             for tag, buf in self.w0_pad.items():
                 net = self.actor if tag == "a" else self.critic
@@ -281,33 +286,32 @@ class FeedForwardEngine:
             dy = new_dy
 
     def _backward16(self, x_a: torch.Tensor, x_c: torch.Tensor, dmu: torch.Tensor, dvalue: torch.Tensor):
-        """fp16-storage backward: narrow-head kernel (fp32 math, writes S * dZ3 as fp16), then per layer one grouped
-        wgrad launch (dW += dZ^T H / S, bias gradient from the same tiles) and one grouped dgrad launch."""
+        """fp16-storage backward: narrow-head kernel (fp32 math, writes S * dZ3 as fp16), one grouped dgrad launch per
+        hidden layer down the chain (every dZ_l stays in its own buffer), then ONE wgrad launch for all layers of both
+        nets (dW += dZ^T H / S, bias gradients from the same tiles; k-splits balanced across the problems)."""
         M = x_a.shape[0]
         S, prec = self.grad_scale, nat.PREC_FP16
         nets = ((self.actor, self.h_a, self.g_a, x_a, dmu), (self.critic, self.h_c, self.g_c, x_c, dvalue))
-        hprobs, dy = [], []
+        dz = lambda net, gbuf, l: gbuf[l - 1][:M * net.dims[l]].view(M, net.dims[l])   # gradient at the output of layer l-1
+        hprobs, wprobs = [], []
         for net, hs, gbuf, _, d_out in nets:
             lin, l = net.layers[-1], net.L - 1
-            dx = gbuf[0][:M * net.dims[l]].view(M, net.dims[l])
-            hprobs.append((d_out, lin.weight, hs[l - 1][:M], dx, lin.weight.grad, lin.bias.grad, net.acts[l - 1], S))
-            dy.append(dx)
+            hprobs.append((d_out, lin.weight, hs[l - 1][:M], dz(net, gbuf, l), lin.weight.grad, lin.bias.grad,
+                           net.acts[l - 1], S))
         linear_backward_head(hprobs)
-        for k in range(1, self.actor.L):
-            wprobs, dprobs, new_dy = [], [], list(dy)
-            for ni, (net, hs, gbuf, x_in, _) in enumerate(nets):
-                l = net.L - 1 - k
+        for l in range(self.actor.L - 2, -1, -1):
+            dprobs = []
+            for net, hs, gbuf, x_in, _ in nets:
                 lin = net.layers[l]
                 inp = x_in if l == 0 else hs[l - 1][:M]
-                wprobs.append((dy[ni], inp, lin.weight.grad, lin.bias.grad, 1.0 / S))
+                dy = dz(net, gbuf, l + 1)
+                wprobs.append((dy, inp, lin.weight.grad, lin.bias.grad, 1.0 / S))
                 if l > 0:
-                    dx = gbuf[k % 2][:M * net.dims[l]].view(M, net.dims[l])
-                    dprobs.append((dy[ni], self.group.shadow16(lin.weight), inp, dx, net.acts[l - 1]))
-                    new_dy[ni] = dx
-            linear_backward_weight(wprobs, prec)
+                    dprobs.append((dy, self.group.shadow16(lin.weight), inp, dz(net, gbuf, l), net.acts[l - 1]))
             if dprobs:
                 linear_backward_data(dprobs, prec)
-            dy = new_dy
+        wprobs.sort(key=lambda p: -(p[2].shape[0] * p[2].shape[1]))   # heaviest tiles first in the round-robin schedule
+        linear_backward_weight(wprobs, prec)
 
     def gaussian_head(self, mu, z, actions_out, logp_out, sigma_out):
         nat.check(nat.lib().rslrl_gaussian_act(mu.data_ptr(), self.std_param.data_ptr(), self.std_type, z.data_ptr(),

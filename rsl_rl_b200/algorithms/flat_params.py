@@ -46,6 +46,7 @@ class FlatParamGroup:
         self.exp_avg = torch.zeros(off, **f32)
         self.exp_avg_sq = torch.zeros(off, **f32)
         self.values16 = None  # fp16 shadow of `values` (same element offsets), see enable_shadow16()
+        self.shadow16_stale = True
         self.bind()
 
     def _view(self, flat: torch.Tensor, i: int) -> torch.Tensor:
@@ -72,9 +73,11 @@ class FlatParamGroup:
             self.values16 = torch.zeros(self.numel, dtype=torch.float16, device=self.device)
         self.refresh_shadow16()
 
-    def refresh_shadow16(self):
-        """values16 = fp16(values): one launch over the flat buffer (after every optimiser step / parameter load)."""
-        if self.values16 is not None:
+    def refresh_shadow16(self, force: bool = True):
+        """values16 = fp16(values): one launch over the flat buffer.  The one-launch optimiser step keeps the shadow
+        current by itself (force=False then skips the launch); parameter loads / broadcasts need force=True."""
+        if self.values16 is not None and (force or self.shadow16_stale):
+            self.shadow16_stale = False
             nat.check(nat.lib().rslrl_convert_f32_f16(self.values.data_ptr(), self.numel, self.values16.data_ptr(),
                                                       self.numel, 1, self.numel, self.numel, nat.stream_ptr()))
 
@@ -224,7 +227,8 @@ class FusedAdam(torch.optim.Adam):
                 self.peer_world, self.peer_rank, peers, self._peer_flags, g.values.data_ptr(), g.exp_avg.data_ptr(),
                 g.exp_avg_sq.data_ptr(), g.numel, self.dev_state.ptr(), self._ar_ws.data_ptr(), float(max_grad_norm),
                 int(adaptive), float(desired_kl or 0.0), int(round_lr_fp32), int(use_kl), beta1, beta2, pg["eps"],
-                int(zero_grad), nat.stream_ptr()))
+                int(zero_grad), nat.ptr(g.values16), nat.stream_ptr()))
+            g.shadow16_stale = False   # the Adam phase rewrote the fp16 shadow
             self._host_step += 1
             return
         nat.check(L.rslrl_grad_norm_lr(g.grads.data_ptr(), g.numel, g.kl_slot.data_ptr() if use_kl else None,
@@ -234,6 +238,7 @@ class FusedAdam(torch.optim.Adam):
         nat.check(L.rslrl_adam_step(g.values.data_ptr(), g.grads.data_ptr(), g.exp_avg.data_ptr(),
                                     g.exp_avg_sq.data_ptr(), g.numel, self.dev_state.ptr(), beta1, beta2, pg["eps"],
                                     int(zero_grad), nat.stream_ptr()))
+        g.shadow16_stale = True
         self._host_step += 1
 
     def sync_host_state(self, lr: float):

@@ -408,7 +408,7 @@ class PPO:
                     torch.distributed.all_reduce(self._group.grads_ext, op=torch.distributed.ReduceOp.SUM)
                 opt.fused_step(world_size=self.gpu_world_size, max_grad_norm=self.max_grad_norm, adaptive=adaptive,
                                desired_kl=self.desired_kl or 0.0, round_lr_fp32=self.is_multi_gpu)
-                eng.refresh_padded()
+                eng.refresh_padded(after_step=True)
 
     def _update_fused(self):
         st, eng, opt = self.storage, self._engine, self.optimizer

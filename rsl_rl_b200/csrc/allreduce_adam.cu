@@ -15,6 +15,8 @@
 //   4  wait for the peers' "done reading" flags of block b, then clear slice b of the local gradient buffer
 // With world == 1 the flag phases vanish and the kernel is clip + KL-LR + Adam in one launch instead of two.
 // All scalars stay on the device (rslrl_opt_state_t); the kernel is CUDA-graph capturable (epoch in device memory).
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace rslrl {
@@ -34,6 +36,7 @@ struct ArParams {
   const float* peer_grads[kArMaxWorld];  // gradient buffer [P + 4] of every rank (own rank included)
   unsigned int* peer_flags[kArMaxWorld]; // flag buffer [2][kArMaxBlocks][kArMaxWorld] of every rank
   float* p;
+  __half* p16;  // optional fp16 shadow of p (same element offsets), refreshed by the Adam phase
   float* g;  // own gradient buffer (= peer_grads[rank])
   float* m;
   float* v;
@@ -210,6 +213,13 @@ __global__ void __launch_bounds__(kArThreads, 1) allreduce_clip_adam_kernel(cons
       ((float4*)prm.p)[i] = pp;
       ((float4*)prm.m)[i] = mm;
       ((float4*)prm.v)[i] = vv;
+      if (prm.p16 != nullptr) {
+        const __half2 lo = __floats2half2_rn(pp.x, pp.y), hi = __floats2half2_rn(pp.z, pp.w);
+        uint2 o;
+        o.x = *(const unsigned int*)&lo;
+        o.y = *(const unsigned int*)&hi;
+        ((uint2*)prm.p16)[i] = o;
+      }
     }
   }
 
@@ -236,9 +246,10 @@ int rslrl_allreduce_clip_adam(int world, int rank, const float* const* peer_grad
                               unsigned int* const* peer_flags_host, float* p, float* m, float* v, int64_t P,
                               rslrl_opt_state_t* state, void* workspace, double max_grad_norm, int adaptive,
                               double desired_kl, int round_lr_fp32, int use_kl, double beta1, double beta2, double eps,
-                              int zero_grad, rslrl_stream_t stream) {
+                              int zero_grad, void* p16_shadow, rslrl_stream_t stream) {
   using namespace rslrl;
   const char* what = "rslrl_allreduce_clip_adam";
+  RSLRL_CHECK_ARG(((uintptr_t)p16_shadow & 7) == 0, what);
   RSLRL_CHECK_ARG(world >= 1 && world <= kArMaxWorld && rank >= 0 && rank < world, what);
   RSLRL_CHECK_ARG(peer_grads_host && p && m && v && state && workspace && P > 0 && (P % 4) == 0, what);
   RSLRL_CHECK_ARG(world == 1 || peer_flags_host, what);
@@ -252,7 +263,7 @@ int rslrl_allreduce_clip_adam(int world, int rank, const float* const* peer_grad
     }
   }
   RSLRL_CHECK_ARG((((uintptr_t)p | (uintptr_t)m | (uintptr_t)v) & 15) == 0, what);
-  prm.p = p; prm.g = const_cast<float*>(peer_grads_host[rank]); prm.m = m; prm.v = v; prm.P = P;
+  prm.p = p; prm.p16 = (__half*)p16_shadow; prm.g = const_cast<float*>(peer_grads_host[rank]); prm.m = m; prm.v = v; prm.P = P;
   prm.state = state; prm.ws = (ArWorkspace*)workspace;
   prm.world = world; prm.rank = rank; prm.adaptive = adaptive; prm.round_lr_fp32 = round_lr_fp32;
   prm.use_kl = use_kl; prm.zero_grad = zero_grad;

@@ -334,6 +334,19 @@ __device__ __forceinline__ float4 headb_load4(const void* base, size_t elem) {
     return __ldg((const float4*)((const float*)base + elem));
   }
 }
+// raw (unconverted) form: what the software pipeline keeps in registers while the load is in flight
+template <bool F16> struct HeadbRaw { using type = float4; };
+template <> struct HeadbRaw<true> { using type = uint2; };
+template <bool F16>
+__device__ __forceinline__ typename HeadbRaw<F16>::type headb_load_raw(const void* base, size_t elem) {
+  if constexpr (F16) return __ldg((const uint2*)((const __half*)base + elem));
+  else return __ldg((const float4*)((const float*)base + elem));
+}
+__device__ __forceinline__ float4 headb_cvt(float4 r) { return r; }
+__device__ __forceinline__ float4 headb_cvt(uint2 r) {
+  const float2 a = __half22float2(*(const __half2*)&r.x), b = __half22float2(*(const __half2*)&r.y);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
 template <bool F16>
 __device__ __forceinline__ void headb_store4(void* base, size_t elem, float4 o) {
   if constexpr (F16) {
@@ -370,17 +383,30 @@ __global__ void __launch_bounds__(HEADB_WARPS * 32, 2) head_backward_kernel(cons
     for (int a = 0; a < HEADB_MAX_N; ++a) dw[a][0] = dw[a][1] = dw[a][2] = dw[a][3] = 0.f;
     float db_acc = 0.f;
     __syncthreads();
+    // software pipeline: the loads of the next HEADB_ROWS rows are in flight while the current ones are consumed
+    float dyn[HEADB_ROWS];
+    typename HeadbRaw<F16>::type hvn[HEADB_ROWS];
+    auto fetch = [&](int row) {
+#pragma unroll
+      for (int j = 0; j < HEADB_ROWS; ++j) {
+        const int r = row + j * nwarps;
+        const bool ok = r < P.M;
+        dyn[j] = (ok && lane < N) ? __ldg(P.dy + (size_t)r * P.ldy + lane) : 0.f;
+        if (ok && col_ok) hvn[j] = headb_load_raw<F16>(P.h, (size_t)r * P.ldh + col);
+        else hvn[j] = typename HeadbRaw<F16>::type{};
+      }
+    };
+    fetch(gwarp);
     for (int row = gwarp; row < P.M; row += HEADB_ROWS * nwarps) {
       float dyl[HEADB_ROWS];
       float4 hv[HEADB_ROWS], dx[HEADB_ROWS];
 #pragma unroll
       for (int j = 0; j < HEADB_ROWS; ++j) {
-        const int r = row + j * nwarps;
-        const bool ok = r < P.M;
-        dyl[j] = (ok && lane < N) ? __ldg(P.dy + (size_t)r * P.ldy + lane) : 0.f;
-        hv[j] = (ok && col_ok) ? headb_load4<F16>(P.h, (size_t)r * P.ldh + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+        dyl[j] = dyn[j];
+        hv[j] = headb_cvt(hvn[j]);
         dx[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
+      if (row + HEADB_ROWS * nwarps < P.M) fetch(row + HEADB_ROWS * nwarps);
 #pragma unroll
       for (int j = 0; j < HEADB_ROWS; ++j) db_acc += dyl[j];
 #pragma unroll

@@ -50,8 +50,10 @@ struct TcProblem {
   int block_n, tiles_m, tiles_n, splits, kb_per_split, num_kb;
 };
 
+constexpr int TC_MAX_PROBLEMS = 6;  // 6 x 640 B of kernel parameters (< 4 KB)
+
 struct alignas(64) TcBatch {
-  TcProblem p[2];
+  TcProblem p[TC_MAX_PROBLEMS];
 };
 
 // ------------------------------------------------------------------------------- persistent kernel
@@ -72,6 +74,15 @@ constexpr int TCP_STAGING = TCP_EPI_WARPS * 2 * 4096;  // fwd / wgrad: two 32x32
 constexpr int TCP_H_CHUNKS = 8;                        // dgrad: ring of H chunk buffers, 16 KB each
 constexpr int TCP_H_BYTES = TCP_H_CHUNKS * 16384;
 constexpr int TCP_RING_BUDGET_DGRAD = 96 * 1024;
+// The fp16 wgrad streams every operand byte exactly once per tile row/column and is bound by the bytes it keeps in
+// flight: one staging slot per epilogue warp (32 KB) leaves 192 KB = four 48 KB stages to the operand ring.
+constexpr int tcp_staging_slots(int mode, bool f16) { return (mode == 2 && f16) ? 1 : 2; }
+constexpr int tcp_staging_bytes(int mode, bool f16) {
+  return mode == 1 ? TCP_H_BYTES : TCP_EPI_WARPS * tcp_staging_slots(mode, f16) * 4096;
+}
+constexpr int tcp_ring_budget(int mode, bool f16) {
+  return mode == 1 ? TCP_RING_BUDGET_DGRAD : ((mode == 2 && f16) ? 192 * 1024 : TCP_RING_BUDGET);
+}
 constexpr int TCP_MAX_BLOCK_N = 256;
 
 struct TcpScalars {  // per-problem scalars mirrored into shared memory once per CTA
@@ -122,18 +133,18 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
   for (int i = 0; i < n_problems; ++i) max_bn = max(max_bn, batch.p[i].block_n);
   const uint32_t a_bytes = TC_BLOCK_M * TC_BLOCK_K * 4;
   const uint32_t stage_bytes = a_bytes + (uint32_t)max_bn * TC_BLOCK_K * 4;
-  int stages = (MODE == TC_DGRAD ? TCP_RING_BUDGET_DGRAD : TCP_RING_BUDGET) / stage_bytes;
+  int stages = tcp_ring_budget(MODE, F16) / stage_bytes;
   stages = stages > TCP_MAX_STAGES ? TCP_MAX_STAGES : stages;
   uint8_t* const staging = ring + (size_t)stages * stage_bytes;  // 1024-byte aligned (stage_bytes is a multiple of 2048)
-  uint64_t* const full_bar = (uint64_t*)(staging + (MODE == TC_DGRAD ? TCP_H_BYTES : TCP_STAGING));
+  uint64_t* const full_bar = (uint64_t*)(staging + tcp_staging_bytes(MODE, F16));
   uint64_t* const empty_bar = full_bar + TCP_MAX_STAGES;
   uint64_t* const tmem_full = empty_bar + TCP_MAX_STAGES;   // [2]
   uint64_t* const tmem_empty = tmem_full + 2;               // [2]
   uint64_t* const h_full = tmem_empty + 2;                  // [TCP_H_CHUNKS]  (dgrad)
   uint64_t* const h_empty = h_full + TCP_H_CHUNKS;          // [TCP_H_CHUNKS]
   uint32_t* const tmem_ptr_smem = (uint32_t*)(h_empty + TCP_H_CHUNKS);
-  TcpScalars* const sp = (TcpScalars*)(tmem_ptr_smem + 4);  // [2]
-  float* const bias_stage = (float*)(sp + 2);               // [TCP_EPI_WARPS][32], 16-byte aligned
+  TcpScalars* const sp = (TcpScalars*)(tmem_ptr_smem + 4);  // [TC_MAX_PROBLEMS]
+  float* const bias_stage = (float*)(sp + TC_MAX_PROBLEMS);               // [TCP_EPI_WARPS][32], 16-byte aligned
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) TRACE(0);
@@ -273,7 +284,8 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
     const int ew = warp - 2;
     const int q = warp & 3;      // TMEM sub-partition
     const int half = ew >> 2;    // chunk parity handled by this warp
-    uint8_t* const slot_base = staging + (size_t)ew * 8192;   // fwd / wgrad staging slots of this warp
+    constexpr int SLOTS = tcp_staging_slots(MODE, F16);
+    uint8_t* const slot_base = staging + (size_t)ew * SLOTS * 4096;   // fwd / wgrad staging slots of this warp
     const uint32_t sw = (uint32_t)(lane & 7);
     int j = 0;
     uint32_t n_issued = 0;       // chunks processed by this warp so far (selects the staging slot)
@@ -405,7 +417,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
           continue;
         }
 
-        const uint32_t slot = n_issued & 1;
+        const uint32_t slot = SLOTS == 2 ? (n_issued & 1) : 0;
         uint8_t* const slot_ptr = slot_base + slot * 4096;
         uint8_t* const my_row = slot_ptr + lane * 128;
         if (MODE == TC_FWD) {
@@ -438,8 +450,10 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
           for (int i = 0; i < 32; ++i) x[i] *= P.out_scale;
         }
         if (P.tma_out) {
-          if (lane == 0)  // the slot's previous store (two chunks ago) must have been read
-            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          if (lane == 0) {  // the slot's previous store (SLOTS chunks ago) must have been read
+            if (SLOTS == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          }
           __syncwarp();
 #pragma unroll
           for (int u = 0; u < 8; ++u)
@@ -510,22 +524,50 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
       const int kb1 = min(sp[pi].num_kb, kb0 + sp[pi].kb_per_split);
       float* const db_ptr = sp[pi].db;
       const bool active = db_ptr != nullptr && tn == 0;
+      if constexpr (F16) {
+        // thread <-> (16-byte chunk c = 8 features, row group g): 8 x LDS.128 per k-block instead of 64 two-byte loads;
+        // rows g, g + 8, ... share (row & 7) = g, so the swizzled chunk offset is a per-thread constant
+        const int c = f & 15, g = f >> 4;
+        const uint32_t base = (uint32_t)(c >> 3) * 8192u + (uint32_t)g * 128u + ((uint32_t)((c & 7) ^ g) << 4);
+        float acc8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % stages;
+          mbar_wait(&full_bar[s], (it / stages) & 1);
+          if (active) {
+            const uint8_t* sa = ring + (size_t)s * stage_bytes + base;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint4 v = *(const uint4*)(sa + i * 1024);
+              const float2 p0 = unpack_f16x2(v.x), p1 = unpack_f16x2(v.y), p2 = unpack_f16x2(v.z), p3 = unpack_f16x2(v.w);
+              acc8[0] += p0.x; acc8[1] += p0.y; acc8[2] += p1.x; acc8[3] += p1.y;
+              acc8[4] += p2.x; acc8[5] += p2.y; acc8[6] += p3.x; acc8[7] += p3.y;
+            }
+          }
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty_bar[s])) : "memory");
+        }
+        if (active) {  // the two row groups of a warp share a chunk: fold them, then one atomic per feature per warp
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc8[e] += __shfl_xor_sync(0xffffffffu, acc8[e], 16);
+          if (lane < 16) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int feat = tm * TC_BLOCK_M + c * 8 + e;
+              if (feat < sp[pi].M) atomicAdd(db_ptr + feat, acc8[e] * sp[pi].out_scale);
+            }
+          }
+        }
+        continue;
+      }
       float acc = 0.f;
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int s = it % stages;
         mbar_wait(&full_bar[s], (it / stages) & 1);
         if (active) {
           const uint8_t* sa = ring + (size_t)s * stage_bytes;
-          if constexpr (F16) {  // 64-feature boxes of 64 rows x 128 bytes, 16-byte chunks XORed with (row & 7)
-            const uint32_t fo = (uint32_t)(f >> 6) * 8192u + (uint32_t)(f & 7) * 2u, fc = (uint32_t)((f & 63) >> 3);
-#pragma unroll 16
-            for (int r = 0; r < 64; ++r)
-              acc += __half2float(*(const __half*)(sa + fo + (uint32_t)r * 128u + ((fc ^ (uint32_t)(r & 7)) << 4)));
-          } else {
 #pragma unroll
-            for (int r = 0; r < TC_BLOCK_K; ++r)
-              acc += *(const float*)(sa + foff + (uint32_t)r * 128u + ((fchunk ^ (uint32_t)(r & 3)) << 5));
-          }
+          for (int r = 0; r < TC_BLOCK_K; ++r)
+            acc += *(const float*)(sa + foff + (uint32_t)r * 128u + ((fchunk ^ (uint32_t)(r & 3)) << 5));
         }
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty_bar[s])) : "memory");
@@ -655,10 +697,10 @@ static int launch_tc_persistent(TcBatch& b, int n, cudaStream_t st, const char* 
   }
   if (total == 0) return 0;
   const size_t stage = (size_t)(TC_BLOCK_M + max_bn) * TC_BLOCK_K * 4;
-  size_t stages = (MODE == TC_DGRAD ? TCP_RING_BUDGET_DGRAD : TCP_RING_BUDGET) / stage;
+  size_t stages = tcp_ring_budget(MODE, F16) / stage;
   if (stages > TCP_MAX_STAGES) stages = TCP_MAX_STAGES;
-  const size_t smem = stages * stage + (MODE == TC_DGRAD ? TCP_H_BYTES : TCP_STAGING) +
-                      (2 * TCP_MAX_STAGES + 4 + 2 * TCP_H_CHUNKS) * 8 + 16 + 2 * sizeof(TcpScalars) +
+  const size_t smem = stages * stage + tcp_staging_bytes(MODE, F16) +
+                      (2 * TCP_MAX_STAGES + 4 + 2 * TCP_H_CHUNKS) * 8 + 16 + TC_MAX_PROBLEMS * sizeof(TcpScalars) +
                       TCP_EPI_WARPS * 128 + 1024;
   const int grid = total < num_sms() ? total : num_sms();
   tc_gemm_persistent_kernel<MODE, F16><<<grid, TCP_THREADS, smem, st>>>(b, n);
@@ -803,11 +845,20 @@ int tc16_linear_backward_data(int n, const rslrl_linear_bwd_data_t* pr, cudaStre
   return launch_tc<TC_DGRAD, true>(b, n, st, what);
 }
 
+// Relative cost of one k-block of a wgrad tile: proportional to the bytes it streams (128 + block_n rows of 128 B)
+// when the ring is full-width, but never below the latency floor of a ring stage (measured with the in-kernel
+// timeline: 0.82 us for a 48 KB k-block, 0.72 us for a 24 KB one -> floor at 0.88 of the full-width cost).
+static double wgrad16_kb_cost(int block_n) {
+  const double bytes = TC_BLOCK_M + block_n, floor_ = 0.88 * (TC_BLOCK_M + TCP_MAX_BLOCK_N);
+  return bytes > floor_ ? bytes : floor_;
+}
+
 int tc16_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* pr, cudaStream_t st) {
   const char* what = "rslrl_linear_backward_weight(fp16)";
-  if (n > 2) return -1;
+  if (n > TC_MAX_PROBLEMS) return -1;
   TcBatch b{};
   int tiles_all = 0;
+  double cost_all = 0.0;  // smem bytes streamed by all tiles of all problems (the mainloops are L2->SM bound)
   for (int i = 0; i < n; ++i) {
     const rslrl_linear_bwd_weight_t& q = pr[i];
     // dW[N,K] += scale * dY[M,N]^T X[M,K]: reduction M in k-blocks of 64 rows; both operands MN-major 64x64 boxes
@@ -817,6 +868,7 @@ int tc16_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* pr, cuda
     P.tiles_m = (q.N + TC_BLOCK_M - 1) / TC_BLOCK_M;
     P.tiles_n = (q.K + P.block_n - 1) / P.block_n;
     tiles_all += P.tiles_m * P.tiles_n;
+    cost_all += (double)P.tiles_m * P.tiles_n * ((q.M + 63) / 64) * wgrad16_kb_cost(P.block_n);
   }
   for (int i = 0; i < n; ++i) {
     const rslrl_linear_bwd_weight_t& q = pr[i];
@@ -828,13 +880,25 @@ int tc16_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* pr, cuda
     }
     P.C = q.dw; P.db = q.db; P.M = q.N; P.N = q.K; P.K = q.M; P.ldc = q.K; P.out_scale = q.scale; P.tma_out = 1;
     P.num_kb = (q.M + 63) / 64;
-    int want = (2 * kNumSMs + tiles_all - 1) / tiles_all;   // ~2 CTAs worth of work per SM
-    int max_s = P.num_kb / 4;                               // at least 4 k-blocks (256 rows) per split
-    if (max_s < 1) max_s = 1;
-    if (want > max_s) want = max_s;
-    if (want < 1) want = 1;
-    P.kb_per_split = (P.num_kb + want - 1) / want;
-    P.splits = (P.num_kb + P.kb_per_split - 1) / P.kb_per_split;
+  }
+  // k-splits: every work item (tile x k-range) of every grouped problem streams about the same number of bytes, and
+  // there are at most items_per_sm * #SMs of them (one more would add a whole extra round to the static round-robin
+  // schedule): grow the per-item byte budget until the item count fits
+  static const int items_per_sm = [] { const char* e = getenv("RSLRL_WGRAD_ITEMS_PER_SM"); return e ? atoi(e) : 2; }();
+  const int budget = items_per_sm * num_sms();
+  double unit = cost_all / budget;
+  for (int iter = 0; iter < 64; ++iter, unit *= 1.03) {
+    int total = 0;
+    for (int i = 0; i < n; ++i) {
+      TcProblem& P = b.p[i];
+      int kps = (int)(unit / wgrad16_kb_cost(P.block_n) + 0.999);
+      if (kps < 4) kps = 4;                                 // at least 4 k-blocks (256 rows) per split
+      if (kps > P.num_kb) kps = P.num_kb;
+      P.kb_per_split = kps;
+      P.splits = (P.num_kb + kps - 1) / kps;
+      total += P.tiles_m * P.tiles_n * P.splits;
+    }
+    if (total <= budget) break;
   }
   return launch_tc<TC_WGRAD, true>(b, n, st, what);
 }
