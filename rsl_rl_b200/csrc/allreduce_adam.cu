@@ -96,6 +96,8 @@ __global__ void __launch_bounds__(kArThreads, 1) allreduce_clip_adam_kernel(cons
   __shared__ double s_red[32];
   __shared__ double s_scal[4];  // clip_scale, step_size, bc2_sqrt
 
+  pdl_trigger();
+  pdl_wait();
   const int W = prm.world, rank = prm.rank, b = blockIdx.x, G = gridDim.x, tid = threadIdx.x;
   ArWorkspace* const ws = prm.ws;
   const unsigned int epoch = *((volatile unsigned int*)&ws->epoch);
@@ -300,7 +302,7 @@ int rslrl_allreduce_clip_adam(int world, int rank, const float* const* peer_grad
     }
     smem_set = smem;
   }
-  allreduce_clip_adam_kernel<<<(int)grid, kArThreads, smem, (cudaStream_t)stream>>>(prm);
+  launch_chain_kernel(allreduce_clip_adam_kernel, dim3((int)grid), dim3(kArThreads), smem, (cudaStream_t)stream, prm);
   return finish_launch(what);
 }
 

@@ -25,6 +25,33 @@ inline int finish_launch(const char* what) {
   return 0;
 }
 
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------------------------
+// The update() chain is ~7 back-to-back launches per minibatch, each 10-60 us long, so launch latency and prologues
+// (barrier init, TMEM allocation, descriptor prefetch) are a visible share.  Kernels of the chain call pdl_trigger()
+// first thing (the NEXT kernel's CTAs may then be scheduled as soon as SM resources free up) and pdl_wait() before
+// their first access to global memory (returns once the PREVIOUS kernel has completed and flushed).  Every kernel
+// launched with the attribute executes pdl_wait(), so completion stays transitive along the stream.
+// Opt-in (RSLRL_PDL=1); by default everything is launched with plain stream order.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                       Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 #define RSLRL_CHECK_ARG(cond, what)                      \
   do {                                                   \
     if (!(cond)) {                                       \

@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include <cuda_fp16.h>
 
@@ -13,6 +14,8 @@ namespace rslrl {
 __global__ void __launch_bounds__(256) convert_f32_f16_kernel(const float* __restrict__ src, long long ld_src,
                                                              __half* __restrict__ dst, long long ld_dst, long long rows,
                                                              int cols, int cols_pad, int vec) {
+  pdl_trigger();
+  pdl_wait();
   const int per_row = vec ? cols_pad / 4 : cols_pad;
   const long long total = rows * per_row;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
@@ -44,6 +47,13 @@ void set_error(const char* fmt, ...) {
 }
 
 void count_launch(unsigned long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+  // default OFF: measured on B200 (profiles/experiments/notes/r1_pdl.md) the programmatic edges made the graph-replayed
+  // iteration slower (6.08 vs 5.63 ms); the hooks stay for further experiments (RSLRL_PDL=1)
+  static const bool on = [] { const char* e = getenv("RSLRL_PDL"); return e && e[0] == '1'; }();
+  return on;
+}
 
 }  // namespace rslrl
 
@@ -77,8 +87,9 @@ int rslrl_convert_f32_f16(const float* src, int64_t ld_src, void* dst, int64_t l
   const long long total = rows * (long long)(vec ? cols_pad / 4 : cols_pad);
   long long blocks = (total + 255) / 256;
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-  convert_f32_f16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(src, ld_src, (__half*)dst, ld_dst, rows, cols,
-                                                                       cols_pad, vec);
+  cudaError_t e = launch_chain_kernel(convert_f32_f16_kernel, dim3((int)blocks), dim3(256), 0, (cudaStream_t)stream, src,
+                                      (long long)ld_src, (__half*)dst, (long long)ld_dst, (long long)rows, cols, cols_pad, vec);
+  (void)e;
   return finish_launch(what);
 }
 

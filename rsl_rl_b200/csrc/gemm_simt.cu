@@ -361,6 +361,8 @@ __device__ __forceinline__ void headb_store4(void* base, size_t elem, float4 o) 
 
 template <bool F16>
 __global__ void __launch_bounds__(HEADB_WARPS * 32, 2) head_backward_kernel(const HeadBwdBatch batch) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float s_dw[HEADB_MAX_N][128];
   __shared__ __align__(16) float s_w[HEADB_MAX_N][128];
   __shared__ float s_db[HEADB_MAX_N];
@@ -475,8 +477,8 @@ int head_linear_backward(int n, const rslrl_linear_bwd_head_t* pr, cudaStream_t 
   }
   // one block per SM per problem: the weight-gradient partials end in global atomics (N x K per block), so fewer,
   // longer-running blocks keep the per-address contention at 148
-  if (pr[0].f16) head_backward_kernel<true><<<dim3(kNumSMs, n), HEADB_WARPS * 32, 0, st>>>(b);
-  else head_backward_kernel<false><<<dim3(kNumSMs, n), HEADB_WARPS * 32, 0, st>>>(b);
+  if (pr[0].f16) launch_chain_kernel(head_backward_kernel<true>, dim3(kNumSMs, n), dim3(HEADB_WARPS * 32), 0, st, b);
+  else launch_chain_kernel(head_backward_kernel<false>, dim3(kNumSMs, n), dim3(HEADB_WARPS * 32), 0, st, b);
   return finish_launch("rslrl_linear_backward_head");
 }
 

@@ -74,14 +74,14 @@ constexpr int TCP_STAGING = TCP_EPI_WARPS * 2 * 4096;  // fwd / wgrad: two 32x32
 constexpr int TCP_H_CHUNKS = 8;                        // dgrad: ring of H chunk buffers, 16 KB each
 constexpr int TCP_H_BYTES = TCP_H_CHUNKS * 16384;
 constexpr int TCP_RING_BUDGET_DGRAD = 96 * 1024;
-// The fp16 wgrad streams every operand byte exactly once per tile row/column and is bound by the bytes it keeps in
-// flight: one staging slot per epilogue warp (32 KB) leaves 192 KB = four 48 KB stages to the operand ring.
-constexpr int tcp_staging_slots(int mode, bool f16) { return (mode == 2 && f16) ? 1 : 2; }
-constexpr int tcp_staging_bytes(int mode, bool f16) {
+// (measured: a single staging slot per epilogue warp + a 4-stage 192 KB ring is slower than 2 slots + 3 stages -- the
+// serialised epilogue, 8 us instead of 3 us per 128x256 tile, costs more than the deeper ring gains)
+__host__ __device__ constexpr int tcp_staging_slots(int mode, bool f16) { return 2; }
+__host__ __device__ constexpr int tcp_staging_bytes(int mode, bool f16) {
   return mode == 1 ? TCP_H_BYTES : TCP_EPI_WARPS * tcp_staging_slots(mode, f16) * 4096;
 }
-constexpr int tcp_ring_budget(int mode, bool f16) {
-  return mode == 1 ? TCP_RING_BUDGET_DGRAD : ((mode == 2 && f16) ? 192 * 1024 : TCP_RING_BUDGET);
+__host__ __device__ constexpr int tcp_ring_budget(int mode, bool f16) {
+  return mode == 1 ? TCP_RING_BUDGET_DGRAD : TCP_RING_BUDGET;
 }
 constexpr int TCP_MAX_BLOCK_N = 256;
 
@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) TRACE(0);
+  pdl_trigger();
 
   if (threadIdx.x < n_problems) {
     const TcProblem& P = batch.p[threadIdx.x];
@@ -183,6 +184,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_wait();  // the prologue above touched no global memory; the operands below come from the previous kernels
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -703,7 +705,7 @@ static int launch_tc_persistent(TcBatch& b, int n, cudaStream_t st, const char* 
                       (2 * TCP_MAX_STAGES + 4 + 2 * TCP_H_CHUNKS) * 8 + 16 + TC_MAX_PROBLEMS * sizeof(TcpScalars) +
                       TCP_EPI_WARPS * 128 + 1024;
   const int grid = total < num_sms() ? total : num_sms();
-  tc_gemm_persistent_kernel<MODE, F16><<<grid, TCP_THREADS, smem, st>>>(b, n);
+  launch_chain_kernel(tc_gemm_persistent_kernel<MODE, F16>, dim3(grid), dim3(TCP_THREADS), smem, st, b, n);
   return finish_launch(what);
 }
 

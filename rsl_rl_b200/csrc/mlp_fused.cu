@@ -115,17 +115,7 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp3_forward_kernel(const __gri
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   MF_TRACE(threadIdx.x == 0, 0);
 
-  // biases of every layer of every net -> shared memory (read by the epilogues as broadcast 16-byte loads)
-  for (int i = threadIdx.x; i < n_nets * MF_MAX_BIAS; i += MF_THREADS) {
-    const int ni = i / MF_MAX_BIAS, o = i - ni * MF_MAX_BIAS;
-    const MfNet& P = batch.net[ni];
-    float v = 0.f;
-    if (o < 512) { if (o < P.N1 && P.b[0]) v = __ldg(P.b[0] + o); }
-    else if (o < 768) { if (o - 512 < P.N2 && P.b[1]) v = __ldg(P.b[1] + o - 512); }
-    else if (o < 896) { if (o - 768 < P.N3 && P.b[2]) v = __ldg(P.b[2] + o - 768); }
-    else { if (o - 896 < P.N4 && P.b[3]) v = __ldg(P.b[3] + o - 896); }
-    bias_s[i] = v;
-  }
+  pdl_trigger();
   if (warp == 0 && elect_one()) {
     for (int i = 0; i < n_nets; ++i) {
       const MfNet& P = batch.net[i];
@@ -154,6 +144,18 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp3_forward_kernel(const __gri
                  "r"(512u)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  pdl_wait();  // everything above touched no global memory; the parameters below were written by the previous kernels
+  // biases of every layer of every net -> shared memory (read by the epilogues as broadcast 16-byte loads)
+  for (int i = threadIdx.x; i < n_nets * MF_MAX_BIAS; i += MF_THREADS) {
+    const int ni = i / MF_MAX_BIAS, o = i - ni * MF_MAX_BIAS;
+    const MfNet& P = batch.net[ni];
+    float v = 0.f;
+    if (o < 512) { if (o < P.N1 && P.b[0]) v = __ldg(P.b[0] + o); }
+    else if (o < 768) { if (o - 512 < P.N2 && P.b[1]) v = __ldg(P.b[1] + o - 512); }
+    else if (o < 896) { if (o - 768 < P.N3 && P.b[2]) v = __ldg(P.b[2] + o - 768); }
+    else { if (o - 896 < P.N4 && P.b[3]) v = __ldg(P.b[3] + o - 896); }
+    bias_s[i] = v;
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -573,8 +575,8 @@ int mlp3_forward_fused(int n, const rslrl_mlp3_fwd_t* nets, cudaStream_t st) {
   }
   const int total = (nets[0].M + TC_BLOCK_M - 1) / TC_BLOCK_M * n;
   const int grid = total < tc_num_sms() ? total : tc_num_sms();
-  if (f16) mlp3_forward_kernel<true><<<grid, MF_THREADS, smem, st>>>(b, n);
-  else mlp3_forward_kernel<false><<<grid, MF_THREADS, smem, st>>>(b, n);
+  if (f16) launch_chain_kernel(mlp3_forward_kernel<true>, dim3(grid), dim3(MF_THREADS), smem, st, b, n);
+  else launch_chain_kernel(mlp3_forward_kernel<false>, dim3(grid), dim3(MF_THREADS), smem, st, b, n);
   return finish_launch(what);
 }
 

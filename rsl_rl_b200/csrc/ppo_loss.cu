@@ -71,6 +71,8 @@ ppo_loss_kernel(const float* __restrict__ mu, const float* __restrict__ std_para
                 float* __restrict__ dvalue, int dvalue_stride, float* dstd, float* db_mu, float* db_value,
                 float* kl_out, double* loss_sums, LossWorkspace* ws, long long rows, long long mb_orig,
                 int A, float clip, float c_v, float c_e, int use_clipped) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float s_sigma[kMaxActions], s_logs[kMaxActions], s_2var[kMaxActions];
   __shared__ double s_red[4 * 32];
   __shared__ float s_dstd[kMaxActions], s_dbmu[kMaxActions];
@@ -328,10 +330,10 @@ int rslrl_ppo_loss_fwd_bwd(const float* mu, const float* std_param, int std_type
                    ((((uintptr_t)mu | (uintptr_t)actions | (uintptr_t)old_mu | (uintptr_t)old_sigma |
                       (uintptr_t)dmu) & 15) == 0);
   auto kern = vec ? ppo_loss_kernel<true> : ppo_loss_kernel<false>;
-  kern<<<blocks, kLossThreads, 0, (cudaStream_t)stream>>>(
-      mu, std_param, std_type, value, actions, old_logp, advantages, returns, old_values, old_mu, old_sigma, adv_stats,
-      dmu, dmu_stride, dvalue, dvalue_stride, dstd, db_mu, db_value, kl_out, loss_sums, (LossWorkspace*)workspace, rows,
-      mb_orig, A, (float)clip_param,
+  launch_chain_kernel(
+      kern, dim3(blocks), dim3(kLossThreads), 0, (cudaStream_t)stream, mu, std_param, std_type, value, actions, old_logp, advantages, returns, old_values, old_mu, old_sigma, adv_stats,
+      dmu, dmu_stride, dvalue, dvalue_stride, dstd, db_mu, db_value, kl_out, loss_sums, (LossWorkspace*)workspace, (long long)rows,
+      (long long)mb_orig, A, (float)clip_param,
       (float)value_loss_coef, (float)entropy_coef, use_clipped_value_loss);
   return finish_launch(what);
 }
