@@ -110,6 +110,7 @@ class FeedForwardEngine:
                 K = net.dims[0]
                 if K % 4:
                     self.w0_pad[tag] = torch.zeros(net.dims[1], (K + 3) // 4 * 4, **f32)
+        self._stage_bufs = {}
         self.refresh_padded()
         # whole-MLP forward in one launch (activations stay on chip between the layers): tf32 mode, eligible shapes
         self.fused_fwd = self.f16 or (precision == "tf32" and os.environ.get("RSLRL_FUSED_MLP", "1") != "0"
@@ -156,6 +157,12 @@ class FeedForwardEngine:
         """Grouped forward of actor and critic on M = x.shape[0] rows; hidden activations stay in
         self.h_a / self.h_c (rows [:M]) for the backward pass."""
         M = (x_a if actor else x_c).shape[0]
+        if self.f16 and not self._fused_inputs_ok(x_a if actor else None, x_c if critic else None):
+            # the fp16 path has no layer-by-layer forward: stage inputs whose rows are not 16-byte aligned (e.g. 235
+            # concatenated observation columns) in a zero-padded buffer
+            shared = x_c is x_a
+            x_a = self._staged(x_a, "a") if actor else x_a
+            x_c = x_a if (shared and actor) else (self._staged(x_c, "c") if critic else x_c)
         if self.fused_fwd and self._fused_inputs_ok(x_a if actor else None, x_c if critic else None):
             nets = []
             if actor:
@@ -181,6 +188,18 @@ class FeedForwardEngine:
                 probs.append((xin, w, lin.bias, out, self.critic.acts[l]))
                 in_c = out
             linear_forward(probs, self.prec)
+
+    def _staged(self, x: torch.Tensor, tag: str) -> torch.Tensor:
+        M, K = x.shape
+        key = (tag, M, K)
+        buf = self._stage_bufs.get(key)
+        if buf is None:
+            with torch.inference_mode(False):
+                buf = torch.zeros(M, (K + 3) // 4 * 4, dtype=torch.float32, device=self.device)
+            self._stage_bufs[key] = buf
+        view = buf[:, :K]
+        view.copy_(x)
+        return view
 
     def _fused_inputs_ok(self, x_a, x_c) -> bool:
         return all(x is None or (x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0 and x.stride(1) == 1)

@@ -231,7 +231,15 @@ class PPO:
         else:
             zbuf.normal_()  # same draw as torch.normal(mean, std): normal_(0,1) on a tensor of mu's shape
         if not self.use_cuda_graph:
-            plan["fwd"](x_a.data_ptr(), x_c.data_ptr())
+            if eng.f16 and not eng._fused_inputs_ok(x_a, x_c):
+                # the fp16 path has only the fused forward: rows that are not 16-byte aligned go through the padded
+                # static input buffers
+                sa.copy_(x_a)
+                if sc is not sa:
+                    sc.copy_(x_c)
+                plan["fwd_static"](sa.data_ptr(), sc.data_ptr())
+            else:
+                plan["fwd"](x_a.data_ptr(), x_c.data_ptr())
             eng.gaussian_head(mu_s, zbuf, act_s, logp_s, sig_s)
         else:
             # forward + Gaussian head of step s replayed from a CUDA graph reading static input buffers

@@ -864,7 +864,7 @@ int tc16_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* pr, cuda
   for (int i = 0; i < n; ++i) {
     const rslrl_linear_bwd_weight_t& q = pr[i];
     // dW[N,K] += scale * dY[M,N]^T X[M,K]: reduction M in k-blocks of 64 rows; both operands MN-major 64x64 boxes
-    if (!tma_ok16(q.dy, q.ldy) || !tma_ok16(q.x, q.ldx) || !tma_ok(q.dw, q.K)) return -1;
+    if (!tma_ok16(q.dy, q.ldy) || !tma_ok16(q.x, q.ldx)) return -1;
     TcProblem& P = b.p[i];
     P.block_n = q.K >= max_block_n() ? max_block_n() : (q.K + 63) / 64 * 64;
     P.tiles_m = (q.N + TC_BLOCK_M - 1) / TC_BLOCK_M;
@@ -875,12 +875,14 @@ int tc16_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* pr, cuda
   for (int i = 0; i < n; ++i) {
     const rslrl_linear_bwd_weight_t& q = pr[i];
     TcProblem& P = b.p[i];
+    // (a weight matrix whose rows are not 16-byte aligned, e.g. 235 inputs, takes the vector-atomic epilogue)
+    const bool c_tma = tma_ok(q.dw, q.K);
     if (!make_map16(&P.map_a, q.dy, q.M, q.N, q.ldy, 64, 64) || !make_map16(&P.map_b, q.x, q.M, q.K, q.ldx, 64, 64) ||
-        !make_map(&P.map_c, q.dw, q.N, q.K, q.K, 32, 32, false, false)) {
+        (c_tma && !make_map(&P.map_c, q.dw, q.N, q.K, q.K, 32, 32, false, false))) {
       set_error("%s: cuTensorMapEncodeTiled failed", what);
       return 1;
     }
-    P.C = q.dw; P.db = q.db; P.M = q.N; P.N = q.K; P.K = q.M; P.ldc = q.K; P.out_scale = q.scale; P.tma_out = 1;
+    P.C = q.dw; P.db = q.db; P.M = q.N; P.N = q.K; P.K = q.M; P.ldc = q.K; P.out_scale = q.scale; P.tma_out = c_tma ? 1 : 0;
     P.num_kb = (q.M + 63) / 64;
   }
   // k-splits: every work item (tile x k-range) of every grouped problem streams about the same number of bytes, and

@@ -275,3 +275,27 @@ def test_fp16_three_iterations_with_cuda_graphs_shadow_follows_parameters():
     if abs(ratio - 1.0) < 1e-9:
         u, ur = res[-1]["mine"].astype(np.float64) - init, res[-1]["ref"].astype(np.float64) - init
         assert np.linalg.norm(u - ur) / np.linalg.norm(ur) < 0.15
+
+
+def test_fp16_unaligned_observation_width_vs_oracle():
+    """gemm_precision='fp16' with observation width 10 (rows not 16-byte aligned): zero-padded first-layer shadow,
+    staged inputs for the last-value forward, padded fp16 observation copy and the vector-atomic epilogue for the first
+    layer's weight gradient."""
+    meta, obs, rewards, dones, time_outs, z, perms = _synthetic_problem(512, 8, 10, 6, [128, 128, 64], 3, seed=13)
+    r = _run_both(meta, obs, rewards, dones, time_outs, z, perms, 1, use_cuda_graph=False, gemm_precision="fp16")[0]
+    s, st = r["alg"].storage, r["st"]
+    assert r["alg"]._engine.f16 and r["alg"]._engine.w0_pad
+    assert rel_err(s.mu.cpu().numpy(), st["mu"]) < 1e-3
+    assert rel_err(s.values.cpu().numpy(), st["values"]) < 1e-3
+    assert rel_err(s.returns.cpu().numpy(), st["returns"]) < 1e-3
+    init = np.concatenate([v.reshape(-1) for v in _init_params_like_torch(meta, 0).values()]).astype(np.float64)
+    if abs(r["lr_mine"] - r["lr_ref"]) < 1e-12:
+        upd, upd_ref = r["mine"].astype(np.float64) - init, r["ref"].astype(np.float64) - init
+        assert np.linalg.norm(upd - upd_ref) / np.linalg.norm(upd_ref) < 5e-2
+    # three iterations with the rollout / update graphs active (the LR may hit its clamp at 1e-2 here, so the two
+    # trajectories are only compared when they coincide)
+    res = _run_both(meta, obs, rewards, dones, time_outs, z, perms, 3, use_cuda_graph=True, gemm_precision="fp16")
+    assert 1e-5 <= res[-1]["lr_mine"] <= 1e-2 and np.isfinite(res[-1]["mine"]).all()
+    if abs(res[-1]["lr_mine"] / res[-1]["lr_ref"] - 1.0) < 1e-9:
+        u, ur = res[-1]["mine"].astype(np.float64) - init, res[-1]["ref"].astype(np.float64) - init
+        assert np.linalg.norm(u - ur) / np.linalg.norm(ur) < 0.15

@@ -24,7 +24,7 @@ def main():
     for mode in ("graph", "eager"):
         torch.manual_seed(100 + rank)  # different initial weights per rank: the broadcast must align them
         env = SynthVecEnv(1024, {"policy": 48}, 12, device=dev, seed=rank)
-        cfg = bench.train_cfg("tf32", use_cuda_graph=(mode == "graph"))
+        cfg = bench.train_cfg(os.environ.get("RSLRL_PRECISION", "fp16"), use_cuda_graph=(mode == "graph"))
         runner = OnPolicyRunner(env, cfg, log_dir=None, device=dev)
         runner.learn(5)
         torch.cuda.synchronize()
