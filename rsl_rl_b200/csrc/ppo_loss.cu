@@ -9,6 +9,8 @@
 // last block to finish (threadfence + ticket) publishes the results and clears the workspace, so
 // there is no extra reduction launch, no host involvement and nothing to zero between launches.
 // Algorithmic traffic: (20*A + 24) bytes per sample.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace rslrl {
@@ -265,6 +267,193 @@ ppo_loss_kernel(const float* __restrict__ mu, const float* __restrict__ std_para
   }
 }
 
+// Same objective, four threads per sample row (thread <-> 4 consecutive actions, A <= 16, 16-byte aligned rows).
+// The row-per-thread kernel above leaves ~5 warps on an SM at the C2 minibatch (24 576 rows), i.e. one warp per
+// scheduler with a ~2 800-instruction dependent chain each; here a row's chain is ~4x shorter and there are 4x more
+// warps to hide its latencies.  Row sums (log-prob) are quad shuffles, the per-action column sums (dL/dsigma) are
+// strided warp shuffles; everything else is identical, including the tie rules and the last-block publish.
+constexpr int kQuadThreads = 256;
+__global__ void __launch_bounds__(kQuadThreads)
+ppo_loss_quad_kernel(const float* __restrict__ mu, const float* __restrict__ std_param, int std_type,
+                     const float* __restrict__ value, const float* __restrict__ actions,
+                     const float* __restrict__ old_logp, const float* __restrict__ advantages,
+                     const float* __restrict__ returns, const float* __restrict__ old_values,
+                     const float* __restrict__ old_mu, const float* __restrict__ old_sigma,
+                     const double* __restrict__ adv_stats, float* __restrict__ dmu, int dmu_stride,
+                     float* __restrict__ dvalue, int dvalue_stride, float* dstd, float* db_mu, float* db_value,
+                     float* kl_out, double* loss_sums, LossWorkspace* ws, long long rows, long long mb_orig,
+                     int A, float clip, float c_v, float c_e, int use_clipped) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float s_sigma[kMaxActions], s_logs[kMaxActions], s_2var[kMaxActions];
+  __shared__ double s_red[4 * 32];
+  __shared__ float s_dstd[kMaxActions], s_dbmu[kMaxActions];
+  __shared__ bool s_last;
+  if (threadIdx.x < A) {
+    const float p = std_param[threadIdx.x];
+    const float s = std_type == RSLRL_STD_LOG ? expf(p) : p;
+    s_sigma[threadIdx.x] = s;
+    s_logs[threadIdx.x] = logf(s);
+    s_2var[threadIdx.x] = 2.f * (s * s);
+    s_dstd[threadIdx.x] = 0.f;
+    s_dbmu[threadIdx.x] = 0.f;
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, qd = threadIdx.x & 3, c = qd * 4;
+  const long long i = (long long)blockIdx.x * (kQuadThreads / 4) + (threadIdx.x >> 2);
+  const bool valid = i < rows;
+  const bool mine = valid && c < A;          // this thread owns actions [c, c + 4) of row i
+  const bool lead = valid && qd == 0;        // the thread of the quad that accounts for the per-row scalars
+  const long long j = valid ? i % mb_orig : 0;
+  const float lo = 1.0f - clip, hi = 1.0f + clip;
+  const float g = 1.0f / (float)rows;
+
+  float lp = 0.f, kl = 0.f;
+  float d[4] = {0.f, 0.f, 0.f, 0.f};
+  if (mine) {
+    const float4 m4 = *(const float4*)(mu + i * A + c), a4 = *(const float4*)(actions + i * A + c);
+    const float mm[4] = {m4.x, m4.y, m4.z, m4.w}, aa[4] = {a4.x, a4.y, a4.z, a4.w};
+    const bool do_kl = i < mb_orig;
+    float omv[4] = {0, 0, 0, 0}, osv[4] = {1, 1, 1, 1};
+    if (do_kl) {
+      const float4 o4 = __ldg((const float4*)(old_mu + j * A + c)), s4 = __ldg((const float4*)(old_sigma + j * A + c));
+      omv[0] = o4.x; omv[1] = o4.y; omv[2] = o4.z; omv[3] = o4.w;
+      osv[0] = s4.x; osv[1] = s4.y; osv[2] = s4.z; osv[3] = s4.w;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      d[q] = aa[q] - mm[q];
+      lp += -(d[q] * d[q]) / s_2var[c + q] - s_logs[c + q] - kLogSqrt2Pi;
+      if (do_kl) {
+        const float dm = omv[q] - mm[q];
+        kl += logf(s_sigma[c + q] / osv[q] + 1.0e-5f) + (osv[q] * osv[q] + dm * dm) / s_2var[c + q] - 0.5f;
+      }
+    }
+  }
+  // log-prob of the row: sum over the quad (every thread of the quad ends up with the same value)
+  lp += __shfl_xor_sync(0xffffffffu, lp, 1);
+  lp += __shfl_xor_sync(0xffffffffu, lp, 2);
+
+  float g_lp = 0.f, surr = 0.f, vl = 0.f, dv_sum = 0.f;
+  if (valid) {
+    float adv = __ldg(advantages + j);
+    if (adv_stats) {  // per-minibatch normalisation (ppo.py:221-223), unbiased std
+      const double n = (double)mb_orig;
+      const double mean = adv_stats[0] / n;
+      double var = (adv_stats[1] - adv_stats[0] * adv_stats[0] / n) / (n - 1.0);
+      var = var > 0.0 ? var : 0.0;
+      adv = (adv - (float)mean) / ((float)sqrt(var) + 1e-8f);
+    }
+    const float ratio = expf(lp - __ldg(old_logp + j));
+    const float s1 = -adv * ratio;
+    const float clamped = fminf(fmaxf(ratio, lo), hi);
+    const float s2 = -adv * clamped;
+    // aten maximum backward: grad to the larger input, grad/2 to both on ties
+    const float g1 = s1 > s2 ? g : (s1 == s2 ? 0.5f * g : 0.f);
+    const float g2 = s2 > s1 ? g : (s1 == s2 ? 0.5f * g : 0.f);
+    const float in_range = (ratio >= lo && ratio <= hi) ? 1.f : 0.f;  // clamp backward mask (inclusive)
+    g_lp = (g1 * (-adv) + g2 * (-adv) * in_range) * ratio;
+    if (lead) {
+      surr = fmaxf(s1, s2);
+      const float v = value[i], R = __ldg(returns + j);
+      float dv_out;
+      if (use_clipped) {
+        const float vo = __ldg(old_values + j);
+        const float dv = v - vo;
+        const float vclip = vo + fminf(fmaxf(dv, -clip), clip);
+        const float e1 = v - R, e2 = vclip - R;
+        const float l1 = e1 * e1, l2 = e2 * e2;
+        vl = fmaxf(l1, l2);
+        const float ga = l1 > l2 ? g : (l1 == l2 ? 0.5f * g : 0.f);
+        const float gb = l2 > l1 ? g : (l1 == l2 ? 0.5f * g : 0.f);
+        const float in_v = (dv >= -clip && dv <= clip) ? 1.f : 0.f;
+        dv_out = c_v * (ga * 2.f * e1 + gb * 2.f * e2 * in_v);
+      } else {
+        const float e = R - v;
+        vl = e * e;
+        dv_out = c_v * g * (-2.f) * e;
+      }
+      dvalue[i * dvalue_stride] = dv_out;
+      dv_sum = dv_out;
+    }
+  }
+
+  // dL/dmu for this thread's four actions and the per-action dL/dsigma column sums (lanes with equal (lane & 3))
+  {
+    float o[4], ds[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float s = c + q < A ? s_sigma[c + q] : 1.f;
+      const float var = s * s;
+      o[q] = g_lp * d[q] / var;
+      ds[q] = mine ? g_lp * (d[q] * d[q] / (var * s) - 1.f / s) : 0.f;
+    }
+    if (mine) *(float4*)(dmu + i * dmu_stride + c) = make_float4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+      for (int off = 4; off < 32; off <<= 1) ds[q] += __shfl_xor_sync(0xffffffffu, ds[q], off);
+      if (db_mu != nullptr) {
+        float sm = mine ? o[q] : 0.f;
+#pragma unroll
+        for (int off = 4; off < 32; off <<= 1) sm += __shfl_xor_sync(0xffffffffu, sm, off);
+        if (lane < 4 && c + q < A) atomicAdd(&s_dbmu[c + q], sm);
+      }
+      if (lane < 4 && c + q < A) atomicAdd(&s_dstd[c + q], ds[q]);
+    }
+  }
+
+  double red[4] = {(double)kl, (double)surr, (double)vl, (double)dv_sum};
+  block_sum<4>(red, s_red);
+  if (threadIdx.x == 0) {
+    atomicAdd(&ws->acc[0], red[0]);
+    atomicAdd(&ws->acc[1], red[1]);
+    atomicAdd(&ws->acc[2], red[2]);
+    atomicAdd(&ws->acc[3], red[3]);
+  }
+  __syncthreads();
+  if (threadIdx.x < A) {
+    atomicAdd(&ws->acc[4 + threadIdx.x], (double)s_dstd[threadIdx.x]);
+    if (db_mu != nullptr) atomicAdd(&ws->acc[4 + kMaxActions + threadIdx.x], (double)s_dbmu[threadIdx.x]);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&ws->ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // ---- last block: publish and clear (as in ppo_loss_kernel)
+  if (threadIdx.x < A) {
+    const int a = threadIdx.x;
+    const float s = s_sigma[a];
+    double gsum = *((volatile double*)&ws->acc[4 + a]);
+    if (std_type == RSLRL_STD_LOG) gsum = gsum * (double)s - (double)c_e;
+    else gsum = gsum - (double)c_e / (double)s;
+    dstd[a] += (float)gsum;
+    ws->acc[4 + a] = 0.0;
+    if (db_mu != nullptr) {
+      db_mu[a] += (float)*((volatile double*)&ws->acc[4 + kMaxActions + a]);
+      ws->acc[4 + kMaxActions + a] = 0.0;
+    }
+  }
+  if (threadIdx.x == 0) {
+    const double klm = *((volatile double*)&ws->acc[0]) / (double)mb_orig;
+    if (kl_out) *kl_out = (float)klm;
+    if (db_value) *db_value += (float)*((volatile double*)&ws->acc[3]);
+    float ent = 0.f;
+    for (int a = 0; a < A; ++a) ent += kEntropyConst + s_logs[a];
+    if (loss_sums) {
+      loss_sums[0] += *((volatile double*)&ws->acc[1]) / (double)rows;
+      loss_sums[1] += *((volatile double*)&ws->acc[2]) / (double)rows;
+      loss_sums[2] += (double)ent;
+    }
+    ws->acc[0] = ws->acc[1] = ws->acc[2] = ws->acc[3] = 0.0;
+    __threadfence();
+    ws->ticket = 0u;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 sum_sumsq_kernel(const float* __restrict__ x, long long n, double* out, SumWorkspace* ws) {
   __shared__ double s_red[2 * 32];
@@ -329,6 +518,16 @@ int rslrl_ppo_loss_fwd_bwd(const float* mu, const float* std_param, int std_type
   const bool vec = (A % 4 == 0) && (dmu_stride % 4 == 0) &&
                    ((((uintptr_t)mu | (uintptr_t)actions | (uintptr_t)old_mu | (uintptr_t)old_sigma |
                       (uintptr_t)dmu) & 15) == 0);
+  static const bool quad_ok = [] { const char* e = getenv("RSLRL_LOSS_QUAD"); return !(e && e[0] == '0'); }();
+  if (vec && A <= 16 && quad_ok) {  // four threads per row
+    const int qblocks = (int)((rows + kQuadThreads / 4 - 1) / (kQuadThreads / 4));
+    launch_chain_kernel(
+        ppo_loss_quad_kernel, dim3(qblocks), dim3(kQuadThreads), 0, (cudaStream_t)stream, mu, std_param, std_type, value,
+        actions, old_logp, advantages, returns, old_values, old_mu, old_sigma, adv_stats, dmu, dmu_stride, dvalue,
+        dvalue_stride, dstd, db_mu, db_value, kl_out, loss_sums, (LossWorkspace*)workspace, (long long)rows,
+        (long long)mb_orig, A, (float)clip_param, (float)value_loss_coef, (float)entropy_coef, use_clipped_value_loss);
+    return finish_launch(what);
+  }
   auto kern = vec ? ppo_loss_kernel<true> : ppo_loss_kernel<false>;
   launch_chain_kernel(
       kern, dim3(blocks), dim3(kLossThreads), 0, (cudaStream_t)stream, mu, std_param, std_type, value, actions, old_logp, advantages, returns, old_values, old_mu, old_sigma, adv_stats,
