@@ -347,8 +347,14 @@ def run_ours(args):
     if rank == 0:
         peaks = measured_peaks()
         dom = time_dominant_kernel(runner.alg)
+        # DRAM bytes (read + write) per dense launch from the committed `ncu --set full` capture of one minibatch
+        # (profiles/r1_ncu_full_update_fp16.txt: forward 38.1 MB, head backward 14.2, dgrad 38.6 + 88.9, grouped wgrad 172.3;
+        # profiles/r1_ncu_full_update.txt for the tf32 build); None for modes without a capture
+        traffic = {"fp16": 352.1e6 / 5}.get(args.precision)
         roofline = dict(bound="tensor", achieved=dom["tflops"], peak=peaks["tf_sustained"], unit="TFLOP/s",
-                        frac=dom["tflops"] / peaks["tf_sustained"], traffic=None,
+                        frac=dom["tflops"] / peaks["tf_sustained"], traffic=traffic,
+                        traffic_note="dram__bytes_read.sum + dram__bytes_write.sum averaged over the 5 dense launches of "
+                                     "one minibatch (ncu --set full, profiles/r1_ncu_full_update_fp16.txt)",
                         kernel=("sgemm_kernel (fp32 CUDA-core FMA)" if args.precision == "fp32"
                                 else f"mlp3_forward_kernel + tc_gemm_persistent_kernel<dgrad|wgrad> ({args.precision} tcgen05): "
                                      "all dense launches of one minibatch forward + backward"),

@@ -24,7 +24,7 @@ extern "C" {
 
 #define RSLRL_ABI_VERSION 1
 #define RSLRL_MAX_SEGMENTS 16 /* max obs groups / gather fields per launch */
-#define RSLRL_MAX_PROBLEMS 6  /* max GEMM problems grouped into one launch (fp16 wgrad: 3 layers x actor, critic) */
+#define RSLRL_MAX_PROBLEMS 8  /* max GEMM problems grouped into one launch (fp16 wgrad: 4 layers x actor, critic) */
 
 typedef void* rslrl_stream_t;
 
@@ -201,7 +201,10 @@ int rslrl_mlp3_forward(int n, const rslrl_mlp3_fwd_t* nets_host, rslrl_stream_t 
  *   kl_out [1]  = mean KL(old||new) over the first mb_orig rows as fp32 (ppo.py:262-269); may alias
  *                 the tail slot of the flat gradient buffer so that it rides the gradient all-reduce
  *   loss_sums  double[3] += {surrogate_mean, value_loss_mean, entropy_mean} of this minibatch
- *   workspace  rslrl_loss_workspace_bytes() bytes, zero-initialised once by the caller */
+ *   workspace  rslrl_loss_workspace_bytes() bytes, zero-initialised once by the caller
+ *   dmu16 / dvalue16 (may be NULL; need A % 4 == 0, A <= 16, 16-byte aligned rows): fp16 copies
+ *              grad_scale16 * dmu, grad_scale16 * dvalue (row strides in elements, multiples of 8) = the scaled output
+ *              gradients the RSLRL_PREC_FP16 backward starts from */
 int64_t rslrl_loss_workspace_bytes(void);
 int rslrl_ppo_loss_fwd_bwd(const float* mu, const float* std_param, int std_type, const float* value,
                            const float* actions, const float* old_logp, const float* advantages,
@@ -210,7 +213,8 @@ int rslrl_ppo_loss_fwd_bwd(const float* mu, const float* std_param, int std_type
                            float* dvalue, int dvalue_stride, float* dstd, float* db_mu, float* db_value,
                            float* kl_out, double* loss_sums, void* workspace, int64_t rows,
                            int64_t mb_orig, int A, double clip_param, double value_loss_coef,
-                           double entropy_coef, int use_clipped_value_loss, rslrl_stream_t stream);
+                           double entropy_coef, int use_clipped_value_loss, void* dmu16, int dmu16_stride,
+                           void* dvalue16, int dvalue16_stride, double grad_scale16, rslrl_stream_t stream);
 
 /* sum and sum of squares of x[0..n) into out[2] (double, overwritten): statistics for
  * ppo.py:221-223 per-minibatch advantage normalisation. */

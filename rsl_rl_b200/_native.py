@@ -22,7 +22,7 @@ ACT_CODES = {"identity": 0, "elu": 1, "relu": 2, "tanh": 3, "sigmoid": 4, "lrelu
 PREC_FP32, PREC_TF32, PREC_FP16 = 0, 1, 2
 PREC_CODES = {"fp32": PREC_FP32, "tf32": PREC_TF32, "fp16": PREC_FP16}
 STD_SCALAR, STD_LOG = 0, 1
-MAX_SEGMENTS, MAX_PROBLEMS = 16, 6
+MAX_SEGMENTS, MAX_PROBLEMS = 16, 8
 
 
 class LinearFwd(C.Structure):
@@ -111,7 +111,8 @@ _SIGNATURES["rslrl_ppo_loss_fwd_bwd"] = (c_int, [
     c_void_p, c_void_p, c_void_p,                   # old_mu, old_sigma, adv_stats
     c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,  # dmu, dmu_stride, dvalue, dvalue_stride, dstd, db_mu, db_value
     c_void_p, c_void_p, c_void_p,                   # kl_out, loss_sums, workspace
-    c_i64, c_i64, c_int, c_double, c_double, c_double, c_int, c_void_p])
+    c_i64, c_i64, c_int, c_double, c_double, c_double, c_int,
+    c_void_p, c_int, c_void_p, c_int, c_double, c_void_p])  # dmu16, stride, dvalue16, stride, grad_scale16, stream
 
 _lib = None
 

@@ -101,6 +101,13 @@ class FeedForwardEngine:
         # gradient heads keep a 16-byte row pitch so that TMA can read them (dvalue: 1 used column of 4)
         self.dmu = torch.zeros(R, (self.A + 3) // 4 * 4, **f32)[:, :self.A]
         self.dvalue = torch.zeros(R, 4, **f32)[:, :1]
+        # fp16 path, A % 4 == 0: the loss kernel also emits S * dmu, S * dvalue as fp16 (16-byte row pitch) and the output
+        # layers run through the tensor-core dgrad / grouped wgrad like every other layer (no narrow-head kernel)
+        self.head16 = self.f16 and self.A % 4 == 0 and os.environ.get("RSLRL_HEAD16", "1") != "0"
+        if self.head16:
+            f16 = dict(dtype=torch.float16, device=self.device)
+            self.dmu16 = torch.zeros(R, (self.A + 7) // 8 * 8, **f16)[:, :self.A]
+            self.dvalue16 = torch.zeros(R, 8, **f16)[:, :1]
         # First-layer weights whose row pitch is not a multiple of 16 bytes (e.g. 235 inputs) cannot be described to
         # TMA: keep a zero-padded shadow [N, pad4(K)] that the tensor-core forward reads (refreshed after every
         # optimiser step); inputs are then read at their padded width (pad columns are kept at zero).
@@ -313,11 +320,20 @@ class FeedForwardEngine:
         nets = ((self.actor, self.h_a, self.g_a, x_a, dmu), (self.critic, self.h_c, self.g_c, x_c, dvalue))
         dz = lambda net, gbuf, l: gbuf[l - 1][:M * net.dims[l]].view(M, net.dims[l])   # gradient at the output of layer l-1
         hprobs, wprobs = [], []
-        for net, hs, gbuf, _, d_out in nets:
-            lin, l = net.layers[-1], net.L - 1
-            hprobs.append((d_out, lin.weight, hs[l - 1][:M], dz(net, gbuf, l), lin.weight.grad, lin.bias.grad,
-                           net.acts[l - 1], S))
-        linear_backward_head(hprobs)
+        if self.head16:
+            # output layers on the tensor cores: dY16 = S * dL/d(mu|V) was written by the loss kernel
+            dprobs = []
+            for (net, hs, gbuf, _, _), dy16 in zip(nets, (self.dmu16[:M], self.dvalue16[:M])):
+                lin, l = net.layers[-1], net.L - 1
+                wprobs.append((dy16, hs[l - 1][:M], lin.weight.grad, lin.bias.grad, 1.0 / S))
+                dprobs.append((dy16, self.group.shadow16(lin.weight), hs[l - 1][:M], dz(net, gbuf, l), net.acts[l - 1]))
+            linear_backward_data(dprobs, prec)
+        else:
+            for net, hs, gbuf, _, d_out in nets:
+                lin, l = net.layers[-1], net.L - 1
+                hprobs.append((d_out, lin.weight, hs[l - 1][:M], dz(net, gbuf, l), lin.weight.grad, lin.bias.grad,
+                               net.acts[l - 1], S))
+            linear_backward_head(hprobs)
         for l in range(self.actor.L - 2, -1, -1):
             dprobs = []
             for net, hs, gbuf, x_in, _ in nets:
@@ -352,4 +368,7 @@ class FeedForwardEngine:
             self.dvalue.stride(0), self.std_param.grad.data_ptr(), None, None, nat.ptr(kl_out), nat.ptr(loss_sums),
             self.loss_ws.data_ptr(), rows,
             mb_orig, self.A, hp["clip_param"], hp["value_loss_coef"], hp["entropy_coef"],
-            int(hp["use_clipped_value_loss"]), nat.stream_ptr()))
+            int(hp["use_clipped_value_loss"]),
+            self.dmu16.data_ptr() if self.head16 else None, self.dmu16.stride(0) if self.head16 else 0,
+            self.dvalue16.data_ptr() if self.head16 else None, self.dvalue16.stride(0) if self.head16 else 0,
+            self.grad_scale, nat.stream_ptr()))

@@ -38,6 +38,7 @@ from .flat_params import FlatParamGroup, FusedAdam
 
 
 _GRAPH_COLLECTIVES = os.environ.get("RSLRL_GRAPH_COLLECTIVES", "1") != "0"
+_ACT_GRAPH = os.environ.get("RSLRL_ACT_GRAPH", "1") != "0"   # per-step act() graphs (forward + Gaussian head)
 
 
 class PPO:
@@ -230,7 +231,7 @@ class PPO:
             zbuf.copy_(self.policy._noise_fn(mu_s))
         else:
             zbuf.normal_()  # same draw as torch.normal(mean, std): normal_(0,1) on a tensor of mu's shape
-        if not self.use_cuda_graph:
+        if not (self.use_cuda_graph and _ACT_GRAPH):
             if eng.f16 and not eng._fused_inputs_ok(x_a, x_c):
                 # the fp16 path has only the fused forward: rows that are not 16-byte aligned go through the padded
                 # static input buffers

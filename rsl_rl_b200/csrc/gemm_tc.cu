@@ -50,7 +50,7 @@ struct TcProblem {
   int block_n, tiles_m, tiles_n, splits, kb_per_split, num_kb;
 };
 
-constexpr int TC_MAX_PROBLEMS = 6;  // 6 x 640 B of kernel parameters (< 4 KB)
+constexpr int TC_MAX_PROBLEMS = 8;  // 8 x 640 B of kernel parameters (CUDA >= 12.1 allows up to 32 KB)
 
 struct alignas(64) TcBatch {
   TcProblem p[TC_MAX_PROBLEMS];

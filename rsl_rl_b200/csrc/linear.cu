@@ -80,7 +80,7 @@ int rslrl_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* probs_h
   if (precision == RSLRL_PREC_FP16) {
     const int rc = tc16_linear_backward_weight(n, probs_host, (cudaStream_t)stream);
     if (rc < 0) {
-      set_error("%s(fp16): shape not eligible (needs 16-byte aligned rows of dy and x, at most 6 problems)", what);
+      set_error("%s(fp16): shape not eligible (needs 16-byte aligned rows of dy and x, at most 8 problems)", what);
       return 4;
     }
     return rc;

@@ -9,6 +9,8 @@
 // last block to finish (threadfence + ticket) publishes the results and clears the workspace, so
 // there is no extra reduction launch, no host involvement and nothing to zero between launches.
 // Algorithmic traffic: (20*A + 24) bytes per sample.
+#include <cuda_fp16.h>
+
 #include <cstdlib>
 
 #include "common.cuh"
@@ -282,7 +284,8 @@ ppo_loss_quad_kernel(const float* __restrict__ mu, const float* __restrict__ std
                      const double* __restrict__ adv_stats, float* __restrict__ dmu, int dmu_stride,
                      float* __restrict__ dvalue, int dvalue_stride, float* dstd, float* db_mu, float* db_value,
                      float* kl_out, double* loss_sums, LossWorkspace* ws, long long rows, long long mb_orig,
-                     int A, float clip, float c_v, float c_e, int use_clipped) {
+                     int A, float clip, float c_v, float c_e, int use_clipped, __half* __restrict__ dmu16,
+                     int dmu16_stride, __half* __restrict__ dvalue16, int dvalue16_stride, float scale16) {
   pdl_trigger();
   pdl_wait();
   __shared__ float s_sigma[kMaxActions], s_logs[kMaxActions], s_2var[kMaxActions];
@@ -375,6 +378,7 @@ ppo_loss_quad_kernel(const float* __restrict__ mu, const float* __restrict__ std
         dv_out = c_v * g * (-2.f) * e;
       }
       dvalue[i * dvalue_stride] = dv_out;
+      if (dvalue16 != nullptr) dvalue16[i * dvalue16_stride] = __float2half_rn(dv_out * scale16);
       dv_sum = dv_out;
     }
   }
@@ -389,7 +393,16 @@ ppo_loss_quad_kernel(const float* __restrict__ mu, const float* __restrict__ std
       o[q] = g_lp * d[q] / var;
       ds[q] = mine ? g_lp * (d[q] * d[q] / (var * s) - 1.f / s) : 0.f;
     }
-    if (mine) *(float4*)(dmu + i * dmu_stride + c) = make_float4(o[0], o[1], o[2], o[3]);
+    if (mine) {
+      *(float4*)(dmu + i * dmu_stride + c) = make_float4(o[0], o[1], o[2], o[3]);
+      if (dmu16 != nullptr) {  // scaled fp16 copy: the A operand of the fp16 output-layer backward
+        const __half2 lo2 = __floats2half2_rn(o[0] * scale16, o[1] * scale16), hi2 = __floats2half2_rn(o[2] * scale16, o[3] * scale16);
+        uint2 w;
+        w.x = *(const unsigned int*)&lo2;
+        w.y = *(const unsigned int*)&hi2;
+        *(uint2*)(dmu16 + i * dmu16_stride + c) = w;
+      }
+    }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
 #pragma unroll
@@ -507,7 +520,8 @@ int rslrl_ppo_loss_fwd_bwd(const float* mu, const float* std_param, int std_type
                            float* dvalue, int dvalue_stride, float* dstd, float* db_mu, float* db_value,
                            float* kl_out, double* loss_sums, void* workspace, int64_t rows,
                            int64_t mb_orig, int A, double clip_param, double value_loss_coef,
-                           double entropy_coef, int use_clipped_value_loss, rslrl_stream_t stream) {
+                           double entropy_coef, int use_clipped_value_loss, void* dmu16, int dmu16_stride,
+                           void* dvalue16, int dvalue16_stride, double grad_scale16, rslrl_stream_t stream) {
   using namespace rslrl;
   const char* what = "rslrl_ppo_loss_fwd_bwd";
   RSLRL_CHECK_ARG(mu && std_param && value && actions && old_logp && advantages && returns && old_values, what);
@@ -519,14 +533,20 @@ int rslrl_ppo_loss_fwd_bwd(const float* mu, const float* std_param, int std_type
                    ((((uintptr_t)mu | (uintptr_t)actions | (uintptr_t)old_mu | (uintptr_t)old_sigma |
                       (uintptr_t)dmu) & 15) == 0);
   static const bool quad_ok = [] { const char* e = getenv("RSLRL_LOSS_QUAD"); return !(e && e[0] == '0'); }();
+  RSLRL_CHECK_ARG(dmu16 == nullptr || (dmu16_stride % 4 == 0 && ((uintptr_t)dmu16 & 7) == 0), what);
   if (vec && A <= 16 && quad_ok) {  // four threads per row
     const int qblocks = (int)((rows + kQuadThreads / 4 - 1) / (kQuadThreads / 4));
     launch_chain_kernel(
         ppo_loss_quad_kernel, dim3(qblocks), dim3(kQuadThreads), 0, (cudaStream_t)stream, mu, std_param, std_type, value,
         actions, old_logp, advantages, returns, old_values, old_mu, old_sigma, adv_stats, dmu, dmu_stride, dvalue,
         dvalue_stride, dstd, db_mu, db_value, kl_out, loss_sums, (LossWorkspace*)workspace, (long long)rows,
-        (long long)mb_orig, A, (float)clip_param, (float)value_loss_coef, (float)entropy_coef, use_clipped_value_loss);
+        (long long)mb_orig, A, (float)clip_param, (float)value_loss_coef, (float)entropy_coef, use_clipped_value_loss,
+        (__half*)dmu16, dmu16_stride, (__half*)dvalue16, dvalue16_stride, (float)grad_scale16);
     return finish_launch(what);
+  }
+  if (dmu16 != nullptr || dvalue16 != nullptr) {
+    set_error("%s: fp16 gradient outputs need A %% 4 == 0, A <= 16 and 16-byte aligned rows", what);
+    return 4;
   }
   auto kern = vec ? ppo_loss_kernel<true> : ppo_loss_kernel<false>;
   launch_chain_kernel(

@@ -290,6 +290,11 @@ def _run_loss(mu, std_param, std_type, value, actions, old_logp, adv, ret, old_v
         stats = torch.zeros(2, dtype=torch.float64, device=DEV)
         sws = torch.zeros(64, dtype=torch.uint8, device=DEV)
         nat.check(nat.lib().rslrl_sum_sumsq(d["adv"].data_ptr(), mb_orig, stats.data_ptr(), sws.data_ptr(), nat.stream_ptr()))
+    # optional scaled fp16 copies of the output gradients (four-threads-per-row kernel only: A % 4 == 0, A <= 16)
+    f16out = A % 4 == 0 and A <= 16
+    S16 = 4096.0
+    dmu16 = torch.zeros(rows, (A + 7) // 8 * 8, device=DEV, dtype=torch.float16)
+    dv16 = torch.zeros(rows, 8, device=DEV, dtype=torch.float16)
     for _ in range(2):  # twice: the workspace must clean itself up
         dstd.zero_(); sums.zero_(); db_mu.zero_(); db_v.zero_()
         nat.check(nat.lib().rslrl_ppo_loss_fwd_bwd(
@@ -297,8 +302,12 @@ def _run_loss(mu, std_param, std_type, value, actions, old_logp, adv, ret, old_v
             d["old_logp"].data_ptr(), d["adv"].data_ptr(), d["ret"].data_ptr(), d["old_v"].data_ptr(), d["old_mu"].data_ptr(),
             d["old_sigma"].data_ptr(), nat.ptr(stats), dmu.data_ptr(), A4, dv.data_ptr(), 4, dstd.data_ptr(),
             db_mu.data_ptr(), db_v.data_ptr(), kl.data_ptr(), sums.data_ptr(), ws.data_ptr(), rows, mb_orig, A, 0.2, 1.0,
-            0.01, int(clipped), nat.stream_ptr()))
+            0.01, int(clipped), dmu16.data_ptr() if f16out else None, dmu16.stride(0), dv16.data_ptr() if f16out else None,
+            dv16.stride(0), S16, nat.stream_ptr()))
     torch.cuda.synchronize()
+    if f16out:
+        assert torch.equal(dmu16[:, :A], (dmu * S16).half()) and torch.equal(dv16[:, 0], (dv * S16).half())
+        assert float(dmu16[:, A:].abs().sum()) == 0.0 and float(dv16[:, 1:].abs().sum()) == 0.0
     # the fused bias gradients of the two output layers are the column sums of dmu / dvalue
     assert rel_err(db_mu.cpu().numpy(), dmu.double().sum(0).cpu().numpy()) < 1e-5
     assert abs(float(db_v) - float(dv.double().sum())) < 1e-5 * max(1e-6, float(dv.double().abs().sum()))
