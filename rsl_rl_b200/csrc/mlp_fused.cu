@@ -17,6 +17,8 @@
 // Numerics are those of the layer-by-layer tcgen05 path (gemm_tc.cu): operands rounded fp32 -> tf32 to nearest
 // (TMA does it for x and the weights, the epilogue for the activations), fp32 accumulation in the same k order.
 // Replaces rsl_rl/networks/mlp.py:106-114 (MLP.forward) for actor and critic in one launch.
+#include <cstdlib>
+
 #include "tc_ptx.cuh"
 
 namespace rslrl {
@@ -87,6 +89,27 @@ __device__ __forceinline__ float elu_max_form(float z) {
   return fmaxf(z, ex2_approx(fminf(z, 0.f) * 1.4426950408889634f) - 1.f);
 }
 
+// ---- 2-CTA cluster helpers: the two CTAs of a cluster work on adjacent row tiles of the SAME net, so they consume the
+// same weight k-blocks in the same order; each CTA fetches half of every weight k-block and TMA-multicasts it into
+// both CTAs' rings (half the L2->SM weight traffic per SM, which is what bounds the layer-1/2 phase of a tile).
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+// MMA completion -> arrive on the barrier at the same offset in every CTA of the mask
+__device__ __forceinline__ void tcgen05_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(cta_mask)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -94,9 +117,11 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // F16: the activations leave the epilogue as fp16 (granules of 128 rows x 64 columns, still 128-byte rows), layers 2-4
 // run as kind::f16 MMAs against the fp16 weight shadows and the saved activations are stored as fp16.  Layer 1 is
 // tf32 in both modes (x and W1 are fp32 in HBM).
-template <bool F16>
+// MC: launched as clusters of two CTAs with multicast weight loads (see the helpers above).
+template <bool F16, bool MC>
 __global__ void __launch_bounds__(MF_THREADS, 1) mlp3_forward_kernel(const __grid_constant__ MfBatch batch,
                                                                      const int n_nets) {
+  const int cta_rank = MC ? (int)(blockIdx.x & 1) : 0;   // cluster dims (2,1,1): rank = blockIdx.x % 2
   constexpr int GK = F16 ? 64 : 32;    // activation columns per granule = k-block of layers 2-4
   constexpr int KB2 = 128 / GK;        // granules per 128-column chunk of layer 1
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -127,7 +152,7 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp3_forward_kernel(const __gri
     }
     for (int s = 0; s < MF_W_STAGES; ++s) {
       mbar_init(&w_full[s], 1);
-      mbar_init(&w_empty[s], 1);
+      mbar_init(&w_empty[s], MC ? 2 : 1);   // MMA commits of every CTA that receives the stage
     }
     for (int g = 0; g < MF_GRANULES; ++g) {
       mbar_init(&g_full[g], F16 ? 8 : 4);   // the row-quarter warps (x 2 column halves in fp16) that write a granule
@@ -145,6 +170,7 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp3_forward_kernel(const __gri
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (MC) cluster_sync_all();  // the peer's barriers are initialised before anything is multicast into this CTA
   pdl_wait();  // everything above touched no global memory; the parameters below were written by the previous kernels
   // biases of every layer of every net -> shared memory (read by the epilogues as broadcast 16-byte loads)
   for (int i = threadIdx.x; i < n_nets * MF_MAX_BIAS; i += MF_THREADS) {
@@ -163,8 +189,13 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp3_forward_kernel(const __gri
   const uint32_t tmem_base = *tmem_ptr_smem;
   MF_TRACE(threadIdx.x == 0, 1);
 
+  // work items: (net, 128-row tile), net fastest.  MC: a cluster takes the pair (net, tiles 2k and 2k+1) - a phantom
+  // tile past the end of an odd tile count loads zeros and stores nothing (TMA clips, the output rows are guarded)
   const int tiles_m = (batch.net[0].M + TC_BLOCK_M - 1) / TC_BLOCK_M;
-  const int total = tiles_m * n_nets;
+  const int it0 = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int it_step = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int total = MC ? n_nets * ((tiles_m + 1) / 2) : tiles_m * n_nets;
+  auto item_m0 = [&](int t) { return (MC ? (t / n_nets) * 2 + cta_rank : t / n_nets) * TC_BLOCK_M; };
 
   if (warp == 0) {
     // ===================================================================== TMA producer (weight ring)
@@ -176,17 +207,28 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp3_forward_kernel(const __gri
         ++it;
         return wring + (size_t)s * MF_W_STAGE_BYTES;
       };
-      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+      for (int t = it0; t < total; t += it_step) {
         const MfNet& P = batch.net[t % n_nets];
-        const int m0 = (t / n_nets) * TC_BLOCK_M;
+        const int m0 = item_m0(t);
         const int kb0 = (P.K0 + TC_BLOCK_K - 1) / TC_BLOCK_K, C1 = P.N1 / 128;
+        // a weight k-block of `rows` rows arrives as two half-row boxes: fetched and multicast by one CTA each (MC), or
+        // both fetched locally
+        auto wload = [&](uint8_t* dst, const CUtensorMap* map, int s, int col, int row0, int rows) {
+          const int half = rows / 2;
+          if (MC) {
+            tma_load_2d_mc(dst + (size_t)cta_rank * half * 128, map, &w_full[s], col, row0 + cta_rank * half, (uint16_t)3);
+          } else {
+            tma_load_2d(dst, map, &w_full[s], col, row0);
+            tma_load_2d(dst + (size_t)half * 128, map, &w_full[s], col, row0 + half);
+          }
+        };
         auto l1 = [&](int c) {  // x k-block + the chunk's W1 k-block per stage
           for (int kb = 0; kb < kb0; ++kb) {
             int s;
             uint8_t* dst = stage(s);
             mbar_expect_tx(&w_full[s], 2u * 16384u);
             tma_load_2d(dst, &P.map_x, &w_full[s], kb * TC_BLOCK_K, m0);
-            tma_load_2d(dst + 16384, &P.map_w1, &w_full[s], kb * TC_BLOCK_K, c * 128);
+            wload(dst + 16384, &P.map_w1, s, kb * TC_BLOCK_K, c * 128, 128);
           }
         };
         auto l2p = [&](int c) {
@@ -194,7 +236,7 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp3_forward_kernel(const __gri
             int s;
             uint8_t* dst = stage(s);
             mbar_expect_tx(&w_full[s], (uint32_t)P.N2 * 128u);
-            tma_load_2d(dst, &P.map_w2, &w_full[s], (c * KB2 + kb) * GK, 0);
+            wload(dst, &P.map_w2, s, (c * KB2 + kb) * GK, 0, P.N2);
           }
         };
         l1(0);
@@ -210,7 +252,7 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp3_forward_kernel(const __gri
           uint8_t* dst = stage(s);
           mbar_expect_tx(&w_full[s], (uint32_t)(pack3 * P.N3) * 128u);
           for (int i = 0; i < pack3; ++i)
-            tma_load_2d(dst + (size_t)i * P.N3 * 128, &P.map_w3, &w_full[s], (kb + i) * GK, 0);
+            wload(dst + (size_t)i * P.N3 * 128, &P.map_w3, s, (kb + i) * GK, 0, P.N3);
         }
         {
           const int nkb4 = P.N3 / GK;
@@ -262,7 +304,7 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp3_forward_kernel(const __gri
       ++use[a];
     };
     int tj = -1;
-    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+    for (int t = it0; t < total; t += it_step) {
       ++tj;
       const MfNet& P = batch.net[t % n_nets];
       const int kb0 = (P.K0 + TC_BLOCK_K - 1) / TC_BLOCK_K, C1 = P.N1 / 128;
@@ -278,7 +320,7 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp3_forward_kernel(const __gri
           const uint32_t base = wait_w(s);
           tcgen05_fence_after();
           kblock(tmem_base + (uint32_t)a * 128u, base, base + 16384u, idesc1, kb == 0, false);
-          if (elect_one()) tcgen05_commit(&w_empty[s]);
+          if (elect_one()) { if (MC) tcgen05_commit_mc(&w_empty[s], (uint16_t)3); else tcgen05_commit(&w_empty[s]); }
           __syncwarp();
         }
         publish_acc(a);
@@ -297,7 +339,7 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp3_forward_kernel(const __gri
             if (elect_one()) tcgen05_commit(&g_empty[g]);
             __syncwarp();
           }
-          if (elect_one()) tcgen05_commit(&w_empty[s]);
+          if (elect_one()) { if (MC) tcgen05_commit_mc(&w_empty[s], (uint16_t)3); else tcgen05_commit(&w_empty[s]); }
           __syncwarp();
         }
       };
@@ -322,9 +364,9 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp3_forward_kernel(const __gri
   } else if (warp == 2) {
     // ===================================================================== granule store warp
     int gn = 0;
-    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+    for (int t = it0; t < total; t += it_step) {
       const MfNet& P = batch.net[t % n_nets];
-      const int m0 = (t / n_nets) * TC_BLOCK_M;
+      const int m0 = item_m0(t);
       const int n1 = P.N1 / GK, n2 = P.N2 / GK, n3 = P.N3 / GK;
       for (int i = 0; i < n1 + n2 + n3; ++i, ++gn) {
         const int g = gn % MF_GRANULES;
@@ -352,11 +394,11 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp3_forward_kernel(const __gri
     int gbase = 0;
     uint32_t use[3] = {0, 0, 0};
     int tj = -1;
-    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+    for (int t = it0; t < total; t += it_step) {
       ++tj;
       const int ni = t % n_nets;
       const MfNet& P = batch.net[ni];
-      const int m0 = (t / n_nets) * TC_BLOCK_M;
+      const int m0 = item_m0(t);
       const int C1 = P.N1 / 128;
       const float* const bias_net = bias_s + ni * MF_MAX_BIAS;
       const int act = P.act;
@@ -501,6 +543,7 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp3_forward_kernel(const __gri
   }
 
   __syncthreads();
+  if (MC) cluster_sync_all();  // the peer may still multicast commits into this CTA's barriers until it is done too
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -528,7 +571,7 @@ int mlp3_forward_fused(int n, const rslrl_mlp3_fwd_t* nets, cudaStream_t st) {
     if ((q.precision == RSLRL_PREC_FP16) != f16) return -1;
     MfNet& P = b.net[i];
     bool ok = tc_make_map(&P.map_x, q.x, q.M, q.K0, q.ldx, 32, 128, true) &&
-              tc_make_map(&P.map_w1, (const float*)q.w[0], q.N1, q.K0, q.ldw0, 32, 128, true);
+              tc_make_map(&P.map_w1, (const float*)q.w[0], q.N1, q.K0, q.ldw0, 32, 64, true);
     if (f16) {
       // fp16 rows: 16-byte alignment = pitch % 8; N3 must fill whole 64-column granules
       if (q.N3 % 64 || q.N1 % 8 || q.N2 % 8 || ((uintptr_t)q.w[1] & 15) || ((uintptr_t)q.w[2] & 15) || ((uintptr_t)q.w[3] & 15))
@@ -536,8 +579,8 @@ int mlp3_forward_fused(int n, const rslrl_mlp3_fwd_t* nets, cudaStream_t st) {
       if (store)
         for (int l = 0; l < 3; ++l)
           if (((uintptr_t)q.h[l] & 15) || q.ldh[l] % 8) return -1;
-      ok = ok && tc_make_map16(&P.map_w2, q.w[1], q.N2, q.N1, q.N1, 64, q.N2) &&
-           tc_make_map16(&P.map_w3, q.w[2], q.N3, q.N2, q.N2, 64, q.N3) &&
+      ok = ok && tc_make_map16(&P.map_w2, q.w[1], q.N2, q.N1, q.N1, 64, q.N2 / 2) &&
+           tc_make_map16(&P.map_w3, q.w[2], q.N3, q.N2, q.N2, 64, q.N3 / 2) &&
            tc_make_map16(&P.map_w4, q.w[3], q.N4, q.N3, q.N3, 64, 16);
       if (ok && store)
         ok = tc_make_map16(&P.map_h1, q.h[0], q.M, q.N1, q.ldh[0], 64, 128) &&
@@ -545,8 +588,8 @@ int mlp3_forward_fused(int n, const rslrl_mlp3_fwd_t* nets, cudaStream_t st) {
              tc_make_map16(&P.map_h3, q.h[2], q.M, q.N3, q.ldh[2], 64, 128);
     } else {
       if (store && (!ok16(q.h[0], q.ldh[0]) || !ok16(q.h[1], q.ldh[1]) || !ok16(q.h[2], q.ldh[2]))) return -1;
-      ok = ok && tc_make_map(&P.map_w2, (const float*)q.w[1], q.N2, q.N1, q.N1, 32, q.N2, true) &&
-           tc_make_map(&P.map_w3, (const float*)q.w[2], q.N3, q.N2, q.N2, 32, q.N3, true) &&
+      ok = ok && tc_make_map(&P.map_w2, (const float*)q.w[1], q.N2, q.N1, q.N1, 32, q.N2 / 2, true) &&
+           tc_make_map(&P.map_w3, (const float*)q.w[2], q.N3, q.N2, q.N2, 32, q.N3 / 2, true) &&
            tc_make_map(&P.map_w4, (const float*)q.w[3], q.N4, q.N3, q.N3, 32, 16, true);
       if (ok && store)
         ok = tc_make_map(&P.map_h1, (const float*)q.h[0], q.M, q.N1, q.ldh[0], 32, 128, false) &&
@@ -561,22 +604,56 @@ int mlp3_forward_fused(int n, const rslrl_mlp3_fwd_t* nets, cudaStream_t st) {
     P.y = q.y; P.M = q.M; P.K0 = q.K0; P.N1 = q.N1; P.N2 = q.N2; P.N3 = q.N3; P.N4 = q.N4; P.ldy = q.ldy;
     P.act = q.act; P.store_h = store ? 1 : 0;
   }
-  static bool attr_set[2] = {false, false};
   const size_t smem = MF_W_STAGES * MF_W_STAGE_BYTES + MF_GRANULES * MF_GRANULE_BYTES + 2 * MF_MAX_BIAS * 4 +
                       (2 * MF_W_STAGES + 2 * MF_GRANULES + 6) * 8 + 16 + 1024;
-  if (!attr_set[f16]) {
-    cudaError_t e = f16 ? cudaFuncSetAttribute(mlp3_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                        : cudaFuncSetAttribute(mlp3_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // clusters of two CTAs with multicast weight loads: opt-in (RSLRL_MF_MULTICAST=1).  Measured on B200
+  // (profiles/experiments/notes/r1_mlp3_multicast.md): 53.3 us vs 51.2 us without - the per-SM ingest path, not the L2
+  // read bandwidth, bounds the weight stream, and multicast delivers the same bytes into every SM.
+  static const bool mc_env = [] { const char* e = getenv("RSLRL_MF_MULTICAST"); return e && e[0] == '1'; }();
+  const int tiles_m = (nets[0].M + TC_BLOCK_M - 1) / TC_BLOCK_M;
+  const bool mc = mc_env && (tc_num_sms() % 2 == 0);
+  using Kern = void (*)(const MfBatch, const int);
+  const Kern kern = f16 ? (mc ? (Kern)mlp3_forward_kernel<true, true> : (Kern)mlp3_forward_kernel<true, false>)
+                        : (mc ? (Kern)mlp3_forward_kernel<false, true> : (Kern)mlp3_forward_kernel<false, false>);
+  static bool attr_set[4] = {false, false, false, false};
+  const int ki = (f16 ? 2 : 0) + (mc ? 1 : 0);
+  if (!attr_set[ki]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
       return 1;
     }
-    attr_set[f16] = true;
+    attr_set[ki] = true;
   }
-  const int total = (nets[0].M + TC_BLOCK_M - 1) / TC_BLOCK_M * n;
-  const int grid = total < tc_num_sms() ? total : tc_num_sms();
-  if (f16) launch_chain_kernel(mlp3_forward_kernel<true>, dim3(grid), dim3(MF_THREADS), smem, st, b, n);
-  else launch_chain_kernel(mlp3_forward_kernel<false>, dim3(grid), dim3(MF_THREADS), smem, st, b, n);
+  if (mc) {
+    const int pairs = n * ((tiles_m + 1) / 2);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(tc_num_sms() / 2 * 2);
+    cfg.blockDim = dim3(MF_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    // persistent kernel: never more clusters than can be co-resident (GPCs with an odd SM count strand one SM each)
+    static int max_clusters[4] = {0, 0, 0, 0};
+    if (max_clusters[ki] == 0) {
+      int mcl = 0;
+      if (cudaOccupancyMaxActiveClusters(&mcl, kern, &cfg) != cudaSuccess || mcl < 1) mcl = tc_num_sms() / 2;
+      (void)cudaGetLastError();
+      max_clusters[ki] = mcl;
+    }
+    cfg.gridDim = dim3(2 * (pairs < max_clusters[ki] ? pairs : max_clusters[ki]));
+    cudaLaunchKernelEx(&cfg, kern, b, n);
+  } else {
+    const int total = tiles_m * n;
+    const int grid = total < tc_num_sms() ? total : tc_num_sms();
+    launch_chain_kernel(kern, dim3(grid), dim3(MF_THREADS), smem, st, b, n);
+  }
   return finish_launch(what);
 }
 
