@@ -64,7 +64,15 @@ def test_flat_param_group_views_and_rebinding():
     net = _toy()
     before = [p.detach().clone() for p in net.parameters()]
     g = FlatParamGroup(net.parameters(), "cpu")
-    assert g.numel % 4 == 0 and all(o % 4 == 0 for o in g.offsets)
+    # 32-byte tensor starts: float4 / TMA alignment in fp32 and 16 bytes in the fp16 weight shadow of the same offsets
+    assert g.numel % 8 == 0 and all(o % 8 == 0 for o in g.offsets)
+    assert g.values16 is None and g.shadow16_stale       # the shadow only exists in gemm_precision="fp16" mode
+    g.values16 = torch.zeros(g.numel, dtype=torch.float16)
+    for q in net.parameters():
+        v = g.shadow16(q)
+        assert v.shape == q.shape and v.data_ptr() % 16 == g.values16.data_ptr() % 16
+        assert (v.data_ptr() - g.values16.data_ptr()) // 2 == (q.data_ptr() - g.values.data_ptr()) // 4
+    g.values16 = None
     for p, b in zip(net.parameters(), before):
         assert torch.equal(p, b)
     assert g.is_bound()
