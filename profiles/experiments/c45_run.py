@@ -1,0 +1,62 @@
+"""BASELINE configs C4 (ActorCriticRecurrent, LSTM 256) and C5 (RND intrinsic reward + symmetry augmentation with mirror
+loss) at 4096 envs, 24 steps, on the seeded synthetic VecEnv: iteration time of the composite update path
+(PPO._update_composite: native GEMM / storage / GAE / trajectory / optimiser kernels under autograd, cuDNN LSTM cell).
+usage: python profiles/experiments/c45_run.py [c4|c5] [precision]"""
+import os, sys, io, contextlib, time
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
+import numpy as np
+import torch
+import bench
+from rsl_rl_b200.env import SynthVecEnv
+from rsl_rl_b200.runners import OnPolicyRunner
+
+which = sys.argv[1] if len(sys.argv) > 1 else "c4"
+prec = sys.argv[2] if len(sys.argv) > 2 else "tf32"
+dev, N = "cuda:0", 4096
+
+
+def _signed_perm(dim, device):
+    rng = np.random.default_rng(1000 + dim)
+    return (torch.as_tensor(rng.permutation(dim), device=device),
+            torch.as_tensor(rng.choice([-1.0, 1.0], size=dim), dtype=torch.float32, device=device))
+
+
+def _mirror(x):
+    perm, sign = _signed_perm(x.shape[-1], x.device)
+    return x[..., perm] * sign
+
+
+def mirror_augmentation(obs=None, actions=None, env=None):
+    obs_out = None
+    if obs is not None:
+        n = obs.batch_size[0]
+        obs_out = type(obs)({k: torch.cat([v, _mirror(v)], dim=0) for k, v in obs.items()}, batch_size=[2 * n])
+    return obs_out, (None if actions is None else torch.cat([actions, _mirror(actions)], dim=0))
+
+
+cfg = bench.train_cfg(prec)
+if which == "c4":
+    cfg["policy"].update(class_name="ActorCriticRecurrent", rnn_type="lstm", rnn_hidden_dim=256, rnn_num_layers=1)
+else:
+    cfg["obs_groups"]["rnd_state"] = ["policy"]
+    cfg["algorithm"]["rnd_cfg"] = dict(weight=1.0, weight_schedule=None, reward_normalization=False,
+                                       state_normalization=False, learning_rate=1e-3, num_outputs=1,
+                                       predictor_hidden_dims=[-1], target_hidden_dims=[-1])
+    cfg["algorithm"]["symmetry_cfg"] = dict(use_data_augmentation=True, use_mirror_loss=True, mirror_loss_coeff=0.5,
+                                            data_augmentation_func=mirror_augmentation)
+with contextlib.redirect_stdout(io.StringIO()):
+    env = SynthVecEnv(N, {"policy": 48}, 12, device=dev, seed=0)
+    runner = OnPolicyRunner(env, cfg, log_dir=None, device=dev)
+    runner.learn(2)
+torch.cuda.synchronize()
+runner.profile_phases = True
+K = 5
+t0 = time.perf_counter()
+with contextlib.redirect_stdout(io.StringIO()):
+    runner.learn(K)
+torch.cuda.synchronize()
+dt = (time.perf_counter() - t0) / K
+p = torch.cat([q.detach().reshape(-1) for q in runner.alg.policy.parameters()])
+print(f"{which.upper()} {prec} envs={N}: {dt*1e3:.1f} ms/iter, {N*24/dt/1e6:.2f} M env-steps/s, phases "
+      f"{ {k: round(v, 2) for k, v in runner.phase_times.items()} }, lr {runner.alg.learning_rate:.3e}, "
+      f"params finite {bool(torch.isfinite(p).all())}, fused path {runner.alg.fused}")
