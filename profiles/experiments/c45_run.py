@@ -15,10 +15,15 @@ prec = sys.argv[2] if len(sys.argv) > 2 else "tf32"
 dev, N = "cuda:0", 4096
 
 
-def _signed_perm(dim, device):
-    rng = np.random.default_rng(1000 + dim)
-    return (torch.as_tensor(rng.permutation(dim), device=device),
-            torch.as_tensor(rng.choice([-1.0, 1.0], size=dim), dtype=torch.float32, device=device))
+_cache = {}
+
+
+def _signed_perm(dim, device):   # built once per width: a function that uploads host data per call cannot be graph-captured
+    if dim not in _cache:
+        rng = np.random.default_rng(1000 + dim)
+        _cache[dim] = (torch.as_tensor(rng.permutation(dim), device=device),
+                       torch.as_tensor(rng.choice([-1.0, 1.0], size=dim), dtype=torch.float32, device=device))
+    return _cache[dim]
 
 
 def _mirror(x):
@@ -47,7 +52,7 @@ else:
 with contextlib.redirect_stdout(io.StringIO()):
     env = SynthVecEnv(N, {"policy": 48}, 12, device=dev, seed=0)
     runner = OnPolicyRunner(env, cfg, log_dir=None, device=dev)
-    runner.learn(2)
+    runner.learn(4)
 torch.cuda.synchronize()
 runner.profile_phases = True
 K = 5
@@ -59,4 +64,4 @@ dt = (time.perf_counter() - t0) / K
 p = torch.cat([q.detach().reshape(-1) for q in runner.alg.policy.parameters()])
 print(f"{which.upper()} {prec} envs={N}: {dt*1e3:.1f} ms/iter, {N*24/dt/1e6:.2f} M env-steps/s, phases "
       f"{ {k: round(v, 2) for k, v in runner.phase_times.items()} }, lr {runner.alg.learning_rate:.3e}, "
-      f"params finite {bool(torch.isfinite(p).all())}, fused path {runner.alg.fused}")
+      f"params finite {bool(torch.isfinite(p).all())}, fused path {runner.alg.fused}, composite graph {runner.alg._cgraph is not None}")

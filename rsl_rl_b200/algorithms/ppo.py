@@ -145,6 +145,8 @@ class PPO:
         if self.symmetry is not None:
             self._engine_reason = self._engine_reason or "symmetry"
         self._graph = None
+        self._cgraph, self._cgraph_key, self._cgraph_failed, self._cgraph_launches = None, None, False, 0
+        self._csums, self._cperm = None, None
         self._graph_failed = False
         self._graph_key = None
         self._graph_launches = 0
@@ -471,6 +473,7 @@ class PPO:
         `torch.distributed.destroy_process_group()`: the multi-GPU update graph holds NCCL work."""
         torch.cuda.synchronize()
         self._graph, self._graph_key = None, None
+        self._cgraph, self._cgraph_key = None, None
         for plan in self._act_plans.values():
             plan["graph"] = None
             plan["visits"] = 0
@@ -508,20 +511,86 @@ class PPO:
         this path has no per-minibatch host synchronisation either."""
         pol, st, opt = self.policy, self.storage, self.optimizer
         M, E = self.num_mini_batches, self.num_learning_epochs
-        gen = (st.recurrent_mini_batch_generator(M, E) if pol.is_recurrent else st.mini_batch_generator(M, E))
-        sums = torch.zeros(5, dtype=torch.float64, device=self.device)  # value, surrogate, entropy, rnd, symmetry
         self._group.ensure_bound()
-        self._group.zero_grad()
         if self.rnd:
             self._rnd_group.ensure_bound()
-            self._rnd_group.zero_grad()
             self.rnd_optimizer.dev_state.set_lr(self.rnd_optimizer.param_groups[0]["lr"])
         opt.dev_state.set_lr(self.learning_rate)
+        if self._csums is None:
+            self._csums = torch.zeros(5, dtype=torch.float64, device=self.device)  # value, surrogate, entropy, rnd, symmetry
+        sums = self._csums
+
+        # Feed-forward policies (RND / symmetry configurations): every shape is static and nothing returns to the host
+        # inside the minibatch loop, so the loop - gathers, forward, autograd backward, optimiser steps - is captured into
+        # ONE CUDA graph after two eager updates and replayed; only the permutation is drawn outside (copied into a
+        # static buffer).  A user augmentation function that cannot be captured (e.g. one that uploads host data on
+        # every call) makes the capture fail once: the update then stays eager.  Recurrent policies have data-dependent
+        # trajectory counts and stay eager.
+        graph_ok = (self.use_cuda_graph and not pol.is_recurrent and not self.is_multi_gpu and self._mb_hook is None
+                    and not self._cgraph_failed and os.environ.get("RSLRL_COMPOSITE_GRAPH", "1") != "0")
+        if graph_ok and self._eager_updates >= 2:
+            B = M * ((st.num_envs * st.num_transitions_per_env) // M)
+            perm = st._randperm(B)
+            if self._cperm is None:
+                self._cperm = torch.empty(B, dtype=torch.int64, device=self.device)
+            self._cperm.copy_(perm)
+            key = (self._hyper_key(), st.actions.data_ptr(), self._group.values.data_ptr(), B)
+            if self._cgraph is None or self._cgraph_key != key:
+                torch.cuda.synchronize()
+                steps = (opt._host_step, self.rnd_optimizer._host_step if self.rnd else 0)
+                before = nat.launch_count()
+                g = torch.cuda.CUDAGraph()
+                orig_randperm = st._randperm
+                st._randperm = lambda n: self._cperm
+                try:
+                    with torch.cuda.graph(g):
+                        self._composite_minibatches(sums)
+                    self._cgraph, self._cgraph_key = g, key
+                    self._cgraph_launches = nat.launch_count() - before
+                except Exception as exc:
+                    print(f"[rsl_rl_b200] composite update() could not be captured into a CUDA graph "
+                          f"({type(exc).__name__}: {exc}); running eagerly")
+                    self._cgraph_failed, self._cgraph = True, None
+                    torch.cuda.synchronize()
+                finally:
+                    st._randperm = orig_randperm
+                    nat.lib().rslrl_add_launch_count(-(nat.launch_count() - before) & 0xFFFFFFFFFFFFFFFF)
+                    opt._host_step = steps[0]
+                    if self.rnd:
+                        self.rnd_optimizer._host_step = steps[1]
+            if self._cgraph is not None:
+                self._cgraph.replay()
+                nat.lib().rslrl_add_launch_count(self._cgraph_launches)
+                opt._host_step += M * E
+                if self.rnd:
+                    self.rnd_optimizer._host_step += M * E
+                return self._composite_finish(sums)
+            st._randperm_once = perm   # capture failed: this update runs eagerly on the permutation already drawn
+        self._eager_updates += 1
+        self._composite_minibatches(sums)
+        return self._composite_finish(sums)
+
+    def _composite_minibatches(self, sums):
+        """The minibatch loop of the composite update (everything it puts on the stream is graph-capturable for
+        feed-forward policies)."""
+        pol, st, opt = self.policy, self.storage, self.optimizer
+        M, E = self.num_mini_batches, self.num_learning_epochs
+        once = getattr(st, "_randperm_once", None)
+        st._randperm_once = None
+        orig_randperm = st._randperm
+        if once is not None:   # reuse the permutation drawn before a failed capture (keeps the RNG stream aligned)
+            st._randperm = lambda n: once
+        gen = (st.recurrent_mini_batch_generator(M, E) if pol.is_recurrent else st.mini_batch_generator(M, E))
+        sums.zero_()
+        self._group.zero_grad()
+        if self.rnd:
+            self._rnd_group.zero_grad()
         adaptive = self.desired_kl is not None and self.schedule == "adaptive"
         clip = self.clip_param
 
         for (obs_b, actions_b, target_values_b, adv_b, returns_b, old_logp_b, old_mu_b, old_sigma_b, hid_b,
              masks_b) in gen:
+            st._randperm = orig_randperm   # the generator has drawn its permutation by now
             num_aug = 1
             original_batch_size = obs_b.batch_size[0]
             if self.normalize_advantage_per_mini_batch:
@@ -605,7 +674,9 @@ class PPO:
                 if symmetry_loss is not None:
                     sums[4] += symmetry_loss.detach()
 
-        n = E * M
+    def _composite_finish(self, sums):
+        opt, st = self.optimizer, self.storage
+        n = self.num_learning_epochs * self.num_mini_batches
         info = opt.dev_state.read()
         host = (sums / n).cpu().tolist()
         self.learning_rate = info["lr"]

@@ -84,3 +84,65 @@ def test_composite_learn_iterations_match_reference_golden(name):
             for k, v in alg.rnd.state_dict().items():
                 assert rel_err(v.cpu().numpy(), g[p + "final_rnd." + k]) < 5e-5, k
         assert alg.last_update_info["step"] == int(g[p + "adam.step"])
+
+
+def _small_rnd_sym_runner(aug, use_graph):
+    from rsl_rl_b200.env import SynthVecEnv
+    from rsl_rl_b200.runners import OnPolicyRunner
+    torch.manual_seed(0)
+    env = SynthVecEnv(256, {"policy": 16}, 4, device=DEV, seed=3)
+    cfg = dict(num_steps_per_env=8, save_interval=10 ** 9,
+               obs_groups={"policy": ["policy"], "critic": ["policy"], "rnd_state": ["policy"]},
+               policy=dict(class_name="ActorCritic", actor_hidden_dims=[64, 32], critic_hidden_dims=[64, 32],
+                           activation="elu", init_noise_std=1.0),
+               algorithm=dict(class_name="PPO", learning_rate=1e-3, num_learning_epochs=2, num_mini_batches=2,
+                              schedule="adaptive", desired_kl=0.01, use_cuda_graph=use_graph,
+                              rnd_cfg=dict(weight=1.0, weight_schedule=None, reward_normalization=False,
+                                           state_normalization=False, learning_rate=1e-3, num_outputs=1,
+                                           predictor_hidden_dims=[-1], target_hidden_dims=[-1]),
+                              symmetry_cfg=dict(use_data_augmentation=True, use_mirror_loss=True, mirror_loss_coeff=0.5,
+                                                data_augmentation_func=aug)))
+    return OnPolicyRunner(env, cfg, log_dir=None, device=DEV)
+
+
+def test_composite_update_cuda_graph_matches_eager_and_falls_back():
+    """Feed-forward composite update (RND + symmetry): the minibatch loop replayed from one CUDA graph gives the same
+    parameters as the eager loop; an augmentation function that cannot be captured (uploads host data on every call)
+    falls back to eager instead of failing."""
+    from oracle.symmetry_example import mirror_augmentation as uploading_aug   # builds its index tensors from numpy per call
+    cache = {}
+
+    def cached_aug(obs=None, actions=None, env=None):
+        def mirror(x):
+            d = x.shape[-1]
+            if d not in cache:
+                g = torch.Generator().manual_seed(100 + d)
+                cache[d] = (torch.randperm(d, generator=g).to(DEV), (torch.randint(0, 2, (d,), generator=g) * 2 - 1).float().to(DEV))
+            perm, sign = cache[d]
+            return x[..., perm] * sign
+        obs_out = None
+        if obs is not None:
+            n = obs.batch_size[0]
+            obs_out = type(obs)({k: torch.cat([v, mirror(v)], dim=0) for k, v in obs.items()}, batch_size=[2 * n])
+        return obs_out, (None if actions is None else torch.cat([actions, mirror(actions)], dim=0))
+
+    finals = {}
+    for mode in ("eager", "graph"):
+        runner = _small_rnd_sym_runner(cached_aug, mode == "graph")
+        torch.manual_seed(5)
+        runner.learn(5)
+        alg = runner.alg
+        assert not alg.fused
+        assert (alg._cgraph is not None) == (mode == "graph")
+        finals[mode] = (torch.cat([q.detach().reshape(-1) for q in alg.policy.parameters()]).cpu().numpy(),
+                        alg.learning_rate, alg.last_update_info["step"])
+    assert finals["eager"][2] == finals["graph"][2] == 5 * 2 * 2
+    assert abs(finals["eager"][1] - finals["graph"][1]) < 1e-15
+    assert rel_err(finals["graph"][0], finals["eager"][0]) < 1e-4
+    # fallback
+    runner = _small_rnd_sym_runner(uploading_aug, True)
+    runner.learn(4)
+    alg = runner.alg
+    assert alg._cgraph is None and alg._cgraph_failed
+    p = torch.cat([q.detach().reshape(-1) for q in alg.policy.parameters()])
+    assert bool(torch.isfinite(p).all()) and alg.last_update_info["step"] == 4 * 2 * 2
