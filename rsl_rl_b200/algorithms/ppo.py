@@ -111,8 +111,9 @@ class PPO:
         self.policy.to(self.device)
         self.policy.set_gemm_precision(gemm_precision)
         if self.rnd is not None:
-            self.rnd.predictor.precision = gemm_precision
-            self.rnd.target.precision = gemm_precision
+            # (MLPs called under autograd have no fp16-storage variant: tensor cores there mean tf32)
+            self.rnd.predictor.precision = "tf32" if gemm_precision == "fp16" else gemm_precision
+            self.rnd.target.precision = "tf32" if gemm_precision == "fp16" else gemm_precision
         self._group = FlatParamGroup(self.policy.parameters(), self.device)
         self.optimizer = FusedAdam(self._group, lr=learning_rate)
         if self.is_multi_gpu and os.environ.get("RSLRL_ALLREDUCE", "p2p") == "p2p":
@@ -139,11 +140,10 @@ class PPO:
         self.use_cuda_graph = use_cuda_graph
         self.rng_compat = rng_compat
         self._engine = None
+        # the fused engine drives the ROLLOUT of every feed-forward ActorCritic; the UPDATE additionally needs the plain
+        # PPO objective (RND / symmetry go through the composite update on the same parameters)
         self._engine_reason = _engine.supports(self.policy)
-        if self.rnd is not None:
-            self._engine_reason = self._engine_reason or "RND"
-        if self.symmetry is not None:
-            self._engine_reason = self._engine_reason or "symmetry"
+        self._update_reason = "RND" if self.rnd is not None else ("symmetry" if self.symmetry is not None else None)
         self._graph = None
         self._cgraph, self._cgraph_key, self._cgraph_failed, self._cgraph_launches = None, None, False, 0
         self._csums, self._cperm = None, None
@@ -178,12 +178,24 @@ class PPO:
         if self._engine_reason is None:
             B = num_envs * num_transitions_per_env
             mb = B // self.num_mini_batches
-            self._engine = _engine.FeedForwardEngine(self.policy, B, num_envs, mb, self.device, self.gemm_precision,
-                                                     self._group)
-            self._alloc_update_buffers(num_envs, num_transitions_per_env)
+            precision = self.gemm_precision
+            if self._update_reason is not None and precision == "fp16":
+                precision = "tf32"   # the composite update runs the MLPs under autograd (tf32 tensor cores there)
+            self._engine = _engine.FeedForwardEngine(self.policy, B if self._update_reason is None else num_envs, num_envs,
+                                                     mb if self._update_reason is None else num_envs, self.device,
+                                                     precision, self._group)
+            self._last_values = torch.empty(num_envs, 1, dtype=torch.float32, device=self.device)
+            if self._update_reason is None:
+                self._alloc_update_buffers(num_envs, num_transitions_per_env)
 
     @property
     def fused(self) -> bool:
+        """update() runs on the fused feed-forward engine."""
+        return self._engine is not None and self._update_reason is None
+
+    @property
+    def rollout_fused(self) -> bool:
+        """act() / process_env_step() / compute_returns() run on the fused engine (any feed-forward ActorCritic)."""
         return self._engine is not None
 
     # ------------------------------------------------------------------------------------------
@@ -199,7 +211,7 @@ class PPO:
 
     def act(self, obs):
         """Reference ppo.py:129-140."""
-        if not self.fused:
+        if not self.rollout_fused:
             return self._act_composite(obs)
         st, eng, tr = self.storage, self._engine, self.transition
         s = st.step
@@ -299,7 +311,7 @@ class PPO:
             self.intrinsic_rewards = self.rnd.get_intrinsic_reward(obs)
             intrinsic = self.intrinsic_rewards
         time_outs = extras["time_outs"] if "time_outs" in extras else None
-        if self.fused and tr.actions is not None and tr.actions.data_ptr() == self.storage.actions[self.storage.step].data_ptr():
+        if self.rollout_fused and tr.actions is not None and tr.actions.data_ptr() == self.storage.actions[self.storage.step].data_ptr():
             self.storage._store_in_place(tr.observations, rewards, dones, time_outs, intrinsic, self.gamma)
         else:
             self.storage._store(tr, time_outs=time_outs, intrinsic=intrinsic, gamma=self.gamma)
@@ -308,7 +320,7 @@ class PPO:
 
     def compute_returns(self, obs):
         """Reference ppo.py:171-176."""
-        if self.fused:
+        if self.rollout_fused:
             _, x_c = self._inputs(obs)
             last_values = self._last_values
             self._engine.forward(x_c, x_c, None, last_values, actor=False)
@@ -339,7 +351,6 @@ class PPO:
         self._p_ret = torch.empty(Bp, **f32)
         self._p_logp = torch.empty(Bp, **f32)
         self._perm = torch.empty(Bp, dtype=torch.int64, device=dev)
-        self._last_values = torch.empty(N, 1, **f32)
         self._discard = torch.empty(self._mb, A, **f32)
         if self._engine.f16:   # fp16 copies of the permuted observations: the B operand of the first layer's wgrad
             pad8 = lambda d: (d + 7) // 8 * 8
