@@ -74,7 +74,8 @@ ppo_loss_kernel(const float* __restrict__ mu, const float* __restrict__ std_para
                 const double* __restrict__ adv_stats, float* __restrict__ dmu, int dmu_stride,
                 float* __restrict__ dvalue, int dvalue_stride, float* dstd, float* db_mu, float* db_value,
                 float* kl_out, double* loss_sums, LossWorkspace* ws, long long rows, long long mb_orig,
-                int A, float clip, float c_v, float c_e, int use_clipped) {
+                int A, float clip, float c_v, float c_e, int use_clipped, __half* __restrict__ dmu16, int dmu16_stride,
+                __half* __restrict__ dvalue16, int dvalue16_stride, float scale16) {
   pdl_trigger();
   pdl_wait();
   __shared__ float s_sigma[kMaxActions], s_logs[kMaxActions], s_2var[kMaxActions];
@@ -178,6 +179,7 @@ ppo_loss_kernel(const float* __restrict__ mu, const float* __restrict__ std_para
       dv_out = c_v * g * (-2.f) * e;
     }
     dvalue[i * dvalue_stride] = dv_out;
+    if (dvalue16 != nullptr) dvalue16[i * dvalue16_stride] = __float2half_rn(dv_out * scale16);
     dv_sum = dv_out;
   }
 
@@ -214,6 +216,13 @@ ppo_loss_kernel(const float* __restrict__ mu, const float* __restrict__ std_para
       if (valid) {
         if (VEC) *(float4*)(dm + c) = make_float4(o[0], o[1], o[2], o[3]);
         else for (int q = 0; q < nq; ++q) dm[c + q] = o[q];
+        if (VEC && dmu16 != nullptr) {  // scaled fp16 copy (A % 4 == 0): the A operand of the fp16 output-layer backward
+          const __half2 lo2 = __floats2half2_rn(o[0] * scale16, o[1] * scale16), hi2 = __floats2half2_rn(o[2] * scale16, o[3] * scale16);
+          uint2 w;
+          w.x = *(const unsigned int*)&lo2;
+          w.y = *(const unsigned int*)&hi2;
+          *(uint2*)(dmu16 + i * dmu16_stride + c) = w;
+        }
       }
     }
   }
@@ -534,7 +543,9 @@ int rslrl_ppo_loss_fwd_bwd(const float* mu, const float* std_param, int std_type
                       (uintptr_t)dmu) & 15) == 0);
   static const bool quad_ok = [] { const char* e = getenv("RSLRL_LOSS_QUAD"); return !(e && e[0] == '0'); }();
   RSLRL_CHECK_ARG(dmu16 == nullptr || (dmu16_stride % 4 == 0 && ((uintptr_t)dmu16 & 7) == 0), what);
-  if (vec && A <= 16 && quad_ok) {  // four threads per row
+  // four threads per row while a thread per row could not fill the machine (measured at 393 216 rows: 58 us for the
+  // row-per-thread kernel, 80 us for this one); beyond that the row-per-thread kernel
+  if (vec && A <= 16 && quad_ok && rows <= (long long)kNumSMs * 1024) {
     const int qblocks = (int)((rows + kQuadThreads / 4 - 1) / (kQuadThreads / 4));
     launch_chain_kernel(
         ppo_loss_quad_kernel, dim3(qblocks), dim3(kQuadThreads), 0, (cudaStream_t)stream, mu, std_param, std_type, value,
@@ -544,8 +555,8 @@ int rslrl_ppo_loss_fwd_bwd(const float* mu, const float* std_param, int std_type
         (__half*)dmu16, dmu16_stride, (__half*)dvalue16, dvalue16_stride, (float)grad_scale16);
     return finish_launch(what);
   }
-  if (dmu16 != nullptr || dvalue16 != nullptr) {
-    set_error("%s: fp16 gradient outputs need A %% 4 == 0, A <= 16 and 16-byte aligned rows", what);
+  if ((dmu16 != nullptr || dvalue16 != nullptr) && !vec) {
+    set_error("%s: fp16 gradient outputs need A %% 4 == 0 and 16-byte aligned rows", what);
     return 4;
   }
   auto kern = vec ? ppo_loss_kernel<true> : ppo_loss_kernel<false>;
@@ -553,7 +564,8 @@ int rslrl_ppo_loss_fwd_bwd(const float* mu, const float* std_param, int std_type
       kern, dim3(blocks), dim3(kLossThreads), 0, (cudaStream_t)stream, mu, std_param, std_type, value, actions, old_logp, advantages, returns, old_values, old_mu, old_sigma, adv_stats,
       dmu, dmu_stride, dvalue, dvalue_stride, dstd, db_mu, db_value, kl_out, loss_sums, (LossWorkspace*)workspace, (long long)rows,
       (long long)mb_orig, A, (float)clip_param,
-      (float)value_loss_coef, (float)entropy_coef, use_clipped_value_loss);
+      (float)value_loss_coef, (float)entropy_coef, use_clipped_value_loss, (__half*)dmu16, dmu16_stride, (__half*)dvalue16,
+      dvalue16_stride, (float)grad_scale16);
   return finish_launch(what);
 }
 

@@ -331,7 +331,8 @@ def test_ppo_loss_against_reference_autograd(tag):
     assert abs(sums[2] - float(f("entropy"))) < 1e-5 * abs(float(f("entropy")))
 
 
-@pytest.mark.parametrize("A,std_type,rows,aug", [(12, 0, 24576, 1), (12, 1, 5000, 1), (7, 0, 999, 1), (12, 0, 4096, 2)])
+@pytest.mark.parametrize("A,std_type,rows,aug", [(12, 0, 24576, 1), (12, 1, 5000, 1), (7, 0, 999, 1), (12, 0, 4096, 2),
+                                                 (12, 0, 160000, 1)])   # > 148 * 1024 rows: the row-per-thread kernel
 def test_ppo_loss_against_oracle(A, std_type, rows, aug):
     rng = np.random.default_rng(rows + A)
     mb = rows
