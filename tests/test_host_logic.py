@@ -113,3 +113,24 @@ def test_fused_adam_is_a_torch_adam_with_compatible_state_dict():
     g.grads.normal_()
     opt.step()
     assert g.is_bound()
+
+
+def test_fp16_storage_has_the_operand_precision_of_tf32():
+    """within fp16's normal range a value stored as fp16 carries the same 10-bit mantissa the tensor core
+    keeps of a tf32 operand (relative rounding error <= 2^-11 for both), and the power-of-two gradient scale of the
+    fp16 path is exact."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal(200000) * np.exp(rng.uniform(-6, 6, 200000))).astype(np.float32)
+    x = x[(np.abs(x) > 6.2e-5) & (np.abs(x) < 6.0e4)]                      # fp16 normal range
+    f16 = x.astype(np.float16).astype(np.float32)
+    u = x.view(np.uint32)
+    tf32 = ((u + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)   # round-to-nearest tf32 (ties away)
+    rel16 = np.abs(f16 - x) / np.abs(x)
+    rel32 = np.abs(tf32 - x) / np.abs(x)
+    assert rel16.max() <= 2.0 ** -11 and rel32.max() <= 2.0 ** -11
+    ties = (u & np.uint32(0x1FFF)) == np.uint32(0x1000)                    # the two roundings only differ on exact ties
+    assert np.array_equal(f16[~ties], tf32[~ties])
+    S = np.float32(2.0 ** 15)
+    g = (rng.standard_normal(1000) * 1e-5).astype(np.float32)
+    assert np.array_equal((g * S) / S, g)                                  # scaling by a power of two is exact
