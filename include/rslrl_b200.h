@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define RSLRL_ABI_VERSION 1
+#define RSLRL_ABI_VERSION 2
 #define RSLRL_MAX_SEGMENTS 16 /* max obs groups / gather fields per launch */
 #define RSLRL_MAX_PROBLEMS 8  /* max GEMM problems grouped into one launch (fp16 wgrad: 4 layers x actor, critic) */
 
@@ -166,6 +166,16 @@ typedef struct {
   int act;           /* RSLRL_ACT_* of the three hidden layers */
   int precision;     /* RSLRL_PREC_TF32 (0 is read as TF32) or RSLRL_PREC_FP16: layer 1 always runs in tf32 on the
                         fp32 x / w[0]; layers 2-4 consume the on-chip activations as tf32 or fp16 */
+  /* Optional Gaussian policy head fused into the output epilogue (PPO.act, rsl_rl/algorithms/ppo.py:129-140 ->
+   * modules/actor_critic.py:130-146): with head_z != NULL the N4 outputs y = mu are also turned into
+   *   head_actions[M,N4] = head_z * sigma + mu,  head_logp[M] = sum log N(actions; mu, sigma),  head_sigma[M,N4] = sigma
+   * (sigma from head_std[N4] as in rslrl_gaussian_act; same arithmetic, bit for bit).  head_sigma may be NULL. */
+  const float* head_z;
+  const float* head_std;
+  int head_std_type;
+  float* head_actions;
+  float* head_logp;
+  float* head_sigma;
 } rslrl_mlp3_fwd_t;
 
 /* Each call runs `n` independent problems (e.g. actor and critic) in one launch; *_host arrays live
@@ -182,6 +192,13 @@ int rslrl_linear_backward_head(int n, const rslrl_linear_bwd_head_t* probs_host,
 /* Returns 4 when a net's shape is not eligible (N1 in 128..512 step 128, N2 in {128,256}, N3 <= 128 step 32,
  * N4 <= 16, 16-byte aligned rows, same M for all nets): the caller then runs the layers one by one. */
 int rslrl_mlp3_forward(int n, const rslrl_mlp3_fwd_t* nets_host, rslrl_stream_t stream);
+/* Launch plan of rslrl_mlp3_forward for the rollout (PPO.act is called once per env step with new observation
+ * pointers but otherwise identical arguments): create() validates the nets and encodes every TMA descriptor once;
+ * run() only re-encodes the descriptor of an input whose pointer changed (x_host[i] replaces nets[i].x) and launches.
+ * Weight / bias / output pointers are captured by value: re-create the plan when they move. */
+int rslrl_mlp3_plan_create(int n, const rslrl_mlp3_fwd_t* nets_host, void** plan_out);
+int rslrl_mlp3_plan_run(void* plan, const float* const* x_host, rslrl_stream_t stream);
+void rslrl_mlp3_plan_destroy(void* plan);
 
 /* ---- PPO objective (rsl_rl/algorithms/ppo.py:255-315), forward + hand-derived backward ---------- */
 

@@ -23,6 +23,7 @@ PREC_FP32, PREC_TF32, PREC_FP16 = 0, 1, 2
 PREC_CODES = {"fp32": PREC_FP32, "tf32": PREC_TF32, "fp16": PREC_FP16}
 STD_SCALAR, STD_LOG = 0, 1
 MAX_SEGMENTS, MAX_PROBLEMS = 16, 8
+ABI_VERSION = 2   # RSLRL_ABI_VERSION of include/rslrl_b200.h
 
 
 class LinearFwd(C.Structure):
@@ -50,7 +51,10 @@ class LinearBwdHead(C.Structure):
 class Mlp3Fwd(C.Structure):
     _fields_ = [("x", c_void_p), ("w", c_void_p * 4), ("b", c_void_p * 4), ("h", c_void_p * 3), ("y", c_void_p),
                 ("M", c_int), ("K0", c_int), ("N1", c_int), ("N2", c_int), ("N3", c_int), ("N4", c_int),
-                ("ldx", c_int), ("ldw0", c_int), ("ldh", c_int * 3), ("ldy", c_int), ("act", c_int), ("precision", c_int)]
+                ("ldx", c_int), ("ldw0", c_int), ("ldh", c_int * 3), ("ldy", c_int), ("act", c_int), ("precision", c_int),
+                # optional Gaussian policy head fused into the output epilogue (rollout)
+                ("head_z", c_void_p), ("head_std", c_void_p), ("head_std_type", c_int), ("head_actions", c_void_p),
+                ("head_logp", c_void_p), ("head_sigma", c_void_p)]
 
 
 class OptState(C.Structure):
@@ -82,6 +86,9 @@ _SIGNATURES = {
     "rslrl_linear_backward_weight": (c_int, [c_int, c_void_p, c_int, c_void_p]),
     "rslrl_linear_backward_head": (c_int, [c_int, c_void_p, c_void_p]),
     "rslrl_mlp3_forward": (c_int, [c_int, c_void_p, c_void_p]),
+    "rslrl_mlp3_plan_create": (c_int, [c_int, c_void_p, C.POINTER(c_void_p)]),
+    "rslrl_mlp3_plan_run": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "rslrl_mlp3_plan_destroy": (None, [c_void_p]),
     "rslrl_loss_workspace_bytes": (c_i64, []),
     "rslrl_sum_sumsq": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_void_p]),
     "rslrl_optim_workspace_bytes": (c_i64, [c_i64]),
@@ -137,7 +144,7 @@ def lib():
             fn = getattr(handle, name)  # AttributeError here == header/library mismatch
             fn.restype = res
             fn.argtypes = args
-        if handle.rslrl_abi_version() != 1:
+        if handle.rslrl_abi_version() != ABI_VERSION:
             raise RuntimeError("rsl_rl_b200: ABI version mismatch between _native.py and the shared library")
         _lib = handle
     return _lib

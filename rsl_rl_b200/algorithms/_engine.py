@@ -41,6 +41,35 @@ class _Net:
         self.L = len(self.layers)
 
 
+class _Mlp3Plan:
+    """Owner of a `rslrl_mlp3_plan_*` handle; call it with one input pointer per net."""
+
+    def __init__(self, structs, n: int):
+        import ctypes as C
+
+        self._lib = nat.lib()
+        self._handle = C.c_void_p()
+        nat.check(self._lib.rslrl_mlp3_plan_create(n, structs, C.byref(self._handle)))
+        self._xs = (C.c_void_p * n)()
+        self._run = self._lib.rslrl_mlp3_plan_run
+
+    def __call__(self, *x_ptrs: int):
+        xs = self._xs
+        for i, p in enumerate(x_ptrs):
+            xs[i] = p
+        rc = self._run(self._handle, xs, nat.stream_ptr())
+        if rc != 0:
+            nat.check(rc)
+
+    def __del__(self):
+        h, self._handle = getattr(self, "_handle", None), None
+        if h:
+            try:
+                self._lib.rslrl_mlp3_plan_destroy(h)
+            except Exception:
+                pass
+
+
 def supports(policy) -> Optional[str]:
     """None if the fused feed-forward engine can drive `policy`, else the reason it cannot."""
     from ..modules.actor_critic import ActorCritic
@@ -275,6 +304,20 @@ class FeedForwardEngine:
                 check(fn(n, arr, prec, st))
 
         return run
+
+    def build_act_plan(self, M: int, ld_a: int, ld_c: int, mu_out, v_out, z, actions_out, logp_out, sigma_out):
+        """One-launch rollout step (fused forward of actor + critic with the Gaussian policy head in the actor's output
+        epilogue): a C-side launch plan with every TMA descriptor pre-encoded; returns callable(xa_ptr, xc_ptr).  None
+        when the fused forward does not cover this policy / input layout."""
+        if not (self.fused_fwd and ld_a % 4 == 0 and ld_c % 4 == 0):
+            return None
+        sa = self._mlp3("a", 0, ld_a, M, mu_out, store=False)
+        sc = self._mlp3("c", 0, ld_c, M, v_out, store=False)
+        sa.head_z, sa.head_std, sa.head_std_type = z.data_ptr(), self.std_param.data_ptr(), self.std_type
+        sa.head_actions, sa.head_logp, sa.head_sigma = actions_out.data_ptr(), logp_out.data_ptr(), nat.ptr(sigma_out)
+        sa.x = sc.x = z.data_ptr()   # placeholder (any valid 16-byte aligned pointer): run() patches the real inputs
+        arr = (nat.Mlp3Fwd * 2)(sa, sc)
+        return _Mlp3Plan(arr, 2)
 
     def backward(self, x_a: torch.Tensor, x_c: torch.Tensor, dmu: torch.Tensor, dvalue: torch.Tensor):
         """dL/dW, dL/db accumulated into the parameters' .grad views (flat gradient buffer).  fp16 mode: x_a / x_c are

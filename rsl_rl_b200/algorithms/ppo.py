@@ -153,6 +153,8 @@ class PPO:
         self._eager_updates = 0
         self._act_plans = {}
         self._act_in = None
+        self._lineup = None
+        self._draw_offset = None   # Philox offset consumed by one discarded torch.normal draw in update()
         self._mb_hook = None  # test hook: called after every minibatch backward in eager mode
         self.last_update_info = {}
 
@@ -223,41 +225,31 @@ class PPO:
         key = (x_a.stride(0), x_c.stride(0), x_a.shape[1], x_c.shape[1], self._group.values.data_ptr())
         plan = self._act_plans.get(s)
         if plan is None or plan["key"] != key:
-            self._group.ensure_bound()
-            nat.require_cuda(x_a, x_c)
-            views = (st.mu[s], st.values[s], st.actions[s], st.actions_log_prob[s], st.sigma[s])
-            if self._act_in is None or self._act_in[0].shape != x_a.shape or self._act_in[1].shape != x_c.shape:
-                with torch.inference_mode(False):  # plain tensors: act() may also be called outside inference mode
-                    pad4 = lambda d: (d + 3) // 4 * 4
-                    z = lambda t: torch.zeros(t.shape[0], pad4(t.shape[1]), dtype=torch.float32,
-                                              device=t.device)[:, :t.shape[1]]      # 16-byte row pitch, zero pad
-                    sa = z(x_a)
-                    sc = sa if x_c.data_ptr() == x_a.data_ptr() else z(x_c)
-                    self._act_in = (sa, sc, torch.empty(views[0].shape, dtype=torch.float32, device=x_a.device))
-            sa, sc, _ = self._act_in
-            plan = dict(key=key, views=views, graph=None, launches=0, visits=0,
-                        fwd=eng.build_forward_plan(st.num_envs, x_a.stride(0), x_c.stride(0), views[0], views[1]),
-                        fwd_static=eng.build_forward_plan(st.num_envs, sa.stride(0), sc.stride(0), views[0], views[1]))
-            self._act_plans[s] = plan
+            plan = self._build_act_plan(s, x_a, x_c, key)
         mu_s, val_s, act_s, logp_s, sig_s = plan["views"]
         sa, sc, zbuf = self._act_in
         if self.policy._noise_fn is not None:
             zbuf.copy_(self.policy._noise_fn(mu_s))
         else:
             zbuf.normal_()  # same draw as torch.normal(mean, std): normal_(0,1) on a tensor of mu's shape
-        if not (self.use_cuda_graph and _ACT_GRAPH):
-            if eng.f16 and not eng._fused_inputs_ok(x_a, x_c):
-                # the fp16 path has only the fused forward: rows that are not 16-byte aligned go through the padded
-                # static input buffers
+        one = plan["one_launch"]
+        if one is not None:
+            # ONE launch per env step: fused forward of both nets, Gaussian head in the actor's output epilogue, results
+            # written straight into row s of the rollout buffer.  Observations are read in place when their rows are
+            # 16-byte aligned, otherwise through the zero-padded staging buffers.
+            if plan["direct"] and x_a.data_ptr() % 16 == 0 and x_c.data_ptr() % 16 == 0:
+                one(x_a.data_ptr(), x_c.data_ptr())
+            else:
                 sa.copy_(x_a)
                 if sc is not sa:
                     sc.copy_(x_c)
-                plan["fwd_static"](sa.data_ptr(), sc.data_ptr())
-            else:
-                plan["fwd"](x_a.data_ptr(), x_c.data_ptr())
+                plan["one_static"](sa.data_ptr(), sc.data_ptr())
+        elif not (self.use_cuda_graph and _ACT_GRAPH):
+            plan["fwd"](x_a.data_ptr(), x_c.data_ptr())
             eng.gaussian_head(mu_s, zbuf, act_s, logp_s, sig_s)
         else:
-            # forward + Gaussian head of step s replayed from a CUDA graph reading static input buffers
+            # layer-by-layer forward (fp32 mode / shapes the fused forward does not cover) + Gaussian head of step s
+            # replayed from a CUDA graph reading static input buffers
             sa.copy_(x_a)
             if sc is not sa:
                 sc.copy_(x_c)
@@ -285,6 +277,32 @@ class PPO:
         tr.observations = obs
         self.policy._mean, self.policy._std = tr.action_mean, tr.action_sigma
         return tr.actions
+
+    def _build_act_plan(self, s, x_a, x_c, key):
+        st, eng = self.storage, self._engine
+        self._group.ensure_bound()
+        nat.require_cuda(x_a, x_c)
+        views = (st.mu[s], st.values[s], st.actions[s], st.actions_log_prob[s], st.sigma[s])
+        if self._act_in is None or self._act_in[0].shape != x_a.shape or self._act_in[1].shape != x_c.shape:
+            with torch.inference_mode(False):  # plain tensors: act() may also be called outside inference mode
+                pad4 = lambda d: (d + 3) // 4 * 4
+                z = lambda t: torch.zeros(t.shape[0], pad4(t.shape[1]), dtype=torch.float32,
+                                          device=t.device)[:, :t.shape[1]]      # 16-byte row pitch, zero pad
+                sa = z(x_a)
+                sc = sa if x_c.data_ptr() == x_a.data_ptr() else z(x_c)
+                self._act_in = (sa, sc, torch.empty(views[0].shape, dtype=torch.float32, device=x_a.device))
+        sa, sc, zbuf = self._act_in
+        N = st.num_envs
+        direct = x_a.stride(0) % 4 == 0 and x_c.stride(0) % 4 == 0 and x_a.stride(1) == 1 and x_c.stride(1) == 1
+        one = eng.build_act_plan(N, x_a.stride(0), x_c.stride(0), *views[:2], zbuf, *views[2:]) if direct else None
+        one_static = eng.build_act_plan(N, sa.stride(0), sc.stride(0), *views[:2], zbuf, *views[2:])
+        plan = dict(key=key, views=views, graph=None, launches=0, visits=0, direct=direct and one is not None,
+                    one_launch=one if one is not None else one_static, one_static=one_static, fwd=None, fwd_static=None)
+        if one_static is None:   # no fused forward for this policy / precision: layer-by-layer launch plans
+            plan["fwd"] = eng.build_forward_plan(N, x_a.stride(0), x_c.stride(0), views[0], views[1])
+            plan["fwd_static"] = eng.build_forward_plan(N, sa.stride(0), sc.stride(0), views[0], views[1])
+        self._act_plans[s] = plan
+        return plan
 
     def _act_composite(self, obs):
         tr = self.transition
@@ -439,8 +457,7 @@ class PPO:
         perm = st._randperm(M * self._mb)
         self._perm.copy_(perm)
         if self.rng_compat:  # the reference's policy.act() inside update() draws (and discards) a sample per minibatch
-            for _ in range(M * E):
-                self._discard.normal_()
+            self._skip_discarded_draws(M * E)
         opt.dev_state.set_lr(self.learning_rate)
 
         # multi-GPU: the per-minibatch NCCL all-reduce is captured with the kernels (NCCL collectives are graph
@@ -479,6 +496,20 @@ class PPO:
         opt._host_step += M * E
         return self._finish_update()
 
+    def _skip_discarded_draws(self, count: int):
+        """Advances the CUDA generator exactly as `count` calls of `torch.normal(mean, std)` on a [minibatch, A] mean
+        would (reference ppo.py:249 -> actor_critic.py:140): the Philox offset one such call consumes is measured once
+        with a real `normal_()` launch, after which the stream is advanced arithmetically -- no launches."""
+        idx = torch.device(self.device).index
+        gen = torch.cuda.default_generators[torch.cuda.current_device() if idx is None else idx]
+        if self._draw_offset is None:
+            before = gen.get_offset()
+            self._discard.normal_()
+            self._draw_offset = gen.get_offset() - before
+            count -= 1
+        if count > 0:
+            gen.set_offset(gen.get_offset() + self._draw_offset * count)
+
     def release_graphs(self):
         """Drops the captured CUDA graphs (update() and the per-step act() graphs).  Call it before
         `torch.distributed.destroy_process_group()`: the multi-GPU update graph holds NCCL work."""
@@ -506,6 +537,13 @@ class PPO:
 
     def update(self):
         """Reference ppo.py:178-422."""
+        if self.is_multi_gpu and self.optimizer.peer_allreduce:
+            # Line the ranks up on the stream before the first peer-memory step: rank 0 alone saves checkpoints and
+            # logs between iterations, and the in-kernel flag wait should only ever see kernel-level skew (NCCL simply
+            # waits; no host synchronisation here).
+            if self._lineup is None:
+                self._lineup = torch.zeros(1, dtype=torch.int32, device=self.device)
+            torch.distributed.all_reduce(self._lineup)
         if self.fused:
             return self._update_fused()
         return self._update_composite()

@@ -16,6 +16,7 @@
 // With world == 1 the flag phases vanish and the kernel is clip + KL-LR + Adam in one launch instead of two.
 // All scalars stay on the device (rslrl_opt_state_t); the kernel is CUDA-graph capturable (epoch in device memory).
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -45,6 +46,7 @@ struct ArParams {
   ArWorkspace* ws;
   int world, rank, adaptive, round_lr_fp32, use_kl, zero_grad;
   double max_norm, desired_kl, beta1, beta2, eps;
+  long long timeout_cycles;  // spin limit of the peer / grid waits (RSLRL_PEER_TIMEOUT_S, default 30 min)
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
@@ -71,11 +73,14 @@ __device__ __forceinline__ float ld_volatile_f(const float* p) {
   return v;
 }
 
-// bounded spin (a dead peer traps this rank instead of hanging its GPU)
-__device__ __forceinline__ void wait_flag(const unsigned int* flag, unsigned int stamp) {
+// Spin on a peer's flag.  Ordinary rank skew (rank 0 saving a checkpoint, logging) must simply be waited out, as NCCL
+// does; the limit only turns a DEAD peer into a reported trap instead of a hung GPU.  It is configurable
+// (RSLRL_PEER_TIMEOUT_S, default 1800 s) and PPO.update() additionally lines the ranks up with one NCCL collective
+// before the first peer step, so the spin never sees more than kernel-level skew.
+__device__ __forceinline__ void wait_flag(const unsigned int* flag, unsigned int stamp, long long limit) {
   const long long t0 = clock64();
   while ((int)(ld_acquire_sys(flag) - stamp) < 0) {
-    if (clock64() - t0 > 8000000000LL) {
+    if (clock64() - t0 > limit) {
       printf("rslrl allreduce_clip_adam: peer flag timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
       __trap();
     }
@@ -115,7 +120,7 @@ __global__ void __launch_bounds__(kArThreads, 1) allreduce_clip_adam_kernel(cons
     if (tid < W && tid != rank) {
       __threadfence_system();
       st_release_sys(prm.peer_flags[tid] + (0 * kArMaxBlocks + b) * kArMaxWorld + rank, stamp);
-      wait_flag(prm.peer_flags[rank] + (0 * kArMaxBlocks + b) * kArMaxWorld + tid, stamp);
+      wait_flag(prm.peer_flags[rank] + (0 * kArMaxBlocks + b) * kArMaxWorld + tid, stamp, prm.timeout_cycles);
     }
     __syncthreads();
   }
@@ -152,7 +157,7 @@ __global__ void __launch_bounds__(kArThreads, 1) allreduce_clip_adam_kernel(cons
     const unsigned long long target = (unsigned long long)stamp * (unsigned long long)G;
     const long long t0 = clock64();
     while (ld_acquire_gpu(&ws->arrivals) < target) {
-      if (clock64() - t0 > 8000000000LL) {
+      if (clock64() - t0 > prm.timeout_cycles) {
         printf("rslrl allreduce_clip_adam: grid barrier timeout (block %d)\n", b);
         __trap();
       }
@@ -227,7 +232,7 @@ __global__ void __launch_bounds__(kArThreads, 1) allreduce_clip_adam_kernel(cons
 
   // ---- 4: the peers have read slice b of this rank's gradients -> clear it for the next backward pass
   if (W > 1) {
-    if (tid < W && tid != rank) wait_flag(prm.peer_flags[rank] + (1 * kArMaxBlocks + b) * kArMaxWorld + tid, stamp);
+    if (tid < W && tid != rank) wait_flag(prm.peer_flags[rank] + (1 * kArMaxBlocks + b) * kArMaxWorld + tid, stamp, prm.timeout_cycles);
     __syncthreads();
   }
   if (prm.zero_grad) {
@@ -269,6 +274,16 @@ int rslrl_allreduce_clip_adam(int world, int rank, const float* const* peer_grad
   prm.state = state; prm.ws = (ArWorkspace*)workspace;
   prm.world = world; prm.rank = rank; prm.adaptive = adaptive; prm.round_lr_fp32 = round_lr_fp32;
   prm.use_kl = use_kl; prm.zero_grad = zero_grad;
+  {
+    static long long cycles = 0;
+    if (cycles == 0) {
+      const char* env = getenv("RSLRL_PEER_TIMEOUT_S");
+      double sec = env ? atof(env) : 1800.0;
+      if (!(sec > 0.0)) sec = 1800.0;
+      cycles = (long long)(sec * 2.0e9);  // clock64 ticks at <= ~2 GHz
+    }
+    prm.timeout_cycles = cycles;
+  }
   prm.max_norm = max_grad_norm; prm.desired_kl = desired_kl; prm.beta1 = beta1; prm.beta2 = beta2; prm.eps = eps;
 
   int sms = kNumSMs;

@@ -11,37 +11,43 @@
 // advantages are bit-identical to the reference.  The normalisation needs the global mean and
 // unbiased std of all T*N advantages: per-thread fp64 partials -> warp shuffles -> one fp64 pair per
 // block in a workspace -> grid barrier -> every block reduces the per-block pairs in the same order
-// (deterministic) -> the advantages, still in registers, are written once.
+// (deterministic) -> returns and advantages, still in registers, are written once.
 // Algorithmic traffic: 17*T*N + 4*N bytes.
-// The barrier is a ticket counter in the workspace (all blocks are co-resident: the grid never exceeds what
-// the occupancy API reports as simultaneously resident, and the wait is bounded); it costs ~1 us for <=592
-// blocks and, unlike a cooperative launch, lets consecutive launches overlap their ramp-up.  The last block
-// to leave re-arms the counters, so the workspace only has to be zero ONCE (at allocation).
+//
+// Round-2 shape of the kernel (the round-1 one ran at 0.29 of the HBM peak at 65 536 envs):
+//   * NOTHING is stored before the barrier: the scan keeps `returns` in the registers that held the rewards and both
+//     outputs leave after the barrier, so the arrival fence has no store queue to drain and the barrier sits directly
+//     behind the last load;
+//   * the grid is at most one block per SM (block size grows with N), so the barrier is <= 148 arrivals polled with
+//     ld.acquire, and the per-block partial pairs are reduced by one warp;
+//   * the launch is COOPERATIVE (cudaLaunchAttributeCooperative): co-residency of the spinning blocks is guaranteed by
+//     the driver (or the launch fails) whatever else shares the device; the wait is unbounded like any grid.sync().
+// The last block to leave re-arms the counters, so the workspace only has to be zero ONCE (at allocation).
 #include "common.cuh"
 
 namespace rslrl {
 
-constexpr int kGaeThreads = 128;
-constexpr int kGaeMaxBlocks = 4096;  // workspace capacity (pairs of doubles)
+constexpr int kGaeThreads = 128;      // grid-stride fallback kernel
+constexpr int kGaeMaxBlocks = 4096;   // workspace capacity (pairs of doubles)
 
 struct GaeBarrier {
   unsigned int arrived;
   unsigned int departed;
 };
 
+__device__ __forceinline__ unsigned int gae_ld_acquire(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ void gae_grid_barrier(GaeBarrier* bar) {
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
     atomicAdd(&bar->arrived, 1u);
-    const long long t0 = clock64();
-    while (*((volatile unsigned int*)&bar->arrived) < gridDim.x) {
-      if (clock64() - t0 > 4000000000LL) {
-        printf("rslrl gae: grid barrier timeout (block %d)\n", blockIdx.x);
-        __trap();
-      }
+    while (gae_ld_acquire(&bar->arrived) < gridDim.x) {
     }
-    __threadfence();
   }
   __syncthreads();
 }
@@ -67,21 +73,24 @@ __device__ __forceinline__ void gae_finalize_stats(double s, double ss, double* 
     partials[2 * blockIdx.x + 1] = v[1];
   }
   gae_grid_barrier(bar);
-  double t[2] = {0.0, 0.0};
-  for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
-    t[0] += partials[2 * i];
-    t[1] += partials[2 * i + 1];
+  if (threadIdx.x < 32) {   // one warp, fixed order: every block derives the same bits
+    double t0 = 0.0, t1 = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) {
+      t0 += __ldcg(partials + 2 * i);
+      t1 += __ldcg(partials + 2 * i + 1);
+    }
+    t0 = warp_sum(t0);
+    t1 = warp_sum(t1);
+    if (threadIdx.x == 0) {
+      const double n = (double)B;
+      const double mean = t0 / n;
+      double var = (t1 - t0 * t0 / n) / (n - 1.0);  // unbiased, as torch.Tensor.std()
+      var = var > 0.0 ? var : 0.0;
+      smem[0] = mean;
+      smem[1] = sqrt(var);
+    }
   }
-  block_sum<2>(t, smem);
-  gae_grid_barrier_release(bar);
-  if (threadIdx.x == 0) {
-    const double n = (double)B;
-    const double mean = t[0] / n;
-    double var = (t[1] - t[0] * t[0] / n) / (n - 1.0);  // unbiased, as torch.Tensor.std()
-    var = var > 0.0 ? var : 0.0;
-    smem[0] = mean;
-    smem[1] = sqrt(var);
-  }
+  gae_grid_barrier_release(bar);   // (contains the __syncthreads that publishes smem[0..1])
   __syncthreads();
   mean_f = (float)smem[0];
   denom_f = __fadd_rn((float)smem[1], 1e-8f);
@@ -89,17 +98,16 @@ __device__ __forceinline__ void gae_finalize_stats(double s, double ss, double* 
 
 // One env per thread, whole trajectory in registers.
 template <int TMAX>
-__global__ void __launch_bounds__(kGaeThreads)
+__global__ void __launch_bounds__(512, 1)
 gae_norm_reg_kernel(const float* __restrict__ rewards, const float* __restrict__ values,
                     const uint8_t* __restrict__ dones, const float* __restrict__ last_values,
                     float* __restrict__ returns, float* __restrict__ advantages, double* __restrict__ partials,
                     GaeBarrier* bar, int T, int N, float gamma, float lam, int normalize) {
   __shared__ double smem[64];
-  const int n = blockIdx.x * kGaeThreads + threadIdx.x;
-  float a[TMAX];
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  float r[TMAX], v[TMAX];   // r[i] is overwritten by returns[i] during the scan
   double s = 0.0, ss = 0.0;
   if (n < N) {
-    float r[TMAX], v[TMAX];
     uint8_t d[TMAX];
 #pragma unroll
     for (int i = 0; i < TMAX; ++i) {
@@ -120,9 +128,8 @@ gae_norm_reg_kernel(const float* __restrict__ rewards, const float* __restrict__
         const float delta = __fsub_rn(__fadd_rn(r[i], __fmul_rn(ng, next_v)), v[i]);
         adv = __fadd_rn(delta, __fmul_rn(__fmul_rn(ng, lam), adv));
         const float ret = __fadd_rn(adv, v[i]);
-        returns[(size_t)i * N + n] = ret;
+        r[i] = ret;
         const float x = __fsub_rn(ret, v[i]);
-        a[i] = x;
         s += (double)x;
         ss += (double)x * (double)x;
         next_v = v[i];
@@ -135,8 +142,9 @@ gae_norm_reg_kernel(const float* __restrict__ rewards, const float* __restrict__
 #pragma unroll
     for (int i = 0; i < TMAX; ++i) {
       if (i < T) {
-        const float x = normalize ? __fdiv_rn(__fsub_rn(a[i], mean_f), denom_f) : a[i];
-        advantages[(size_t)i * N + n] = x;
+        const float x = __fsub_rn(r[i], v[i]);
+        returns[(size_t)i * N + n] = r[i];
+        advantages[(size_t)i * N + n] = normalize ? __fdiv_rn(__fsub_rn(x, mean_f), denom_f) : x;
       }
     }
   }
@@ -180,28 +188,44 @@ gae_norm_generic_kernel(const float* __restrict__ rewards, const float* __restri
     }
 }
 
-template <typename K>
-static int max_coop_blocks(K kernel) {
-  int dev = 0, sms = 0, per_sm = 0;
+static int device_sms() {
+  int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kGaeThreads, 0);
-  int cap = sms * per_sm;
-  return cap < kGaeMaxBlocks ? cap : kGaeMaxBlocks;
+  return sms;
 }
 
-template <int TMAX>
-static int launch_reg(void** args, int blocks, cudaStream_t st) {
-  static int cap = -1;
-  if (cap < 0) cap = max_coop_blocks(gae_norm_reg_kernel<TMAX>);
-  if (blocks > cap) return -1;  // more envs than resident threads: caller uses the grid-stride kernel
-  cudaError_t e = cudaLaunchKernel((void*)gae_norm_reg_kernel<TMAX>, dim3(blocks), dim3(kGaeThreads), args, 0, st);
+// cooperative launch: the driver guarantees that all blocks are co-resident (or rejects the launch)
+template <typename K>
+static int launch_coop(K kernel, int blocks, int threads, void** args, cudaStream_t st) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(blocks);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelExC(&cfg, (const void*)kernel, args);
   if (e != cudaSuccess) {
     set_error("rslrl_gae_norm: %s", cudaGetErrorString(e));
     return 1;
   }
   count_launch();
   return 0;
+}
+
+template <int TMAX>
+static int launch_reg(void** args, int N, cudaStream_t st) {
+  // at most one block per SM: the block size grows with the env count (128 .. 512 threads)
+  const int sms = device_sms();
+  int threads = 128;
+  while (threads < 512 && (N + threads - 1) / threads > sms) threads *= 2;
+  const int blocks = (N + threads - 1) / threads;
+  if (blocks > sms) return -1;  // more envs than one wave of register-resident threads: grid-stride kernel
+  return launch_coop(gae_norm_reg_kernel<TMAX>, blocks, threads, args, st);
 }
 
 }  // namespace rslrl
@@ -225,23 +249,18 @@ int rslrl_gae_norm(const float* rewards, const float* values, const uint8_t* don
   GaeBarrier* bar = (GaeBarrier*)(partials + 2 * kGaeMaxBlocks);
   void* args[] = {&rewards, &values, &dones, &last_values, &returns, &advantages, &partials, &bar,
                   &T,       &N,      &gamma, &lam,         &normalize};
-  const int blocks = (N + kGaeThreads - 1) / kGaeThreads;
   int rc = -1;
-  if (T <= 8) rc = launch_reg<8>(args, blocks, st);
-  else if (T <= 16) rc = launch_reg<16>(args, blocks, st);
-  else if (T <= 24) rc = launch_reg<24>(args, blocks, st);
-  else if (T <= 32) rc = launch_reg<32>(args, blocks, st);
+  if (T <= 8) rc = launch_reg<8>(args, N, st);
+  else if (T <= 16) rc = launch_reg<16>(args, N, st);
+  else if (T <= 24) rc = launch_reg<24>(args, N, st);
+  else if (T <= 32) rc = launch_reg<32>(args, N, st);
   if (rc >= 0) return rc;
-  static int cap = -1;
-  if (cap < 0) cap = max_coop_blocks(gae_norm_generic_kernel);
-  const int gblocks = blocks < cap ? blocks : cap;
-  cudaError_t e = cudaLaunchKernel((void*)gae_norm_generic_kernel, dim3(gblocks), dim3(kGaeThreads), args, 0, st);
-  if (e != cudaSuccess) {
-    set_error("rslrl_gae_norm: %s", cudaGetErrorString(e));
-    return 1;
-  }
-  count_launch();
-  return 0;
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gae_norm_generic_kernel, kGaeThreads, 0);
+  int cap = device_sms() * (per_sm > 0 ? per_sm : 1);
+  if (cap > kGaeMaxBlocks) cap = kGaeMaxBlocks;
+  const int blocks = (N + kGaeThreads - 1) / kGaeThreads;
+  return launch_coop(gae_norm_generic_kernel, blocks < cap ? blocks : cap, kGaeThreads, args, st);
 }
 
 }  // extern "C"

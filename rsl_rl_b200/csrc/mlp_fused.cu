@@ -50,6 +50,13 @@ struct MfNet {
   const float* b[4];
   float* y;
   int M, K0, N1, N2, N3, N4, ldy, act, store_h;
+  // fused Gaussian head (rollout): actions = z * sigma + mu, log-prob, sigma rows; head_z == nullptr: off
+  const float* head_z;
+  const float* head_std;
+  float* head_actions;
+  float* head_logp;
+  float* head_sigma;
+  int head_std_type;
 };
 
 struct alignas(64) MfBatch {
@@ -129,7 +136,8 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp3_forward_kernel(const __gri
   uint8_t* const wring = smem_raw + pad;
   uint8_t* const gring = wring + MF_W_STAGES * MF_W_STAGE_BYTES;
   float* const bias_s = (float*)(gring + MF_GRANULES * MF_GRANULE_BYTES);  // [2][MF_MAX_BIAS]
-  uint64_t* const w_full = (uint64_t*)(bias_s + 2 * MF_MAX_BIAS);
+  float* const head_s = bias_s + 2 * MF_MAX_BIAS;                          // [2][3][16]: sigma, log sigma, 2 sigma^2
+  uint64_t* const w_full = (uint64_t*)(head_s + 2 * 48);
   uint64_t* const w_empty = w_full + MF_W_STAGES;
   uint64_t* const g_full = w_empty + MF_W_STAGES;
   uint64_t* const g_empty = g_full + MF_GRANULES;
@@ -182,6 +190,17 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp3_forward_kernel(const __gri
     else if (o < 896) { if (o - 768 < P.N3 && P.b[2]) v = __ldg(P.b[2] + o - 768); }
     else { if (o - 896 < P.N4 && P.b[3]) v = __ldg(P.b[3] + o - 896); }
     bias_s[i] = v;
+  }
+  if (threadIdx.x < n_nets * 16) {   // Gaussian head constants (same expressions as gaussian_act_kernel)
+    const int ni = threadIdx.x >> 4, a = threadIdx.x & 15;
+    const MfNet& P = batch.net[ni];
+    if (P.head_z != nullptr && a < P.N4) {
+      const float p = __ldg(P.head_std + a);
+      const float sg = P.head_std_type == RSLRL_STD_LOG ? expf(p) : p;
+      head_s[ni * 48 + a] = sg;
+      head_s[ni * 48 + 16 + a] = logf(sg);
+      head_s[ni * 48 + 32 + a] = 2.f * (sg * sg);
+    }
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -529,9 +548,30 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp3_forward_kernel(const __gri
           if (row < P.M) {
             float* const yr = P.y + (size_t)row * P.ldy;
             const float* const b4 = bias_net + 896;
+            if (P.head_z == nullptr) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (i < P.N4) yr[i] = __uint_as_float(v[i]) + b4[i];
+              for (int i = 0; i < 16; ++i)
+                if (i < P.N4) yr[i] = __uint_as_float(v[i]) + b4[i];
+            } else {
+              // Gaussian policy head on this lane's row (arithmetic of gaussian_act_kernel, bit for bit)
+              const float* const hs = head_s + ni * 48;
+              const float* const zr = P.head_z + (size_t)row * P.N4;
+              float* const ar = P.head_actions + (size_t)row * P.N4;
+              float lp = 0.f;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                if (i < P.N4) {
+                  const float mean = __uint_as_float(v[i]) + b4[i], sg = hs[i];
+                  const float a = __fadd_rn(__fmul_rn(__ldg(zr + i), sg), mean);
+                  yr[i] = mean;
+                  ar[i] = a;
+                  const float d = a - mean;
+                  lp += -(d * d) / hs[32 + i] - hs[16 + i] - 0.91893853320467274178f;
+                  if (P.head_sigma) P.head_sigma[(size_t)row * P.N4 + i] = sg;
+                }
+              }
+              P.head_logp[row] = lp;
+            }
           }
         } else {
           release_only(1);
@@ -550,14 +590,17 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp3_forward_kernel(const __gri
   }
 }
 
+static_assert(sizeof(rslrl_mlp3_fwd_t) == 208, "rslrl_mlp3_fwd_t layout is mirrored by _native.Mlp3Fwd (ctypes)");
+
 static bool ok16(const void* p, long long ld) { return ((uintptr_t)p & 15) == 0 && (ld % 4) == 0; }
 
-// 0 ok, 1 error, -1 not eligible (caller runs the layers one by one)
-int mlp3_forward_fused(int n, const rslrl_mlp3_fwd_t* nets, cudaStream_t st) {
+static int mlp3_launch(const MfBatch& b, int n, bool f16, int M, cudaStream_t st);
+
+// Validates the nets and encodes the tensor maps.  0 ok, 1 error, -1 not eligible (caller runs the layers one by one)
+static int mlp3_build(int n, const rslrl_mlp3_fwd_t* nets, MfBatch& b, bool& f16) {
   const char* what = "rslrl_mlp3_forward";
   if (n < 1 || n > 2) return -1;
-  const bool f16 = nets[0].precision == RSLRL_PREC_FP16;
-  MfBatch b{};
+  f16 = nets[0].precision == RSLRL_PREC_FP16;
   for (int i = 0; i < n; ++i) {
     const rslrl_mlp3_fwd_t& q = nets[i];
     if (q.M != nets[0].M) return -1;
@@ -603,14 +646,40 @@ int mlp3_forward_fused(int n, const rslrl_mlp3_fwd_t* nets, cudaStream_t st) {
     for (int l = 0; l < 4; ++l) P.b[l] = q.b[l];
     P.y = q.y; P.M = q.M; P.K0 = q.K0; P.N1 = q.N1; P.N2 = q.N2; P.N3 = q.N3; P.N4 = q.N4; P.ldy = q.ldy;
     P.act = q.act; P.store_h = store ? 1 : 0;
+    P.head_z = q.head_z; P.head_std = q.head_std; P.head_actions = q.head_actions; P.head_logp = q.head_logp;
+    P.head_sigma = q.head_sigma; P.head_std_type = q.head_std_type;
+    if (q.head_z != nullptr && (!q.head_std || !q.head_actions || !q.head_logp)) {
+      set_error("%s: head_z needs head_std, head_actions and head_logp", what);
+      return 1;
+    }
   }
-  const size_t smem = MF_W_STAGES * MF_W_STAGE_BYTES + MF_GRANULES * MF_GRANULE_BYTES + 2 * MF_MAX_BIAS * 4 +
+  return 0;
+}
+
+int mlp3_forward_fused(int n, const rslrl_mlp3_fwd_t* nets, cudaStream_t st) {
+  MfBatch b{};
+  bool f16 = false;
+  const int rc = mlp3_build(n, nets, b, f16);
+  if (rc != 0) return rc;
+  return mlp3_launch(b, n, f16, nets[0].M, st);
+}
+
+struct Mlp3Plan {
+  MfBatch b;
+  int n;
+  bool f16;
+  rslrl_mlp3_fwd_t nets[2];
+};
+
+static int mlp3_launch(const MfBatch& b, int n, bool f16, int M, cudaStream_t st) {
+  const char* what = "rslrl_mlp3_forward";
+  const size_t smem = MF_W_STAGES * MF_W_STAGE_BYTES + MF_GRANULES * MF_GRANULE_BYTES + 2 * MF_MAX_BIAS * 4 + 2 * 48 * 4 +
                       (2 * MF_W_STAGES + 2 * MF_GRANULES + 6) * 8 + 16 + 1024;
   // clusters of two CTAs with multicast weight loads: opt-in (RSLRL_MF_MULTICAST=1).  Measured on B200
   // (profiles/experiments/notes/r1_mlp3_multicast.md): 53.3 us vs 51.2 us without - the per-SM ingest path, not the L2
   // read bandwidth, bounds the weight stream, and multicast delivers the same bytes into every SM.
   static const bool mc_env = [] { const char* e = getenv("RSLRL_MF_MULTICAST"); return e && e[0] == '1'; }();
-  const int tiles_m = (nets[0].M + TC_BLOCK_M - 1) / TC_BLOCK_M;
+  const int tiles_m = (M + TC_BLOCK_M - 1) / TC_BLOCK_M;
   const bool mc = mc_env && (tc_num_sms() % 2 == 0);
   using Kern = void (*)(const MfBatch, const int);
   const Kern kern = f16 ? (mc ? (Kern)mlp3_forward_kernel<true, true> : (Kern)mlp3_forward_kernel<true, false>)
@@ -677,6 +746,53 @@ extern "C" int rslrl_mlp3_forward(int n, const rslrl_mlp3_fwd_t* nets_host, rslr
   }
   return rc;
 }
+
+extern "C" int rslrl_mlp3_plan_create(int n, const rslrl_mlp3_fwd_t* nets_host, void** plan_out) {
+  using namespace rslrl;
+  const char* what = "rslrl_mlp3_plan_create";
+  RSLRL_CHECK_ARG(n > 0 && n <= 2 && nets_host && plan_out, what);
+  for (int i = 0; i < n; ++i) {
+    const rslrl_mlp3_fwd_t& p = nets_host[i];
+    RSLRL_CHECK_ARG(p.x && p.y && p.w[0] && p.w[1] && p.w[2] && p.w[3] && p.M > 0 && p.ldx >= p.K0 && p.ldw0 >= p.K0 &&
+                        p.ldy >= p.N4,
+                    what);
+  }
+  Mlp3Plan* plan = new Mlp3Plan();
+  plan->n = n;
+  for (int i = 0; i < n; ++i) plan->nets[i] = nets_host[i];
+  const int rc = mlp3_build(n, nets_host, plan->b, plan->f16);
+  if (rc != 0) {
+    delete plan;
+    if (rc < 0) {
+      set_error("%s: shape not eligible for the fused forward", what);
+      return 4;
+    }
+    return rc;
+  }
+  *plan_out = plan;
+  return 0;
+}
+
+extern "C" int rslrl_mlp3_plan_run(void* plan_v, const float* const* x_host, rslrl_stream_t stream) {
+  using namespace rslrl;
+  const char* what = "rslrl_mlp3_plan_run";
+  RSLRL_CHECK_ARG(plan_v && x_host, what);
+  Mlp3Plan* plan = (Mlp3Plan*)plan_v;
+  for (int i = 0; i < plan->n; ++i) {
+    rslrl_mlp3_fwd_t& q = plan->nets[i];
+    RSLRL_CHECK_ARG(x_host[i] != nullptr && ((uintptr_t)x_host[i] & 15) == 0, what);
+    if (x_host[i] != q.x) {   // only the input descriptor depends on the observation pointer
+      q.x = x_host[i];
+      if (!tc_make_map(&plan->b.net[i].map_x, q.x, q.M, q.K0, q.ldx, 32, 128, true)) {
+        set_error("%s: cuTensorMapEncodeTiled failed", what);
+        return 1;
+      }
+    }
+  }
+  return mlp3_launch(plan->b, plan->n, plan->f16, plan->nets[0].M, (cudaStream_t)stream);
+}
+
+extern "C" void rslrl_mlp3_plan_destroy(void* plan) { delete (rslrl::Mlp3Plan*)plan; }
 
 #ifdef RSLRL_TC_TRACE
 extern "C" int rslrl_debug_read_trace_mlp3(unsigned long long* host) {

@@ -14,8 +14,12 @@ namespace rslrl {
 
 constexpr int kOptThreads = 256;
 
+constexpr int kOptMaxBlocks = kNumSMs * 4;
+
+// per-block partials summed by the last block in index order: every rank derives bit-identical clip_scale / lr from
+// identical (all-reduced) gradients, whatever order its blocks retire in
 struct NormWorkspace {
-  double sumsq;
+  double partial[kOptMaxBlocks];
   unsigned int ticket;
   unsigned int pad_;
 };
@@ -26,6 +30,7 @@ grad_norm_lr_kernel(const float* __restrict__ g, long long P, const float* __res
                     double desired_kl, int round_lr_fp32, double beta1, double beta2) {
   __shared__ double s_red[32];
   __shared__ bool s_last;
+  __shared__ double s_total;
   double acc[1] = {0.0};
   const long long tid = (long long)blockIdx.x * kOptThreads + threadIdx.x;
   const long long stride = (long long)gridDim.x * kOptThreads;
@@ -41,15 +46,22 @@ grad_norm_lr_kernel(const float* __restrict__ g, long long P, const float* __res
   }
   block_sum<1>(acc, s_red);
   if (threadIdx.x == 0) {
-    atomicAdd(&ws->sumsq, acc[0]);
+    ws->partial[blockIdx.x] = acc[0];
     __threadfence();
     s_last = atomicAdd(&ws->ticket, 1u) == gridDim.x - 1;
   }
   __syncthreads();
-  if (!s_last || threadIdx.x != 0) return;
+  if (!s_last) return;
   __threadfence();
-  const double sumsq = *((volatile double*)&ws->sumsq);
-  ws->sumsq = 0.0;
+  if (threadIdx.x < 32) {  // fixed-shape tree over the partials in index order (deterministic)
+    double s = 0.0;
+    for (int j = threadIdx.x; j < (int)gridDim.x; j += 32) s += *((volatile double*)&ws->partial[j]);
+    s = warp_sum(s);
+    if (threadIdx.x == 0) s_total = s;
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  const double sumsq = s_total;
   const double w = (double)world;
   const double norm = sqrt(sumsq) / w;  // ||mean over ranks of g||
   double coef = 1.0;
@@ -120,7 +132,7 @@ adam_step_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict
 
 static int opt_blocks(long long P) {
   long long b = (P / 4 + kOptThreads - 1) / kOptThreads;
-  if (b > kNumSMs * 4) b = kNumSMs * 4;
+  if (b > kOptMaxBlocks) b = kOptMaxBlocks;
   return b < 1 ? 1 : (int)b;
 }
 

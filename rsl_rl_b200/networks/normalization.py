@@ -46,7 +46,7 @@ class EmpiricalNormalization(nn.Module):
         delta = mean_x - self._mean
         self._mean += rate * delta
         self._var += rate * (var_x - self._var + delta * (mean_x - self._mean))
-        self._std = torch.sqrt(self._var)
+        torch.sqrt(self._var, out=self._std)   # in place: CUDA graphs and act() plans hold this buffer's address
 
     @torch.jit.unused
     def inverse(self, y):

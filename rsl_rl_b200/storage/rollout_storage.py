@@ -149,8 +149,11 @@ class RolloutStorage:
                     self.rewards[s].data_ptr(), self.dones[s].data_ptr())
             self._store_plans[s] = plan
         src_arr, dst_arr, dim_arr, values_ptr, rew_row, done_row = plan
-        for i, k in enumerate(self._obs_keys):
-            src_arr[i] = nat.f32c(obs[k]).data_ptr()
+        keep = []   # converted copies must outlive the launch (their blocks could otherwise be recycled by the
+        for i, k in enumerate(self._obs_keys):   # conversions below, which are enqueued before the kernel)
+            src = nat.f32c(obs[k])
+            keep.append(src)
+            src_arr[i] = src.data_ptr()
         rewards = nat.f32c(rewards)
         dones, dcode = nat.flag_tensor(dones)
         to_ptr, tcode = None, 0
@@ -159,11 +162,13 @@ class RolloutStorage:
                 time_outs = time_outs.to(rewards.device)
             time_outs, tcode = nat.flag_tensor(time_outs)
             to_ptr = time_outs.data_ptr()
-        intr = None if intrinsic is None else nat.f32c(intrinsic).data_ptr()
+        intr_t = None if intrinsic is None else nat.f32c(intrinsic)
+        nat.require_cuda(rewards, dones, intr_t, *keep)
         nat.check(nat.lib().rslrl_store_transition(
             len(self._obs_keys), src_arr, dst_arr, dim_arr, None, None, None, 0, values_ptr, None,
-            rewards.data_ptr(), dones.data_ptr(), dcode, to_ptr, tcode, intr, float(gamma), None, None, None, None, None,
-            rew_row, done_row, self.num_envs, self._A, nat.stream_ptr()))
+            rewards.data_ptr(), dones.data_ptr(), dcode, to_ptr, tcode, nat.ptr(intr_t), float(gamma), None, None, None,
+            None, None, rew_row, done_row, self.num_envs, self._A, nat.stream_ptr()))
+        del keep, intr_t
         self.step += 1
 
     def _save_hidden_states(self, hidden_states):

@@ -558,3 +558,71 @@ def test_mlp3_fused_forward_matches_layerwise_tf32_path():
         linear_forward([(h, ws[l], bs[l], out, nat.ACT_CODES["elu"] if l < 3 else 0)], nat.PREC_TF32)
         h = out
     assert rel_err(y.cpu().numpy(), h.cpu().numpy()) < 5e-4
+
+
+@pytest.mark.parametrize("M,A,std_type,prec", [(4096, 12, "scalar", "tf32"), (1000, 12, "log", "fp16"), (77, 5, "scalar", "tf32")])
+def test_mlp3_plan_with_fused_gaussian_head_bit_exact_vs_separate_kernels(M, A, std_type, prec):
+    """The one-launch rollout step (rslrl_mlp3_plan_run with the Gaussian head in the actor's output epilogue) gives the
+    bits of rslrl_mlp3_forward followed by rslrl_gaussian_act, also after the input pointer changes."""
+    import ctypes as C
+    from rsl_rl_b200.networks.mlp import mlp3_forward, mlp3_struct
+    nat = _nat()
+    torch.manual_seed(M + A)
+    f16 = prec == "fp16"
+    dims = [[48, 512, 256, 128, A], [48, 512, 256, 128, 1]]
+    std = (torch.rand(A, device=DEV) + 0.3) if std_type == "scalar" else torch.randn(A, device=DEV) * 0.3
+    code = nat.STD_SCALAR if std_type == "scalar" else nat.STD_LOG
+    z = torch.randn(M, A, device=DEV)
+    nets = []
+    for d in dims:
+        ws = [torch.randn(d[l + 1], d[l], device=DEV) / d[l] ** 0.5 for l in range(4)]
+        bs = [torch.randn(d[l + 1], device=DEV) * 0.3 for l in range(4)]
+        wk = [ws[0]] + [w.half() if f16 else w for w in ws[1:]]
+        nets.append((ws, bs, wk))
+    xs = [torch.randn(M, 48, device=DEV) for _ in range(3)]
+    y_ref, y_new = [torch.empty(M, d[4], device=DEV) for d in dims], [torch.empty(M, d[4], device=DEV) for d in dims]
+    act_ref, lp_ref, sig_ref = torch.empty(M, A, device=DEV), torch.empty(M, device=DEV), torch.empty(M, A, device=DEV)
+    act_new, lp_new, sig_new = torch.empty(M, A, device=DEV), torch.empty(M, device=DEV), torch.empty(M, A, device=DEV)
+    P = nat.PREC_FP16 if f16 else nat.PREC_TF32
+    mk = lambda x, i, y: mlp3_struct(x.data_ptr(), 48, M, nets[i][2], nets[i][1], None, y, nat.ACT_CODES["elu"], P)
+    sa, sc = mk(xs[0], 0, y_new[0]), mk(xs[0], 1, y_new[1])
+    sa.head_z, sa.head_std, sa.head_std_type = z.data_ptr(), std.data_ptr(), code
+    sa.head_actions, sa.head_logp, sa.head_sigma = act_new.data_ptr(), lp_new.data_ptr(), sig_new.data_ptr()
+    arr = (nat.Mlp3Fwd * 2)(sa, sc)
+    handle = C.c_void_p()
+    nat.check(nat.lib().rslrl_mlp3_plan_create(2, arr, C.byref(handle)))
+    try:
+        for x in xs + [xs[0]]:
+            mlp3_forward([mk(x, 0, y_ref[0]), mk(x, 1, y_ref[1])])
+            nat.check(nat.lib().rslrl_gaussian_act(y_ref[0].data_ptr(), std.data_ptr(), code, z.data_ptr(), act_ref.data_ptr(),
+                                                   lp_ref.data_ptr(), sig_ref.data_ptr(), M, A, nat.stream_ptr()))
+            ptrs = (C.c_void_p * 2)(x.data_ptr(), x.data_ptr())
+            nat.check(nat.lib().rslrl_mlp3_plan_run(handle, ptrs, nat.stream_ptr()))
+            torch.cuda.synchronize()
+            for a, b in ((y_ref[0], y_new[0]), (y_ref[1], y_new[1]), (act_ref, act_new), (lp_ref, lp_new), (sig_ref, sig_new)):
+                assert torch.equal(a, b)
+    finally:
+        nat.lib().rslrl_mlp3_plan_destroy(handle)
+
+
+def test_update_rng_skip_matches_the_discarded_draws():
+    """rng_compat: update() advances the Philox offset instead of launching the 20 discarded torch.normal draws of the
+    reference (ppo.py:249); the generator state afterwards must be the one real draws would leave."""
+    from rsl_rl_b200.algorithms.ppo import PPO
+    mb, A, n = 24576, 12, 20
+    gen = torch.cuda.default_generators[0]
+    buf = torch.empty(mb, A, device=DEV)
+
+    class Stub:  # the two attributes _skip_discarded_draws touches
+        device, _discard, _draw_offset = DEV, buf, None
+
+    for trial in range(2):   # trial 0 measures the per-draw offset with one real launch, trial 1 is launch-free
+        torch.manual_seed(123 + trial)
+        for _ in range(n):
+            torch.normal(torch.zeros(mb, A, device=DEV), torch.ones(mb, A, device=DEV))
+        expect_state, expect_next = gen.get_state().clone(), torch.randperm(1000, device=DEV)
+        torch.manual_seed(123 + trial)
+        PPO._skip_discarded_draws(Stub, n)
+        assert torch.equal(gen.get_state(), expect_state)
+        assert torch.equal(torch.randperm(1000, device=DEV), expect_next)
+    assert Stub._draw_offset is not None and Stub._draw_offset > 0
