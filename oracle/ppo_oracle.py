@@ -429,7 +429,8 @@ def update(params, adam_state, lr, storage, perm, cfg, world_hook=None):
             sums["entropy"] += info["entropy"]
             trace.append(dict(kl=kl, lr=lr, total_norm=total_norm, grads=raw,
                               surrogate=info["surrogate"], value_loss=info["value_loss"],
-                              entropy=info["entropy"]))
+                              entropy=info["entropy"],
+                              params_after=np.concatenate([v.reshape(-1) for v in params.values()])))
     n = E * M
     return {k: v / n for k, v in sums.items()}, lr, trace
 

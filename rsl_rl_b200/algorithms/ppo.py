@@ -143,6 +143,13 @@ class PPO:
         # the fused engine drives the ROLLOUT of every feed-forward ActorCritic; the UPDATE additionally needs the plain
         # PPO objective (RND / symmetry go through the composite update on the same parameters)
         self._engine_reason = _engine.supports(self.policy)
+        self._obs_fast = None
+        if self._engine_reason is None:
+            pol = self.policy
+            ga, gc = list(pol.obs_groups["policy"]), list(pol.obs_groups["critic"])
+            if (len(ga) == 1 and len(gc) == 1 and isinstance(pol.actor_obs_normalizer, nn.Identity)
+                    and isinstance(pol.critic_obs_normalizer, nn.Identity)):
+                self._obs_fast = (ga[0], None if gc[0] == ga[0] else gc[0])
         self._update_reason = "RND" if self.rnd is not None else ("symmetry" if self.symmetry is not None else None)
         self._graph = None
         self._cgraph, self._cgraph_key, self._cgraph_failed, self._cgraph_launches = None, None, False, 0
@@ -221,7 +228,15 @@ class PPO:
             raise OverflowError("Rollout buffer overflow! You should call clear() before adding new transitions.")
         if s == 0 and eng.needs_refresh:
             eng.refresh_padded()  # parameters may have been loaded / modified since the last optimiser step
-        x_a, x_c = self._inputs(obs)
+        fast = self._obs_fast
+        if fast is None:
+            x_a, x_c = self._inputs(obs)
+        else:   # one observation group per set, no normaliser: the env's tensors are the network inputs
+            x_a = obs[fast[0]]
+            x_c = x_a if fast[1] is None else obs[fast[1]]
+            if x_a.dtype != torch.float32 or x_c.dtype != torch.float32 or not x_a.is_contiguous() \
+                    or not x_c.is_contiguous():
+                x_a, x_c = self._inputs(obs)
         key = (x_a.stride(0), x_c.stride(0), x_a.shape[1], x_c.shape[1], self._group.values.data_ptr())
         plan = self._act_plans.get(s)
         if plan is None or plan["key"] != key:
@@ -275,8 +290,9 @@ class PPO:
         tr.actions_log_prob = logp_s.view(-1)
         tr.action_mean, tr.action_sigma = mu_s, sig_s
         tr.observations = obs
-        self.policy._mean, self.policy._std = tr.action_mean, tr.action_sigma
-        return tr.actions
+        pd = self.policy.__dict__   # plain attributes (set in _init_noise): skip nn.Module.__setattr__'s type checks
+        pd["_mean"], pd["_std"] = mu_s, sig_s
+        return act_s
 
     def _build_act_plan(self, s, x_a, x_c, key):
         st, eng = self.storage, self._engine

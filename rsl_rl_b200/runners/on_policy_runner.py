@@ -99,6 +99,7 @@ class OnPolicyRunner:
         self.git_status_repos = [rsl_rl_b200.__file__]
         self.profile_phases = False
         self.phase_times = {}
+        self._env_device, self._action_ring, self._action_slot = None, None, 0
 
     # ------------------------------------------------------------------------------------------
     def learn(self, num_learning_iterations: int, init_at_random_ep_len: bool = False):
@@ -132,7 +133,7 @@ class OnPolicyRunner:
             with torch.inference_mode():
                 for _ in range(self.num_steps_per_env):
                     actions = self.alg.act(obs)
-                    obs, rewards, dones, extras = self.env.step(actions.to(self.env.device))
+                    obs, rewards, dones, extras = self.env.step(self._actions_for_env(actions))
                     # host-resident envs: pinned buffers are copied asynchronously (stream ordered; the blocking
                     # device->host copy of the next actions is the synchronisation point the env relies on)
                     obs, rewards, dones = self._to_device(obs), self._to_device(rewards), self._to_device(dones)
@@ -179,6 +180,27 @@ class OnPolicyRunner:
             self.phase_times = {k: v / num_learning_iterations for k, v in acc.items()}
         if logging and not self.disable_logs:
             self.save(os.path.join(self.log_dir, f"model_{self.current_learning_iteration}.pt"))
+
+    def _actions_for_env(self, actions):
+        """`actions.to(self.env.device)` of the reference (on_policy_runner.py:104).  For a host-resident env the copy
+        lands in a small ring of PINNED buffers (asynchronous copy + one stream synchronisation) instead of a pageable
+        staging copy: this read-back is the one blocking point of every env step."""
+        if not actions.is_cuda:
+            return actions.to(self.env.device)
+        env_dev = self._env_device
+        if env_dev is None:
+            env_dev = self._env_device = torch.device(self.env.device)
+        if env_dev.type != "cpu":
+            return actions if env_dev == actions.device else actions.to(env_dev)
+        ring = self._action_ring
+        if ring is None or ring[0].shape != actions.shape or ring[0].dtype != actions.dtype:
+            ring = self._action_ring = [torch.empty(actions.shape, dtype=actions.dtype, pin_memory=True) for _ in range(2)]
+            self._action_slot = 0
+        self._action_slot ^= 1
+        host = ring[self._action_slot]
+        host.copy_(actions, non_blocking=True)
+        torch.cuda.current_stream(actions.device).synchronize()
+        return host
 
     def _to_device(self, x):
         if isinstance(x, torch.Tensor):
