@@ -135,6 +135,8 @@ typedef struct {
   float* db;      /* [N]   accumulated:  db += scale * colsum(dy); may be NULL */
   int M, N, K, ldy, ldx;
   float scale;    /* 0 is read as 1; the fp16 path passes 1 / dx_scale of the chain's head */
+  const float* scale_dev; /* NULL, or a device float multiplied into `scale` when the kernel starts: element [1] of the
+                             rslrl_ppo_loss_fwd_bwd scale_state (1 / the dynamic gradient scale of this minibatch) */
 } rslrl_linear_bwd_weight_t;
 
 typedef struct {
@@ -221,7 +223,12 @@ void rslrl_mlp3_plan_destroy(void* plan);
  *   workspace  rslrl_loss_workspace_bytes() bytes, zero-initialised once by the caller
  *   dmu16 / dvalue16 (may be NULL; need A % 4 == 0, A <= 16, 16-byte aligned rows): fp16 copies
  *              grad_scale16 * dmu, grad_scale16 * dvalue (row strides in elements, multiples of 8) = the scaled output
- *              gradients the RSLRL_PREC_FP16 backward starts from */
+ *              gradients the RSLRL_PREC_FP16 backward starts from
+ *   scale_state (may be NULL) device float[8], zero-initialised except [2] = the first scale: DYNAMIC power-of-two scale
+ *              replacing grad_scale16 -- [0] scale S used by the most recent launch, [1] 1/S (pass its address as
+ *              rslrl_linear_bwd_weight_t.scale_dev of the same minibatch), [2] S of the next launch (derived from the
+ *              largest |gradient| this launch saw, so that S*max sits 16x below fp16's limit), [3] scratch,
+ *              [4] uint32 count of launches whose scaled gradients saturated fp16 (the caller reports it) */
 int64_t rslrl_loss_workspace_bytes(void);
 int rslrl_ppo_loss_fwd_bwd(const float* mu, const float* std_param, int std_type, const float* value,
                            const float* actions, const float* old_logp, const float* advantages,
@@ -231,7 +238,8 @@ int rslrl_ppo_loss_fwd_bwd(const float* mu, const float* std_param, int std_type
                            float* kl_out, double* loss_sums, void* workspace, int64_t rows,
                            int64_t mb_orig, int A, double clip_param, double value_loss_coef,
                            double entropy_coef, int use_clipped_value_loss, void* dmu16, int dmu16_stride,
-                           void* dvalue16, int dvalue16_stride, double grad_scale16, rslrl_stream_t stream);
+                           void* dvalue16, int dvalue16_stride, double grad_scale16, float* scale_state,
+                           rslrl_stream_t stream);
 
 /* sum and sum of squares of x[0..n) into out[2] (double, overwritten): statistics for
  * ppo.py:221-223 per-minibatch advantage normalisation. */

@@ -101,13 +101,29 @@ def mlp_layers(params: dict, prefix: str):
     return out
 
 
+# Optional emulation of tensor-core operand rounding (tests only): with GEMM_ROUND = "tf32" every matmul operand is
+# rounded to tf32 (10-bit mantissa, nearest, ties away) before an fp32-accumulated product -- the arithmetic class of
+# cuBLAS TF32 / tcgen05 kind::tf32.  It measures the NOISE FLOOR of that class against the fp32 oracle (e.g. how far one
+# Adam step moves parameters whose gradient sign is decided by rounding noise); it is not a model of any kernel.
+GEMM_ROUND = None
+
+
+def _r(a: np.ndarray) -> np.ndarray:
+    if GEMM_ROUND is None:
+        return a
+    if GEMM_ROUND == "tf32":
+        u = np.ascontiguousarray(a, dtype=F32).view(np.uint32)
+        return ((u + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(F32)
+    raise ValueError(GEMM_ROUND)
+
+
 def mlp_forward(layers, x: np.ndarray, activation: str = "elu"):
     """Returns (y, cache) where cache holds every layer input / pre-activation / output."""
     cache = []
     h = x.astype(F32, copy=False)
     n = len(layers)
     for li, (W, b) in enumerate(layers):
-        z = h @ W.T + b
+        z = _r(h) @ _r(W).T + b
         if li < n - 1:
             hn = act_forward(activation, z)
         else:
@@ -127,9 +143,9 @@ def mlp_backward(layers, cache, dy: np.ndarray, activation: str = "elu", need_dx
         if li < n - 1:
             d = act_backward(activation, z, h, d)
         W, _ = layers[li]
-        grads[li] = ((d.T @ x_in).astype(F32), d.sum(axis=0, dtype=np.float64).astype(F32))
+        grads[li] = ((_r(d).T @ _r(x_in)).astype(F32), d.sum(axis=0, dtype=np.float64).astype(F32))
         if li > 0 or need_dx:
-            d = (d @ W).astype(F32)
+            d = (_r(d) @ _r(W)).astype(F32)
     return grads, (d if need_dx else None)
 
 

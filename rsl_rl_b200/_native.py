@@ -39,7 +39,8 @@ class LinearBwdData(C.Structure):
 
 class LinearBwdWeight(C.Structure):
     _fields_ = [("dy", c_void_p), ("x", c_void_p), ("dw", c_void_p), ("db", c_void_p),
-                ("M", c_int), ("N", c_int), ("K", c_int), ("ldy", c_int), ("ldx", c_int), ("scale", C.c_float)]
+                ("M", c_int), ("N", c_int), ("K", c_int), ("ldy", c_int), ("ldx", c_int), ("scale", C.c_float),
+                ("scale_dev", c_void_p)]
 
 
 class LinearBwdHead(C.Structure):
@@ -119,7 +120,7 @@ _SIGNATURES["rslrl_ppo_loss_fwd_bwd"] = (c_int, [
     c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,  # dmu, dmu_stride, dvalue, dvalue_stride, dstd, db_mu, db_value
     c_void_p, c_void_p, c_void_p,                   # kl_out, loss_sums, workspace
     c_i64, c_i64, c_int, c_double, c_double, c_double, c_int,
-    c_void_p, c_int, c_void_p, c_int, c_double, c_void_p])  # dmu16, stride, dvalue16, stride, grad_scale16, stream
+    c_void_p, c_int, c_void_p, c_int, c_double, c_void_p, c_void_p])  # dmu16, stride, dvalue16, stride, grad_scale16, scale_state, stream
 
 _lib = None
 

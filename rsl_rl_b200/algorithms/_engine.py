@@ -88,7 +88,7 @@ def supports(policy) -> Optional[str]:
 
 class FeedForwardEngine:
     def __init__(self, policy, storage_rows: int, num_envs: int, minibatch_rows: int, device, precision: str,
-                 param_group: Optional[FlatParamGroup] = None):
+                 param_group: Optional[FlatParamGroup] = None, scale_state: Optional[torch.Tensor] = None):
         self.policy = policy
         self.device = torch.device(device)
         self.prec = nat.PREC_CODES[precision]
@@ -133,10 +133,21 @@ class FeedForwardEngine:
         # fp16 path, A % 4 == 0: the loss kernel also emits S * dmu, S * dvalue as fp16 (16-byte row pitch) and the output
         # layers run through the tensor-core dgrad / grouped wgrad like every other layer (no narrow-head kernel)
         self.head16 = self.f16 and self.A % 4 == 0 and os.environ.get("RSLRL_HEAD16", "1") != "0"
+        self.scale_state = None
         if self.head16:
             f16 = dict(dtype=torch.float16, device=self.device)
             self.dmu16 = torch.zeros(R, (self.A + 7) // 8 * 8, **f16)[:, :self.A]
             self.dvalue16 = torch.zeros(R, 8, **f16)[:, :1]
+            # Dynamic power-of-two gradient scale, resident on the device (include/rslrl_b200.h, scale_state): the loss
+            # kernel scales its fp16 outputs with the value derived from the previous minibatch's largest gradient and
+            # the weight-gradient kernel divides by the same value; [4] counts launches that saturated fp16.
+            # It lives in the optimiser's device state block when one is given, so that the saturation counter comes
+            # back with the one read of update().
+            if os.environ.get("RSLRL_DYNAMIC_SCALE", "1") != "0":
+                self.scale_state = (scale_state if scale_state is not None
+                                    else torch.zeros(8, dtype=torch.float32, device=self.device))
+                self.scale_state.zero_()
+                self.scale_state[0], self.scale_state[1], self.scale_state[2] = self.grad_scale, 1.0 / self.grad_scale, self.grad_scale
         # First-layer weights whose row pitch is not a multiple of 16 bytes (e.g. 235 inputs) cannot be described to
         # TMA: keep a zero-padded shadow [N, pad4(K)] that the tensor-core forward reads (refreshed after every
         # optimiser step); inputs are then read at their padded width (pad columns are kept at zero).
@@ -354,12 +365,25 @@ class FeedForwardEngine:
                 linear_backward_data(dprobs, self.prec)
             dy = new_dy
 
+    def fp16_saturation_events(self) -> int:
+        """Loss launches (since the last call) whose scaled fp16 output gradients left fp16's finite range (they were
+        saturated, the step was still taken).  One device read: call it once per update() at most."""
+        if self.scale_state is None:
+            return 0
+        n = int(self.scale_state[4:5].clone().view(torch.int32).item())
+        if n:
+            self.scale_state[4:5].zero_()
+        return n
+
     def _backward16(self, x_a: torch.Tensor, x_c: torch.Tensor, dmu: torch.Tensor, dvalue: torch.Tensor):
         """fp16-storage backward: narrow-head kernel (fp32 math, writes S * dZ3 as fp16), one grouped dgrad launch per
         hidden layer down the chain (every dZ_l stays in its own buffer), then ONE wgrad launch for all layers of both
         nets (dW += dZ^T H / S, bias gradients from the same tiles; k-splits balanced across the problems)."""
         M = x_a.shape[0]
         S, prec = self.grad_scale, nat.PREC_FP16
+        dyn = self.scale_state is not None
+        inv_s = 1.0 if dyn else 1.0 / S                                         # static factor of the wgrad epilogue
+        inv_dev = self.scale_state[1:2].data_ptr() if dyn else None            # device-resident 1 / (dynamic scale)
         nets = ((self.actor, self.h_a, self.g_a, x_a, dmu), (self.critic, self.h_c, self.g_c, x_c, dvalue))
         dz = lambda net, gbuf, l: gbuf[l - 1][:M * net.dims[l]].view(M, net.dims[l])   # gradient at the output of layer l-1
         hprobs, wprobs = [], []
@@ -368,7 +392,7 @@ class FeedForwardEngine:
             dprobs = []
             for (net, hs, gbuf, _, _), dy16 in zip(nets, (self.dmu16[:M], self.dvalue16[:M])):
                 lin, l = net.layers[-1], net.L - 1
-                wprobs.append((dy16, hs[l - 1][:M], lin.weight.grad, lin.bias.grad, 1.0 / S))
+                wprobs.append((dy16, hs[l - 1][:M], lin.weight.grad, lin.bias.grad, inv_s, inv_dev))
                 dprobs.append((dy16, self.group.shadow16(lin.weight), hs[l - 1][:M], dz(net, gbuf, l), net.acts[l - 1]))
             linear_backward_data(dprobs, prec)
         else:
@@ -383,7 +407,7 @@ class FeedForwardEngine:
                 lin = net.layers[l]
                 inp = x_in if l == 0 else hs[l - 1][:M]
                 dy = dz(net, gbuf, l + 1)
-                wprobs.append((dy, inp, lin.weight.grad, lin.bias.grad, 1.0 / S))
+                wprobs.append((dy, inp, lin.weight.grad, lin.bias.grad, inv_s, inv_dev))
                 if l > 0:
                     dprobs.append((dy, self.group.shadow16(lin.weight), inp, dz(net, gbuf, l), net.acts[l - 1]))
             if dprobs:
@@ -414,4 +438,4 @@ class FeedForwardEngine:
             int(hp["use_clipped_value_loss"]),
             self.dmu16.data_ptr() if self.head16 else None, self.dmu16.stride(0) if self.head16 else 0,
             self.dvalue16.data_ptr() if self.head16 else None, self.dvalue16.stride(0) if self.head16 else 0,
-            self.grad_scale, nat.stream_ptr()))
+            self.grad_scale, nat.ptr(self.scale_state), nat.stream_ptr()))

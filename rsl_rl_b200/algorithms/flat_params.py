@@ -142,7 +142,8 @@ class DeviceOptState:
     """`rslrl_opt_state_t` in device memory followed by the loss accumulators, read back with ONE copy.
 
     layout (8-byte words): [0] lr [1] clip_scale [2] total_norm [3] step_size [4] bc2_sqrt [5] kl_mean
-                           [6] step (int64) [7] pad | [8..10] loss sums (surrogate, value, entropy) [11..15] spare
+                           [6] step (int64) [7] pad | [8..10] loss sums (surrogate, value, entropy) [11] spare
+                           [12..15] = 8 floats: the dynamic fp16 gradient scale state of rslrl_ppo_loss_fwd_bwd
     """
 
     WORDS = 16
@@ -152,6 +153,7 @@ class DeviceOptState:
         self.as_int = self.buf.view(torch.int64)
         self.buf[0] = lr
         self.loss_sums = self.buf[8:11]
+        self.scale_state = self.buf[12:16].view(torch.float32)   # float[8], see include/rslrl_b200.h
 
     def ptr(self) -> int:
         return self.buf.data_ptr()
@@ -165,8 +167,12 @@ class DeviceOptState:
     def read(self):
         host = self.buf.cpu()
         step = int(host.view(torch.int64)[6])
+        sat = int(host.view(torch.int32)[2 * 12 + 4])   # scale_state[4]: saturated fp16 gradient launches
+        if sat:
+            self.scale_state[4:5].zero_()
         return dict(lr=float(host[0]), clip_scale=float(host[1]), total_norm=float(host[2]), kl_mean=float(host[5]),
-                    step=step, loss_sums=[float(host[8]), float(host[9]), float(host[10])])
+                    step=step, loss_sums=[float(host[8]), float(host[9]), float(host[10])], fp16_saturations=sat,
+                    fp16_grad_scale=float(host.view(torch.float32)[2 * 12 + 2]))
 
 
 class FusedAdam(torch.optim.Adam):

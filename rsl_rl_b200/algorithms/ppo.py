@@ -161,6 +161,7 @@ class PPO:
         self._act_plans = {}
         self._act_in = None
         self._lineup = None
+        self._fp16_saturations = 0   # running count of saturated fp16 gradient launches (dynamic scale)
         self._draw_offset = None   # Philox offset consumed by one discarded torch.normal draw in update()
         self._mb_hook = None  # test hook: called after every minibatch backward in eager mode
         self.last_update_info = {}
@@ -192,7 +193,8 @@ class PPO:
                 precision = "tf32"   # the composite update runs the MLPs under autograd (tf32 tensor cores there)
             self._engine = _engine.FeedForwardEngine(self.policy, B if self._update_reason is None else num_envs, num_envs,
                                                      mb if self._update_reason is None else num_envs, self.device,
-                                                     precision, self._group)
+                                                     precision, self._group,
+                                                     scale_state=self.optimizer.dev_state.scale_state)
             self._last_values = torch.empty(num_envs, 1, dtype=torch.float32, device=self.device)
             if self._update_reason is None:
                 self._alloc_update_buffers(num_envs, num_transitions_per_env)
@@ -547,6 +549,12 @@ class PPO:
         self.learning_rate = info["lr"]
         self.optimizer.sync_host_state(self.learning_rate)
         self.last_update_info = info
+        self._fp16_saturations += info.get("fp16_saturations", 0)
+        if info.get("fp16_saturations", 0):
+            import warnings
+            warnings.warn(f"rsl_rl_b200: {info['fp16_saturations']} minibatch(es) of this update had output gradients "
+                          "beyond the fp16 range at the current dynamic scale (saturated, then rescaled); a persistent "
+                          "warning means gemm_precision='tf32' is the safer choice for this reward scale")
         self.storage.clear()
         s = info["loss_sums"]
         return {"value_function": s[1] / n, "surrogate": s[0] / n, "entropy": s[2] / n}

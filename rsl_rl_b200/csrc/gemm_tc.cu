@@ -47,6 +47,7 @@ struct TcProblem {
   int M, N, K;        // C is [M,N], reduction length K
   int ldc, act, tma_out;
   float out_scale;    // wgrad: dW, db += out_scale * (...)  (undoes the power-of-two gradient scaling of the fp16 path)
+  const float* out_scale_dev;  // optional device-resident factor multiplied into out_scale (dynamic gradient scale)
   int block_n, tiles_m, tiles_n, splits, kb_per_split, num_kb;
 };
 
@@ -185,6 +186,8 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   pdl_wait();  // the prologue above touched no global memory; the operands below come from the previous kernels
+  if (MODE == TC_WGRAD && threadIdx.x < n_problems && batch.p[threadIdx.x].out_scale_dev != nullptr)
+    sp[threadIdx.x].out_scale *= __ldcg(batch.p[threadIdx.x].out_scale_dev);  // 1 / (dynamic scale of this minibatch)
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -803,7 +806,7 @@ int tc_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* pr, cudaSt
       set_error("%s: cuTensorMapEncodeTiled failed", what);
       return 1;
     }
-    P.C = q.dw; P.db = q.db; P.M = q.N; P.N = q.K; P.K = q.M; P.ldc = q.K; P.out_scale = q.scale;
+    P.C = q.dw; P.db = q.db; P.M = q.N; P.N = q.K; P.K = q.M; P.ldc = q.K; P.out_scale = q.scale; P.out_scale_dev = q.scale_dev;
     P.tma_out = tma_ok(q.dw, q.K) && make_map(&P.map_c, q.dw, q.N, q.K, q.K, 32, 32, false, false);
     P.num_kb = (q.M + TC_BLOCK_K - 1) / TC_BLOCK_K;
     int want = (2 * kNumSMs + tiles_all - 1) / tiles_all;   // ~2 CTAs worth of work per SM
@@ -882,7 +885,7 @@ int tc16_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* pr, cuda
       set_error("%s: cuTensorMapEncodeTiled failed", what);
       return 1;
     }
-    P.C = q.dw; P.db = q.db; P.M = q.N; P.N = q.K; P.K = q.M; P.ldc = q.K; P.out_scale = q.scale; P.tma_out = c_tma ? 1 : 0;
+    P.C = q.dw; P.db = q.db; P.M = q.N; P.N = q.K; P.K = q.M; P.ldc = q.K; P.out_scale = q.scale; P.out_scale_dev = q.scale_dev; P.tma_out = c_tma ? 1 : 0;
     P.num_kb = (q.M + 63) / 64;
   }
   // k-splits: every work item (tile x k-range) of every grouped problem streams about the same number of bytes, and

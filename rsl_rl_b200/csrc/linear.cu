@@ -70,6 +70,7 @@ int rslrl_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* probs_h
   for (int i = 0; i < n; ++i) {
     const rslrl_linear_bwd_weight_t& p = probs_host[i];
     RSLRL_CHECK_ARG(p.dy && p.x && p.dw && p.M > 0 && p.N > 0 && p.K > 0 && p.ldy >= p.N && p.ldx >= p.K, what);
+    RSLRL_CHECK_ARG(p.scale_dev == nullptr || precision == RSLRL_PREC_FP16, what);  // dynamic scale: fp16 chain only
   }
   if (precision == RSLRL_PREC_FP32) return simt_linear_backward_weight(n, probs_host, (cudaStream_t)stream);
   if (precision == RSLRL_PREC_TF32) {

@@ -34,6 +34,45 @@ struct SumWorkspace {
   unsigned int pad_;
 };
 
+// ---- dynamic power-of-two scale of the fp16 gradient copies (S * dmu, S * dvalue) ---------------------------------------
+// scale_state (device float[8], optional): [0] S of the most recent launch, [1] 1 / S (read by the weight-gradient
+// kernel of the same minibatch), [2] S for the NEXT launch, [3] running max |gradient| of the current launch (uint bits),
+// [4] saturation events (uint): launches in which S * max|gradient| left fp16's finite range.  Every launch scales with
+// the value the previous one left in [2] (chosen so that S * max lands in [2^11, 2^12): 16x headroom for growth between
+// consecutive minibatches, 2^-26 of the maximum still representable); the last block of a launch publishes [0], [1],
+// counts a saturation if there was one and derives [2] from the maximum it saw.
+#define RSLRL_LOSS_SCALE_PROLOGUE                                                                     \
+  const float scale16 = scale_state != nullptr ? __ldcg(scale_state + 2) : scale16_arg;               \
+  __shared__ unsigned int s_gmax;                                                                     \
+  if (threadIdx.x == 0) s_gmax = 0u;
+
+__device__ __forceinline__ void loss_scale_track(float* scale_state, unsigned int* s_gmax, float local_max) {
+  if (scale_state == nullptr) return;
+  float m = local_max;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(s_gmax, __float_as_uint(m));
+}
+__device__ __forceinline__ void loss_scale_block_publish(float* scale_state, const unsigned int* s_gmax) {
+  // after a __syncthreads: one global atomic per block
+  if (scale_state != nullptr && threadIdx.x == 0 && *s_gmax != 0u) atomicMax((unsigned int*)(scale_state + 3), *s_gmax);
+}
+__device__ __forceinline__ void loss_scale_finalize(float* scale_state, float S) {
+  // last block, one thread, after the ticket fence
+  if (scale_state == nullptr) return;
+  const float mx = __uint_as_float(*((volatile unsigned int*)(scale_state + 3)));
+  scale_state[0] = S;
+  scale_state[1] = 1.0f / S;
+  if (mx * S > 60000.0f) atomicAdd((unsigned int*)(scale_state + 4), 1u);
+  float next = S;
+  if (mx > 0.f && isfinite(mx)) {
+    next = exp2f(floorf(log2f(4096.0f / mx)));
+    next = fminf(fmaxf(next, 9.5367431640625e-07f), 1073741824.0f);   // [2^-20, 2^30]
+  }
+  scale_state[2] = next;
+  *((unsigned int*)(scale_state + 3)) = 0u;
+}
+
 __global__ void __launch_bounds__(kLossThreads)
 gaussian_act_kernel(const float* __restrict__ mu, const float* __restrict__ std_param, int std_type,
                     const float* __restrict__ z, float* __restrict__ actions, float* __restrict__ log_prob,
@@ -75,9 +114,10 @@ ppo_loss_kernel(const float* __restrict__ mu, const float* __restrict__ std_para
                 float* __restrict__ dvalue, int dvalue_stride, float* dstd, float* db_mu, float* db_value,
                 float* kl_out, double* loss_sums, LossWorkspace* ws, long long rows, long long mb_orig,
                 int A, float clip, float c_v, float c_e, int use_clipped, __half* __restrict__ dmu16, int dmu16_stride,
-                __half* __restrict__ dvalue16, int dvalue16_stride, float scale16) {
+                __half* __restrict__ dvalue16, int dvalue16_stride, float scale16_arg, float* scale_state) {
   pdl_trigger();
   pdl_wait();
+  RSLRL_LOSS_SCALE_PROLOGUE
   __shared__ float s_sigma[kMaxActions], s_logs[kMaxActions], s_2var[kMaxActions];
   __shared__ double s_red[4 * 32];
   __shared__ float s_dstd[kMaxActions], s_dbmu[kMaxActions];
@@ -138,7 +178,7 @@ ppo_loss_kernel(const float* __restrict__ mu, const float* __restrict__ std_para
     }
   }
 
-  float g_lp = 0.f, surr = 0.f, vl = 0.f, dv_sum = 0.f;
+  float g_lp = 0.f, surr = 0.f, vl = 0.f, dv_sum = 0.f, gmax = 0.f;
   if (valid) {
     float adv = __ldg(advantages + j);
     if (adv_stats) {  // per-minibatch normalisation (ppo.py:221-223), unbiased std
@@ -181,6 +221,7 @@ ppo_loss_kernel(const float* __restrict__ mu, const float* __restrict__ std_para
     dvalue[i * dvalue_stride] = dv_out;
     if (dvalue16 != nullptr) dvalue16[i * dvalue16_stride] = __float2half_rn(dv_out * scale16);
     dv_sum = dv_out;
+    gmax = fabsf(dv_out);
   }
 
   // second pass over the row: dL/dmu and the per-action dL/dsigma column sums
@@ -216,6 +257,7 @@ ppo_loss_kernel(const float* __restrict__ mu, const float* __restrict__ std_para
       if (valid) {
         if (VEC) *(float4*)(dm + c) = make_float4(o[0], o[1], o[2], o[3]);
         else for (int q = 0; q < nq; ++q) dm[c + q] = o[q];
+        gmax = fmaxf(fmaxf(gmax, fmaxf(fabsf(o[0]), fabsf(o[1]))), fmaxf(fabsf(o[2]), fabsf(o[3])));
         if (VEC && dmu16 != nullptr) {  // scaled fp16 copy (A % 4 == 0): the A operand of the fp16 output-layer backward
           const __half2 lo2 = __floats2half2_rn(o[0] * scale16, o[1] * scale16), hi2 = __floats2half2_rn(o[2] * scale16, o[3] * scale16);
           uint2 w;
@@ -227,8 +269,10 @@ ppo_loss_kernel(const float* __restrict__ mu, const float* __restrict__ std_para
     }
   }
 
+  loss_scale_track(scale_state, &s_gmax, gmax);
   double red[4] = {(double)kl, (double)surr, (double)vl, (double)dv_sum};
-  block_sum<4>(red, s_red);
+  block_sum<4>(red, s_red);   // (its barriers also order the shared-memory maximum)
+  loss_scale_block_publish(scale_state, &s_gmax);
   if (threadIdx.x == 0) {
     atomicAdd(&ws->acc[0], red[0]);
     atomicAdd(&ws->acc[1], red[1]);
@@ -273,6 +317,7 @@ ppo_loss_kernel(const float* __restrict__ mu, const float* __restrict__ std_para
       loss_sums[2] += (double)ent;
     }
     ws->acc[0] = ws->acc[1] = ws->acc[2] = ws->acc[3] = 0.0;
+    loss_scale_finalize(scale_state, scale16);
     __threadfence();
     ws->ticket = 0u;
   }
@@ -294,9 +339,10 @@ ppo_loss_quad_kernel(const float* __restrict__ mu, const float* __restrict__ std
                      float* __restrict__ dvalue, int dvalue_stride, float* dstd, float* db_mu, float* db_value,
                      float* kl_out, double* loss_sums, LossWorkspace* ws, long long rows, long long mb_orig,
                      int A, float clip, float c_v, float c_e, int use_clipped, __half* __restrict__ dmu16,
-                     int dmu16_stride, __half* __restrict__ dvalue16, int dvalue16_stride, float scale16) {
+                     int dmu16_stride, __half* __restrict__ dvalue16, int dvalue16_stride, float scale16_arg, float* scale_state) {
   pdl_trigger();
   pdl_wait();
+  RSLRL_LOSS_SCALE_PROLOGUE
   __shared__ float s_sigma[kMaxActions], s_logs[kMaxActions], s_2var[kMaxActions];
   __shared__ double s_red[4 * 32];
   __shared__ float s_dstd[kMaxActions], s_dbmu[kMaxActions];
@@ -347,7 +393,7 @@ ppo_loss_quad_kernel(const float* __restrict__ mu, const float* __restrict__ std
   lp += __shfl_xor_sync(0xffffffffu, lp, 1);
   lp += __shfl_xor_sync(0xffffffffu, lp, 2);
 
-  float g_lp = 0.f, surr = 0.f, vl = 0.f, dv_sum = 0.f;
+  float g_lp = 0.f, surr = 0.f, vl = 0.f, dv_sum = 0.f, gmax = 0.f;
   if (valid) {
     float adv = __ldg(advantages + j);
     if (adv_stats) {  // per-minibatch normalisation (ppo.py:221-223), unbiased std
@@ -389,6 +435,7 @@ ppo_loss_quad_kernel(const float* __restrict__ mu, const float* __restrict__ std
       dvalue[i * dvalue_stride] = dv_out;
       if (dvalue16 != nullptr) dvalue16[i * dvalue16_stride] = __float2half_rn(dv_out * scale16);
       dv_sum = dv_out;
+      gmax = fabsf(dv_out);
     }
   }
 
@@ -403,6 +450,7 @@ ppo_loss_quad_kernel(const float* __restrict__ mu, const float* __restrict__ std
       ds[q] = mine ? g_lp * (d[q] * d[q] / (var * s) - 1.f / s) : 0.f;
     }
     if (mine) {
+      gmax = fmaxf(fmaxf(gmax, fmaxf(fabsf(o[0]), fabsf(o[1]))), fmaxf(fabsf(o[2]), fabsf(o[3])));
       *(float4*)(dmu + i * dmu_stride + c) = make_float4(o[0], o[1], o[2], o[3]);
       if (dmu16 != nullptr) {  // scaled fp16 copy: the A operand of the fp16 output-layer backward
         const __half2 lo2 = __floats2half2_rn(o[0] * scale16, o[1] * scale16), hi2 = __floats2half2_rn(o[2] * scale16, o[3] * scale16);
@@ -426,8 +474,10 @@ ppo_loss_quad_kernel(const float* __restrict__ mu, const float* __restrict__ std
     }
   }
 
+  loss_scale_track(scale_state, &s_gmax, gmax);
   double red[4] = {(double)kl, (double)surr, (double)vl, (double)dv_sum};
-  block_sum<4>(red, s_red);
+  block_sum<4>(red, s_red);   // (its barriers also order the shared-memory maximum)
+  loss_scale_block_publish(scale_state, &s_gmax);
   if (threadIdx.x == 0) {
     atomicAdd(&ws->acc[0], red[0]);
     atomicAdd(&ws->acc[1], red[1]);
@@ -471,6 +521,7 @@ ppo_loss_quad_kernel(const float* __restrict__ mu, const float* __restrict__ std
       loss_sums[2] += (double)ent;
     }
     ws->acc[0] = ws->acc[1] = ws->acc[2] = ws->acc[3] = 0.0;
+    loss_scale_finalize(scale_state, scale16);
     __threadfence();
     ws->ticket = 0u;
   }
@@ -530,7 +581,8 @@ int rslrl_ppo_loss_fwd_bwd(const float* mu, const float* std_param, int std_type
                            float* kl_out, double* loss_sums, void* workspace, int64_t rows,
                            int64_t mb_orig, int A, double clip_param, double value_loss_coef,
                            double entropy_coef, int use_clipped_value_loss, void* dmu16, int dmu16_stride,
-                           void* dvalue16, int dvalue16_stride, double grad_scale16, rslrl_stream_t stream) {
+                           void* dvalue16, int dvalue16_stride, double grad_scale16, float* scale_state,
+                           rslrl_stream_t stream) {
   using namespace rslrl;
   const char* what = "rslrl_ppo_loss_fwd_bwd";
   RSLRL_CHECK_ARG(mu && std_param && value && actions && old_logp && advantages && returns && old_values, what);
@@ -552,7 +604,7 @@ int rslrl_ppo_loss_fwd_bwd(const float* mu, const float* std_param, int std_type
         actions, old_logp, advantages, returns, old_values, old_mu, old_sigma, adv_stats, dmu, dmu_stride, dvalue,
         dvalue_stride, dstd, db_mu, db_value, kl_out, loss_sums, (LossWorkspace*)workspace, (long long)rows,
         (long long)mb_orig, A, (float)clip_param, (float)value_loss_coef, (float)entropy_coef, use_clipped_value_loss,
-        (__half*)dmu16, dmu16_stride, (__half*)dvalue16, dvalue16_stride, (float)grad_scale16);
+        (__half*)dmu16, dmu16_stride, (__half*)dvalue16, dvalue16_stride, (float)grad_scale16, scale_state);
     return finish_launch(what);
   }
   if ((dmu16 != nullptr || dvalue16 != nullptr) && !vec) {
@@ -565,7 +617,7 @@ int rslrl_ppo_loss_fwd_bwd(const float* mu, const float* std_param, int std_type
       dmu, dmu_stride, dvalue, dvalue_stride, dstd, db_mu, db_value, kl_out, loss_sums, (LossWorkspace*)workspace, (long long)rows,
       (long long)mb_orig, A, (float)clip_param,
       (float)value_loss_coef, (float)entropy_coef, use_clipped_value_loss, (__half*)dmu16, dmu16_stride, (__half*)dvalue16,
-      dvalue16_stride, (float)grad_scale16);
+      dvalue16_stride, (float)grad_scale16, scale_state);
   return finish_launch(what);
 }
 

@@ -87,13 +87,13 @@ def linear_backward_data(problems: Sequence[Tuple], precision: int):
 
 
 def linear_backward_weight(problems: Sequence[Tuple], precision: int):
-    """problems: (dy[M,N], x[M,K], dw[N,K] (accumulated), db[N]|None (accumulated)[, scale])."""
+    """problems: (dy[M,N], x[M,K], dw[N,K] (accumulated), db[N]|None (accumulated)[, scale[, scale_dev_ptr]])."""
     arr = (nat.LinearBwdWeight * len(problems))()
     for i, prob in enumerate(problems):
         dy, x, dw, db = prob[:4]
         arr[i] = nat.LinearBwdWeight(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), nat.ptr(db), dy.shape[0],
                                      dw.shape[0], dw.shape[1], dy.stride(0), x.stride(0),
-                                     prob[4] if len(prob) > 4 else 1.0)
+                                     prob[4] if len(prob) > 4 else 1.0, prob[5] if len(prob) > 5 else None)
     nat.check(nat.lib().rslrl_linear_backward_weight(len(problems), arr, precision, nat.stream_ptr()))
 
 

@@ -159,7 +159,9 @@ class RolloutStorage:
         to_ptr, tcode = None, 0
         if time_outs is not None:
             if time_outs.device != rewards.device:
-                time_outs = time_outs.to(rewards.device)
+                # (pinned host source: asynchronous like the runner's copies of obs / rewards / dones; the next blocking
+                # read-back of the actions is the synchronisation point the env relies on)
+                time_outs = time_outs.to(rewards.device, non_blocking=time_outs.is_pinned())
             time_outs, tcode = nat.flag_tensor(time_outs)
             to_ptr = time_outs.data_ptr()
         intr_t = None if intrinsic is None else nat.f32c(intrinsic)

@@ -303,7 +303,7 @@ def _run_loss(mu, std_param, std_type, value, actions, old_logp, adv, ret, old_v
             d["old_sigma"].data_ptr(), nat.ptr(stats), dmu.data_ptr(), A4, dv.data_ptr(), 4, dstd.data_ptr(),
             db_mu.data_ptr(), db_v.data_ptr(), kl.data_ptr(), sums.data_ptr(), ws.data_ptr(), rows, mb_orig, A, 0.2, 1.0,
             0.01, int(clipped), dmu16.data_ptr() if f16out else None, dmu16.stride(0), dv16.data_ptr() if f16out else None,
-            dv16.stride(0), S16, nat.stream_ptr()))
+            dv16.stride(0), S16, None, nat.stream_ptr()))
     torch.cuda.synchronize()
     if f16out:
         assert torch.equal(dmu16[:, :A], (dmu * S16).half()) and torch.equal(dv16[:, 0], (dv * S16).half())

@@ -195,39 +195,60 @@ def test_c1_shape_full_iteration_vs_oracle():
     assert rel_err(r["mine"], r["ref"]) < 1e-4
 
 
+def _check_tensor_core_class(r, floor):
+    """North-star class for TF32 / 16-bit GEMMs (1e-3): rollout products, the first-minibatch gradient in MAX norm and
+    the per-minibatch parameter trace in relative L2 up to the first KL-adaptive LR decision that differs.
+    The max norm of the parameter trace is bounded by the class's own noise floor instead: Adam divides the gradient by
+    its magnitude, so a gradient element whose SIGN is decided by operand rounding moves its parameter by +-lr either
+    way -- the fp32 oracle with tf32-rounded matmul operands (tools/parity_report.tf32_noise_floor) shows the same
+    2 * lr = 2.9e-3 after one step, at every shape."""
+    for k in ("rollout.mu", "rollout.values", "rollout.actions_log_prob", "rollout.returns", "rollout.advantages"):
+        assert r[k] < 1e-3, (k, r[k])
+    assert r["rollout.dones_equal"] and r["finite"]
+    assert r["grad0.max_norm"] < 1e-3, r["grad0.max_norm"]
+    assert r["lr.steps_in_agreement"] >= 1
+    assert r["params_after.rel_l2_until_lr_divergence"] < 1e-3, r["params_after.rel_l2_until_lr_divergence"]
+    assert r["params_after.max_norm_until_lr_divergence"] < 1.25 * floor["params_after_max_norm"] + 1e-4, \
+        (r["params_after.max_norm_until_lr_divergence"], floor["params_after_max_norm"])
+    if r["lr.steps_in_agreement"] < 20:   # a KL within rounding noise of a threshold flipped one decision: 1.5x steps
+        ratio = r["lr.mine"] / r["lr.ref"]
+        assert min(abs(ratio - 1.5 ** k) for k in range(-4, 5)) < 1e-6, "lr trajectories differ by more than threshold flips"
+
+
 @pytest.mark.parametrize("prec", ["tf32", "fp16"])
-def test_tf32_tensor_core_iteration_vs_oracle(prec):
-    """gemm_precision='tf32' / 'fp16' (tcgen05) at the C1 shape: policy outputs and losses within the 1e-3 class.
-    Post-update parameters are compared in relative L2 norm of the UPDATE (theta_new - theta_old): Adam's
-    sign-like normalisation makes a max-norm comparison of 20 accumulated steps meaningless at tf32 noise."""
-    meta, obs, rewards, dones, time_outs, z, perms = _synthetic_problem(4096, 24, 48, 12, [512, 256, 128], 1, seed=9)
-    r = _run_both(meta, obs, rewards, dones, time_outs, z, perms, 1, capture_grads=True, use_cuda_graph=False,
-                  gemm_precision=prec)[0]
-    st, alg = r["st"], r["alg"]
-    s = alg.storage
-    assert alg._engine.f16 == (prec == "fp16")
-    assert rel_err(s.mu.cpu().numpy(), st["mu"]) < 1e-3
-    assert rel_err(s.values.cpu().numpy(), st["values"]) < 1e-3
-    assert rel_err(s.actions_log_prob.cpu().numpy(), st["actions_log_prob"]) < 1e-3
-    assert rel_err(s.returns.cpu().numpy(), st["returns"]) < 1e-3
-    grp = alg._group
-    pick = torch.cat([torch.arange(o, o + q.numel()) for o, q in zip(grp.offsets, grp.params)]).to(DEV)
-    g0, g0_ref = r["raw"][0][pick].cpu().numpy().astype(np.float64), r["trace"][0]["grads"].astype(np.float64)
-    assert np.linalg.norm(g0 - g0_ref) / np.linalg.norm(g0_ref) < 2e-3
-    init = np.concatenate([v.reshape(-1) for v in _init_params_like_torch(meta, 0).values()]).astype(np.float64)
-    upd, upd_ref = r["mine"].astype(np.float64) - init, r["ref"].astype(np.float64) - init
-    print(prec, "update rel L2 err", np.linalg.norm(upd - upd_ref) / np.linalg.norm(upd_ref),
-          "max-norm param err", rel_err(r["mine"], r["ref"]), "lr", r["lr_mine"], r["lr_ref"])
-    # The KL-adaptive rule is a threshold decision per minibatch: tf32 rounding (and the summation order of the
-    # split-K reductions) may legitimately flip one of the 20 decisions when a KL lands within ~1e-3 of a
-    # threshold, which rescales every later step by 1.5x.  The accumulated update is therefore only compared
-    # when the two learning-rate trajectories ended in the same place.
-    if abs(r["lr_mine"] - r["lr_ref"]) < 1e-12:
-        assert np.linalg.norm(upd - upd_ref) / np.linalg.norm(upd_ref) < 5e-2
-        assert rel_err(r["mine"], r["ref"]) < 1e-2
-    else:
-        ratio = r["lr_mine"] / r["lr_ref"]
-        assert min(abs(ratio - 1.5 ** k) for k in range(-3, 4)) < 1e-6, "lr trajectories differ by more than threshold flips"
+def test_tensor_core_iteration_vs_oracle_c1(prec):
+    """gemm_precision='tf32' / 'fp16' (tcgen05) at the C1/C2 shape (4096 envs, obs 48, MLP [512,256,128])."""
+    from tools import parity_report as R
+    r = R.compare("c1", prec)
+    print({k: v for k, v in r.items() if k != "params_after.max_norm_per_step"})
+    _check_tensor_core_class(r, R.tf32_noise_floor("c1"))
+
+
+def test_tensor_core_iteration_vs_oracle_c3_layout():
+    """The benchmark default (fp16) on C3's observation layout: two groups 48 + 187 = 235 columns (rows not 16-byte
+    aligned: padded first-layer shadow, staged rollout inputs, vector-atomic first-layer weight gradient), 8192 envs."""
+    from tools import parity_report as R
+    r = R.compare("c3", "fp16")
+    print({k: v for k, v in r.items() if k != "params_after.max_norm_per_step"})
+    _check_tensor_core_class(r, R.tf32_noise_floor("c1"))   # (the floor is 2 * lr at every shape; c1's is cached)
+
+
+@pytest.mark.parametrize("reward_scale", [1e4, 1e-4])
+def test_fp16_gradient_range_is_tracked(reward_scale):
+    """fp16 storage of the layer gradients under extreme reward magnitudes (value-loss gradients ~ reward scale): the
+    device-resident dynamic power-of-two scale follows the gradient magnitude, nothing saturates after the first
+    minibatch has calibrated it, results stay finite and in the 1e-3 class."""
+    from tools import parity_report as R
+    R.SHAPES["range"] = dict(N=1024, T=8, groups={"policy": 48}, A=12, hidden=[128, 128, 64], seed=31)
+    r = R.compare("range", "fp16", reward_scale=reward_scale)
+    print({k: v for k, v in r.items() if k != "params_after.max_norm_per_step"})
+    assert r["finite"]
+    for k in ("rollout.mu", "rollout.values", "rollout.returns"):
+        assert r[k] < 1e-3, (k, r[k])
+    assert r["grad0.max_norm"] < 2e-3 or r["fp16_saturation_events"] > 0, r["grad0.max_norm"]
+    # at most the very first minibatch (scale still at its initial guess) may saturate; it is counted, never silent
+    assert r["fp16_saturation_events"] <= 1, r["fp16_saturation_events"]
+    assert r["params_after.rel_l2_until_lr_divergence"] is None or r["params_after.rel_l2_until_lr_divergence"] < 2e-3
 
 
 def test_tf32_unaligned_observation_width_vs_oracle():

@@ -67,20 +67,42 @@ def init_params(meta, seed=0):
     return OrderedDict((k, v.detach().numpy().copy()) for k, v in pol.named_parameters())
 
 
-def oracle_run(shape: str, reward_scale: float = 1.0):
+def oracle_run(shape: str, reward_scale: float = 1.0, gemm_round=None):
+    """gemm_round="tf32": the oracle with every matmul operand rounded to tf32 (noise floor of the tensor-core class)."""
     from oracle import ppo_oracle as O
 
-    key = (shape, reward_scale)
+    key = (shape, reward_scale, gemm_round)
     if key not in _ORACLE_CACHE:
+        O.GEMM_ROUND = gemm_round
         meta, obs, rewards, dones, time_outs, z, perm = problem(shape, reward_scale)
         params = init_params(meta)
         cfg = dict(meta["alg"], activation="elu", noise_std_type="scalar")
         cat = np.concatenate([obs[k] for k in meta["obs_groups"]["policy"]], axis=-1)
         stream = dict(obs_actor=cat, obs_critic=cat, rewards=rewards, dones=dones, time_outs=time_outs)
         st, last_values, loss_dict, lr, trace = O.learn_iteration(params, O.adam_init(params), 1e-3, stream, z, perm, cfg)
+        O.GEMM_ROUND = None
         _ORACLE_CACHE[key] = dict(st=st, lr=lr, trace=trace, loss=loss_dict,
                                   final=np.concatenate([v.reshape(-1) for v in params.values()]))
     return _ORACLE_CACHE[key]
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def tf32_noise_floor(shape: str):
+    """fp32 oracle vs the same oracle with tf32-rounded matmul operands: what the arithmetic class itself costs."""
+    ref, emu = oracle_run(shape), oracle_run(shape, gemm_round="tf32")
+    n = 0
+    while n < len(ref["trace"]) and abs(emu["trace"][n]["lr"] - ref["trace"][n]["lr"]) <= 1e-12 * ref["trace"][n]["lr"]:
+        n += 1
+    per_step = [rel_err(emu["trace"][i]["params_after"], ref["trace"][i]["params_after"]) for i in range(n)]
+    l2 = [rel_l2(emu["trace"][i]["params_after"], ref["trace"][i]["params_after"]) for i in range(n)]
+    return dict(shape=shape, what="oracle(tf32-rounded matmul operands) vs oracle(fp32)",
+                grad0_max_norm=rel_err(emu["trace"][0]["grads"], ref["trace"][0]["grads"]), lr_steps_in_agreement=n,
+                params_after_max_norm=max(per_step) if per_step else None, params_after_step1=per_step[0] if per_step else None,
+                params_after_rel_l2=max(l2) if l2 else None)
 
 
 def cuda_run(shape: str, precision: str, reward_scale: float = 1.0, dev="cuda:0"):
@@ -121,6 +143,7 @@ def cuda_run(shape: str, precision: str, reward_scale: float = 1.0, dev="cuda:0"
     s = alg.storage
     storage = {k: getattr(s, k).cpu().numpy().copy() for k in ("mu", "values", "actions_log_prob", "returns", "advantages", "dones")}
     info = dict(alg.last_update_info)
+    info["fp16_saturation_events"] = alg._fp16_saturations
     del runner, alg, env
     torch.cuda.empty_cache()
     return dict(grads=grads, params_after=params_after, lr_after=lr_after, storage=storage, final=final, init=init,
@@ -146,6 +169,8 @@ def compare(shape: str, precision: str, reward_scale: float = 1.0):
     out["lr.mine"], out["lr.ref"] = mine["lr_after"][-1], lr_ref[-1]
     per_step = [rel_err(mine["params_after"][i], trace[i]["params_after"]) for i in range(agree)]
     out["params_after.max_norm_per_step"] = per_step
+    l2 = [rel_l2(mine["params_after"][i], trace[i]["params_after"]) for i in range(agree)]
+    out["params_after.rel_l2_until_lr_divergence"] = max(l2) if l2 else None
     out["params_after.max_norm_until_lr_divergence"] = max(per_step) if per_step else None
     out["params_after.step1"] = per_step[0] if per_step else None
     init = np.concatenate([v.reshape(-1) for v in mine["init"].values()]).astype(np.float64)
@@ -154,6 +179,7 @@ def compare(shape: str, precision: str, reward_scale: float = 1.0):
         out["update.rel_l2"] = float(np.linalg.norm(upd - upd_ref) / np.linalg.norm(upd_ref))
         out["params_final.max_norm"] = rel_err(mine["final"], ref["final"])
     out["finite"] = bool(np.isfinite(mine["final"]).all())
+    out["fp16_saturation_events"] = mine["info"]["fp16_saturation_events"]
     return out
 
 
@@ -169,10 +195,15 @@ def main():
             r = compare(shape, prec)
             rows.append(r)
             print(json.dumps({k: v for k, v in r.items() if k != "params_after.max_norm_per_step"}), flush=True)
+    floors = []
+    if "tf32" in args.precisions or "fp16" in args.precisions:
+        for shape in args.shapes.split(","):
+            floors.append(tf32_noise_floor(shape))
+            print(json.dumps(floors[-1]), flush=True)
     with open(args.out, "w") as fh:
         json.dump(dict(note="max-abs error / max-abs reference value against oracle/ppo_oracle.py (numpy fp32); one learn() "
                             "iteration with shared noise and permutation; shapes: " + json.dumps(SHAPES),
-                       rows=rows), fh, indent=1)
+                       rows=rows, tf32_class_noise_floor=floors), fh, indent=1)
     print("wrote", args.out)
 
 
