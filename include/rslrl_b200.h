@@ -202,6 +202,19 @@ int rslrl_mlp3_plan_create(int n, const rslrl_mlp3_fwd_t* nets_host, void** plan
 int rslrl_mlp3_plan_run(void* plan, const float* const* x_host, rslrl_stream_t stream);
 void rslrl_mlp3_plan_destroy(void* plan);
 
+/* ---- running-statistics normaliser (rsl_rl/networks/normalization.py:44-66) ---------------------------- */
+
+/* EmpiricalNormalization.update(x) in one launch: batch mean / biased variance of x [N,D] (row stride ldx) folded into the
+ * running buffers mean/var/std [D] and count (int64, device) with the reference's Chan update in its fp32 operation order;
+ * `until` < 0 disables the freeze test, otherwise nothing changes once count >= until (tested on the device).
+ * workspace: rslrl_empirical_norm_workspace_bytes(D) bytes, zero-initialised once. */
+int64_t rslrl_empirical_norm_workspace_bytes(int D);
+int rslrl_empirical_norm_update(const float* x, int64_t ldx, int64_t N, int D, float* mean, float* var, float* std,
+                                int64_t* count, int64_t until, void* workspace, rslrl_stream_t stream);
+/* EmpiricalNormalization.forward: y = (x - mean) / (std + eps), bit-exact in fp32; y row stride ldy >= D. */
+int rslrl_empirical_normalize(const float* x, int64_t ldx, int64_t N, int D, const float* mean, const float* std,
+                              double eps, float* y, int64_t ldy, rslrl_stream_t stream);
+
 /* ---- PPO objective (rsl_rl/algorithms/ppo.py:255-315), forward + hand-derived backward ---------- */
 
 /* rows = num_aug * mb_orig samples (symmetry augmentation repeats the per-sample scalars,

@@ -167,7 +167,7 @@ def _storage_arrays(storage):
 
 def scenario_ppo_mlp(out_dir, name, *, num_envs, num_steps, group_dims, obs_groups, num_actions, hidden,
                      activation, noise_std_type, alg_overrides, iterations, seed=0, p_done=0.1,
-                     policy_class="ActorCritic", policy_extra=None, rnd_cfg=None, symmetry=False):
+                     policy_class="ActorCritic", policy_extra=None, rnd_cfg=None, symmetry=False, checkpoint=False):
     import torch
     from rsl_rl.runners import OnPolicyRunner
 
@@ -202,6 +202,15 @@ def scenario_ppo_mlp(out_dir, name, *, num_envs, num_steps, group_dims, obs_grou
     with Recorder() as rec:
         runner = OnPolicyRunner(env, cfg, log_dir=tempfile.mkdtemp(prefix="golden_"), device="cpu")
         rec.watch_optimizer(runner.alg.optimizer, runner.alg.policy)
+        logged = []                       # what the reference's log() sees: episode reward / length buffers (f1)
+        orig_log = runner.log
+
+        def log_and_record(locs, *a, **k):
+            logged.append(dict(rew=list(locs["rewbuffer"]), length=list(locs["lenbuffer"]),
+                               loss={kk: float(vv) for kk, vv in locs["loss_dict"].items()}))
+            return orig_log(locs, *a, **k)
+
+        runner.log = log_and_record
         for k, v in _state_arrays(runner.alg.policy).items():
             data[f"init.{k}"] = v
         meta["param_names"] = [k for k, _ in runner.alg.policy.named_parameters()]
@@ -250,8 +259,15 @@ def scenario_ppo_mlp(out_dir, name, *, num_envs, num_steps, group_dims, obs_grou
             data[p + "adam.exp_avg_sq"] = np.concatenate([ost[i]["exp_avg_sq"].numpy().reshape(-1) for i in range(len(ost))])
             data[p + "adam.step"] = np.array(float(ost[0]["step"]))
             data[p + "learning_rate"] = np.array(runner.alg.learning_rate, dtype=np.float64)
-    # loss dict of the last update is not returned by learn(); recompute means from a fresh update is not
-    # possible without re-running, so the per-minibatch losses are pinned through params/grad traces instead.
+            if logged:
+                data[p + "log.rewbuffer"] = np.array(logged[-1]["rew"], dtype=np.float64)
+                data[p + "log.lenbuffer"] = np.array(logged[-1]["length"], dtype=np.float64)
+                for kk, vv in logged[-1]["loss"].items():
+                    data[p + "log.loss." + kk] = np.array(vv, dtype=np.float64)
+        if checkpoint:   # a reference-written checkpoint (on_policy_runner.py:289-305) for the round-trip test (f3)
+            ckpt = os.path.join(out_dir, name + "_ref_checkpoint.pt")
+            runner.save(ckpt)
+            print("wrote", ckpt, f"{os.path.getsize(ckpt) / 1024:.0f} KiB")
     data["meta"] = np.array(repr(meta))
     path = os.path.join(out_dir, name + ".npz")
     np.savez_compressed(path, **data)
@@ -452,6 +468,20 @@ def main():
         rnd_cfg=dict(weight=1.0, weight_schedule=None, reward_normalization=False, state_normalization=False,
                      learning_rate=1e-3, num_outputs=1, predictor_hidden_dims=[-1], target_hidden_dims=[-1]),
         symmetry=True)
+    # observation normalisers on (EmpiricalNormalization, networks/normalization.py:44-66); 4 iterations so that the CUDA
+    # path is checked eager -> graph capture -> graph replay with the running statistics changing every env step
+    todo["ppo_mlp_norm"] = lambda: scenario_ppo_mlp(
+        args.out, "ppo_mlp_norm", num_envs=64, num_steps=8, group_dims={"policy": 12, "priv": 6},
+        obs_groups={"policy": ["policy"], "critic": ["policy", "priv"]}, num_actions=4, hidden=[32, 16, 8],
+        activation="elu", noise_std_type="scalar", alg_overrides={}, iterations=4, seed=12,
+        policy_extra=dict(actor_obs_normalization=True, critic_obs_normalization=True), checkpoint=True)
+    # RND with state and reward normalisation (EmpiricalDiscountedVariationNormalization, normalization.py:75-130)
+    todo["ppo_rnd_norm_small"] = lambda: scenario_ppo_mlp(
+        args.out, "ppo_rnd_norm_small", num_envs=48, num_steps=6, group_dims={"policy": 11},
+        obs_groups={"policy": ["policy"], "critic": ["policy"]}, num_actions=4, hidden=[24, 12],
+        activation="elu", noise_std_type="scalar", alg_overrides=dict(num_learning_epochs=2), iterations=3, seed=18,
+        rnd_cfg=dict(weight=1.0, weight_schedule=None, reward_normalization=True, state_normalization=True,
+                     learning_rate=1e-3, num_outputs=1, predictor_hidden_dims=[-1], target_hidden_dims=[-1]))
     for name, fn in todo.items():
         if args.only in (None, name):
             fn()

@@ -108,6 +108,11 @@ _SIGNATURES = {
     "rslrl_split_and_pad": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_void_p]),
     "rslrl_unpad": (c_int, [c_void_p] * 4 + [c_int] * 7 + [c_void_p]),
     "rslrl_hidden_at_starts": (c_int, [c_void_p] * 4 + [c_int] * 7 + [c_void_p]),
+    "rslrl_empirical_norm_workspace_bytes": (c_i64, [c_int]),
+    "rslrl_empirical_norm_update": (c_int, [c_void_p, c_i64, c_i64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_i64,
+                                            c_void_p, c_void_p]),
+    "rslrl_empirical_normalize": (c_int, [c_void_p, c_i64, c_i64, c_int, c_void_p, c_void_p, c_double, c_void_p, c_i64,
+                                          c_void_p]),
     "rslrl_fill_zero": (c_int, [c_void_p, c_i64, c_void_p]),
     "rslrl_convert_f32_f16": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_i64, c_int, c_int, c_void_p]),
 }

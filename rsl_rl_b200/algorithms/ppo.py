@@ -423,12 +423,13 @@ class PPO:
         st._gather(fields, widths, self._perm, outs, strides, cols)
         xa = self._xa_raw[:, :self._Oa]
         xc = self._xc_raw[:, :self._Oc]
+        # observation normalisers: applied IN PLACE on the permuted copy (one launch each, 16-byte row pitch kept)
         if not isinstance(pol.actor_obs_normalizer, nn.Identity):
-            xa = nat.f32c(pol.actor_obs_normalizer(xa))
+            pol.actor_obs_normalizer(xa, out=self._xa_raw)
         if pol.critic_shares_actor_input:
             xc = xa
         elif not isinstance(pol.critic_obs_normalizer, nn.Identity):
-            xc = nat.f32c(pol.critic_obs_normalizer(xc))
+            pol.critic_obs_normalizer(xc, out=self._xc_raw)
         return xa, xc
 
     def _to_f16(self, x: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:

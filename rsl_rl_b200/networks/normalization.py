@@ -1,12 +1,18 @@
 """Running-statistics normalisers (mirror of `rsl_rl/networks/normalization.py`; buffers keep the
 reference's names `_mean, _var, _std, count` so checkpoints are interchangeable).
 
-These are off in every benchmark configuration; they are plain device-side
-tensor algebra here and are the next fusion candidate (section 8f)."""
+On CUDA tensors `update()` is ONE launch (`rslrl_empirical_norm_update`: batch statistics + Chan update, the `until`
+test on the device, no host synchronisation -- the reference's `if self.count >= self.until` is a device->host sync per
+env step) and `forward()` is one launch (`rslrl_empirical_normalize`, bit-exact `(x - mean) / (std + eps)`).  All four
+buffers are updated IN PLACE: CUDA graphs and the rollout launch plans hold their addresses.  `forward()` keeps the plain
+tensor expression for tensors that need autograd, for tracing / export and for host tensors (inference surface);
+`update()` is a training-path operation and exists on CUDA only."""
 from __future__ import annotations
 
 import torch
 from torch import nn
+
+from .. import _native as nat
 
 
 class EmpiricalNormalization(nn.Module):
@@ -20,6 +26,7 @@ class EmpiricalNormalization(nn.Module):
         self.register_buffer("_var", torch.ones(shape).unsqueeze(0))
         self.register_buffer("_std", torch.ones(shape).unsqueeze(0))
         self.register_buffer("count", torch.tensor(0, dtype=torch.long))
+        self._ws = None
 
     @property
     def mean(self):
@@ -29,24 +36,50 @@ class EmpiricalNormalization(nn.Module):
     def std(self):
         return self._std.squeeze(0).clone()
 
-    def forward(self, x):
-        return (x - self._mean) / (self._std + self.eps)
+    def _rows(self, x):
+        """x viewed as [N, D] fp32 rows (D = number of statistics) -> (tensor, N, D, row stride) or None."""
+        D = self._mean.numel()
+        if not (x.is_cuda and x.dtype == torch.float32 and self._mean.is_cuda):
+            return None
+        if x.dim() == 0 or (D > 1 and x.shape[-1] != D):
+            return None
+        if x.dim() == 2 and D > 1 and x.stride(1) == 1:
+            return x, x.shape[0], D, x.stride(0)
+        x = x.contiguous()
+        return x, x.numel() // D, D, D
+
+    def forward(self, x, out: torch.Tensor = None):
+        """`out` (optional, [N, >= D] fp32 with unit column stride): write the result there (any row pitch)."""
+        rows = None if (x.requires_grad and torch.is_grad_enabled()) or torch.jit.is_tracing() else self._rows(x)
+        if rows is None:
+            y = (x - self._mean) / (self._std + self.eps)
+            return y if out is None else out.copy_(y)
+        xr, N, D, ldx = rows
+        if out is None:
+            y = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+            ldy = D
+        else:
+            y, ldy = out, out.stride(0)
+        nat.check(nat.lib().rslrl_empirical_normalize(xr.data_ptr(), ldx, N, D, self._mean.data_ptr(), self._std.data_ptr(),
+                                                      float(self.eps), y.data_ptr(), ldy, nat.stream_ptr()))
+        return y
 
     @torch.jit.unused
     def update(self, x):
         if not self.training:
             return
-        if self.until is not None and self.count >= self.until:
-            return
-        n = x.shape[0]
-        self.count += n
-        rate = n / self.count
-        var_x = torch.var(x, dim=0, unbiased=False, keepdim=True)
-        mean_x = torch.mean(x, dim=0, keepdim=True)
-        delta = mean_x - self._mean
-        self._mean += rate * delta
-        self._var += rate * (var_x - self._var + delta * (mean_x - self._mean))
-        torch.sqrt(self._var, out=self._std)   # in place: CUDA graphs and act() plans hold this buffer's address
+        rows = self._rows(x.detach())
+        if rows is None:
+            raise RuntimeError("rsl_rl_b200.EmpiricalNormalization.update runs on CUDA fp32 tensors only (got "
+                               f"{x.dtype} on {x.device}); there is no CPU path")
+        xr, N, D, ldx = rows
+        if self._ws is None or self._ws.device != x.device:
+            self._ws = torch.zeros(int(nat.lib().rslrl_empirical_norm_workspace_bytes(D)), dtype=torch.uint8,
+                                   device=x.device)
+        until = -1 if self.until is None else int(self.until)
+        nat.check(nat.lib().rslrl_empirical_norm_update(xr.data_ptr(), ldx, N, D, self._mean.data_ptr(),
+                                                        self._var.data_ptr(), self._std.data_ptr(), self.count.data_ptr(),
+                                                        until, self._ws.data_ptr(), nat.stream_ptr()))
 
     @torch.jit.unused
     def inverse(self, y):
@@ -76,6 +109,7 @@ class EmpiricalDiscountedVariationNormalization(nn.Module):
     def forward(self, rew):
         if self.training:
             self.emp_norm.update(self.disc_avg.update(rew))
-        if self.emp_norm._std > 0:
-            return rew / self.emp_norm._std
-        return rew
+        # (the reference branches on `_std > 0` on the host, normalization.py:98-101: a device->host sync per env step;
+        # the same selection is made elementwise on the device here)
+        std = self.emp_norm._std
+        return torch.where(std > 0, rew / std, rew)

@@ -43,7 +43,7 @@ def _runner_from_golden(g, meta):
     return runner
 
 
-@pytest.mark.parametrize("name", ["ppo_lstm_small", "ppo_rnd_sym_small"])
+@pytest.mark.parametrize("name", ["ppo_lstm_small", "ppo_rnd_sym_small", "ppo_rnd_norm_small"])
 def test_composite_learn_iterations_match_reference_golden(name):
     torch.backends.cudnn.allow_tf32 = False   # the fp32 parity class
     g = load(name)

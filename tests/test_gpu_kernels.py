@@ -626,3 +626,52 @@ def test_update_rng_skip_matches_the_discarded_draws():
         assert torch.equal(gen.get_state(), expect_state)
         assert torch.equal(torch.randperm(1000, device=DEV), expect_next)
     assert Stub._draw_offset is not None and Stub._draw_offset > 0
+
+
+# ------------------------------------------------------------------------------------ running normaliser
+@pytest.mark.parametrize("N,D,strided", [(4096, 48, False), (65536, 235, False), (777, 5, True), (4096, 1, False), (33, 300, True)])
+def test_empirical_normalization_kernels(N, D, strided):
+    """EmpiricalNormalization.update / forward on the fused kernels vs the reference's tensor expressions
+    (normalization.py:44-66) evaluated by torch in fp64 / fp32; forward is bit-exact."""
+    from rsl_rl_b200.networks import EmpiricalNormalization
+    torch.manual_seed(N + D)
+    norm = EmpiricalNormalization(shape=[D] if D > 1 else [], until=None).to(DEV)
+    mean, var, count = torch.zeros(1, D, dtype=torch.float64), torch.ones(1, D, dtype=torch.float64), 0
+    ptrs = (norm._mean.data_ptr(), norm._var.data_ptr(), norm._std.data_ptr(), norm.count.data_ptr())
+    for step in range(5):
+        if strided:
+            x = (torch.randn(N, D + 3, device=DEV) * (1 + step) + 3.0 * step)[:, :D]
+        else:
+            x = torch.randn(N, D, device=DEV) * (1 + step) + 3.0 * step
+        xin = x[:, 0] if D == 1 and not strided else x
+        norm.update(xin)
+        xd = x.double().cpu().reshape(N, D)
+        count += N
+        rate = np.float32(N) / np.float32(count)
+        mean_x, var_x = xd.mean(0, keepdim=True), xd.var(0, unbiased=False, keepdim=True)
+        delta = mean_x - mean
+        mean = mean + float(rate) * delta
+        var = var + float(rate) * (var_x - var + delta * (mean_x - mean))
+        assert int(norm.count) == count
+        assert rel_err(norm._mean.cpu().numpy().reshape(1, D), mean.numpy()) < 2e-6, step
+        assert rel_err(norm._var.cpu().numpy().reshape(1, D), var.numpy()) < 2e-6, step
+        assert torch.equal(norm._std, torch.sqrt(norm._var))
+        y = norm(xin)
+        assert torch.equal(y, (xin - norm._mean) / (norm._std + norm.eps))      # bit-exact forward
+        out = torch.zeros(N, D + 5, device=DEV)
+        if xin.dim() == 2:
+            norm(xin, out=out)
+            assert torch.equal(out[:, :D], y) and float(out[:, D:].abs().sum()) == 0.0
+    assert ptrs == (norm._mean.data_ptr(), norm._var.data_ptr(), norm._std.data_ptr(), norm.count.data_ptr()), \
+        "buffers must be updated in place (CUDA graphs hold their addresses)"
+    # `until`: frozen once count >= until (tested on the device), eval() mode never updates
+    frozen = EmpiricalNormalization(shape=[D] if D > 1 else [], until=N).to(DEV)
+    x = torch.randn(N, D, device=DEV)
+    frozen.update(x if D > 1 else x[:, 0])
+    snap = frozen._mean.clone()
+    frozen.update((x if D > 1 else x[:, 0]) + 5.0)
+    assert torch.equal(frozen._mean, snap) and int(frozen.count) == N
+    norm.eval()
+    snap = norm._mean.clone()
+    norm.update(xin)
+    assert torch.equal(norm._mean, snap)

@@ -19,17 +19,17 @@ def _train_cfg(meta, **alg_extra):
                 obs_groups={k: list(v) for k, v in meta["obs_groups"].items()},
                 policy=dict(class_name="ActorCritic", actor_hidden_dims=list(meta["hidden"]),
                             critic_hidden_dims=list(meta["hidden"]), activation=meta["activation"],
-                            init_noise_std=1.0, noise_std_type=meta["noise_std_type"]),
+                            init_noise_std=1.0, noise_std_type=meta["noise_std_type"], **meta.get("policy_extra", {})),
                 algorithm=alg)
 
 
-def _make_runner(meta, obs_streams, rewards, dones, time_outs, init_params, **alg_extra):
+def _make_runner(meta, obs_streams, rewards, dones, time_outs, init_params, log_dir=None, **alg_extra):
     from rsl_rl_b200.env import ReplayVecEnv
     from rsl_rl_b200.runners import OnPolicyRunner
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
     env = ReplayVecEnv({k: t(v) for k, v in obs_streams.items()}, t(rewards), t(dones), t(time_outs),
                        meta["num_actions"], device=DEV)
-    runner = OnPolicyRunner(env, _train_cfg(meta, **alg_extra), log_dir=None, device=DEV)
+    runner = OnPolicyRunner(env, _train_cfg(meta, **alg_extra), log_dir=log_dir, device=DEV)
     runner.alg.policy.load_state_dict({k: t(v).to(DEV) for k, v in init_params.items()})
     assert runner.alg.fused, runner.alg._engine_reason
     return runner, env
@@ -324,3 +324,155 @@ def test_fp16_unaligned_observation_width_vs_oracle():
     if abs(res[-1]["lr_mine"] / res[-1]["lr_ref"] - 1.0) < 1e-9:
         u, ur = res[-1]["mine"].astype(np.float64) - init, res[-1]["ref"].astype(np.float64) - init
         assert np.linalg.norm(u - ur) / np.linalg.norm(ur) < 0.15
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# observation normalisers, logging path, checkpoints -- against the unmodified reference's golden run
+# ----------------------------------------------------------------------------------------------------------------------
+def _golden_stream(g, meta):
+    T, iters = meta["num_steps"], meta["iterations"]
+    obs = {k: np.concatenate([g[f"it{i}.stream.obs.{k}"][:T + (i == iters - 1)] for i in range(iters)])
+           for k in meta["group_dims"]}
+    cat = lambda key: np.concatenate([g[f"it{i}.stream.{key}"] for i in range(iters)])
+    return obs, cat("rewards"), cat("dones"), cat("time_outs")
+
+
+def _drive_golden(g, meta, runner, iters, on_iter=None):
+    alg = runner.alg
+    for it in range(iters):
+        p = f"it{it}."
+        zq = [torch.from_numpy(z).to(DEV) for z in g[p + "z_rollout"]]
+        alg.policy._noise_fn = lambda like, q=zq: q.pop(0)
+        perm = torch.from_numpy(g[p + "perm"]).to(DEV)
+        alg.storage._randperm = lambda n, perm=perm: perm
+        runner.learn(1)
+        if on_iter is not None:
+            on_iter(it, p)
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_observation_normalisers_match_reference_golden(use_graph):
+    """actor/critic_obs_normalization=True (EmpiricalNormalization, reference normalization.py:44-66) over four
+    iterations: the running statistics change every env step while act() launch plans and -- with use_graph -- the
+    captured update() graph hold the buffers' addresses (eager -> capture -> replay)."""
+    g = load("ppo_mlp_norm")
+    meta = meta_of(g)
+    obs, rewards, dones, time_outs = _golden_stream(g, meta)
+    init = OrderedDict((k[len("init."):], g[k]) for k in g.files if k.startswith("init."))
+    runner, env = _make_runner(meta, obs, rewards, dones, time_outs, init, use_cuda_graph=use_graph)
+    alg = runner.alg
+    names = meta["param_names"]
+
+    def check(it, p):
+        sd = alg.policy.state_dict()
+        for key in ("actor_obs_normalizer._mean", "actor_obs_normalizer._var", "actor_obs_normalizer._std",
+                    "critic_obs_normalizer._mean", "critic_obs_normalizer._var", "critic_obs_normalizer._std"):
+            assert rel_err(sd[key].cpu().numpy(), g[p + "final." + key]) < 1e-5, (it, key)
+        assert int(sd["actor_obs_normalizer.count"]) == int(g[p + "final.actor_obs_normalizer.count"])
+        assert rel_err(alg.storage.mu.cpu().numpy(), g[p + "storage.mu"]) < 2e-5, it
+        assert rel_err(alg.storage.values.cpu().numpy(), g[p + "storage.values"]) < 2e-5, it
+        assert rel_err(alg.storage.returns.cpu().numpy(), g[p + "storage.returns"]) < 2e-5, it
+        mine = np.concatenate([sd[k].cpu().numpy().reshape(-1) for k in names])
+        assert abs(alg.learning_rate - float(g[p + "learning_rate"])) < 1e-15, it
+        assert rel_err(mine, g[p + "mb.params_after"][-1]) < 5e-5, it
+
+    _drive_golden(g, meta, runner, meta["iterations"], check)
+    assert (alg._graph is not None) == use_graph
+
+
+def test_logging_path_matches_reference_buffers(tmp_path):
+    """log_dir set: the device-side episode statistics, flushed once per iteration, reproduce the
+    reference's rewbuffer / lenbuffer contents (on_policy_runner.py:113-139) and the logged mean losses."""
+    g = load("ppo_mlp_small")
+    meta = meta_of(g)
+    obs, rewards, dones, time_outs = _golden_stream(g, meta)
+    init = OrderedDict((k, g[f"init.{k}"]) for k in meta["param_names"])
+    runner, env = _make_runner(meta, obs, rewards, dones, time_outs, init, log_dir=str(tmp_path), use_cuda_graph=False)
+    seen = []
+    orig_log = runner.log
+
+    def log_and_record(locs, *a, **k):
+        seen.append(dict(rew=list(locs["rewbuffer"]), length=list(locs["lenbuffer"]), loss=dict(locs["loss_dict"])))
+        return orig_log(locs, *a, **k)
+
+    runner.log = log_and_record
+
+    def check(it, p):
+        ref_rew, ref_len = g[p + "log.rewbuffer"], g[p + "log.lenbuffer"]
+        assert len(seen) == it + 1
+        assert np.array_equal(np.asarray(seen[-1]["length"], dtype=np.float64), ref_len), it
+        assert len(seen[-1]["rew"]) == len(ref_rew)
+        if len(ref_rew):
+            assert rel_err(np.asarray(seen[-1]["rew"]), ref_rew) < 1e-5, it
+        for k in ("value_function", "surrogate", "entropy"):
+            ref = float(g[p + "log.loss." + k])
+            assert abs(seen[-1]["loss"][k] - ref) < 1e-4 * max(1.0, abs(ref)), (it, k)
+
+    _drive_golden(g, meta, runner, meta["iterations"], check)
+    import os
+    assert any(f.startswith("events.out.tfevents") for f in os.listdir(tmp_path)), "no TensorBoard event file written"
+    assert any(f.startswith("model_") for f in os.listdir(tmp_path)), "no checkpoint written at the end of learn()"
+
+
+def test_reference_checkpoint_round_trip(tmp_path):
+    """a checkpoint WRITTEN BY THE REFERENCE (tests/golden/ppo_mlp_norm_ref_checkpoint.pt, saved by
+    oracle/make_golden.py after four iterations, on_policy_runner.py:289-305) loads into this runner (parameters,
+    normaliser buffers, Adam moments / step / lr, iteration counter), training resumes from it, and a checkpoint written
+    here has the reference's structure (and loads into the reference when its install travelled with the repo)."""
+    import os
+    from tests.golden_util import GOLDEN
+    g = load("ppo_mlp_norm")
+    meta = meta_of(g)
+    obs, rewards, dones, time_outs = _golden_stream(g, meta)
+    init = OrderedDict((k[len("init."):], g[k]) for k in g.files if k.startswith("init."))
+    runner, env = _make_runner(meta, obs, rewards, dones, time_outs, init, log_dir=str(tmp_path), use_cuda_graph=False)
+    path = os.path.join(GOLDEN, "ppo_mlp_norm_ref_checkpoint.pt")
+    ref_ckpt = torch.load(path, map_location="cpu", weights_only=False)
+    runner.load(path)
+    alg = runner.alg
+    last = f"it{meta['iterations'] - 1}."
+    sd = alg.policy.state_dict()
+    for k in sd:
+        assert np.array_equal(sd[k].cpu().numpy(), g[last + "final." + k]), k
+    grp = alg._group
+    pick = torch.cat([torch.arange(o, o + q.numel()) for o, q in zip(grp.offsets, grp.params)]).to(DEV)
+    assert np.array_equal(grp.exp_avg[pick].cpu().numpy(), g[last + "adam.exp_avg"])
+    assert np.array_equal(grp.exp_avg_sq[pick].cpu().numpy(), g[last + "adam.exp_avg_sq"])
+    assert alg.optimizer._host_step == int(g[last + "adam.step"])
+    assert runner.current_learning_iteration == ref_ckpt["iter"]
+    # resume: one more iteration on fresh data runs on the loaded state (Adam step counter keeps counting)
+    alg.learning_rate = ref_ckpt["optimizer_state_dict"]["param_groups"][0]["lr"]
+    env.t = 0
+    runner.learn(1)
+    assert alg.last_update_info["step"] == int(g[last + "adam.step"]) + 8
+    assert all(bool(torch.isfinite(v).all()) for v in alg.policy.state_dict().values())
+    # save: same top-level structure, same keys, shapes and dtypes as the reference's file
+    mine_path = os.path.join(str(tmp_path), "mine.pt")
+    runner.save(mine_path)
+    mine = torch.load(mine_path, map_location="cpu", weights_only=False)
+    assert set(ref_ckpt.keys()) <= set(mine.keys()), (sorted(ref_ckpt.keys()), sorted(mine.keys()))
+    for k, v in ref_ckpt["model_state_dict"].items():
+        assert mine["model_state_dict"][k].shape == v.shape and mine["model_state_dict"][k].dtype == v.dtype, k
+    ro, mo = ref_ckpt["optimizer_state_dict"], mine["optimizer_state_dict"]
+    assert set(ro["state"].keys()) == set(mo["state"].keys())
+    for i in ro["state"]:
+        assert set(ro["state"][i].keys()) == set(mo["state"][i].keys())
+        assert ro["state"][i]["exp_avg"].shape == mo["state"][i]["exp_avg"].shape
+    assert {k for k in ro["param_groups"][0]} <= {k for k in mo["param_groups"][0]}
+    # ... and the reference itself loads it (CPU), when baseline/_ref is present
+    from oracle import reference_arm as R
+    if R.available() is None:
+        R.import_reference()
+        from rsl_rl.runners import OnPolicyRunner as RefRunner
+        import contextlib, io
+        cfg = _train_cfg(meta)
+        for k in ("gemm_precision", "use_cuda_graph", "rng_compat"):
+            cfg["algorithm"].pop(k, None)
+        renv = R.make_env(meta["num_envs"], meta["group_dims"], meta["num_actions"], "cpu")
+        with contextlib.redirect_stdout(io.StringIO()):
+            ref_runner = RefRunner(renv, cfg, log_dir=None, device="cpu")
+            ref_runner.load(mine_path)
+        rsd = ref_runner.alg.policy.state_dict()
+        for k, v in alg.policy.state_dict().items():
+            assert torch.equal(rsd[k], v.cpu()), k
+        assert ref_runner.current_learning_iteration == runner.current_learning_iteration
