@@ -202,6 +202,21 @@ int rslrl_mlp3_plan_create(int n, const rslrl_mlp3_fwd_t* nets_host, void** plan
 int rslrl_mlp3_plan_run(void* plan, const float* const* x_host, rslrl_stream_t stream);
 void rslrl_mlp3_plan_destroy(void* plan);
 
+/* ---- LSTM cell (rsl_rl/networks/memory.py:27-37 -> nn.LSTM) ------------------------------------------------ */
+
+/* One time step of an LSTM layer after its two projections (PyTorch gate order i, f, g, o along the 4H axis):
+ *   xg [n,4H] = x_t W_ih^T + b_ih (hoisted over all steps), hg [n,4H] = h_{t-1} W_hh^T, b_hh [4H] or NULL, c_prev [n,H]
+ *   -> gates_act [n,4H] (activated gates, saved for the backward pass; NULL for inference), c_out [n,H], h_out [n,H].
+ * H % 4 == 0, every pointer 16-byte aligned, rows dense. */
+int rslrl_lstm_cell_forward(const float* xg, const float* hg, const float* b_hh, const float* c_prev, float* gates_act,
+                            float* c_out, float* h_out, int64_t n, int H, rslrl_stream_t stream);
+/* Backward of the same step: dh_out (gradient of the layer output at t, may be NULL), dh_rec (gradient arriving through
+ * h_t from step t+1, may be NULL), dc_next (may be NULL) -> dgates [n,4H] (gradient of the pre-activation gates: the
+ * operand of the dW_ih / dW_hh / db products and of dh_{t-1} = dgates W_hh) and dc_prev [n,H]. */
+int rslrl_lstm_cell_backward(const float* dh_out, const float* dh_rec, const float* dc_next, const float* gates_act,
+                             const float* c_prev, const float* c_cur, float* dgates, float* dc_prev, int64_t n, int H,
+                             rslrl_stream_t stream);
+
 /* ---- running-statistics normaliser (rsl_rl/networks/normalization.py:44-66) ---------------------------- */
 
 /* EmpiricalNormalization.update(x) in one launch: batch mean / biased variance of x [N,D] (row stride ldx) folded into the

@@ -102,9 +102,10 @@ class GaussianHeadMixin:
         return (-((actions - self._mean) ** 2) / (2 * var) - torch.log(self._std) - _LOG_SQRT_2PI).sum(dim=-1)
 
     def set_gemm_precision(self, precision: str):
+        from ..networks.memory import Memory
         for m in self.modules():
-            if isinstance(m, MLP):
-                # (the autograd path of an MLP has no fp16-storage variant: tensor cores there mean tf32)
+            if isinstance(m, (MLP, Memory)):
+                # (the autograd path of an MLP / LSTM has no fp16-storage variant: tensor cores there mean tf32)
                 m.precision = "tf32" if precision == "fp16" else precision
 
 

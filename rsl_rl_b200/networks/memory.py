@@ -1,14 +1,16 @@
 """Recurrent memory in front of the MLPs (mirror of `rsl_rl/networks/memory.py`).
 
-State-dict keys stay `rnn.weight_ih_l0`, ... (an `nn.LSTM` / `nn.GRU` owns the parameters).  The padded
-trajectory layout and its inverse come from the segmented-scan kernels (utils.TrajectoryIndex); the
-recurrence itself currently runs through the cuDNN RNN that `nn.LSTM` dispatches to (library call --
-a persistent sm_100a LSTM kernel is the open item of SURVEY.md section 8 row A14)."""
+State-dict keys stay `rnn.weight_ih_l0`, ... (an `nn.LSTM` / `nn.GRU` module owns the parameters).  The padded
+trajectory layout and its inverse come from the segmented-scan kernels (utils.TrajectoryIndex).  The LSTM recurrence
+runs on this library's kernels (networks/lstm.py: hoisted input projection + per-step recurrent projection on the GEMM
+kernels, fused cell kernels, hand-written backward through time) -- `self.rnn` is only the parameter container on the
+CUDA path; it is called as a module for host tensors (export / inference off the training path) and for GRUs."""
 from __future__ import annotations
 
 import torch.nn as nn
 
 from ..utils.utils import unpad_trajectories
+from .lstm import lstm_forward
 
 
 class Memory(nn.Module):
@@ -18,16 +20,23 @@ class Memory(nn.Module):
         self.rnn = rnn_cls(input_size=input_size, hidden_size=hidden_size, num_layers=num_layers)
         self.hidden_states = None
         self._unpad = None  # optional fast unpad (set by the recurrent generator): callable(out) -> [T, N_mb, H]
+        self.precision = "fp32"   # GEMM arithmetic of the native LSTM path ("fp32" | "tf32"), set by PPO
+        self.native = isinstance(self.rnn, nn.LSTM)
+
+    def _rnn(self, x, hidden):
+        if self.native and x.is_cuda:
+            return lstm_forward(self.rnn, x, hidden, self.precision)
+        return self.rnn(x, hidden)
 
     def forward(self, input, masks=None, hidden_states=None):
         batch_mode = masks is not None
         if batch_mode:
             if hidden_states is None:
                 raise ValueError("Hidden states not passed to memory module during policy update")
-            out, _ = self.rnn(input, hidden_states)
+            out, _ = self._rnn(input, hidden_states)
             out = unpad_trajectories(out, masks)
         else:
-            out, self.hidden_states = self.rnn(input.unsqueeze(0), self.hidden_states)
+            out, self.hidden_states = self._rnn(input.unsqueeze(0), self.hidden_states)
         return out
 
     def reset(self, dones=None, hidden_states=None):

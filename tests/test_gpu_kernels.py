@@ -675,3 +675,34 @@ def test_empirical_normalization_kernels(N, D, strided):
     snap = norm._mean.clone()
     norm.update(xin)
     assert torch.equal(norm._mean, snap)
+
+
+# ------------------------------------------------------------------------------------------------ LSTM
+@pytest.mark.parametrize("T,n,D,H,L,prec,tol", [(24, 1500, 48, 256, 1, "fp32", 2e-5), (8, 33, 10, 16, 1, "fp32", 2e-5),
+                                                (6, 40, 12, 32, 2, "fp32", 2e-5), (24, 1024, 48, 256, 1, "tf32", 2e-3)])
+def test_native_lstm_matches_torch_lstm(T, n, D, H, L, prec, tol):
+    """networks/lstm.py (hoisted input GEMM, per-step recurrent GEMM + fused cell kernels, hand-written BPTT) against
+    torch.nn.LSTM evaluated in fp64 on the host: outputs, final states and every parameter gradient."""
+    from rsl_rl_b200.networks.lstm import lstm_forward
+    torch.manual_seed(T + n + H)
+    rnn = torch.nn.LSTM(D, H, num_layers=L).to(DEV)
+    ref = torch.nn.LSTM(D, H, num_layers=L).double()
+    ref.load_state_dict({k: v.detach().cpu().double() for k, v in rnn.state_dict().items()})
+    x = torch.randn(T, n, D, device=DEV)
+    h0, c0 = torch.randn(L, n, H, device=DEV) * 0.5, torch.randn(L, n, H, device=DEV) * 0.5
+    w = torch.randn(T, n, H, device=DEV)                       # loss = sum(out * w) + sum(h_n) - sum(c_n)
+    out, (hn, cn) = lstm_forward(rnn, x, (h0, c0), prec)
+    (out * w).sum().add(hn.sum()).sub(cn.sum()).backward()
+    xr = x.cpu().double().requires_grad_(True)
+    out_r, (hn_r, cn_r) = ref(xr, (h0.cpu().double(), c0.cpu().double()))
+    (out_r * w.cpu().double()).sum().add(hn_r.sum()).sub(cn_r.sum()).backward()
+    assert rel_err(out.detach().cpu().numpy(), out_r.detach().numpy()) < tol
+    assert rel_err(hn.detach().cpu().numpy(), hn_r.detach().numpy()) < tol
+    assert rel_err(cn.detach().cpu().numpy(), cn_r.detach().numpy()) < tol
+    for (k, p), pr in zip(rnn.named_parameters(), ref.parameters()):
+        assert rel_err(p.grad.cpu().numpy(), pr.grad.numpy()) < 5 * tol, k
+    # inference path (no autograd, hidden state None -> zeros) agrees with the training path
+    with torch.inference_mode():
+        out_i, (hn_i, cn_i) = lstm_forward(rnn, x, None, prec)
+        out_z, _ = ref(xr.detach())
+    assert rel_err(out_i.cpu().numpy(), out_z.detach().numpy()) < tol

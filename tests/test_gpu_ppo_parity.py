@@ -234,7 +234,7 @@ def test_tensor_core_iteration_vs_oracle_c3_layout():
     from tools import parity_report as R
     r = R.compare("c3", "fp16")
     print({k: v for k, v in r.items() if k != "params_after.max_norm_per_step"})
-    _check_tensor_core_class(r, R.tf32_noise_floor("c1"))   # (the floor is 2 * lr at every shape; c1's is cached)
+    _check_tensor_core_class(r, R.tf32_noise_floor("c3"))
 
 
 @pytest.mark.parametrize("reward_scale", [1e4, 1e-4])
