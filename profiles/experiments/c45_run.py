@@ -65,3 +65,14 @@ p = torch.cat([q.detach().reshape(-1) for q in runner.alg.policy.parameters()])
 print(f"{which.upper()} {prec} envs={N}: {dt*1e3:.1f} ms/iter, {N*24/dt/1e6:.2f} M env-steps/s, phases "
       f"{ {k: round(v, 2) for k, v in runner.phase_times.items()} }, lr {runner.alg.learning_rate:.3e}, "
       f"params finite {bool(torch.isfinite(p).all())}, fused path {runner.alg.fused}, composite graph {runner.alg._cgraph is not None}")
+if os.environ.get("RSLRL_HOST_PROFILE") == "1":   # where the host time of one iteration goes
+    import cProfile, pstats
+    pr = cProfile.Profile()
+    pr.enable()
+    with contextlib.redirect_stdout(io.StringIO()):
+        runner.learn(2)
+    torch.cuda.synchronize()
+    pr.disable()
+    s = io.StringIO()
+    pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(30)
+    print(s.getvalue()[:7000])

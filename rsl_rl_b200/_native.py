@@ -110,6 +110,8 @@ _SIGNATURES = {
     "rslrl_hidden_at_starts": (c_int, [c_void_p] * 4 + [c_int] * 7 + [c_void_p]),
     "rslrl_lstm_cell_forward": (c_int, [c_void_p] * 7 + [c_i64, c_int, c_void_p]),
     "rslrl_lstm_cell_backward": (c_int, [c_void_p] * 8 + [c_i64, c_int, c_void_p]),
+    "rslrl_lstm_layer_forward": (c_int, [c_void_p] * 7 + [c_int, c_i64, c_int, c_int, c_void_p]),
+    "rslrl_lstm_layer_backward": (c_int, [c_void_p] * 9 + [c_int, c_int, c_i64, c_int, c_int, c_void_p]),
     "rslrl_empirical_norm_workspace_bytes": (c_i64, [c_int]),
     "rslrl_empirical_norm_update": (c_int, [c_void_p, c_i64, c_i64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_i64,
                                             c_void_p, c_void_p]),

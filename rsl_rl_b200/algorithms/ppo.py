@@ -161,6 +161,7 @@ class PPO:
         self._act_plans = {}
         self._act_in = None
         self._lineup = None
+        self._cf = None   # permuted rollout copy of the fused RND / symmetry update
         self._fp16_saturations = 0   # running count of saturated fp16 gradient launches (dynamic scale)
         self._draw_offset = None   # Philox offset consumed by one discarded torch.normal draw in update()
         self._mb_hook = None  # test hook: called after every minibatch backward in eager mode
@@ -515,19 +516,31 @@ class PPO:
         opt._host_step += M * E
         return self._finish_update()
 
-    def _skip_discarded_draws(self, count: int):
-        """Advances the CUDA generator exactly as `count` calls of `torch.normal(mean, std)` on a [minibatch, A] mean
-        would (reference ppo.py:249 -> actor_critic.py:140): the Philox offset one such call consumes is measured once
-        with a real `normal_()` launch, after which the stream is advanced arithmetically -- no launches."""
+    def _skip_discarded_draws(self, count: int, rows: int = None):
+        """Advances the CUDA generator exactly as `count` calls of `torch.normal(mean, std)` on a [rows, A] mean
+        (default: one minibatch) would (reference ppo.py:249 -> actor_critic.py:140): the Philox offset one such call
+        consumes is measured once per shape with a real `normal_()` launch, after which the stream is advanced
+        arithmetically -- no launches."""
         idx = torch.device(self.device).index
         gen = torch.cuda.default_generators[torch.cuda.current_device() if idx is None else idx]
+        discard = getattr(self, "_discard", None)
+        if rows is None:
+            rows = discard.shape[0]
         if self._draw_offset is None:
+            self._draw_offset = {}
+        per_draw = self._draw_offset.get(rows)
+        if per_draw is None:
+            if discard is not None and rows == discard.shape[0]:
+                buf = discard
+            else:
+                A = discard.shape[1] if discard is not None else self._engine.A
+                buf = torch.empty(rows, A, dtype=torch.float32, device=self.device)
             before = gen.get_offset()
-            self._discard.normal_()
-            self._draw_offset = gen.get_offset() - before
+            buf.normal_()
+            per_draw = self._draw_offset[rows] = gen.get_offset() - before
             count -= 1
         if count > 0:
-            gen.set_offset(gen.get_offset() + self._draw_offset * count)
+            gen.set_offset(gen.get_offset() + per_draw * count)
 
     def release_graphs(self):
         """Drops the captured CUDA graphs (update() and the per-step act() graphs).  Call it before
@@ -644,9 +657,126 @@ class PPO:
         self._composite_minibatches(sums)
         return self._composite_finish(sums)
 
+    def _composite_fusable(self) -> bool:
+        """RND and / or symmetry AUGMENTATION on a feed-forward ActorCritic: the policy objective runs on the fused
+        engine (no autograd); only the RND predictor's small MSE stays under autograd."""
+        return (self._engine is not None and not self.policy.is_recurrent
+                and (self.symmetry is None or bool(self.symmetry["use_data_augmentation"]))
+                and os.environ.get("RSLRL_COMPOSITE_FUSED", "1") != "0")
+
+    def _composite_engine(self, rows: int):
+        """The engine with activation / gradient buffers for `rows` minibatch rows (k * minibatch with k-fold
+        augmentation); the rollout keeps using the same object."""
+        eng = self._engine
+        if eng.rows < rows:
+            eng = self._engine = _engine.FeedForwardEngine(self.policy, rows, self.storage.num_envs, rows, self.device,
+                                                           "tf32" if self.gemm_precision == "fp16" else self.gemm_precision,
+                                                           self._group)
+            self._act_plans.clear()
+        return eng
+
+    def _composite_minibatches_fused(self, sums):
+        """Minibatch loop of the RND / symmetry configurations on the fused engine (reference ppo.py:199-395):
+        one permuted gather of the rollout per update; per minibatch the user's augmentation function (torch ops),
+        the grouped actor + critic forward on the k-fold batch, ONE loss launch (the per-sample scalars of the augmented
+        rows are indexed i % minibatch instead of being repeat()-ed, ppo.py:240-244; entropy and KL on the original
+        rows only, :255-257), the mirror-loss gradient added to dL/dmu of the augmented rows (the reference's third
+        actor forward `act_inference(obs_aug)` recomputes exactly `mu`, :331-343), the hand-written backward and the
+        fused optimiser step.  The RND predictor's MSE (:352-363) is two tiny MLPs under autograd on the native GEMMs."""
+        pol, st, opt = self.policy, self.storage, self.optimizer
+        M, E = self.num_mini_batches, self.num_learning_epochs
+        N, T = st.num_envs, st.num_transitions_per_env
+        mb = (N * T) // M
+        B = mb * M
+        once = getattr(st, "_randperm_once", None)
+        st._randperm_once = None
+        perm = once if once is not None else st._randperm(B)
+        capturing = torch.cuda.is_current_stream_capturing()
+        f32 = dict(dtype=torch.float32, device=self.device)
+        if self._cf is None or self._cf["B"] != B:
+            A = self._engine.A
+            self._cf = dict(B=B, obs={k: torch.empty(B, int(v[0, 0].numel()), **f32) for k, v in st.observations.items()},
+                            actions=torch.empty(B, A, **f32), mu=torch.empty(B, A, **f32), sigma=torch.empty(B, A, **f32),
+                            values=torch.empty(B, **f32), adv=torch.empty(B, **f32), ret=torch.empty(B, **f32),
+                            logp=torch.empty(B, **f32), discard={})
+        cf = self._cf
+        fields, widths, outs, strides, cols = [], [], [], [], []
+        for k, src in st.observations.items():
+            w = cf["obs"][k].shape[1]
+            fields.append(src); widths.append(w); outs.append(cf["obs"][k]); strides.append(w); cols.append(0)
+        A = self._engine.A
+        for src, dst, w in ((st.actions, cf["actions"], A), (st.mu, cf["mu"], A), (st.sigma, cf["sigma"], A),
+                            (st.values, cf["values"], 1), (st.advantages, cf["adv"], 1), (st.returns, cf["ret"], 1),
+                            (st.actions_log_prob, cf["logp"], 1)):
+            fields.append(src); widths.append(w); outs.append(dst); strides.append(w); cols.append(0)
+        st._gather(fields, widths, perm, outs, strides, cols)
+        ds = opt.dev_state
+        nat.check(nat.lib().rslrl_fill_zero(ds.loss_sums.data_ptr(), 24, nat.stream_ptr()))
+        sums.zero_()
+        self._group.zero_grad()
+        if self.rnd:
+            self._rnd_group.zero_grad()
+        adaptive = self.desired_kl is not None and self.schedule == "adaptive"
+        hp = self._hyper()
+        sym = self.symmetry
+        TD = type(st.observations)
+        for _ in range(E):
+            for i in range(M):
+                r = slice(i * mb, (i + 1) * mb)
+                obs_b = TD({k: v[r] for k, v in cf["obs"].items()}, batch_size=[mb], device=self.device)
+                obs_in, actions_in, k_aug = obs_b, cf["actions"][r], 1
+                if sym:
+                    obs_in, actions_in = sym["data_augmentation_func"](obs=obs_b, actions=actions_in, env=sym["_env"])
+                    k_aug = int(obs_in.batch_size[0] / mb)
+                rows = k_aug * mb
+                eng = self._composite_engine(rows)
+                x_a = nat.f32c(pol.actor_obs_normalizer(pol.get_actor_obs(obs_in)))
+                x_c = x_a if pol.critic_shares_actor_input else nat.f32c(pol.critic_obs_normalizer(pol.get_critic_obs(obs_in)))
+                mu, value = eng.mu[:rows], eng.value[:rows]
+                eng.forward(x_a, x_c, mu, value)
+                if self.rng_compat:   # the sample the reference's policy.act() draws and discards (ppo.py:249)
+                    if capturing:
+                        d = cf["discard"].get(rows)
+                        if d is None:
+                            d = cf["discard"][rows] = torch.empty(rows, A, **f32)
+                        d.normal_()
+                    else:
+                        self._skip_discarded_draws(1, rows)
+                eng.loss(rows, mb, mu, value, nat.f32c(actions_in), cf["logp"][r], cf["adv"][r], cf["ret"][r],
+                         cf["values"][r], cf["mu"][r], cf["sigma"][r], self._group.kl_slot, ds.loss_sums, hp,
+                         self.normalize_advantage_per_mini_batch)
+                if sym:
+                    _, target = sym["data_augmentation_func"](obs=None, actions=mu[:mb], env=sym["_env"])
+                    diff = mu[mb:rows] - target[mb:rows]
+                    sums[4] += (diff * diff).mean()
+                    if sym["use_mirror_loss"]:
+                        eng.dmu[mb:rows].add_(diff, alpha=float(sym["mirror_loss_coeff"]) * 2.0 / diff.numel())
+                eng.backward(x_a, x_c, eng.dmu[:rows], eng.dvalue[:rows])
+                if self.rnd:
+                    with torch.no_grad():
+                        rnd_state = self.rnd.state_normalizer(self.rnd.get_rnd_state(obs_b))
+                    rnd_loss = torch.nn.functional.mse_loss(self.rnd.predictor(rnd_state),
+                                                            self.rnd.target(rnd_state).detach())
+                    rnd_loss.backward()
+                    sums[3] += rnd_loss.detach()
+                if self.is_multi_gpu:
+                    if not opt.peer_allreduce:
+                        torch.distributed.all_reduce(self._group.grads_ext, op=torch.distributed.ReduceOp.SUM)
+                    if self.rnd:
+                        torch.distributed.all_reduce(self._rnd_group.grads_ext, op=torch.distributed.ReduceOp.SUM)
+                opt.fused_step(world_size=self.gpu_world_size, max_grad_norm=self.max_grad_norm, adaptive=adaptive,
+                               desired_kl=self.desired_kl or 0.0, round_lr_fp32=self.is_multi_gpu, use_kl=adaptive)
+                if self.rnd:
+                    self.rnd_optimizer.fused_step(world_size=self.gpu_world_size, max_grad_norm=0.0, use_kl=False)
+                eng.refresh_padded(after_step=True)
+        # loss accumulators of the fused kernel: [surrogate, value, entropy] -> the composite order
+        sums[0:1].copy_(ds.loss_sums[1:2]); sums[1:2].copy_(ds.loss_sums[0:1]); sums[2:3].copy_(ds.loss_sums[2:3])
+
     def _composite_minibatches(self, sums):
         """The minibatch loop of the composite update (everything it puts on the stream is graph-capturable for
         feed-forward policies)."""
+        if self._composite_fusable():
+            return self._composite_minibatches_fused(sums)
         pol, st, opt = self.policy, self.storage, self.optimizer
         M, E = self.num_mini_batches, self.num_learning_epochs
         once = getattr(st, "_randperm_once", None)

@@ -87,6 +87,24 @@ __device__ __forceinline__ void wait_flag(const unsigned int* flag, unsigned int
   }
 }
 
+// Optional in-kernel timeline (build with -DRSLRL_AR_TRACE, read with tools/mgpu_phase_trace.py): per launch and block,
+// globaltimer stamps at 0 entry, 1 peers' backward complete (phase A), 2 slice reduced (phase 1), 3 grid barrier passed,
+// 4 Adam done, 5 peers done reading / exit.  Ring of kArTraceLaunches launches.
+#ifdef RSLRL_AR_TRACE
+constexpr int kArTraceLaunches = 64;
+__device__ unsigned long long g_ar_trace[kArTraceLaunches * kArMaxBlocks * 8];
+__device__ __forceinline__ void ar_trace(unsigned int epoch, int slot) {
+  if (threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    g_ar_trace[((epoch % kArTraceLaunches) * kArMaxBlocks + blockIdx.x) * 8 + slot] = t;
+  }
+}
+#define AR_TRACE(slot) ar_trace(epoch, slot)
+#else
+#define AR_TRACE(slot) do { } while (0)
+#endif
+
 __device__ __forceinline__ void adam_elem1(float& p, float g, float& m, float& v, float scale, float w1, float b2,
                                            float w2, float bc2_sqrt, float eps, float neg_step) {
   const float gc = g * scale;
@@ -115,6 +133,7 @@ __global__ void __launch_bounds__(kArThreads, 1) allreduce_clip_adam_kernel(cons
   const double lr_old = prm.state->lr;
   const long long step_old = prm.state->step;
 
+  AR_TRACE(0);
   // ---- A: every rank's backward is complete
   if (W > 1) {
     if (tid < W && tid != rank) {
@@ -125,6 +144,7 @@ __global__ void __launch_bounds__(kArThreads, 1) allreduce_clip_adam_kernel(cons
     __syncthreads();
   }
 
+  AR_TRACE(1);
   // ---- 1: reduce slice b over the ranks (fixed order), keep it in shared memory, sum of squares
   double acc[1] = {0.0};
   for (long long i = i0 + tid; i < i1; i += kArThreads) {
@@ -149,6 +169,7 @@ __global__ void __launch_bounds__(kArThreads, 1) allreduce_clip_adam_kernel(cons
       st_release_sys(prm.peer_flags[tid] + (1 * kArMaxBlocks + b) * kArMaxWorld + rank, stamp);
   }
 
+  AR_TRACE(2);
   // ---- 2: grid barrier, then norm / clip / lr / bias corrections (redundantly per block, deterministic order)
   if (tid == 0) {
     ws->partial[b] = acc[0];
@@ -205,6 +226,7 @@ __global__ void __launch_bounds__(kArThreads, 1) allreduce_clip_adam_kernel(cons
   }
   __syncthreads();
 
+  AR_TRACE(3);
   // ---- 3: Adam on slice b
   {
     const float scale = (float)s_scal[0], neg_step = (float)(-s_scal[1]), bc2_sqrt = (float)s_scal[2];
@@ -230,6 +252,7 @@ __global__ void __launch_bounds__(kArThreads, 1) allreduce_clip_adam_kernel(cons
     }
   }
 
+  AR_TRACE(4);
   // ---- 4: the peers have read slice b of this rank's gradients -> clear it for the next backward pass
   if (W > 1) {
     if (tid < W && tid != rank) wait_flag(prm.peer_flags[rank] + (1 * kArMaxBlocks + b) * kArMaxWorld + tid, stamp, prm.timeout_cycles);
@@ -238,6 +261,7 @@ __global__ void __launch_bounds__(kArThreads, 1) allreduce_clip_adam_kernel(cons
   if (prm.zero_grad) {
     for (long long i = i0 + tid; i < i1; i += kArThreads) ((float4*)prm.g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  AR_TRACE(5);
 }
 
 }  // namespace rslrl
@@ -320,5 +344,12 @@ int rslrl_allreduce_clip_adam(int world, int rank, const float* const* peer_grad
   launch_chain_kernel(allreduce_clip_adam_kernel, dim3((int)grid), dim3(kArThreads), smem, (cudaStream_t)stream, prm);
   return finish_launch(what);
 }
+
+#ifdef RSLRL_AR_TRACE
+int rslrl_debug_read_trace_allreduce(unsigned long long* host) {
+  return (int)cudaMemcpyFromSymbol(host, rslrl::g_ar_trace,
+                                   sizeof(unsigned long long) * rslrl::kArTraceLaunches * rslrl::kArMaxBlocks * 8);
+}
+#endif
 
 }  // extern "C"

@@ -141,4 +141,59 @@ int rslrl_lstm_cell_backward(const float* dh_out, const float* dh_rec, const flo
   return finish_launch(what);
 }
 
+// ---- whole-layer drivers: the time loop runs in C (one GEMM + one cell launch per step), not in the caller -----------
+// xg [T*n,4H] is the hoisted input projection; h_all / c_all are [(T+1),n,H] with slot 0 = initial state (the caller
+// fills it), slot t+1 = state after step t; gates [T,n,4H] (NULL: inference); hg [n,4H] scratch.
+int rslrl_lstm_layer_forward(const float* xg, const float* w_hh, const float* b_hh, float* h_all, float* c_all,
+                             float* gates, float* hg, int T, int64_t n, int H, int precision, rslrl_stream_t stream) {
+  using namespace rslrl;
+  const char* what = "rslrl_lstm_layer_forward";
+  RSLRL_CHECK_ARG(xg && w_hh && h_all && c_all && hg && T > 0 && n > 0 && H > 0 && (H % 4) == 0, what);
+  const size_t nH = (size_t)n * H, nG = (size_t)n * 4 * H;
+  for (int t = 0; t < T; ++t) {
+    rslrl_linear_fwd_t p{};
+    p.x = h_all + t * nH; p.w = w_hh; p.b = nullptr; p.y = hg;
+    p.M = (int)n; p.N = 4 * H; p.K = H; p.ldx = H; p.ldy = 4 * H; p.act = RSLRL_ACT_IDENTITY;
+    int rc = rslrl_linear_forward(1, &p, precision, stream);
+    if (rc != 0) return rc;
+    rc = rslrl_lstm_cell_forward(xg + t * nG, hg, b_hh, c_all + t * nH, gates ? gates + t * nG : nullptr,
+                                 c_all + (t + 1) * nH, h_all + (t + 1) * nH, n, H, stream);
+    if (rc != 0) return rc;
+  }
+  return 0;
+}
+
+// Backward through time: dout [T,n,H] (may be NULL), dhT / dcT gradients of the final state (may be NULL) ->
+// dgates [T,n,4H]; dh_scratch / dc_scratch are [2][n,H]; on return slot 0 of each holds d h_0 / d c_0
+// (d h_0 only when need_dh0).
+int rslrl_lstm_layer_backward(const float* dout, const float* dhT, const float* dcT, const float* gates,
+                              const float* c_all, const float* w_hh, float* dgates, float* dh_scratch,
+                              float* dc_scratch, int need_dh0, int T, int64_t n, int H, int precision,
+                              rslrl_stream_t stream) {
+  using namespace rslrl;
+  const char* what = "rslrl_lstm_layer_backward";
+  RSLRL_CHECK_ARG(gates && c_all && w_hh && dgates && dh_scratch && dc_scratch && T > 0 && n > 0 && H > 0 && (H % 4) == 0,
+                  what);
+  const size_t nH = (size_t)n * H, nG = (size_t)n * 4 * H;
+  const float* dh_rec = dhT;
+  const float* dc = dcT;
+  for (int t = T - 1; t >= 0; --t) {
+    float* dc_prev = dc_scratch + (size_t)(t & 1) * nH;
+    int rc = rslrl_lstm_cell_backward(dout ? dout + t * nH : nullptr, dh_rec, dc, gates + t * nG, c_all + t * nH,
+                                      c_all + (t + 1) * nH, dgates + t * nG, dc_prev, n, H, stream);
+    if (rc != 0) return rc;
+    dc = dc_prev;
+    if (t > 0 || need_dh0) {
+      float* dh = dh_scratch + (size_t)(t & 1) * nH;
+      rslrl_linear_bwd_data_t q{};
+      q.dy = dgates + t * nG; q.w = w_hh; q.h = nullptr; q.dx = dh;
+      q.M = (int)n; q.N = 4 * H; q.K = H; q.ldy = 4 * H; q.ldh = 0; q.ldx = H; q.act = RSLRL_ACT_IDENTITY; q.db_prev = nullptr;
+      rc = rslrl_linear_backward_data(1, &q, precision, stream);
+      if (rc != 0) return rc;
+      dh_rec = dh;
+    }
+  }
+  return 0;
+}
+
 }  // extern "C"

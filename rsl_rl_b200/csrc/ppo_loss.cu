@@ -46,6 +46,9 @@ struct SumWorkspace {
   __shared__ unsigned int s_gmax;                                                                     \
   if (threadIdx.x == 0) s_gmax = 0u;
 
+// saturating conversion guard: a scaled gradient beyond fp16's range becomes +-65504 (counted by the caller), never inf
+__device__ __forceinline__ float sat16(float x) { return fminf(fmaxf(x, -65504.f), 65504.f); }
+
 __device__ __forceinline__ void loss_scale_track(float* scale_state, unsigned int* s_gmax, float local_max) {
   if (scale_state == nullptr) return;
   float m = local_max;
@@ -219,7 +222,7 @@ ppo_loss_kernel(const float* __restrict__ mu, const float* __restrict__ std_para
       dv_out = c_v * g * (-2.f) * e;
     }
     dvalue[i * dvalue_stride] = dv_out;
-    if (dvalue16 != nullptr) dvalue16[i * dvalue16_stride] = __float2half_rn(dv_out * scale16);
+    if (dvalue16 != nullptr) dvalue16[i * dvalue16_stride] = __float2half_rn(sat16(dv_out * scale16));
     dv_sum = dv_out;
     gmax = fabsf(dv_out);
   }
@@ -259,7 +262,7 @@ ppo_loss_kernel(const float* __restrict__ mu, const float* __restrict__ std_para
         else for (int q = 0; q < nq; ++q) dm[c + q] = o[q];
         gmax = fmaxf(fmaxf(gmax, fmaxf(fabsf(o[0]), fabsf(o[1]))), fmaxf(fabsf(o[2]), fabsf(o[3])));
         if (VEC && dmu16 != nullptr) {  // scaled fp16 copy (A % 4 == 0): the A operand of the fp16 output-layer backward
-          const __half2 lo2 = __floats2half2_rn(o[0] * scale16, o[1] * scale16), hi2 = __floats2half2_rn(o[2] * scale16, o[3] * scale16);
+          const __half2 lo2 = __floats2half2_rn(sat16(o[0] * scale16), sat16(o[1] * scale16)), hi2 = __floats2half2_rn(sat16(o[2] * scale16), sat16(o[3] * scale16));
           uint2 w;
           w.x = *(const unsigned int*)&lo2;
           w.y = *(const unsigned int*)&hi2;
@@ -433,7 +436,7 @@ ppo_loss_quad_kernel(const float* __restrict__ mu, const float* __restrict__ std
         dv_out = c_v * g * (-2.f) * e;
       }
       dvalue[i * dvalue_stride] = dv_out;
-      if (dvalue16 != nullptr) dvalue16[i * dvalue16_stride] = __float2half_rn(dv_out * scale16);
+      if (dvalue16 != nullptr) dvalue16[i * dvalue16_stride] = __float2half_rn(sat16(dv_out * scale16));
       dv_sum = dv_out;
       gmax = fabsf(dv_out);
     }
@@ -453,7 +456,7 @@ ppo_loss_quad_kernel(const float* __restrict__ mu, const float* __restrict__ std
       gmax = fmaxf(fmaxf(gmax, fmaxf(fabsf(o[0]), fabsf(o[1]))), fmaxf(fabsf(o[2]), fabsf(o[3])));
       *(float4*)(dmu + i * dmu_stride + c) = make_float4(o[0], o[1], o[2], o[3]);
       if (dmu16 != nullptr) {  // scaled fp16 copy: the A operand of the fp16 output-layer backward
-        const __half2 lo2 = __floats2half2_rn(o[0] * scale16, o[1] * scale16), hi2 = __floats2half2_rn(o[2] * scale16, o[3] * scale16);
+        const __half2 lo2 = __floats2half2_rn(sat16(o[0] * scale16), sat16(o[1] * scale16)), hi2 = __floats2half2_rn(sat16(o[2] * scale16), sat16(o[3] * scale16));
         uint2 w;
         w.x = *(const unsigned int*)&lo2;
         w.y = *(const unsigned int*)&hi2;

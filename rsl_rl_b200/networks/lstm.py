@@ -40,10 +40,10 @@ def _layer_forward(x, h0, c0, w_ih, w_hh, b_ih, b_hh, prec: int, save: bool):
     c_all[0].copy_(c0)
     gates = torch.empty(T, n, 4 * H, **f32) if save else None
     hg = torch.empty(n, 4 * H, **f32)
-    for t in range(T):
-        linear_forward([(h_all[t], w_hh, None, hg, _IDENT)], prec)     # recurrent projection
-        _cell_forward(xg[t * n:(t + 1) * n], hg, b_hh, c_all[t], None if gates is None else gates[t], c_all[t + 1],
-                      h_all[t + 1])
+    # the time loop runs in C: per step one recurrent projection (h_{t-1} W_hh^T) + one fused cell launch
+    nat.check(nat.lib().rslrl_lstm_layer_forward(xg.data_ptr(), w_hh.data_ptr(), nat.ptr(b_hh), h_all.data_ptr(),
+                                                 c_all.data_ptr(), nat.ptr(gates), hg.data_ptr(), T, n, H, prec,
+                                                 nat.stream_ptr()))
     return h_all, c_all, gates, x2d
 
 
@@ -66,18 +66,15 @@ class _LSTMLayerFunction(torch.autograd.Function):
         f32 = dict(dtype=torch.float32, device=gates.device)
         dout = None if dout is None else nat.f32c(dout)
         dgates = torch.empty(T, n, H4, **f32)
-        dh_rec = None if dhT is None else nat.f32c(dhT)
-        dc = None if dcT is None else nat.f32c(dcT)
-        dc_bufs = (torch.empty(n, H, **f32), torch.empty(n, H, **f32))
-        dh_bufs = (torch.empty(n, H, **f32), torch.empty(n, H, **f32))
-        for t in range(T - 1, -1, -1):
-            dc_prev = dc_bufs[t & 1]
-            _cell_backward(None if dout is None else dout[t], dh_rec, dc, gates[t], c_all[t], c_all[t + 1], dgates[t],
-                           dc_prev)
-            dc = dc_prev
-            if t > 0 or ctx.needs_input_grad[1]:
-                dh_rec = dh_bufs[t & 1]
-                linear_backward_data([(dgates[t], w_hh, None, dh_rec, _IDENT)], prec)   # dh_{t-1} = dG_t W_hh
+        dhT = None if dhT is None else nat.f32c(dhT)
+        dcT = None if dcT is None else nat.f32c(dcT)
+        dh_bufs, dc_bufs = torch.empty(2, n, H, **f32), torch.empty(2, n, H, **f32)
+        # backward through time in C: per step one fused cell-backward launch + dh_{t-1} = dG_t W_hh
+        nat.check(nat.lib().rslrl_lstm_layer_backward(nat.ptr(dout), nat.ptr(dhT), nat.ptr(dcT), gates.data_ptr(),
+                                                      c_all.data_ptr(), w_hh.data_ptr(), dgates.data_ptr(),
+                                                      dh_bufs.data_ptr(), dc_bufs.data_ptr(),
+                                                      int(bool(ctx.needs_input_grad[1])), T, n, H, prec, nat.stream_ptr()))
+        dh_rec, dc = dh_bufs[0], dc_bufs[0]
         dg2d = dgates.view(T * n, H4)
         dw_ih, dw_hh = torch.zeros_like(w_ih), torch.zeros_like(w_hh)
         db = torch.zeros(H4, **f32) if ctx.has_bias else None

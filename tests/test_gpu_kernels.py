@@ -625,7 +625,7 @@ def test_update_rng_skip_matches_the_discarded_draws():
         PPO._skip_discarded_draws(Stub, n)
         assert torch.equal(gen.get_state(), expect_state)
         assert torch.equal(torch.randperm(1000, device=DEV), expect_next)
-    assert Stub._draw_offset is not None and Stub._draw_offset > 0
+    assert Stub._draw_offset and all(v > 0 for v in Stub._draw_offset.values())
 
 
 # ------------------------------------------------------------------------------------ running normaliser
