@@ -52,10 +52,10 @@ else:
 with contextlib.redirect_stdout(io.StringIO()):
     env = SynthVecEnv(N, {"policy": 48}, 12, device=dev, seed=0)
     runner = OnPolicyRunner(env, cfg, log_dir=None, device=dev)
-    runner.learn(4)
+    runner.learn(int(os.environ.get('RSLRL_C45_WARMUP', '4')))
 torch.cuda.synchronize()
 runner.profile_phases = True
-K = 5
+K = int(os.environ.get('RSLRL_C45_ITERS', '5'))
 t0 = time.perf_counter()
 with contextlib.redirect_stdout(io.StringIO()):
     runner.learn(K)

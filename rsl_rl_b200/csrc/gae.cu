@@ -28,11 +28,11 @@
 namespace rslrl {
 
 constexpr int kGaeThreads = 128;      // grid-stride fallback kernel
-constexpr int kGaeMaxBlocks = 4096;   // workspace capacity (pairs of doubles)
+constexpr int kGaeMaxBlocks = 592;    // workspace capacity (pairs of doubles): 4 blocks per SM on 148 SMs
 
 struct GaeBarrier {
-  unsigned int arrived;
-  unsigned int departed;
+  unsigned int count;  // arrivals of the current generation (atomicInc wraps it back to 0 at gridDim.x: self re-arming)
+  unsigned int gen;    // generation: flipped by the last arriver, polled by everybody else
 };
 
 __device__ __forceinline__ unsigned int gae_ld_acquire(const unsigned int* p) {
@@ -40,44 +40,48 @@ __device__ __forceinline__ unsigned int gae_ld_acquire(const unsigned int* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void gae_st_release(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
+// Sense-reversing grid barrier (co-residency guaranteed by the cooperative launch): no departure phase, nothing to
+// reset between launches, grid size may differ from launch to launch.
 __device__ __forceinline__ void gae_grid_barrier(GaeBarrier* bar) {
   __syncthreads();
   if (threadIdx.x == 0) {
+    const unsigned int gen = gae_ld_acquire(&bar->gen);   // cannot change before this block has arrived
     __threadfence();
-    atomicAdd(&bar->arrived, 1u);
-    while (gae_ld_acquire(&bar->arrived) < gridDim.x) {
+    if (atomicInc(&bar->count, gridDim.x - 1) == gridDim.x - 1) {
+      gae_st_release(&bar->gen, gen + 1u);
+    } else {
+      while (gae_ld_acquire(&bar->gen) == gen) {
+      }
     }
   }
   __syncthreads();
-}
-
-__device__ __forceinline__ void gae_grid_barrier_release(GaeBarrier* bar) {
-  // called after the post-barrier reads: the last block out re-arms the barrier for the next launch
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    if (atomicAdd(&bar->departed, 1u) == gridDim.x - 1) {
-      bar->arrived = 0u;
-      bar->departed = 0u;
-      __threadfence();
-    }
-  }
 }
 
 __device__ __forceinline__ void gae_finalize_stats(double s, double ss, double* partials, double* smem,
                                                    GaeBarrier* bar, int64_t B, float& mean_f, float& denom_f) {
   double v[2] = {s, ss};
   block_sum<2>(v, smem);
-  if (threadIdx.x == 0) {
-    partials[2 * blockIdx.x] = v[0];
-    partials[2 * blockIdx.x + 1] = v[1];
-  }
+  if (threadIdx.x == 0) *(double2*)(partials + 2 * blockIdx.x) = make_double2(v[0], v[1]);
+  GAE_TRACE(2);
   gae_grid_barrier(bar);
-  if (threadIdx.x < 32) {   // one warp, fixed order: every block derives the same bits
+  GAE_TRACE(3);
+  if (threadIdx.x < 32) {   // one warp, fixed order (every block derives the same bits); all loads in flight at once
+    constexpr int kPer = (kGaeMaxBlocks + 31) / 32;
+    double2 p[kPer];
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const int i = threadIdx.x + 32 * k;
+      p[k] = i < (int)gridDim.x ? __ldcg((const double2*)(partials + 2 * i)) : make_double2(0.0, 0.0);
+    }
     double t0 = 0.0, t1 = 0.0;
-    for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) {
-      t0 += __ldcg(partials + 2 * i);
-      t1 += __ldcg(partials + 2 * i + 1);
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      t0 += p[k].x;
+      t1 += p[k].y;
     }
     t0 = warp_sum(t0);
     t1 = warp_sum(t1);
@@ -90,8 +94,8 @@ __device__ __forceinline__ void gae_finalize_stats(double s, double ss, double* 
       smem[1] = sqrt(var);
     }
   }
-  gae_grid_barrier_release(bar);   // (contains the __syncthreads that publishes smem[0..1])
   __syncthreads();
+  GAE_TRACE(4);
   mean_f = (float)smem[0];
   denom_f = __fadd_rn((float)smem[1], 1e-8f);
 }
@@ -104,6 +108,7 @@ gae_norm_reg_kernel(const float* __restrict__ rewards, const float* __restrict__
                     float* __restrict__ returns, float* __restrict__ advantages, double* __restrict__ partials,
                     GaeBarrier* bar, int T, int N, float gamma, float lam, int normalize) {
   __shared__ double smem[64];
+  GAE_TRACE(0);
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   float r[TMAX], v[TMAX];   // r[i] is overwritten by returns[i] during the scan
   double s = 0.0, ss = 0.0;
@@ -137,6 +142,7 @@ gae_norm_reg_kernel(const float* __restrict__ rewards, const float* __restrict__
     }
   }
   float mean_f = 0.f, denom_f = 1.f;
+  GAE_TRACE(1);
   if (normalize) gae_finalize_stats(s, ss, partials, smem, bar, (int64_t)T * N, mean_f, denom_f);
   if (n < N) {
 #pragma unroll
@@ -148,6 +154,7 @@ gae_norm_reg_kernel(const float* __restrict__ rewards, const float* __restrict__
       }
     }
   }
+  GAE_TRACE(5);
 }
 
 // Any T, any N: grid-stride over envs, raw advantages staged through `advantages` itself.
@@ -221,10 +228,10 @@ template <int TMAX>
 static int launch_reg(void** args, int N, cudaStream_t st) {
   // at most one block per SM: the block size grows with the env count (128 .. 512 threads)
   const int sms = device_sms();
-  int threads = 128;
-  while (threads < 512 && (N + threads - 1) / threads > sms) threads *= 2;
+  int threads = ((N + sms - 1) / sms + 31) / 32 * 32;   // one block per SM, every SM used
+  if (threads < 128) threads = 128;
+  if (threads > 512) return -1;  // more envs than one wave of register-resident threads: grid-stride kernel
   const int blocks = (N + threads - 1) / threads;
-  if (blocks > sms) return -1;  // more envs than one wave of register-resident threads: grid-stride kernel
   return launch_coop(gae_norm_reg_kernel<TMAX>, blocks, threads, args, st);
 }
 
@@ -262,5 +269,11 @@ int rslrl_gae_norm(const float* rewards, const float* values, const uint8_t* don
   const int blocks = (N + kGaeThreads - 1) / kGaeThreads;
   return launch_coop(gae_norm_generic_kernel, blocks < cap ? blocks : cap, kGaeThreads, args, st);
 }
+
+#ifdef RSLRL_GAE_TRACE
+int rslrl_debug_read_trace_gae(unsigned long long* host) {
+  return (int)cudaMemcpyFromSymbol(host, rslrl::g_gae_trace, sizeof(unsigned long long) * 148 * 8);
+}
+#endif
 
 }  // extern "C"

@@ -163,16 +163,17 @@ int rslrl_lstm_layer_forward(const float* xg, const float* w_hh, const float* b_
   return 0;
 }
 
-// Backward through time: dout [T,n,H] (may be NULL), dhT / dcT gradients of the final state (may be NULL) ->
+// Backward through time: dout [T,n,H] (may be NULL), dhT / dcT gradients of the final state (may be NULL), w_hh_t [H,4H] =
+// W_hh transposed ->
 // dgates [T,n,4H]; dh_scratch / dc_scratch are [2][n,H]; on return slot 0 of each holds d h_0 / d c_0
 // (d h_0 only when need_dh0).
 int rslrl_lstm_layer_backward(const float* dout, const float* dhT, const float* dcT, const float* gates,
-                              const float* c_all, const float* w_hh, float* dgates, float* dh_scratch,
+                              const float* c_all, const float* w_hh_t, float* dgates, float* dh_scratch,
                               float* dc_scratch, int need_dh0, int T, int64_t n, int H, int precision,
                               rslrl_stream_t stream) {
   using namespace rslrl;
   const char* what = "rslrl_lstm_layer_backward";
-  RSLRL_CHECK_ARG(gates && c_all && w_hh && dgates && dh_scratch && dc_scratch && T > 0 && n > 0 && H > 0 && (H % 4) == 0,
+  RSLRL_CHECK_ARG(gates && c_all && w_hh_t && dgates && dh_scratch && dc_scratch && T > 0 && n > 0 && H > 0 && (H % 4) == 0,
                   what);
   const size_t nH = (size_t)n * H, nG = (size_t)n * 4 * H;
   const float* dh_rec = dhT;
@@ -184,11 +185,13 @@ int rslrl_lstm_layer_backward(const float* dout, const float* dhT, const float* 
     if (rc != 0) return rc;
     dc = dc_prev;
     if (t > 0 || need_dh0) {
+      // dh_{t-1} = dG_t W_hh, issued as the FORWARD product dG_t (W_hh^T)^T against the transposed copy of W_hh the caller
+      // passes ([H,4H] row-major): a plain K-major GEMM without activation, which the tensor-core forward kernel covers
       float* dh = dh_scratch + (size_t)(t & 1) * nH;
-      rslrl_linear_bwd_data_t q{};
-      q.dy = dgates + t * nG; q.w = w_hh; q.h = nullptr; q.dx = dh;
-      q.M = (int)n; q.N = 4 * H; q.K = H; q.ldy = 4 * H; q.ldh = 0; q.ldx = H; q.act = RSLRL_ACT_IDENTITY; q.db_prev = nullptr;
-      rc = rslrl_linear_backward_data(1, &q, precision, stream);
+      rslrl_linear_fwd_t q{};
+      q.x = dgates + t * nG; q.w = w_hh_t; q.b = nullptr; q.y = dh;
+      q.M = (int)n; q.N = H; q.K = 4 * H; q.ldx = 4 * H; q.ldy = H; q.act = RSLRL_ACT_IDENTITY;
+      rc = rslrl_linear_forward(1, &q, precision, stream);
       if (rc != 0) return rc;
       dh_rec = dh;
     }

@@ -70,8 +70,9 @@ class _LSTMLayerFunction(torch.autograd.Function):
         dcT = None if dcT is None else nat.f32c(dcT)
         dh_bufs, dc_bufs = torch.empty(2, n, H, **f32), torch.empty(2, n, H, **f32)
         # backward through time in C: per step one fused cell-backward launch + dh_{t-1} = dG_t W_hh
+        w_hh_t = w_hh.detach().t().contiguous()   # [H, 4H]: dh_{t-1} = dG_t W_hh as a forward product
         nat.check(nat.lib().rslrl_lstm_layer_backward(nat.ptr(dout), nat.ptr(dhT), nat.ptr(dcT), gates.data_ptr(),
-                                                      c_all.data_ptr(), w_hh.data_ptr(), dgates.data_ptr(),
+                                                      c_all.data_ptr(), w_hh_t.data_ptr(), dgates.data_ptr(),
                                                       dh_bufs.data_ptr(), dc_bufs.data_ptr(),
                                                       int(bool(ctx.needs_input_grad[1])), T, n, H, prec, nat.stream_ptr()))
         dh_rec, dc = dh_bufs[0], dc_bufs[0]

@@ -1,7 +1,7 @@
 """In-kernel phase breakdown of `allreduce_clip_adam_kernel` at N ranks (run under torchrun with a trace build):
 
-    python -m rsl_rl_b200._build --out rsl_rl_b200/lib/librslrl_b200_artrace.so -DRSLRL_AR_TRACE
-    RSLRL_B200_LIB=rsl_rl_b200/lib/librslrl_b200_artrace.so python -m torch.distributed.run --nnodes=1 \
+    python -m rsl_rl_b200._build --out rsl_rl_b200/lib/librslrl_b200_trace.so -DRSLRL_AR_TRACE -DRSLRL_GAE_TRACE
+    RSLRL_B200_LIB=rsl_rl_b200/lib/librslrl_b200_trace.so python -m torch.distributed.run --nnodes=1 \
         --nproc-per-node N --master-addr 127.0.0.1 --master-port 29521 tools/mgpu_phase_trace.py
 
 Each rank runs bench-shaped learn() iterations (C2, fp16), then reads the globaltimer stamps of the last 64 optimiser
