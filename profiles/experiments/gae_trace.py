@@ -30,8 +30,7 @@ for N in (4096, 65536):
         e0.record(); st.compute_returns(last, 0.99, 0.95); e1.record(); e1.synchronize()
         buf = (C.c_ulonglong * (148 * 8))()
         assert lib.rslrl_debug_read_trace_gae(buf) == 0
-        threads = 128
-        while threads < 512 and (N + threads - 1) // threads > 148: threads *= 2
+        threads = max(128, ((N + 147) // 148 + 31) // 32 * 32)
         blocks = (N + threads - 1) // threads
         stp = [[buf[b * 8 + s] for s in range(6)] for b in range(blocks)]
         t0 = min(r[0] for r in stp)

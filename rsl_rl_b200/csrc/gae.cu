@@ -30,6 +30,22 @@ namespace rslrl {
 constexpr int kGaeThreads = 128;      // grid-stride fallback kernel
 constexpr int kGaeMaxBlocks = 592;    // workspace capacity (pairs of doubles): 4 blocks per SM on 148 SMs
 
+// Optional in-kernel timeline (build with -DRSLRL_GAE_TRACE; profiles/experiments/gae_trace.py): per block globaltimer at
+// 0 entry, 1 loads landed + scan done, 2 partials published (barrier arrival), 3 barrier passed, 4 statistics known, 5 exit.
+#ifdef RSLRL_GAE_TRACE
+__device__ unsigned long long g_gae_trace[148 * 8];
+__device__ __forceinline__ void gae_trace(int slot) {
+  if (threadIdx.x == 0 && blockIdx.x < 148) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    g_gae_trace[blockIdx.x * 8 + slot] = t;
+  }
+}
+#define GAE_TRACE(slot) gae_trace(slot)
+#else
+#define GAE_TRACE(slot) do { } while (0)
+#endif
+
 struct GaeBarrier {
   unsigned int count;  // arrivals of the current generation (atomicInc wraps it back to 0 at gridDim.x: self re-arming)
   unsigned int gen;    // generation: flipped by the last arriver, polled by everybody else
