@@ -240,8 +240,8 @@ def test_tensor_core_iteration_vs_oracle_c3_layout():
 @pytest.mark.parametrize("reward_scale", [1e4, 1e-4])
 def test_fp16_gradient_range_is_tracked(reward_scale):
     """fp16 storage of the layer gradients under extreme reward magnitudes (value-loss gradients ~ reward scale): the
-    device-resident dynamic power-of-two scale follows the gradient magnitude, nothing saturates after the first
-    minibatch has calibrated it, results stay finite and in the 1e-3 class."""
+    device-resident dynamic power-of-two scale is calibrated on the first minibatch and then follows the gradient
+    magnitude; nothing saturates, results stay finite and in the tensor-core class."""
     from tools import parity_report as R
     R.SHAPES["range"] = dict(N=1024, T=8, groups={"policy": 48}, A=12, hidden=[128, 128, 64], seed=31)
     r = R.compare("range", "fp16", reward_scale=reward_scale)
@@ -249,10 +249,9 @@ def test_fp16_gradient_range_is_tracked(reward_scale):
     assert r["finite"]
     for k in ("rollout.mu", "rollout.values", "rollout.returns"):
         assert r[k] < 1e-3, (k, r[k])
-    assert r["grad0.max_norm"] < 2e-3 or r["fp16_saturation_events"] > 0, r["grad0.max_norm"]
-    # at most the very first minibatch (scale still at its initial guess) may saturate; it is counted, never silent
-    assert r["fp16_saturation_events"] <= 1, r["fp16_saturation_events"]
-    assert r["params_after.rel_l2_until_lr_divergence"] is None or r["params_after.rel_l2_until_lr_divergence"] < 2e-3
+    assert r["fp16_saturation_events"] == 0, r["fp16_saturation_events"]
+    assert r["grad0.max_norm"] < 2e-3, r["grad0.max_norm"]
+    assert r["params_after.rel_l2_until_lr_divergence"] is None or r["params_after.rel_l2_until_lr_divergence"] < 3e-3
 
 
 def test_tf32_unaligned_observation_width_vs_oracle():
