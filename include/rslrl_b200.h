@@ -217,19 +217,26 @@ int rslrl_lstm_cell_backward(const float* dh_out, const float* dh_rec, const flo
                              const float* c_prev, const float* c_cur, float* dgates, float* dc_prev, int64_t n, int H,
                              rslrl_stream_t stream);
 
-/* Whole-layer drivers (the time loop in C: one recurrent projection + one cell launch per step).  Forward: xg [T*n,4H]
- * hoisted input projection, h_all / c_all [(T+1),n,H] with slot 0 = initial state (filled by the caller) and slot t+1 =
- * state after step t, gates [T,n,4H] or NULL (inference), hg [n,4H] scratch.  Backward through time: dout [T,n,H] / dhT /
- * dcT (each may be NULL), w_hh_t [H,4H] = W_hh transposed (dh_{t-1} = dgates_t W_hh runs as a forward product) ->
- * dgates [T,n,4H]; dh_scratch / dc_scratch [2][n,H], slot 0 of each = d h_0 / d c_0 on return
- * (d h_0 only when need_dh0).  The weight gradients are two products over all T*n rows (rslrl_linear_backward_weight with
- * dgates against the layer input and against h_all[0..T-1]). */
-int rslrl_lstm_layer_forward(const float* xg, const float* w_hh, const float* b_hh, float* h_all, float* c_all,
-                             float* gates, float* hg, int T, int64_t n, int H, int precision, rslrl_stream_t stream);
-int rslrl_lstm_layer_backward(const float* dout, const float* dhT, const float* dcT, const float* gates,
-                              const float* c_all, const float* w_hh_t, float* dgates, float* dh_scratch,
-                              float* dc_scratch, int need_dh0, int T, int64_t n, int H, int precision,
+/* Whole-layer drivers: the time loop runs in C, one grouped recurrent-projection launch + one cell launch per step for
+ * 1 or 2 LSTM layers of equal shape (the actor's and the critic's memory advance together).
+ * Forward: xg [T*n,4H] hoisted input projection, h_all / c_all [(T+1),n,H] with slot 0 = initial state (filled by the
+ * caller) and slot t+1 = state after step t, gates [T,n,4H] or NULL (inference), hg [n,4H] scratch.
+ * Backward through time: dout [T,n,H] / dhT / dcT (each may be NULL), w_hh_t [H,4H] = W_hh transposed (dh_{t-1} =
+ * dgates_t W_hh runs as a forward product) -> dgates [T,n,4H]; dh_scratch / dc_scratch [2][n,H], slot 0 of each = d h_0 /
+ * d c_0 on return (d h_0 only when need_dh0).  The weight gradients are two products over all T*n rows
+ * (rslrl_linear_backward_weight with dgates against the layer input and against h_all[0..T-1]). */
+typedef struct {
+  const float* xg; const float* w_hh; const float* b_hh;
+  float* h_all; float* c_all; float* gates; float* hg;
+} rslrl_lstm_fwd_t;
+typedef struct {
+  const float* dout; const float* dhT; const float* dcT; const float* gates; const float* c_all; const float* w_hh_t;
+  float* dgates; float* dh_scratch; float* dc_scratch;
+} rslrl_lstm_bwd_t;
+int rslrl_lstm_layers_forward(int n_nets, const rslrl_lstm_fwd_t* nets_host, int T, int64_t n, int H, int precision,
                               rslrl_stream_t stream);
+int rslrl_lstm_layers_backward(int n_nets, const rslrl_lstm_bwd_t* nets_host, int need_dh0, int T, int64_t n, int H,
+                               int precision, rslrl_stream_t stream);
 
 /* ---- running-statistics normaliser (rsl_rl/networks/normalization.py:44-66) ---------------------------- */
 

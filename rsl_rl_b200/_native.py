@@ -58,6 +58,15 @@ class Mlp3Fwd(C.Structure):
                 ("head_logp", c_void_p), ("head_sigma", c_void_p)]
 
 
+class LstmFwd(C.Structure):
+    _fields_ = [(k, c_void_p) for k in ("xg", "w_hh", "b_hh", "h_all", "c_all", "gates", "hg")]
+
+
+class LstmBwd(C.Structure):
+    _fields_ = [(k, c_void_p) for k in ("dout", "dhT", "dcT", "gates", "c_all", "w_hh_t", "dgates", "dh_scratch",
+                                        "dc_scratch")]
+
+
 class OptState(C.Structure):
     _fields_ = [("lr", c_double), ("clip_scale", c_double), ("total_norm", c_double), ("step_size", c_double),
                 ("bc2_sqrt", c_double), ("kl_mean", c_double), ("step", C.c_longlong), ("pad_", C.c_longlong)]
@@ -110,8 +119,8 @@ _SIGNATURES = {
     "rslrl_hidden_at_starts": (c_int, [c_void_p] * 4 + [c_int] * 7 + [c_void_p]),
     "rslrl_lstm_cell_forward": (c_int, [c_void_p] * 7 + [c_i64, c_int, c_void_p]),
     "rslrl_lstm_cell_backward": (c_int, [c_void_p] * 8 + [c_i64, c_int, c_void_p]),
-    "rslrl_lstm_layer_forward": (c_int, [c_void_p] * 7 + [c_int, c_i64, c_int, c_int, c_void_p]),
-    "rslrl_lstm_layer_backward": (c_int, [c_void_p] * 9 + [c_int, c_int, c_i64, c_int, c_int, c_void_p]),
+    "rslrl_lstm_layers_forward": (c_int, [c_int, c_void_p, c_int, c_i64, c_int, c_int, c_void_p]),
+    "rslrl_lstm_layers_backward": (c_int, [c_int, c_void_p, c_int, c_int, c_i64, c_int, c_int, c_void_p]),
     "rslrl_empirical_norm_workspace_bytes": (c_i64, [c_int]),
     "rslrl_empirical_norm_update": (c_int, [c_void_p, c_i64, c_i64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_i64,
                                             c_void_p, c_void_p]),

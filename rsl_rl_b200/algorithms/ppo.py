@@ -327,8 +327,12 @@ class PPO:
         tr = self.transition
         if self.policy.is_recurrent:
             tr.hidden_states = self.policy.get_hidden_states()
-        tr.actions = self.policy.act(obs).detach()
-        tr.values = self.policy.evaluate(obs).detach()
+        if hasattr(self.policy, "act_evaluate"):   # recurrent policy: both memories in grouped launches
+            actions, values = self.policy.act_evaluate(obs)
+            tr.actions, tr.values = actions.detach(), values.detach()
+        else:
+            tr.actions = self.policy.act(obs).detach()
+            tr.values = self.policy.evaluate(obs).detach()
         tr.actions_log_prob = self.policy.get_actions_log_prob(tr.actions).detach()
         tr.action_mean = self.policy.action_mean.detach()
         tr.action_sigma = self.policy.action_std.detach()
@@ -809,9 +813,13 @@ class PPO:
                 adv_b = adv_b.repeat(num_aug, 1)
                 returns_b = returns_b.repeat(num_aug, 1)
 
-            pol.act(obs_b, masks=masks_b, hidden_states=hid_b[0])  # also draws the sample the reference discards
-            logp = pol.get_actions_log_prob(actions_b)
-            value = pol.evaluate(obs_b, masks=masks_b, hidden_states=hid_b[1])
+            if pol.is_recurrent and hasattr(pol, "act_evaluate"):   # both memories advance in grouped launches
+                _, value = pol.act_evaluate(obs_b, masks=masks_b, hidden_states=hid_b)
+                logp = pol.get_actions_log_prob(actions_b)
+            else:
+                pol.act(obs_b, masks=masks_b, hidden_states=hid_b[0])  # also draws the sample the reference discards
+                logp = pol.get_actions_log_prob(actions_b)
+                value = pol.evaluate(obs_b, masks=masks_b, hidden_states=hid_b[1])
             mu_b = pol.action_mean[:original_batch_size]
             sigma_b = pol.action_std[:original_batch_size]
             entropy_b = pol.entropy[:original_batch_size]

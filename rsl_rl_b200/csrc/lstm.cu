@@ -21,10 +21,24 @@ constexpr int kLstmThreads = 256;
 
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.f / (1.f + expf(-x)); }
 
+struct LstmFwdArgs {
+  const float *xg, *hg, *b_hh, *c_prev;
+  float *gates_act, *c_out, *h_out;
+};
+struct LstmFwdBatch { LstmFwdArgs net[2]; };
+struct LstmBwdArgs {
+  const float *dh_out, *dh_rec, *dc_next, *gates_act, *c_prev, *c_cur;
+  float *dgates, *dc_prev;
+};
+struct LstmBwdBatch { LstmBwdArgs net[2]; };
+
+// blockIdx.y = net (actor / critic memories of equal shape run in one launch)
 __global__ void __launch_bounds__(kLstmThreads)
-lstm_cell_forward_kernel(const float* __restrict__ xg, const float* __restrict__ hg, const float* __restrict__ b_hh,
-                         const float* __restrict__ c_prev, float* __restrict__ gates_act, float* __restrict__ c_out,
-                         float* __restrict__ h_out, long long n, int H) {
+lstm_cell_forward_kernel(const __grid_constant__ LstmFwdBatch batch, long long n, int H) {
+  const LstmFwdArgs& a = batch.net[blockIdx.y];
+  const float* __restrict__ xg = a.xg; const float* __restrict__ hg = a.hg; const float* __restrict__ b_hh = a.b_hh;
+  const float* __restrict__ c_prev = a.c_prev; float* __restrict__ gates_act = a.gates_act;
+  float* __restrict__ c_out = a.c_out; float* __restrict__ h_out = a.h_out;
   const int H4 = H >> 2;
   const long long total = n * H4;
   for (long long idx = (long long)blockIdx.x * kLstmThreads + threadIdx.x; idx < total;
@@ -62,10 +76,12 @@ lstm_cell_forward_kernel(const float* __restrict__ xg, const float* __restrict__
 }
 
 __global__ void __launch_bounds__(kLstmThreads)
-lstm_cell_backward_kernel(const float* __restrict__ dh_out, const float* __restrict__ dh_rec,
-                          const float* __restrict__ dc_next, const float* __restrict__ gates_act,
-                          const float* __restrict__ c_prev, const float* __restrict__ c_cur,
-                          float* __restrict__ dgates, float* __restrict__ dc_prev, long long n, int H) {
+lstm_cell_backward_kernel(const __grid_constant__ LstmBwdBatch batch, long long n, int H) {
+  const LstmBwdArgs& a = batch.net[blockIdx.y];
+  const float* __restrict__ dh_out = a.dh_out; const float* __restrict__ dh_rec = a.dh_rec;
+  const float* __restrict__ dc_next = a.dc_next; const float* __restrict__ gates_act = a.gates_act;
+  const float* __restrict__ c_prev = a.c_prev; const float* __restrict__ c_cur = a.c_cur;
+  float* __restrict__ dgates = a.dgates; float* __restrict__ dc_prev = a.dc_prev;
   const int H4 = H >> 2;
   const long long total = n * H4;
   for (long long idx = (long long)blockIdx.x * kLstmThreads + threadIdx.x; idx < total;
@@ -112,6 +128,15 @@ static int lstm_blocks(long long work) {
   return b < 1 ? 1 : (int)b;
 }
 
+static int launch_cell_forward(const LstmFwdBatch& b, int n_nets, long long n, int H, cudaStream_t st) {
+  lstm_cell_forward_kernel<<<dim3(lstm_blocks(n * (H / 4)), n_nets), kLstmThreads, 0, st>>>(b, n, H);
+  return finish_launch("rslrl_lstm_cell_forward");
+}
+static int launch_cell_backward(const LstmBwdBatch& b, int n_nets, long long n, int H, cudaStream_t st) {
+  lstm_cell_backward_kernel<<<dim3(lstm_blocks(n * (H / 4)), n_nets), kLstmThreads, 0, st>>>(b, n, H);
+  return finish_launch("rslrl_lstm_cell_backward");
+}
+
 }  // namespace rslrl
 
 extern "C" {
@@ -123,9 +148,9 @@ int rslrl_lstm_cell_forward(const float* xg, const float* hg, const float* b_hh,
   RSLRL_CHECK_ARG(xg && hg && c_prev && c_out && h_out && n > 0 && H > 0 && (H % 4) == 0, what);
   RSLRL_CHECK_ARG((((uintptr_t)xg | (uintptr_t)hg | (uintptr_t)b_hh | (uintptr_t)c_prev | (uintptr_t)gates_act |
                     (uintptr_t)c_out | (uintptr_t)h_out) & 15) == 0, what);
-  lstm_cell_forward_kernel<<<lstm_blocks(n * (H / 4)), kLstmThreads, 0, (cudaStream_t)stream>>>(
-      xg, hg, b_hh, c_prev, gates_act, c_out, h_out, n, H);
-  return finish_launch(what);
+  LstmFwdBatch b{};
+  b.net[0] = LstmFwdArgs{xg, hg, b_hh, c_prev, gates_act, c_out, h_out};
+  return launch_cell_forward(b, 1, n, H, (cudaStream_t)stream);
 }
 
 int rslrl_lstm_cell_backward(const float* dh_out, const float* dh_rec, const float* dc_next, const float* gates_act,
@@ -136,64 +161,80 @@ int rslrl_lstm_cell_backward(const float* dh_out, const float* dh_rec, const flo
   RSLRL_CHECK_ARG(gates_act && c_prev && c_cur && dgates && dc_prev && n > 0 && H > 0 && (H % 4) == 0, what);
   RSLRL_CHECK_ARG((((uintptr_t)dh_out | (uintptr_t)dh_rec | (uintptr_t)dc_next | (uintptr_t)gates_act |
                     (uintptr_t)c_prev | (uintptr_t)c_cur | (uintptr_t)dgates | (uintptr_t)dc_prev) & 15) == 0, what);
-  lstm_cell_backward_kernel<<<lstm_blocks(n * (H / 4)), kLstmThreads, 0, (cudaStream_t)stream>>>(
-      dh_out, dh_rec, dc_next, gates_act, c_prev, c_cur, dgates, dc_prev, n, H);
-  return finish_launch(what);
+  LstmBwdBatch b{};
+  b.net[0] = LstmBwdArgs{dh_out, dh_rec, dc_next, gates_act, c_prev, c_cur, dgates, dc_prev};
+  return launch_cell_backward(b, 1, n, H, (cudaStream_t)stream);
 }
 
-// ---- whole-layer drivers: the time loop runs in C (one GEMM + one cell launch per step), not in the caller -----------
-// xg [T*n,4H] is the hoisted input projection; h_all / c_all are [(T+1),n,H] with slot 0 = initial state (the caller
-// fills it), slot t+1 = state after step t; gates [T,n,4H] (NULL: inference); hg [n,4H] scratch.
-int rslrl_lstm_layer_forward(const float* xg, const float* w_hh, const float* b_hh, float* h_all, float* c_all,
-                             float* gates, float* hg, int T, int64_t n, int H, int precision, rslrl_stream_t stream) {
+// ---- whole-layer drivers: the time loop runs in C (one GEMM launch + one cell launch per step for ALL nets), not in the
+// caller.  `nets` describes 1 or 2 LSTM layers of equal shape (the actor's and the critic's memory) that advance together:
+// their recurrent projections are one grouped GEMM launch and their cells one launch per step.
+//   forward:  xg [T*n,4H] hoisted input projection; h_all / c_all [(T+1),n,H] with slot 0 = initial state (filled by the
+//             caller), slot t+1 = state after step t; gates [T,n,4H] (NULL: inference); hg [n,4H] scratch.
+//   backward: dout [T,n,H] / dhT / dcT (each may be NULL), w_hh_t [H,4H] = W_hh transposed (dh_{t-1} = dG_t W_hh runs as
+//             a forward product) -> dgates [T,n,4H]; dh_scratch / dc_scratch [2][n,H], slot 0 of each = d h_0 / d c_0 on
+//             return (d h_0 only when need_dh0).
+int rslrl_lstm_layers_forward(int n_nets, const rslrl_lstm_fwd_t* nets, int T, int64_t n, int H, int precision,
+                              rslrl_stream_t stream) {
   using namespace rslrl;
-  const char* what = "rslrl_lstm_layer_forward";
-  RSLRL_CHECK_ARG(xg && w_hh && h_all && c_all && hg && T > 0 && n > 0 && H > 0 && (H % 4) == 0, what);
+  const char* what = "rslrl_lstm_layers_forward";
+  RSLRL_CHECK_ARG(nets && n_nets >= 1 && n_nets <= 2 && T > 0 && n > 0 && H > 0 && (H % 4) == 0, what);
+  for (int i = 0; i < n_nets; ++i)
+    RSLRL_CHECK_ARG(nets[i].xg && nets[i].w_hh && nets[i].h_all && nets[i].c_all && nets[i].hg, what);
   const size_t nH = (size_t)n * H, nG = (size_t)n * 4 * H;
   for (int t = 0; t < T; ++t) {
-    rslrl_linear_fwd_t p{};
-    p.x = h_all + t * nH; p.w = w_hh; p.b = nullptr; p.y = hg;
-    p.M = (int)n; p.N = 4 * H; p.K = H; p.ldx = H; p.ldy = 4 * H; p.act = RSLRL_ACT_IDENTITY;
-    int rc = rslrl_linear_forward(1, &p, precision, stream);
+    rslrl_linear_fwd_t p[2] = {};
+    LstmFwdBatch cb{};
+    for (int i = 0; i < n_nets; ++i) {
+      const rslrl_lstm_fwd_t& q = nets[i];
+      p[i].x = q.h_all + t * nH; p[i].w = q.w_hh; p[i].b = nullptr; p[i].y = q.hg;
+      p[i].M = (int)n; p[i].N = 4 * H; p[i].K = H; p[i].ldx = H; p[i].ldy = 4 * H; p[i].act = RSLRL_ACT_IDENTITY;
+      cb.net[i] = LstmFwdArgs{q.xg + t * nG, q.hg, q.b_hh, q.c_all + t * nH, q.gates ? q.gates + t * nG : nullptr,
+                              q.c_all + (t + 1) * nH, q.h_all + (t + 1) * nH};
+    }
+    int rc = rslrl_linear_forward(n_nets, p, precision, stream);
     if (rc != 0) return rc;
-    rc = rslrl_lstm_cell_forward(xg + t * nG, hg, b_hh, c_all + t * nH, gates ? gates + t * nG : nullptr,
-                                 c_all + (t + 1) * nH, h_all + (t + 1) * nH, n, H, stream);
+    rc = launch_cell_forward(cb, n_nets, n, H, (cudaStream_t)stream);
     if (rc != 0) return rc;
   }
   return 0;
 }
 
-// Backward through time: dout [T,n,H] (may be NULL), dhT / dcT gradients of the final state (may be NULL), w_hh_t [H,4H] =
-// W_hh transposed ->
-// dgates [T,n,4H]; dh_scratch / dc_scratch are [2][n,H]; on return slot 0 of each holds d h_0 / d c_0
-// (d h_0 only when need_dh0).
-int rslrl_lstm_layer_backward(const float* dout, const float* dhT, const float* dcT, const float* gates,
-                              const float* c_all, const float* w_hh_t, float* dgates, float* dh_scratch,
-                              float* dc_scratch, int need_dh0, int T, int64_t n, int H, int precision,
-                              rslrl_stream_t stream) {
+int rslrl_lstm_layers_backward(int n_nets, const rslrl_lstm_bwd_t* nets, int need_dh0, int T, int64_t n, int H,
+                               int precision, rslrl_stream_t stream) {
   using namespace rslrl;
-  const char* what = "rslrl_lstm_layer_backward";
-  RSLRL_CHECK_ARG(gates && c_all && w_hh_t && dgates && dh_scratch && dc_scratch && T > 0 && n > 0 && H > 0 && (H % 4) == 0,
-                  what);
+  const char* what = "rslrl_lstm_layers_backward";
+  RSLRL_CHECK_ARG(nets && n_nets >= 1 && n_nets <= 2 && T > 0 && n > 0 && H > 0 && (H % 4) == 0, what);
+  for (int i = 0; i < n_nets; ++i)
+    RSLRL_CHECK_ARG(nets[i].gates && nets[i].c_all && nets[i].w_hh_t && nets[i].dgates && nets[i].dh_scratch &&
+                        nets[i].dc_scratch, what);
   const size_t nH = (size_t)n * H, nG = (size_t)n * 4 * H;
-  const float* dh_rec = dhT;
-  const float* dc = dcT;
+  const float* dh_rec[2] = {nets[0].dhT, n_nets > 1 ? nets[1].dhT : nullptr};
+  const float* dc[2] = {nets[0].dcT, n_nets > 1 ? nets[1].dcT : nullptr};
   for (int t = T - 1; t >= 0; --t) {
-    float* dc_prev = dc_scratch + (size_t)(t & 1) * nH;
-    int rc = rslrl_lstm_cell_backward(dout ? dout + t * nH : nullptr, dh_rec, dc, gates + t * nG, c_all + t * nH,
-                                      c_all + (t + 1) * nH, dgates + t * nG, dc_prev, n, H, stream);
+    LstmBwdBatch cb{};
+    for (int i = 0; i < n_nets; ++i) {
+      const rslrl_lstm_bwd_t& q = nets[i];
+      float* dc_prev = q.dc_scratch + (size_t)(t & 1) * nH;
+      cb.net[i] = LstmBwdArgs{q.dout ? q.dout + t * nH : nullptr, dh_rec[i], dc[i], q.gates + t * nG, q.c_all + t * nH,
+                              q.c_all + (t + 1) * nH, q.dgates + t * nG, dc_prev};
+      dc[i] = dc_prev;
+    }
+    int rc = launch_cell_backward(cb, n_nets, n, H, (cudaStream_t)stream);
     if (rc != 0) return rc;
-    dc = dc_prev;
     if (t > 0 || need_dh0) {
-      // dh_{t-1} = dG_t W_hh, issued as the FORWARD product dG_t (W_hh^T)^T against the transposed copy of W_hh the caller
-      // passes ([H,4H] row-major): a plain K-major GEMM without activation, which the tensor-core forward kernel covers
-      float* dh = dh_scratch + (size_t)(t & 1) * nH;
-      rslrl_linear_fwd_t q{};
-      q.x = dgates + t * nG; q.w = w_hh_t; q.b = nullptr; q.y = dh;
-      q.M = (int)n; q.N = H; q.K = 4 * H; q.ldx = 4 * H; q.ldy = H; q.act = RSLRL_ACT_IDENTITY;
-      rc = rslrl_linear_forward(1, &q, precision, stream);
+      // dh_{t-1} = dG_t W_hh as the FORWARD product dG_t (W_hh^T)^T: a plain K-major GEMM without activation, which the
+      // tensor-core forward kernel covers (the data-gradient kernel is specialised to activation derivatives)
+      rslrl_linear_fwd_t p[2] = {};
+      for (int i = 0; i < n_nets; ++i) {
+        const rslrl_lstm_bwd_t& q = nets[i];
+        float* dh = q.dh_scratch + (size_t)(t & 1) * nH;
+        p[i].x = q.dgates + t * nG; p[i].w = q.w_hh_t; p[i].b = nullptr; p[i].y = dh;
+        p[i].M = (int)n; p[i].N = H; p[i].K = 4 * H; p[i].ldx = 4 * H; p[i].ldy = H; p[i].act = RSLRL_ACT_IDENTITY;
+        dh_rec[i] = dh;
+      }
+      rc = rslrl_linear_forward(n_nets, p, precision, stream);
       if (rc != 0) return rc;
-      dh_rec = dh;
     }
   }
   return 0;

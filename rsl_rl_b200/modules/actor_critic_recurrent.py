@@ -78,6 +78,17 @@ class ActorCriticRecurrent(GaussianHeadMixin, nn.Module):
         x = self.critic_obs_normalizer(self.get_critic_obs(obs))
         return self.critic(self.memory_c(x, masks, hidden_states).squeeze(0))
 
+    def act_evaluate(self, obs, masks=None, hidden_states=(None, None)):
+        """`act(obs, masks, hidden_states[0])` followed by `evaluate(obs, masks, hidden_states[1])` with the two memories
+        advanced together (grouped LSTM launches): returns (actions, values).  Same results, same RNG consumption."""
+        x_a = self.actor_obs_normalizer(self.get_actor_obs(obs))
+        x_c = self.critic_obs_normalizer(self.get_critic_obs(obs))
+        out_a, out_c = Memory.forward_pair(self.memory_a, self.memory_c, x_a, x_c, masks, hidden_states[0],
+                                           hidden_states[1])
+        self.update_distribution(out_a.squeeze(0))
+        actions = self.sample()
+        return actions, self.critic(out_c.squeeze(0))
+
     def get_hidden_states(self):
         return self.memory_a.hidden_states, self.memory_c.hidden_states
 

@@ -10,7 +10,7 @@ from __future__ import annotations
 import torch.nn as nn
 
 from ..utils.utils import unpad_trajectories
-from .lstm import lstm_forward
+from .lstm import lstm_forward, lstm_forward_group
 
 
 class Memory(nn.Module):
@@ -38,6 +38,26 @@ class Memory(nn.Module):
         else:
             out, self.hidden_states = self._rnn(input.unsqueeze(0), self.hidden_states)
         return out
+
+    @staticmethod
+    def forward_pair(mem_a: "Memory", mem_c: "Memory", input_a, input_c, masks=None, hidden_a=None, hidden_c=None):
+        """`mem_a(input_a, masks, hidden_a)` and `mem_c(input_c, masks, hidden_c)` with both LSTMs advanced together
+        (grouped launches) when they are native LSTMs of equal shape on CUDA; otherwise two ordinary calls."""
+        ra, rc = mem_a.rnn, mem_c.rnn
+        same = (mem_a.native and mem_c.native and input_a.is_cuda and input_c.is_cuda
+                and (ra.num_layers, ra.hidden_size, ra.bias) == (rc.num_layers, rc.hidden_size, rc.bias)
+                and input_a.shape[:-1] == input_c.shape[:-1])
+        if not same:
+            return mem_a(input_a, masks, hidden_a), mem_c(input_c, masks, hidden_c)
+        if masks is not None:
+            if hidden_a is None or hidden_c is None:
+                raise ValueError("Hidden states not passed to memory module during policy update")
+            (out_a, _), (out_c, _) = lstm_forward_group([ra, rc], [input_a, input_c], [hidden_a, hidden_c], mem_a.precision)
+            return unpad_trajectories(out_a, masks), unpad_trajectories(out_c, masks)
+        (out_a, mem_a.hidden_states), (out_c, mem_c.hidden_states) = lstm_forward_group(
+            [ra, rc], [input_a.unsqueeze(0), input_c.unsqueeze(0)], [mem_a.hidden_states, mem_c.hidden_states],
+            mem_a.precision)
+        return out_a, out_c
 
     def reset(self, dones=None, hidden_states=None):
         if dones is None:

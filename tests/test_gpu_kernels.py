@@ -707,3 +707,27 @@ def test_native_lstm_matches_torch_lstm(T, n, D, H, L, prec, tol):
         out_i, (hn_i, cn_i) = lstm_forward(rnn, x, None, prec)
         out_z, _ = ref(xr.detach())
     assert rel_err(out_i.cpu().numpy(), out_z.detach().numpy()) < tol
+
+
+def test_native_lstm_group_of_two_matches_separate_calls():
+    """lstm_forward_group (actor and critic memories advanced together: grouped GEMM and cell launches) gives the bits of
+    two separate lstm_forward calls, outputs and gradients."""
+    from rsl_rl_b200.networks.lstm import lstm_forward, lstm_forward_group
+    torch.manual_seed(3)
+    T, n, H = 12, 700, 64
+    ra, rc = torch.nn.LSTM(48, H).to(DEV), torch.nn.LSTM(20, H).to(DEV)
+    xa, xc = torch.randn(T, n, 48, device=DEV), torch.randn(T, n, 20, device=DEV)
+    ha = (torch.randn(1, n, H, device=DEV), torch.randn(1, n, H, device=DEV))
+    hc = (torch.randn(1, n, H, device=DEV), torch.randn(1, n, H, device=DEV))
+    w = torch.randn(T, n, H, device=DEV)
+    (oa, (hna, cna)), (oc, (hnc, cnc)) = lstm_forward_group([ra, rc], [xa, xc], [ha, hc], "fp32")
+    ((oa * w).sum() + (oc * w).sum() * 0.5 + hna.sum() - cnc.sum()).backward()
+    grads = [p.grad.clone() for r in (ra, rc) for p in r.parameters()]
+    for r in (ra, rc):
+        r.zero_grad()
+    oa2, (hna2, cna2) = lstm_forward(ra, xa, ha, "fp32")
+    oc2, (hnc2, cnc2) = lstm_forward(rc, xc, hc, "fp32")
+    ((oa2 * w).sum() + (oc2 * w).sum() * 0.5 + hna2.sum() - cnc2.sum()).backward()
+    assert torch.equal(oa, oa2) and torch.equal(oc, oc2) and torch.equal(hna, hna2) and torch.equal(cnc, cnc2)
+    for g, p in zip(grads, [p for r in (ra, rc) for p in r.parameters()]):
+        assert rel_err(g.cpu().numpy(), p.grad.cpu().numpy()) < 1e-6
