@@ -199,6 +199,16 @@ def require_cuda(*tensors: torch.Tensor):
                                % t.device)
 
 
+def require_device_readable(*tensors: torch.Tensor):
+    """CUDA tensors, or PINNED host tensors (page-locked memory is mapped into the device address space under UVA, so a
+    kernel may read it in place over PCIe/NVLink-C2C: used for the few small per-step env outputs -- rewards, dones,
+    time-outs -- of a host-resident env instead of one cudaMemcpyAsync each)."""
+    for t in tensors:
+        if t is not None and not t.is_cuda and not t.is_pinned():
+            raise RuntimeError("rsl_rl_b200 kernels need CUDA (or pinned host) tensors, got a pageable tensor on %s; "
+                               "there is no CPU path" % t.device)
+
+
 def f32c(t: torch.Tensor) -> torch.Tensor:
     """fp32 + contiguous view of `t` (copies only when needed)."""
     if t.dtype != torch.float32:

@@ -7,10 +7,14 @@ kernels, fused cell kernels, hand-written backward through time) -- `self.rnn` i
 CUDA path; it is called as a module for host tensors (export / inference off the training path) and for GRUs."""
 from __future__ import annotations
 
+import os
+
 import torch.nn as nn
 
 from ..utils.utils import unpad_trajectories
 from .lstm import lstm_forward, lstm_forward_group
+
+_GROUP = os.environ.get("RSLRL_LSTM_GROUP", "1") != "0"   # actor + critic memories in grouped launches (A/B switch)
 
 
 class Memory(nn.Module):
@@ -44,7 +48,7 @@ class Memory(nn.Module):
         """`mem_a(input_a, masks, hidden_a)` and `mem_c(input_c, masks, hidden_c)` with both LSTMs advanced together
         (grouped launches) when they are native LSTMs of equal shape on CUDA; otherwise two ordinary calls."""
         ra, rc = mem_a.rnn, mem_c.rnn
-        same = (mem_a.native and mem_c.native and input_a.is_cuda and input_c.is_cuda
+        same = (_GROUP and mem_a.native and mem_c.native and input_a.is_cuda and input_c.is_cuda
                 and (ra.num_layers, ra.hidden_size, ra.bias) == (rc.num_layers, rc.hidden_size, rc.bias)
                 and input_a.shape[:-1] == input_c.shape[:-1])
         if not same:

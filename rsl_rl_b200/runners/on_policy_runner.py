@@ -119,6 +119,10 @@ class OnPolicyRunner:
             print(f"Synchronizing parameters for rank {self.gpu_global_rank}...")
             self.alg.broadcast_parameters()
 
+        # Host-resident env + fused rollout + no logging: the small per-step outputs (rewards, dones, time-outs) stay in
+        # the env's PINNED buffers and the store kernel reads them in place (one launch instead of three copies + one).
+        zero_copy = (getattr(self.alg, "rollout_fused", False) and not logging and not getattr(self.alg, "rnd", None)
+                     and os.environ.get("RSLRL_ZERO_COPY_STEP", "1") != "0")
         prof = self.profile_phases
         if prof:
             ev = lambda: torch.cuda.Event(enable_timing=True)
@@ -136,7 +140,9 @@ class OnPolicyRunner:
                     obs, rewards, dones, extras = self.env.step(self._actions_for_env(actions))
                     # host-resident envs: pinned buffers are copied asynchronously (stream ordered; the blocking
                     # device->host copy of the next actions is the synchronisation point the env relies on)
-                    obs, rewards, dones = self._to_device(obs), self._to_device(rewards), self._to_device(dones)
+                    obs = self._to_device(obs)
+                    if not (zero_copy and not rewards.is_cuda and rewards.is_pinned() and dones.is_pinned()):
+                        rewards, dones = self._to_device(rewards), self._to_device(dones)
                     self.alg.process_env_step(obs, rewards, dones, extras)
                     if logging:
                         if "episode" in extras:

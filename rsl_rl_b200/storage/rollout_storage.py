@@ -158,14 +158,13 @@ class RolloutStorage:
         dones, dcode = nat.flag_tensor(dones)
         to_ptr, tcode = None, 0
         if time_outs is not None:
-            if time_outs.device != rewards.device:
-                # (pinned host source: asynchronous like the runner's copies of obs / rewards / dones; the next blocking
-                # read-back of the actions is the synchronisation point the env relies on)
-                time_outs = time_outs.to(rewards.device, non_blocking=time_outs.is_pinned())
+            if not time_outs.is_cuda and not time_outs.is_pinned():   # pinned host flags are read in place by the kernel
+                time_outs = time_outs.to(self.device)
             time_outs, tcode = nat.flag_tensor(time_outs)
             to_ptr = time_outs.data_ptr()
         intr_t = None if intrinsic is None else nat.f32c(intrinsic)
-        nat.require_cuda(rewards, dones, intr_t, *keep)
+        nat.require_cuda(intr_t, *keep)
+        nat.require_device_readable(rewards, dones, time_outs)   # device, or pinned host memory read in place
         nat.check(nat.lib().rslrl_store_transition(
             len(self._obs_keys), src_arr, dst_arr, dim_arr, None, None, None, 0, values_ptr, None,
             rewards.data_ptr(), dones.data_ptr(), dcode, to_ptr, tcode, nat.ptr(intr_t), float(gamma), None, None, None,
