@@ -22,7 +22,7 @@
 
 namespace rslrl {
 
-constexpr int kArThreads = 512;
+constexpr int kArThreads = 1024;  // one float4 per thread at the PPO sizes (P ~ 0.4-0.6 M): one NVLink latency per phase
 constexpr int kArMaxBlocks = 148;
 constexpr int kArMaxWorld = 8;
 
@@ -35,7 +35,8 @@ struct ArWorkspace {
 
 struct ArParams {
   const float* peer_grads[kArMaxWorld];  // gradient buffer [P + 4] of every rank (own rank included)
-  unsigned int* peer_flags[kArMaxWorld]; // flag buffer [2][kArMaxBlocks][kArMaxWorld] of every rank
+  unsigned int* peer_flags[kArMaxWorld]; // flag buffer [3][kArMaxBlocks][kArMaxWorld] of every rank
+  float* peer_results[kArMaxWorld];      // two-step mode: reduced-gradient buffer [P] of every rank (else null)
   float* p;
   __half* p16;  // optional fp16 shadow of p (same element offsets), refreshed by the Adam phase
   float* g;  // own gradient buffer (= peer_grads[rank])
@@ -147,14 +148,51 @@ __global__ void __launch_bounds__(kArThreads, 1) allreduce_clip_adam_kernel(cons
   AR_TRACE(1);
   // ---- 1: reduce slice b over the ranks (fixed order), keep it in shared memory, sum of squares
   double acc[1] = {0.0};
-  for (long long i = i0 + tid; i < i1; i += kArThreads) {
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int k = 0; k < W; ++k) {
-      const float4 x = (k == rank) ? *(const float4*)(prm.g + 4 * i) : ld_volatile_f4(prm.peer_grads[k] + 4 * i);
-      s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
+  const bool two_step = W > 1 && prm.peer_results[0] != nullptr;
+  if (!two_step) {
+    // one step: every rank pulls slice b of EVERY peer ((W-1) x slice bytes inbound per rank; best for small worlds)
+    for (long long i = i0 + tid; i < i1; i += kArThreads) {
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < W; ++k) {
+        const float4 x = (k == rank) ? *(const float4*)(prm.g + 4 * i) : ld_volatile_f4(prm.peer_grads[k] + 4 * i);
+        s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
+      }
+      *(float4*)(s_slice + 4 * (i - i0)) = s;
+      acc[0] += (double)s.x * s.x + (double)s.y * s.y + (double)s.z * s.z + (double)s.w * s.w;
     }
-    *(float4*)(s_slice + 4 * (i - i0)) = s;
-    acc[0] += (double)s.x * s.x + (double)s.y * s.y + (double)s.z * s.z + (double)s.w * s.w;
+  } else {
+    // two steps (reduce-scatter + all-gather inside the slice): rank r reduces sub-slice r of slice b over all ranks
+    // (fixed order) and WRITES the sums into every rank's result buffer; after a cross-rank flag barrier every rank
+    // reads the whole reduced slice from its LOCAL result buffer.  Inbound + outbound traffic per rank is
+    // 2 (W-1)/W x slice instead of (W-1) x slice, and all ranks hold bit-identical sums by construction.
+    const long long len = i1 - i0, per_r = (len + W - 1) / W;
+    const long long s0 = i0 + (long long)rank * per_r < i1 ? i0 + (long long)rank * per_r : i1;
+    const long long s1 = s0 + per_r < i1 ? s0 + per_r : i1;
+    for (long long i = s0 + tid; i < s1; i += kArThreads) {
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < W; ++k) {
+        const float4 x = (k == rank) ? *(const float4*)(prm.g + 4 * i) : ld_volatile_f4(prm.peer_grads[k] + 4 * i);
+        s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
+      }
+      for (int k = 0; k < W; ++k) *(float4*)(prm.peer_results[k] + 4 * i) = s;
+    }
+    __threadfence_system();
+    __syncthreads();
+    // B (early): this rank is done reading slice b of its peers' gradients
+    if (tid < W && tid != rank)
+      st_release_sys(prm.peer_flags[tid] + (1 * kArMaxBlocks + b) * kArMaxWorld + rank, stamp);
+    // C: the reduced sub-slices of every rank have landed in this rank's result buffer
+    if (tid < W && tid != rank) {
+      st_release_sys(prm.peer_flags[tid] + (2 * kArMaxBlocks + b) * kArMaxWorld + rank, stamp);
+      wait_flag(prm.peer_flags[rank] + (2 * kArMaxBlocks + b) * kArMaxWorld + tid, stamp, prm.timeout_cycles);
+    }
+    __syncthreads();
+    const float* res = prm.peer_results[rank];
+    for (long long i = i0 + tid; i < i1; i += kArThreads) {
+      const float4 s = ld_volatile_f4(res + 4 * i);
+      *(float4*)(s_slice + 4 * (i - i0)) = s;
+      acc[0] += (double)s.x * s.x + (double)s.y * s.y + (double)s.z * s.z + (double)s.w * s.w;
+    }
   }
   float kl_sum = 0.f;
   if (prm.use_kl && tid == 0) {  // the minibatch KL rides in the tail of the gradient buffer (4 bytes per rank)
@@ -163,7 +201,7 @@ __global__ void __launch_bounds__(kArThreads, 1) allreduce_clip_adam_kernel(cons
   block_sum<1>(acc, s_red);
 
   // ---- B: tell the peers that their slice b has been read (they may clear it)
-  if (W > 1) {
+  if (W > 1 && !two_step) {
     __syncthreads();
     if (tid < W && tid != rank)
       st_release_sys(prm.peer_flags[tid] + (1 * kArMaxBlocks + b) * kArMaxWorld + rank, stamp);
@@ -270,11 +308,12 @@ extern "C" {
 
 int64_t rslrl_allreduce_adam_workspace_bytes(void) { return (int64_t)sizeof(rslrl::ArWorkspace); }
 int64_t rslrl_allreduce_adam_flag_bytes(void) {
-  return (int64_t)(2 * rslrl::kArMaxBlocks * rslrl::kArMaxWorld * sizeof(unsigned int));
+  return (int64_t)(3 * rslrl::kArMaxBlocks * rslrl::kArMaxWorld * sizeof(unsigned int));
 }
 
 int rslrl_allreduce_clip_adam(int world, int rank, const float* const* peer_grads_host,
-                              unsigned int* const* peer_flags_host, float* p, float* m, float* v, int64_t P,
+                              unsigned int* const* peer_flags_host, float* const* peer_results_host, float* p, float* m,
+                              float* v, int64_t P,
                               rslrl_opt_state_t* state, void* workspace, double max_grad_norm, int adaptive,
                               double desired_kl, int round_lr_fp32, int use_kl, double beta1, double beta2, double eps,
                               int zero_grad, void* p16_shadow, rslrl_stream_t stream) {
@@ -291,6 +330,10 @@ int rslrl_allreduce_clip_adam(int world, int rank, const float* const* peer_grad
     if (world > 1) {
       RSLRL_CHECK_ARG(peer_flags_host[k] != nullptr, what);
       prm.peer_flags[k] = peer_flags_host[k];
+      if (peer_results_host != nullptr) {
+        RSLRL_CHECK_ARG(peer_results_host[k] != nullptr && ((uintptr_t)peer_results_host[k] & 15) == 0, what);
+        prm.peer_results[k] = peer_results_host[k];
+      }
     }
   }
   RSLRL_CHECK_ARG((((uintptr_t)p | (uintptr_t)m | (uintptr_t)v) & 15) == 0, what);
