@@ -339,11 +339,16 @@ int rslrl_adam_step(float* p, float* g, float* m, float* v, int64_t P, const rsl
  * peer_results_host (may be NULL): per rank a peer-addressable buffer of P floats.  When given, the reduction runs in two
  * steps inside every slice -- rank r sums sub-slice r over all ranks and writes the result into every rank's buffer,
  * then all ranks read the reduced slice locally -- which moves 2 (W-1)/W x P floats per rank instead of (W-1) x P
- * (worth it from 4 ranks up) and makes the sums bit-identical on all ranks by construction. */
+ * (worth it from 4 ranks up) and makes the sums bit-identical on all ranks by construction.
+ * peer_stage_host (may be NULL): per rank a peer-addressable staging buffer of 2 * world * (P + 4) floats.  When given the
+ * exchange is PUSHED: every rank writes its own gradients (its share of every slice) into the owners' staging buffers
+ * and flags them, so a step costs one NVLink hop instead of the pull protocol's two ("is your backward complete?" +
+ * the read round trip), and nobody reads a peer's gradient buffer any more. */
 int64_t rslrl_allreduce_adam_workspace_bytes(void);
 int64_t rslrl_allreduce_adam_flag_bytes(void);
 int rslrl_allreduce_clip_adam(int world, int rank, const float* const* peer_grads_host,
-                              unsigned int* const* peer_flags_host, float* const* peer_results_host, float* p, float* m, float* v, int64_t P,
+                              unsigned int* const* peer_flags_host, float* const* peer_results_host,
+                              float* const* peer_stage_host, float* p, float* m, float* v, int64_t P,
                               rslrl_opt_state_t* state, void* workspace, double max_grad_norm, int adaptive,
                               double desired_kl, int round_lr_fp32, int use_kl, double beta1, double beta2, double eps,
                               int zero_grad, void* p16_shadow, rslrl_stream_t stream);

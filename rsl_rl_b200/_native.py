@@ -108,7 +108,8 @@ _SIGNATURES = {
                                 c_int, c_void_p]),
     "rslrl_allreduce_adam_workspace_bytes": (c_i64, []),
     "rslrl_allreduce_adam_flag_bytes": (c_i64, []),
-    "rslrl_allreduce_clip_adam": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64,
+    "rslrl_allreduce_clip_adam": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_i64,
                                           c_void_p, c_void_p, c_double, c_int, c_double, c_int, c_int, c_double,
                                           c_double, c_double, c_int, c_void_p, c_void_p]),
     "rslrl_traj_workspace_bytes": (c_i64, [c_int, c_int]),

@@ -123,20 +123,25 @@ class FlatParamGroup:
         torch.cuda.synchronize()
         res = symm_mem.empty(self.numel, dtype=torch.float32, device=self.device)   # reduced gradients (two-step mode)
         res.zero_()
+        world = dist.get_world_size(group)
+        stage = symm_mem.empty(2 * world * (self.numel + ALIGN // 2), dtype=torch.float32, device=self.device)  # push mode
+        stage.zero_()
         torch.cuda.synchronize()
         hg = symm_mem.rendezvous(g, group)
         hf = symm_mem.rendezvous(flags, group)
         hr = symm_mem.rendezvous(res, group)
+        hs = symm_mem.rendezvous(stage, group)
         with torch.no_grad():
             g.copy_(self.grads_ext)
         self.grads_ext = g
         self.grads = g[:self.numel]
         self.kl_slot = g[self.numel:self.numel + 1]
-        self._symm = (hg, hf, hr, flags, res)  # keep the handles (and the mappings) alive
+        self._symm = (hg, hf, hr, hs, flags, res, stage)  # keep the handles (and the mappings) alive
         self.bind()
         torch.cuda.synchronize()
         dist.barrier(group)
-        return [int(p) for p in hg.buffer_ptrs], [int(p) for p in hf.buffer_ptrs], [int(p) for p in hr.buffer_ptrs]
+        return ([int(p) for p in hg.buffer_ptrs], [int(p) for p in hf.buffer_ptrs], [int(p) for p in hr.buffer_ptrs],
+                [int(p) for p in hs.buffer_ptrs])
 
     def zero_grad(self):
         nat.check(nat.lib().rslrl_fill_zero(self.grads_ext.data_ptr(), self.grads_ext.numel() * 4, nat.stream_ptr()))
@@ -202,12 +207,12 @@ class FusedAdam(torch.optim.Adam):
         self._ar_ws = torch.zeros(int(nat.lib().rslrl_allreduce_adam_workspace_bytes()), dtype=torch.uint8,
                                   device=group.device)
         self.peer_world, self.peer_rank = 1, 0
-        self._peer_grads = self._peer_flags = self._peer_results = None
+        self._peer_grads = self._peer_flags = self._peer_results = self._peer_stage = None
         self.one_launch = os.environ.get("RSLRL_ONE_LAUNCH_STEP", "1") != "0"
 
     def enable_peer_allreduce(self, rank: int, world: int, group=None):
         """Gradients move to symmetric memory; from now on fused_step() all-reduces them itself (collective call)."""
-        grads, flags, results = self.group.make_symmetric(group)
+        grads, flags, results, stage = self.group.make_symmetric(group)
         if len(grads) != world:
             raise RuntimeError("symmetric-memory rendezvous returned %d peers for world size %d" % (len(grads), world))
         self.peer_world, self.peer_rank = world, rank
@@ -215,6 +220,8 @@ class FusedAdam(torch.optim.Adam):
         # two-step reduction (reduce-scatter + all-gather inside every slice) from RSLRL_TWO_STEP_MIN_WORLD ranks up
         two_step = world >= int(os.environ.get("RSLRL_TWO_STEP_MIN_WORLD", "4"))
         self._peer_results = nat.void_array(results) if two_step else None
+        # pushed exchange (one NVLink hop per step) unless RSLRL_ALLREDUCE_PUSH=0 (pull protocol of round 1)
+        self._peer_stage = nat.void_array(stage) if os.environ.get("RSLRL_ALLREDUCE_PUSH", "1") != "0" else None
 
     @property
     def peer_allreduce(self) -> bool:
@@ -238,7 +245,8 @@ class FusedAdam(torch.optim.Adam):
             peers = self._peer_grads if self.peer_allreduce else nat.void_array([g.grads_ext.data_ptr()])
             nat.check(L.rslrl_allreduce_clip_adam(
                 self.peer_world, self.peer_rank, peers, self._peer_flags,
-                self._peer_results if self.peer_allreduce else None, g.values.data_ptr(), g.exp_avg.data_ptr(),
+                self._peer_results if self.peer_allreduce else None,
+                self._peer_stage if self.peer_allreduce else None, g.values.data_ptr(), g.exp_avg.data_ptr(),
                 g.exp_avg_sq.data_ptr(), g.numel, self.dev_state.ptr(), self._ar_ws.data_ptr(), float(max_grad_norm),
                 int(adaptive), float(desired_kl or 0.0), int(round_lr_fp32), int(use_kl), beta1, beta2, pg["eps"],
                 int(zero_grad), nat.ptr(g.values16), nat.stream_ptr()))

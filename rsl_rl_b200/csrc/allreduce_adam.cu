@@ -37,6 +37,7 @@ struct ArParams {
   const float* peer_grads[kArMaxWorld];  // gradient buffer [P + 4] of every rank (own rank included)
   unsigned int* peer_flags[kArMaxWorld]; // flag buffer [3][kArMaxBlocks][kArMaxWorld] of every rank
   float* peer_results[kArMaxWorld];      // two-step mode: reduced-gradient buffer [P] of every rank (else null)
+  float* peer_stage[kArMaxWorld];        // push mode: staging buffer [world][P + 4] of every rank (else null)
   float* p;
   __half* p16;  // optional fp16 shadow of p (same element offsets), refreshed by the Adam phase
   float* g;  // own gradient buffer (= peer_grads[rank])
@@ -135,8 +136,39 @@ __global__ void __launch_bounds__(kArThreads, 1) allreduce_clip_adam_kernel(cons
   const long long step_old = prm.state->step;
 
   AR_TRACE(0);
-  // ---- A: every rank's backward is complete
-  if (W > 1) {
+  const bool push = W > 1 && prm.peer_stage[0] != nullptr;
+  const bool two_step = W > 1 && prm.peer_results[0] != nullptr;
+  const long long RS = P + 4;   // row stride of a staging buffer (floats): [parity][src rank][P gradients | KL tail]
+  // (double buffered by launch parity: a rank can start pushing launch n+1 while a peer still reads launch n's copy;
+  // it cannot reach launch n+2 before that peer has entered n+1, i.e. finished reading n)
+  const size_t stage_par = (size_t)(epoch & 1u) * (size_t)W * (size_t)RS;
+  // ---- PUSH mode, step 1: this rank's share of slice b goes to its owner(s) -- no "is your backward complete" round
+  // trip: a rank pushes its own finished gradients and the receiver waits for "data landed" flags (one NVLink hop per
+  // step; the pull protocol below needs two for the same step).  One-hop variant (small worlds): every rank owns
+  // every element.  Two-step variant: rank r owns sub-slice r of slice b.
+  if (push) {
+    const long long len = i1 - i0, per_r = (len + W - 1) / W;
+    for (long long i = i0 + tid; i < i1; i += kArThreads) {
+      const float4 x = *(const float4*)(prm.g + 4 * i);
+      if (two_step) {
+        const int o = (int)((i - i0) / per_r);
+        if (o != rank) *(float4*)(prm.peer_stage[o] + stage_par + (size_t)rank * RS + 4 * i) = x;
+      } else {
+        for (int k = 0; k < W; ++k)
+          if (k != rank) *(float4*)(prm.peer_stage[k] + stage_par + (size_t)rank * RS + 4 * i) = x;
+      }
+    }
+    if (prm.use_kl && tid < W && tid != rank) prm.peer_stage[tid][stage_par + (size_t)rank * RS + P] = prm.g[P];
+    __threadfence_system();
+    __syncthreads();
+    if (tid < W && tid != rank) {
+      st_release_sys(prm.peer_flags[tid] + (0 * kArMaxBlocks + b) * kArMaxWorld + rank, stamp);
+      wait_flag(prm.peer_flags[rank] + (0 * kArMaxBlocks + b) * kArMaxWorld + tid, stamp, prm.timeout_cycles);
+    }
+    __syncthreads();
+  }
+  // ---- A (pull mode): every rank's backward is complete
+  if (W > 1 && !push) {
     if (tid < W && tid != rank) {
       __threadfence_system();
       st_release_sys(prm.peer_flags[tid] + (0 * kArMaxBlocks + b) * kArMaxWorld + rank, stamp);
@@ -148,13 +180,18 @@ __global__ void __launch_bounds__(kArThreads, 1) allreduce_clip_adam_kernel(cons
   AR_TRACE(1);
   // ---- 1: reduce slice b over the ranks (fixed order), keep it in shared memory, sum of squares
   double acc[1] = {0.0};
-  const bool two_step = W > 1 && prm.peer_results[0] != nullptr;
+  const float* const stage = push ? prm.peer_stage[rank] + stage_par : nullptr;   // local staging buffer (written by the peers)
+  // contribution of rank k to element i: local gradients for k == rank, else the pushed copy / the peer's buffer
+  auto contrib = [&](int k, long long i) -> float4 {
+    if (k == rank) return *(const float4*)(prm.g + 4 * i);
+    return push ? ld_volatile_f4(stage + (size_t)k * RS + 4 * i) : ld_volatile_f4(prm.peer_grads[k] + 4 * i);
+  };
   if (!two_step) {
-    // one step: every rank pulls slice b of EVERY peer ((W-1) x slice bytes inbound per rank; best for small worlds)
+    // one step: slice b of EVERY rank is summed here in fixed rank order ((W-1) x slice bytes inbound per rank)
     for (long long i = i0 + tid; i < i1; i += kArThreads) {
       float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int k = 0; k < W; ++k) {
-        const float4 x = (k == rank) ? *(const float4*)(prm.g + 4 * i) : ld_volatile_f4(prm.peer_grads[k] + 4 * i);
+        const float4 x = contrib(k, i);
         s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
       }
       *(float4*)(s_slice + 4 * (i - i0)) = s;
@@ -171,15 +208,15 @@ __global__ void __launch_bounds__(kArThreads, 1) allreduce_clip_adam_kernel(cons
     for (long long i = s0 + tid; i < s1; i += kArThreads) {
       float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int k = 0; k < W; ++k) {
-        const float4 x = (k == rank) ? *(const float4*)(prm.g + 4 * i) : ld_volatile_f4(prm.peer_grads[k] + 4 * i);
+        const float4 x = contrib(k, i);
         s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
       }
       for (int k = 0; k < W; ++k) *(float4*)(prm.peer_results[k] + 4 * i) = s;
     }
     __threadfence_system();
     __syncthreads();
-    // B (early): this rank is done reading slice b of its peers' gradients
-    if (tid < W && tid != rank)
+    // B (early, pull mode): this rank is done reading slice b of its peers' gradients
+    if (!push && tid < W && tid != rank)
       st_release_sys(prm.peer_flags[tid] + (1 * kArMaxBlocks + b) * kArMaxWorld + rank, stamp);
     // C: the reduced sub-slices of every rank have landed in this rank's result buffer
     if (tid < W && tid != rank) {
@@ -196,12 +233,13 @@ __global__ void __launch_bounds__(kArThreads, 1) allreduce_clip_adam_kernel(cons
   }
   float kl_sum = 0.f;
   if (prm.use_kl && tid == 0) {  // the minibatch KL rides in the tail of the gradient buffer (4 bytes per rank)
-    for (int k = 0; k < W; ++k) kl_sum += (k == rank) ? prm.g[P] : ld_volatile_f(prm.peer_grads[k] + P);
+    for (int k = 0; k < W; ++k)
+      kl_sum += (k == rank) ? prm.g[P] : (push ? ld_volatile_f(stage + (size_t)k * RS + P) : ld_volatile_f(prm.peer_grads[k] + P));
   }
   block_sum<1>(acc, s_red);
 
   // ---- B: tell the peers that their slice b has been read (they may clear it)
-  if (W > 1 && !two_step) {
+  if (W > 1 && !two_step && !push) {
     __syncthreads();
     if (tid < W && tid != rank)
       st_release_sys(prm.peer_flags[tid] + (1 * kArMaxBlocks + b) * kArMaxWorld + rank, stamp);
@@ -292,7 +330,7 @@ __global__ void __launch_bounds__(kArThreads, 1) allreduce_clip_adam_kernel(cons
 
   AR_TRACE(4);
   // ---- 4: the peers have read slice b of this rank's gradients -> clear it for the next backward pass
-  if (W > 1) {
+  if (W > 1 && !push) {   // (push mode: nobody reads this rank's gradient buffer remotely)
     if (tid < W && tid != rank) wait_flag(prm.peer_flags[rank] + (1 * kArMaxBlocks + b) * kArMaxWorld + tid, stamp, prm.timeout_cycles);
     __syncthreads();
   }
@@ -312,8 +350,8 @@ int64_t rslrl_allreduce_adam_flag_bytes(void) {
 }
 
 int rslrl_allreduce_clip_adam(int world, int rank, const float* const* peer_grads_host,
-                              unsigned int* const* peer_flags_host, float* const* peer_results_host, float* p, float* m,
-                              float* v, int64_t P,
+                              unsigned int* const* peer_flags_host, float* const* peer_results_host,
+                              float* const* peer_stage_host, float* p, float* m, float* v, int64_t P,
                               rslrl_opt_state_t* state, void* workspace, double max_grad_norm, int adaptive,
                               double desired_kl, int round_lr_fp32, int use_kl, double beta1, double beta2, double eps,
                               int zero_grad, void* p16_shadow, rslrl_stream_t stream) {
@@ -333,6 +371,10 @@ int rslrl_allreduce_clip_adam(int world, int rank, const float* const* peer_grad
       if (peer_results_host != nullptr) {
         RSLRL_CHECK_ARG(peer_results_host[k] != nullptr && ((uintptr_t)peer_results_host[k] & 15) == 0, what);
         prm.peer_results[k] = peer_results_host[k];
+      }
+      if (peer_stage_host != nullptr) {
+        RSLRL_CHECK_ARG(peer_stage_host[k] != nullptr && ((uintptr_t)peer_stage_host[k] & 15) == 0, what);
+        prm.peer_stage[k] = peer_stage_host[k];
       }
     }
   }
