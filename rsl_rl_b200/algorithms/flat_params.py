@@ -103,9 +103,14 @@ class FlatParamGroup:
     def moment_views(self, i: int):
         return self._view(self.exp_avg, i), self._view(self.exp_avg_sq, i)
 
-    def make_symmetric(self, group=None):
-        """Moves the gradient buffer into symmetric (peer-mapped) memory so that every rank can read every other
-        rank's gradients over NVLink (collective call).  Returns (peer gradient pointers, peer flag pointers)."""
+    def make_symmetric(self, group=None, push: bool = True):
+        """Peer-addressable (symmetric) buffers for the in-kernel all-reduce (collective call).  Returns
+        (peer gradient pointers, peer flag pointers, peer result pointers, peer staging pointers).
+
+        push=True (default): the exchange is pushed through a staging buffer, so the gradient buffer itself STAYS in
+        ordinary device memory (the weight-gradient kernels keep reducing into plain cached memory) and only flags,
+        staging and result buffers are symmetric.  push=False (round-1 pull protocol): the gradient buffer moves into
+        symmetric memory so that the peers can read it over NVLink."""
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
 
@@ -114,33 +119,37 @@ class FlatParamGroup:
             symm_mem.enable_symm_mem_for_group(group.group_name)
         except Exception:
             pass
+        world = dist.get_world_size(group)
         n = self.numel + ALIGN
-        g = symm_mem.empty(n, dtype=torch.float32, device=self.device)
-        g.zero_()
         flags = symm_mem.empty(int(nat.lib().rslrl_allreduce_adam_flag_bytes()) // 4, dtype=torch.int32,
                                device=self.device)
         flags.zero_()
-        torch.cuda.synchronize()
         res = symm_mem.empty(self.numel, dtype=torch.float32, device=self.device)   # reduced gradients (two-step mode)
         res.zero_()
-        world = dist.get_world_size(group)
-        stage = symm_mem.empty(2 * world * (self.numel + ALIGN // 2), dtype=torch.float32, device=self.device)  # push mode
+        stage = symm_mem.empty(2 * world * (self.numel + ALIGN // 2), dtype=torch.float32, device=self.device)
         stage.zero_()
+        g = None
+        if not push:
+            g = symm_mem.empty(n, dtype=torch.float32, device=self.device)
+            g.zero_()
         torch.cuda.synchronize()
-        hg = symm_mem.rendezvous(g, group)
         hf = symm_mem.rendezvous(flags, group)
         hr = symm_mem.rendezvous(res, group)
         hs = symm_mem.rendezvous(stage, group)
-        with torch.no_grad():
-            g.copy_(self.grads_ext)
-        self.grads_ext = g
-        self.grads = g[:self.numel]
-        self.kl_slot = g[self.numel:self.numel + 1]
-        self._symm = (hg, hf, hr, hs, flags, res, stage)  # keep the handles (and the mappings) alive
-        self.bind()
+        hg = None
+        if not push:
+            hg = symm_mem.rendezvous(g, group)
+            with torch.no_grad():
+                g.copy_(self.grads_ext)
+            self.grads_ext = g
+            self.grads = g[:self.numel]
+            self.kl_slot = g[self.numel:self.numel + 1]
+            self.bind()
+        self._symm = (hg, hf, hr, hs, flags, res, stage, g)  # keep the handles (and the mappings) alive
         torch.cuda.synchronize()
         dist.barrier(group)
-        return ([int(p) for p in hg.buffer_ptrs], [int(p) for p in hf.buffer_ptrs], [int(p) for p in hr.buffer_ptrs],
+        grads = [int(p) for p in hg.buffer_ptrs] if hg is not None else [self.grads_ext.data_ptr()] * world
+        return (grads, [int(p) for p in hf.buffer_ptrs], [int(p) for p in hr.buffer_ptrs],
                 [int(p) for p in hs.buffer_ptrs])
 
     def zero_grad(self):
@@ -212,7 +221,8 @@ class FusedAdam(torch.optim.Adam):
 
     def enable_peer_allreduce(self, rank: int, world: int, group=None):
         """Gradients move to symmetric memory; from now on fused_step() all-reduces them itself (collective call)."""
-        grads, flags, results, stage = self.group.make_symmetric(group)
+        push = os.environ.get("RSLRL_ALLREDUCE_PUSH", "1") != "0"   # 0: pull protocol of round 1
+        grads, flags, results, stage = self.group.make_symmetric(group, push=push)
         if len(grads) != world:
             raise RuntimeError("symmetric-memory rendezvous returned %d peers for world size %d" % (len(grads), world))
         self.peer_world, self.peer_rank = world, rank
@@ -221,7 +231,7 @@ class FusedAdam(torch.optim.Adam):
         two_step = world >= int(os.environ.get("RSLRL_TWO_STEP_MIN_WORLD", "4"))
         self._peer_results = nat.void_array(results) if two_step else None
         # pushed exchange (one NVLink hop per step) unless RSLRL_ALLREDUCE_PUSH=0 (pull protocol of round 1)
-        self._peer_stage = nat.void_array(stage) if os.environ.get("RSLRL_ALLREDUCE_PUSH", "1") != "0" else None
+        self._peer_stage = nat.void_array(stage) if push else None
 
     @property
     def peer_allreduce(self) -> bool:
