@@ -349,7 +349,7 @@ def time_hbm_kernels(device, N: int, group_dims: dict, precision: str, peak_gbs:
             s["dmu"].data_ptr(), A, s["dv"].data_ptr(), 4, dstd.data_ptr(), None, None, kl.data_ptr(), sums.data_ptr(),
             ws.data_ptr(), mb, mb, A, 0.2, 1.0, 0.01, 1,
             s["dmu16"].data_ptr() if f16 else None, 16 if f16 else 0, s["dv16"].data_ptr() if f16 else None,
-            8 if f16 else 0, float(mb), None, nat.stream_ptr()))
+            8 if f16 else 0, float(mb), None, None, nat.stream_ptr()))
 
     us = _rotating_time(loss_call, n_l)
     out["loss"] = entry(loss_bytes, us, n_l, "PPO objective forward + backward of one minibatch"

@@ -278,6 +278,18 @@ int rslrl_empirical_normalize(const float* x, int64_t ldx, int64_t N, int D, con
  *              rslrl_linear_bwd_weight_t.scale_dev of the same minibatch), [2] S of the next launch (derived from the
  *              largest |gradient| this launch saw, so that S*max sits 16x below fp16's limit), [3] scratch,
  *              [4] uint32 count of launches whose scaled gradients saturated fp16 (the caller reports it) */
+/* Optional fused DATA gradient of the two output layers (RSLRL_PREC_FP16 chain, A % 4 == 0, A <= 16, rows <= 148 * 1024):
+ * with dz_actor != NULL the loss kernel also writes, as fp16 scaled like dmu16,
+ *   dz_actor [rows,K3] = (dL/dmu W_actor) * act'(h_actor),  dz_critic [rows,K3] = (dL/dV W_critic) * act'(h_critic)
+ * i.e. the gradient at the output of the last hidden layer (what rslrl_linear_backward_data on the K = A / K = 1 output
+ * layers produced).  w_* are the fp32 output-layer weights [A,K3] / [1,K3], h_* the saved fp16 activations (row stride
+ * ldh, as dz_*), K3 % 32 == 0, K3 <= 128, `act` the hidden activation code. */
+typedef struct {
+  const float* w_actor; const float* w_critic;
+  const void* h_actor; const void* h_critic;
+  void* dz_actor; void* dz_critic;
+  int K3, ldh, act;
+} rslrl_loss_head_t;
 int64_t rslrl_loss_workspace_bytes(void);
 int rslrl_ppo_loss_fwd_bwd(const float* mu, const float* std_param, int std_type, const float* value,
                            const float* actions, const float* old_logp, const float* advantages,
@@ -288,7 +300,7 @@ int rslrl_ppo_loss_fwd_bwd(const float* mu, const float* std_param, int std_type
                            int64_t mb_orig, int A, double clip_param, double value_loss_coef,
                            double entropy_coef, int use_clipped_value_loss, void* dmu16, int dmu16_stride,
                            void* dvalue16, int dvalue16_stride, double grad_scale16, float* scale_state,
-                           rslrl_stream_t stream);
+                           const rslrl_loss_head_t* head_host, rslrl_stream_t stream);
 
 /* sum and sum of squares of x[0..n) into out[2] (double, overwritten): statistics for
  * ppo.py:221-223 per-minibatch advantage normalisation. */

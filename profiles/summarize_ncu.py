@@ -53,5 +53,30 @@ def report(path, pattern=None):
                 print(f"   {k:85s} {r[hdr.index(k)]} {units[hdr.index(k)]}")
 
 
+def traffic(path, key, pattern="mlp3_forward|tc_gemm", out="profiles/dense_traffic.json"):
+    """DRAM bytes (read + write) of the captured dense launches of ONE minibatch -> profiles/dense_traffic.json[key]
+    (read by bench.py for roofline.traffic).  usage: traffic <file.ncu-rep> <config>_<precision> [regex] [out.json]"""
+    import json
+    import os
+    txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(txt.splitlines()))
+    hdr, units = rows[0], rows[1]
+    ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    total, n, per = 0.0, 0, []
+    for r in rows[2:]:
+        if not re.search(pattern, r[ki]):
+            continue
+        b = float(r[ri].replace(",", "")) * scale[units[ri]] + float(r[wi].replace(",", "")) * scale[units[wi]]
+        total += b
+        n += 1
+        per.append((re.sub(r"\(.*", "", r[ki])[-48:], round(b / 1e6, 2)))
+    data = json.load(open(out)) if os.path.exists(out) else {}
+    data[key] = dict(bytes_per_minibatch=total, launches_per_minibatch=n, per_launch_mb=per,
+                     source=f"ncu --set full, {os.path.basename(path)}")
+    json.dump(data, open(out, "w"), indent=1)
+    print(key, f"{total / 1e6:.1f} MB over {n} launches", per)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "report": report}[sys.argv[1]](*sys.argv[2:])
+    {"launches": launches, "report": report, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])

@@ -67,6 +67,11 @@ class LstmBwd(C.Structure):
                                         "dc_scratch")]
 
 
+class LossHead(C.Structure):
+    _fields_ = [("w_actor", c_void_p), ("w_critic", c_void_p), ("h_actor", c_void_p), ("h_critic", c_void_p),
+                ("dz_actor", c_void_p), ("dz_critic", c_void_p), ("K3", c_int), ("ldh", c_int), ("act", c_int)]
+
+
 class OptState(C.Structure):
     _fields_ = [("lr", c_double), ("clip_scale", c_double), ("total_norm", c_double), ("step_size", c_double),
                 ("bc2_sqrt", c_double), ("kl_mean", c_double), ("step", C.c_longlong), ("pad_", C.c_longlong)]
@@ -139,7 +144,7 @@ _SIGNATURES["rslrl_ppo_loss_fwd_bwd"] = (c_int, [
     c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,  # dmu, dmu_stride, dvalue, dvalue_stride, dstd, db_mu, db_value
     c_void_p, c_void_p, c_void_p,                   # kl_out, loss_sums, workspace
     c_i64, c_i64, c_int, c_double, c_double, c_double, c_int,
-    c_void_p, c_int, c_void_p, c_int, c_double, c_void_p, c_void_p])  # dmu16, stride, dvalue16, stride, grad_scale16, scale_state, stream
+    c_void_p, c_int, c_void_p, c_int, c_double, c_void_p, c_void_p, c_void_p])  # dmu16, stride, dvalue16, stride, grad_scale16, scale_state, head, stream
 
 _lib = None
 

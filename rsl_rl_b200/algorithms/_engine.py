@@ -135,6 +135,12 @@ class FeedForwardEngine:
         self.head16 = self.f16 and self.A % 4 == 0 and os.environ.get("RSLRL_HEAD16", "1") != "0"
         self.scale_state = None
         self._scale_calibrated = False
+        self._head_struct = None
+        # output-layer data gradient fused into the loss kernel (same hidden width and activation in both nets)
+        self.fused_head_dgrad = (self.head16 and self.actor.dims[-2] == self.critic.dims[-2]
+                                 and self.actor.dims[-2] % 32 == 0 and self.actor.dims[-2] <= 128
+                                 and self.actor.acts[-2] == self.critic.acts[-2]
+                                 and os.environ.get("RSLRL_FUSED_HEAD_DGRAD", "1") != "0")
         if self.head16:
             f16 = dict(dtype=torch.float16, device=self.device)
             self.dmu16 = torch.zeros(R, (self.A + 7) // 8 * 8, **f16)[:, :self.A]
@@ -395,7 +401,8 @@ class FeedForwardEngine:
                 lin, l = net.layers[-1], net.L - 1
                 wprobs.append((dy16, hs[l - 1][:M], lin.weight.grad, lin.bias.grad, inv_s, inv_dev))
                 dprobs.append((dy16, self.group.shadow16(lin.weight), hs[l - 1][:M], dz(net, gbuf, l), net.acts[l - 1]))
-            linear_backward_data(dprobs, prec)
+            if not (self.fused_head_dgrad and M <= 148 * 1024):   # (else the loss kernel already wrote both dZ3)
+                linear_backward_data(dprobs, prec)
         else:
             for net, hs, gbuf, _, d_out in nets:
                 lin, l = net.layers[-1], net.L - 1
@@ -415,6 +422,20 @@ class FeedForwardEngine:
                 linear_backward_data(dprobs, prec)
         wprobs.sort(key=lambda p: -(p[2].shape[0] * p[2].shape[1]))   # heaviest tiles first in the round-robin schedule
         linear_backward_weight(wprobs, prec)
+
+    def _loss_head(self, rows: int):
+        """rslrl_loss_head_t for the loss launch: the data gradient of the two output layers fused into the loss kernel
+        (fp16 chain with fp16 output-gradient copies, four-threads-per-row kernel); None otherwise."""
+        if not self.fused_head_dgrad or rows > 148 * 1024:
+            return None
+        if self._head_struct is None:
+            la, lc = self.actor.layers[-1], self.critic.layers[-1]
+            K3 = self.actor.dims[-2]
+            h = nat.LossHead(la.weight.data_ptr(), lc.weight.data_ptr(), self.h_a[-1].data_ptr(), self.h_c[-1].data_ptr(),
+                             self.g_a[-1].data_ptr(), self.g_c[-1].data_ptr(), K3, K3, self.actor.acts[-2])
+            import ctypes
+            self._head_struct = (h, ctypes.byref(h))
+        return self._head_struct[1]
 
     def gaussian_head(self, mu, z, actions_out, logp_out, sigma_out):
         nat.check(nat.lib().rslrl_gaussian_act(mu.data_ptr(), self.std_param.data_ptr(), self.std_type, z.data_ptr(),
@@ -440,7 +461,7 @@ class FeedForwardEngine:
                 int(hp["use_clipped_value_loss"]),
                 self.dmu16.data_ptr() if self.head16 else None, self.dmu16.stride(0) if self.head16 else 0,
                 self.dvalue16.data_ptr() if self.head16 else None, self.dvalue16.stride(0) if self.head16 else 0,
-                self.grad_scale, nat.ptr(self.scale_state), nat.stream_ptr()))
+                self.grad_scale, nat.ptr(self.scale_state), self._loss_head(rows), nat.stream_ptr()))
 
         if self.scale_state is not None and not self._scale_calibrated and not torch.cuda.is_current_stream_capturing():
             # The very first minibatch of a run: one extra launch whose only lasting effect is scale_state[2] -- the

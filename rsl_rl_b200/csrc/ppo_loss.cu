@@ -331,6 +331,22 @@ ppo_loss_kernel(const float* __restrict__ mu, const float* __restrict__ std_para
 // scheduler with a ~2 800-instruction dependent chain each; here a row's chain is ~4x shorter and there are 4x more
 // warps to hide its latencies.  Row sums (log-prob) are quad shuffles, the per-action column sums (dL/dsigma) are
 // strided warp shuffles; everything else is identical, including the tie rules and the last-block publish.
+// Optional fused data gradient of the two OUTPUT layers (fp16-storage path): with `head.dz_a != nullptr` the kernel also
+// writes  dZ3 = S * (dL/dmu W4_actor) * act'(H3_actor)  and  S * (dL/dV W4_critic) * act'(H3_critic)  as fp16 -- the
+// gradients at the output of the last hidden layer, i.e. what a separate K = 12 / K = 1 tensor-core launch produced
+// before (12 us per minibatch at 4 % tensor activity, for 25 MB of traffic).  Each thread of a quad owns a quarter of the
+// hidden width; the 12 + 1 output gradients of the row are exchanged with quad shuffles, the weights sit in shared memory.
+struct LossHead {
+  const float* w_a;    // [A, K3] actor output-layer weight (fp32 master)
+  const float* w_c;    // [1, K3] critic output-layer weight
+  const __half* h_a;   // [rows, K3] saved activations of the last hidden layer (row stride ldh)
+  const __half* h_c;
+  __half* dz_a;        // [rows, K3] outputs (row stride ldh)
+  __half* dz_c;
+  int K3, ldh, act;
+};
+constexpr int kHeadMaxK3 = 128;
+
 constexpr int kQuadThreads = 256;
 __global__ void __launch_bounds__(kQuadThreads)
 ppo_loss_quad_kernel(const float* __restrict__ mu, const float* __restrict__ std_param, int std_type,
@@ -342,10 +358,17 @@ ppo_loss_quad_kernel(const float* __restrict__ mu, const float* __restrict__ std
                      float* __restrict__ dvalue, int dvalue_stride, float* dstd, float* db_mu, float* db_value,
                      float* kl_out, double* loss_sums, LossWorkspace* ws, long long rows, long long mb_orig,
                      int A, float clip, float c_v, float c_e, int use_clipped, __half* __restrict__ dmu16,
-                     int dmu16_stride, __half* __restrict__ dvalue16, int dvalue16_stride, float scale16_arg, float* scale_state) {
+                     int dmu16_stride, __half* __restrict__ dvalue16, int dvalue16_stride, float scale16_arg,
+                     float* scale_state, const LossHead head) {
   pdl_trigger();
   pdl_wait();
   RSLRL_LOSS_SCALE_PROLOGUE
+  __shared__ __align__(16) float s_wa[16 * kHeadMaxK3];   // actor output-layer weight (A <= 16 rows)
+  __shared__ __align__(16) float s_wc[kHeadMaxK3];
+  if (head.dz_a != nullptr) {
+    for (int t = threadIdx.x; t < A * head.K3; t += kQuadThreads) s_wa[t] = __ldg(head.w_a + t);
+    for (int t = threadIdx.x; t < head.K3; t += kQuadThreads) s_wc[t] = __ldg(head.w_c + t);
+  }
   __shared__ float s_sigma[kMaxActions], s_logs[kMaxActions], s_2var[kMaxActions];
   __shared__ double s_red[4 * 32];
   __shared__ float s_dstd[kMaxActions], s_dbmu[kMaxActions];
@@ -461,6 +484,52 @@ ppo_loss_quad_kernel(const float* __restrict__ mu, const float* __restrict__ std
         w.x = *(const unsigned int*)&lo2;
         w.y = *(const unsigned int*)&hi2;
         *(uint2*)(dmu16 + i * dmu16_stride + c) = w;
+      }
+    }
+    if (head.dz_a != nullptr) {   // uniform branch: fused data gradient of the two output layers
+      // all dL/dmu of the row (this quad's 4 x 4 values) and its dL/dV (held by the quad's lead thread)
+      float dm[16];
+      const int qbase = lane & ~3;
+#pragma unroll
+      for (int src = 0; src < 4; ++src)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dm[4 * src + q] = __shfl_sync(0xffffffffu, mine ? o[q] : 0.f, qbase + src);
+      const float dvr = __shfl_sync(0xffffffffu, dv_sum, qbase);
+      if (valid) {
+        const int cols = head.K3 >> 2, c0 = qd * cols;          // this thread's quarter of the hidden width
+        const __half* ha = head.h_a + i * head.ldh + c0;
+        const __half* hc = head.h_c + i * head.ldh + c0;
+        __half* za = head.dz_a + i * head.ldh + c0;
+        __half* zc = head.dz_c + i * head.ldh + c0;
+        for (int cc = 0; cc < cols; cc += 8) {                   // 8 hidden units (16 bytes of fp16) at a time
+          float ga[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int a = 0; a < 16; ++a) {   // (unrolled with a guard: dm[] stays in registers)
+            if (a >= A) break;
+            const float4 w0 = *(const float4*)(s_wa + a * head.K3 + c0 + cc);
+            const float4 w1 = *(const float4*)(s_wa + a * head.K3 + c0 + cc + 4);
+            ga[0] += dm[a] * w0.x; ga[1] += dm[a] * w0.y; ga[2] += dm[a] * w0.z; ga[3] += dm[a] * w0.w;
+            ga[4] += dm[a] * w1.x; ga[5] += dm[a] * w1.y; ga[6] += dm[a] * w1.z; ga[7] += dm[a] * w1.w;
+          }
+          const float4 v0 = *(const float4*)(s_wc + c0 + cc), v1 = *(const float4*)(s_wc + c0 + cc + 4);
+          const float gc[8] = {dvr * v0.x, dvr * v0.y, dvr * v0.z, dvr * v0.w, dvr * v1.x, dvr * v1.y, dvr * v1.z, dvr * v1.w};
+          const uint4 pa = *(const uint4*)(ha + cc), pc = *(const uint4*)(hc + cc);
+          const __half2* ha2 = (const __half2*)&pa;
+          const __half2* hc2 = (const __half2*)&pc;
+          uint4 oa, oc;
+          __half2* oa2 = (__half2*)&oa;
+          __half2* oc2 = (__half2*)&oc;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float2 fa = __half22float2(ha2[u]), fc = __half22float2(hc2[u]);
+            oa2[u] = __floats2half2_rn(sat16(ga[2 * u] * act_grad_from_output(head.act, fa.x) * scale16),
+                                       sat16(ga[2 * u + 1] * act_grad_from_output(head.act, fa.y) * scale16));
+            oc2[u] = __floats2half2_rn(sat16(gc[2 * u] * act_grad_from_output(head.act, fc.x) * scale16),
+                                       sat16(gc[2 * u + 1] * act_grad_from_output(head.act, fc.y) * scale16));
+          }
+          *(uint4*)(za + cc) = oa;
+          *(uint4*)(zc + cc) = oc;
+        }
       }
     }
 #pragma unroll
@@ -585,7 +654,7 @@ int rslrl_ppo_loss_fwd_bwd(const float* mu, const float* std_param, int std_type
                            int64_t mb_orig, int A, double clip_param, double value_loss_coef,
                            double entropy_coef, int use_clipped_value_loss, void* dmu16, int dmu16_stride,
                            void* dvalue16, int dvalue16_stride, double grad_scale16, float* scale_state,
-                           rslrl_stream_t stream) {
+                           const rslrl_loss_head_t* head_host, rslrl_stream_t stream) {
   using namespace rslrl;
   const char* what = "rslrl_ppo_loss_fwd_bwd";
   RSLRL_CHECK_ARG(mu && std_param && value && actions && old_logp && advantages && returns && old_values, what);
@@ -600,6 +669,20 @@ int rslrl_ppo_loss_fwd_bwd(const float* mu, const float* std_param, int std_type
   RSLRL_CHECK_ARG(dmu16 == nullptr || (dmu16_stride % 4 == 0 && ((uintptr_t)dmu16 & 7) == 0), what);
   // four threads per row while a thread per row could not fill the machine (measured at 393 216 rows: 58 us for the
   // row-per-thread kernel, 80 us for this one); beyond that the row-per-thread kernel
+  LossHead head{};
+  if (head_host != nullptr && head_host->dz_actor != nullptr) {
+    const rslrl_loss_head_t& h = *head_host;
+    RSLRL_CHECK_ARG(h.w_actor && h.w_critic && h.h_actor && h.h_critic && h.dz_actor && h.dz_critic, what);
+    RSLRL_CHECK_ARG(h.K3 > 0 && h.K3 <= kHeadMaxK3 && (h.K3 % 32) == 0 && h.ldh >= h.K3 && (h.ldh % 8) == 0, what);
+    RSLRL_CHECK_ARG((((uintptr_t)h.h_actor | (uintptr_t)h.h_critic | (uintptr_t)h.dz_actor | (uintptr_t)h.dz_critic) & 15) == 0, what);
+    if (!(vec && A <= 16 && quad_ok && rows <= (long long)kNumSMs * 1024)) {
+      set_error("%s: the fused output-layer data gradient needs the four-threads-per-row kernel (A %% 4 == 0, A <= 16, "
+                "rows <= %d)", what, kNumSMs * 1024);
+      return 4;
+    }
+    head.w_a = h.w_actor; head.w_c = h.w_critic; head.h_a = (const __half*)h.h_actor; head.h_c = (const __half*)h.h_critic;
+    head.dz_a = (__half*)h.dz_actor; head.dz_c = (__half*)h.dz_critic; head.K3 = h.K3; head.ldh = h.ldh; head.act = h.act;
+  }
   if (vec && A <= 16 && quad_ok && rows <= (long long)kNumSMs * 1024) {
     const int qblocks = (int)((rows + kQuadThreads / 4 - 1) / (kQuadThreads / 4));
     launch_chain_kernel(
@@ -607,7 +690,7 @@ int rslrl_ppo_loss_fwd_bwd(const float* mu, const float* std_param, int std_type
         actions, old_logp, advantages, returns, old_values, old_mu, old_sigma, adv_stats, dmu, dmu_stride, dvalue,
         dvalue_stride, dstd, db_mu, db_value, kl_out, loss_sums, (LossWorkspace*)workspace, (long long)rows,
         (long long)mb_orig, A, (float)clip_param, (float)value_loss_coef, (float)entropy_coef, use_clipped_value_loss,
-        (__half*)dmu16, dmu16_stride, (__half*)dvalue16, dvalue16_stride, (float)grad_scale16, scale_state);
+        (__half*)dmu16, dmu16_stride, (__half*)dvalue16, dvalue16_stride, (float)grad_scale16, scale_state, head);
     return finish_launch(what);
   }
   if ((dmu16 != nullptr || dvalue16 != nullptr) && !vec) {

@@ -295,6 +295,21 @@ def _run_loss(mu, std_param, std_type, value, actions, old_logp, adv, ret, old_v
     S16 = 4096.0
     dmu16 = torch.zeros(rows, (A + 7) // 8 * 8, device=DEV, dtype=torch.float16)
     dv16 = torch.zeros(rows, 8, device=DEV, dtype=torch.float16)
+    # optional fused data gradient of the two output layers (same kernel): dZ3 = S * (dY W4) * ELU'(H3) as fp16
+    head, head_keep = None, None
+    if f16out and rows <= 148 * 1024:
+        import ctypes
+        K3 = 128
+        g = torch.Generator(device=DEV).manual_seed(rows)
+        h_a = torch.nn.functional.elu(torch.randn(rows, K3, device=DEV, generator=g)).half()
+        h_c = torch.nn.functional.elu(torch.randn(rows, K3, device=DEV, generator=g)).half()
+        w_a = torch.randn(A, K3, device=DEV, generator=g) / K3 ** 0.5
+        w_c = torch.randn(1, K3, device=DEV, generator=g) / K3 ** 0.5
+        dz_a = torch.full((rows, K3), float("nan"), device=DEV, dtype=torch.float16)
+        dz_c = torch.full((rows, K3), float("nan"), device=DEV, dtype=torch.float16)
+        hs = nat.LossHead(w_a.data_ptr(), w_c.data_ptr(), h_a.data_ptr(), h_c.data_ptr(), dz_a.data_ptr(), dz_c.data_ptr(),
+                          K3, K3, nat.ACT_CODES["elu"])
+        head, head_keep = ctypes.byref(hs), (hs, h_a, h_c, w_a, w_c, dz_a, dz_c)
     for _ in range(2):  # twice: the workspace must clean itself up
         dstd.zero_(); sums.zero_(); db_mu.zero_(); db_v.zero_()
         nat.check(nat.lib().rslrl_ppo_loss_fwd_bwd(
@@ -303,12 +318,19 @@ def _run_loss(mu, std_param, std_type, value, actions, old_logp, adv, ret, old_v
             d["old_sigma"].data_ptr(), nat.ptr(stats), dmu.data_ptr(), A4, dv.data_ptr(), 4, dstd.data_ptr(),
             db_mu.data_ptr(), db_v.data_ptr(), kl.data_ptr(), sums.data_ptr(), ws.data_ptr(), rows, mb_orig, A, 0.2, 1.0,
             0.01, int(clipped), dmu16.data_ptr() if f16out else None, dmu16.stride(0), dv16.data_ptr() if f16out else None,
-            dv16.stride(0), S16, None, nat.stream_ptr()))
+            dv16.stride(0), S16, None, head, nat.stream_ptr()))
     torch.cuda.synchronize()
     if f16out:
         sat = lambda t: (t * S16).clamp(-65504.0, 65504.0).half()   # saturating conversion (never inf)
         assert torch.equal(dmu16[:, :A], sat(dmu)) and torch.equal(dv16[:, 0], sat(dv))
         assert float(dmu16[:, A:].abs().sum()) == 0.0 and float(dv16[:, 1:].abs().sum()) == 0.0
+    if head is not None:
+        _, h_a, h_c, w_a, w_c, dz_a, dz_c = head_keep
+        egrad = lambda h: torch.where(h > 0, torch.ones_like(h), h + 1.0)
+        ref_a = (dmu.double() @ w_a.double()) * egrad(h_a.double()) * S16
+        ref_c = (dv.double()[:, None] * w_c.double()) * egrad(h_c.double()) * S16
+        assert rel_err(dz_a.double().clamp(-65504, 65504).cpu().numpy(), ref_a.clamp(-65504, 65504).cpu().numpy()) < 1e-3
+        assert rel_err(dz_c.double().clamp(-65504, 65504).cpu().numpy(), ref_c.clamp(-65504, 65504).cpu().numpy()) < 1e-3
     # the fused bias gradients of the two output layers are the column sums of dmu / dvalue
     assert rel_err(db_mu.cpu().numpy(), dmu.double().sum(0).cpu().numpy()) < 1e-5
     assert abs(float(db_v) - float(dv.double().sum())) < 1e-5 * max(1e-6, float(dv.double().abs().sum()))
