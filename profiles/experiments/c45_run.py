@@ -76,3 +76,16 @@ if os.environ.get("RSLRL_HOST_PROFILE") == "1":   # where the host time of one i
     s = io.StringIO()
     pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(30)
     print(s.getvalue()[:7000])
+if os.environ.get("RSLRL_KERNEL_TABLE") == "1":   # device-time table of one iteration (CUPTI through torch.profiler)
+    from torch.profiler import profile, ProfilerActivity
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        with contextlib.redirect_stdout(io.StringIO()):
+            runner.learn(1)
+        torch.cuda.synchronize()
+    rows = [e for e in prof.key_averages() if e.device_time_total > 0 and e.device_type.name == "CUDA"]
+    rows.sort(key=lambda e: -e.device_time_total)
+    tot = sum(e.device_time_total for e in rows)
+    print(f"kernel table of one iteration: {tot / 1e3:.2f} ms of device time, {sum(e.count for e in rows)} launches")
+    for e in rows[:40]:
+        print(f"{100 * e.device_time_total / tot:6.2f}%  {e.device_time_total / 1e3:9.3f} ms  n={e.count:5d}  "
+              f"mean {e.device_time_total / e.count:8.2f} us  {e.key[:110]}")

@@ -231,6 +231,16 @@ __global__ void __launch_bounds__(kArThreads, 1) allreduce_clip_adam_kernel(cons
       acc[0] += (double)s.x * s.x + (double)s.y * s.y + (double)s.z * s.z + (double)s.w * s.w;
     }
   }
+  // Adam operands of this thread's first (at the PPO sizes: only) element: fetched BEFORE the grid barrier, so that the
+  // barrier wait hides their DRAM latency and the phase after it is arithmetic + stores
+  const long long ipre = i0 + tid;
+  const bool has_pre = ipre < i1;
+  float4 pre_p = make_float4(0.f, 0.f, 0.f, 0.f), pre_m = pre_p, pre_v = pre_p;
+  if (has_pre) {
+    pre_p = ((const float4*)prm.p)[ipre];
+    pre_m = ((const float4*)prm.m)[ipre];
+    pre_v = ((const float4*)prm.v)[ipre];
+  }
   float kl_sum = 0.f;
   if (prm.use_kl && tid == 0) {  // the minibatch KL rides in the tail of the gradient buffer (4 bytes per rank)
     for (int k = 0; k < W; ++k)
@@ -247,10 +257,14 @@ __global__ void __launch_bounds__(kArThreads, 1) allreduce_clip_adam_kernel(cons
 
   AR_TRACE(2);
   // ---- 2: grid barrier, then norm / clip / lr / bias corrections (redundantly per block, deterministic order)
+  // Adam bias corrections of step t (fp64 pow): computed while the other blocks arrive
+  double bc1 = 1.0, bc2 = 1.0;
   if (tid == 0) {
     ws->partial[b] = acc[0];
     __threadfence();
     atomicAdd(&ws->arrivals, 1ull);
+    bc1 = 1.0 - pow(prm.beta1, (double)(step_old + 1));
+    bc2 = 1.0 - pow(prm.beta2, (double)(step_old + 1));
     const unsigned long long target = (unsigned long long)stamp * (unsigned long long)G;
     const long long t0 = clock64();
     while (ld_acquire_gpu(&ws->arrivals) < target) {
@@ -282,8 +296,6 @@ __global__ void __launch_bounds__(kArThreads, 1) allreduce_clip_adam_kernel(cons
         if (prm.round_lr_fp32) lr = (double)(float)lr;
       }
       const long long t = step_old + 1;
-      const double bc1 = 1.0 - pow(prm.beta1, (double)t);
-      const double bc2 = 1.0 - pow(prm.beta2, (double)t);
       s_scal[0] = coef / w;
       s_scal[1] = lr / bc1;
       s_scal[2] = sqrt(bc2);
@@ -309,7 +321,9 @@ __global__ void __launch_bounds__(kArThreads, 1) allreduce_clip_adam_kernel(cons
     const float w1 = (float)(1.0 - prm.beta1), b2 = (float)prm.beta2, w2 = (float)(1.0 - prm.beta2);
     const float eps = (float)prm.eps;
     for (long long i = i0 + tid; i < i1; i += kArThreads) {
-      float4 pp = ((float4*)prm.p)[i], mm = ((float4*)prm.m)[i], vv = ((float4*)prm.v)[i];
+      float4 pp, mm, vv;
+      if (i == ipre) { pp = pre_p; mm = pre_m; vv = pre_v; }
+      else { pp = ((float4*)prm.p)[i]; mm = ((float4*)prm.m)[i]; vv = ((float4*)prm.v)[i]; }
       const float4 gg = *(const float4*)(s_slice + 4 * (i - i0));
       adam_elem1(pp.x, gg.x, mm.x, vv.x, scale, w1, b2, w2, bc2_sqrt, eps, neg_step);
       adam_elem1(pp.y, gg.y, mm.y, vv.y, scale, w1, b2, w2, bc2_sqrt, eps, neg_step);

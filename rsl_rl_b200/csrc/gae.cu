@@ -23,7 +23,19 @@
 //   * the launch is COOPERATIVE (cudaLaunchAttributeCooperative): co-residency of the spinning blocks is guaranteed by
 //     the driver (or the launch fails) whatever else shares the device; the wait is unbounded like any grid.sync().
 // The last block to leave re-arms the counters, so the workspace only has to be zero ONCE (at allocation).
+//
+// TMA-staged kernel (gae_norm_tma_kernel, the default whenever N % 16 == 0 and T <= 32): a block owns a contiguous span
+// of envs; for a fixed step that span is one contiguous run of bytes in every [T,N] array, so the block's whole input
+// arrives as 3 T + 1 bulk copies (cp.async.bulk -> shared memory, one mbarrier) issued by one warp instead of 3 T scalar
+// loads per thread, and the outputs leave as 2 T bulk stores from shared memory (the returns rows while the statistics
+// are still being reduced).  The scan itself is unchanged (one env per thread, registers, the reference's fp32 op order).
+// Up to 8 192 envs the blocks form ONE thread-block cluster (<= 16 CTAs): the per-block fp64 partials are exchanged
+// through distributed shared memory behind the hardware cluster barrier - no cooperative launch, no global-memory
+// barrier; larger rollouts keep the cooperative grid barrier below.
+#include <cstdlib>
+
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace rslrl {
 
@@ -211,6 +223,158 @@ gae_norm_generic_kernel(const float* __restrict__ rewards, const float* __restri
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------- TMA-staged kernel
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"((uint64_t)src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* dst, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               ::"l"((uint64_t)dst), "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ double ld_cluster_f64(const double* local_ptr, uint32_t cta_rank) {
+  uint32_t remote;
+  double v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_ptr)), "r"(cta_rank));
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(remote) : "memory");
+  return v;
+}
+
+// nb = envs per block (multiple of 16, <= blockDim.x); CLUSTER: the whole grid is one cluster of gridDim.x CTAs.
+template <int TMAX, bool CLUSTER>
+__global__ void __launch_bounds__(512, 1)
+gae_norm_tma_kernel(const float* __restrict__ rewards, const float* __restrict__ values,
+                    const uint8_t* __restrict__ dones, const float* __restrict__ last_values,
+                    float* __restrict__ returns, float* __restrict__ advantages, double* __restrict__ partials,
+                    GaeBarrier* bar, int T, int N, int nb, float gamma, float lam, int normalize) {
+  extern __shared__ __align__(128) uint8_t gae_smem[];
+  __shared__ double s_red[64];
+  __shared__ __align__(16) double s_part[2];
+  __shared__ __align__(8) uint64_t s_mbar;
+  float* const s_r = (float*)gae_smem;                      // [T][nb] rewards, overwritten by the returns
+  float* const s_v = s_r + (size_t)T * nb;                  // [T][nb] values, overwritten by the advantages
+  uint8_t* const s_d = (uint8_t*)(s_v + (size_t)T * nb);    // [T][nb]
+  float* const s_last = (float*)(s_d + (size_t)T * nb);     // [nb]
+  GAE_TRACE(0);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int n0 = blockIdx.x * nb;
+  const int cnt = min(nb, N - n0);                          // envs of this block (multiple of 16)
+  if (tid == 0) {
+    mbar_init(&s_mbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid < 32) {   // one warp issues the bulk copies: lane <-> steps lane, lane + 32, ...
+    if (lane == 0) mbar_expect_tx(&s_mbar, (uint32_t)cnt * (9u * (uint32_t)T + 4u));
+    __syncwarp();
+    for (int t = lane; t < T; t += 32) {
+      const size_t o = (size_t)t * N + n0;
+      bulk_load(s_r + (size_t)t * nb, rewards + o, (uint32_t)cnt * 4u, &s_mbar);
+      bulk_load(s_v + (size_t)t * nb, values + o, (uint32_t)cnt * 4u, &s_mbar);
+      bulk_load(s_d + (size_t)t * nb, dones + o, (uint32_t)cnt, &s_mbar);
+    }
+    if (lane == 0) bulk_load(s_last, last_values + n0, (uint32_t)cnt * 4u, &s_mbar);
+  }
+  mbar_wait(&s_mbar, 0);
+
+  float x[TMAX];   // raw advantages of this thread's env
+  double s = 0.0, ss = 0.0;
+  const bool live = tid < cnt;
+  if (live) {
+    float r[TMAX], v[TMAX];
+    uint8_t d[TMAX];
+#pragma unroll
+    for (int i = 0; i < TMAX; ++i) {
+      if (i < T) {
+        r[i] = s_r[(size_t)i * nb + tid];
+        v[i] = s_v[(size_t)i * nb + tid];
+        d[i] = s_d[(size_t)i * nb + tid];
+      }
+    }
+    float next_v = s_last[tid];
+    float adv = 0.f;
+#pragma unroll
+    for (int i = TMAX - 1; i >= 0; --i) {
+      if (i < T) {
+        const float nnt = __fsub_rn(1.0f, (float)d[i]);
+        const float ng = __fmul_rn(nnt, gamma);
+        const float delta = __fsub_rn(__fadd_rn(r[i], __fmul_rn(ng, next_v)), v[i]);
+        adv = __fadd_rn(delta, __fmul_rn(__fmul_rn(ng, lam), adv));
+        const float ret = __fadd_rn(adv, v[i]);
+        s_r[(size_t)i * nb + tid] = ret;
+        x[i] = __fsub_rn(ret, v[i]);
+        s += (double)x[i];
+        ss += (double)x[i] * (double)x[i];
+        next_v = v[i];
+      }
+    }
+  }
+  GAE_TRACE(1);
+  // returns rows leave now (bulk stores from shared memory), overlapping the reduction of the statistics
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (tid < 32) {
+    for (int t = lane; t < T; t += 32) bulk_store(returns + (size_t)t * N + n0, s_r + (size_t)t * nb, (uint32_t)cnt * 4u);
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+
+  float mean_f = 0.f, denom_f = 1.f;
+  if (normalize) {
+    if constexpr (CLUSTER) {
+      double v2[2] = {s, ss};
+      block_sum<2>(v2, s_red);
+      if (tid == 0) { s_part[0] = v2[0]; s_part[1] = v2[1]; }
+      GAE_TRACE(2);
+      asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+      GAE_TRACE(3);
+      if (tid < 32) {   // every CTA sums the partials of all CTAs in the same order: identical bits everywhere
+        double t0 = 0.0, t1 = 0.0;
+        if (lane < (int)gridDim.x) {
+          t0 = ld_cluster_f64(&s_part[0], (uint32_t)lane);
+          t1 = ld_cluster_f64(&s_part[1], (uint32_t)lane);
+        }
+        t0 = warp_sum(t0);
+        t1 = warp_sum(t1);
+        if (lane == 0) {
+          const double n = (double)T * (double)N;
+          const double mean = t0 / n;
+          double var = (t1 - t0 * t0 / n) / (n - 1.0);  // unbiased, as torch.Tensor.std()
+          var = var > 0.0 ? var : 0.0;
+          s_red[0] = mean;
+          s_red[1] = sqrt(var);
+        }
+      }
+      // nobody leaves (and frees its shared memory) before every CTA has read the partials
+      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+      __syncthreads();
+      GAE_TRACE(4);
+      mean_f = (float)s_red[0];
+      denom_f = __fadd_rn((float)s_red[1], 1e-8f);
+    } else {
+      gae_finalize_stats(s, ss, partials, s_red, bar, (int64_t)T * N, mean_f, denom_f);
+    }
+  }
+  if (live) {
+#pragma unroll
+    for (int i = 0; i < TMAX; ++i)
+      if (i < T) s_v[(size_t)i * nb + tid] = normalize ? __fdiv_rn(__fsub_rn(x[i], mean_f), denom_f) : x[i];
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (tid < 32) {
+    for (int t = lane; t < T; t += 32) bulk_store(advantages + (size_t)t * N + n0, s_v + (size_t)t * nb, (uint32_t)cnt * 4u);
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  if constexpr (CLUSTER) {
+    if (normalize) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
+  GAE_TRACE(5);
+}
+
 static int device_sms() {
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
@@ -251,6 +415,99 @@ static int launch_reg(void** args, int N, cudaStream_t st) {
   return launch_coop(gae_norm_reg_kernel<TMAX>, blocks, threads, args, st);
 }
 
+
+// TMA-staged path: 0 launched, 1 error, -1 not eligible
+template <int TMAX>
+static int launch_tma(void** args_in, const void* const* ptrs, int T, int N, int normalize, cudaStream_t st) {
+  for (int i = 0; i < 6; ++i)
+    if ((uintptr_t)ptrs[i] & 15) return -1;
+  if (N % 16 != 0 || T > TMAX) return -1;
+  static const bool off = [] { const char* e = getenv("RSLRL_GAE_TMA"); return e && e[0] == '0'; }();
+  if (off) return -1;
+  const int sms = device_sms();
+  const bool cluster = normalize && N <= 16 * 512;
+  int blocks, nb;
+  if (cluster) {
+    blocks = 16;
+    while (blocks > 1 && blocks * 32 > N) blocks >>= 1;          // at least 32 envs per CTA
+    nb = ((N + blocks - 1) / blocks + 15) / 16 * 16;
+    blocks = (N + nb - 1) / nb;
+    if (blocks & (blocks - 1)) {                                  // keep the cluster size a power of two
+      int p2 = 1;
+      while (p2 < blocks) p2 <<= 1;
+      blocks = p2 >> 1;
+      nb = ((N + blocks - 1) / blocks + 15) / 16 * 16;
+      blocks = (N + nb - 1) / nb;
+      if (blocks & (blocks - 1)) return -1;
+    }
+  } else {
+    nb = ((N + sms - 1) / sms + 15) / 16 * 16;
+    if (nb < 32) nb = 32;
+    blocks = (N + nb - 1) / nb;
+  }
+  if (nb > 512 || blocks > kGaeMaxBlocks) return -1;
+  const int threads = (nb + 31) / 32 * 32;
+  const size_t smem = (size_t)nb * (9 * (size_t)T + 4);
+  void* args[14];
+  for (int i = 0; i < 10; ++i) args[i] = args_in[i];
+  args[10] = &nb;
+  args[11] = args_in[10];
+  args[12] = args_in[11];
+  args[13] = args_in[12];
+  const void* kern = cluster ? (const void*)gae_norm_tma_kernel<TMAX, true> : (const void*)gae_norm_tma_kernel<TMAX, false>;
+  static size_t smem_set[2] = {0, 0};
+  static int cluster_ok = -1;   // 16-CTA clusters need the non-portable attribute and a GPC that can host them
+  if (smem > smem_set[cluster]) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return -1;
+    }
+    smem_set[cluster] = 200 * 1024;
+  }
+  if (smem > 200 * 1024) return -1;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(blocks);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (cluster) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = blocks;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    if (cluster_ok < 0) {
+      cluster_ok = 0;
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+        cudaLaunchConfig_t probe = cfg;
+        cudaLaunchAttribute pa[1];
+        pa[0] = attr[0];
+        pa[0].val.clusterDim.x = 16;
+        probe.attrs = pa;
+        probe.gridDim = dim3(16);
+        probe.blockDim = dim3(512);
+        probe.dynamicSmemBytes = 200 * 1024;
+        int nc = 0;
+        if (cudaOccupancyMaxActiveClusters(&nc, kern, &probe) == cudaSuccess && nc >= 1) cluster_ok = 1;
+      }
+      (void)cudaGetLastError();
+    }
+    if (!cluster_ok && blocks > 8) return -1;
+  } else {
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = normalize ? 1 : 0;
+  }
+  cudaError_t e = cudaLaunchKernelExC(&cfg, kern, args);
+  if (e != cudaSuccess) {
+    set_error("rslrl_gae_norm: %s", cudaGetErrorString(e));
+    return 1;
+  }
+  count_launch();
+  return 0;
+}
+
 }  // namespace rslrl
 
 extern "C" {
@@ -273,6 +530,12 @@ int rslrl_gae_norm(const float* rewards, const float* values, const uint8_t* don
   void* args[] = {&rewards, &values, &dones, &last_values, &returns, &advantages, &partials, &bar,
                   &T,       &N,      &gamma, &lam,         &normalize};
   int rc = -1;
+  const void* ptrs[6] = {rewards, values, dones, last_values, returns, advantages};
+  if (T <= 8) rc = launch_tma<8>(args, ptrs, T, N, normalize, st);
+  else if (T <= 16) rc = launch_tma<16>(args, ptrs, T, N, normalize, st);
+  else if (T <= 24) rc = launch_tma<24>(args, ptrs, T, N, normalize, st);
+  else if (T <= 32) rc = launch_tma<32>(args, ptrs, T, N, normalize, st);
+  if (rc >= 0) return rc;
   if (T <= 8) rc = launch_reg<8>(args, N, st);
   else if (T <= 16) rc = launch_reg<16>(args, N, st);
   else if (T <= 24) rc = launch_reg<24>(args, N, st);

@@ -334,8 +334,12 @@ ppo_loss_kernel(const float* __restrict__ mu, const float* __restrict__ std_para
 // Optional fused data gradient of the two OUTPUT layers (fp16-storage path): with `head.dz_a != nullptr` the kernel also
 // writes  dZ3 = S * (dL/dmu W4_actor) * act'(H3_actor)  and  S * (dL/dV W4_critic) * act'(H3_critic)  as fp16 -- the
 // gradients at the output of the last hidden layer, i.e. what a separate K = 12 / K = 1 tensor-core launch produced
-// before (12 us per minibatch at 4 % tensor activity, for 25 MB of traffic).  Each thread of a quad owns a quarter of the
-// hidden width; the 12 + 1 output gradients of the row are exchanged with quad shuffles, the weights sit in shared memory.
+// before (12 us per minibatch at 4 % tensor activity, for 25 MB of traffic).  The block's 64 rows of S * dL/dmu (fp16, the
+// same values the dmu16 copy holds) and S * dL/dV are staged in shared memory; warps 0-3 then run the actor's
+// [64 x 16] x [16 x K3] product as warp-level m16n8k16 MMAs (fp16 operands, fp32 accumulation: the arithmetic of the
+// tensor-core launch it replaces) with the column order of the B fragments chosen so that every lane ends up with 8
+// CONSECUTIVE hidden units of its two rows (one 16-byte load of H3 and one 16-byte store of dZ3 per 32-column group);
+// warps 4-7 do the critic's rank-1 product elementwise, 16 lanes per 256-byte row.
 struct LossHead {
   const float* w_a;    // [A, K3] actor output-layer weight (fp32 master)
   const float* w_c;    // [1, K3] critic output-layer weight
@@ -346,6 +350,7 @@ struct LossHead {
   int K3, ldh, act;
 };
 constexpr int kHeadMaxK3 = 128;
+constexpr int kHeadPitch = 24;   // halfs per shared-memory row of the head operands (48 bytes)
 
 constexpr int kQuadThreads = 256;
 __global__ void __launch_bounds__(kQuadThreads)
@@ -363,11 +368,18 @@ ppo_loss_quad_kernel(const float* __restrict__ mu, const float* __restrict__ std
   pdl_trigger();
   pdl_wait();
   RSLRL_LOSS_SCALE_PROLOGUE
-  __shared__ __align__(16) float s_wa[16 * kHeadMaxK3];   // actor output-layer weight (A <= 16 rows)
+  // fused output-layer data gradient: W4^T of the actor as fp16 [K3][16 actions] and the block's S * dL/dmu rows, both
+  // with a 48-byte row pitch (conflict-free 4-byte fragment loads); critic weight (fp16-rounded) and S * dL/dV as floats
+  __shared__ __align__(16) __half s_wt[kHeadMaxK3 * kHeadPitch];
+  __shared__ __align__(16) __half s_dm16[(kQuadThreads / 4) * kHeadPitch];
   __shared__ __align__(16) float s_wc[kHeadMaxK3];
+  __shared__ float s_dv[kQuadThreads / 4];
   if (head.dz_a != nullptr) {
-    for (int t = threadIdx.x; t < A * head.K3; t += kQuadThreads) s_wa[t] = __ldg(head.w_a + t);
-    for (int t = threadIdx.x; t < head.K3; t += kQuadThreads) s_wc[t] = __ldg(head.w_c + t);
+    for (int t = threadIdx.x; t < 16 * head.K3; t += kQuadThreads) {
+      const int col = t >> 4, a = t & 15;
+      s_wt[col * kHeadPitch + a] = __float2half_rn(a < A ? __ldg(head.w_a + a * head.K3 + col) : 0.f);
+    }
+    for (int t = threadIdx.x; t < head.K3; t += kQuadThreads) s_wc[t] = __half2float(__float2half_rn(__ldg(head.w_c + t)));
   }
   __shared__ float s_sigma[kMaxActions], s_logs[kMaxActions], s_2var[kMaxActions];
   __shared__ double s_red[4 * 32];
@@ -487,48 +499,80 @@ ppo_loss_quad_kernel(const float* __restrict__ mu, const float* __restrict__ std
       }
     }
     if (head.dz_a != nullptr) {   // uniform branch: fused data gradient of the two output layers
-      // all dL/dmu of the row (this quad's 4 x 4 values) and its dL/dV (held by the quad's lead thread)
-      float dm[16];
-      const int qbase = lane & ~3;
+      const int rl = threadIdx.x >> 2;   // row of this quad inside the block
+      {
+        const __half2 lo2 = __floats2half2_rn(mine ? sat16(o[0] * scale16) : 0.f, mine ? sat16(o[1] * scale16) : 0.f);
+        const __half2 hi2 = __floats2half2_rn(mine ? sat16(o[2] * scale16) : 0.f, mine ? sat16(o[3] * scale16) : 0.f);
+        uint2 w;
+        w.x = *(const unsigned int*)&lo2;
+        w.y = *(const unsigned int*)&hi2;
+        *(uint2*)(s_dm16 + rl * kHeadPitch + c) = w;
+        if (qd == 0) s_dv[rl] = lead ? __half2float(__float2half_rn(sat16(dv_sum * scale16))) : 0.f;
+      }
+      __syncthreads();
+      const int warp = threadIdx.x >> 5;
+      const long long row0 = (long long)blockIdx.x * (kQuadThreads / 4);
+      if (warp < 4) {
+        // ---- actor: rows [16 warp, 16 warp + 16) x K3 columns on m16n8k16 MMAs
+        const int gq = lane >> 2, tq = lane & 3, r0 = 16 * warp;
+        const unsigned int a0 = *(const unsigned int*)(s_dm16 + (r0 + gq) * kHeadPitch + 2 * tq);
+        const unsigned int a1 = *(const unsigned int*)(s_dm16 + (r0 + gq + 8) * kHeadPitch + 2 * tq);
+        const unsigned int a2 = *(const unsigned int*)(s_dm16 + (r0 + gq) * kHeadPitch + 2 * tq + 8);
+        const unsigned int a3 = *(const unsigned int*)(s_dm16 + (r0 + gq + 8) * kHeadPitch + 2 * tq + 8);
+        const long long ra = row0 + r0 + gq, rb = ra + 8;
+        for (int base = 0; base < head.K3; base += 32) {
+          float acc[4][4];
 #pragma unroll
-      for (int src = 0; src < 4; ++src)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) dm[4 * src + q] = __shfl_sync(0xffffffffu, mine ? o[q] : 0.f, qbase + src);
-      const float dvr = __shfl_sync(0xffffffffu, dv_sum, qbase);
-      if (valid) {
-        const int cols = head.K3 >> 2, c0 = qd * cols;          // this thread's quarter of the hidden width
-        const __half* ha = head.h_a + i * head.ldh + c0;
-        const __half* hc = head.h_c + i * head.ldh + c0;
-        __half* za = head.dz_a + i * head.ldh + c0;
-        __half* zc = head.dz_c + i * head.ldh + c0;
-        for (int cc = 0; cc < cols; cc += 8) {                   // 8 hidden units (16 bytes of fp16) at a time
-          float ga[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-          for (int a = 0; a < 16; ++a) {   // (unrolled with a guard: dm[] stays in registers)
-            if (a >= A) break;
-            const float4 w0 = *(const float4*)(s_wa + a * head.K3 + c0 + cc);
-            const float4 w1 = *(const float4*)(s_wa + a * head.K3 + c0 + cc + 4);
-            ga[0] += dm[a] * w0.x; ga[1] += dm[a] * w0.y; ga[2] += dm[a] * w0.z; ga[3] += dm[a] * w0.w;
-            ga[4] += dm[a] * w1.x; ga[5] += dm[a] * w1.y; ga[6] += dm[a] * w1.z; ga[7] += dm[a] * w1.w;
+          for (int jj = 0; jj < 4; ++jj) {
+            // B fragment of MMA jj: n index gq <-> hidden unit base + (gq >> 1) * 8 + 2 jj + (gq & 1), so that this lane's
+            // accumulator columns (n = 2 tq, 2 tq + 1) over jj = 0..3 are the 8 consecutive units base + 8 tq .. + 7
+            const int col = base + (gq >> 1) * 8 + 2 * jj + (gq & 1);
+            const unsigned int b0 = *(const unsigned int*)(s_wt + col * kHeadPitch + 2 * tq);
+            const unsigned int b1 = *(const unsigned int*)(s_wt + col * kHeadPitch + 2 * tq + 8);
+            asm volatile(
+                "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                : "=f"(acc[jj][0]), "=f"(acc[jj][1]), "=f"(acc[jj][2]), "=f"(acc[jj][3])
+                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(0.f));
           }
-          const float4 v0 = *(const float4*)(s_wc + c0 + cc), v1 = *(const float4*)(s_wc + c0 + cc + 4);
-          const float gc[8] = {dvr * v0.x, dvr * v0.y, dvr * v0.z, dvr * v0.w, dvr * v1.x, dvr * v1.y, dvr * v1.z, dvr * v1.w};
-          const uint4 pa = *(const uint4*)(ha + cc), pc = *(const uint4*)(hc + cc);
-          const __half2* ha2 = (const __half2*)&pa;
-          const __half2* hc2 = (const __half2*)&pc;
-          uint4 oa, oc;
-          __half2* oa2 = (__half2*)&oa;
-          __half2* oc2 = (__half2*)&oc;
+#pragma unroll
+          for (int half_ = 0; half_ < 2; ++half_) {
+            const long long r = half_ ? rb : ra;
+            if (r < rows) {
+              const uint4 hv = *(const uint4*)(head.h_a + r * head.ldh + base + 8 * tq);
+              const __half2* h2 = (const __half2*)&hv;
+              uint4 ov;
+              __half2* o2 = (__half2*)&ov;
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const float2 f = __half22float2(h2[jj]);
+                o2[jj] = __floats2half2_rn(sat16(acc[jj][2 * half_] * act_grad_from_output(head.act, f.x)),
+                                           sat16(acc[jj][2 * half_ + 1] * act_grad_from_output(head.act, f.y)));
+              }
+              *(uint4*)(head.dz_a + r * head.ldh + base + 8 * tq) = ov;
+            }
+          }
+        }
+      } else {
+        // ---- critic: dZ3[r][k] = (S dL/dV[r]) * w[k] * act'(H3[r][k]); consecutive lanes walk one row in 16-byte chunks
+        const int chunks = head.K3 >> 3, tasks = (kQuadThreads / 4) * chunks;
+        for (int task = threadIdx.x - 128; task < tasks; task += 128) {
+          const int rr = task / chunks, ch = task - rr * chunks;
+          const long long r = row0 + rr;
+          if (r >= rows) continue;
+          const float dvr = s_dv[rr];
+          const float4 v0 = *(const float4*)(s_wc + 8 * ch), v1 = *(const float4*)(s_wc + 8 * ch + 4);
+          const float wv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+          const uint4 hv = *(const uint4*)(head.h_c + r * head.ldh + 8 * ch);
+          const __half2* h2 = (const __half2*)&hv;
+          uint4 ov;
+          __half2* o2 = (__half2*)&ov;
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const float2 fa = __half22float2(ha2[u]), fc = __half22float2(hc2[u]);
-            oa2[u] = __floats2half2_rn(sat16(ga[2 * u] * act_grad_from_output(head.act, fa.x) * scale16),
-                                       sat16(ga[2 * u + 1] * act_grad_from_output(head.act, fa.y) * scale16));
-            oc2[u] = __floats2half2_rn(sat16(gc[2 * u] * act_grad_from_output(head.act, fc.x) * scale16),
-                                       sat16(gc[2 * u + 1] * act_grad_from_output(head.act, fc.y) * scale16));
+            const float2 f = __half22float2(h2[u]);
+            o2[u] = __floats2half2_rn(sat16(dvr * wv[2 * u] * act_grad_from_output(head.act, f.x)),
+                                      sat16(dvr * wv[2 * u + 1] * act_grad_from_output(head.act, f.y)));
           }
-          *(uint4*)(za + cc) = oa;
-          *(uint4*)(zc + cc) = oc;
+          *(uint4*)(head.dz_c + r * head.ldh + 8 * ch) = ov;
         }
       }
     }

@@ -327,8 +327,10 @@ def _run_loss(mu, std_param, std_type, value, actions, old_logp, adv, ret, old_v
     if head is not None:
         _, h_a, h_c, w_a, w_c, dz_a, dz_c = head_keep
         egrad = lambda h: torch.where(h > 0, torch.ones_like(h), h + 1.0)
-        ref_a = (dmu.double() @ w_a.double()) * egrad(h_a.double()) * S16
-        ref_c = (dv.double()[:, None] * w_c.double()) * egrad(h_c.double()) * S16
+        # the product consumes the (saturated) fp16 copies S * dmu, S * dV and the fp16-rounded weights with fp32
+        # accumulation: the arithmetic of the tensor-core launch this fusion replaces
+        ref_a = (dmu16[:, :A].double() @ w_a.half().double()) * egrad(h_a.double())
+        ref_c = (dv16[:, :1].double() * w_c.half().double()) * egrad(h_c.double())
         assert rel_err(dz_a.double().clamp(-65504, 65504).cpu().numpy(), ref_a.clamp(-65504, 65504).cpu().numpy()) < 1e-3
         assert rel_err(dz_c.double().clamp(-65504, 65504).cpu().numpy(), ref_c.clamp(-65504, 65504).cpu().numpy()) < 1e-3
     # the fused bias gradients of the two output layers are the column sums of dmu / dvalue
