@@ -606,7 +606,8 @@ def run_ours(args):
             cpu = cpu_reference_sample(args.config)
         line = dict(metric=cfg["metric"], value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms / K,
                     higher_is_better=True, scaling="weak", vs_baseline=None,
-                    dtype={"fp32": "f32", "tf32": "tf32", "fp16": "fp16 operands, fp32 accumulate"}[args.precision],
+                    dtype={"fp32": "f32", "tf32": "tf32", "fp16": "fp16 operands, fp32 accumulate",
+                           "tf32x3": "f32 (3xTF32 split-operand tensor-core products, fp32 accumulate)"}[args.precision],
                     data="synthetic", config=workload_config(args.config, world),
                     arm=dict(parallelism=f"dp{world}", gemm_precision=args.precision,
                              cuda_graph=bool(runner.alg._graph is not None)),
@@ -674,7 +675,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default=os.environ.get("RSLRL_BENCH_CONFIG", "c2"), choices=sorted(CONFIGS))
-    ap.add_argument("--precision", default=os.environ.get("RSLRL_PRECISION", "fp16"), choices=["fp32", "tf32", "fp16"])
+    ap.add_argument("--precision", default=os.environ.get("RSLRL_PRECISION", "fp16"), choices=["fp32", "tf32", "fp16", "tf32x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-cuda", action="store_true")
     ap.add_argument("--only-timed", action="store_true", help="profiling aid: warm-up + timed region only")

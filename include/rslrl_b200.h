@@ -46,7 +46,10 @@ enum {
   RSLRL_ACT_LRELU = 5, RSLRL_ACT_SELU = 6, RSLRL_ACT_SOFTPLUS = 7
 };
 /* GEMM arithmetic: fp32 CUDA-core FMA (1e-5 parity class) or TF32 tcgen05 tensor cores (1e-3 class) */
-enum { RSLRL_PREC_FP32 = 0, RSLRL_PREC_TF32 = 1, RSLRL_PREC_FP16 = 2 };
+enum { RSLRL_PREC_FP32 = 0, RSLRL_PREC_TF32 = 1, RSLRL_PREC_FP16 = 2, RSLRL_PREC_TF32X3 = 3 };
+/* RSLRL_PREC_TF32X3 ("3xTF32"): fp32 operands split on chip into hi = tf32(x) and lo = x - hi, three tensor-core products
+ * (lo*hi + hi*lo + hi*hi) into one fp32 accumulator: the 1e-5 error class of the reference's fp32 arithmetic
+ * (torch.backends.cuda.matmul.allow_tf32 = False) at tensor-core speed.  Accepted by the rslrl_linear_* entry points. */
 /* RSLRL_PREC_FP16 ("16-bit activation storage"): the saved activations h, the layer gradients dy / dx, the
  * minibatch observations x and a shadow copy of the weights are IEEE fp16 in HBM (10-bit mantissa = the precision
  * tf32 gives the same operands) and the MMAs are tcgen05 kind::f16 with fp32 accumulation.  Master weights, weight /
@@ -305,6 +308,23 @@ int rslrl_ppo_loss_fwd_bwd(const float* mu, const float* std_param, int std_type
 /* sum and sum of squares of x[0..n) into out[2] (double, overwritten): statistics for
  * ppo.py:221-223 per-minibatch advantage normalisation. */
 int rslrl_sum_sumsq(const float* x, int64_t n, double* out, void* workspace, rslrl_stream_t stream);
+
+/* ---- Random Network Distillation (rsl_rl/modules/rnd.py:113-135, get_intrinsic_reward) ---------------- */
+
+/* One small MLP: num_layers Linear layers, w[l] is [dims[l+1], dims[l]] row-major, b[l] [dims[l+1]] or NULL, act[l] the
+ * RSLRL_ACT_* code applied after layer l (0 after the last one).  Widths <= 128, at most 4 layers. */
+typedef struct {
+  const float* w[4];
+  const float* b[4];
+  int act[4];
+  int dims[5];
+  int num_layers;
+} rslrl_rnd_net_t;
+
+/* out[i] = scale * || target(x_i) - predictor(x_i) ||_2 for n rows of x (row stride ldx, floats): both embedding
+ * networks, the gap, the norm and the weight in ONE launch (weights resident in shared memory, fp32 FMA). */
+int rslrl_rnd_reward(const rslrl_rnd_net_t* target, const rslrl_rnd_net_t* predictor, const float* x, int64_t ldx,
+                     int64_t n, float* out, double scale, rslrl_stream_t stream);
 
 /* ---- optimiser (rsl_rl/algorithms/ppo.py:260-294 KL-adaptive LR, :380 clip_grad_norm_, :381 Adam) -- */
 

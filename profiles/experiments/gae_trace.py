@@ -32,7 +32,10 @@ for N in (4096, 65536):
         assert lib.rslrl_debug_read_trace_gae(buf) == 0
         threads = max(128, ((N + 147) // 148 + 31) // 32 * 32)
         blocks = (N + threads - 1) // threads
-        stp = [[buf[b * 8 + s] for s in range(6)] for b in range(blocks)]
+        stp = [[buf[b * 8 + s] for s in range(6)] for b in range(148)]
+        newest = max(r[0] for r in stp)   # blocks of THIS launch: entry stamps within 1 ms of the newest one
+        stp = [r for r in stp if r[0] and newest - r[0] < 1_000_000]
+        blocks = len(stp)
         t0 = min(r[0] for r in stp)
         rows.append(dict(event_us=e0.elapsed_time(e1) * 1e3, kernel_us=(max(r[5] for r in stp) - t0) / 1e3,
                          entry_spread=(max(r[0] for r in stp) - t0) / 1e3,

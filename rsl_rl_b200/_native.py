@@ -19,8 +19,8 @@ c_void_p, c_int, c_i64, c_double = C.c_void_p, C.c_int, C.c_int64, C.c_double
 U8, I32, I64, F32 = 0, 1, 2, 3
 ACT_CODES = {"identity": 0, "elu": 1, "relu": 2, "tanh": 3, "sigmoid": 4, "lrelu": 5, "selu": 6, "softplus": 7,
              "crelu": 1}  # nn.CELU(alpha=1) == nn.ELU(alpha=1)
-PREC_FP32, PREC_TF32, PREC_FP16 = 0, 1, 2
-PREC_CODES = {"fp32": PREC_FP32, "tf32": PREC_TF32, "fp16": PREC_FP16}
+PREC_FP32, PREC_TF32, PREC_FP16, PREC_TF32X3 = 0, 1, 2, 3
+PREC_CODES = {"fp32": PREC_FP32, "tf32": PREC_TF32, "fp16": PREC_FP16, "tf32x3": PREC_TF32X3}
 STD_SCALAR, STD_LOG = 0, 1
 MAX_SEGMENTS, MAX_PROBLEMS = 16, 8
 ABI_VERSION = 2   # RSLRL_ABI_VERSION of include/rslrl_b200.h
@@ -70,6 +70,10 @@ class LstmBwd(C.Structure):
 class LossHead(C.Structure):
     _fields_ = [("w_actor", c_void_p), ("w_critic", c_void_p), ("h_actor", c_void_p), ("h_critic", c_void_p),
                 ("dz_actor", c_void_p), ("dz_critic", c_void_p), ("K3", c_int), ("ldh", c_int), ("act", c_int)]
+
+
+class RndNet(C.Structure):
+    _fields_ = [("w", c_void_p * 4), ("b", c_void_p * 4), ("act", c_int * 4), ("dims", c_int * 5), ("num_layers", c_int)]
 
 
 class OptState(C.Structure):
@@ -133,6 +137,7 @@ _SIGNATURES = {
     "rslrl_empirical_normalize": (c_int, [c_void_p, c_i64, c_i64, c_int, c_void_p, c_void_p, c_double, c_void_p, c_i64,
                                           c_void_p]),
     "rslrl_fill_zero": (c_int, [c_void_p, c_i64, c_void_p]),
+    "rslrl_rnd_reward": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_double, c_void_p]),
     "rslrl_convert_f32_f16": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_i64, c_int, c_int, c_void_p]),
 }
 

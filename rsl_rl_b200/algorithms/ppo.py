@@ -38,6 +38,11 @@ from .flat_params import FlatParamGroup, FusedAdam
 
 
 _GRAPH_COLLECTIVES = os.environ.get("RSLRL_GRAPH_COLLECTIVES", "1") != "0"
+# GEMM arithmetic a drop-in user gets without asking: the reference computes in fp32 (allow_tf32 is off by default in
+# torch), so the default must be an fp32-CLASS mode.  "tf32x3" = three split-operand tcgen05 products per GEMM (gradients
+# within 2e-6 of the fp32 oracle at the C1 shape, 3x faster than the CUDA-core "fp32" mode); shapes TMA cannot describe
+# fall back to the CUDA-core kernels per launch.
+DEFAULT_GEMM_PRECISION = "tf32x3"
 _ACT_GRAPH = os.environ.get("RSLRL_ACT_GRAPH", "1") != "0"   # per-step act() graphs (forward + Gaussian head)
 
 
@@ -65,7 +70,9 @@ class PPO:
         symmetry_cfg: dict | None = None,
         multi_gpu_cfg: dict | None = None,
         # --- rsl_rl_b200 extensions (all optional) ---
-        gemm_precision: str = "fp32",   # "fp32": CUDA-core FMA (1e-5 class) | "tf32": tcgen05 tensor cores (1e-3 class)
+        gemm_precision: str | None = None,   # None: $RSLRL_GEMM_PRECISION or DEFAULT_GEMM_PRECISION
+                                         # "tf32x3": 3xTF32 split-operand tcgen05 products (fp32 class, 1e-5)
+                                         # | "fp32": CUDA-core FMA (1e-5 class) | "tf32": tcgen05 tensor cores (1e-3 class)
                                          # | "fp16": tcgen05 kind::f16 on fp16-stored activations/gradients (1e-3 class)
         use_cuda_graph: bool = True,     # capture update() into one CUDA graph (single-GPU fused path)
         rng_compat: bool = True,         # consume the RNG exactly like the reference (discarded draws in update())
@@ -73,6 +80,10 @@ class PPO:
         if torch.device(device).type != "cuda":
             raise RuntimeError(f"rsl_rl_b200.PPO runs on a CUDA device only (got device={device!r}); "
                                "there is no CPU fallback.")
+        if gemm_precision is None:
+            gemm_precision = os.environ.get("RSLRL_GEMM_PRECISION", DEFAULT_GEMM_PRECISION)
+        if gemm_precision not in nat.PREC_CODES:
+            raise ValueError(f"gemm_precision must be one of {sorted(nat.PREC_CODES)}, got {gemm_precision!r}")
         nat.lib()
         self.device = device
         self.is_multi_gpu = multi_gpu_cfg is not None
@@ -190,8 +201,8 @@ class PPO:
             B = num_envs * num_transitions_per_env
             mb = B // self.num_mini_batches
             precision = self.gemm_precision
-            if self._update_reason is not None and precision == "fp16":
-                precision = "tf32"   # the composite update runs the MLPs under autograd (tf32 tensor cores there)
+            if self._update_reason is not None and precision == "fp16" and not self._composite_fp16_ok():
+                precision = "tf32"   # (shapes the fp16-storage chain does not cover, or the autograd composite path)
             self._engine = _engine.FeedForwardEngine(self.policy, B if self._update_reason is None else num_envs, num_envs,
                                                      mb if self._update_reason is None else num_envs, self.device,
                                                      precision, self._group,
@@ -668,15 +679,34 @@ class PPO:
                 and (self.symmetry is None or bool(self.symmetry["use_data_augmentation"]))
                 and os.environ.get("RSLRL_COMPOSITE_FUSED", "1") != "0")
 
+    def _composite_fp16_ok(self) -> bool:
+        """gemm_precision='fp16' on the fused RND / symmetry update: the 16-bit storage chain needs the shapes the fused
+        forward covers (3 hidden layers, widths multiples of 64, A % 4 == 0)."""
+        if not self._composite_fusable() or os.environ.get("RSLRL_COMPOSITE_FP16", "1") == "0":
+            return False
+        pol = self.policy
+        from ..networks.mlp import mlp3_eligible
+        for net in (_engine._Net(pol.actor), _engine._Net(pol.critic)):
+            if not mlp3_eligible(net.dims, net.acts) or any(d % 64 for d in net.dims[1:-1]) or net.dims[-1] > 12:
+                return False
+        return _engine._Net(pol.actor).dims[-1] % 4 == 0
+
     def _composite_engine(self, rows: int):
         """The engine with activation / gradient buffers for `rows` minibatch rows (k * minibatch with k-fold
         augmentation); the rollout keeps using the same object."""
         eng = self._engine
         if eng.rows < rows:
+            precision = self.gemm_precision
+            if precision == "fp16" and not self._composite_fp16_ok():
+                precision = "tf32"
             eng = self._engine = _engine.FeedForwardEngine(self.policy, rows, self.storage.num_envs, rows, self.device,
-                                                           "tf32" if self.gemm_precision == "fp16" else self.gemm_precision,
-                                                           self._group)
+                                                           precision, self._group,
+                                                           scale_state=self.optimizer.dev_state.scale_state)
             self._act_plans.clear()
+        if eng.f16 and self.symmetry and self.symmetry["use_mirror_loss"]:
+            # the mirror-loss gradient is added to dL/dmu AFTER the loss launch: the fp16 copy of dL/dmu is rebuilt from
+            # the sum and the output layer's data gradient runs as its own launch (not inside the loss kernel)
+            eng.fused_head_dgrad = False
         return eng
 
     def _composite_minibatches_fused(self, sums):
@@ -755,7 +785,15 @@ class PPO:
                     sums[4] += (diff * diff).mean()
                     if sym["use_mirror_loss"]:
                         eng.dmu[mb:rows].add_(diff, alpha=float(sym["mirror_loss_coeff"]) * 2.0 / diff.numel())
-                eng.backward(x_a, x_c, eng.dmu[:rows], eng.dvalue[:rows])
+                        if eng.f16:   # S * (dL/dmu + mirror gradient) as fp16, S = the scale this loss launch used
+                            S = eng.scale_state[0] if eng.scale_state is not None else eng.grad_scale
+                            eng.dmu16[mb:rows].copy_((eng.dmu[mb:rows] * S).clamp_(-65504.0, 65504.0))
+                if eng.f16:   # fp16 copies of the (augmented) minibatch observations: B operand of the first layer's wgrad
+                    x16a = self._x16(cf, "a", x_a)
+                    x16c = x16a if x_c is x_a else self._x16(cf, "c", x_c)
+                    eng.backward(x16a, x16c, eng.dmu[:rows], eng.dvalue[:rows])
+                else:
+                    eng.backward(x_a, x_c, eng.dmu[:rows], eng.dvalue[:rows])
                 if self.rnd:
                     with torch.no_grad():
                         rnd_state = self.rnd.state_normalizer(self.rnd.get_rnd_state(obs_b))
@@ -775,6 +813,13 @@ class PPO:
                 eng.refresh_padded(after_step=True)
         # loss accumulators of the fused kernel: [surrogate, value, entropy] -> the composite order
         sums[0:1].copy_(ds.loss_sums[1:2]); sums[1:2].copy_(ds.loss_sums[0:1]); sums[2:3].copy_(ds.loss_sums[2:3])
+
+    def _x16(self, cf, tag: str, x: torch.Tensor) -> torch.Tensor:
+        key = ("x16", tag, x.shape[0], x.shape[1])
+        buf = cf.get(key)
+        if buf is None:
+            buf = cf[key] = torch.zeros(x.shape[0], (x.shape[1] + 7) // 8 * 8, dtype=torch.float16, device=self.device)
+        return self._to_f16(x, buf)
 
     def _composite_minibatches(self, sums):
         """The minibatch loop of the composite update (everything it puts on the stream is graph-capturable for

@@ -425,10 +425,11 @@ static int launch_tma(void** args_in, const void* const* ptrs, int T, int N, int
   static const bool off = [] { const char* e = getenv("RSLRL_GAE_TMA"); return e && e[0] == '0'; }();
   if (off) return -1;
   const int sms = device_sms();
-  const bool cluster = normalize && N <= 16 * 512;
+  static const int cluster_max = [] { const char* e = getenv("RSLRL_GAE_CLUSTER_MAX"); return e ? atoi(e) : 16; }();
+  const bool cluster = normalize && cluster_max >= 1 && N <= cluster_max * 512;
   int blocks, nb;
   if (cluster) {
-    blocks = 16;
+    blocks = cluster_max;
     while (blocks > 1 && blocks * 32 > N) blocks >>= 1;          // at least 32 envs per CTA
     nb = ((N + blocks - 1) / blocks + 15) / 16 * 16;
     blocks = (N + nb - 1) / nb;

@@ -77,14 +77,23 @@ constexpr int TCP_H_BYTES = TCP_H_CHUNKS * 16384;
 constexpr int TCP_RING_BUDGET_DGRAD = 96 * 1024;
 // (measured: a single staging slot per epilogue warp + a 4-stage 192 KB ring is slower than 2 slots + 3 stages -- the
 // serialised epilogue, 8 us instead of 3 us per 128x256 tile, costs more than the deeper ring gains)
-__host__ __device__ constexpr int tcp_staging_slots(int mode, bool f16) { return 2; }
-__host__ __device__ constexpr int tcp_staging_bytes(int mode, bool f16) {
-  return mode == 1 ? TCP_H_BYTES : TCP_EPI_WARPS * tcp_staging_slots(mode, f16) * 4096;
+// (3xTF32: the mainloop is three times longer per tile, so one staging slot is enough and its 32 KB buy a third ring stage)
+__host__ __device__ constexpr int tcp_staging_slots(int mode, bool f16, bool x3 = false) { return x3 ? 1 : 2; }
+__host__ __device__ constexpr int tcp_staging_bytes(int mode, bool f16, bool x3 = false) {
+  return mode == 1 ? (x3 ? 4 * 16384 : TCP_H_BYTES) : TCP_EPI_WARPS * tcp_staging_slots(mode, f16, x3) * 4096;
 }
-__host__ __device__ constexpr int tcp_ring_budget(int mode, bool f16) {
-  return mode == 1 ? TCP_RING_BUDGET_DGRAD : TCP_RING_BUDGET;
+__host__ __device__ constexpr int tcp_ring_budget(int mode, bool f16, bool x3 = false) {
+  return mode == 1 ? (x3 ? TCP_RING_BUDGET : TCP_RING_BUDGET_DGRAD) : (x3 ? 192 * 1024 : TCP_RING_BUDGET);
 }
 constexpr int TCP_MAX_BLOCK_N = 256;
+// X3 = "3xTF32": fp32-class products on the tf32 tensor cores.  The operands arrive as raw fp32 (FLOAT32 tensor maps:
+// the MMA truncates them to tf32, hi = x & 0xffffe000); four extra converter warps write lo = x - hi (exact in fp32) of
+// every staged k-block into a second copy of the stage, and every k-step issues three MMAs into the same accumulator:
+// A_lo B_hi + A_hi B_lo + A_hi B_hi (the dropped lo x lo term and the truncation of lo are ~2^-21 relative).
+constexpr int TCP_X3_WARPS = 4;
+constexpr int TCP_X3_BLOCK_N = 128;                    // stage = 2 x (16 KB + 16 KB): two stages in the ring
+__host__ __device__ constexpr int tcp_threads(bool x3) { return TCP_THREADS + (x3 ? TCP_X3_WARPS * 32 : 0); }
+__host__ __device__ constexpr int tcp_h_chunks(bool x3) { return x3 ? 4 : TCP_H_CHUNKS; }
 
 struct TcpScalars {  // per-problem scalars mirrored into shared memory once per CTA
   float* C;
@@ -113,9 +122,11 @@ __device__ __forceinline__ unsigned long long gtime() {
 
 // F16 = operands (and the dgrad's H input / dX output) are fp16 in HBM: kind::f16 MMAs, k-blocks of 64 elements (the
 // same 128-byte rows), MN-major operands in the plain 128-byte swizzle (64-element atoms, 8 KB TMA boxes).
-template <int MODE, bool F16>
-__global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(const __grid_constant__ TcBatch batch,
-                                                                            const int n_problems) {
+template <int MODE, bool F16, bool X3 = false>
+__global__ void __launch_bounds__(tcp_threads(X3), 1) tc_gemm_persistent_kernel(const __grid_constant__ TcBatch batch,
+                                                                                const int n_problems) {
+  static_assert(!(F16 && X3), "3xTF32 is an fp32-operand mode");
+  constexpr int HCH = tcp_h_chunks(X3);        // dgrad: H chunk buffers in the ring
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr bool A_MN = MODE == TC_WGRAD;
   constexpr bool B_MN = MODE != TC_FWD;
@@ -133,13 +144,15 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
   int max_bn = 16;
   for (int i = 0; i < n_problems; ++i) max_bn = max(max_bn, batch.p[i].block_n);
   const uint32_t a_bytes = TC_BLOCK_M * TC_BLOCK_K * 4;
-  const uint32_t stage_bytes = a_bytes + (uint32_t)max_bn * TC_BLOCK_K * 4;
-  int stages = tcp_ring_budget(MODE, F16) / stage_bytes;
+  const uint32_t raw_bytes = a_bytes + (uint32_t)max_bn * TC_BLOCK_K * 4;   // operands as TMA delivers them
+  const uint32_t stage_bytes = X3 ? 2u * raw_bytes : raw_bytes;             // X3: + the lo = x - tf32(x) copies behind them
+  int stages = tcp_ring_budget(MODE, F16, X3) / stage_bytes;
   stages = stages > TCP_MAX_STAGES ? TCP_MAX_STAGES : stages;
   uint8_t* const staging = ring + (size_t)stages * stage_bytes;  // 1024-byte aligned (stage_bytes is a multiple of 2048)
-  uint64_t* const full_bar = (uint64_t*)(staging + tcp_staging_bytes(MODE, F16));
+  uint64_t* const full_bar = (uint64_t*)(staging + tcp_staging_bytes(MODE, F16, X3));
   uint64_t* const empty_bar = full_bar + TCP_MAX_STAGES;
-  uint64_t* const tmem_full = empty_bar + TCP_MAX_STAGES;   // [2]
+  uint64_t* const conv_bar = empty_bar + TCP_MAX_STAGES;    // X3: lo copies of the stage written
+  uint64_t* const tmem_full = conv_bar + TCP_MAX_STAGES;    // [2]
   uint64_t* const tmem_empty = tmem_full + 2;               // [2]
   uint64_t* const h_full = tmem_empty + 2;                  // [TCP_H_CHUNKS]  (dgrad)
   uint64_t* const h_empty = h_full + TCP_H_CHUNKS;          // [TCP_H_CHUNKS]
@@ -168,12 +181,13 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], MODE == TC_WGRAD ? 5 : 1);  // MMA commit (+ the 4 reducer warps in wgrad)
+      mbar_init(&conv_bar[s], TCP_X3_WARPS);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], TCP_EPI_WARPS);
     }
-    for (int w = 0; w < TCP_H_CHUNKS; ++w) {
+    for (int w = 0; w < HCH; ++w) {
       mbar_init(&h_full[w], 1);
       mbar_init(&h_empty[w], 4);  // the four row-group warps that consume a chunk
     }
@@ -259,7 +273,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
       tcgen05_fence_after();
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int s = it % stages;
-        mbar_wait(&full_bar[s], (it / stages) & 1);
+        mbar_wait(X3 ? &conv_bar[s] : &full_bar[s], (it / stages) & 1);
         if (it == 0 && lane == 0) TRACE(3);
         tcgen05_fence_after();
         if (elect_one()) {
@@ -271,8 +285,20 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
                                      : make_smem_desc(sa + k * 32, 16, 1024, kLayoutSw128);
             const uint64_t db = B_MN ? make_smem_desc(sb + k * MN_KADV, MN_BOX, MN_SBO, MN_LAYOUT)
                                      : make_smem_desc(sb + k * 32, 16, 1024, kLayoutSw128);
-            if (F16) umma_f16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            else umma_tf32(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if constexpr (X3) {
+              // small terms first: A_lo B_hi + A_hi B_lo, then the leading product
+              const uint64_t da_lo = A_MN ? make_smem_desc(sa + raw_bytes + k * MN_KADV, MN_BOX, MN_SBO, MN_LAYOUT)
+                                          : make_smem_desc(sa + raw_bytes + k * 32, 16, 1024, kLayoutSw128);
+              const uint64_t db_lo = B_MN ? make_smem_desc(sb + raw_bytes + k * MN_KADV, MN_BOX, MN_SBO, MN_LAYOUT)
+                                          : make_smem_desc(sb + raw_bytes + k * 32, 16, 1024, kLayoutSw128);
+              umma_tf32(d_tmem, da_lo, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              umma_tf32(d_tmem, da, db_lo, idesc, 1u);
+              umma_tf32(d_tmem, da, db, idesc, 1u);
+            } else if (F16) {
+              umma_f16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            } else {
+              umma_tf32(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
           }
         }
         __syncwarp();
@@ -289,7 +315,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
     const int ew = warp - 2;
     const int q = warp & 3;      // TMEM sub-partition
     const int half = ew >> 2;    // chunk parity handled by this warp
-    constexpr int SLOTS = tcp_staging_slots(MODE, F16);
+    constexpr int SLOTS = tcp_staging_slots(MODE, F16, X3);
     uint8_t* const slot_base = staging + (size_t)ew * SLOTS * 4096;   // fwd / wgrad staging slots of this warp
     const uint32_t sw = (uint32_t)(lane & 7);
     int j = 0;
@@ -327,10 +353,10 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[as])) : "memory");
           }
           const int g = gbase + c;
-          const int hs = g % TCP_H_CHUNKS;
+          const int hs = g % HCH;
           uint8_t* const blk = staging + (size_t)hs * 16384 + q * 4096;
           uint8_t* const my_row = blk + lane * 128;
-          mbar_wait(&h_full[hs], (uint32_t)(g / TCP_H_CHUNKS) & 1u);
+          mbar_wait(&h_full[hs], (uint32_t)(g / HCH) & 1u);
           // branch-free inner loop per activation (the act code is uniform: hoisted out of the 64-element loop)
           auto scale_chunk = [&](auto grad) {
 #pragma unroll
@@ -388,10 +414,10 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
         if (MODE == TC_DGRAD) {
           // H chunk (128 rows x 32 cols, 128-byte swizzle) streamed in by warp 10; this warp owns rows [32q, 32q+32)
           const int g = gbase + c;
-          const int hs = g % TCP_H_CHUNKS;
+          const int hs = g % HCH;
           uint8_t* const blk = staging + (size_t)hs * 16384 + q * 4096;
           uint8_t* const my_row = blk + lane * 128;
-          mbar_wait(&h_full[hs], (uint32_t)(g / TCP_H_CHUNKS) & 1u);
+          mbar_wait(&h_full[hs], (uint32_t)(g / HCH) & 1u);
           auto scale_chunk = [&](auto grad) {  // act code is uniform: one branch per chunk, none per element
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
@@ -497,6 +523,39 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     tcgen05_fence_before();
+  } else if (X3 && warp >= TCP_THREADS / 32) {
+    // ===================================================================== 3xTF32 converter warps
+    // lo = x - (x & 0xffffe000) for every 16-byte chunk of the staged A and B tiles (element-wise: the swizzled
+    // layouts of the raw tiles and of their lo copies are identical)
+    const int ct = (warp - TCP_THREADS / 32) * 32 + lane;   // 0 .. 127
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int pi, split, tm, tn;
+      decode(t, pi, split, tm, tn);
+      const int kb0 = split * sp[pi].kb_per_split;
+      const int kb1 = min(sp[pi].num_kb, kb0 + sp[pi].kb_per_split);
+      const int chunks = (int)(a_bytes >> 4) + sp[pi].block_n * 8;   // 16-byte chunks of A (16 KB) + B (block_n x 128 B)
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const int s = it % stages;
+        mbar_wait(&full_bar[s], (it / stages) & 1);
+        const uint4* const src = (const uint4*)(ring + (size_t)s * stage_bytes);
+        uint4* const dst = (uint4*)(ring + (size_t)s * stage_bytes + raw_bytes);
+#pragma unroll 4
+        for (int c = ct; c < chunks; c += TCP_X3_WARPS * 32) {
+          const uint4 v = src[c];
+          uint4 o;
+          // lo = x - hi is exact; it is rounded to NEAREST tf32 here (the MMA would truncate it: a coherent bias)
+          o.x = (__float_as_uint(__uint_as_float(v.x) - __uint_as_float(v.x & 0xffffe000u)) + 0x1000u) & 0xffffe000u;
+          o.y = (__float_as_uint(__uint_as_float(v.y) - __uint_as_float(v.y & 0xffffe000u)) + 0x1000u) & 0xffffe000u;
+          o.z = (__float_as_uint(__uint_as_float(v.z) - __uint_as_float(v.z & 0xffffe000u)) + 0x1000u) & 0xffffe000u;
+          o.w = (__float_as_uint(__uint_as_float(v.w) - __uint_as_float(v.w & 0xffffe000u)) + 0x1000u) & 0xffffe000u;
+          dst[c] = o;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&conv_bar[s])) : "memory");
+      }
+    }
   } else if (MODE == TC_DGRAD) {
     // ===================================================================== H producer (dgrad), warp 10
     if (warp == 2 + TCP_EPI_WARPS && elect_one()) {
@@ -509,8 +568,8 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
         const int m0 = tm * TC_BLOCK_M, n0 = tn * block_n;
         const int nchunks = (block_n + CH - 1) / CH;
         for (int c = 0; c < nchunks; ++c, ++g) {
-          const int hs = g % TCP_H_CHUNKS;
-          mbar_wait(&h_empty[hs], ((uint32_t)(g / TCP_H_CHUNKS) & 1u) ^ 1u);
+          const int hs = g % HCH;
+          mbar_wait(&h_empty[hs], ((uint32_t)(g / HCH) & 1u) ^ 1u);
           mbar_expect_tx(&h_full[hs], 16384u);
           tma_load_2d(staging + (size_t)hs * 16384, map_h, &h_full[hs], n0 + c * CH, m0);  // box {CH cols, 128 rows}
         }
@@ -683,11 +742,11 @@ int tc_num_sms() {
   return n;
 }
 
-template <int MODE, bool F16 = false>
+template <int MODE, bool F16 = false, bool X3 = false>
 static int launch_tc_persistent(TcBatch& b, int n, cudaStream_t st, const char* what) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_gemm_persistent_kernel<MODE, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_persistent_kernel<MODE, F16, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          227 * 1024);
     if (e != cudaSuccess) {
       set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
@@ -701,28 +760,32 @@ static int launch_tc_persistent(TcBatch& b, int n, cudaStream_t st, const char* 
     if (b.p[i].block_n > max_bn) max_bn = b.p[i].block_n;
   }
   if (total == 0) return 0;
-  const size_t stage = (size_t)(TC_BLOCK_M + max_bn) * TC_BLOCK_K * 4;
-  size_t stages = tcp_ring_budget(MODE, F16) / stage;
+  const size_t stage = (size_t)(TC_BLOCK_M + max_bn) * TC_BLOCK_K * 4 * (X3 ? 2 : 1);
+  size_t stages = tcp_ring_budget(MODE, F16, X3) / stage;
   if (stages > TCP_MAX_STAGES) stages = TCP_MAX_STAGES;
-  const size_t smem = stages * stage + tcp_staging_bytes(MODE, F16) +
-                      (2 * TCP_MAX_STAGES + 4 + 2 * TCP_H_CHUNKS) * 8 + 16 + TC_MAX_PROBLEMS * sizeof(TcpScalars) +
+  if (stages < 2) {
+    set_error("%s: tile too wide for the operand ring", what);
+    return 1;
+  }
+  const size_t smem = stages * stage + tcp_staging_bytes(MODE, F16, X3) +
+                      (3 * TCP_MAX_STAGES + 4 + 2 * TCP_H_CHUNKS) * 8 + 16 + TC_MAX_PROBLEMS * sizeof(TcpScalars) +
                       TCP_EPI_WARPS * 128 + 1024;
   const int grid = total < num_sms() ? total : num_sms();
-  launch_chain_kernel(tc_gemm_persistent_kernel<MODE, F16>, dim3(grid), dim3(TCP_THREADS), smem, st, b, n);
+  launch_chain_kernel(tc_gemm_persistent_kernel<MODE, F16, X3>, dim3(grid), dim3(tcp_threads(X3)), smem, st, b, n);
   return finish_launch(what);
 }
 
-template <int MODE, bool F16 = false>
+template <int MODE, bool F16 = false, bool X3 = false>
 static int launch_tc(TcBatch& b, int n, cudaStream_t st, const char* what) {
   for (int i = 0; i < n; ++i)
     if (b.p[i].out_scale == 0.f) b.p[i].out_scale = 1.f;
-  return launch_tc_persistent<MODE, F16>(b, n, st, what);
+  return launch_tc_persistent<MODE, F16, X3>(b, n, st, what);
 }
 
 // Each tc_* entry returns 0 on success, 1 on error, and -1 if a problem cannot be described to TMA
 // (caller falls back to the fp32 kernel for the whole group).
-int tc_linear_forward(int n, const rslrl_linear_fwd_t* pr, cudaStream_t st) {
-  const char* what = "rslrl_linear_forward(tf32)";
+int tc_linear_forward(int n, const rslrl_linear_fwd_t* pr, cudaStream_t st, bool x3) {
+  const char* what = x3 ? "rslrl_linear_forward(tf32x3)" : "rslrl_linear_forward(tf32)";
   if (n > 2) return -1;
   TcBatch b{};
   for (int i = 0; i < n; ++i) {
@@ -730,8 +793,9 @@ int tc_linear_forward(int n, const rslrl_linear_fwd_t* pr, cudaStream_t st) {
     if (!tma_ok(q.x, q.ldx) || !tma_ok(q.w, q.K)) return -1;
     TcProblem& P = b.p[i];
     P.block_n = pick_block_n(q.N);
-    if (!make_map(&P.map_a, q.x, q.M, q.K, q.ldx, TC_BLOCK_K, TC_BLOCK_M, false) ||
-        !make_map(&P.map_b, q.w, q.N, q.K, q.K, TC_BLOCK_K, P.block_n, false)) {
+    if (x3 && P.block_n > TCP_X3_BLOCK_N) P.block_n = TCP_X3_BLOCK_N;
+    if (!make_map(&P.map_a, q.x, q.M, q.K, q.ldx, TC_BLOCK_K, TC_BLOCK_M, false, !x3) ||
+        !make_map(&P.map_b, q.w, q.N, q.K, q.K, TC_BLOCK_K, P.block_n, false, !x3)) {
       set_error("%s: cuTensorMapEncodeTiled failed", what);
       return 1;
     }
@@ -742,11 +806,11 @@ int tc_linear_forward(int n, const rslrl_linear_fwd_t* pr, cudaStream_t st) {
     P.num_kb = (q.K + TC_BLOCK_K - 1) / TC_BLOCK_K;
     P.splits = 1; P.kb_per_split = P.num_kb;
   }
-  return launch_tc<TC_FWD>(b, n, st, what);
+  return x3 ? launch_tc<TC_FWD, false, true>(b, n, st, what) : launch_tc<TC_FWD>(b, n, st, what);
 }
 
-int tc_linear_backward_data(int n, const rslrl_linear_bwd_data_t* pr, cudaStream_t st) {
-  const char* what = "rslrl_linear_backward_data(tf32)";
+int tc_linear_backward_data(int n, const rslrl_linear_bwd_data_t* pr, cudaStream_t st, bool x3) {
+  const char* what = x3 ? "rslrl_linear_backward_data(tf32x3)" : "rslrl_linear_backward_data(tf32)";
   if (n > 2) return -1;
   TcBatch b{};
   for (int i = 0; i < n; ++i) {
@@ -754,10 +818,11 @@ int tc_linear_backward_data(int n, const rslrl_linear_bwd_data_t* pr, cudaStream
     // dX[M,K] = dY[M,N] W[N,K]: reduction N; B = W is MN-major (K contiguous) -> K must be whole 32-atoms
     if (!tma_ok(q.dy, q.ldy) || !tma_ok(q.w, q.K) || (q.K % 32) != 0) return -1;
     TcProblem& P = b.p[i];
-    P.block_n = q.K >= max_block_n() ? max_block_n() : q.K;
+    const int bn_cap = x3 ? TCP_X3_BLOCK_N : max_block_n();
+    P.block_n = q.K >= bn_cap ? bn_cap : q.K;
     if (q.K % P.block_n != 0) return -1;
-    if (!make_map(&P.map_a, (const float*)q.dy, q.M, q.N, q.ldy, TC_BLOCK_K, TC_BLOCK_M, false) ||
-        !make_map(&P.map_b, (const float*)q.w, q.N, q.K, q.K, 32, TC_BLOCK_K, true)) {
+    if (!make_map(&P.map_a, (const float*)q.dy, q.M, q.N, q.ldy, TC_BLOCK_K, TC_BLOCK_M, false, !x3) ||
+        !make_map(&P.map_b, (const float*)q.w, q.N, q.K, q.K, 32, TC_BLOCK_K, true, !x3)) {
       set_error("%s: cuTensorMapEncodeTiled failed", what);
       return 1;
     }
@@ -775,15 +840,15 @@ int tc_linear_backward_data(int n, const rslrl_linear_bwd_data_t* pr, cudaStream
     P.num_kb = (q.N + TC_BLOCK_K - 1) / TC_BLOCK_K;
     P.splits = 1; P.kb_per_split = P.num_kb;
   }
-  const int rc = launch_tc<TC_DGRAD>(b, n, st, what);
+  const int rc = x3 ? launch_tc<TC_DGRAD, false, true>(b, n, st, what) : launch_tc<TC_DGRAD>(b, n, st, what);
   if (rc) return rc;
   for (int i = 0; i < n; ++i)  // optional fused-API output: bias gradient of the previous layer
     if (pr[i].db_prev && colsum_accumulate((const float*)pr[i].dx, pr[i].M, pr[i].K, pr[i].ldx, pr[i].db_prev, st)) return 1;
   return 0;
 }
 
-int tc_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* pr, cudaStream_t st) {
-  const char* what = "rslrl_linear_backward_weight(tf32)";
+int tc_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* pr, cudaStream_t st, bool x3) {
+  const char* what = x3 ? "rslrl_linear_backward_weight(tf32x3)" : "rslrl_linear_backward_weight(tf32)";
   if (n > 2) return -1;
   TcBatch b{};
   int tiles_all = 0;
@@ -794,6 +859,7 @@ int tc_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* pr, cudaSt
     TcProblem& P = b.p[i];
     P.block_n = pick_block_n(q.K);
     if (P.block_n < 32) P.block_n = 32;
+    if (x3 && P.block_n > TCP_X3_BLOCK_N) P.block_n = TCP_X3_BLOCK_N;
     P.tiles_m = (q.N + TC_BLOCK_M - 1) / TC_BLOCK_M;
     P.tiles_n = (q.K + P.block_n - 1) / P.block_n;
     tiles_all += P.tiles_m * P.tiles_n;
@@ -801,8 +867,8 @@ int tc_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* pr, cudaSt
   for (int i = 0; i < n; ++i) {
     const rslrl_linear_bwd_weight_t& q = pr[i];
     TcProblem& P = b.p[i];
-    if (!make_map(&P.map_a, (const float*)q.dy, q.M, q.N, q.ldy, 32, TC_BLOCK_K, true) ||
-        !make_map(&P.map_b, (const float*)q.x, q.M, q.K, q.ldx, 32, TC_BLOCK_K, true)) {
+    if (!make_map(&P.map_a, (const float*)q.dy, q.M, q.N, q.ldy, 32, TC_BLOCK_K, true, !x3) ||
+        !make_map(&P.map_b, (const float*)q.x, q.M, q.K, q.ldx, 32, TC_BLOCK_K, true, !x3)) {
       set_error("%s: cuTensorMapEncodeTiled failed", what);
       return 1;
     }
@@ -817,7 +883,7 @@ int tc_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* pr, cudaSt
     P.kb_per_split = (P.num_kb + want - 1) / want;
     P.splits = (P.num_kb + P.kb_per_split - 1) / P.kb_per_split;
   }
-  return launch_tc<TC_WGRAD>(b, n, st, what);
+  return x3 ? launch_tc<TC_WGRAD, false, true>(b, n, st, what) : launch_tc<TC_WGRAD>(b, n, st, what);
 }
 
 // ---- fp16-storage variants (RSLRL_PREC_FP16): same kernel, F16 = true.  -1 = shape not eligible (no fallback: the

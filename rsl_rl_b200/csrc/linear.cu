@@ -1,15 +1,15 @@
 // C-ABI entry points for the dense layers: dispatch on the arithmetic mode only (one device target,
-// no fallbacks).  fp32 -> gemm_simt.cu, tf32 -> gemm_tc.cu (tcgen05 / TMEM / TMA).
+// no fallbacks).  fp32 -> gemm_simt.cu, tf32 / tf32x3 (3xTF32, fp32-class) -> gemm_tc.cu (tcgen05 / TMEM / TMA).
 #include "common.cuh"
 
 namespace rslrl {
 int simt_linear_forward(int n, const rslrl_linear_fwd_t* pr, cudaStream_t st);
 int simt_linear_backward_data(int n, const rslrl_linear_bwd_data_t* pr, cudaStream_t st);
 int simt_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* pr, cudaStream_t st);
-int tc_linear_forward(int n, const rslrl_linear_fwd_t* pr, cudaStream_t st);
+int tc_linear_forward(int n, const rslrl_linear_fwd_t* pr, cudaStream_t st, bool x3 = false);
 int head_linear_backward(int n, const rslrl_linear_bwd_head_t* pr, cudaStream_t st);
-int tc_linear_backward_data(int n, const rslrl_linear_bwd_data_t* pr, cudaStream_t st);
-int tc_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* pr, cudaStream_t st);
+int tc_linear_backward_data(int n, const rslrl_linear_bwd_data_t* pr, cudaStream_t st, bool x3 = false);
+int tc_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* pr, cudaStream_t st, bool x3 = false);
 int tc16_linear_backward_data(int n, const rslrl_linear_bwd_data_t* pr, cudaStream_t st);
 int tc16_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* pr, cudaStream_t st);
 }  // namespace rslrl
@@ -25,8 +25,8 @@ int rslrl_linear_forward(int n, const rslrl_linear_fwd_t* probs_host, int precis
     RSLRL_CHECK_ARG(p.x && p.w && p.y && p.M > 0 && p.N > 0 && p.K > 0 && p.ldx >= p.K && p.ldy >= p.N, what);
   }
   if (precision == RSLRL_PREC_FP32) return simt_linear_forward(n, probs_host, (cudaStream_t)stream);
-  if (precision == RSLRL_PREC_TF32) {
-    const int rc = tc_linear_forward(n, probs_host, (cudaStream_t)stream);
+  if (precision == RSLRL_PREC_TF32 || precision == RSLRL_PREC_TF32X3) {
+    const int rc = tc_linear_forward(n, probs_host, (cudaStream_t)stream, precision == RSLRL_PREC_TF32X3);
     // -1: an operand cannot be described to TMA (row pitch not a multiple of 16 bytes) -> exact fp32 kernel
     return rc >= 0 ? rc : simt_linear_forward(n, probs_host, (cudaStream_t)stream);
   }
@@ -45,8 +45,8 @@ int rslrl_linear_backward_data(int n, const rslrl_linear_bwd_data_t* probs_host,
     RSLRL_CHECK_ARG(p.act == RSLRL_ACT_IDENTITY || (p.h && p.ldh >= p.K), what);
   }
   if (precision == RSLRL_PREC_FP32) return simt_linear_backward_data(n, probs_host, (cudaStream_t)stream);
-  if (precision == RSLRL_PREC_TF32) {
-    const int rc = tc_linear_backward_data(n, probs_host, (cudaStream_t)stream);
+  if (precision == RSLRL_PREC_TF32 || precision == RSLRL_PREC_TF32X3) {
+    const int rc = tc_linear_backward_data(n, probs_host, (cudaStream_t)stream, precision == RSLRL_PREC_TF32X3);
     return rc >= 0 ? rc : simt_linear_backward_data(n, probs_host, (cudaStream_t)stream);
   }
   if (precision == RSLRL_PREC_FP16) {
@@ -73,8 +73,8 @@ int rslrl_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* probs_h
     RSLRL_CHECK_ARG(p.scale_dev == nullptr || precision == RSLRL_PREC_FP16, what);  // dynamic scale: fp16 chain only
   }
   if (precision == RSLRL_PREC_FP32) return simt_linear_backward_weight(n, probs_host, (cudaStream_t)stream);
-  if (precision == RSLRL_PREC_TF32) {
-    const int rc = tc_linear_backward_weight(n, probs_host, (cudaStream_t)stream);
+  if (precision == RSLRL_PREC_TF32 || precision == RSLRL_PREC_TF32X3) {
+    const int rc = tc_linear_backward_weight(n, probs_host, (cudaStream_t)stream, precision == RSLRL_PREC_TF32X3);
     if (rc < 0) return simt_linear_backward_weight(n, probs_host, (cudaStream_t)stream);
     return rc;
   }

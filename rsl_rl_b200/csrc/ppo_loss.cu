@@ -22,11 +22,29 @@ constexpr int kMaxActions = 64;
 constexpr float kLogSqrt2Pi = 0.91893853320467274178f;   // log(sqrt(2 pi))
 constexpr float kEntropyConst = 1.41893853320467274178f;  // 0.5 + 0.5 log(2 pi)
 
+// Block partials are added into one of kLossSlots slot sets (slot = blockIdx.x % kLossSlots) instead of one set of
+// addresses: same-address fp64 atomics serialise in L2 (~27 clk each), which at 3 000 - 6 000 blocks (C3 minibatch)
+// was most of the kernel's time; the last block sums the slots in index order.
+constexpr int kLossSlots = 64;
+constexpr int kLossAcc = 4 + 2 * kMaxActions;   // kl, surrogate, value loss, sum(dvalue), dstd[A], sum_rows(dmu)[A]
 struct LossWorkspace {
-  double acc[4 + 2 * kMaxActions];  // kl, surrogate, value loss, sum(dvalue), dstd[A], sum_rows(dmu)[A]
+  double acc[kLossSlots * kLossAcc];
   unsigned int ticket;
   unsigned int pad_;
 };
+
+// last block, all threads: totals over the slots (fixed order) -> s_tot[kLossAcc], slots cleared for the next launch
+__device__ __forceinline__ void loss_collect_slots(LossWorkspace* ws, double* s_tot) {
+  for (int t = threadIdx.x; t < kLossAcc; t += blockDim.x) {
+    double a = 0.0;
+    for (int sl = 0; sl < kLossSlots; ++sl) {
+      a += __ldcg(&ws->acc[sl * kLossAcc + t]);
+      ws->acc[sl * kLossAcc + t] = 0.0;
+    }
+    s_tot[t] = a;
+  }
+  __syncthreads();
+}
 
 struct SumWorkspace {
   double acc[2];
@@ -125,6 +143,7 @@ ppo_loss_kernel(const float* __restrict__ mu, const float* __restrict__ std_para
   __shared__ double s_red[4 * 32];
   __shared__ float s_dstd[kMaxActions], s_dbmu[kMaxActions];
   __shared__ bool s_last;
+  __shared__ double s_tot[kLossAcc];
   if (threadIdx.x < A) {
     const float p = std_param[threadIdx.x];
     const float s = std_type == RSLRL_STD_LOG ? expf(p) : p;
@@ -276,16 +295,17 @@ ppo_loss_kernel(const float* __restrict__ mu, const float* __restrict__ std_para
   double red[4] = {(double)kl, (double)surr, (double)vl, (double)dv_sum};
   block_sum<4>(red, s_red);   // (its barriers also order the shared-memory maximum)
   loss_scale_block_publish(scale_state, &s_gmax);
+  double* const slot = ws->acc + (size_t)(blockIdx.x & (kLossSlots - 1)) * kLossAcc;
   if (threadIdx.x == 0) {
-    atomicAdd(&ws->acc[0], red[0]);
-    atomicAdd(&ws->acc[1], red[1]);
-    atomicAdd(&ws->acc[2], red[2]);
-    atomicAdd(&ws->acc[3], red[3]);
+    atomicAdd(&slot[0], red[0]);
+    atomicAdd(&slot[1], red[1]);
+    atomicAdd(&slot[2], red[2]);
+    atomicAdd(&slot[3], red[3]);
   }
   __syncthreads();
   if (threadIdx.x < A) {
-    atomicAdd(&ws->acc[4 + threadIdx.x], (double)s_dstd[threadIdx.x]);
-    if (db_mu != nullptr) atomicAdd(&ws->acc[4 + kMaxActions + threadIdx.x], (double)s_dbmu[threadIdx.x]);
+    atomicAdd(&slot[4 + threadIdx.x], (double)s_dstd[threadIdx.x]);
+    if (db_mu != nullptr) atomicAdd(&slot[4 + kMaxActions + threadIdx.x], (double)s_dbmu[threadIdx.x]);
   }
   __threadfence();
   __syncthreads();
@@ -294,32 +314,28 @@ ppo_loss_kernel(const float* __restrict__ mu, const float* __restrict__ std_para
   if (!s_last) return;
   __threadfence();
   // ---- last block: publish and clear
+  loss_collect_slots(ws, s_tot);
   if (threadIdx.x < A) {
     const int a = threadIdx.x;
     const float s = s_sigma[a];
     // entropy bonus -c_e * mean_i sum_a log sigma_a  ->  d/dsigma_a = -c_e / sigma_a (x sigma for log-std)
-    double gsum = *((volatile double*)&ws->acc[4 + a]);
+    double gsum = s_tot[4 + a];
     if (std_type == RSLRL_STD_LOG) gsum = gsum * (double)s - (double)c_e;
     else gsum = gsum - (double)c_e / (double)s;
     dstd[a] += (float)gsum;
-    ws->acc[4 + a] = 0.0;
-    if (db_mu != nullptr) {
-      db_mu[a] += (float)*((volatile double*)&ws->acc[4 + kMaxActions + a]);
-      ws->acc[4 + kMaxActions + a] = 0.0;
-    }
+    if (db_mu != nullptr) db_mu[a] += (float)s_tot[4 + kMaxActions + a];
   }
   if (threadIdx.x == 0) {
-    const double klm = *((volatile double*)&ws->acc[0]) / (double)mb_orig;
+    const double klm = s_tot[0] / (double)mb_orig;
     if (kl_out) *kl_out = (float)klm;
-    if (db_value) *db_value += (float)*((volatile double*)&ws->acc[3]);
+    if (db_value) *db_value += (float)s_tot[3];
     float ent = 0.f;
     for (int a = 0; a < A; ++a) ent += kEntropyConst + s_logs[a];
     if (loss_sums) {
-      loss_sums[0] += *((volatile double*)&ws->acc[1]) / (double)rows;
-      loss_sums[1] += *((volatile double*)&ws->acc[2]) / (double)rows;
+      loss_sums[0] += s_tot[1] / (double)rows;
+      loss_sums[1] += s_tot[2] / (double)rows;
       loss_sums[2] += (double)ent;
     }
-    ws->acc[0] = ws->acc[1] = ws->acc[2] = ws->acc[3] = 0.0;
     loss_scale_finalize(scale_state, scale16);
     __threadfence();
     ws->ticket = 0u;
@@ -385,6 +401,7 @@ ppo_loss_quad_kernel(const float* __restrict__ mu, const float* __restrict__ std
   __shared__ double s_red[4 * 32];
   __shared__ float s_dstd[kMaxActions], s_dbmu[kMaxActions];
   __shared__ bool s_last;
+  __shared__ double s_tot[kLossAcc];
   if (threadIdx.x < A) {
     const float p = std_param[threadIdx.x];
     const float s = std_type == RSLRL_STD_LOG ? expf(p) : p;
@@ -594,16 +611,17 @@ ppo_loss_quad_kernel(const float* __restrict__ mu, const float* __restrict__ std
   double red[4] = {(double)kl, (double)surr, (double)vl, (double)dv_sum};
   block_sum<4>(red, s_red);   // (its barriers also order the shared-memory maximum)
   loss_scale_block_publish(scale_state, &s_gmax);
+  double* const slot = ws->acc + (size_t)(blockIdx.x & (kLossSlots - 1)) * kLossAcc;
   if (threadIdx.x == 0) {
-    atomicAdd(&ws->acc[0], red[0]);
-    atomicAdd(&ws->acc[1], red[1]);
-    atomicAdd(&ws->acc[2], red[2]);
-    atomicAdd(&ws->acc[3], red[3]);
+    atomicAdd(&slot[0], red[0]);
+    atomicAdd(&slot[1], red[1]);
+    atomicAdd(&slot[2], red[2]);
+    atomicAdd(&slot[3], red[3]);
   }
   __syncthreads();
   if (threadIdx.x < A) {
-    atomicAdd(&ws->acc[4 + threadIdx.x], (double)s_dstd[threadIdx.x]);
-    if (db_mu != nullptr) atomicAdd(&ws->acc[4 + kMaxActions + threadIdx.x], (double)s_dbmu[threadIdx.x]);
+    atomicAdd(&slot[4 + threadIdx.x], (double)s_dstd[threadIdx.x]);
+    if (db_mu != nullptr) atomicAdd(&slot[4 + kMaxActions + threadIdx.x], (double)s_dbmu[threadIdx.x]);
   }
   __threadfence();
   __syncthreads();
@@ -612,31 +630,28 @@ ppo_loss_quad_kernel(const float* __restrict__ mu, const float* __restrict__ std
   if (!s_last) return;
   __threadfence();
   // ---- last block: publish and clear (as in ppo_loss_kernel)
+  loss_collect_slots(ws, s_tot);
   if (threadIdx.x < A) {
     const int a = threadIdx.x;
     const float s = s_sigma[a];
-    double gsum = *((volatile double*)&ws->acc[4 + a]);
+    // entropy bonus -c_e * mean_i sum_a log sigma_a  ->  d/dsigma_a = -c_e / sigma_a (x sigma for log-std)
+    double gsum = s_tot[4 + a];
     if (std_type == RSLRL_STD_LOG) gsum = gsum * (double)s - (double)c_e;
     else gsum = gsum - (double)c_e / (double)s;
     dstd[a] += (float)gsum;
-    ws->acc[4 + a] = 0.0;
-    if (db_mu != nullptr) {
-      db_mu[a] += (float)*((volatile double*)&ws->acc[4 + kMaxActions + a]);
-      ws->acc[4 + kMaxActions + a] = 0.0;
-    }
+    if (db_mu != nullptr) db_mu[a] += (float)s_tot[4 + kMaxActions + a];
   }
   if (threadIdx.x == 0) {
-    const double klm = *((volatile double*)&ws->acc[0]) / (double)mb_orig;
+    const double klm = s_tot[0] / (double)mb_orig;
     if (kl_out) *kl_out = (float)klm;
-    if (db_value) *db_value += (float)*((volatile double*)&ws->acc[3]);
+    if (db_value) *db_value += (float)s_tot[3];
     float ent = 0.f;
     for (int a = 0; a < A; ++a) ent += kEntropyConst + s_logs[a];
     if (loss_sums) {
-      loss_sums[0] += *((volatile double*)&ws->acc[1]) / (double)rows;
-      loss_sums[1] += *((volatile double*)&ws->acc[2]) / (double)rows;
+      loss_sums[0] += s_tot[1] / (double)rows;
+      loss_sums[1] += s_tot[2] / (double)rows;
       loss_sums[2] += (double)ent;
     }
-    ws->acc[0] = ws->acc[1] = ws->acc[2] = ws->acc[3] = 0.0;
     loss_scale_finalize(scale_state, scale16);
     __threadfence();
     ws->ticket = 0u;
@@ -713,6 +728,10 @@ int rslrl_ppo_loss_fwd_bwd(const float* mu, const float* std_param, int std_type
   RSLRL_CHECK_ARG(dmu16 == nullptr || (dmu16_stride % 4 == 0 && ((uintptr_t)dmu16 & 7) == 0), what);
   // four threads per row while a thread per row could not fill the machine (measured at 393 216 rows: 58 us for the
   // row-per-thread kernel, 80 us for this one); beyond that the row-per-thread kernel
+  static const long long quad_max_rows = [] {
+    const char* e = getenv("RSLRL_LOSS_QUAD_MAX_ROWS");
+    return e ? atoll(e) : (long long)kNumSMs * 1024;
+  }();
   LossHead head{};
   if (head_host != nullptr && head_host->dz_actor != nullptr) {
     const rslrl_loss_head_t& h = *head_host;
@@ -727,7 +746,7 @@ int rslrl_ppo_loss_fwd_bwd(const float* mu, const float* std_param, int std_type
     head.w_a = h.w_actor; head.w_c = h.w_critic; head.h_a = (const __half*)h.h_actor; head.h_c = (const __half*)h.h_critic;
     head.dz_a = (__half*)h.dz_actor; head.dz_c = (__half*)h.dz_critic; head.K3 = h.K3; head.ldh = h.ldh; head.act = h.act;
   }
-  if (vec && A <= 16 && quad_ok && rows <= (long long)kNumSMs * 1024) {
+  if (vec && A <= 16 && quad_ok && rows <= quad_max_rows) {
     const int qblocks = (int)((rows + kQuadThreads / 4 - 1) / (kQuadThreads / 4));
     launch_chain_kernel(
         ppo_loss_quad_kernel, dim3(qblocks), dim3(kQuadThreads), 0, (cudaStream_t)stream, mu, std_param, std_type, value,

@@ -4,6 +4,8 @@ A frozen random `target` MLP and a trained `predictor` MLP embed the `rnd_state`
 intrinsic reward is the L2 distance of the embeddings times a (scheduled) weight."""
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -38,17 +40,62 @@ class RandomNetworkDistillation(nn.Module):
         self.target.eval()
 
     def get_intrinsic_reward(self, obs) -> torch.Tensor:
-        """Reference rnd.py:113-135 (the counter advances once per env step)."""
+        """Reference rnd.py:113-135 (the counter advances once per env step).  On CUDA the two embedding networks, the
+        gap, its norm and (without a reward normaliser) the weight are ONE launch (`rslrl_rnd_reward`)."""
         self.update_counter += 1
         state = self.state_normalizer(self.get_rnd_state(obs))
-        with torch.no_grad():
-            gap = self.target(state) - self.predictor(state)
-        reward = self.reward_normalizer(torch.linalg.norm(gap, dim=1))
         if self.weight_scheduler is not None:
             self.weight = self.weight_scheduler(step=self.update_counter, **self.weight_scheduler_params)
         else:
             self.weight = self.initial_weight
+        plain = isinstance(self.reward_normalizer, torch.nn.Identity)
+        norm = self._native_gap_norm(state, float(self.weight) if plain else 1.0)
+        if norm is not None:
+            return norm if plain else self.reward_normalizer(norm) * self.weight
+        with torch.no_grad():
+            gap = self.target(state) - self.predictor(state)
+        reward = self.reward_normalizer(torch.linalg.norm(gap, dim=1))
         return reward * self.weight
+
+    def _native_gap_norm(self, state: torch.Tensor, scale: float):
+        """scale * ||target(state) - predictor(state)||_2 per row in one launch, or None when the fused kernel does not
+        cover the networks (widths > 128, more than 4 layers, a tuple-shaped output, a last activation)."""
+        from .. import _native as nat
+        import ctypes
+
+        if not state.is_cuda or state.dim() != 2 or os.environ.get("RSLRL_RND_FUSED", "1") == "0":
+            return None
+        plan = getattr(self, "_reward_plan", None)
+        if plan is None:
+            structs = []
+            for mlp in (self.target, self.predictor):
+                if any(isinstance(m, nn.Unflatten) for m in mlp):
+                    structs = None
+                    break
+                layers, acts = mlp.linear_layers(), mlp.layer_activation_codes()
+                dims = [layers[0].in_features] + [l.out_features for l in layers]
+                if len(layers) > 4 or max(dims) > 128 or acts[-1] != 0:
+                    structs = None
+                    break
+                q = nat.RndNet()
+                for i, l in enumerate(layers):
+                    q.w[i], q.b[i], q.act[i] = l.weight.data_ptr(), (l.bias.data_ptr() if l.bias is not None else None), acts[i]
+                for i, d in enumerate(dims):
+                    q.dims[i] = d
+                q.num_layers = len(layers)
+                structs.append((q, [l.weight.data_ptr() for l in layers]))
+            plan = self._reward_plan = structs if structs is not None else False
+        if plan is False:
+            return None
+        for (q, ptrs), mlp in zip(plan, (self.target, self.predictor)):   # parameters re-bound (flat buffers, load_state_dict)
+            if ptrs != [l.weight.data_ptr() for l in mlp.linear_layers()]:
+                self._reward_plan = None
+                return self._native_gap_norm(state, scale)
+        x = nat.f32c(state.detach())
+        out = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+        nat.check(nat.lib().rslrl_rnd_reward(ctypes.byref(plan[0][0]), ctypes.byref(plan[1][0]), x.data_ptr(), x.stride(0),
+                                             x.shape[0], out.data_ptr(), scale, nat.stream_ptr()))
+        return out
 
     def forward(self, *args, **kwargs):
         raise RuntimeError("Forward method is not implemented. Use get_intrinsic_reward instead.")

@@ -171,7 +171,7 @@ def _lin_ref(x, w, b, act):
                                         (2048, 128, 12, "identity"), (2048, 128, 1, "identity"), (130, 5, 3, "tanh"),
                                         (24576, 256, 128, "elu"), (64, 16, 200, "selu"), (300, 33, 65, "sigmoid"),
                                         (300, 33, 65, "lrelu"), (300, 33, 65, "softplus")])
-@pytest.mark.parametrize("prec,tol", [("fp32", 1e-5), ("tf32", 1e-3)])
+@pytest.mark.parametrize("prec,tol", [("fp32", 1e-5), ("tf32", 1e-3), ("tf32x3", 1e-5)])
 def test_linear_forward(M, K, N, act, prec, tol):
     from rsl_rl_b200.networks.mlp import linear_forward
     nat = _nat()
@@ -183,7 +183,7 @@ def test_linear_forward(M, K, N, act, prec, tol):
     assert rel_err(y.cpu().numpy(), ref.cpu().numpy()) < tol
 
 
-@pytest.mark.parametrize("prec,tol", [("fp32", 1e-5), ("tf32", 1e-3)])
+@pytest.mark.parametrize("prec,tol", [("fp32", 1e-5), ("tf32", 1e-3), ("tf32x3", 1e-5)])
 def test_linear_forward_grouped_and_strided_input(prec, tol):
     from rsl_rl_b200.networks.mlp import linear_forward
     nat = _nat()
@@ -200,7 +200,7 @@ def test_linear_forward_grouped_and_strided_input(prec, tol):
 
 @pytest.mark.parametrize("M,K,N,act", [(1000, 512, 256, "elu"), (4096, 128, 12, "elu"), (3000, 128, 1, "relu"),
                                         (24576, 256, 128, "elu"), (513, 37, 5, "tanh"), (600, 48, 512, "identity")])
-@pytest.mark.parametrize("prec,tol", [("fp32", 1e-5), ("tf32", 1e-3)])
+@pytest.mark.parametrize("prec,tol", [("fp32", 1e-5), ("tf32", 1e-3), ("tf32x3", 1e-5)])
 def test_linear_backward(M, K, N, act, prec, tol):
     """dx = (dy W) * act'(h) (+ fused bias gradient of the previous layer), dW += dy^T x, db += colsum(dy)
     against an fp64 restatement."""
@@ -755,3 +755,30 @@ def test_native_lstm_group_of_two_matches_separate_calls():
     assert torch.equal(oa, oa2) and torch.equal(oc, oc2) and torch.equal(hna, hna2) and torch.equal(cnc, cnc2)
     for g, p in zip(grads, [p for r in (ra, rc) for p in r.parameters()]):
         assert rel_err(g.cpu().numpy(), p.grad.cpu().numpy()) < 1e-6
+
+
+@pytest.mark.parametrize("n,D,hidden,out,act", [(4096, 48, [48], 1, "elu"), (1000, 10, [64, 32], 8, "relu"), (33, 128, [128, 128, 7], 5, "tanh")])
+def test_rnd_reward_kernel_matches_torch(n, D, hidden, out, act):
+    """rslrl_rnd_reward (both embedding networks + gap + norm + weight in one launch) against the same expression on torch
+    modules in fp64 (reference rnd.py:113-135)."""
+    from rsl_rl_b200.modules.rnd import RandomNetworkDistillation
+    torch.manual_seed(n + D)
+    rnd = RandomNetworkDistillation(D, {"rnd_state": ["policy"]}, out, hidden, hidden, activation=act, weight=0.37, device=DEV)
+    x = torch.randn(n, D, device=DEV)
+    got = rnd._native_gap_norm(x, 0.37)
+    assert got is not None
+    f = {"elu": torch.nn.functional.elu, "relu": torch.relu, "tanh": torch.tanh}[act]
+
+    def run(mlp, h):
+        layers = mlp.linear_layers()
+        for i, l in enumerate(layers):
+            h = h @ l.weight.double().t() + l.bias.double()
+            if i < len(layers) - 1:
+                h = f(h)
+        return h
+
+    ref = 0.37 * torch.linalg.norm(run(rnd.target, x.double()) - run(rnd.predictor, x.double()), dim=1)
+    assert rel_err(got.cpu().numpy(), ref.cpu().numpy()) < 1e-5
+    obs = {"policy": x}
+    r2 = rnd.get_intrinsic_reward(obs)
+    assert torch.equal(r2, got)
