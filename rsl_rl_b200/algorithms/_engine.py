@@ -337,13 +337,18 @@ class FeedForwardEngine:
         arr = (nat.Mlp3Fwd * 2)(sa, sc)
         return _Mlp3Plan(arr, 2)
 
-    def backward(self, x_a: torch.Tensor, x_c: torch.Tensor, dmu: torch.Tensor, dvalue: torch.Tensor):
+    def backward(self, x_a: torch.Tensor, x_c: torch.Tensor, dmu: torch.Tensor, dvalue: torch.Tensor,
+                 dx_a: Optional[torch.Tensor] = None, dx_c: Optional[torch.Tensor] = None):
         """dL/dW, dL/db accumulated into the parameters' .grad views (flat gradient buffer).  fp16 mode: x_a / x_c are
-        the fp16 copies of the minibatch observations."""
+        the fp16 copies of the minibatch observations.  dx_a / dx_c ([M, K0], optional, not in fp16 mode): also the
+        gradient with respect to the networks' INPUTS (the outputs of a recurrent memory in front of the MLPs)."""
         if self.f16:
+            if dx_a is not None or dx_c is not None:
+                raise NotImplementedError("input gradients are not available on the fp16-storage chain")
             return self._backward16(x_a, x_c, dmu, dvalue)
         M = x_a.shape[0]
         nets = ((self.actor, self.h_a, self.g_a, x_a, dmu), (self.critic, self.h_c, self.g_c, x_c, dvalue))
+        dx_in = (dx_a, dx_c)
         dy = [dmu, dvalue]
         for k in range(max(self.actor.L, self.critic.L)):
             wprobs, dprobs, hprobs, new_dy = [], [], [], list(dy)
@@ -364,6 +369,9 @@ class FeedForwardEngine:
                     dx = gbuf[k % 2][:M * net.dims[l]].view(M, net.dims[l])
                     dprobs.append((dy[ni], lin.weight, inp, dx, net.acts[l - 1]))
                     new_dy[ni] = dx
+                elif dx_in[ni] is not None:
+                    # first layer: identity in front of it (the input tensor stands in for the saved activation)
+                    dprobs.append((dy[ni], lin.weight, inp, dx_in[ni], 0))
             if hprobs:
                 linear_backward_head(hprobs)
             if wprobs:

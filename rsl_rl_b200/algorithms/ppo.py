@@ -162,6 +162,8 @@ class PPO:
                     and isinstance(pol.critic_obs_normalizer, nn.Identity)):
                 self._obs_fast = (ga[0], None if gc[0] == ga[0] else gc[0])
         self._update_reason = "RND" if self.rnd is not None else ("symmetry" if self.symmetry is not None else None)
+        self._recurrent_fused = False
+        self._rc = None   # per-update cache of the fused recurrent path
         self._graph = None
         self._cgraph, self._cgraph_key, self._cgraph_failed, self._cgraph_launches = None, None, False, 0
         self._csums, self._cperm = None, None
@@ -195,8 +197,36 @@ class PPO:
             self.optimizer.one_launch = False
 
     # ------------------------------------------------------------------------------------------
+    def _recurrent_fusable(self) -> bool:
+        """ActorCriticRecurrent with native LSTM memories and the plain PPO objective: rollout and update run on the
+        fused engine (LSTM kernels + fused MLP forward / loss / hand-written backward), no autograd."""
+        from ..modules.actor_critic_recurrent import ActorCriticRecurrent
+        pol = self.policy
+        if type(pol) is not ActorCriticRecurrent or self.rnd is not None or self.symmetry is not None:
+            return False
+        if os.environ.get("RSLRL_RECURRENT_FUSED", "1") == "0" or pol.state_dependent_std:
+            return False
+        ma, mc = pol.memory_a, pol.memory_c
+        if not (ma.native and mc.native):
+            return False
+        ra, rc = ma.rnn, mc.rnn
+        if (ra.num_layers, ra.hidden_size, ra.bias) != (rc.num_layers, rc.hidden_size, rc.bias) or ra.hidden_size % 4:
+            return False
+        for mlp in (pol.actor, pol.critic):
+            if any(isinstance(m, nn.Unflatten) for m in mlp) or mlp.layer_activation_codes()[-1] != 0:
+                return False
+        return True
+
     def init_storage(self, training_type, num_envs, num_transitions_per_env, obs, actions_shape):
         self.storage = RolloutStorage(training_type, num_envs, num_transitions_per_env, obs, actions_shape, self.device)
+        if self._engine_reason is not None and self._recurrent_fusable() and num_envs % self.num_mini_batches == 0:
+            # recurrent policy: the engine drives the MLPs behind the memories (inputs = LSTM outputs)
+            rows = num_transitions_per_env * (num_envs // self.num_mini_batches)
+            precision = "tf32" if self.gemm_precision == "fp16" else self.gemm_precision
+            self._engine = _engine.FeedForwardEngine(self.policy, rows, num_envs, rows, self.device, precision, self._group)
+            self._update_reason = "recurrent"
+            self._recurrent_fused = True
+            self._last_values = torch.empty(num_envs, 1, dtype=torch.float32, device=self.device)
         if self._engine_reason is None:
             B = num_envs * num_transitions_per_env
             mb = B // self.num_mini_batches
@@ -243,7 +273,16 @@ class PPO:
         if s == 0 and eng.needs_refresh:
             eng.refresh_padded()  # parameters may have been loaded / modified since the last optimiser step
         fast = self._obs_fast
-        if fast is None:
+        if self._recurrent_fused:
+            # both memories advance one step together (native LSTM kernels); their outputs feed the fused MLP forward
+            from ..networks.memory import Memory
+            pol = self.policy
+            tr.hidden_states = pol.get_hidden_states()
+            o_a = pol.actor_obs_normalizer(pol.get_actor_obs(obs))
+            o_c = pol.critic_obs_normalizer(pol.get_critic_obs(obs))
+            out_a, out_c = Memory.forward_pair(pol.memory_a, pol.memory_c, o_a, o_c)
+            x_a, x_c = nat.f32c(out_a.squeeze(0)), nat.f32c(out_c.squeeze(0))
+        elif fast is None:
             x_a, x_c = self._inputs(obs)
         else:   # one observation group per set, no normaliser: the env's tensors are the network inputs
             x_a = obs[fast[0]]
@@ -364,6 +403,8 @@ class PPO:
             intrinsic = self.intrinsic_rewards
         time_outs = extras["time_outs"] if "time_outs" in extras else None
         if self.rollout_fused and tr.actions is not None and tr.actions.data_ptr() == self.storage.actions[self.storage.step].data_ptr():
+            if tr.hidden_states is not None:
+                self.storage._save_hidden_states(tr.hidden_states)
             self.storage._store_in_place(tr.observations, rewards, dones, time_outs, intrinsic, self.gamma)
         else:
             self.storage._store(tr, time_outs=time_outs, intrinsic=intrinsic, gamma=self.gamma)
@@ -372,7 +413,7 @@ class PPO:
 
     def compute_returns(self, obs):
         """Reference ppo.py:171-176."""
-        if self.rollout_fused:
+        if self.rollout_fused and not self._recurrent_fused:
             _, x_c = self._inputs(obs)
             last_values = self._last_values
             self._engine.forward(x_c, x_c, None, last_values, actor=False)
@@ -563,6 +604,8 @@ class PPO:
         torch.cuda.synchronize()
         self._graph, self._graph_key = None, None
         self._cgraph, self._cgraph_key = None, None
+        if self._rc is not None:
+            self._rc["graphs"] = None
         for plan in self._act_plans.values():
             plan["graph"] = None
             plan["visits"] = 0
@@ -814,6 +857,157 @@ class PPO:
         # loss accumulators of the fused kernel: [surrogate, value, entropy] -> the composite order
         sums[0:1].copy_(ds.loss_sums[1:2]); sums[1:2].copy_(ds.loss_sums[0:1]); sums[2:3].copy_(ds.loss_sums[2:3])
 
+    def _recurrent_minibatches_fused(self, sums):
+        """Minibatch loop of a recurrent policy on the engine, without autograd (reference ppo.py:199-395 with
+        rollout_storage.py:206-260): per minibatch (a block of env columns, all T steps) the padded trajectories go
+        through both LSTMs together (native forward with saved gates), the outputs are un-padded into the [T * envs, H]
+        input of the fused MLP forward, ONE loss launch, the hand-written MLP backward INCLUDING the gradient with respect
+        to the LSTM outputs, which is padded back and sent through the native backward-through-time; every weight
+        gradient accumulates straight into the flat gradient buffer; one fused optimiser step.  The trajectory index,
+        the padded observations, the hidden states at the trajectory starts and the per-sample tensors are built once per
+        update (recurrent minibatches are not shuffled)."""
+        from ..networks.lstm import _layers_backward, _layers_forward
+        from ..utils.utils import TrajectoryIndex
+        pol, st, opt, eng = self.policy, self.storage, self.optimizer, self._engine
+        M, E = self.num_mini_batches, self.num_learning_epochs
+        T, N = st.num_transitions_per_env, st.num_envs
+        mbN = N // M
+        rows = T * mbN
+        A = eng.A
+        f32 = dict(dtype=torch.float32, device=self.device)
+        TD = type(st.observations)
+        rnns = [pol.memory_a.rnn, pol.memory_c.rnn]
+        L, H, has_bias = rnns[0].num_layers, rnns[0].hidden_size, bool(rnns[0].bias)
+        prec = nat.PREC_CODES["tf32" if pol.memory_a.precision == "fp16" else pol.memory_a.precision]
+        index = TrajectoryIndex(st.dones)
+        offs = index.offsets_host()           # the one host read of the update
+        st._last_trajectory_index = index
+        flat = lambda x, w, a, b: x[:, a:b].reshape(rows, w).contiguous()
+        cached = []
+        for i in range(M):
+            a, b = i * mbN, (i + 1) * mbN
+            f, l = offs[a], offs[b]
+            obs_pad = TD({k: index.split_and_pad(st.observations[k], f, l) for k in st._obs_keys}, batch_size=[T, l - f],
+                         device=self.device)
+            x_a = nat.f32c(pol.actor_obs_normalizer(pol.get_actor_obs(obs_pad)))
+            x_c = nat.f32c(pol.critic_obs_normalizer(pol.get_critic_obs(obs_pad)))
+            hid = []
+            for saved in (st.saved_hidden_states_a, st.saved_hidden_states_c):
+                if saved is None:
+                    z = torch.zeros(L, l - f, H, **f32)
+                    hid.append((z, z))
+                else:
+                    hid.append(tuple(index.hidden_at_starts(s_, f, l) for s_ in saved))
+            cached.append(dict(a=a, b=b, f=f, l=l, x=(x_a, x_c), hid=hid,
+                               actions=flat(st.actions, A, a, b), logp=flat(st.actions_log_prob, 1, a, b).view(-1),
+                               adv=flat(st.advantages, 1, a, b).view(-1), ret=flat(st.returns, 1, a, b).view(-1),
+                               values=flat(st.values, 1, a, b).view(-1), mu=flat(st.mu, A, a, b),
+                               sigma=flat(st.sigma, A, a, b)))
+        ds = opt.dev_state
+        nat.check(nat.lib().rslrl_fill_zero(ds.loss_sums.data_ptr(), 24, nat.stream_ptr()))
+        sums.zero_()
+        self._group.zero_grad()
+        adaptive = self.desired_kl is not None and self.schedule == "adaptive"
+        hp = self._hyper()
+        rc = self._rc
+        if rc is None or rc["rows"] != rows:
+            rc = self._rc = dict(rows=rows, dxa=torch.empty(rows, H, **f32), dxc=torch.empty(rows, H, **f32),
+                                 db=[torch.zeros(4 * H, **f32) for _ in range(2)] if has_bias else [None, None])
+        par = lambda r, name, l_: getattr(r, f"{name}_l{l_}")
+        rc["updates"] = rc.get("updates", 0) + 1
+        # Every minibatch has static shapes within an update (its trajectory count is fixed once the rollout is known), so
+        # its ~150 launches (two C time loops of per-step projections + cells among them) are captured into ONE CUDA graph
+        # at the first epoch and replayed in the others; the graphs die with the update (the trajectory counts of the
+        # next rollout differ).  The first update of a run stays eager (lazy initialisations).
+        use_graph = (self.use_cuda_graph and not self.is_multi_gpu and E > 1 and rc["updates"] > 1
+                     and os.environ.get("RSLRL_RECURRENT_GRAPH", "1") != "0")
+        graphs = [None] * len(cached)
+
+        def minibatch(mb):
+                a, b, f, l = mb["a"], mb["b"], mb["f"], mb["l"]
+                # ---- both memories forward over the padded trajectories (all layers), gates saved
+                inps, saved_layers = list(mb["x"]), []
+                for l_ in range(L):
+                    res = _layers_forward(inps, [mb["hid"][g][0][l_] for g in range(2)], [mb["hid"][g][1][l_] for g in range(2)],
+                                          [par(r, "weight_ih", l_).detach() for r in rnns], [par(r, "weight_hh", l_).detach() for r in rnns],
+                                          [par(r, "bias_ih", l_).detach() if has_bias else None for r in rnns],
+                                          [par(r, "bias_hh", l_).detach() if has_bias else None for r in rnns], prec, save=True)
+                    saved_layers.append(res)
+                    inps = [r_[0][1:] for r_ in res]
+                xa = index.unpad(inps[0], a, b, f).view(rows, H)
+                xc = index.unpad(inps[1], a, b, f).view(rows, H)
+                mu, value = eng.mu[:rows], eng.value[:rows]
+                eng.forward(xa, xc, mu, value)
+                eng.loss(rows, rows, mu, value, mb["actions"], mb["logp"], mb["adv"], mb["ret"], mb["values"], mb["mu"],
+                         mb["sigma"], self._group.kl_slot, ds.loss_sums, hp, self.normalize_advantage_per_mini_batch)
+                eng.backward(xa, xc, eng.dmu[:rows], eng.dvalue[:rows], dx_a=rc["dxa"], dx_c=rc["dxc"])
+                # ---- gradients of the memory outputs back onto the padded trajectories, then backward through time
+                douts = [index.pad_columns(rc["dxa"].view(T, mbN, H), a, f, l), index.pad_columns(rc["dxc"].view(T, mbN, H), a, f, l)]
+                for l_ in range(L - 1, -1, -1):
+                    res = saved_layers[l_]
+                    per = [(res[g][3], res[g][0], res[g][1], res[g][2], par(rnns[g], "weight_ih", l_).detach(),
+                            par(rnns[g], "weight_hh", l_).detach()) for g in range(2)]
+                    for d_ in rc["db"]:
+                        if d_ is not None:
+                            d_.zero_()
+                    targets = [(par(rnns[g], "weight_ih", l_).grad, par(rnns[g], "weight_hh", l_).grad, rc["db"][g]) for g in range(2)]
+                    back = _layers_backward(per, [(douts[g], None, None) for g in range(2)], prec, has_bias,
+                                            [l_ > 0, l_ > 0], False, targets)
+                    if has_bias:
+                        for g in range(2):   # b_ih and b_hh receive the same gradient
+                            par(rnns[g], "bias_ih", l_).grad.add_(rc["db"][g])
+                            par(rnns[g], "bias_hh", l_).grad.add_(rc["db"][g])
+                    douts = [back[g][0] for g in range(2)]
+                if self.is_multi_gpu and not opt.peer_allreduce:
+                    torch.distributed.all_reduce(self._group.grads_ext, op=torch.distributed.ReduceOp.SUM)
+                opt.fused_step(world_size=self.gpu_world_size, max_grad_norm=self.max_grad_norm, adaptive=adaptive,
+                               desired_kl=self.desired_kl or 0.0, round_lr_fp32=self.is_multi_gpu, use_kl=adaptive)
+                eng.refresh_padded(after_step=True)
+
+        for _ in range(E):
+            for i, mb in enumerate(cached):
+                if self.rng_compat:   # the sample the reference's policy.act() draws and discards (ppo.py:249): host side
+                    self._skip_discarded_draws(1, rows)
+                if not use_graph:
+                    minibatch(mb)
+                    continue
+                if graphs[i] is None:
+                    host_step, before = opt._host_step, nat.launch_count()
+                    g = self._capture_graph(lambda mb=mb: minibatch(mb))
+                    mb["launches"] = nat.launch_count() - before
+                    nat.lib().rslrl_add_launch_count(-mb["launches"] & 0xFFFFFFFFFFFFFFFF)   # capture launched nothing
+                    opt._host_step = host_step
+                    graphs[i] = g
+                graphs[i].replay()
+                nat.lib().rslrl_add_launch_count(mb["launches"])
+                opt._host_step += 1
+        # loss accumulators of the fused kernel: [surrogate, value, entropy] -> the composite order
+        sums[0:1].copy_(ds.loss_sums[1:2]); sums[1:2].copy_(ds.loss_sums[0:1]); sums[2:3].copy_(ds.loss_sums[2:3])
+        # the graphs of this update stay alive until the next update has captured its own in the same memory pool: the
+        # pool then keeps its blocks and the new captures reuse them (no cudaMalloc / cudaFree per update)
+        rc["graphs"] = graphs if use_graph else None
+
+    def _capture_graph(self, fn):
+        """Captures what `fn` puts on the stream into a CUDA graph in this object's persistent graph memory pool.
+        (torch.cuda.graph() empties the caching allocator and runs the garbage collector before every capture -- tens of
+        milliseconds, and every later allocation becomes a cudaMalloc; graphs that are re-captured on every update
+        cannot afford that.)"""
+        if getattr(self, "_graph_pool", None) is None:
+            self._graph_pool = torch.cuda.graph_pool_handle()
+            self._cap_stream = torch.cuda.Stream()
+        g = torch.cuda.CUDAGraph()
+        cur = torch.cuda.current_stream()
+        side = self._cap_stream
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            g.capture_begin(pool=self._graph_pool)
+            try:
+                fn()
+            finally:
+                g.capture_end()
+        cur.wait_stream(side)
+        return g
+
     def _x16(self, cf, tag: str, x: torch.Tensor) -> torch.Tensor:
         key = ("x16", tag, x.shape[0], x.shape[1])
         buf = cf.get(key)
@@ -826,6 +1020,8 @@ class PPO:
         feed-forward policies)."""
         if self._composite_fusable():
             return self._composite_minibatches_fused(sums)
+        if self._recurrent_fused:
+            return self._recurrent_minibatches_fused(sums)
         pol, st, opt = self.policy, self.storage, self.optimizer
         M, E = self.num_mini_batches, self.num_learning_epochs
         once = getattr(st, "_randperm_once", None)

@@ -36,6 +36,26 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 bool pdl_enabled();
 
+// Shared-memory carve-out: the tcgen05 kernels of the chain run with the maximum shared-memory configuration (227 KB);
+// a kernel without a preference gets a small carve-out, and switching the L1 / shared split between two consecutive
+// kernels needs idle SMs.  With the preference set on the small kernels of the chain (loss, optimiser, LSTM cells, ...)
+// every launch keeps the same split.  RSLRL_SMEM_CARVEOUT=0 / 1 (A/B switch).
+// Measured (profiles/experiments/notes/r2_carveout.md): the recurrent update alternates a 227 KB GEMM and a cell kernel 48
+// times per time loop -- with the preference on the cell kernels C4 drops from 56 to 46 ms per iteration (always on for
+// them); on the feed-forward chain (7 launches per minibatch) it is neutral to slightly negative (5.08 -> 5.20 ms), so the
+// other kernels only follow RSLRL_SMEM_CARVEOUT=1.
+bool carveout_enabled();
+template <typename K>
+inline void prefer_max_smem(K kernel, bool always = false) {
+  static bool done = false;   // one flag per kernel type (template instantiation)
+  if (!done) {
+    if (always || carveout_enabled())
+      (void)cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    (void)cudaGetLastError();
+    done = true;
+  }
+}
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_chain_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                                        Args&&... args) {
@@ -49,6 +69,7 @@ inline cudaError_t launch_chain_kernel(void (*kernel)(KArgs...), dim3 grid, dim3
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  prefer_max_smem(kernel);
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

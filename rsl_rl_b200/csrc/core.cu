@@ -39,6 +39,11 @@ __global__ void __launch_bounds__(256) convert_f32_f16_kernel(const float* __res
 static thread_local char g_err[512] = "";
 static std::atomic<unsigned long long> g_launches{0};
 
+bool carveout_enabled() {
+  static const bool on = [] { const char* e = getenv("RSLRL_SMEM_CARVEOUT"); return e != nullptr && e[0] == '1'; }();
+  return on;
+}
+
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);

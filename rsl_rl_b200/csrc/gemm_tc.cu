@@ -828,7 +828,9 @@ int tc_linear_backward_data(int n, const rslrl_linear_bwd_data_t* pr, cudaStream
     }
     P.C = (float*)q.dx; P.M = q.M; P.N = q.K; P.K = q.N; P.ldc = q.ldx; P.act = q.act;
     if (!tma_ok(q.dx, q.ldx)) return -1;
-    if (q.act == RSLRL_ACT_IDENTITY || !tma_ok(q.h, q.ldh)) return -1;  // (no saved activation: exact fp32 kernel)
+    // (act == IDENTITY with an h of the output's shape: the factor is 1 whatever h holds -- used for the data gradient
+    //  that leaves an MLP towards a recurrent memory; without any h tensor the exact fp32 kernel runs)
+    if (q.h == nullptr || !tma_ok(q.h, q.ldh)) return -1;
     if (!make_map(&P.map_c, (const float*)q.dx, q.M, q.K, q.ldx, 32, 32, false, false) ||
         !make_map(&P.map_h, (const float*)q.h, q.M, q.K, q.ldh, 32, TC_BLOCK_M, false, false)) {
       set_error("%s: cuTensorMapEncodeTiled failed", what);

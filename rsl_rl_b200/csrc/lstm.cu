@@ -129,10 +129,12 @@ static int lstm_blocks(long long work) {
 }
 
 static int launch_cell_forward(const LstmFwdBatch& b, int n_nets, long long n, int H, cudaStream_t st) {
+  prefer_max_smem(lstm_cell_forward_kernel, true);
   lstm_cell_forward_kernel<<<dim3(lstm_blocks(n * (H / 4)), n_nets), kLstmThreads, 0, st>>>(b, n, H);
   return finish_launch("rslrl_lstm_cell_forward");
 }
 static int launch_cell_backward(const LstmBwdBatch& b, int n_nets, long long n, int H, cudaStream_t st) {
+  prefer_max_smem(lstm_cell_backward_kernel, true);
   lstm_cell_backward_kernel<<<dim3(lstm_blocks(n * (H / 4)), n_nets), kLstmThreads, 0, st>>>(b, n, H);
   return finish_launch("rslrl_lstm_cell_backward");
 }

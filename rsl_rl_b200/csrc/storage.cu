@@ -221,6 +221,7 @@ int rslrl_store_transition(int n_groups, const float* const* obs_src_host, float
   p.gamma = (float)gamma; p.N = N; p.A = A;
   RSLRL_CHECK_ARG(!time_outs || values, what);
   dim3 grid(grid_for(max_units / 4 + 1), p.n_copy + 1 + (p.sigma ? 1 : 0));
+  prefer_max_smem(store_transition_kernel);
   store_transition_kernel<<<grid, kCopyThreads, 0, (cudaStream_t)stream>>>(p);
   return finish_launch(what);
 }

@@ -74,7 +74,9 @@ class RandomNetworkDistillation(nn.Module):
                     break
                 layers, acts = mlp.linear_layers(), mlp.layer_activation_codes()
                 dims = [layers[0].in_features] + [l.out_features for l in layers]
-                if len(layers) > 4 or max(dims) > 128 or acts[-1] != 0:
+                n_par = sum(a * b + b for a, b in zip(dims[:-1], dims[1:]))
+                # (both networks' parameters + three 32-row activation tiles must fit in 200 KB of shared memory)
+                if len(layers) > 4 or max(dims) > 128 or acts[-1] != 0 or (2 * n_par + 96 * 129) * 4 > 200 * 1024:
                     structs = None
                     break
                 q = nat.RndNet()

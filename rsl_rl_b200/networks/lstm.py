@@ -72,49 +72,68 @@ class _LSTMGroupFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, *grads):
-        G, prec = ctx.G, ctx.prec
+        G = ctx.G
         saved = ctx.saved_tensors
-        arr, keep, per_net = (nat.LstmBwd * G)(), [], []
+        per = [saved[6 * g:6 * g + 6] for g in range(G)]
+        need_dx = [ctx.needs_input_grad[3 + g] for g in range(G)]
         need_h0 = any(ctx.needs_input_grad[3 + G + g] for g in range(G))
-        for g in range(G):
-            x2d, h_all, c_all, gates, w_ih, w_hh = saved[6 * g:6 * g + 6]
-            T, n, H4 = gates.shape
-            H = H4 // 4
-            f32 = dict(dtype=torch.float32, device=gates.device)
-            dout, dhT, dcT = (None if t is None else nat.f32c(t) for t in grads[3 * g:3 * g + 3])
-            dgates = torch.empty(T, n, H4, **f32)
-            dh_bufs, dc_bufs = torch.empty(2, n, H, **f32), torch.empty(2, n, H, **f32)
-            w_hh_t = w_hh.detach().t().contiguous()   # [H, 4H]: dh_{t-1} = dG_t W_hh as a forward product
-            arr[g] = nat.LstmBwd(nat.ptr(dout), nat.ptr(dhT), nat.ptr(dcT), gates.data_ptr(), c_all.data_ptr(),
-                                 w_hh_t.data_ptr(), dgates.data_ptr(), dh_bufs.data_ptr(), dc_bufs.data_ptr())
-            keep.append((dout, dhT, dcT, w_hh_t))
-            per_net.append((x2d, h_all, w_ih, w_hh, dgates, dh_bufs, dc_bufs, T, n, H))
-        T, n, H = per_net[0][7:]
-        # backward through time in C: per step one fused cell-backward launch + the grouped dh_{t-1} product
-        nat.check(nat.lib().rslrl_lstm_layers_backward(G, arr, int(need_h0), T, n, H, prec, nat.stream_ptr()))
-        dxs, dh0s, dc0s, dw_ihs, dw_hhs, dbs, wprobs = [], [], [], [], [], [], []
-        for g in range(G):
-            x2d, h_all, w_ih, w_hh, dgates, dh_bufs, dc_bufs, T, n, H = per_net[g]
-            dg2d = dgates.view(T * n, 4 * H)
-            dw_ih, dw_hh = torch.zeros_like(w_ih), torch.zeros_like(w_hh)
-            db = torch.zeros(4 * H, dtype=torch.float32, device=dgates.device) if ctx.has_bias else None
-            # weight gradients of all steps as two products over T*n rows (h_all[:T] = the h_{t-1} of every step)
-            wprobs += [(dg2d, x2d, dw_ih, db), (dg2d, h_all[:T].view(T * n, H), dw_hh, None)]
-            dx = None
-            if ctx.needs_input_grad[3 + g]:
-                dx = torch.empty(T * n, w_ih.shape[1], dtype=torch.float32, device=dgates.device)
-                linear_backward_data([(dg2d, w_ih, None, dx, _IDENT)], prec)
-                dx = dx.view(T, n, -1)
+        res = _layers_backward(per, [grads[3 * g:3 * g + 3] for g in range(G)], ctx.prec, ctx.has_bias, need_dx, need_h0)
+        dxs, dh0s, dc0s, dw_ihs, dw_hhs, dbs = [], [], [], [], [], []
+        for g, (dx, dh0, dc0, dw_ih, dw_hh, db) in enumerate(res):
             dxs.append(dx)
-            dh0s.append(dh_bufs[0] if ctx.needs_input_grad[3 + G + g] else None)
-            dc0s.append(dc_bufs[0] if ctx.needs_input_grad[3 + 2 * G + g] else None)
+            dh0s.append(dh0 if ctx.needs_input_grad[3 + G + g] else None)
+            dc0s.append(dc0 if ctx.needs_input_grad[3 + 2 * G + g] else None)
             dw_ihs.append(dw_ih); dw_hhs.append(dw_hh); dbs.append(db)
-        for i in range(0, len(wprobs), 2):                       # (the tensor-core wgrad groups two problems per launch)
-            linear_backward_weight(wprobs[i:i + 2], prec)
         out = [None, None, None] + dxs + dh0s + dc0s + dw_ihs + dw_hhs
         if ctx.has_bias:
             out += dbs + dbs                                      # b_ih and b_hh receive the same gradient
         return tuple(out)
+
+
+def _layers_backward(per, grads, prec: int, has_bias: bool, need_dx, need_h0: bool, targets=None):
+    """Backward through time of one layer of G <= 2 LSTMs advanced together.
+    per[g] = (x2d, h_all, c_all, gates, w_ih, w_hh) as saved by `_layers_forward(save=True)`; grads[g] = (dout [T,n,H] | None,
+    dh_T | None, dc_T | None).  targets[g] = (dw_ih, dw_hh, db | None) to ACCUMULATE into (e.g. the .grad views of the flat
+    gradient buffer); fresh zero tensors otherwise.  Returns per net (dx [T,n,D] | None, dh0, dc0, dw_ih, dw_hh, db)."""
+    G = len(per)
+    arr, keep, per_net = (nat.LstmBwd * G)(), [], []
+    for g in range(G):
+        x2d, h_all, c_all, gates, w_ih, w_hh = per[g]
+        T, n, H4 = gates.shape
+        H = H4 // 4
+        f32 = dict(dtype=torch.float32, device=gates.device)
+        dout, dhT, dcT = (None if t is None else nat.f32c(t) for t in grads[g])
+        dgates = torch.empty(T, n, H4, **f32)
+        dh_bufs, dc_bufs = torch.empty(2, n, H, **f32), torch.empty(2, n, H, **f32)
+        w_hh_t = w_hh.detach().t().contiguous()   # [H, 4H]: dh_{t-1} = dG_t W_hh as a forward product
+        arr[g] = nat.LstmBwd(nat.ptr(dout), nat.ptr(dhT), nat.ptr(dcT), gates.data_ptr(), c_all.data_ptr(),
+                             w_hh_t.data_ptr(), dgates.data_ptr(), dh_bufs.data_ptr(), dc_bufs.data_ptr())
+        keep.append((dout, dhT, dcT, w_hh_t))
+        per_net.append((x2d, h_all, w_ih, w_hh, dgates, dh_bufs, dc_bufs, T, n, H))
+    T, n, H = per_net[0][7:]
+    # backward through time in C: per step one fused cell-backward launch + the grouped dh_{t-1} product
+    nat.check(nat.lib().rslrl_lstm_layers_backward(G, arr, int(need_h0), T, n, H, prec, nat.stream_ptr()))
+    out, wprobs = [], []
+    for g in range(G):
+        x2d, h_all, w_ih, w_hh, dgates, dh_bufs, dc_bufs, T, n, H = per_net[g]
+        dg2d = dgates.view(T * n, 4 * H)
+        if targets is not None:
+            dw_ih, dw_hh, db = targets[g]
+        else:
+            dw_ih, dw_hh = torch.zeros_like(w_ih), torch.zeros_like(w_hh)
+            db = torch.zeros(4 * H, dtype=torch.float32, device=dgates.device) if has_bias else None
+        # weight gradients of all steps as two products over T*n rows (h_all[:T] = the h_{t-1} of every step)
+        wprobs += [(dg2d, x2d, dw_ih, db), (dg2d, h_all[:T].view(T * n, H), dw_hh, None)]
+        dx = None
+        if need_dx[g]:
+            dx = torch.empty(T * n, w_ih.shape[1], dtype=torch.float32, device=dgates.device)
+            # (x2d stands in for the saved activation of an identity layer: the tensor-core data-gradient kernel then runs)
+            linear_backward_data([(dg2d, w_ih, x2d, dx, _IDENT)], prec)
+            dx = dx.view(T, n, -1)
+        out.append((dx, dh_bufs[0], dc_bufs[0], dw_ih, dw_hh, db))
+    for i in range(0, len(wprobs), 2):                       # (the tensor-core wgrad groups two problems per launch)
+        linear_backward_weight(wprobs[i:i + 2], prec)
+    return out
 
 
 def lstm_forward_group(rnns: Sequence[torch.nn.LSTM], xs: Sequence[torch.Tensor],

@@ -168,8 +168,9 @@ class _MLPFunction(torch.autograd.Function):
             if li > 0 or need_dx:
                 dx = torch.empty(M, w.shape[1], dtype=torch.float32, device=d.device)
                 if M > 0:
-                    linear_backward_data([(d, w, hs[li] if li > 0 else None, dx, acts[li - 1] if li > 0 else 0)],
-                                         precision)
+                    # (li == 0: identity in front of the first layer; the layer INPUT stands in for the saved activation so
+                    #  that the tensor-core data-gradient kernel runs -- its factor is 1 whatever the tensor holds)
+                    linear_backward_data([(d, w, hs[li], dx, acts[li - 1] if li > 0 else 0)], precision)
                 d = dx
         dx_out = d.reshape(ctx.x_shape) if need_dx else None
         return (dx_out, None, None, *grads)

@@ -109,6 +109,20 @@ class TrajectoryIndex:
                                                 last_traj, cap, nat.stream_ptr()))
         return out.reshape(T, cap, *tail)
 
+    def pad_columns(self, x: torch.Tensor, env0: int, first_traj: int, last_traj: int) -> torch.Tensor:
+        """split_and_pad of a tensor that holds only the env columns [env0, env0 + x.shape[1]) of the rollout
+        ([T, ne, D] -> [T, last_traj - first_traj, D], zero padded): the inverse of `unpad` (gradients on their way back
+        into a recurrent memory)."""
+        T, ne, D = x.shape
+        xc = nat.f32c(x)
+        cap = last_traj - first_traj
+        out = torch.empty(T, cap, D, dtype=torch.float32, device=x.device)
+        # the kernel addresses x[(start + p), env, :] with the ABSOLUTE env index: shift the base by env0 columns
+        nat.check(nat.lib().rslrl_split_and_pad(xc.data_ptr() - env0 * D * 4, self.traj_len.data_ptr(),
+                                                self.traj_env.data_ptr(), self.traj_start.data_ptr(), out.data_ptr(), T, ne,
+                                                D, first_traj, last_traj, cap, nat.stream_ptr()))
+        return out
+
     def unpad(self, padded: torch.Tensor, env0: int, env1: int, first_traj: int) -> torch.Tensor:
         T = self.T
         cap = padded.shape[1]

@@ -50,6 +50,8 @@ def test_composite_learn_iterations_match_reference_golden(name):
     meta = meta_of(g)
     runner = _runner_from_golden(g, meta)
     alg, st = runner.alg, runner.alg.storage
+    if name == "ppo_lstm_small":   # the recurrent configuration runs on the engine (native LSTM + fused MLP path), no autograd
+        assert alg._recurrent_fused and alg.rollout_fused and not alg.fused
     for it in range(meta["iterations"]):
         p = f"it{it}."
         zq = [torch.from_numpy(z).to(DEV) for z in g[p + "z_rollout"]]
@@ -146,3 +148,35 @@ def test_composite_update_cuda_graph_matches_eager_and_falls_back():
     assert alg._cgraph is None and alg._cgraph_failed
     p = torch.cat([q.detach().reshape(-1) for q in alg.policy.parameters()])
     assert bool(torch.isfinite(p).all()) and alg.last_update_info["step"] == 4 * 2 * 2
+
+
+def _lstm_runner(use_graph, hidden=(64, 32), envs=256, rnn=32):
+    from rsl_rl_b200.env import SynthVecEnv
+    from rsl_rl_b200.runners import OnPolicyRunner
+    torch.manual_seed(0)
+    env = SynthVecEnv(envs, {"policy": 16}, 4, device=DEV, seed=3, p_done=0.05)
+    cfg = dict(num_steps_per_env=8, save_interval=10 ** 9, obs_groups={"policy": ["policy"], "critic": ["policy"]},
+               policy=dict(class_name="ActorCriticRecurrent", actor_hidden_dims=list(hidden), critic_hidden_dims=list(hidden),
+                           activation="elu", init_noise_std=1.0, rnn_type="lstm", rnn_hidden_dim=rnn, rnn_num_layers=1),
+               algorithm=dict(class_name="PPO", learning_rate=1e-3, num_learning_epochs=3, num_mini_batches=2,
+                              schedule="adaptive", desired_kl=0.01, use_cuda_graph=use_graph, gemm_precision="fp32"))
+    return OnPolicyRunner(env, cfg, log_dir=None, device=DEV)
+
+
+def test_recurrent_update_on_the_engine_matches_the_autograd_path_and_graph_replay(monkeypatch):
+    """ActorCriticRecurrent: (a) the hand-written recurrent update on the engine (native LSTM forward / backward through
+    time, fused MLP path, no autograd) gives the parameters of the autograd composite path; (b) replaying every
+    minibatch of the later epochs from its CUDA graph gives the parameters of the eager loop."""
+    finals = {}
+    for mode in ("autograd", "eager", "graph"):
+        monkeypatch.setenv("RSLRL_RECURRENT_FUSED", "0" if mode == "autograd" else "1")
+        runner = _lstm_runner(mode == "graph")
+        alg = runner.alg
+        assert alg._recurrent_fused == (mode != "autograd")
+        torch.manual_seed(5)
+        runner.learn(4)
+        finals[mode] = (torch.cat([q.detach().reshape(-1) for q in alg.policy.parameters()]).cpu().numpy(), alg.learning_rate)
+    assert finals["eager"][1] == finals["graph"][1]
+    assert rel_err(finals["graph"][0], finals["eager"][0]) < 1e-6
+    assert abs(finals["eager"][1] - finals["autograd"][1]) < 1e-12
+    assert rel_err(finals["eager"][0], finals["autograd"][0]) < 5e-5
