@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define RSLRL_ABI_VERSION 2
+#define RSLRL_ABI_VERSION 3
 #define RSLRL_MAX_SEGMENTS 16 /* max obs groups / gather fields per launch */
 #define RSLRL_MAX_PROBLEMS 8  /* max GEMM problems grouped into one launch (fp16 wgrad: 4 layers x actor, critic) */
 
@@ -174,13 +174,17 @@ typedef struct {
   /* Optional Gaussian policy head fused into the output epilogue (PPO.act, rsl_rl/algorithms/ppo.py:129-140 ->
    * modules/actor_critic.py:130-146): with head_z != NULL the N4 outputs y = mu are also turned into
    *   head_actions[M,N4] = head_z * sigma + mu,  head_logp[M] = sum log N(actions; mu, sigma),  head_sigma[M,N4] = sigma
-   * (sigma from head_std[N4] as in rslrl_gaussian_act; same arithmetic, bit for bit).  head_sigma may be NULL. */
+   * (sigma from head_std[N4] as in rslrl_gaussian_act; same arithmetic, bit for bit).  head_sigma may be NULL.
+   * head_actions_host (may be NULL): a second destination of the actions, e.g. PINNED HOST memory mapped into the device
+   * address space: a host-resident simulator then reads the actions after one stream synchronisation, without a
+   * device-to-host copy (the `actions.to(self.env.device)` of on_policy_runner.py:104). */
   const float* head_z;
   const float* head_std;
   int head_std_type;
   float* head_actions;
   float* head_logp;
   float* head_sigma;
+  float* head_actions_host;
 } rslrl_mlp3_fwd_t;
 
 /* Each call runs `n` independent problems (e.g. actor and critic) in one launch; *_host arrays live

@@ -23,7 +23,7 @@ PREC_FP32, PREC_TF32, PREC_FP16, PREC_TF32X3 = 0, 1, 2, 3
 PREC_CODES = {"fp32": PREC_FP32, "tf32": PREC_TF32, "fp16": PREC_FP16, "tf32x3": PREC_TF32X3}
 STD_SCALAR, STD_LOG = 0, 1
 MAX_SEGMENTS, MAX_PROBLEMS = 16, 8
-ABI_VERSION = 2   # RSLRL_ABI_VERSION of include/rslrl_b200.h
+ABI_VERSION = 3   # RSLRL_ABI_VERSION of include/rslrl_b200.h
 
 
 class LinearFwd(C.Structure):
@@ -55,7 +55,7 @@ class Mlp3Fwd(C.Structure):
                 ("ldx", c_int), ("ldw0", c_int), ("ldh", c_int * 3), ("ldy", c_int), ("act", c_int), ("precision", c_int),
                 # optional Gaussian policy head fused into the output epilogue (rollout)
                 ("head_z", c_void_p), ("head_std", c_void_p), ("head_std_type", c_int), ("head_actions", c_void_p),
-                ("head_logp", c_void_p), ("head_sigma", c_void_p)]
+                ("head_logp", c_void_p), ("head_sigma", c_void_p), ("head_actions_host", c_void_p)]
 
 
 class LstmFwd(C.Structure):

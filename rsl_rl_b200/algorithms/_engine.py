@@ -323,7 +323,8 @@ class FeedForwardEngine:
 
         return run
 
-    def build_act_plan(self, M: int, ld_a: int, ld_c: int, mu_out, v_out, z, actions_out, logp_out, sigma_out):
+    def build_act_plan(self, M: int, ld_a: int, ld_c: int, mu_out, v_out, z, actions_out, logp_out, sigma_out,
+                       actions_host=None):
         """One-launch rollout step (fused forward of actor + critic with the Gaussian policy head in the actor's output
         epilogue): a C-side launch plan with every TMA descriptor pre-encoded; returns callable(xa_ptr, xc_ptr).  None
         when the fused forward does not cover this policy / input layout."""
@@ -333,6 +334,7 @@ class FeedForwardEngine:
         sc = self._mlp3("c", 0, ld_c, M, v_out, store=False)
         sa.head_z, sa.head_std, sa.head_std_type = z.data_ptr(), self.std_param.data_ptr(), self.std_type
         sa.head_actions, sa.head_logp, sa.head_sigma = actions_out.data_ptr(), logp_out.data_ptr(), nat.ptr(sigma_out)
+        sa.head_actions_host = nat.ptr(actions_host)   # optional second copy of the actions in pinned host memory
         sa.x = sc.x = z.data_ptr()   # placeholder (any valid 16-byte aligned pointer): run() patches the real inputs
         arr = (nat.Mlp3Fwd * 2)(sa, sc)
         return _Mlp3Plan(arr, 2)

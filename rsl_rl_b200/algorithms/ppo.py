@@ -164,6 +164,8 @@ class PPO:
         self._update_reason = "RND" if self.rnd is not None else ("symmetry" if self.symmetry is not None else None)
         self._recurrent_fused = False
         self._rc = None   # per-update cache of the fused recurrent path
+        self._host_actions, self._host_actions_id = None, 0   # pinned [2, N, A] ring the act kernel also writes (host envs)
+        self.last_host_actions = None   # the ring slot the most recent act() wrote, valid after a stream synchronisation
         self._graph = None
         self._cgraph, self._cgraph_key, self._cgraph_failed, self._cgraph_launches = None, None, False, 0
         self._csums, self._cperm = None, None
@@ -290,7 +292,7 @@ class PPO:
             if x_a.dtype != torch.float32 or x_c.dtype != torch.float32 or not x_a.is_contiguous() \
                     or not x_c.is_contiguous():
                 x_a, x_c = self._inputs(obs)
-        key = (x_a.stride(0), x_c.stride(0), x_a.shape[1], x_c.shape[1], self._group.values.data_ptr())
+        key = (x_a.stride(0), x_c.stride(0), x_a.shape[1], x_c.shape[1], self._group.values.data_ptr(), self._host_actions_id)
         plan = self._act_plans.get(s)
         if plan is None or plan["key"] != key:
             plan = self._build_act_plan(s, x_a, x_c, key)
@@ -301,6 +303,7 @@ class PPO:
         else:
             zbuf.normal_()  # same draw as torch.normal(mean, std): normal_(0,1) on a tensor of mu's shape
         one = plan["one_launch"]
+        self.last_host_actions = plan["host"] if one is not None else None
         if one is not None:
             # ONE launch per env step: fused forward of both nets, Gaussian head in the actor's output epilogue, results
             # written straight into row s of the rollout buffer.  Observations are read in place when their rows are
@@ -347,6 +350,14 @@ class PPO:
         pd["_mean"], pd["_std"] = mu_s, sig_s
         return act_s
 
+    def enable_host_actions(self, ring: torch.Tensor):
+        """ring: PINNED host tensor [2, num_envs, num_actions].  From the next act() on, the one-launch rollout step also
+        writes its actions into ring[step & 1] (mapped pinned memory): a host-resident env reads them after one stream
+        synchronisation instead of a device-to-host copy (`last_host_actions`)."""
+        if not (ring.is_pinned() and ring.dtype == torch.float32 and ring.dim() == 3 and ring.shape[0] == 2):
+            raise ValueError("enable_host_actions: a pinned float32 [2, num_envs, num_actions] tensor is required")
+        self._host_actions, self._host_actions_id = ring, self._host_actions_id + 1
+
     def _build_act_plan(self, s, x_a, x_c, key):
         st, eng = self.storage, self._engine
         self._group.ensure_bound()
@@ -363,9 +374,10 @@ class PPO:
         sa, sc, zbuf = self._act_in
         N = st.num_envs
         direct = x_a.stride(0) % 4 == 0 and x_c.stride(0) % 4 == 0 and x_a.stride(1) == 1 and x_c.stride(1) == 1
-        one = eng.build_act_plan(N, x_a.stride(0), x_c.stride(0), *views[:2], zbuf, *views[2:]) if direct else None
-        one_static = eng.build_act_plan(N, sa.stride(0), sc.stride(0), *views[:2], zbuf, *views[2:])
-        plan = dict(key=key, views=views, graph=None, launches=0, visits=0, direct=direct and one is not None,
+        host = None if self._host_actions is None else self._host_actions[s & 1]
+        one = eng.build_act_plan(N, x_a.stride(0), x_c.stride(0), *views[:2], zbuf, *views[2:], actions_host=host) if direct else None
+        one_static = eng.build_act_plan(N, sa.stride(0), sc.stride(0), *views[:2], zbuf, *views[2:], actions_host=host)
+        plan = dict(key=key, views=views, graph=None, launches=0, visits=0, direct=direct and one is not None, host=host,
                     one_launch=one if one is not None else one_static, one_static=one_static, fwd=None, fwd_static=None)
         if one_static is None:   # no fused forward for this policy / precision: layer-by-layer launch plans
             plan["fwd"] = eng.build_forward_plan(N, x_a.stride(0), x_c.stride(0), views[0], views[1])

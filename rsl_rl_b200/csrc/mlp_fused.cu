@@ -56,6 +56,7 @@ struct MfNet {
   float* head_actions;
   float* head_logp;
   float* head_sigma;
+  float* head_actions_host;
   int head_std_type;
 };
 
@@ -557,6 +558,7 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp3_forward_kernel(const __gri
               const float* const hs = head_s + ni * 48;
               const float* const zr = P.head_z + (size_t)row * P.N4;
               float* const ar = P.head_actions + (size_t)row * P.N4;
+              float* const ah = P.head_actions_host ? P.head_actions_host + (size_t)row * P.N4 : nullptr;
               float lp = 0.f;
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
@@ -565,6 +567,7 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp3_forward_kernel(const __gri
                   const float a = __fadd_rn(__fmul_rn(__ldg(zr + i), sg), mean);
                   yr[i] = mean;
                   ar[i] = a;
+                  if (ah) ah[i] = a;
                   const float d = a - mean;
                   lp += -(d * d) / hs[32 + i] - hs[16 + i] - 0.91893853320467274178f;
                   if (P.head_sigma) P.head_sigma[(size_t)row * P.N4 + i] = sg;
@@ -590,7 +593,7 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp3_forward_kernel(const __gri
   }
 }
 
-static_assert(sizeof(rslrl_mlp3_fwd_t) == 208, "rslrl_mlp3_fwd_t layout is mirrored by _native.Mlp3Fwd (ctypes)");
+static_assert(sizeof(rslrl_mlp3_fwd_t) == 216, "rslrl_mlp3_fwd_t layout is mirrored by _native.Mlp3Fwd (ctypes)");
 
 static bool ok16(const void* p, long long ld) { return ((uintptr_t)p & 15) == 0 && (ld % 4) == 0; }
 
@@ -647,7 +650,7 @@ static int mlp3_build(int n, const rslrl_mlp3_fwd_t* nets, MfBatch& b, bool& f16
     P.y = q.y; P.M = q.M; P.K0 = q.K0; P.N1 = q.N1; P.N2 = q.N2; P.N3 = q.N3; P.N4 = q.N4; P.ldy = q.ldy;
     P.act = q.act; P.store_h = store ? 1 : 0;
     P.head_z = q.head_z; P.head_std = q.head_std; P.head_actions = q.head_actions; P.head_logp = q.head_logp;
-    P.head_sigma = q.head_sigma; P.head_std_type = q.head_std_type;
+    P.head_sigma = q.head_sigma; P.head_std_type = q.head_std_type; P.head_actions_host = q.head_actions_host;
     if (q.head_z != nullptr && (!q.head_std || !q.head_actions || !q.head_logp)) {
       set_error("%s: head_z needs head_std, head_actions and head_logp", what);
       return 1;

@@ -28,10 +28,10 @@ def test_library_builds_and_exports_every_declared_symbol():
 
 def test_loader_checks_abi_and_struct_layout():
     lib = nat.lib()
-    assert lib.rslrl_abi_version() == 2
+    assert lib.rslrl_abi_version() == 3
     assert ctypes.sizeof(nat.OptState) == 64
     assert ctypes.sizeof(nat.LinearFwd) == 4 * 8 + 6 * 4 and ctypes.sizeof(nat.LinearBwdData) == 4 * 8 + 7 * 4 + 4 + 8
-    assert ctypes.sizeof(nat.Mlp3Fwd) == 208   # static_assert'ed on the C side (mlp_fused.cu)
+    assert ctypes.sizeof(nat.Mlp3Fwd) == 216   # static_assert'ed on the C side (mlp_fused.cu)
     assert lib.rslrl_gae_workspace_bytes(4096) >= 16
     assert lib.rslrl_loss_workspace_bytes() >= 8 * (4 + 64)
 

@@ -503,3 +503,34 @@ def test_reference_checkpoint_round_trip(tmp_path):
         for k, v in alg.policy.state_dict().items():
             assert torch.equal(rsd[k], v.cpu()), k
         assert ref_runner.current_learning_iteration == runner.current_learning_iteration
+
+
+@pytest.mark.parametrize("direct", ["0", "1"])
+def test_host_resident_env_receives_the_actions_written_by_the_rollout_kernel(direct, monkeypatch):
+    """Env on the host (pinned buffers).  direct=1 (opt-in, RSLRL_HOST_ACTIONS=1): from the second env step on the one-launch
+    rollout kernel writes the actions into a pinned ring as well and the runner hands that ring slot to the env after one
+    stream synchronisation (no device-to-host copy); direct=0: pinned copy ring.  Either way what the env receives must be
+    exactly what the rollout buffer holds."""
+    monkeypatch.setenv("RSLRL_HOST_ACTIONS", direct)
+    from rsl_rl_b200.env import PinnedHostEnv
+    from rsl_rl_b200.runners import OnPolicyRunner
+    import bench
+
+    class Recording(PinnedHostEnv):
+        def __init__(self, *a, **k):
+            super().__init__(*a, **k)
+            self.seen = []
+
+        def step(self, actions):
+            assert not actions.is_cuda
+            self.seen.append(actions.clone())
+            return super().step(actions)
+
+    env = Recording(512, {"policy": 48}, 12, pool=8, seed=1)
+    runner = OnPolicyRunner(env, bench.train_cfg("fp16"), log_dir=None, device=DEV)
+    runner.learn(2)
+    alg = runner.alg
+    assert (alg._host_actions is not None and alg.last_host_actions is not None) == (direct == "1")
+    T = alg.storage.num_transitions_per_env
+    got = torch.stack(env.seen[-T:])                      # the second iteration
+    assert torch.equal(got, alg.storage.actions.cpu())
