@@ -86,6 +86,22 @@ int rslrl_store_transition(int n_groups, const float* const* obs_src_host, float
                            float* sigma_row, float* values_row, float* log_prob_row, float* rewards_row,
                            uint8_t* dones_row, int N, int A, rslrl_stream_t stream);
 
+/* The same launch for the rollout fast path (PPO.act has already written actions / mean / sigma / value / log-prob of the
+ * step in place): everything that is fixed for a step index lives in a plan the host builds once; per env step only the
+ * source pointers are passed.  Observations, rewards (+ intrinsic) with the time-out bootstrap and dones move. */
+typedef struct {
+  float* obs_dst[RSLRL_MAX_SEGMENTS]; /* row `step` of every observation group's [T,N,d] buffer */
+  int obs_dim[RSLRL_MAX_SEGMENTS];
+  const float* values_row;            /* row `step` of values (read for the bootstrap) */
+  float* rewards_row;
+  uint8_t* dones_row;
+  double gamma;
+  int n_groups, N, A;
+} rslrl_store_plan_t;
+int rslrl_store_step(const rslrl_store_plan_t* plan, const float* const* obs_src_host, const float* rewards,
+                     const void* dones, int dones_dtype, const void* time_outs, int time_outs_dtype,
+                     const float* intrinsic, rslrl_stream_t stream);
+
 /* RolloutStorage.compute_returns (rsl_rl/storage/rollout_storage.py:127-149): reverse GAE scan over T
  * with done masking, returns, advantages = returns - values, and (normalize != 0) the global
  * rewards/values/returns/advantages: [T,N] fp32, dones: [T,N] u8, last_values: [N].

@@ -72,6 +72,11 @@ class LossHead(C.Structure):
                 ("dz_actor", c_void_p), ("dz_critic", c_void_p), ("K3", c_int), ("ldh", c_int), ("act", c_int)]
 
 
+class StorePlan(C.Structure):
+    _fields_ = [("obs_dst", c_void_p * 16), ("obs_dim", c_int * 16), ("values_row", c_void_p), ("rewards_row", c_void_p),
+                ("dones_row", c_void_p), ("gamma", c_double), ("n_groups", c_int), ("N", c_int), ("A", c_int)]
+
+
 class RndNet(C.Structure):
     _fields_ = [("w", c_void_p * 4), ("b", c_void_p * 4), ("act", c_int * 4), ("dims", c_int * 5), ("num_layers", c_int)]
 
@@ -137,6 +142,7 @@ _SIGNATURES = {
     "rslrl_empirical_normalize": (c_int, [c_void_p, c_i64, c_i64, c_int, c_void_p, c_void_p, c_double, c_void_p, c_i64,
                                           c_void_p]),
     "rslrl_fill_zero": (c_int, [c_void_p, c_i64, c_void_p]),
+    "rslrl_store_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "rslrl_rnd_reward": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_double, c_void_p]),
     "rslrl_convert_f32_f16": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_i64, c_int, c_int, c_void_p]),
 }

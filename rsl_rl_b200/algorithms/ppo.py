@@ -164,6 +164,7 @@ class PPO:
         self._update_reason = "RND" if self.rnd is not None else ("symmetry" if self.symmetry is not None else None)
         self._recurrent_fused = False
         self._rc = None   # per-update cache of the fused recurrent path
+        self._in_place_actions = None
         self._host_actions, self._host_actions_id = None, 0   # pinned [2, N, A] ring the act kernel also writes (host envs)
         self.last_host_actions = None   # the ring slot the most recent act() wrote, valid after a stream synchronisation
         self._graph = None
@@ -343,6 +344,7 @@ class PPO:
                 plan["graph"].replay()
                 nat.lib().rslrl_add_launch_count(plan["launches"])
         tr.actions, tr.values = act_s, val_s
+        self._in_place_actions = act_s   # process_env_step recognises the in-place row by identity
         tr.actions_log_prob = logp_s.view(-1)
         tr.action_mean, tr.action_sigma = mu_s, sig_s
         tr.observations = obs
@@ -414,7 +416,8 @@ class PPO:
             self.intrinsic_rewards = self.rnd.get_intrinsic_reward(obs)
             intrinsic = self.intrinsic_rewards
         time_outs = extras["time_outs"] if "time_outs" in extras else None
-        if self.rollout_fused and tr.actions is not None and tr.actions.data_ptr() == self.storage.actions[self.storage.step].data_ptr():
+        if tr.actions is not None and tr.actions is self._in_place_actions:   # act() wrote row `step` in place
+            self._in_place_actions = None
             if tr.hidden_states is not None:
                 self.storage._save_hidden_states(tr.hidden_states)
             self.storage._store_in_place(tr.observations, rewards, dones, time_outs, intrinsic, self.gamma)

@@ -226,6 +226,32 @@ int rslrl_store_transition(int n_groups, const float* const* obs_src_host, float
   return finish_launch(what);
 }
 
+int rslrl_store_step(const rslrl_store_plan_t* plan, const float* const* obs_src_host, const float* rewards,
+                     const void* dones, int dones_dtype, const void* time_outs, int time_outs_dtype,
+                     const float* intrinsic, rslrl_stream_t stream) {
+  using namespace rslrl;
+  const char* what = "rslrl_store_step";
+  RSLRL_CHECK_ARG(plan && obs_src_host && rewards && dones, what);
+  RSLRL_CHECK_ARG(plan->n_groups >= 0 && plan->n_groups <= RSLRL_MAX_SEGMENTS && plan->N > 0, what);
+  RSLRL_CHECK_ARG(!time_outs || plan->values_row, what);
+  StoreParams p{};
+  long long max_units = plan->N;
+  for (int g = 0; g < plan->n_groups; ++g) {
+    RSLRL_CHECK_ARG(obs_src_host[g] && plan->obs_dst[g], what);
+    const long long count = (long long)plan->N * plan->obs_dim[g];
+    p.copy[p.n_copy++] = CopySeg{obs_src_host[g], plan->obs_dst[g], count};
+    if (count > max_units) max_units = count;
+  }
+  p.rewards = rewards; p.values = plan->values_row; p.intrinsic = intrinsic; p.time_outs = time_outs; p.dones = dones;
+  p.rewards_row = plan->rewards_row; p.dones_row = plan->dones_row;
+  p.time_outs_dtype = time_outs_dtype; p.dones_dtype = dones_dtype;
+  p.gamma = (float)plan->gamma; p.N = plan->N; p.A = plan->A;
+  dim3 grid(grid_for(max_units / 4 + 1), p.n_copy + 1);
+  prefer_max_smem(store_transition_kernel);
+  store_transition_kernel<<<grid, kCopyThreads, 0, (cudaStream_t)stream>>>(p);
+  return finish_launch(what);
+}
+
 int rslrl_permute_gather(int n_fields, const float* const* src_host, float* const* dst_host,
                          const int* row_floats_host, const int* dst_stride_host, const int* dst_col_host,
                          const int64_t* idx, int64_t n_rows, rslrl_stream_t stream) {

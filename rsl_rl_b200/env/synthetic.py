@@ -46,14 +46,15 @@ class SynthVecEnv(VecEnv):
         self._done_blk = done.long()
         self._to_blk = (torch.rand(b, n, generator=g, device=dev) < self.p_timeout) & done
         # per-step views made once per block: step() then costs no tensor operations at all
-        self._obs_rows = [{k: v[j] for k, v in self._obs_blk.items()} for j in range(b + 1)]
+        self._obs_rows = [TensorDict({k: v[j] for k, v in self._obs_blk.items()}, batch_size=[self.num_envs], device=dev)
+                          for j in range(b + 1)]
         self._rew_rows, self._done_rows, self._to_rows = (list(t.unbind(0)) for t in
                                                           (self._rew_blk, self._done_blk, self._to_blk))
         self._i = 0
         self._j = 0
 
     def _next_obs(self):
-        obs = TensorDict(self._obs_rows[self._j], batch_size=[self.num_envs], device=self.device)
+        obs = self._obs_rows[self._j]
         self._j += 1
         return obs
 

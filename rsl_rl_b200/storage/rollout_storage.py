@@ -23,6 +23,17 @@ from ..utils.tensordict_lite import TensorDict, is_tensordict_like
 from ..utils.utils import TrajectoryIndex
 
 
+_FLAGS = nat._FLAG_DTYPES
+_store_step_fn = None
+
+
+def _store_step():
+    global _store_step_fn
+    if _store_step_fn is None:
+        _store_step_fn = nat.lib().rslrl_store_step
+    return _store_step_fn
+
+
 class RolloutStorage:
     class Transition:
         """One env step of data (reference rollout_storage.py:15-29)."""
@@ -137,40 +148,58 @@ class RolloutStorage:
     def _store_in_place(self, obs, rewards, dones, time_outs=None, intrinsic=None, gamma: float = 0.0):
         """Fast path of `_store` for PPO's fused rollout: actions / mean / sigma / value / log-prob of this step
         were already written into row `step` by `PPO.act`, so only observations, rewards (with the bootstrap)
-        and dones move.  Argument arrays are built once per step index and patched with the source pointers."""
+        and dones move.  Everything fixed for a step index sits in a C-side plan (`rslrl_store_plan_t`) built once; per
+        env step only the source pointers cross the ctypes boundary."""
         s = self.step
         if s >= self.num_transitions_per_env:
             raise OverflowError("Rollout buffer overflow! You should call clear() before adding new transitions.")
         plan = self._store_plans.get(s)
-        if plan is None:
-            dsts = [self.observations[k][s] for k in self._obs_keys]
-            plan = (nat.void_array([0] * len(dsts)), nat.void_array([d.data_ptr() for d in dsts]),
-                    nat.int_array([int(d[0].numel()) for d in dsts]), self.values[s].data_ptr(),
-                    self.rewards[s].data_ptr(), self.dones[s].data_ptr())
+        if plan is None or plan[2] != gamma:
+            sp = nat.StorePlan()
+            for i, k in enumerate(self._obs_keys):
+                d = self.observations[k][s]
+                sp.obs_dst[i], sp.obs_dim[i] = d.data_ptr(), int(d[0].numel())
+            sp.values_row, sp.rewards_row, sp.dones_row = self.values[s].data_ptr(), self.rewards[s].data_ptr(), self.dones[s].data_ptr()
+            sp.gamma, sp.n_groups, sp.N, sp.A = float(gamma), len(self._obs_keys), self.num_envs, self._A
+            import ctypes
+            plan = (sp, nat.void_array([0] * len(self._obs_keys)), gamma, ctypes.byref(sp))
             self._store_plans[s] = plan
-        src_arr, dst_arr, dim_arr, values_ptr, rew_row, done_row = plan
+        src_arr, plan_ref = plan[1], plan[3]
+        f32 = torch.float32
         keep = []   # converted copies must outlive the launch (their blocks could otherwise be recycled by the
         for i, k in enumerate(self._obs_keys):   # conversions below, which are enqueued before the kernel)
-            src = nat.f32c(obs[k])
-            keep.append(src)
+            src = obs[k]
+            if src.dtype is not f32 or not src.is_contiguous():
+                src = nat.f32c(src)
+                keep.append(src)
+            if not src.is_cuda:
+                nat.require_cuda(src)
             src_arr[i] = src.data_ptr()
-        rewards = nat.f32c(rewards)
-        dones, dcode = nat.flag_tensor(dones)
+        if rewards.dtype is not f32 or not rewards.is_contiguous():
+            rewards = nat.f32c(rewards)
+        dcode = _FLAGS.get(dones.dtype)
+        if dcode is None or not dones.is_contiguous():
+            dones, dcode = nat.flag_tensor(dones)
         to_ptr, tcode = None, 0
         if time_outs is not None:
             if not time_outs.is_cuda and not time_outs.is_pinned():   # pinned host flags are read in place by the kernel
                 time_outs = time_outs.to(self.device)
-            time_outs, tcode = nat.flag_tensor(time_outs)
+            tcode = _FLAGS.get(time_outs.dtype)
+            if tcode is None or not time_outs.is_contiguous():
+                time_outs, tcode = nat.flag_tensor(time_outs)
             to_ptr = time_outs.data_ptr()
-        intr_t = None if intrinsic is None else nat.f32c(intrinsic)
-        nat.require_cuda(intr_t, *keep)
-        nat.require_device_readable(rewards, dones, time_outs)   # device, or pinned host memory read in place
-        nat.check(nat.lib().rslrl_store_transition(
-            len(self._obs_keys), src_arr, dst_arr, dim_arr, None, None, None, 0, values_ptr, None,
-            rewards.data_ptr(), dones.data_ptr(), dcode, to_ptr, tcode, nat.ptr(intr_t), float(gamma), None, None, None,
-            None, None, rew_row, done_row, self.num_envs, self._A, nat.stream_ptr()))
+        intr_t = None
+        if intrinsic is not None:
+            intr_t = nat.f32c(intrinsic)
+            nat.require_cuda(intr_t)
+        if not (rewards.is_cuda and dones.is_cuda and (time_outs is None or time_outs.is_cuda)):
+            nat.require_device_readable(rewards, dones, time_outs)   # device, or pinned host memory read in place
+        rc = _store_step()(plan_ref, src_arr, rewards.data_ptr(), dones.data_ptr(), dcode, to_ptr, tcode,
+                           None if intr_t is None else intr_t.data_ptr(), nat.stream_ptr())
+        if rc:
+            nat.check(rc)
         del keep, intr_t
-        self.step += 1
+        self.step = s + 1
 
     def _save_hidden_states(self, hidden_states):
         """Reference rollout_storage.py:105-122 (LSTM: (h, c) tuples, GRU: single tensors)."""
