@@ -291,9 +291,14 @@ __global__ void __launch_bounds__(tcp_threads(X3), 1) tc_gemm_persistent_kernel(
                                           : make_smem_desc(sa + raw_bytes + k * 32, 16, 1024, kLayoutSw128);
               const uint64_t db_lo = B_MN ? make_smem_desc(sb + raw_bytes + k * MN_KADV, MN_BOX, MN_SBO, MN_LAYOUT)
                                           : make_smem_desc(sb + raw_bytes + k * 32, 16, 1024, kLayoutSw128);
-              umma_tf32(d_tmem, da_lo, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-              umma_tf32(d_tmem, da, db_lo, idesc, 1u);
-              umma_tf32(d_tmem, da, db, idesc, 1u);
+              // The correction terms go to their OWN accumulator (columns 128.. of this TMEM buffer; tiles are at most 128
+              // wide in this mode): the tensor core truncates when it adds into an fp32 accumulator, a coherent bias that
+              // grows with the number of accumulations -- the main chain now sees one addition per k-step instead of three,
+              // and the epilogue adds the two accumulators with one rounding.
+              const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
+              umma_tf32(d_tmem + 128u, da_lo, db, idesc, acc);
+              umma_tf32(d_tmem + 128u, da, db_lo, idesc, 1u);
+              umma_tf32(d_tmem, da, db, idesc, acc);
             } else if (F16) {
               umma_f16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             } else {
@@ -396,6 +401,11 @@ __global__ void __launch_bounds__(tcp_threads(X3), 1) tc_gemm_persistent_kernel(
         const uint32_t taddr = tmem_base + (uint32_t)as * 256u + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
         if (ncols == 32) TMEM_LD_32x32(taddr, v);
         else TMEM_LD_32x16(taddr, v);
+        uint32_t w[X3 ? 32 : 1];   // 3xTF32: the accumulator of the correction terms A_lo B_hi + A_hi B_lo (columns 128..)
+        if constexpr (X3) {
+          if (ncols == 32) TMEM_LD_32x32(taddr + 128u, w);
+          else TMEM_LD_32x16(taddr + 128u, w);
+        }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (c + 2 >= nchunks) {  // last TMEM read of this tile by this warp: hand the accumulator back
           tcgen05_fence_before();
@@ -409,6 +419,15 @@ __global__ void __launch_bounds__(tcp_threads(X3), 1) tc_gemm_persistent_kernel(
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i) x[i] = (i < 16) ? __uint_as_float(v[i]) : 0.f;
+        }
+        if constexpr (X3) {   // main + correction accumulator: one rounding
+          if (ncols == 32) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) x[i] += __uint_as_float(w[i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[i] += __uint_as_float(w[i]);
+          }
         }
 
         if (MODE == TC_DGRAD) {

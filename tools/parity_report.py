@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Measured parity of the CUDA path against the numpy oracle at benchmark shapes, per GEMM precision.
 
-    python tools/parity_report.py [--out profiles/parity_r2.json] [--shapes c1,c3] [--precisions fp32,tf32,fp16]
+    python tools/parity_report.py [--out profiles/parity_r2.json] [--shapes c1,c3] [--precisions tf32x3,fp32,tf32,fp16]
 
 For each (shape, precision): one full learn() iteration (rollout on a recorded synthetic stream, GAE, 5 x 4 minibatches)
 with the noise and the permutation shared with the oracle; errors are max-abs error / max-abs reference value (SURVEY
@@ -187,7 +187,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "parity_r2.json"))
     ap.add_argument("--shapes", default="c1,c3")
-    ap.add_argument("--precisions", default="fp32,tf32,fp16")
+    ap.add_argument("--precisions", default="tf32x3,fp32,tf32,fp16")
     args = ap.parse_args()
     rows = []
     for shape in args.shapes.split(","):
@@ -196,7 +196,7 @@ def main():
             rows.append(r)
             print(json.dumps({k: v for k, v in r.items() if k != "params_after.max_norm_per_step"}), flush=True)
     floors = []
-    if "tf32" in args.precisions or "fp16" in args.precisions:
+    if "tf32" in args.precisions.split(",") or "fp16" in args.precisions.split(","):
         for shape in args.shapes.split(","):
             floors.append(tf32_noise_floor(shape))
             print(json.dumps(floors[-1]), flush=True)
