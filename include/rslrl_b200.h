@@ -210,6 +210,25 @@ int rslrl_linear_backward_data(int n, const rslrl_linear_bwd_data_t* probs_host,
                                rslrl_stream_t stream);
 int rslrl_linear_backward_weight(int n, const rslrl_linear_bwd_weight_t* probs_host, int precision,
                                  rslrl_stream_t stream);
+/* Fused data-gradient chain of the two wide hidden layers of a 3-hidden-layer MLP on the fp16-storage path
+ * (autograd of rsl_rl/networks/mlp.py:106-114 for layers 3 and 2, both nets in one launch):
+ *   dz2 = (dz3 w3) * act'(h2),   dz1 = (dz2 w2) * act'(h1)
+ * The dz2 tile stays in shared memory between the two products (it is still stored: the weight gradient of layer 2
+ * needs it).  All tensors fp16 with 16-byte aligned rows; w3 [N3,N2] and w2 [N2,N1] are the fp16 weight shadows.
+ * Returns 4 when the shape is not eligible (N3 in {64,128}, N2 in {128,256}, N1 in {128,256,512}, equal shapes for all nets):
+ * the caller then issues two rslrl_linear_backward_data launches. */
+typedef struct {
+  const void* dz3; /* [M,N3], row stride ld_dz3 */
+  const void* w3;
+  const void* w2;
+  const void* h2;  /* [M,N2], row stride ldh2: saved activation of hidden layer 2 */
+  const void* h1;  /* [M,N1], row stride ldh1 */
+  void* dz2;       /* [M,N2] out, row stride ld_dz2 */
+  void* dz1;       /* [M,N1] out, row stride ld_dz1 */
+  int M, N1, N2, N3, ld_dz3, ldh2, ldh1, ld_dz2, ld_dz1, act;
+} rslrl_dgrad_chain_t;
+int rslrl_dgrad_chain16(int n, const rslrl_dgrad_chain_t* nets_host, rslrl_stream_t stream);
+
 /* Backward of a NARROW layer (N <= 12: the action and value heads), data- and weight-gradient fused in one fp32
  * launch that reads h and writes dx exactly once.  Returns a non-zero code (message via rslrl_last_error) if a
  * problem does not qualify (N > 12, K % 4 != 0, unaligned rows); callers then use the two general calls. */

@@ -72,6 +72,12 @@ class LossHead(C.Structure):
                 ("dz_actor", c_void_p), ("dz_critic", c_void_p), ("K3", c_int), ("ldh", c_int), ("act", c_int)]
 
 
+class DgradChain(C.Structure):
+    _fields_ = [("dz3", c_void_p), ("w3", c_void_p), ("w2", c_void_p), ("h2", c_void_p), ("h1", c_void_p), ("dz2", c_void_p),
+                ("dz1", c_void_p), ("M", c_int), ("N1", c_int), ("N2", c_int), ("N3", c_int), ("ld_dz3", c_int),
+                ("ldh2", c_int), ("ldh1", c_int), ("ld_dz2", c_int), ("ld_dz1", c_int), ("act", c_int)]
+
+
 class StorePlan(C.Structure):
     _fields_ = [("obs_dst", c_void_p * 16), ("obs_dim", c_int * 16), ("values_row", c_void_p), ("rewards_row", c_void_p),
                 ("dones_row", c_void_p), ("gamma", c_double), ("n_groups", c_int), ("N", c_int), ("A", c_int)]
@@ -142,6 +148,7 @@ _SIGNATURES = {
     "rslrl_empirical_normalize": (c_int, [c_void_p, c_i64, c_i64, c_int, c_void_p, c_void_p, c_double, c_void_p, c_i64,
                                           c_void_p]),
     "rslrl_fill_zero": (c_int, [c_void_p, c_i64, c_void_p]),
+    "rslrl_dgrad_chain16": (c_int, [c_int, c_void_p, c_void_p]),
     "rslrl_store_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "rslrl_rnd_reward": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_double, c_void_p]),
     "rslrl_convert_f32_f16": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_i64, c_int, c_int, c_void_p]),

@@ -136,6 +136,13 @@ class FeedForwardEngine:
         self.scale_state = None
         self._scale_calibrated = False
         self._head_struct = None
+        # the two middle layers' data gradients as one fused launch (fp16 chain, 3 hidden layers, equal shapes and
+        # activations in both nets, N2 in {128, 256}, N1 in {128, 256, 512}); RSLRL_DGRAD_CHAIN=0: two launches
+        a, c = self.actor, self.critic
+        self.dgrad_chain = (self.f16 and a.L == 4 and c.L == 4 and a.dims[1:4] == c.dims[1:4] and a.acts[:3] == c.acts[:3]
+                            and a.acts[0] == a.acts[1] and a.dims[3] in (64, 128)
+                            and a.dims[2] in (128, 256) and a.dims[1] in (128, 256, 512)
+                            and os.environ.get("RSLRL_DGRAD_CHAIN", "1") != "0")
         # output-layer data gradient fused into the loss kernel (same hidden width and activation in both nets)
         self.fused_head_dgrad = (self.head16 and self.actor.dims[-2] == self.critic.dims[-2]
                                  and self.actor.dims[-2] % 32 == 0 and self.actor.dims[-2] <= 128
@@ -419,6 +426,7 @@ class FeedForwardEngine:
                 hprobs.append((d_out, lin.weight, hs[l - 1][:M], dz(net, gbuf, l), lin.weight.grad, lin.bias.grad,
                                net.acts[l - 1], S))
             linear_backward_head(hprobs)
+        chained = self._dgrad_chain(M, nets, dz)   # both middle layers' data gradients of both nets in ONE launch
         for l in range(self.actor.L - 2, -1, -1):
             dprobs = []
             for net, hs, gbuf, x_in, _ in nets:
@@ -426,12 +434,29 @@ class FeedForwardEngine:
                 inp = x_in if l == 0 else hs[l - 1][:M]
                 dy = dz(net, gbuf, l + 1)
                 wprobs.append((dy, inp, lin.weight.grad, lin.bias.grad, inv_s, inv_dev))
-                if l > 0:
+                if l > 0 and not chained:
                     dprobs.append((dy, self.group.shadow16(lin.weight), inp, dz(net, gbuf, l), net.acts[l - 1]))
             if dprobs:
                 linear_backward_data(dprobs, prec)
         wprobs.sort(key=lambda p: -(p[2].shape[0] * p[2].shape[1]))   # heaviest tiles first in the round-robin schedule
         linear_backward_weight(wprobs, prec)
+
+    def _dgrad_chain(self, M: int, nets, dz) -> bool:
+        """dZ2 = (dZ3 W3) * act'(H2), dZ1 = (dZ2 W2) * act'(H1) for actor and critic in one launch
+        (`rslrl_dgrad_chain16`, csrc/dgrad_fused.cu).  False: not eligible / switched off (two layer-by-layer launches)."""
+        if not self.dgrad_chain:
+            return False
+        arr = (nat.DgradChain * 2)()
+        for i, (net, hs, gbuf, _, _) in enumerate(nets):
+            l3, l2 = net.layers[2], net.layers[1]
+            d3, d2, d1 = dz(net, gbuf, 3), dz(net, gbuf, 2), dz(net, gbuf, 1)
+            h2, h1 = hs[1][:M], hs[0][:M]
+            arr[i] = nat.DgradChain(d3.data_ptr(), self.group.shadow16(l3.weight).data_ptr(),
+                                    self.group.shadow16(l2.weight).data_ptr(), h2.data_ptr(), h1.data_ptr(), d2.data_ptr(),
+                                    d1.data_ptr(), M, net.dims[1], net.dims[2], net.dims[3], d3.stride(0), h2.stride(0),
+                                    h1.stride(0), d2.stride(0), d1.stride(0), net.acts[1])
+        nat.check(nat.lib().rslrl_dgrad_chain16(2, arr, nat.stream_ptr()))
+        return True
 
     def _loss_head(self, rows: int):
         """rslrl_loss_head_t for the loss launch: the data gradient of the two output layers fused into the loss kernel

@@ -162,3 +162,42 @@ def test_fp16_convert_strided_and_flat():
     nat.check(nat.lib().rslrl_convert_f32_f16(flat.data_ptr(), flat.numel(), out.data_ptr(), flat.numel(), 1,
                                               flat.numel(), flat.numel(), nat.stream_ptr()))
     assert torch.equal(out, flat.half())
+
+
+@pytest.mark.parametrize("M,N1,N2,N3,act", [(24576, 512, 256, 128, "elu"), (1000, 512, 256, 128, "elu"), (4096, 256, 128, 64, "tanh"),
+                                            (333, 128, 128, 64, "relu")])
+def test_fp16_dgrad_chain_matches_two_layerwise_launches(M, N1, N2, N3, act):
+    """rslrl_dgrad_chain16 (dZ2 and dZ1 of both nets in one launch, the dZ2 tile feeding the second product from shared
+    memory) against two rslrl_linear_backward_data launches (same fp16 operands, fp32 accumulation) and against fp64."""
+    import ctypes
+    from rsl_rl_b200.networks.mlp import linear_backward_data
+    nat = _nat()
+    torch.manual_seed(M + N1)
+    f = {"elu": torch.nn.functional.elu, "tanh": torch.tanh, "relu": torch.relu}[act]
+    code = nat.ACT_CODES[act]
+    arr, nets = (nat.DgradChain * 2)(), []
+    for i in range(2):
+        h1, h2 = f(torch.randn(M, N1, device=DEV)).half(), f(torch.randn(M, N2, device=DEV)).half()
+        w3, w2 = (torch.randn(N3, N2, device=DEV) / N3 ** 0.5).half(), (torch.randn(N2, N1, device=DEV) / N2 ** 0.5).half()
+        dz3 = torch.randn(M, N3, device=DEV).half()
+        dz2 = torch.full((M, N2), float("nan"), device=DEV, dtype=torch.float16)
+        dz1 = torch.full((M, N1), float("nan"), device=DEV, dtype=torch.float16)
+        arr[i] = nat.DgradChain(dz3.data_ptr(), w3.data_ptr(), w2.data_ptr(), h2.data_ptr(), h1.data_ptr(), dz2.data_ptr(),
+                                dz1.data_ptr(), M, N1, N2, N3, N3, N2, N1, N2, N1, code)
+        nets.append((h1, h2, w3, w2, dz3, dz2, dz1))
+    for _ in range(2):   # twice: the kernel must leave nothing behind
+        nat.check(nat.lib().rslrl_dgrad_chain16(2, arr, nat.stream_ptr()))
+    torch.cuda.synchronize()
+    for h1, h2, w3, w2, dz3, dz2, dz1 in nets:
+        r2 = torch.empty_like(dz2)
+        r1 = torch.empty_like(dz1)
+        linear_backward_data([(dz3, w3, h2, r2, code)], nat.PREC_FP16)
+        linear_backward_data([(r2, w2, h1, r1, code)], nat.PREC_FP16)
+        torch.cuda.synchronize()
+        assert torch.equal(dz2, r2)
+        assert rel_err(dz1.float().cpu().numpy(), r1.float().cpu().numpy()) < 1e-6
+        grad = {"elu": lambda h: np.where(h > 0, 1.0, h + 1.0), "tanh": lambda h: 1 - h ** 2, "relu": lambda h: (h > 0) * 1.0}[act]
+        ref2 = (dz3.double() @ w3.double()).cpu().numpy() * grad(h2.double().cpu().numpy())
+        assert rel_err(dz2.float().cpu().numpy(), ref2) < TOL
+        ref1 = (dz2.double() @ w2.double()).cpu().numpy() * grad(h1.double().cpu().numpy())
+        assert rel_err(dz1.float().cpu().numpy(), ref1) < TOL
