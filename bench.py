@@ -570,8 +570,10 @@ def run_ours(args):
                                       f"minibatch ({traffic_src})" if traffic is not None else
                                       "no ncu --set full capture of this build / mode under profiles/"),
                         kernel=("sgemm_kernel (fp32 CUDA-core FMA)" if args.precision == "fp32"
-                                else f"mlp3_forward_kernel + tc_gemm_persistent_kernel<dgrad|wgrad> ({args.precision} tcgen05): "
-                                     "all dense launches of one minibatch forward + backward"),
+                                else ("mlp3_forward_kernel + dgrad_chain16_kernel + tc_gemm_persistent_kernel<wgrad> (fp16 tcgen05): "
+                                      "all dense launches of one minibatch forward + backward" if args.precision == "fp16" else
+                                      f"mlp3_forward_kernel / tc_gemm_persistent_kernel<fwd|dgrad|wgrad> ({args.precision} "
+                                      "tcgen05): all dense launches of one minibatch forward + backward")),
                         avg_launch_us=dom["avg_launch_us"], flops_per_launch=dom["flops_per_launch"],
                         launches_per_minibatch=dom["launches_per_minibatch"], us_per_minibatch=1e3 * dom["ms_per_minibatch"],
                         peak_source=peaks["source"] + ", bf16 dense BURST peak (the dense launches are timed alone in "

@@ -105,7 +105,10 @@ int rslrl_store_step(const rslrl_store_plan_t* plan, const float* const* obs_src
 /* RolloutStorage.compute_returns (rsl_rl/storage/rollout_storage.py:127-149): reverse GAE scan over T
  * with done masking, returns, advantages = returns - values, and (normalize != 0) the global
  * rewards/values/returns/advantages: [T,N] fp32, dones: [T,N] u8, last_values: [N].
- * (adv - mean) / (std_unbiased + 1e-8) normalisation, in ONE kernel (grid barrier inside).
+ * (adv - mean) / (std_unbiased + 1e-8) normalisation, in ONE kernel.  N % 16 == 0 and T <= 32: inputs staged through
+ * shared memory with bulk copies; up to 8 192 envs the grid is one thread-block cluster (statistics over distributed
+ * shared memory), above that a cooperative launch with a grid barrier; other shapes: register / grid-stride kernels with
+ * the same barrier.  Returns and un-normalised advantages are bit-identical to the reference's fp32 op order.
  * workspace: rslrl_gae_workspace_bytes(N) bytes of device scratch, zero-initialised ONCE by the caller
  * (the kernel re-arms it); one workspace must not be shared by launches that may run concurrently. */
 int64_t rslrl_gae_workspace_bytes(int N);
