@@ -53,6 +53,23 @@ struct alignas(64) DcBatch {
   DcNet net[2];
 };
 
+// Optional in-kernel timeline (build with -DRSLRL_DC_TRACE; profiles/experiments/dgrad_chain_trace.py): per CTA 64 slots:
+// 0 entry, 1 prologue done, then per tile j < 3 (base 2 + 20 j): +0 S1 operands landed, +1 S1 issued, +2+p pass p issued
+// (MMA warp), +8 E1 done, +9+p epilogue of pass p done (epilogue warp 0 / warp 8 for odd passes).
+#ifdef RSLRL_DC_TRACE
+__device__ unsigned long long g_dc_trace[148 * 64];
+__device__ __forceinline__ void dc_trace(int slot) {
+  if (slot < 64) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    g_dc_trace[blockIdx.x * 64 + slot] = t;
+  }
+}
+#define DC_TRACE(cond, slot) do { if (cond) dc_trace(slot); } while (0)
+#else
+#define DC_TRACE(cond, slot) do { } while (0)
+#endif
+
 __device__ __forceinline__ void dc_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -75,6 +92,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dgrad_chain16_kernel(const __gr
   uint32_t* const tmem_ptr_smem = (uint32_t*)(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  DC_TRACE(threadIdx.x == 0, 0);
   if (warp == 0 && elect_one()) {
     for (int i = 0; i < n_nets; ++i) {
       const DcNet& P = batch.net[i];
@@ -113,6 +131,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dgrad_chain16_kernel(const __gr
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  DC_TRACE(threadIdx.x == 0, 1);
 
   const int tiles_m = (batch.net[0].M + TC_BLOCK_M - 1) / TC_BLOCK_M;
   const int total = tiles_m * n_nets;
@@ -198,6 +217,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dgrad_chain16_kernel(const __gr
         const int sa_stage = it % DC_OP_STAGES;
         mbar_wait(&op_full[sa_stage], (it / DC_OP_STAGES) & 1);
         ++it;
+        DC_TRACE(lane == 0 && j < 3, 2 + 20 * j);
         const uint32_t a_base = smem_u32(opring + (size_t)sa_stage * DC_OP_STAGE_BYTES);
         for (int kb = 0; kb < nkb1; ++kb, ++it) {
           const int s = it % DC_OP_STAGES;
@@ -211,6 +231,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dgrad_chain16_kernel(const __gr
           __syncwarp();
         }
         publish();
+        DC_TRACE(lane == 0 && j < 3, 2 + 20 * j + 1);
       }
       // ---- second product, NH passes of 128 columns, A = the granules the first epilogue leaves in shared memory
       for (int h = 0; h < NH; ++h) {
@@ -234,6 +255,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dgrad_chain16_kernel(const __gr
           __syncwarp();
         }
         publish();
+        DC_TRACE(lane == 0 && j < 3 && h < 6, 2 + 20 * j + 2 + h);
       }
     }
   } else if (warp == 2) {
@@ -336,10 +358,12 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dgrad_chain16_kernel(const __gr
 
       // ---- first epilogue: accumulator x act'(H2) -> dZ2 granules (+ bulk store of dZ2)
       run_job(true, nch1, 0, &P.map_dz2, 0);
+      DC_TRACE(ew == 0 && lane == 0 && j < 3, 2 + 20 * j + 8);
       // ---- second epilogue per pass: accumulator x act'(H1) -> dZ1 (bulk store); passes alternate between the group pairs
       for (int h = 0; h < NH; ++h) {
         run_job(false, nch2, 2 * (h & 1), &P.map_dz1, h * NB2);
         g += nch2;
+        DC_TRACE(ew == 8 * (h & 1) && lane == 0 && j < 3 && h < 6, 2 + 20 * j + 9 + h);
       }
     }
     tcgen05_fence_before();
@@ -404,3 +428,9 @@ extern "C" int rslrl_dgrad_chain16(int n, const rslrl_dgrad_chain_t* nets_host, 
   launch_chain_kernel(dgrad_chain16_kernel, dim3(grid), dim3(DC_THREADS), smem, (cudaStream_t)stream, b, n);
   return finish_launch(what);
 }
+
+#ifdef RSLRL_DC_TRACE
+extern "C" int rslrl_debug_read_trace_dgrad_chain(unsigned long long* host) {
+  return (int)cudaMemcpyFromSymbol(host, rslrl::g_dc_trace, sizeof(unsigned long long) * 148 * 64);
+}
+#endif
