@@ -274,6 +274,109 @@ def scenario_ppo_mlp(out_dir, name, *, num_envs, num_steps, group_dims, obs_grou
     print("wrote", path, f"{os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def scenario_distillation(out_dir, name, *, num_envs, num_steps, group_dims, obs_groups, teacher_groups, num_actions,
+                          hidden, activation, policy_class, policy_extra, teacher_class, teacher_extra, alg_overrides,
+                          iterations, seed=0, p_done=0.1):
+    """Teacher-student distillation: `DistillationRunner.learn` of the unmodified reference
+    (runners/distillation_runner.py:56-150, algorithms/distillation.py:84-150) with the teacher taken from a reference
+    PPO policy's state dict (student_teacher.py:168-206: `actor.*` -> `teacher.*`).  Recorded per iteration: the env
+    stream, the sampling noise, the rollout buffer, the parameters after every optimiser step, the loss, the carried
+    hidden states."""
+    import torch
+    import rsl_rl.modules as ref_modules
+    from rsl_rl.runners import DistillationRunner
+
+    RecordingEnv = make_env_class()
+    torch.manual_seed(seed)
+    env = RecordingEnv(num_envs, group_dims, num_actions, seed=seed + 100, p_done=p_done)
+    # the "RL checkpoint" the teacher comes from: a reference actor-critic whose policy set is the teacher's observations
+    obs0 = env.get_observations()
+    teacher_policy = getattr(ref_modules, teacher_class)(
+        obs0, {"policy": list(teacher_groups), "critic": list(teacher_groups)}, num_actions,
+        actor_hidden_dims=list(hidden), critic_hidden_dims=list(hidden), activation=activation, **teacher_extra)
+    if teacher_extra.get("actor_obs_normalization"):
+        g = torch.Generator().manual_seed(seed + 5)
+        for _ in range(3):   # non-trivial running statistics in the checkpoint
+            fake = {k: 1.5 * torch.randn(num_envs, d, generator=g) + 0.3 for k, d in group_dims.items()}
+            teacher_policy.update_normalization(fake)
+    teacher_sd = teacher_policy.state_dict()
+    alg = dict(class_name="Distillation", num_learning_epochs=1, gradient_length=15, learning_rate=1e-3,
+               max_grad_norm=None, loss_type="mse", optimizer="adam")
+    alg.update(alg_overrides)
+    cfg = dict(num_steps_per_env=num_steps, save_interval=10 ** 9, obs_groups={k: list(v) for k, v in obs_groups.items()},
+               policy=dict(class_name=policy_class, student_hidden_dims=list(hidden), teacher_hidden_dims=list(hidden),
+                           activation=activation, init_noise_std=0.1, **policy_extra),
+               algorithm=dict(alg))
+    meta = dict(num_envs=num_envs, num_steps=num_steps, num_actions=num_actions, hidden=list(hidden),
+                activation=activation, iterations=iterations, obs_groups={k: list(v) for k, v in obs_groups.items()},
+                group_dims=dict(group_dims), alg={k: v for k, v in alg.items() if k != "class_name"},
+                policy_class=policy_class, policy_extra=dict(policy_extra), teacher_class=teacher_class,
+                teacher_groups=list(teacher_groups), teacher_extra=dict(teacher_extra))
+    data = {}
+    for k, v in teacher_sd.items():
+        data[f"teacher_ckpt.{k}"] = v.detach().numpy().copy()
+    with Recorder() as rec:
+        runner = DistillationRunner(env, cfg, log_dir=tempfile.mkdtemp(prefix="golden_"), device="cpu")
+        resumed = runner.alg.policy.load_state_dict(teacher_sd)
+        assert resumed is False and runner.alg.policy.loaded_teacher
+        rec.watch_optimizer(runner.alg.optimizer, runner.alg.policy)
+        for k, v in _state_arrays(runner.alg.policy).items():
+            data[f"init.{k}"] = v
+        meta["param_names"] = [k for k, _ in runner.alg.policy.named_parameters()]
+        meta["student_param_names"] = ["student." + k for k, _ in runner.alg.policy.student.named_parameters()]
+        losses = []
+        orig_update = runner.alg.update
+        snap = {}
+
+        def update_and_record():
+            st = runner.alg.storage
+            for kk, vv in st.observations.items():
+                snap[f"obs.{kk}"] = vv.numpy().copy()
+            for kk in ("actions", "privileged_actions", "rewards", "dones"):
+                snap[kk] = getattr(st, kk).numpy().copy()
+            out = orig_update()
+            losses.append(out)
+            return out
+
+        runner.alg.update = update_and_record
+        for it in range(iterations):
+            n_norm, n_clip, n_step = len(rec.normal_z), len(rec.clip_calls), len(rec.step_calls)
+            first_obs, first_step = len(env.obs_log) - 1, len(env.rew_log)
+            runner.learn(1)
+            p = f"it{it}."
+            T = num_steps
+            for g in group_dims:
+                data[p + f"stream.obs.{g}"] = np.stack([env.obs_log[first_obs + t][g] for t in range(T + 1)])
+            data[p + "stream.rewards"] = np.stack(env.rew_log[first_step:first_step + T])
+            data[p + "stream.dones"] = np.stack(env.done_log[first_step:first_step + T])
+            zs = rec.normal_z[n_norm:]
+            assert len(zs) == T, len(zs)
+            data[p + "z_rollout"] = np.stack(zs)
+            for kk, vv in snap.items():
+                data[p + "storage." + kk] = vv
+            clips, steps = rec.clip_calls[n_clip:], rec.step_calls[n_step:]
+            if clips:
+                data[p + "mb.raw_grads"] = np.stack([c[0] for c in clips])     # student MLP gradients only
+                data[p + "mb.total_norm"] = np.array([c[1] for c in clips])
+            data[p + "mb.lr"] = np.array([s[0] for s in steps])
+            data[p + "mb.params_after"] = np.stack([s[1] for s in steps])
+            data[p + "loss.behavior"] = np.array(losses[-1]["behavior"], dtype=np.float64)
+            for k, v in _state_arrays(runner.alg.policy).items():
+                data[p + f"final.{k}"] = v
+            hs = runner.alg.last_hidden_states
+            if hs is not None:
+                for tag, h in zip(("s", "t"), hs):
+                    if h is None:
+                        continue
+                    for i, x in enumerate(h if isinstance(h, tuple) else (h,)):
+                        data[p + f"hidden_{tag}{i}"] = x.detach().numpy().copy()
+            data[p + "num_updates"] = np.array(runner.alg.num_updates)
+    data["meta"] = np.array(repr(meta))
+    path = os.path.join(out_dir, name + ".npz")
+    np.savez_compressed(path, **data)
+    print("wrote", path, f"{os.path.getsize(path) / 1024:.0f} KiB")
+
+
 def scenario_loss_terms(out_dir):
     """Per-minibatch loss values + autograd gradients w.r.t. (mu, sigma, value) from the reference's
     own expressions, evaluated through a real PPO.update() with the optimiser step recorded."""
@@ -482,6 +585,41 @@ def main():
         activation="elu", noise_std_type="scalar", alg_overrides=dict(num_learning_epochs=2), iterations=3, seed=18,
         rnd_cfg=dict(weight=1.0, weight_schedule=None, reward_normalization=True, state_normalization=True,
                      learning_rate=1e-3, num_outputs=1, predictor_hidden_dims=[-1], target_hidden_dims=[-1]))
+    # state-dependent standard deviation (second actor head, actor_critic.py:119-128), GRU memories
+    # (networks/memory.py:23) and teacher-student distillation
+    todo["ppo_sdstd_log_small"] = lambda: scenario_ppo_mlp(
+        args.out, "ppo_sdstd_log_small", num_envs=48, num_steps=6, group_dims={"policy": 11},
+        obs_groups={"policy": ["policy"], "critic": ["policy"]}, num_actions=4, hidden=[24, 12],
+        activation="elu", noise_std_type="log", alg_overrides=dict(num_learning_epochs=2), iterations=2, seed=21,
+        policy_extra=dict(state_dependent_std=True))
+    todo["ppo_sdstd_scalar_small"] = lambda: scenario_ppo_mlp(
+        args.out, "ppo_sdstd_scalar_small", num_envs=48, num_steps=6, group_dims={"policy": 11},
+        obs_groups={"policy": ["policy"], "critic": ["policy"]}, num_actions=4, hidden=[24, 12],
+        activation="tanh", noise_std_type="scalar", alg_overrides=dict(num_learning_epochs=2), iterations=2, seed=22,
+        policy_extra=dict(state_dependent_std=True))
+    todo["ppo_gru_small"] = lambda: scenario_ppo_mlp(
+        args.out, "ppo_gru_small", num_envs=32, num_steps=8, group_dims={"policy": 10},
+        obs_groups={"policy": ["policy"], "critic": ["policy"]}, num_actions=3, hidden=[24, 12],
+        activation="elu", noise_std_type="scalar", alg_overrides=dict(num_learning_epochs=2), iterations=2, seed=23,
+        p_done=0.15, policy_class="ActorCriticRecurrent",
+        policy_extra=dict(rnn_type="gru", rnn_hidden_dim=16, rnn_num_layers=1))
+    todo["distill_mlp_small"] = lambda: scenario_distillation(
+        args.out, "distill_mlp_small", num_envs=48, num_steps=10, group_dims={"policy": 9, "priv": 5},
+        obs_groups={"policy": ["policy"], "teacher": ["policy", "priv"]}, teacher_groups=["policy", "priv"],
+        num_actions=3, hidden=[24, 12], activation="elu", policy_class="StudentTeacher",
+        policy_extra=dict(student_obs_normalization=True, teacher_obs_normalization=True, noise_std_type="scalar"),
+        teacher_class="ActorCritic", teacher_extra=dict(actor_obs_normalization=True),
+        alg_overrides=dict(num_learning_epochs=2, gradient_length=4, max_grad_norm=1.0, loss_type="mse"),
+        iterations=2, seed=31)
+    todo["distill_lstm_small"] = lambda: scenario_distillation(
+        args.out, "distill_lstm_small", num_envs=32, num_steps=8, group_dims={"policy": 10, "priv": 4},
+        obs_groups={"policy": ["policy"], "teacher": ["policy", "priv"]}, teacher_groups=["policy", "priv"],
+        num_actions=3, hidden=[24, 12], activation="elu", policy_class="StudentTeacherRecurrent",
+        policy_extra=dict(noise_std_type="log", rnn_type="lstm", rnn_hidden_dim=16, rnn_num_layers=1,
+                          teacher_recurrent=True),
+        teacher_class="ActorCriticRecurrent", teacher_extra=dict(rnn_type="lstm", rnn_hidden_dim=16, rnn_num_layers=1),
+        alg_overrides=dict(num_learning_epochs=1, gradient_length=3, max_grad_norm=0.5, loss_type="huber"),
+        iterations=2, seed=32, p_done=0.15)
     for name, fn in todo.items():
         if args.only in (None, name):
             fn()

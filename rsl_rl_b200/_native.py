@@ -216,9 +216,20 @@ def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+def on_device(t: torch.Tensor) -> bool:
+    """Whether `t` lives in memory the kernels can address (the one predicate every "is this a device tensor" test goes
+    through, so that the host-logic tests can stand a host-memory emulation of the ABI in: tests/host_emulation.py)."""
+    return t.is_cuda
+
+
+def require_cuda_device(device, what: str):
+    if torch.device(device).type != "cuda":
+        raise RuntimeError(f"{what} runs on a CUDA device only (got device={device!r}); there is no CPU fallback.")
+
+
 def require_cuda(*tensors: torch.Tensor):
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is not None and not on_device(t):
             raise RuntimeError("rsl_rl_b200 kernels need CUDA tensors (got a tensor on %s); there is no CPU path"
                                % t.device)
 

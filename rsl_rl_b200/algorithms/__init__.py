@@ -1,4 +1,5 @@
-"""RL algorithms (mirror of `rsl_rl.algorithms`; Distillation is out of scope)."""
+"""RL algorithms (mirror of `rsl_rl.algorithms`)."""
+from .distillation import Distillation
 from .ppo import PPO
 
-__all__ = ["PPO"]
+__all__ = ["PPO", "Distillation"]

@@ -1,0 +1,198 @@
+"""Teacher-student distillation (mirror of `rsl_rl/algorithms/distillation.py` of the reference).
+
+Same constructor and methods (`init_storage, act, process_env_step, update, broadcast_parameters, reduce_parameters`), same
+attributes (`policy, optimizer, storage, transition, last_hidden_states, num_updates, learning_rate, ...`).  Underneath:
+
+* rollout: student and teacher forward on the library's GEMM / LSTM kernels, the step goes into the rollout buffer with
+  one launch (`RolloutStorage._store_distillation`);
+* update: the behaviour-cloning loss over `gradient_length` consecutive steps is differentiated through the hand-written
+  backward of the MLP / LSTM kernels (networks/mlp.py, networks/lstm.py); gradients land in the flat gradient buffer,
+  clip + Adam is the fused optimiser kernel (`FusedAdam.fused_step`);
+* no host synchronisation inside the loop: the reference reads `behavior_loss.item()` every step
+  (distillation.py:122), here the sum stays on the device (fp64, same order of additions) and is read once.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.nn as nn
+
+from .. import _native as nat
+from ..storage import RolloutStorage
+from ..utils import resolve_optimizer
+from .flat_params import FlatParamGroup, FusedAdam
+from .ppo import DEFAULT_GEMM_PRECISION
+
+
+def _detached(hidden):
+    """`hidden` (None, a tensor, or nested tuples of them) with every tensor detached."""
+    if hidden is None:
+        return None
+    if isinstance(hidden, torch.Tensor):
+        return hidden.detach()
+    return tuple(_detached(h) for h in hidden)
+
+
+class Distillation:
+    """Distillation algorithm for training a student model to mimic a teacher model."""
+
+    def __init__(self, policy, num_learning_epochs=1, gradient_length=15, learning_rate=1e-3, max_grad_norm=None,
+                 loss_type="mse", optimizer="adam", device="cpu", multi_gpu_cfg: dict | None = None,
+                 # --- rsl_rl_b200 extension (optional) ---
+                 gemm_precision: str | None = None):   # see PPO: "tf32x3" (default) | "fp32" | "tf32" | "fp16" (-> tf32)
+        nat.require_cuda_device(device, "rsl_rl_b200.Distillation")
+        if gemm_precision is None:
+            gemm_precision = os.environ.get("RSLRL_GEMM_PRECISION", DEFAULT_GEMM_PRECISION)
+        if gemm_precision not in nat.PREC_CODES:
+            raise ValueError(f"gemm_precision must be one of {sorted(nat.PREC_CODES)}, got {gemm_precision!r}")
+        loss_fns = {"mse": nn.functional.mse_loss, "huber": nn.functional.huber_loss}
+        if loss_type not in loss_fns:
+            raise ValueError(f"Unknown loss type: {loss_type}. Supported types are: {list(loss_fns.keys())}")
+        optimizer_cls = resolve_optimizer(optimizer)   # ValueError for unknown names, like the reference
+        nat.lib()
+        self.device = device
+        self.is_multi_gpu = multi_gpu_cfg is not None
+        if multi_gpu_cfg is not None:
+            self.gpu_global_rank = multi_gpu_cfg["global_rank"]
+            self.gpu_world_size = multi_gpu_cfg["world_size"]
+        else:
+            self.gpu_global_rank = 0
+            self.gpu_world_size = 1
+
+        self.policy = policy
+        self.policy.to(self.device)
+        self.policy.set_gemm_precision(gemm_precision)
+        self.gemm_precision = gemm_precision
+        self.storage: RolloutStorage = None  # type: ignore
+        self.rnd = None   # (the runner's logging / checkpoint code asks every algorithm)
+
+        # Every parameter of the policy, in `policy.parameters()` order like the reference's optimiser (so optimiser
+        # state dicts index the same tensors), lives in one flat buffer.  Teacher and noise parameters never receive a
+        # gradient: their flat gradient stays exactly zero and Adam leaves them unchanged.
+        self._group = FlatParamGroup(self.policy.parameters(), self.device)
+        if optimizer_cls is torch.optim.Adam:
+            self.optimizer = FusedAdam(self._group, lr=learning_rate)
+        else:   # AdamW / SGD / RMSprop: torch's own CUDA optimiser on the flat-buffer views
+            self.optimizer = optimizer_cls(self._group.params, lr=learning_rate)
+        self._fused_adam = isinstance(self.optimizer, FusedAdam)
+        self._student_slice = self._flat_slice(self.policy.student)
+
+        self.transition = RolloutStorage.Transition()
+        self.last_hidden_states = None
+
+        self.num_learning_epochs = num_learning_epochs
+        self.gradient_length = gradient_length
+        self.learning_rate = learning_rate
+        self.max_grad_norm = max_grad_norm
+        self.loss_fn = loss_fns[loss_type]
+        self.num_updates = 0
+        self._loss_sum = torch.zeros(1, dtype=torch.float64, device=self.device)
+        self._mb_hook = None   # test hook: called after every optimiser step
+        self.last_update_info = {}
+
+    def _flat_slice(self, module: nn.Module) -> slice:
+        """The contiguous span of the flat buffers that holds `module`'s parameters (padding between tensors is zero)."""
+        ids = {id(p) for p in module.parameters()}
+        idx = [i for i, p in enumerate(self._group.params) if id(p) in ids]
+        if not idx or idx != list(range(idx[0], idx[-1] + 1)):
+            raise RuntimeError("the student's parameters are not contiguous in policy.parameters()")
+        g = self._group
+        return slice(g.offsets[idx[0]], g.offsets[idx[-1]] + g.params[idx[-1]].numel())
+
+    # ------------------------------------------------------------------------------------------
+    def init_storage(self, training_type, num_envs, num_transitions_per_env, obs, actions_shape):
+        self.storage = RolloutStorage(training_type, num_envs, num_transitions_per_env, obs, actions_shape, self.device)
+
+    def act(self, obs):
+        """Reference distillation.py:84-90."""
+        tr = self.transition
+        tr.actions = self.policy.act(obs).detach()
+        tr.privileged_actions = self.policy.evaluate(obs).detach()
+        tr.observations = obs
+        return tr.actions
+
+    def process_env_step(self, obs, rewards, dones, extras):
+        """Reference distillation.py:92-102."""
+        self.policy.update_normalization(obs)
+        tr = self.transition
+        tr.rewards = rewards
+        tr.dones = dones
+        self.storage.add_transitions(tr)
+        tr.clear()
+        self.policy.reset(dones)
+
+    # ------------------------------------------------------------------------------------------
+    def update(self):
+        """Reference distillation.py:104-150.  The loss of `gradient_length` consecutive steps is summed (across epoch
+        boundaries too: `cnt` and the running sum are not reset between epochs), differentiated once, then one optimiser
+        step; hidden states are carried through the whole rollout and cut at the optimiser steps and at dones."""
+        self.num_updates += 1
+        pol, st = self.policy, self.storage
+        self._group.ensure_bound()
+        if self._fused_adam:
+            self.optimizer.dev_state.set_lr(self.learning_rate)
+        self._group.zero_grad()
+        self._loss_sum.zero_()
+        loss = 0
+        cnt = 0
+        for _ in range(self.num_learning_epochs):
+            pol.reset(hidden_states=self.last_hidden_states)
+            pol.detach_hidden_states()
+            for obs, _, privileged_actions, dones in st.generator():
+                actions = pol.act_inference(obs)
+                behavior_loss = self.loss_fn(actions, privileged_actions)
+                loss = loss + behavior_loss
+                self._loss_sum += behavior_loss.detach()
+                cnt += 1
+                if cnt % self.gradient_length == 0:
+                    loss.backward()   # accumulates into the (zeroed) flat gradient views
+                    self._optimizer_step()
+                    pol.detach_hidden_states()
+                    loss = 0
+                    if self._mb_hook is not None:
+                        self._mb_hook()
+                pol.reset(dones.view(-1))
+                pol.detach_hidden_states(dones.view(-1))
+        mean_behavior_loss = float(self._loss_sum.item()) / cnt   # the one device->host read of update()
+        st.clear()
+        # (the reference keeps the attached tensors here and detaches them at the start of the next update; the values are
+        #  the same, detaching now releases the autograd graph of the last `cnt % gradient_length` steps)
+        self.last_hidden_states = _detached(pol.get_hidden_states())
+        pol.detach_hidden_states()
+        if self._fused_adam:
+            self.optimizer.sync_host_state(self.learning_rate)
+        return {"behavior": mean_behavior_loss}
+
+    def _optimizer_step(self):
+        """zero_grad / backward happened; now (multi-GPU) average, clip the STUDENT MLP's gradients (reference
+        distillation.py:131-132 clips `policy.student.parameters()` only -- a recurrent student's memory is not
+        clipped), step, and leave the gradient buffer zeroed for the next accumulation."""
+        g = self._group
+        if self.is_multi_gpu:
+            self.reduce_parameters()
+        if self.max_grad_norm:
+            sl = g.grads[self._student_slice]
+            total_norm = torch.linalg.vector_norm(sl)
+            sl.mul_(torch.clamp(self.max_grad_norm / (total_norm + 1e-6), max=1.0))
+        if self._fused_adam:
+            self.optimizer.fused_step(world_size=1, max_grad_norm=0.0, adaptive=False, use_kl=False, zero_grad=True)
+        else:
+            self.optimizer.step()
+            g.zero_grad()
+
+    # ------------------------------------------------------------------------------------------
+    # multi-GPU helpers (reference distillation.py:156-185)
+    # ------------------------------------------------------------------------------------------
+    def broadcast_parameters(self):
+        """Rank 0's parameters and buffers to every rank: one flat broadcast (the reference pickles the state dict)."""
+        self._group.ensure_bound()
+        torch.distributed.broadcast(self._group.values, src=0)
+        for b in self.policy.buffers():
+            torch.distributed.broadcast(b, src=0)
+
+    def reduce_parameters(self):
+        """Averages the gradients over all ranks in place: one all-reduce of the flat gradient buffer."""
+        self._group.ensure_bound()
+        torch.distributed.all_reduce(self._group.grads, op=torch.distributed.ReduceOp.SUM)
+        self._group.grads /= self.gpu_world_size

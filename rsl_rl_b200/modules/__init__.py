@@ -1,8 +1,10 @@
-"""Policy modules (mirror of `rsl_rl.modules`; the distillation-only StudentTeacher* are out of scope)."""
+"""Policy modules (mirror of `rsl_rl.modules`)."""
 from .actor_critic import ActorCritic
 from .actor_critic_recurrent import ActorCriticRecurrent
 from .rnd import RandomNetworkDistillation, resolve_rnd_config
+from .student_teacher import StudentTeacher
+from .student_teacher_recurrent import StudentTeacherRecurrent
 from .symmetry import resolve_symmetry_config
 
-__all__ = ["ActorCritic", "ActorCriticRecurrent", "RandomNetworkDistillation", "resolve_rnd_config",
-           "resolve_symmetry_config"]
+__all__ = ["ActorCritic", "ActorCriticRecurrent", "StudentTeacher", "StudentTeacherRecurrent",
+           "RandomNetworkDistillation", "resolve_rnd_config", "resolve_symmetry_config"]

@@ -9,8 +9,10 @@ from __future__ import annotations
 
 import os
 
+import torch
 import torch.nn as nn
 
+from .. import _native as nat
 from ..utils.utils import unpad_trajectories
 from .lstm import lstm_forward, lstm_forward_group
 
@@ -28,7 +30,7 @@ class Memory(nn.Module):
         self.native = isinstance(self.rnn, nn.LSTM)
 
     def _rnn(self, x, hidden):
-        if self.native and x.is_cuda:
+        if self.native and nat.on_device(x):
             return lstm_forward(self.rnn, x, hidden, self.precision)
         return self.rnn(x, hidden)
 
@@ -48,7 +50,7 @@ class Memory(nn.Module):
         """`mem_a(input_a, masks, hidden_a)` and `mem_c(input_c, masks, hidden_c)` with both LSTMs advanced together
         (grouped launches) when they are native LSTMs of equal shape on CUDA; otherwise two ordinary calls."""
         ra, rc = mem_a.rnn, mem_c.rnn
-        same = (_GROUP and mem_a.native and mem_c.native and input_a.is_cuda and input_c.is_cuda
+        same = (_GROUP and mem_a.native and mem_c.native and nat.on_device(input_a) and nat.on_device(input_c)
                 and (ra.num_layers, ra.hidden_size, ra.bias) == (rc.num_layers, rc.hidden_size, rc.bias)
                 and input_a.shape[:-1] == input_c.shape[:-1])
         if not same:
@@ -85,6 +87,12 @@ class Memory(nn.Module):
             else:
                 self.hidden_states = self.hidden_states.detach()
         else:
-            states = self.hidden_states if isinstance(self.hidden_states, tuple) else (self.hidden_states,)
-            for h in states:
-                h[..., dones == 1, :] = h[..., dones == 1, :].detach()
+            # rows of done environments leave the autograd graph, the others stay attached (reference memory.py:69-74
+            # assigns `h[..., dones == 1, :] = h[..., dones == 1, :].detach()`: boolean-mask indexing, one host
+            # synchronisation per call; the same selection here is elementwise on the device)
+            done = (dones == 1).view(1, -1, 1)
+            cut = lambda h: torch.where(done, h.detach(), h) if h.requires_grad else h
+            if isinstance(self.hidden_states, tuple):
+                self.hidden_states = tuple(cut(h) for h in self.hidden_states)
+            else:
+                self.hidden_states = cut(self.hidden_states)

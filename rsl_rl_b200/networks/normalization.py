@@ -39,7 +39,7 @@ class EmpiricalNormalization(nn.Module):
     def _rows(self, x):
         """x viewed as [N, D] fp32 rows (D = number of statistics) -> (tensor, N, D, row stride) or None."""
         D = self._mean.numel()
-        if not (x.is_cuda and x.dtype == torch.float32 and self._mean.is_cuda):
+        if not (nat.on_device(x) and x.dtype == torch.float32 and nat.on_device(self._mean)):
             return None
         if x.dim() == 0 or (D > 1 and x.shape[-1] != D):
             return None

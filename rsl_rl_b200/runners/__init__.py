@@ -1,4 +1,5 @@
-"""Runners (mirror of `rsl_rl.runners`; DistillationRunner is out of scope)."""
-from .on_policy_runner import OnPolicyRunner
+"""Runners (mirror of `rsl_rl.runners`)."""
+from .on_policy_runner import OnPolicyRunner  # isort:skip
+from .distillation_runner import DistillationRunner
 
-__all__ = ["OnPolicyRunner"]
+__all__ = ["OnPolicyRunner", "DistillationRunner"]

@@ -83,10 +83,7 @@ class OnPolicyRunner:
         self.save_interval = self.cfg["save_interval"]
 
         obs = self.env.get_observations()
-        default_sets = ["critic"]
-        if "rnd_cfg" in self.alg_cfg and self.alg_cfg["rnd_cfg"] is not None:
-            default_sets.append("rnd_state")
-        self.cfg["obs_groups"] = resolve_obs_groups(obs, self.cfg["obs_groups"], default_sets)
+        self.cfg["obs_groups"] = resolve_obs_groups(obs, self.cfg["obs_groups"], self._default_obs_sets())
         self.alg = self._construct_algorithm(obs)
 
         self.disable_logs = self.is_distributed and self.gpu_global_rank != 0
@@ -100,6 +97,14 @@ class OnPolicyRunner:
         self.profile_phases = False
         self.phase_times = {}
         self._env_device, self._action_ring, self._action_slot = None, None, 0
+
+    def _default_obs_sets(self) -> list:
+        """Observation sets (besides 'policy') the algorithm reads; missing ones fall back to same-named groups or to
+        the 'policy' set (reference on_policy_runner.py:44-47)."""
+        sets = ["critic"]
+        if "rnd_cfg" in self.alg_cfg and self.alg_cfg["rnd_cfg"] is not None:
+            sets.append("rnd_state")
+        return sets
 
     # ------------------------------------------------------------------------------------------
     def learn(self, num_learning_iterations: int, init_at_random_ep_len: bool = False):

@@ -54,12 +54,9 @@ class RolloutStorage:
             self.__init__()
 
     def __init__(self, training_type, num_envs, num_transitions_per_env, obs, actions_shape, device="cpu"):
-        if torch.device(device).type != "cuda":
-            raise RuntimeError(f"rsl_rl_b200.RolloutStorage lives in GPU memory; got device={device!r}. "
-                               "There is no CPU implementation.")
-        if training_type != "rl":
-            raise NotImplementedError("rsl_rl_b200 implements the PPO ('rl') path only; "
-                                      f"training_type={training_type!r} (distillation) is out of scope.")
+        nat.require_cuda_device(device, "rsl_rl_b200.RolloutStorage (it lives in GPU memory)")
+        if training_type not in ("rl", "distillation"):
+            raise ValueError(f"Unknown training_type {training_type!r}: expected 'rl' or 'distillation'.")
         nat.lib()  # fail loudly now if the CUDA library is missing
         self.training_type = training_type
         self.device = device
@@ -76,19 +73,23 @@ class RolloutStorage:
         self.rewards = torch.zeros(T, N, 1, **f32)
         self.actions = torch.zeros(T, N, *actions_shape, **f32)
         self.dones = torch.zeros(T, N, 1, dtype=torch.uint8, device=device)
-        self.values = torch.zeros(T, N, 1, **f32)
-        self.actions_log_prob = torch.zeros(T, N, 1, **f32)
-        self.mu = torch.zeros(T, N, *actions_shape, **f32)
-        self.sigma = torch.zeros(T, N, *actions_shape, **f32)
-        self.returns = torch.zeros(T, N, 1, **f32)
-        self.advantages = torch.zeros(T, N, 1, **f32)
+        if training_type == "distillation":   # reference rollout_storage.py:57-59
+            self.privileged_actions = torch.zeros(T, N, *actions_shape, **f32)
+        if training_type == "rl":             # reference rollout_storage.py:61-68
+            self.values = torch.zeros(T, N, 1, **f32)
+            self.actions_log_prob = torch.zeros(T, N, 1, **f32)
+            self.mu = torch.zeros(T, N, *actions_shape, **f32)
+            self.sigma = torch.zeros(T, N, *actions_shape, **f32)
+            self.returns = torch.zeros(T, N, 1, **f32)
+            self.advantages = torch.zeros(T, N, 1, **f32)
 
         self.saved_hidden_states_a = None
         self.saved_hidden_states_c = None
         self.step = 0
 
         self._store_plans = {}
-        self._gae_ws = torch.zeros(int(nat.lib().rslrl_gae_workspace_bytes(N)), dtype=torch.uint8, device=device)
+        self._gae_ws = (torch.zeros(int(nat.lib().rslrl_gae_workspace_bytes(N)), dtype=torch.uint8, device=device)
+                        if training_type == "rl" else None)
         # hooks used by the parity tests to inject a recorded permutation
         self._randperm = lambda n: torch.randperm(n, requires_grad=False, device=self.device)
 
@@ -97,7 +98,38 @@ class RolloutStorage:
     # ---------------------------------------------------------------------------------------------
     def add_transitions(self, transition: "RolloutStorage.Transition"):
         """Reference rollout_storage.py:77-103."""
-        self._store(transition)
+        if self.training_type == "distillation":
+            self._store_distillation(transition)
+        else:
+            self._store(transition)
+
+    def _store_distillation(self, tr):
+        """Row `step` of observations, actions, privileged (teacher) actions, rewards and dones in ONE launch of the
+        same kernel (`rslrl_store_transition`; the teacher's actions travel in the segment PPO uses for the action mean,
+        the PPO-only fields are absent)."""
+        if self.step >= self.num_transitions_per_env:
+            raise OverflowError("Rollout buffer overflow! You should call clear() before adding new transitions.")
+        s, N, A = self.step, self.num_envs, self._A
+        srcs, dsts, dims = [], [], []
+        for k in self._obs_keys:
+            src = nat.f32c(tr.observations[k])
+            dst = self.observations[k][s]
+            srcs.append(src)
+            dsts.append(dst.data_ptr())
+            dims.append(int(dst[0].numel()))
+        actions, privileged = nat.f32c(tr.actions), nat.f32c(tr.privileged_actions)
+        rewards = nat.f32c(tr.rewards)
+        dones, dcode = nat.flag_tensor(tr.dones)
+        nat.require_cuda(*srcs, actions, privileged, rewards, dones)
+        if actions.numel() != N * A or privileged.numel() != N * A or rewards.numel() != N or dones.numel() != N:
+            raise ValueError("add_transitions: transition fields do not match the storage shape")
+        nat.check(nat.lib().rslrl_store_transition(
+            len(srcs), nat.void_array([t.data_ptr() for t in srcs]), nat.void_array(dsts), nat.int_array(dims),
+            actions.data_ptr(), privileged.data_ptr(), None, 0, None, None, rewards.data_ptr(), dones.data_ptr(), dcode,
+            None, 0, None, 0.0, self.actions[s].data_ptr(), self.privileged_actions[s].data_ptr(), None, None, None,
+            self.rewards[s].data_ptr(), self.dones[s].data_ptr(), N, A, nat.stream_ptr()))
+        self._save_hidden_states(tr.hidden_states)
+        self.step += 1
 
     def _store(self, tr, time_outs: Optional[torch.Tensor] = None, intrinsic: Optional[torch.Tensor] = None,
                gamma: float = 0.0):
@@ -235,7 +267,11 @@ class RolloutStorage:
     # minibatches (feed-forward)
     # ---------------------------------------------------------------------------------------------
     def generator(self):
-        raise ValueError("This function is only available for distillation training.")
+        """Reference rollout_storage.py:152-157: the stored steps in order, as views of row t."""
+        if self.training_type != "distillation":
+            raise ValueError("This function is only available for distillation training.")
+        for i in range(self.num_transitions_per_env):
+            yield self.observations[i], self.actions[i], self.privileged_actions[i], self.dones[i]
 
     def _flat_fields(self):
         """(source tensors [T*N, d], widths) in the order obs groups..., actions, values, advantages, returns,

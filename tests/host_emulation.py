@@ -1,0 +1,303 @@
+"""TEST INFRASTRUCTURE -- a host-memory stand-in for the C ABI of `include/rslrl_b200.h`, for `-m "not gpu"` tests only.
+
+The product has ONE arithmetic back end, the sm_100a library, and refuses to run without it (tests/test_cabi_exports.py::
+test_no_cpu_fallback).  The build container has no GPU, so the HOST LOGIC that sits above the ABI -- which launches are
+issued in which order on which buffers: rollout store, the autograd wiring of the MLP / LSTM functions, hidden-state
+carrying, flat gradient buffers, clip + Adam sequencing -- could otherwise only be checked on the GPU box.  `install()`
+swaps the loaded library for `EmulatedLibrary`, a plain torch/numpy restatement of the entry points those host paths call
+(each method cites the kernel it stands in for), reading and writing the callers' buffers through their raw addresses
+exactly as the kernels do.  It says nothing about the kernels themselves: those are compared with the oracle and the
+golden vectors by the `-m gpu` tests.  Nothing under `rsl_rl_b200/` imports this module.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from rsl_rl_b200 import _native as nat
+
+
+def _view(ptr, count, dtype=np.float32):
+    """numpy view of `count` elements at raw address `ptr`."""
+    if not ptr or count == 0:
+        return None
+    nbytes = int(count) * np.dtype(dtype).itemsize
+    return np.frombuffer((ctypes.c_char * nbytes).from_address(int(ptr)), dtype=dtype)
+
+
+def _mat(ptr, rows, cols, ld):
+    """[rows, cols] fp32 matrix with row stride `ld` at `ptr` (a writable strided numpy view)."""
+    flat = _view(ptr, (rows - 1) * ld + cols)
+    return np.lib.stride_tricks.as_strided(flat, shape=(rows, cols), strides=(4 * ld, 4))
+
+
+def _act(code, z):
+    if code == 0:
+        return z
+    t = torch.from_numpy(np.ascontiguousarray(z))
+    fn = {1: torch.nn.functional.elu, 2: torch.relu, 3: torch.tanh, 4: torch.sigmoid,
+          5: torch.nn.functional.leaky_relu, 6: torch.selu, 7: torch.nn.functional.softplus}[code]
+    return fn(t).numpy()
+
+
+def _act_grad_from_output(code, h):
+    """Derivative of the activation as a function of its OUTPUT h (how the data-gradient kernels evaluate it)."""
+    if code == 0:
+        return np.ones_like(h)
+    if code == 1:
+        return np.where(h > 0, 1.0, h + 1.0).astype(np.float32)
+    if code == 2:
+        return (h > 0).astype(np.float32)
+    if code == 3:
+        return (1.0 - h * h).astype(np.float32)
+    if code == 4:
+        return (h * (1.0 - h)).astype(np.float32)
+    if code == 5:
+        return np.where(h > 0, 1.0, 0.01).astype(np.float32)
+    if code == 6:
+        alpha, scale = 1.6732632423543772, 1.0507009873554805
+        return np.where(h > 0, scale, h + scale * alpha).astype(np.float32)
+    if code == 7:
+        return (1.0 - np.exp(-h)).astype(np.float32)
+    raise ValueError(code)
+
+
+def _sigmoid(x):
+    return (1.0 / (1.0 + np.exp(-x))).astype(np.float32)
+
+
+class EmulatedLibrary:
+    """The subset of the ABI the host paths under test call.  Unknown entry points raise AttributeError."""
+
+    def __init__(self):
+        self.launches = 0
+        self.calls = []
+
+    def _launch(self, name):
+        self.launches += 1
+        self.calls.append(name)
+        return 0
+
+    # ---- plumbing
+    def rslrl_abi_version(self):
+        return nat.ABI_VERSION
+
+    def rslrl_last_error(self):
+        return b"emulated"
+
+    def rslrl_launch_count(self):
+        return self.launches
+
+    def rslrl_reset_launch_count(self):
+        self.launches = 0
+
+    def rslrl_add_launch_count(self, n):
+        self.launches = (self.launches + n) & 0xFFFFFFFFFFFFFFFF
+
+    def rslrl_gae_workspace_bytes(self, N):
+        return 256
+
+    def rslrl_optim_workspace_bytes(self, numel):
+        return 256
+
+    def rslrl_allreduce_adam_workspace_bytes(self):
+        return 256
+
+    def rslrl_allreduce_adam_flag_bytes(self):
+        return 256
+
+    def rslrl_empirical_norm_workspace_bytes(self, D):
+        return 64
+
+    def rslrl_fill_zero(self, ptr, nbytes, stream):
+        _view(ptr, nbytes, np.uint8)[:] = 0
+        return self._launch("fill_zero")
+
+    # ---- csrc/storage.cu: store_transition_kernel
+    def rslrl_store_transition(self, n_groups, obs_src, obs_dst, obs_dim, actions, mu, sigma, sigma_stride, values,
+                               log_prob, rewards, dones, dones_dtype, time_outs, time_outs_dtype, intrinsic, gamma,
+                               actions_row, mu_row, sigma_row, values_row, log_prob_row, rewards_row, dones_row, N, A,
+                               stream):
+        def copy(src, dst, count):
+            if src and dst:
+                _view(dst, count)[:] = _view(src, count)
+
+        for g in range(n_groups):
+            copy(obs_src[g], obs_dst[g], N * obs_dim[g])
+        copy(actions, actions_row, N * A)
+        copy(mu, mu_row, N * A)
+        copy(values, values_row, N)
+        copy(log_prob, log_prob_row, N)
+        if sigma and sigma_row:
+            if sigma_stride == A:
+                copy(sigma, sigma_row, N * A)
+            else:
+                _view(sigma_row, N * A).reshape(N, A)[:] = _view(sigma, A)
+        flag_np = {nat.U8: np.uint8, nat.I32: np.int32, nat.I64: np.int64, nat.F32: np.float32}
+        r = _view(rewards, N).copy()
+        if intrinsic:
+            r = r + _view(intrinsic, N)
+        if time_outs:
+            to = _view(time_outs, N, flag_np[time_outs_dtype]).astype(np.float32)
+            r = r + np.float32(gamma) * (_view(values, N) * to)
+        _view(rewards_row, N)[:] = r
+        _view(dones_row, N, np.uint8)[:] = _view(dones, N, flag_np[dones_dtype]).astype(np.float32).astype(np.int32).astype(np.uint8)
+        return self._launch("store_transition")
+
+    # ---- csrc/linear.cu -> gemm_simt.cu / gemm_tc.cu
+    def rslrl_linear_forward(self, n, probs, precision, stream):
+        for i in range(n):
+            p = probs[i]
+            x, w = _mat(p.x, p.M, p.K, p.ldx), _mat(p.w, p.N, p.K, p.K)
+            z = x.astype(np.float32) @ w.T
+            if p.b:
+                z = z + _view(p.b, p.N)
+            _mat(p.y, p.M, p.N, p.ldy)[:] = _act(p.act, z.astype(np.float32))
+        return self._launch("linear_forward")
+
+    def rslrl_linear_backward_data(self, n, probs, precision, stream):
+        for i in range(n):
+            p = probs[i]
+            dy, w = _mat(p.dy, p.M, p.N, p.ldy), _mat(p.w, p.N, p.K, p.K)
+            dx = dy @ w
+            if p.act != 0:
+                dx = dx * _act_grad_from_output(p.act, _mat(p.h, p.M, p.K, p.ldh))
+            dx = dx.astype(np.float32)
+            _mat(p.dx, p.M, p.K, p.ldx)[:] = dx
+            if p.db_prev:
+                _view(p.db_prev, p.K)[:] += dx.sum(0)
+        return self._launch("linear_backward_data")
+
+    def rslrl_linear_backward_weight(self, n, probs, precision, stream):
+        for i in range(n):
+            p = probs[i]
+            dy, x = _mat(p.dy, p.M, p.N, p.ldy), _mat(p.x, p.M, p.K, p.ldx)
+            scale = np.float32(p.scale if p.scale != 0 else 1.0)
+            if p.scale_dev:
+                scale = scale * _view(p.scale_dev, 1)[0]
+            _mat(p.dw, p.N, p.K, p.K)[:] += scale * (dy.T @ x)
+            if p.db:
+                _view(p.db, p.N)[:] += scale * dy.sum(0)
+        return self._launch("linear_backward_weight")
+
+    # ---- csrc/lstm.cu: whole-layer drivers (time loop in C)
+    def rslrl_lstm_layers_forward(self, n_nets, nets, T, n, H, precision, stream):
+        for i in range(n_nets):
+            q = nets[i]
+            xg = _view(q.xg, T * n * 4 * H).reshape(T, n, 4 * H)
+            w_hh = _view(q.w_hh, 4 * H * H).reshape(4 * H, H)
+            b_hh = _view(q.b_hh, 4 * H) if q.b_hh else 0.0
+            h_all = _view(q.h_all, (T + 1) * n * H).reshape(T + 1, n, H)
+            c_all = _view(q.c_all, (T + 1) * n * H).reshape(T + 1, n, H)
+            gates = _view(q.gates, T * n * 4 * H).reshape(T, n, 4 * H) if q.gates else None
+            for t in range(T):
+                pre = xg[t] + h_all[t] @ w_hh.T + b_hh
+                gi, gf = _sigmoid(pre[:, :H]), _sigmoid(pre[:, H:2 * H])
+                gg, go = np.tanh(pre[:, 2 * H:3 * H]), _sigmoid(pre[:, 3 * H:])
+                c_all[t + 1] = gf * c_all[t] + gi * gg
+                h_all[t + 1] = go * np.tanh(c_all[t + 1])
+                if gates is not None:
+                    gates[t] = np.concatenate([gi, gf, gg, go], axis=1)
+            self._launch("lstm_step_forward")
+        return 0
+
+    def rslrl_lstm_layers_backward(self, n_nets, nets, need_dh0, T, n, H, precision, stream):
+        for i in range(n_nets):
+            q = nets[i]
+            gates = _view(q.gates, T * n * 4 * H).reshape(T, n, 4 * H)
+            c_all = _view(q.c_all, (T + 1) * n * H).reshape(T + 1, n, H)
+            w_hh_t = _view(q.w_hh_t, H * 4 * H).reshape(H, 4 * H)
+            dgates = _view(q.dgates, T * n * 4 * H).reshape(T, n, 4 * H)
+            dh_s = _view(q.dh_scratch, 2 * n * H).reshape(2, n, H)
+            dc_s = _view(q.dc_scratch, 2 * n * H).reshape(2, n, H)
+            dout = _view(q.dout, T * n * H).reshape(T, n, H) if q.dout else None
+            dh_rec = _view(q.dhT, n * H).reshape(n, H).copy() if q.dhT else None
+            dc = _view(q.dcT, n * H).reshape(n, H).copy() if q.dcT else None
+            for t in range(T - 1, -1, -1):
+                gi, gf, gg, go = (gates[t][:, k * H:(k + 1) * H] for k in range(4))
+                dh = np.zeros((n, H), np.float32)
+                if dout is not None:
+                    dh = dh + dout[t]
+                if dh_rec is not None:
+                    dh = dh + dh_rec
+                tc = np.tanh(c_all[t + 1])
+                d_o = dh * tc
+                dcur = dh * go * (1.0 - tc * tc) + (dc if dc is not None else 0.0)
+                dgates[t] = np.concatenate([dcur * gg * gi * (1 - gi), dcur * c_all[t] * gf * (1 - gf),
+                                            dcur * gi * (1 - gg * gg), d_o * go * (1 - go)], axis=1)
+                dc_s[t & 1] = dcur * gf
+                dc = dc_s[t & 1].copy()
+                if t > 0 or need_dh0:
+                    dh_s[t & 1] = dgates[t] @ w_hh_t.T
+                    dh_rec = dh_s[t & 1].copy()
+            self._launch("lstm_step_backward")
+        return 0
+
+    # ---- csrc/normalization.cu
+    def rslrl_empirical_norm_update(self, x, ldx, N, D, mean, var, std, count, until, workspace, stream):
+        cnt = _view(count, 1, np.int64)
+        if until >= 0 and cnt[0] >= until:
+            return self._launch("empirical_norm_update")
+        xt = torch.from_numpy(np.ascontiguousarray(_mat(x, N, D, ldx)))
+        m, v, s = (torch.from_numpy(_view(b, D)) for b in (mean, var, std))
+        cnt[0] += N
+        rate = N / int(cnt[0])
+        var_x = torch.var(xt, dim=0, unbiased=False)
+        mean_x = torch.mean(xt, dim=0)
+        delta = mean_x - m
+        m += rate * delta
+        v += rate * (var_x - v + delta * (mean_x - m))
+        s.copy_(torch.sqrt(v))
+        return self._launch("empirical_norm_update")
+
+    def rslrl_empirical_normalize(self, x, ldx, N, D, mean, std, eps, y, ldy, stream):
+        _mat(y, N, D, ldy)[:] = (_mat(x, N, D, ldx) - _view(mean, D)) / (_view(std, D) + np.float32(eps))
+        return self._launch("empirical_normalize")
+
+    # ---- csrc/allreduce_adam.cu at world size 1: gradient norm, clip, (KL-adaptive LR,) Adam, re-zeroed gradients
+    def rslrl_allreduce_clip_adam(self, world, rank, peers, peer_flags, peer_results, peer_stage, values, exp_avg,
+                                  exp_avg_sq, numel, state, workspace, max_grad_norm, adaptive, desired_kl,
+                                  round_lr_fp32, use_kl, beta1, beta2, eps, zero_grad, values16, stream):
+        assert world == 1, "the emulation covers the single-rank step"
+        g_ext = _view(peers[0], numel + 8)
+        g = g_ext[:numel]
+        st = ctypes.cast(int(state), ctypes.POINTER(nat.OptState)).contents
+        norm = math.sqrt(float(np.sum(g.astype(np.float64) ** 2)))
+        coef = min(max_grad_norm / (norm + 1e-6), 1.0) if max_grad_norm > 0 else 1.0
+        lr = st.lr
+        if adaptive:
+            kl = np.float32(g_ext[numel]) if use_kl else np.float32(0)
+            if kl > np.float32(desired_kl * 2.0):
+                lr = max(1e-5, lr / 1.5)
+            elif np.float32(0) < kl < np.float32(desired_kl / 2.0):
+                lr = min(1e-2, lr * 1.5)
+            if round_lr_fp32:
+                lr = float(np.float32(lr))
+            st.kl_mean = float(kl)
+        t = st.step + 1
+        bc1, bc2 = 1.0 - beta1 ** t, 1.0 - beta2 ** t
+        p, m, v = _view(values, numel), _view(exp_avg, numel), _view(exp_avg_sq, numel)
+        f = np.float32
+        gc = g * f(coef)
+        m[:] = m + (gc - m) * f(1.0 - beta1)
+        v[:] = v * f(beta2) + f(1.0 - beta2) * gc * gc
+        p[:] = p + f(-(lr / bc1)) * (m / (np.sqrt(v) / f(math.sqrt(bc2)) + f(eps)))
+        st.lr, st.clip_scale, st.total_norm, st.step_size, st.bc2_sqrt, st.step = lr, coef, norm, lr / bc1, math.sqrt(bc2), t
+        if zero_grad:
+            g_ext[:] = 0
+        if values16:
+            _view(values16, numel, np.float16)[:] = p.astype(np.float16)
+        return self._launch("allreduce_clip_adam")
+
+
+def install(monkeypatch) -> EmulatedLibrary:
+    """Routes `rsl_rl_b200._native` to the emulation for the duration of one test (pytest's monkeypatch undoes it)."""
+    lib = EmulatedLibrary()
+    monkeypatch.setattr(nat, "_lib", lib)
+    monkeypatch.setattr(nat, "on_device", lambda t: True)
+    monkeypatch.setattr(nat, "require_cuda_device", lambda device, what: None)
+    monkeypatch.setattr(nat, "stream_ptr", lambda: 0)
+    return lib

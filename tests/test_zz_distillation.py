@@ -1,0 +1,208 @@
+"""Teacher-student distillation (Distillation, StudentTeacher, StudentTeacherRecurrent, DistillationRunner)
+against golden traces recorded from the unmodified reference (oracle/make_golden.py: scenario_distillation).
+
+Two legs over the same checks:
+  * `-m gpu`: the product path on cuda:0 (GEMM / LSTM / store / optimiser kernels of the library);
+  * CPU: the same host code above a host-memory emulation of the C ABI (tests/host_emulation.py) -- this pins the host
+    logic (what is launched on which buffers in which order, autograd wiring, hidden-state carrying, checkpoint rules)
+    to the reference's results in the build container, where no GPU exists.  It is not a product path.
+(The file name sorts after every other test module on purpose: these are the newest GPU tests.)
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests.golden_util import load, meta_of, rel_err
+
+CASES = ["distill_mlp_small", "distill_lstm_small"]
+
+
+def _runner(g, meta, device):
+    from rsl_rl_b200.env import ReplayVecEnv
+    from rsl_rl_b200.runners import DistillationRunner
+    T, iters = meta["num_steps"], meta["iterations"]
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    obs = {k: t(np.concatenate([g[f"it{i}.stream.obs.{k}"][:T + (i == iters - 1)] for i in range(iters)]))
+           for k in meta["group_dims"]}
+    cat = lambda key: t(np.concatenate([g[f"it{i}.stream.{key}"] for i in range(iters)]))
+    env = ReplayVecEnv(obs, cat("rewards"), cat("dones"), None, meta["num_actions"], device=device)
+    cfg = dict(num_steps_per_env=T, save_interval=10 ** 9, obs_groups={k: list(v) for k, v in meta["obs_groups"].items()},
+               policy=dict(class_name=meta["policy_class"], student_hidden_dims=list(meta["hidden"]),
+                           teacher_hidden_dims=list(meta["hidden"]), activation=meta["activation"], init_noise_std=0.1,
+                           **meta["policy_extra"]),
+               algorithm=dict(meta["alg"], class_name="Distillation"))
+    return DistillationRunner(env, cfg, log_dir=None, device=device)
+
+
+def _state(g, prefix, device):
+    return {k[len(prefix):]: torch.from_numpy(g[k]).to(device) for k in g.files if k.startswith(prefix)}
+
+
+def _check_distillation(name, device, tol):
+    g = load(name)
+    meta = meta_of(g)
+    runner = _runner(g, meta, device)
+    alg, pol, st = runner.alg, runner.alg.policy, runner.alg.storage
+    assert [k for k, _ in pol.named_parameters()] == meta["param_names"]
+
+    # the runner refuses to train before a teacher is loaded (reference distillation_runner.py:59-61)
+    with pytest.raises(ValueError, match="Teacher model parameters not loaded"):
+        runner.learn(1)
+    # a PPO checkpoint fills the teacher only and does not resume (reference student_teacher.py:184-198)
+    assert pol.load_state_dict(_state(g, "teacher_ckpt.", device)) is False and pol.loaded_teacher
+    init = _state(g, "init.", device)
+    for k, v in pol.state_dict().items():
+        if k.startswith(("teacher", "memory_t")):
+            assert torch.equal(v, init[k]), k
+    assert not pol.teacher.training
+    # a distillation checkpoint fills everything and resumes (:199-204); this also sets the recorded student
+    assert pol.load_state_dict(init) is True
+    with pytest.raises(ValueError, match="does not contain student or teacher"):
+        pol.load_state_dict({"foo.weight": torch.zeros(1)})
+
+    for it in range(meta["iterations"]):
+        p = f"it{it}."
+        zq = [torch.from_numpy(z).to(device) for z in g[p + "z_rollout"]]
+        pol._noise_fn = lambda like, q=zq: q.pop(0)
+        snap, trace = {}, []
+        orig_update = alg.update
+
+        def update_and_snapshot():
+            for k in ("actions", "privileged_actions", "rewards", "dones"):
+                snap[k] = getattr(st, k).cpu().numpy().copy()
+            for k in meta["group_dims"]:
+                snap["obs." + k] = st.observations[k].cpu().numpy().copy()
+            return orig_update()
+
+        alg.update = update_and_snapshot
+        alg._mb_hook = lambda: trace.append(torch.cat([q.detach().reshape(-1) for q in pol.parameters()]).cpu().numpy())
+        losses = {}
+        orig_update_fn = alg.update
+
+        def update_and_keep_loss():
+            out = orig_update_fn()
+            losses.update(out)
+            return out
+
+        alg.update = update_and_keep_loss
+        runner.learn(1)
+        alg.update = orig_update
+        assert not zq, "every recorded draw was consumed"
+        # rollout buffer: observations and dones are copies (bit-exact), actions = mean + std * z, teacher actions
+        assert np.array_equal(snap["dones"], g[p + "storage.dones"])
+        for k in meta["group_dims"]:
+            assert np.array_equal(snap["obs." + k], g[p + "storage.obs." + k]), k
+        assert np.array_equal(snap["rewards"], g[p + "storage.rewards"])
+        assert rel_err(snap["actions"], g[p + "storage.actions"]) < tol
+        assert rel_err(snap["privileged_actions"], g[p + "storage.privileged_actions"]) < tol
+        # every optimiser step of the update (gradient_length steps of summed loss each, student-only clipping)
+        ref_trace = g[p + "mb.params_after"]
+        assert len(trace) == len(ref_trace), (len(trace), len(ref_trace))
+        for i, (mine, ref) in enumerate(zip(trace, ref_trace)):
+            assert rel_err(mine, ref) < 2.5 * tol, (it, i)
+        assert abs(losses["behavior"] - float(g[p + "loss.behavior"])) < 5 * tol * max(1.0, abs(float(g[p + "loss.behavior"])))
+        assert alg.num_updates == int(g[p + "num_updates"])
+        for k, v in pol.state_dict().items():
+            ref = g[p + "final." + k]
+            if k.endswith("count"):
+                assert int(v) == int(ref), k
+            elif k.startswith(("teacher", "memory_t", "std", "log_std")):
+                assert np.array_equal(v.cpu().numpy(), ref), k   # never trained: exactly as loaded
+            else:
+                assert rel_err(v.cpu().numpy(), ref) < 2.5 * tol, k
+        hs = alg.last_hidden_states
+        if pol.is_recurrent:
+            for tag, h in zip(("s", "t"), hs):
+                if h is None:   # the teacher's memory is reset at the start of update() and not advanced by it
+                    assert p + f"hidden_{tag}0" not in g.files
+                    continue
+                for i, x in enumerate(h):
+                    assert not x.requires_grad
+                    assert rel_err(x.cpu().numpy(), g[p + f"hidden_{tag}{i}"]) < 2.5 * tol, (tag, i)
+        else:
+            assert hs is None
+    # optimiser checkpoint surface: a torch Adam state dict over policy.parameters()
+    osd = alg.optimizer.state_dict()
+    assert len(osd["param_groups"][0]["params"]) == len(meta["param_names"])
+    return runner
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_distillation_host_logic_matches_reference_golden_on_the_emulated_abi(name, monkeypatch):
+    from tests import host_emulation
+    lib = host_emulation.install(monkeypatch)
+    _check_distillation(name, "cpu", 2e-5)
+    assert "store_transition" in lib.calls and "allreduce_clip_adam" in lib.calls and "linear_backward_weight" in lib.calls
+    if "lstm" in name:
+        assert "lstm_step_backward" in lib.calls
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_distillation_matches_reference_golden(name):
+    from rsl_rl_b200 import _native as nat
+    before = nat.launch_count()
+    _check_distillation(name, "cuda:0", 2e-5)
+    assert nat.launch_count() > before   # the library's kernels ran (no silent framework path)
+
+
+def test_distillation_storage_and_algorithm_argument_errors(monkeypatch):
+    """Error behaviour of the reference: wrong generator for the training type (rollout_storage.py:153-154,161-162),
+    unknown loss / optimiser names (distillation.py:71, utils.py:75), overflow of the rollout buffer (:79-80)."""
+    from tests import host_emulation
+    host_emulation.install(monkeypatch)
+    from rsl_rl_b200.algorithms import Distillation
+    from rsl_rl_b200.modules import StudentTeacher
+    from rsl_rl_b200.storage import RolloutStorage
+    from rsl_rl_b200.utils import TensorDictLite
+    obs = TensorDictLite({"policy": torch.zeros(4, 3)}, batch_size=[4])
+    st = RolloutStorage("distillation", 4, 2, obs, [2], "cpu")
+    assert not hasattr(st, "values") and st.privileged_actions.shape == (2, 4, 2)
+    with pytest.raises(ValueError, match="only available for reinforcement learning"):
+        next(st.mini_batch_generator(2))
+    with pytest.raises(ValueError, match="only available for reinforcement learning"):
+        next(st.recurrent_mini_batch_generator(2))
+    rl = RolloutStorage("rl", 4, 2, obs, [2], "cpu")
+    with pytest.raises(ValueError, match="only available for distillation"):
+        next(rl.generator())
+    with pytest.raises(ValueError, match="Unknown training_type"):
+        RolloutStorage("other", 4, 2, obs, [2], "cpu")
+    tr = RolloutStorage.Transition()
+    tr.observations, tr.actions, tr.privileged_actions = obs, torch.ones(4, 2), 2 * torch.ones(4, 2)
+    tr.rewards, tr.dones = torch.arange(4.0), torch.tensor([0, 1, 0, 1])
+    st.add_transitions(tr)
+    st.add_transitions(tr)
+    with pytest.raises(OverflowError):
+        st.add_transitions(tr)
+    rows = list(st.generator())
+    assert len(rows) == 2 and torch.equal(rows[1][2], 2 * torch.ones(4, 2)) and rows[1][3].dtype == torch.uint8
+    assert rows[0][3].view(-1).tolist() == [0, 1, 0, 1] and rows[0][0]["policy"].shape == (4, 3)
+
+    policy = StudentTeacher(obs, {"policy": ["policy"], "teacher": ["policy"]}, 2, student_hidden_dims=[8],
+                            teacher_hidden_dims=[8])
+    with pytest.raises(ValueError, match="Unknown loss type"):
+        Distillation(policy, loss_type="l1", device="cpu")
+    with pytest.raises(ValueError, match="Invalid optimizer"):
+        Distillation(policy, optimizer="lion", device="cpu")
+    alg = Distillation(policy, device="cpu", max_grad_norm=1.0)
+    # the clipped span is exactly the student MLP's parameters inside the flat buffer
+    sl = alg._student_slice
+    flat_ids = torch.zeros(alg._group.numel)
+    for p in policy.student.parameters():
+        p.data.fill_(1.0)
+    flat_ids[sl] = 1.0
+    assert torch.equal((alg._group.values == 1.0).float() * flat_ids, (alg._group.values == 1.0).float())
+    assert int((alg._group.values[sl] == 1.0).sum()) == sum(p.numel() for p in policy.student.parameters())
+
+
+def test_distillation_has_no_cpu_path():
+    from rsl_rl_b200.algorithms import Distillation
+    from rsl_rl_b200.modules import StudentTeacher
+    from rsl_rl_b200.utils import TensorDictLite
+    obs = TensorDictLite({"policy": torch.zeros(4, 3)}, batch_size=[4])
+    policy = StudentTeacher(obs, {"policy": ["policy"], "teacher": ["policy"]}, 2, student_hidden_dims=[8],
+                            teacher_hidden_dims=[8])
+    with pytest.raises(RuntimeError, match="no CPU"):
+        Distillation(policy, device="cpu")
+    with pytest.raises(RuntimeError, match="no CPU|CUDA"):
+        policy.act_inference(obs)
