@@ -77,7 +77,11 @@ int rslrl_gaussian_act(const float* mu, const float* std_param, int std_type, co
  * One launch writes row `step` of every [T,N,.] buffer; the *_row pointers already address that row.
  * obs_src_host/obs_dst_host/obs_dim_host: host arrays with one entry per observation group.
  * sigma_stride: 0 -> sigma is [A] and is broadcast, A -> sigma is [N,A].
- * dones / time_outs: dtype codes above; time_outs and intrinsic may be NULL. */
+ * dones / time_outs: dtype codes above; time_outs and intrinsic may be NULL.
+ * A (source, row) pair of actions / mu / sigma / values / log_prob that is NULL is skipped (values may only be NULL when
+ * time_outs is): the distillation rollout buffer (rollout_storage.py:57-59,88-90: observations, actions,
+ * privileged_actions, rewards, dones) is stored with the teacher's actions in the `mu` segment and the PPO-only
+ * fields absent. */
 int rslrl_store_transition(int n_groups, const float* const* obs_src_host, float* const* obs_dst_host,
                            const int* obs_dim_host, const float* actions, const float* mu, const float* sigma,
                            int sigma_stride, const float* values, const float* log_prob, const float* rewards,

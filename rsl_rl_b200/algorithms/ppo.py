@@ -77,9 +77,7 @@ class PPO:
         use_cuda_graph: bool = True,     # capture update() into one CUDA graph (single-GPU fused path)
         rng_compat: bool = True,         # consume the RNG exactly like the reference (discarded draws in update())
     ):
-        if torch.device(device).type != "cuda":
-            raise RuntimeError(f"rsl_rl_b200.PPO runs on a CUDA device only (got device={device!r}); "
-                               "there is no CPU fallback.")
+        nat.require_cuda_device(device, "rsl_rl_b200.PPO")
         if gemm_precision is None:
             gemm_precision = os.environ.get("RSLRL_GEMM_PRECISION", DEFAULT_GEMM_PRECISION)
         if gemm_precision not in nat.PREC_CODES:

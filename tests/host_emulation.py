@@ -147,6 +147,29 @@ class EmulatedLibrary:
         _view(dones_row, N, np.uint8)[:] = _view(dones, N, flag_np[dones_dtype]).astype(np.float32).astype(np.int32).astype(np.uint8)
         return self._launch("store_transition")
 
+    # ---- csrc/gae.cu (arithmetic: the numpy oracle, which is pinned bit-exactly to the reference's golden vectors)
+    def rslrl_gae_norm(self, rewards, values, dones, last_values, returns, advantages, workspace, T, N, gamma, lam,
+                       normalize, stream):
+        from oracle import ppo_oracle as O
+        r, v = _view(rewards, T * N).reshape(T, N), _view(values, T * N).reshape(T, N)
+        d = _view(dones, T * N, np.uint8).reshape(T, N)
+        ret, adv = O.compute_returns(r.copy(), v.copy(), d.copy(), _view(last_values, N).copy(), gamma, lam,
+                                     normalize_advantage=bool(normalize))
+        _view(returns, T * N)[:] = np.asarray(ret, np.float32).reshape(-1)
+        _view(advantages, T * N)[:] = np.asarray(adv, np.float32).reshape(-1)
+        return self._launch("gae_norm")
+
+    # ---- csrc/storage.cu: permute_gather_kernel
+    def rslrl_permute_gather(self, n_fields, src, dst, row_floats, dst_stride, dst_col, idx, n_rows, stream):
+        rows = _view(idx, n_rows, np.int64)
+        for f in range(n_fields):
+            w, ld, col = row_floats[f], dst_stride[f], dst_col[f]
+            total = int(rows.max()) + 1 if n_rows else 0
+            s = _view(src[f], total * w).reshape(total, w)
+            out = _view(dst[f], (n_rows - 1) * ld + col + w)
+            np.lib.stride_tricks.as_strided(out[col:], shape=(n_rows, w), strides=(4 * ld, 4))[:] = s[rows]
+        return self._launch("permute_gather")
+
     # ---- csrc/linear.cu -> gemm_simt.cu / gemm_tc.cu
     def rslrl_linear_forward(self, n, probs, precision, stream):
         for i in range(n):
@@ -235,6 +258,69 @@ class EmulatedLibrary:
                     dh_rec = dh_s[t & 1].copy()
             self._launch("lstm_step_backward")
         return 0
+
+    # ---- csrc/trajectory.cu: segmented scan over dones, masks, split/pad, hidden states at trajectory starts
+    def rslrl_traj_workspace_bytes(self, T, N):
+        return 64
+
+    def rslrl_trajectory_index(self, dones, T, N, traj_id, traj_pos, traj_len, traj_env, traj_start, env_traj_offset,
+                               workspace, stream):
+        d = _view(dones, T * N, np.uint8).reshape(T, N)
+        i32 = lambda ptr, n: _view(ptr, n, np.int32)
+        tid, tpos = i32(traj_id, T * N).reshape(T, N), i32(traj_pos, T * N).reshape(T, N)
+        tlen, tenv, tstart, off = i32(traj_len, T * N), i32(traj_env, T * N), i32(traj_start, T * N), i32(env_traj_offset, N + 1)
+        j = 0
+        for env in range(N):
+            off[env] = j
+            start = 0
+            for t in range(T):
+                if d[t, env] or t == T - 1:
+                    tlen[j], tenv[j], tstart[j] = t - start + 1, env, start
+                    tid[start:t + 1, env] = j
+                    tpos[start:t + 1, env] = np.arange(t - start + 1)
+                    start, j = t + 1, j + 1
+        off[N] = j
+        return self._launch("trajectory_index")
+
+    def rslrl_trajectory_masks(self, traj_len, masks, T, first_traj, n_traj_end, capacity, stream):
+        tlen = _view(traj_len, n_traj_end, np.int32)
+        m = _view(masks, T * capacity, np.uint8).reshape(T, capacity)
+        for j in range(capacity):
+            J = first_traj + j
+            m[:, j] = (np.arange(T) < tlen[J]) if J < n_traj_end else 0
+        return self._launch("trajectory_masks")
+
+    def rslrl_split_and_pad(self, x, traj_len, traj_env, traj_start, padded, T, N, D, first_traj, n_traj_end, capacity,
+                            stream):
+        tlen, tenv, tstart = (_view(q, n_traj_end, np.int32) for q in (traj_len, traj_env, traj_start))
+        out = _view(padded, T * capacity * D).reshape(T, capacity, D)
+        out[:] = 0
+        for j in range(capacity):
+            J = first_traj + j
+            if J < n_traj_end:
+                for q in range(tlen[J]):   # (x may be addressed below its base by pad_columns: element-wise addresses)
+                    out[q, j] = _view(int(x) + 4 * ((int(tstart[J]) + q) * N + int(tenv[J])) * D, D)
+        return self._launch("split_and_pad")
+
+    def rslrl_unpad(self, padded, traj_id, traj_pos, out, T, N, D, env0, env1, first_traj, capacity, stream):
+        pd = _view(padded, T * capacity * D).reshape(T, capacity, D)
+        tid, tpos = (_view(q, T * N, np.int32).reshape(T, N) for q in (traj_id, traj_pos))
+        o = _view(out, T * (env1 - env0) * D).reshape(T, env1 - env0, D)
+        for t in range(T):
+            for env in range(env0, env1):
+                o[t, env - env0] = pd[tpos[t, env], tid[t, env] - first_traj]
+        return self._launch("unpad")
+
+    def rslrl_hidden_at_starts(self, saved, traj_env, traj_start, out, T, L, N, H, first_traj, n_traj_end, capacity,
+                               stream):
+        sv = _view(saved, T * L * N * H).reshape(T, L, N, H)
+        tenv, tstart = (_view(q, n_traj_end, np.int32) for q in (traj_env, traj_start))
+        o = _view(out, L * capacity * H).reshape(L, capacity, H)
+        for j in range(capacity):
+            J = first_traj + j
+            if J < n_traj_end:
+                o[:, j] = sv[tstart[J], :, tenv[J]]
+        return self._launch("hidden_at_starts")
 
     # ---- csrc/normalization.cu
     def rslrl_empirical_norm_update(self, x, ldx, N, D, mean, var, std, count, until, workspace, stream):
