@@ -21,6 +21,7 @@ import torch.nn as nn
 from .. import _native as nat
 from ..storage import RolloutStorage
 from ..utils import resolve_optimizer
+from ..networks.mlp import linear_forward
 from .flat_params import FlatParamGroup, FusedAdam
 from .ppo import DEFAULT_GEMM_PRECISION
 
@@ -89,6 +90,13 @@ class Distillation:
         self.num_updates = 0
         self._loss_sum = torch.zeros(1, dtype=torch.float64, device=self.device)
         self._mb_hook = None   # test hook: called after every optimiser step
+        # the stock feed-forward pair: grouped student / teacher launches in the rollout, batched windows in update()
+        from ..modules.student_teacher import StudentTeacher
+        plain = type(policy) is StudentTeacher and os.environ.get("RSLRL_DISTILL_BATCHED", "1") != "0"
+        self._batched_update = plain
+        self._grouped_rollout = plain and (len(policy.student.linear_layers()) == len(policy.teacher.linear_layers())
+                                           and not any(isinstance(m, nn.Unflatten) for net in (policy.student, policy.teacher)
+                                                       for m in net))
         self.last_update_info = {}
 
     def _flat_slice(self, module: nn.Module) -> slice:
@@ -107,10 +115,34 @@ class Distillation:
     def act(self, obs):
         """Reference distillation.py:84-90."""
         tr = self.transition
-        tr.actions = self.policy.act(obs).detach()
-        tr.privileged_actions = self.policy.evaluate(obs).detach()
+        if self._grouped_rollout:
+            tr.actions, tr.privileged_actions = self._act_grouped(obs)
+        else:
+            tr.actions = self.policy.act(obs).detach()
+            tr.privileged_actions = self.policy.evaluate(obs).detach()
         tr.observations = obs
         return tr.actions
+
+    def _act_grouped(self, obs):
+        """`policy.act(obs)` and `policy.evaluate(obs)` of a feed-forward StudentTeacher with layer i of the student and
+        layer i of the teacher in ONE grouped GEMM launch (no autograd: both results are detached by the caller anyway).
+        Same kernels, same operands, same results as the two module calls."""
+        pol = self.policy
+        hs = nat.f32c(pol.student_obs_normalizer(pol.get_student_obs(obs)))
+        ht = nat.f32c(pol.teacher_obs_normalizer(pol.get_teacher_obs(obs)))
+        nat.require_cuda(hs, ht)
+        prec = nat.PREC_CODES[pol.student.precision]
+        s_layers, t_layers = pol.student.linear_layers(), pol.teacher.linear_layers()
+        s_acts, t_acts = pol.student.layer_activation_codes(), pol.teacher.layer_activation_codes()
+        f32 = dict(dtype=torch.float32, device=hs.device)
+        with torch.no_grad():
+            for ls, lt, a_s, a_t in zip(s_layers, t_layers, s_acts, t_acts):
+                ys = torch.empty(hs.shape[0], ls.weight.shape[0], **f32)
+                yt = torch.empty(ht.shape[0], lt.weight.shape[0], **f32)
+                linear_forward([(hs, ls.weight, ls.bias, ys, a_s), (ht, lt.weight, lt.bias, yt, a_t)], prec)
+                hs, ht = ys, yt
+            pol.set_distribution(hs)
+            return pol._sample(), ht
 
     def process_env_step(self, obs, rewards, dones, extras):
         """Reference distillation.py:92-102."""
@@ -134,6 +166,8 @@ class Distillation:
             self.optimizer.dev_state.set_lr(self.learning_rate)
         self._group.zero_grad()
         self._loss_sum.zero_()
+        if self._batched_update:
+            return self._update_feedforward()
         loss = 0
         cnt = 0
         for _ in range(self.num_learning_epochs):
@@ -160,6 +194,50 @@ class Distillation:
         #  the same, detaching now releases the autograd graph of the last `cnt % gradient_length` steps)
         self.last_hidden_states = _detached(pol.get_hidden_states())
         pol.detach_hidden_states()
+        if self._fused_adam:
+            self.optimizer.sync_host_state(self.learning_rate)
+        return {"behavior": mean_behavior_loss}
+
+    def _update_feedforward(self):
+        """update() of a feed-forward student: a student without memory sees every stored step independently and the
+        weights only change at the optimiser steps, so the `gradient_length` steps between two optimiser steps are ONE
+        batch of gradient_length * num_envs rows -- one forward, one backward per optimiser step instead of
+        gradient_length of each, on GEMMs large enough for the tensor cores.  The objective is the same sum of per-step
+        mean losses (so is its gradient, up to the order of fp32 additions); windows that run across an epoch boundary
+        (the reference does not reset its step counter between epochs) are two contiguous row ranges of the buffer."""
+        pol, st = self.policy, self.storage
+        T, gl = st.num_transitions_per_env, self.gradient_length
+        total = self.num_learning_epochs * T
+        n_steps = 0
+
+        def window_loss(first: int, count: int):
+            """Sum over steps [first, first + count) (modulo T) of the per-step mean loss, as a device scalar."""
+            out = 0
+            k = first
+            while k < first + count:
+                a = k % T
+                b = min(a + (first + count - k), T)
+                obs = st.observations[a:b].flatten(0, 1)
+                target = st.privileged_actions[a:b]
+                actions = pol.act_inference(obs).view(target.shape)
+                per_step = self.loss_fn(actions, target, reduction="none").flatten(1).mean(dim=1)
+                self._loss_sum += per_step.detach().sum(dtype=torch.float64)
+                out = out + per_step.sum()
+                k += b - a
+            return out
+
+        while n_steps + gl <= total:
+            window_loss(n_steps, gl).backward()   # accumulates into the (zeroed) flat gradient views
+            self._optimizer_step()
+            n_steps += gl
+            if self._mb_hook is not None:
+                self._mb_hook()
+        if n_steps < total:   # the trailing steps only enter the reported mean (the reference drops their gradient)
+            with torch.no_grad():
+                window_loss(n_steps, total - n_steps)
+        mean_behavior_loss = float(self._loss_sum.item()) / total   # the one device->host read of update()
+        st.clear()
+        self.last_hidden_states = pol.get_hidden_states()
         if self._fused_adam:
             self.optimizer.sync_host_state(self.learning_rate)
         return {"behavior": mean_behavior_loss}

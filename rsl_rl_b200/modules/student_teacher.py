@@ -60,7 +60,10 @@ class _StudentTeacherBase(nn.Module):
         return self.distribution.entropy().sum(dim=-1)
 
     def update_distribution(self, features):
-        mean = self.student(features)
+        self.set_distribution(self.student(features))
+
+    def set_distribution(self, mean):
+        """The action distribution around a student output `mean` computed elsewhere (Distillation's grouped rollout)."""
         if self.noise_std_type == "scalar":
             std = self.std.expand_as(mean)
         elif self.noise_std_type == "log":

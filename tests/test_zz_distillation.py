@@ -127,22 +127,36 @@ def _check_distillation(name, device, tol):
     return runner
 
 
-@pytest.mark.parametrize("name", CASES)
-def test_distillation_host_logic_matches_reference_golden_on_the_emulated_abi(name, monkeypatch):
+@pytest.mark.parametrize("name,batched", [("distill_mlp_small", True), ("distill_mlp_small", False),
+                                          ("distill_lstm_small", True)])
+def test_distillation_host_logic_matches_reference_golden_on_the_emulated_abi(name, batched, monkeypatch):
+    """`batched`: the feed-forward student's update as one batch per optimiser step and the grouped student / teacher
+    rollout launches (the default) against the step-by-step restatement of the reference's loop; a recurrent student
+    always runs step by step.  The golden's windows (gradient_length 4 over 2 epochs of 10 steps) cross the epoch
+    boundary, and two trailing steps only enter the reported loss."""
     from tests import host_emulation
+    monkeypatch.setenv("RSLRL_DISTILL_BATCHED", "1" if batched else "0")
     lib = host_emulation.install(monkeypatch)
-    _check_distillation(name, "cpu", 2e-5)
+    runner = _check_distillation(name, "cpu", 2e-5)
+    assert runner.alg._batched_update == (batched and name == "distill_mlp_small")
     assert "store_transition" in lib.calls and "allreduce_clip_adam" in lib.calls and "linear_backward_weight" in lib.calls
     if "lstm" in name:
         assert "lstm_step_backward" in lib.calls
+    if name == "distill_mlp_small":
+        # 2 iterations x (10 rollout steps + 2 epochs x 10 stored steps): layer launches per iteration
+        fwd = lib.calls.count("linear_forward")
+        assert fwd == (2 * (10 * 3 + 6 * 3) if batched else 2 * (10 * 6 + 20 * 3)), fwd
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", CASES)
-def test_distillation_matches_reference_golden(name):
+@pytest.mark.parametrize("name,batched", [("distill_mlp_small", True), ("distill_mlp_small", False),
+                                          ("distill_lstm_small", True)])
+def test_distillation_matches_reference_golden(name, batched, monkeypatch):
     from rsl_rl_b200 import _native as nat
+    monkeypatch.setenv("RSLRL_DISTILL_BATCHED", "1" if batched else "0")
     before = nat.launch_count()
-    _check_distillation(name, "cuda:0", 2e-5)
+    runner = _check_distillation(name, "cuda:0", 2e-5)
+    assert runner.alg._batched_update == (batched and name == "distill_mlp_small")
     assert nat.launch_count() > before   # the library's kernels ran (no silent framework path)
 
 
