@@ -276,7 +276,7 @@ def scenario_ppo_mlp(out_dir, name, *, num_envs, num_steps, group_dims, obs_grou
 
 def scenario_distillation(out_dir, name, *, num_envs, num_steps, group_dims, obs_groups, teacher_groups, num_actions,
                           hidden, activation, policy_class, policy_extra, teacher_class, teacher_extra, alg_overrides,
-                          iterations, seed=0, p_done=0.1):
+                          iterations, seed=0, p_done=0.1, checkpoint=False):
     """Teacher-student distillation: `DistillationRunner.learn` of the unmodified reference
     (runners/distillation_runner.py:56-150, algorithms/distillation.py:84-150) with the teacher taken from a reference
     PPO policy's state dict (student_teacher.py:168-206: `actor.*` -> `teacher.*`).  Recorded per iteration: the env
@@ -339,11 +339,19 @@ def scenario_distillation(out_dir, name, *, num_envs, num_steps, group_dims, obs
             return out
 
         runner.alg.update = update_and_record
-        for it in range(iterations):
+        for it in range(iterations + int(checkpoint)):
+            if it == iterations:
+                # a checkpoint WRITTEN BY THE REFERENCE (on_policy_runner.py:289-305) after the last regular iteration, then
+                # one more iteration of the same runner: what a run resumed from that checkpoint has to reproduce (optimiser
+                # moments and step count, normaliser statistics, iteration counter)
+                ckpt = os.path.join(out_dir, name + "_ref_checkpoint.pt")
+                runner.save(ckpt)
+                print("wrote", ckpt, f"{os.path.getsize(ckpt) / 1024:.0f} KiB")
+                data["resume.iter"] = np.array(runner.current_learning_iteration)
             n_norm, n_clip, n_step = len(rec.normal_z), len(rec.clip_calls), len(rec.step_calls)
             first_obs, first_step = len(env.obs_log) - 1, len(env.rew_log)
             runner.learn(1)
-            p = f"it{it}."
+            p = f"it{it}." if it < iterations else "resume."
             T = num_steps
             for g in group_dims:
                 data[p + f"stream.obs.{g}"] = np.stack([env.obs_log[first_obs + t][g] for t in range(T + 1)])
@@ -610,7 +618,7 @@ def main():
         policy_extra=dict(student_obs_normalization=True, teacher_obs_normalization=True, noise_std_type="scalar"),
         teacher_class="ActorCritic", teacher_extra=dict(actor_obs_normalization=True),
         alg_overrides=dict(num_learning_epochs=2, gradient_length=4, max_grad_norm=1.0, loss_type="mse"),
-        iterations=2, seed=31)
+        iterations=2, seed=31, checkpoint=True)
     todo["distill_lstm_small"] = lambda: scenario_distillation(
         args.out, "distill_lstm_small", num_envs=32, num_steps=8, group_dims={"policy": 10, "priv": 4},
         obs_groups={"policy": ["policy"], "teacher": ["policy", "priv"]}, teacher_groups=["policy", "priv"],

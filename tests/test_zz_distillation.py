@@ -17,14 +17,16 @@ from tests.golden_util import load, meta_of, rel_err
 CASES = ["distill_mlp_small", "distill_lstm_small"]
 
 
-def _runner(g, meta, device):
+def _runner(g, meta, device, parts=None):
+    """DistillationRunner on an env that replays the recorded stream of `parts` (default: the regular iterations)."""
     from rsl_rl_b200.env import ReplayVecEnv
     from rsl_rl_b200.runners import DistillationRunner
-    T, iters = meta["num_steps"], meta["iterations"]
+    T = meta["num_steps"]
+    parts = parts or [f"it{i}." for i in range(meta["iterations"])]
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
-    obs = {k: t(np.concatenate([g[f"it{i}.stream.obs.{k}"][:T + (i == iters - 1)] for i in range(iters)]))
+    obs = {k: t(np.concatenate([g[f"{p}stream.obs.{k}"][:T + (p == parts[-1])] for p in parts]))
            for k in meta["group_dims"]}
-    cat = lambda key: t(np.concatenate([g[f"it{i}.stream.{key}"] for i in range(iters)]))
+    cat = lambda key: t(np.concatenate([g[f"{p}stream.{key}"] for p in parts]))
     env = ReplayVecEnv(obs, cat("rewards"), cat("dones"), None, meta["num_actions"], device=device)
     cfg = dict(num_steps_per_env=T, save_interval=10 ** 9, obs_groups={k: list(v) for k, v in meta["obs_groups"].items()},
                policy=dict(class_name=meta["policy_class"], student_hidden_dims=list(meta["hidden"]),
@@ -158,6 +160,72 @@ def test_distillation_matches_reference_golden(name, batched, monkeypatch):
     runner = _check_distillation(name, "cuda:0", 2e-5)
     assert runner.alg._batched_update == (batched and name == "distill_mlp_small")
     assert nat.launch_count() > before   # the library's kernels ran (no silent framework path)
+
+
+def test_distillation_resumes_from_a_reference_written_checkpoint(monkeypatch, tmp_path):
+    """`tests/golden/distill_mlp_small_ref_checkpoint.pt` was written by the reference's `runner.save` after the golden's
+    last regular iteration (its Adam state only has entries for the parameters that ever received a gradient: the student's);
+    the reference then ran one more iteration (`resume.*`).  A fresh runner that loads the checkpoint reproduces that
+    iteration step for step -- optimiser moments, bias-correction step count, normaliser statistics and the iteration
+    counter all came back -- and its own checkpoint loads again with the same result."""
+    import os
+    from tests import host_emulation
+    from tests.golden_util import GOLDEN
+    host_emulation.install(monkeypatch)
+    g = load("distill_mlp_small")
+    meta = meta_of(g)
+    ckpt = os.path.join(GOLDEN, "distill_mlp_small_ref_checkpoint.pt")
+    ref = torch.load(ckpt, weights_only=False)
+    assert sorted(ref["optimizer_state_dict"]["state"].keys()) == [1, 2, 3, 4, 5, 6]   # std (0) and the teacher: no state
+
+    def resumed_runner(path):
+        runner = _runner(g, meta, "cpu", parts=["resume."])
+        runner.load(path)
+        assert runner.alg.policy.loaded_teacher and runner.current_learning_iteration == int(g["resume.iter"])
+        return runner
+
+    def run_resumed_iteration(runner):
+        alg, pol = runner.alg, runner.alg.policy
+        zq = [torch.from_numpy(z) for z in g["resume.z_rollout"]]
+        pol._noise_fn = lambda like, q=zq: q.pop(0)
+        trace = []
+        alg._mb_hook = lambda: trace.append(torch.cat([q.detach().reshape(-1) for q in pol.parameters()]).numpy().copy())
+        runner.learn(1)
+        assert len(trace) == len(g["resume.mb.params_after"])
+        for i, (mine, want) in enumerate(zip(trace, g["resume.mb.params_after"])):
+            assert rel_err(mine, want) < 5e-5, i
+        for k, v in pol.state_dict().items():
+            want = g["resume.final." + k]
+            assert (int(v) == int(want)) if k.endswith("count") else rel_err(v.numpy(), want) < 5e-5, k
+
+    first = resumed_runner(ckpt)
+    for k, v in first.alg.policy.state_dict().items():
+        assert np.array_equal(v.numpy(), g["it1.final." + k]), k          # the checkpoint IS the end of iteration 1
+    opt = first.alg.optimizer
+    assert opt._host_step == int(float(ref["optimizer_state_dict"]["state"][1]["step"])) == 10
+    for i, p in enumerate(first.alg._group.params):
+        m, v = first.alg._group.moment_views(i)
+        if i in ref["optimizer_state_dict"]["state"]:
+            assert torch.equal(m, ref["optimizer_state_dict"]["state"][i]["exp_avg"])
+            assert torch.equal(v, ref["optimizer_state_dict"]["state"][i]["exp_avg_sq"])
+        else:
+            assert not m.any() and not v.any()
+    mine = str(tmp_path / "model_0.pt")
+    first.save(mine)                                   # our checkpoint of the same state, before the resumed iteration
+    saved = torch.load(mine, weights_only=False)
+    assert set(saved) == set(ref) and set(saved["model_state_dict"]) == set(ref["model_state_dict"])
+    assert len(saved["optimizer_state_dict"]["param_groups"][0]["params"]) == 13
+    run_resumed_iteration(first)
+    run_resumed_iteration(resumed_runner(mine))
+    # a PPO checkpoint through the same `load`: teacher only, nothing resumes, the optimiser is left alone
+    ppo_ckpt = str(tmp_path / "ppo.pt")
+    torch.save({"model_state_dict": {k[len("teacher_ckpt."):]: torch.from_numpy(g[k]) for k in g.files
+                                     if k.startswith("teacher_ckpt.")},
+                "optimizer_state_dict": {"state": {}, "param_groups": []}, "iter": 77, "infos": {"from": "ppo"}}, ppo_ckpt)
+    fresh = _runner(g, meta, "cpu", parts=["resume."])
+    assert fresh.load(ppo_ckpt) == {"from": "ppo"} and fresh.current_learning_iteration == 0
+    assert fresh.alg.policy.loaded_teacher and fresh.alg.optimizer._host_step == 0
+    assert np.array_equal(fresh.alg.policy.teacher[0].weight.detach().numpy(), g["teacher_ckpt.actor.0.weight"])
 
 
 def test_distillation_storage_and_algorithm_argument_errors(monkeypatch):
