@@ -67,3 +67,78 @@ def test_two_rank_gradient_exchange_and_identical_parameters(tmp_path):
     a, b = np.load(tmp_path / "rank0.npy"), np.load(tmp_path / "rank1.npy")
     assert np.array_equal(a, b), "ranks disagree after the step"     # bit-identical, as the reference guarantees
     assert 1e-5 <= a[-1] <= 1e-2
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Distillation on two ranks (reference algorithms/distillation.py:156-185: broadcast_parameters / reduce_parameters)
+# ---------------------------------------------------------------------------------------------------------------------
+
+class _Setattr:
+    """pytest's monkeypatch is not available inside a spawned worker; the process ends with the test."""
+
+    def setattr(self, obj, name, value):
+        setattr(obj, name, value)
+
+
+def _distill_streams(N, T, A, dims):
+    rng = np.random.default_rng(7)
+    f = lambda *s: torch.from_numpy(rng.standard_normal(s).astype(np.float32))
+    obs = {k: f(T + 1, N, d) for k, d in dims.items()}
+    return obs, f(T, N), torch.from_numpy((rng.random((T, N)) < 0.1).astype(np.int64)), f(T, N, A)
+
+
+def _distill_run(rank, world, n_per_rank, seed):
+    """One rollout + update of a feed-forward student on the env columns of `rank` (world 1: all columns)."""
+    from rsl_rl_b200.algorithms import Distillation
+    from rsl_rl_b200.modules import StudentTeacher
+    from rsl_rl_b200.utils import TensorDictLite
+    T, A, dims = 6, 3, {"policy": 7, "priv": 4}
+    obs, rew, dones, z = _distill_streams(2 * n_per_rank, T, A, dims)
+    cols = slice(rank * n_per_rank, (rank + 1) * n_per_rank) if world > 1 else slice(None)
+    n = n_per_rank if world > 1 else 2 * n_per_rank
+    td = lambda t: TensorDictLite({k: v[t, cols].contiguous() for k, v in obs.items()}, batch_size=[n])
+    torch.manual_seed(seed)
+    policy = StudentTeacher(td(0), {"policy": ["policy"], "teacher": ["policy", "priv"]}, A, student_hidden_dims=[16, 8],
+                            teacher_hidden_dims=[16, 8])
+    alg = Distillation(policy, num_learning_epochs=2, gradient_length=4, learning_rate=1e-3, max_grad_norm=0.02,
+                       device="cpu", multi_gpu_cfg=None if world == 1 else dict(global_rank=rank, world_size=world))
+    alg.init_storage("distillation", n, T, td(0), [A])
+    if world > 1:
+        alg.broadcast_parameters()     # rank 0's parameters (and buffers) everywhere, one flat broadcast
+    zq = [z[t, cols].clone() for t in range(T)]
+    policy._noise_fn = lambda like: zq.pop(0)
+    with torch.inference_mode():
+        for t in range(T):
+            alg.act(td(t))
+            alg.process_env_step(td(t + 1), rew[t, cols].contiguous(), dones[t, cols].contiguous(), {})
+    loss = alg.update()
+    return torch.cat([p.detach().reshape(-1) for p in policy.parameters()]).numpy().copy(), loss["behavior"]
+
+
+def _distill_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tests import host_emulation
+    host_emulation.install(_Setattr())
+    params, loss = _distill_run(rank, world, 16, seed=100 + rank)   # different initial weights before the broadcast
+    np.save(os.path.join(out_dir, f"distill_rank{rank}.npy"), np.concatenate([params, [loss]]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_distillation_equals_one_rank_on_all_envs(tmp_path, monkeypatch):
+    """Host logic of multi-GPU distillation above the emulated ABI (tests/host_emulation.py), gloo in place of NCCL: after
+    the flat parameter broadcast, gradient averaging before the student-only clip and the fused step, (1) both ranks hold
+    bit-identical parameters and (2) they equal ONE rank training on the union of the envs -- the behaviour-cloning loss is
+    a mean over envs, so the mean of the two ranks' gradients is the gradient of the doubled batch (fp32 summation order
+    aside)."""
+    port = 29900 + os.getpid() % 90
+    mp.spawn(_distill_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a, b = np.load(tmp_path / "distill_rank0.npy"), np.load(tmp_path / "distill_rank1.npy")
+    assert np.array_equal(a[:-1], b[:-1]), "ranks disagree after the update"
+    from tests import host_emulation
+    host_emulation.install(monkeypatch)
+    single, loss = _distill_run(0, 1, 16, seed=100)     # rank 0's initial weights, all 32 envs
+    assert np.abs(a[:-1] - single).max() < 2e-6 * np.abs(single).max()
+    assert abs(0.5 * (a[-1] + b[-1]) - loss) < 1e-6 * max(1.0, abs(loss))   # mean of the ranks' losses = loss on the union
