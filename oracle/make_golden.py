@@ -619,6 +619,15 @@ def main():
         teacher_class="ActorCritic", teacher_extra=dict(actor_obs_normalization=True),
         alg_overrides=dict(num_learning_epochs=2, gradient_length=4, max_grad_norm=1.0, loss_type="mse"),
         iterations=2, seed=31, checkpoint=True)
+    # a stock optimiser with weight decay (utils.py:52-75 resolve_optimizer): parameters without a gradient must not move
+    todo["distill_mlp_adamw"] = lambda: scenario_distillation(
+        args.out, "distill_mlp_adamw", num_envs=32, num_steps=6, group_dims={"policy": 8, "priv": 4},
+        obs_groups={"policy": ["policy"], "teacher": ["policy", "priv"]}, teacher_groups=["policy", "priv"],
+        num_actions=3, hidden=[16, 8], activation="tanh", policy_class="StudentTeacher",
+        policy_extra=dict(noise_std_type="log"), teacher_class="ActorCritic", teacher_extra={},
+        alg_overrides=dict(num_learning_epochs=1, gradient_length=2, max_grad_norm=None, loss_type="huber",
+                           optimizer="adamw", learning_rate=3e-3),
+        iterations=1, seed=33)
     todo["distill_lstm_small"] = lambda: scenario_distillation(
         args.out, "distill_lstm_small", num_envs=32, num_steps=8, group_dims={"policy": 10, "priv": 4},
         obs_groups={"policy": ["policy"], "teacher": ["policy", "priv"]}, teacher_groups=["policy", "priv"],

@@ -78,6 +78,12 @@ class Distillation:
             self.optimizer = optimizer_cls(self._group.params, lr=learning_rate)
         self._fused_adam = isinstance(self.optimizer, FusedAdam)
         self._student_slice = self._flat_slice(self.policy.student)
+        # parameters update() never differentiates (teacher side, noise): the reference's optimiser sees `grad is None`
+        # for them and skips them -- which matters for optimisers that act on a parameter without a gradient (AdamW's
+        # weight decay); their flat gradient views are hidden from a stock optimiser's step for the same effect
+        learnable = {id(p) for name, mod in self.policy.named_children() if name in ("student", "memory_s")
+                     for p in mod.parameters()}
+        self._never_trained = [p for p in self._group.params if id(p) not in learnable]
 
         self.transition = RolloutStorage.Transition()
         self.last_hidden_states = None
@@ -256,7 +262,14 @@ class Distillation:
         if self._fused_adam:
             self.optimizer.fused_step(world_size=1, max_grad_norm=0.0, adaptive=False, use_kl=False, zero_grad=True)
         else:
-            self.optimizer.step()
+            hidden = [(p, p.grad) for p in self._never_trained]
+            for p, _ in hidden:
+                p.grad = None
+            try:
+                self.optimizer.step()
+            finally:
+                for p, grad in hidden:
+                    p.grad = grad
             g.zero_grad()
 
     # ------------------------------------------------------------------------------------------
