@@ -637,6 +637,17 @@ def main():
         teacher_class="ActorCriticRecurrent", teacher_extra=dict(rnn_type="lstm", rnn_hidden_dim=16, rnn_num_layers=1),
         alg_overrides=dict(num_learning_epochs=1, gradient_length=3, max_grad_norm=0.5, loss_type="huber"),
         iterations=2, seed=32, p_done=0.15)
+    # two LSTM layers, a feed-forward teacher, windows of 3 over two epochs of 8 steps: the third window crosses the epoch
+    # boundary (where the reference re-installs the start-of-rollout hidden state), one trailing step
+    todo["distill_lstm2_cross"] = lambda: scenario_distillation(
+        args.out, "distill_lstm2_cross", num_envs=24, num_steps=8, group_dims={"policy": 6, "priv": 3},
+        obs_groups={"policy": ["policy"], "teacher": ["policy", "priv"]}, teacher_groups=["policy", "priv"],
+        num_actions=2, hidden=[16, 8], activation="elu", policy_class="StudentTeacherRecurrent",
+        policy_extra=dict(student_obs_normalization=True, rnn_type="lstm", rnn_hidden_dim=8, rnn_num_layers=2,
+                          teacher_recurrent=False),
+        teacher_class="ActorCritic", teacher_extra={},
+        alg_overrides=dict(num_learning_epochs=2, gradient_length=3, max_grad_norm=None, loss_type="mse"),
+        iterations=2, seed=34, p_done=0.2)
     for name, fn in todo.items():
         if args.only in (None, name):
             fn()

@@ -100,6 +100,11 @@ class Distillation:
         from ..modules.student_teacher import StudentTeacher
         plain = type(policy) is StudentTeacher and os.environ.get("RSLRL_DISTILL_BATCHED", "1") != "0"
         self._batched_update = plain
+        # a student with a native LSTM memory: every run of steps between two optimiser steps as ONE multi-step LSTM call
+        # over the trajectories the dones cut it into (opt-in until it has been measured on the GPU)
+        from ..modules.student_teacher_recurrent import StudentTeacherRecurrent
+        self._windowed_recurrent = (type(policy) is StudentTeacherRecurrent and policy.memory_s.native
+                                    and os.environ.get("RSLRL_DISTILL_WINDOWED", "0") == "1")
         self._grouped_rollout = plain and (len(policy.student.linear_layers()) == len(policy.teacher.linear_layers())
                                            and not any(isinstance(m, nn.Unflatten) for net in (policy.student, policy.teacher)
                                                        for m in net))
@@ -174,6 +179,8 @@ class Distillation:
         self._loss_sum.zero_()
         if self._batched_update:
             return self._update_feedforward()
+        if self._windowed_recurrent:
+            return self._update_recurrent_windows()
         loss = 0
         cnt = 0
         for _ in range(self.num_learning_epochs):
@@ -244,6 +251,92 @@ class Distillation:
         mean_behavior_loss = float(self._loss_sum.item()) / total   # the one device->host read of update()
         st.clear()
         self.last_hidden_states = pol.get_hidden_states()
+        if self._fused_adam:
+            self.optimizer.sync_host_state(self.learning_rate)
+        return {"behavior": mean_behavior_loss}
+
+    def _update_recurrent_windows(self):
+        """update() of a student with a native LSTM memory, one multi-step LSTM call per window instead of one call per
+        stored step.  Gradients never leave a window (hidden states are detached after every optimiser step) and never cross
+        a done (the state is zeroed there), so a run of consecutive steps is a set of independent trajectories -- exactly
+        what the recurrent PPO update is made of: the run's dones are scanned into a trajectory index, the normalised
+        observations are split and padded, the LSTM runs over all of them at once (hoisted input projection, time loop in C,
+        backward through time over the padded grid), the outputs are un-padded into [steps, envs] for the student MLP.
+        A trajectory that starts at the first step of the run continues from the carried state, every other one from
+        zero; the state carried out of the run is every environment's state at the end of its last trajectory (read from
+        the LSTM's state buffers), zeroed where that step was done.  A window that crosses the epoch boundary is two runs:
+        the reference re-installs the start-of-rollout state at every epoch start while its loss sum and step counter
+        carry on."""
+        from ..networks.lstm import lstm_forward, tap_states
+        from ..utils.utils import TrajectoryIndex, unpad_trajectories
+        pol, st = self.policy, self.storage
+        mem = pol.memory_s
+        T, gl, N = st.num_transitions_per_env, self.gradient_length, st.num_envs
+        L, H = mem.rnn.num_layers, mem.rnn.hidden_size
+
+        def run_loss(t0: int, count: int):
+            """Sum of the per-step mean losses of stored steps [t0, t0 + count); advances `mem.hidden_states`."""
+            obs = st.observations[t0:t0 + count].flatten(0, 1)
+            x = pol.student_obs_normalizer(pol.get_student_obs(obs))
+            x = x.reshape(count, N, x.shape[-1])
+            dones = st.dones[t0:t0 + count]
+            index = TrajectoryIndex(dones)
+            n_traj = index.n_traj                                    # the one host read of the run
+            padded = index.split_and_pad(x, 0, n_traj)               # [count, n_traj, D], zero padded
+            masks = index.masks(0, n_traj)
+            envs = index.traj_env[:n_traj].long()
+            prev = mem.hidden_states
+            if prev is None:
+                h0 = c0 = torch.zeros(L, n_traj, H, dtype=torch.float32, device=padded.device)
+            else:
+                continues = (index.traj_start[:n_traj] == 0).view(1, n_traj, 1)
+                h0, c0 = (torch.where(continues, s.detach()[:, envs], torch.zeros((), dtype=s.dtype, device=s.device))
+                          for s in prev)
+            with tap_states() as layers:
+                out, _ = lstm_forward(mem.rnn, padded, (h0, c0), mem.precision)
+            feats = unpad_trajectories(out, masks)                   # [count, N, H]
+            target = st.privileged_actions[t0:t0 + count]
+            actions = pol.student(feats.reshape(count * N, H)).view(target.shape)
+            per_step = self.loss_fn(actions, target, reduction="none").flatten(1).mean(dim=1)
+            self._loss_sum += per_step.detach().sum(dtype=torch.float64)
+            # every environment's state after the run: the end of its last trajectory, zero if that step was done
+            last = index.env_traj_offset[1:N + 1].long() - 1
+            length = index.traj_len[:n_traj].long()[last]
+            alive = (dones[count - 1].view(1, N, 1) != 1)
+            h_n = torch.stack([h_all[length, last] for (h_all, _), in layers]) * alive
+            c_n = torch.stack([c_all[length, last] for (_, c_all), in layers]) * alive
+            mem.hidden_states = (h_n, c_n)
+            if pol.teacher_recurrent and pol.memory_t.hidden_states is not None:   # (only zeroed at dones, never advanced)
+                for t in range(count):
+                    pol.memory_t.reset(dones[t].view(-1))
+            return per_step.sum()
+
+        total, done_steps, in_window, loss = self.num_learning_epochs * T, 0, 0, 0
+        trainable = (total // gl) * gl        # steps after the last full window only enter the reported mean
+        for _ in range(self.num_learning_epochs):
+            pol.reset(hidden_states=self.last_hidden_states)
+            pol.detach_hidden_states()
+            t = 0
+            while t < T:
+                if done_steps >= trainable:
+                    with torch.no_grad():
+                        run_loss(t, T - t)
+                    done_steps, t = done_steps + (T - t), T
+                    continue
+                count = min(gl - in_window, T - t)
+                loss = loss + run_loss(t, count)
+                in_window, t, done_steps = in_window + count, t + count, done_steps + count
+                if in_window == gl:
+                    loss.backward()   # accumulates into the (zeroed) flat gradient views
+                    self._optimizer_step()
+                    pol.detach_hidden_states()
+                    loss, in_window = 0, 0
+                    if self._mb_hook is not None:
+                        self._mb_hook()
+        mean_behavior_loss = float(self._loss_sum.item()) / total
+        st.clear()
+        self.last_hidden_states = _detached(pol.get_hidden_states())
+        pol.detach_hidden_states()
         if self._fused_adam:
             self.optimizer.sync_host_state(self.learning_rate)
         return {"behavior": mean_behavior_loss}

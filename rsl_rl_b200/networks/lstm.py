@@ -45,7 +45,30 @@ def _layers_forward(xs, h0s, c0s, w_ihs, w_hhs, b_ihs, b_hhs, prec: int, save: b
     linear_forward(projections, prec)                 # input projections of ALL steps (and all nets): one launch
     # the time loop runs in C: per step one grouped recurrent projection (h_{t-1} W_hh^T) + one fused cell launch
     nat.check(nat.lib().rslrl_lstm_layers_forward(G, arr, T, n, H, prec, nat.stream_ptr()))
+    if _state_tap is not None:
+        _state_tap.append([(h_all, c_all) for h_all, c_all, _, _ in out])
     return out
+
+
+_state_tap = None
+
+
+class tap_states:
+    """`with tap_states() as layers:` -- every LSTM layer evaluated inside the block appends its per-net
+    `(h_all, c_all)`, the states before step 0 and after every step ([T+1, n, H] each; read-only: they are the buffers the
+    backward pass reads).  For callers that need the cell state at a position inside a sequence (the windowed
+    distillation update picks every environment's state at the end of its last trajectory); outputs and gradients of the
+    LSTM functions are not affected."""
+
+    def __enter__(self):
+        global _state_tap
+        self._outer, _state_tap = _state_tap, []
+        return _state_tap
+
+    def __exit__(self, *exc):
+        global _state_tap
+        _state_tap = self._outer
+        return False
 
 
 class _LSTMGroupFunction(torch.autograd.Function):

@@ -129,6 +129,36 @@ def _check_distillation(name, device, tol):
     return runner
 
 
+def test_windowed_recurrent_distillation_matches_reference_golden_on_the_emulated_abi(monkeypatch):
+    """RSLRL_DISTILL_WINDOWED=1: a recurrent student's update as one multi-step LSTM call per run of steps between two
+    optimiser steps (trajectory split at dones, carried state for the trajectories that continue, state read back at the
+    end of every environment's last trajectory) lands on the same golden as the step-by-step loop: windows of 3 over 8
+    steps (the last two steps only advance the state), dones at 15 %, two iterations so the carried state matters."""
+    from tests import host_emulation
+    monkeypatch.setenv("RSLRL_DISTILL_WINDOWED", "1")
+    lib = host_emulation.install(monkeypatch)
+    runner = _check_distillation("distill_lstm_small", "cpu", 2e-5)
+    assert runner.alg._windowed_recurrent and "trajectory_index" in lib.calls and "split_and_pad" in lib.calls
+    # 2 iterations x (8 rollout steps x 2 memories + 3 runs in the update) multi-step calls instead of 2 x (16 + 8)
+    assert lib.calls.count("lstm_step_forward") == 2 * (16 + 3)
+
+
+@pytest.mark.parametrize("windowed", [False, True])
+def test_recurrent_distillation_across_the_epoch_boundary_two_lstm_layers(windowed, monkeypatch):
+    """Golden `distill_lstm2_cross`: a 2-layer LSTM student, a feed-forward teacher, windows of 3 over two epochs of 8
+    steps -- the third window crosses the epoch boundary, where the reference re-installs the start-of-rollout hidden state
+    while its loss sum and step counter carry on (distillation.py:110-112), and one trailing step only advances the state.
+    Both update paths (step by step, and one multi-step LSTM call per run) land on it."""
+    from tests import host_emulation
+    monkeypatch.setenv("RSLRL_DISTILL_WINDOWED", "1" if windowed else "0")
+    lib = host_emulation.install(monkeypatch)
+    runner = _check_distillation("distill_lstm2_cross", "cpu", 2e-5)
+    assert runner.alg._windowed_recurrent == windowed and runner.alg.policy.memory_s.rnn.num_layers == 2
+    # per iteration: 8 rollout steps, then 16 stored steps = runs [0-2] [3-5] [6-7 | 0] [1-3] [4-6] [7]: 7 multi-step calls
+    per_iter = (8 + 7) if windowed else (8 + 16)
+    assert lib.calls.count("lstm_step_forward") == 2 * per_iter * 2      # (x 2 layers)
+
+
 @pytest.mark.parametrize("name,batched", [("distill_mlp_small", True), ("distill_mlp_small", False),
                                           ("distill_lstm_small", True), ("distill_mlp_adamw", True)])
 def test_distillation_host_logic_matches_reference_golden_on_the_emulated_abi(name, batched, monkeypatch):
