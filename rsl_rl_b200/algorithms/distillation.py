@@ -101,10 +101,11 @@ class Distillation:
         plain = type(policy) is StudentTeacher and os.environ.get("RSLRL_DISTILL_BATCHED", "1") != "0"
         self._batched_update = plain
         # a student with a native LSTM memory: every run of steps between two optimiser steps as ONE multi-step LSTM call
-        # over the trajectories the dones cut it into (opt-in until it has been measured on the GPU)
+        # over the trajectories the dones cut it into (RSLRL_DISTILL_WINDOWED=0: the step-by-step restatement of the
+        # reference's loop, which GRU students always use)
         from ..modules.student_teacher_recurrent import StudentTeacherRecurrent
         self._windowed_recurrent = (type(policy) is StudentTeacherRecurrent and policy.memory_s.native
-                                    and os.environ.get("RSLRL_DISTILL_WINDOWED", "0") == "1")
+                                    and os.environ.get("RSLRL_DISTILL_WINDOWED", "1") != "0")
         self._grouped_rollout = plain and (len(policy.student.linear_layers()) == len(policy.teacher.linear_layers())
                                            and not any(isinstance(m, nn.Unflatten) for net in (policy.student, policy.teacher)
                                                        for m in net))

@@ -130,7 +130,7 @@ def _check_distillation(name, device, tol):
 
 
 def test_windowed_recurrent_distillation_matches_reference_golden_on_the_emulated_abi(monkeypatch):
-    """RSLRL_DISTILL_WINDOWED=1: a recurrent student's update as one multi-step LSTM call per run of steps between two
+    """RSLRL_DISTILL_WINDOWED=1 (the default): a recurrent student's update as one multi-step LSTM call per run of steps between two
     optimiser steps (trajectory split at dones, carried state for the trajectories that continue, state read back at the
     end of every environment's last trajectory) lands on the same golden as the step-by-step loop: windows of 3 over 8
     steps (the last two steps only advance the state), dones at 15 %, two iterations so the carried state matters."""
@@ -159,18 +159,26 @@ def test_recurrent_distillation_across_the_epoch_boundary_two_lstm_layers(window
     assert lib.calls.count("lstm_step_forward") == 2 * per_iter * 2      # (x 2 layers)
 
 
-@pytest.mark.parametrize("name,batched", [("distill_mlp_small", True), ("distill_mlp_small", False),
-                                          ("distill_lstm_small", True), ("distill_mlp_adamw", True)])
-def test_distillation_host_logic_matches_reference_golden_on_the_emulated_abi(name, batched, monkeypatch):
-    """`batched`: the feed-forward student's update as one batch per optimiser step and the grouped student / teacher
-    rollout launches (the default) against the step-by-step restatement of the reference's loop; a recurrent student
-    always runs step by step.  The golden's windows (gradient_length 4 over 2 epochs of 10 steps) cross the epoch
-    boundary, and two trailing steps only enter the reported loss."""
-    from tests import host_emulation
+def _select_update_path(monkeypatch, batched):
+    """batched: the defaults (a feed-forward student's window as one batch + grouped rollout launches, a recurrent
+    student's window as one multi-step LSTM call); otherwise the step-by-step restatement of the reference's loop."""
     monkeypatch.setenv("RSLRL_DISTILL_BATCHED", "1" if batched else "0")
+    monkeypatch.setenv("RSLRL_DISTILL_WINDOWED", "1" if batched else "0")
+
+
+@pytest.mark.parametrize("name,batched", [("distill_mlp_small", True), ("distill_mlp_small", False),
+                                          ("distill_lstm_small", True), ("distill_lstm_small", False),
+                                          ("distill_mlp_adamw", True)])
+def test_distillation_host_logic_matches_reference_golden_on_the_emulated_abi(name, batched, monkeypatch):
+    """Both update paths of either student kind land on the reference's golden.  The feed-forward golden's windows
+    (gradient_length 4 over 2 epochs of 10 steps) cross the epoch boundary; the recurrent golden has two trailing steps
+    that only advance the hidden state."""
+    from tests import host_emulation
+    _select_update_path(monkeypatch, batched)
     lib = host_emulation.install(monkeypatch)
     runner = _check_distillation(name, "cpu", 2e-5)
     assert runner.alg._batched_update == (batched and "mlp" in name)
+    assert runner.alg._windowed_recurrent == (batched and "lstm" in name)
     assert "store_transition" in lib.calls and "linear_backward_weight" in lib.calls
     # torch.optim.Adam is the fused kernel; AdamW / SGD / RMSprop are torch's optimisers on the flat-buffer views
     assert ("allreduce_clip_adam" in lib.calls) == (name != "distill_mlp_adamw")
@@ -185,13 +193,14 @@ def test_distillation_host_logic_matches_reference_golden_on_the_emulated_abi(na
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,batched", [("distill_mlp_small", True), ("distill_mlp_small", False),
-                                          ("distill_lstm_small", True)])
+                                          ("distill_lstm_small", True), ("distill_lstm_small", False)])
 def test_distillation_matches_reference_golden(name, batched, monkeypatch):
     from rsl_rl_b200 import _native as nat
-    monkeypatch.setenv("RSLRL_DISTILL_BATCHED", "1" if batched else "0")
+    _select_update_path(monkeypatch, batched)
     before = nat.launch_count()
     runner = _check_distillation(name, "cuda:0", 2e-5)
     assert runner.alg._batched_update == (batched and name == "distill_mlp_small")
+    assert runner.alg._windowed_recurrent == (batched and name == "distill_lstm_small")
     assert nat.launch_count() > before   # the library's kernels ran (no silent framework path)
 
 
