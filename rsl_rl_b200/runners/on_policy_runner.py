@@ -96,6 +96,7 @@ class OnPolicyRunner:
         self.git_status_repos = [rsl_rl_b200.__file__]
         self.profile_phases = False
         self.phase_times = {}
+        self._needs_returns = hasattr(self.alg, "compute_returns")   # (behaviour cloning has no returns / advantages)
         self._env_device, self._action_ring, self._action_slot = None, None, 0
 
     def _default_obs_sets(self) -> list:
@@ -107,8 +108,12 @@ class OnPolicyRunner:
         return sets
 
     # ------------------------------------------------------------------------------------------
+    def _check_ready(self):
+        """Hook: conditions a subclass wants checked before training starts (DistillationRunner: a loaded teacher)."""
+
     def learn(self, num_learning_iterations: int, init_at_random_ep_len: bool = False):
         self._prepare_logging_writer()
+        self._check_ready()
         if init_at_random_ep_len:
             self.env.episode_length_buf = torch.randint_like(self.env.episode_length_buf,
                                                              high=int(self.env.max_episode_length))
@@ -160,7 +165,8 @@ class OnPolicyRunner:
                 start = stop
                 if prof:
                     e1.record()
-                self.alg.compute_returns(obs)
+                if self._needs_returns:
+                    self.alg.compute_returns(obs)
                 if prof:
                     e2.record()
             loss_dict = self.alg.update()
