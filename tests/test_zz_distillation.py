@@ -270,6 +270,37 @@ def test_distillation_resumes_from_a_reference_written_checkpoint(monkeypatch, t
     assert np.array_equal(fresh.alg.policy.teacher[0].weight.detach().numpy(), g["teacher_ckpt.actor.0.weight"])
 
 
+def test_distillation_runner_logs_and_saves_like_the_on_policy_runner(monkeypatch, tmp_path, capsys):
+    """`log_dir` set: the shared loop's logging path with a Distillation algorithm (loss dict `behavior`, no RND buffers),
+    TensorBoard scalars, the console table, `model_<it>.pt` with the reference's checkpoint keys."""
+    import os
+    pytest.importorskip("tensorboard")
+    from tests import host_emulation
+    host_emulation.install(monkeypatch)
+    g = load("distill_mlp_small")
+    meta = meta_of(g)
+    from rsl_rl_b200.env import ReplayVecEnv
+    from rsl_rl_b200.runners import DistillationRunner
+    runner = _runner(g, meta, "cpu")
+    cfg = dict(num_steps_per_env=meta["num_steps"], save_interval=1, obs_groups={k: list(v) for k, v in meta["obs_groups"].items()},
+               policy=dict(class_name=meta["policy_class"], student_hidden_dims=list(meta["hidden"]),
+                           teacher_hidden_dims=list(meta["hidden"]), activation=meta["activation"], init_noise_std=0.1,
+                           **meta["policy_extra"]),
+               algorithm=dict(meta["alg"], class_name="Distillation"))
+    logged = DistillationRunner(runner.env, cfg, log_dir=str(tmp_path), device="cpu")
+    logged.alg.policy.load_state_dict(_state(g, "init.", "cpu"))
+    zq = [torch.from_numpy(z) for z in g["it0.z_rollout"]]
+    logged.alg.policy._noise_fn = lambda like, q=zq: q.pop(0)
+    logged.learn(1)
+    out = capsys.readouterr().out
+    assert "Learning iteration 0/1" in out and "behavior" in out and "Mean action noise std" in out
+    ckpt = torch.load(os.path.join(str(tmp_path), "model_0.pt"), weights_only=False)
+    assert set(ckpt) == {"model_state_dict", "optimizer_state_dict", "iter", "infos"} and ckpt["iter"] == 0
+    assert any(f.startswith("events.out.tfevents") for f in os.listdir(str(tmp_path)))
+    mine = torch.cat([q.detach().reshape(-1) for q in logged.alg.policy.parameters()]).numpy()
+    assert rel_err(mine, g["it0.mb.params_after"][-1]) < 5e-5      # logging does not change the training
+
+
 def test_distillation_storage_and_algorithm_argument_errors(monkeypatch):
     """Error behaviour of the reference: wrong generator for the training type (rollout_storage.py:153-154,161-162),
     unknown loss / optimiser names (distillation.py:71, utils.py:75), overflow of the rollout buffer (:79-80)."""
