@@ -648,6 +648,15 @@ def main():
         teacher_class="ActorCritic", teacher_extra={},
         alg_overrides=dict(num_learning_epochs=2, gradient_length=3, max_grad_norm=None, loss_type="mse"),
         iterations=2, seed=34, p_done=0.2)
+    # GRU student and teacher (single-tensor hidden states), teacher from a recurrent PPO checkpoint
+    todo["distill_gru_small"] = lambda: scenario_distillation(
+        args.out, "distill_gru_small", num_envs=24, num_steps=7, group_dims={"policy": 6, "priv": 3},
+        obs_groups={"policy": ["policy"], "teacher": ["policy", "priv"]}, teacher_groups=["policy", "priv"],
+        num_actions=2, hidden=[16, 8], activation="elu", policy_class="StudentTeacherRecurrent",
+        policy_extra=dict(rnn_type="gru", rnn_hidden_dim=8, rnn_num_layers=1, teacher_recurrent=True),
+        teacher_class="ActorCriticRecurrent", teacher_extra=dict(rnn_type="gru", rnn_hidden_dim=8, rnn_num_layers=1),
+        alg_overrides=dict(num_learning_epochs=2, gradient_length=3, max_grad_norm=1.0, loss_type="mse"),
+        iterations=2, seed=35, p_done=0.2)
     for name, fn in todo.items():
         if args.only in (None, name):
             fn()

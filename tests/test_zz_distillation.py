@@ -118,7 +118,7 @@ def _check_distillation(name, device, tol):
                 if h is None:   # the teacher's memory is reset at the start of update() and not advanced by it
                     assert p + f"hidden_{tag}0" not in g.files
                     continue
-                for i, x in enumerate(h):
+                for i, x in enumerate(h if isinstance(h, tuple) else (h,)):
                     assert not x.requires_grad
                     assert rel_err(x.cpu().numpy(), g[p + f"hidden_{tag}{i}"]) < 2.5 * tol, (tag, i)
         else:
@@ -268,6 +268,17 @@ def test_distillation_resumes_from_a_reference_written_checkpoint(monkeypatch, t
     assert fresh.load(ppo_ckpt) == {"from": "ppo"} and fresh.current_learning_iteration == 0
     assert fresh.alg.policy.loaded_teacher and fresh.alg.optimizer._host_step == 0
     assert np.array_equal(fresh.alg.policy.teacher[0].weight.detach().numpy(), g["teacher_ckpt.actor.0.weight"])
+
+
+def test_gru_student_distillation_host_logic_on_the_emulated_abi(monkeypatch):
+    """GRU memories on both sides (hidden state = one tensor instead of an (h, c) pair, reference memory.py:23,46-74): the
+    step-by-step update -- the GRU recurrence is torch's (cuDNN on the GPU), everything around it is this library's."""
+    from tests import host_emulation
+    lib = host_emulation.install(monkeypatch)
+    runner = _check_distillation("distill_gru_small", "cpu", 2e-5)
+    alg = runner.alg
+    assert not alg._windowed_recurrent and not alg._batched_update and not alg.policy.memory_s.native
+    assert isinstance(alg.last_hidden_states[0], torch.Tensor) and "lstm_step_forward" not in lib.calls
 
 
 def test_distillation_runner_logs_and_saves_like_the_on_policy_runner(monkeypatch, tmp_path, capsys):
