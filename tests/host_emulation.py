@@ -147,6 +147,74 @@ class EmulatedLibrary:
         _view(dones_row, N, np.uint8)[:] = _view(dones, N, flag_np[dones_dtype]).astype(np.float32).astype(np.int32).astype(np.uint8)
         return self._launch("store_transition")
 
+    # ---- csrc/storage.cu: the rollout fast path (row `step` fixed in a plan, only observations / rewards / dones move)
+    def rslrl_store_step(self, plan_ref, obs_src, rewards, dones, dones_dtype, time_outs, time_outs_dtype, intrinsic,
+                         stream):
+        sp = plan_ref._obj                       # ctypes.byref(rslrl_store_plan_t)
+        n, obs_dst, obs_dim = sp.n_groups, [sp.obs_dst[i] for i in range(sp.n_groups)], [sp.obs_dim[i] for i in range(sp.n_groups)]
+        rc = self.rslrl_store_transition(n, obs_src, obs_dst, obs_dim, None, None, None, 0, sp.values_row, None, rewards,
+                                         dones, dones_dtype, time_outs, time_outs_dtype, intrinsic, sp.gamma, None, None,
+                                         None, None, None, sp.rewards_row, sp.dones_row, sp.N, sp.A, stream)
+        self.calls[-1] = "store_step"
+        return rc
+
+    # ---- csrc/core.cu: Gaussian head of the rollout
+    def rslrl_gaussian_act(self, mu, std_param, std_type, z, actions, logp, sigma_out, n, A, stream):
+        f = np.float32
+        m, zz = _view(mu, n * A).reshape(n, A), _view(z, n * A).reshape(n, A)
+        sigma = _view(std_param, A) if std_type == nat.STD_SCALAR else np.exp(_view(std_param, A))
+        a = (zz * sigma).astype(f) + m                     # two roundings, as normal_().mul_().add_()
+        _view(actions, n * A).reshape(n, A)[:] = a
+        lp = -((a - m) ** 2) / (f(2) * sigma * sigma) - np.log(sigma) - f(math.log(math.sqrt(2 * math.pi)))
+        _view(logp, n)[:] = lp.sum(1)
+        if sigma_out:
+            _view(sigma_out, n * A).reshape(n, A)[:] = sigma
+        return self._launch("gaussian_act")
+
+    # ---- csrc/ppo_loss.cu (arithmetic: the numpy oracle's forward + hand-derived backward)
+    def rslrl_loss_workspace_bytes(self):
+        return 1024
+
+    def rslrl_sum_sumsq(self, x, n, out, workspace, stream):
+        v = _view(x, n).astype(np.float64)
+        _view(out, 2, np.float64)[:] = (v.sum(), (v * v).sum())
+        return self._launch("sum_sumsq")
+
+    def rslrl_ppo_loss_fwd_bwd(self, mu, std_param, std_type, value, actions, old_logp, adv, returns, old_values, old_mu,
+                               old_sigma, adv_stats, dmu, dmu_stride, dvalue, dvalue_stride, dstd, db_mu, db_value,
+                               kl_out, loss_sums, workspace, rows, mb_orig, A, clip_param, value_loss_coef, entropy_coef,
+                               use_clipped, dmu16, dmu16_stride, dvalue16, dvalue16_stride, grad_scale16, scale_state,
+                               head, stream):
+        from oracle import ppo_oracle as O
+        assert rows == mb_orig and not dmu16 and not head, "the emulation covers the fp32-class objective without augmentation"
+        f = np.float32
+        m = _view(mu, rows * A).reshape(rows, A)
+        std = _view(std_param, A)
+        sigma = np.broadcast_to(std if std_type == nat.STD_SCALAR else np.exp(std), (rows, A)).astype(f)
+        a = _view(adv, rows).copy()
+        if adv_stats:                                       # per-minibatch normalisation (ppo.py:221-223), unbiased std
+            s, ss = _view(adv_stats, 2, np.float64)
+            mean = s / rows
+            a = ((a - f(mean)) / (f(math.sqrt(max(ss - rows * mean * mean, 0.0) / (rows - 1))) + f(1e-8))).astype(f)
+        out = O.ppo_loss_fwd_bwd(m, sigma, _view(value, rows), _view(actions, rows * A).reshape(rows, A),
+                                 _view(old_logp, rows), a, _view(returns, rows), _view(old_values, rows), clip_param,
+                                 value_loss_coef, entropy_coef, bool(use_clipped))
+        _mat(dmu, rows, A, dmu_stride)[:] = out["dmu"]
+        _mat(dvalue, rows, 1, dvalue_stride)[:] = out["dvalue"]
+        dsig = out["dsigma"].sum(0) if std_type == nat.STD_SCALAR else (out["dsigma"] * sigma).sum(0)
+        if dstd:
+            _view(dstd, A)[:] += dsig.astype(f)
+        if db_mu:
+            _view(db_mu, A)[:] += out["dmu"].sum(0)
+        if db_value:
+            _view(db_value, 1)[:] += out["dvalue"].sum()
+        if kl_out:
+            _view(kl_out, 1)[0] = O.kl_mean(m, sigma, _view(old_mu, rows * A).reshape(rows, A),
+                                            _view(old_sigma, rows * A).reshape(rows, A))
+        if loss_sums:
+            _view(loss_sums, 3, np.float64)[:] += (out["surrogate"], out["value_loss"], out["entropy"])
+        return self._launch("ppo_loss_fwd_bwd")
+
     # ---- csrc/gae.cu (arithmetic: the numpy oracle, which is pinned bit-exactly to the reference's golden vectors)
     def rslrl_gae_norm(self, rewards, values, dones, last_values, returns, advantages, workspace, T, N, gamma, lam,
                        normalize, stream):
@@ -193,6 +261,19 @@ class EmulatedLibrary:
             if p.db_prev:
                 _view(p.db_prev, p.K)[:] += dx.sum(0)
         return self._launch("linear_backward_data")
+
+    def rslrl_linear_backward_head(self, n, probs, stream):
+        """Narrow output layer: data gradient (x activation derivative of the previous layer), weight and bias gradient."""
+        for i in range(n):
+            p = probs[i]
+            assert not p.f16
+            dy, w, h = _mat(p.dy, p.M, p.N, p.ldy), _mat(p.w, p.N, p.K, p.K), _mat(p.h, p.M, p.K, p.ldh)
+            if p.dx:
+                _mat(p.dx, p.M, p.K, p.ldx)[:] = ((dy @ w) * _act_grad_from_output(p.act, h)).astype(np.float32)
+            _mat(p.dw, p.N, p.K, p.K)[:] += dy.T @ h
+            if p.db:
+                _view(p.db, p.N)[:] += dy.sum(0)
+        return self._launch("linear_backward_head")
 
     def rslrl_linear_backward_weight(self, n, probs, precision, stream):
         for i in range(n):
@@ -385,5 +466,8 @@ def install(monkeypatch) -> EmulatedLibrary:
     monkeypatch.setattr(nat, "_lib", lib)
     monkeypatch.setattr(nat, "on_device", lambda t: True)
     monkeypatch.setattr(nat, "require_cuda_device", lambda device, what: None)
+    monkeypatch.setattr(nat, "require_device_readable", lambda *tensors: None)
+    from rsl_rl_b200.storage import rollout_storage
+    monkeypatch.setattr(rollout_storage, "_store_step_fn", None)   # (a cached entry point of whichever library came first)
     monkeypatch.setattr(nat, "stream_ptr", lambda: 0)
     return lib

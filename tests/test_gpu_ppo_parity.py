@@ -23,20 +23,26 @@ def _train_cfg(meta, **alg_extra):
                 algorithm=alg)
 
 
-def _make_runner(meta, obs_streams, rewards, dones, time_outs, init_params, log_dir=None, **alg_extra):
+def _make_runner(meta, obs_streams, rewards, dones, time_outs, init_params, log_dir=None, device=DEV, **alg_extra):
     from rsl_rl_b200.env import ReplayVecEnv
     from rsl_rl_b200.runners import OnPolicyRunner
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
     env = ReplayVecEnv({k: t(v) for k, v in obs_streams.items()}, t(rewards), t(dones), t(time_outs),
-                       meta["num_actions"], device=DEV)
-    runner = OnPolicyRunner(env, _train_cfg(meta, **alg_extra), log_dir=log_dir, device=DEV)
-    runner.alg.policy.load_state_dict({k: t(v).to(DEV) for k, v in init_params.items()})
+                       meta["num_actions"], device=device)
+    runner = OnPolicyRunner(env, _train_cfg(meta, **alg_extra), log_dir=log_dir, device=device)
+    runner.alg.policy.load_state_dict({k: t(v).to(device) for k, v in init_params.items()})
     assert runner.alg.fused, runner.alg._engine_reason
     return runner, env
 
 
 @pytest.mark.parametrize("name", ["ppo_mlp_small", "ppo_mlp_groups"])
 def test_learn_iterations_match_reference_golden(name):
+    check_learn_iterations_against_golden(name, DEV)
+
+
+def check_learn_iterations_against_golden(name, DEV, **alg_extra):
+    """The feed-forward PPO path (fused engine) replaying a golden trace of the unmodified reference on device `DEV`
+    (also driven by tests/test_host_logic_engine.py above the emulated ABI)."""
     g = load(name)
     meta = meta_of(g)
     names = meta["param_names"]
@@ -46,7 +52,8 @@ def test_learn_iterations_match_reference_golden(name):
            for k in meta["group_dims"]}
     cat = lambda key: np.concatenate([g[f"it{i}.stream.{key}"] for i in range(iters)])
     init = OrderedDict((k, g[f"init.{k}"]) for k in names)
-    runner, env = _make_runner(meta, obs, cat("rewards"), cat("dones"), cat("time_outs"), init, use_cuda_graph=False)
+    runner, env = _make_runner(meta, obs, cat("rewards"), cat("dones"), cat("time_outs"), init, device=DEV,
+                               use_cuda_graph=False, **alg_extra)
     alg = runner.alg
     for it in range(iters):
         p = f"it{it}."
@@ -99,6 +106,7 @@ def test_learn_iterations_match_reference_golden(name):
         assert abs(alg.learning_rate - float(g[p + "learning_rate"])) < 1e-15
         sd = alg.optimizer.state_dict()
         assert float(sd["state"][0]["step"]) == float(g[p + "adam.step"]) and sd["param_groups"][0]["lr"] == alg.learning_rate
+    return runner
 
 
 def _synthetic_problem(N, T, O_dim, A, hidden, iters, seed):
