@@ -63,7 +63,7 @@ class RandomNetworkDistillation(nn.Module):
         from .. import _native as nat
         import ctypes
 
-        if not state.is_cuda or state.dim() != 2 or os.environ.get("RSLRL_RND_FUSED", "1") == "0":
+        if not nat.on_device(state) or state.dim() != 2 or os.environ.get("RSLRL_RND_FUSED", "1") == "0":
             return None
         plan = getattr(self, "_reward_plan", None)
         if plan is None:

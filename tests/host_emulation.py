@@ -186,19 +186,22 @@ class EmulatedLibrary:
                                use_clipped, dmu16, dmu16_stride, dvalue16, dvalue16_stride, grad_scale16, scale_state,
                                head, stream):
         from oracle import ppo_oracle as O
-        assert rows == mb_orig and not dmu16 and not head, "the emulation covers the fp32-class objective without augmentation"
+        assert not dmu16 and not head, "the emulation covers the fp32-class objective"
         f = np.float32
         m = _view(mu, rows * A).reshape(rows, A)
         std = _view(std_param, A)
         sigma = np.broadcast_to(std if std_type == nat.STD_SCALAR else np.exp(std), (rows, A)).astype(f)
-        a = _view(adv, rows).copy()
+        a = _view(adv, mb_orig).copy()
         if adv_stats:                                       # per-minibatch normalisation (ppo.py:221-223), unbiased std
             s, ss = _view(adv_stats, 2, np.float64)
-            mean = s / rows
-            a = ((a - f(mean)) / (f(math.sqrt(max(ss - rows * mean * mean, 0.0) / (rows - 1))) + f(1e-8))).astype(f)
+            mean = s / mb_orig
+            a = ((a - f(mean)) / (f(math.sqrt(max(ss - mb_orig * mean * mean, 0.0) / (mb_orig - 1))) + f(1e-8))).astype(f)
+        # symmetry augmentation: rows = k * mb_orig, the per-sample scalars repeat (row i reads element i % mb_orig)
+        rep = lambda x: np.tile(x, rows // mb_orig)
         out = O.ppo_loss_fwd_bwd(m, sigma, _view(value, rows), _view(actions, rows * A).reshape(rows, A),
-                                 _view(old_logp, rows), a, _view(returns, rows), _view(old_values, rows), clip_param,
-                                 value_loss_coef, entropy_coef, bool(use_clipped))
+                                 rep(_view(old_logp, mb_orig)), rep(a), rep(_view(returns, mb_orig)),
+                                 rep(_view(old_values, mb_orig)), clip_param, value_loss_coef, entropy_coef,
+                                 bool(use_clipped), n_entropy=mb_orig)
         _mat(dmu, rows, A, dmu_stride)[:] = out["dmu"]
         _mat(dvalue, rows, 1, dvalue_stride)[:] = out["dvalue"]
         dsig = out["dsigma"].sum(0) if std_type == nat.STD_SCALAR else (out["dsigma"] * sigma).sum(0)
@@ -208,12 +211,27 @@ class EmulatedLibrary:
             _view(db_mu, A)[:] += out["dmu"].sum(0)
         if db_value:
             _view(db_value, 1)[:] += out["dvalue"].sum()
-        if kl_out:
-            _view(kl_out, 1)[0] = O.kl_mean(m, sigma, _view(old_mu, rows * A).reshape(rows, A),
-                                            _view(old_sigma, rows * A).reshape(rows, A))
+        if kl_out:                                          # KL over the un-augmented block (ppo.py:255-269)
+            _view(kl_out, 1)[0] = O.kl_mean(m[:mb_orig], sigma[:mb_orig], _view(old_mu, mb_orig * A).reshape(mb_orig, A),
+                                            _view(old_sigma, mb_orig * A).reshape(mb_orig, A))
         if loss_sums:
             _view(loss_sums, 3, np.float64)[:] += (out["surrogate"], out["value_loss"], out["entropy"])
         return self._launch("ppo_loss_fwd_bwd")
+
+    # ---- csrc/rnd.cu: intrinsic reward in one launch
+    def rslrl_rnd_reward(self, target, predictor, x, ldx, n, out, scale, stream):
+        def embed(ref):
+            q = ref._obj
+            h = _mat(x, n, q.dims[0], ldx).astype(np.float32)
+            for l in range(q.num_layers):
+                z = h @ _mat(q.w[l], q.dims[l + 1], q.dims[l], q.dims[l]).T
+                if q.b[l]:
+                    z = z + _view(q.b[l], q.dims[l + 1])
+                h = _act(q.act[l], z.astype(np.float32))
+            return h
+        gap = embed(target) - embed(predictor)
+        _view(out, n)[:] = np.float32(scale) * np.sqrt((gap * gap).sum(1))
+        return self._launch("rnd_reward")
 
     # ---- csrc/gae.cu (arithmetic: the numpy oracle, which is pinned bit-exactly to the reference's golden vectors)
     def rslrl_gae_norm(self, rewards, values, dones, last_values, returns, advantages, workspace, T, N, gamma, lam,
@@ -467,6 +485,7 @@ def install(monkeypatch) -> EmulatedLibrary:
     monkeypatch.setattr(nat, "on_device", lambda t: True)
     monkeypatch.setattr(nat, "require_cuda_device", lambda device, what: None)
     monkeypatch.setattr(nat, "require_device_readable", lambda *tensors: None)
+    monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: False)   # (no CUDA runtime here)
     from rsl_rl_b200.storage import rollout_storage
     monkeypatch.setattr(rollout_storage, "_store_step_fn", None)   # (a cached entry point of whichever library came first)
     monkeypatch.setattr(nat, "stream_ptr", lambda: 0)

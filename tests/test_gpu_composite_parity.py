@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-def _runner_from_golden(g, meta):
+def _runner_from_golden(g, meta, DEV=DEV, **alg_extra):
     from oracle.symmetry_example import mirror_augmentation
     from rsl_rl_b200.env import ReplayVecEnv
     from rsl_rl_b200.runners import OnPolicyRunner
@@ -23,7 +23,7 @@ def _runner_from_golden(g, meta):
            for k in meta["group_dims"]}
     cat = lambda key: t(np.concatenate([g[f"it{i}.stream.{key}"] for i in range(iters)]))
     env = ReplayVecEnv(obs, cat("rewards"), cat("dones"), cat("time_outs"), meta["num_actions"], device=DEV)
-    alg = dict(meta["alg"], class_name="PPO", use_cuda_graph=False)
+    alg = dict(meta["alg"], class_name="PPO", use_cuda_graph=False, **alg_extra)
     if meta["rnd_cfg"] is not None:
         alg["rnd_cfg"] = dict(meta["rnd_cfg"])
     if meta["symmetry"]:
@@ -46,9 +46,15 @@ def _runner_from_golden(g, meta):
 @pytest.mark.parametrize("name", ["ppo_lstm_small", "ppo_rnd_sym_small", "ppo_rnd_norm_small"])
 def test_composite_learn_iterations_match_reference_golden(name):
     torch.backends.cudnn.allow_tf32 = False   # the fp32 parity class
+    check_composite_golden(name, DEV)
+
+
+def check_composite_golden(name, DEV, **alg_extra):
+    """A recurrent / RND / symmetry configuration replaying a golden trace of the unmodified reference on device `DEV`
+    (also driven by tests/test_host_logic_engine.py above the emulated ABI)."""
     g = load(name)
     meta = meta_of(g)
-    runner = _runner_from_golden(g, meta)
+    runner = _runner_from_golden(g, meta, DEV, **alg_extra)
     alg, st = runner.alg, runner.alg.storage
     if name == "ppo_lstm_small":   # the recurrent configuration runs on the engine (native LSTM + fused MLP path), no autograd
         assert alg._recurrent_fused and alg.rollout_fused and not alg.fused
@@ -86,6 +92,7 @@ def test_composite_learn_iterations_match_reference_golden(name):
             for k, v in alg.rnd.state_dict().items():
                 assert rel_err(v.cpu().numpy(), g[p + "final_rnd." + k]) < 5e-5, k
         assert alg.last_update_info["step"] == int(g[p + "adam.step"])
+    return runner
 
 
 def _small_rnd_sym_runner(aug, use_graph):

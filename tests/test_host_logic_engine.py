@@ -22,3 +22,19 @@ def test_fused_engine_host_logic_replays_the_reference_golden(name, precision, m
     assert "store_transition" not in calls      # every rollout row was written in place by act() + the per-step plan
     M, E = alg.num_mini_batches, alg.num_learning_epochs
     assert lib.calls.count("ppo_loss_fwd_bwd") == lib.calls.count("allreduce_clip_adam")   # one loss, one step per minibatch
+
+
+@pytest.mark.parametrize("name", ["ppo_rnd_sym_small", "ppo_rnd_norm_small", "ppo_lstm_small"])
+def test_composite_paths_host_logic_replays_the_reference_golden(name, monkeypatch):
+    """RND + symmetry augmentation + mirror loss, RND with state / reward normalisers (both on the fused engine: one
+    permuted gather per update, loss over k * minibatch rows without a materialised repeat, mirror-loss gradient added to
+    dL/dmu, the RND predictor's MSE under autograd, two fused optimiser steps per minibatch) and the recurrent policy, with
+    the checks of tests/test_gpu_composite_parity.py::check_composite_golden."""
+    from tests import host_emulation
+    from tests.test_gpu_composite_parity import check_composite_golden
+    lib = host_emulation.install(monkeypatch)
+    runner = check_composite_golden(name, "cpu", rng_compat=False)
+    calls = set(lib.calls)
+    if "rnd" in name:
+        assert runner.alg._composite_fusable() and {"rnd_reward", "ppo_loss_fwd_bwd", "permute_gather"} <= calls
+        assert lib.calls.count("allreduce_clip_adam") == 2 * lib.calls.count("ppo_loss_fwd_bwd")   # policy + RND predictor

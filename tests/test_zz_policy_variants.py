@@ -14,7 +14,7 @@ import torch
 from tests.golden_util import load, meta_of, rel_err
 
 
-def _runner_from_golden(g, meta, device):
+def _runner_from_golden(g, meta, device, **alg_extra):
     from rsl_rl_b200.env import ReplayVecEnv
     from rsl_rl_b200.runners import OnPolicyRunner
     T, iters = meta["num_steps"], meta["iterations"]
@@ -27,19 +27,20 @@ def _runner_from_golden(g, meta, device):
                policy=dict(class_name=meta["policy_class"], actor_hidden_dims=list(meta["hidden"]),
                            critic_hidden_dims=list(meta["hidden"]), activation=meta["activation"], init_noise_std=1.0,
                            noise_std_type=meta["noise_std_type"], **meta["policy_extra"]),
-               algorithm=dict(meta["alg"], class_name="PPO", use_cuda_graph=False))
+               algorithm=dict(meta["alg"], class_name="PPO", use_cuda_graph=False, **alg_extra))
     runner = OnPolicyRunner(env, cfg, log_dir=None, device=device)
     sd = {k[len("init."):]: t(g[k]).to(device) for k in g.files if k.startswith("init.")}
     runner.alg.policy.load_state_dict(sd)
     return runner
 
 
-def _check_ppo_variant(name, device):
+def _check_ppo_variant(name, device, general_path=True, **alg_extra):
     g = load(name)
     meta = meta_of(g)
-    runner = _runner_from_golden(g, meta, device)
+    runner = _runner_from_golden(g, meta, device, **alg_extra)
     alg, st = runner.alg, runner.alg.storage
-    assert not alg.fused and not alg.rollout_fused     # the general path: modules + autograd functions on the kernels
+    if general_path:   # modules + autograd functions on the kernels (no fused engine)
+        assert not alg.fused and not alg.rollout_fused
     for it in range(meta["iterations"]):
         p = f"it{it}."
         zq = [torch.from_numpy(z).to(device) for z in g[p + "z_rollout"]]
@@ -103,6 +104,19 @@ def test_lstm_policy_autograd_path_on_the_emulated_abi_reproduces_the_reference_
     lib = host_emulation.install(monkeypatch)
     runner = _check_ppo_variant("ppo_lstm_small", "cpu")
     assert runner.alg.policy.memory_a.native and {"lstm_step_forward", "lstm_step_backward"} <= set(lib.calls)
+
+
+def test_lstm_policy_on_the_fused_engine_host_logic_on_the_emulated_abi(monkeypatch):
+    """The recurrent policy's DEFAULT path (PPO._recurrent_minibatches_fused: LSTM step + engine rollout, per minibatch
+    native LSTM over the padded trajectories, un-pad, engine forward / loss / hand-written backward including the gradient
+    into the LSTM outputs, pad, native BPTT into the flat gradient buffer, fused step; no autograd) above the emulated ABI
+    lands on the reference's golden like the autograd path does."""
+    from tests import host_emulation
+    lib = host_emulation.install(monkeypatch)
+    runner = _check_ppo_variant("ppo_lstm_small", "cpu", general_path=False, rng_compat=False)
+    alg = runner.alg
+    assert alg._recurrent_fused and alg.rollout_fused and not alg.fused
+    assert {"lstm_step_forward", "lstm_step_backward", "unpad", "split_and_pad", "ppo_loss_fwd_bwd", "store_step"} <= set(lib.calls)
 
 
 @pytest.mark.gpu
