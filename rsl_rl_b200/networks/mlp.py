@@ -226,6 +226,21 @@ class MLP(nn.Sequential):
                 nn.init.zeros_(module.bias)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if torch.jit.is_scripting():
+            # export surface (reference users script / trace `policy.actor` for deployment): the module IS an
+            # nn.Sequential of Linear / activation / Unflatten modules, so its TorchScript is the plain layer chain
+            for module in self:
+                x = module(x)
+            return x
+        else:
+            return self._forward_kernels(x)
+
+    @torch.jit.unused
+    def _forward_kernels(self, x: torch.Tensor) -> torch.Tensor:
+        if torch.jit.is_tracing():   # torch.jit.trace / ONNX export record standard operators
+            for module in self:
+                x = module(x)
+            return x
         params = []
         for lin in self.linear_layers():
             params += [lin.weight, lin.bias]

@@ -9,6 +9,8 @@ tensor expression for tensors that need autograd, for tracing / export and for h
 `update()` is a training-path operation and exists on CUDA only."""
 from __future__ import annotations
 
+from typing import Optional
+
 import torch
 from torch import nn
 
@@ -48,8 +50,15 @@ class EmpiricalNormalization(nn.Module):
         x = x.contiguous()
         return x, x.numel() // D, D, D
 
-    def forward(self, x, out: torch.Tensor = None):
+    def forward(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """`out` (optional, [N, >= D] fp32 with unit column stride): write the result there (any row pitch)."""
+        if torch.jit.is_scripting():   # export surface: the reference's expression (normalization.py:44-47)
+            return (x - self._mean) / (self._std + self.eps)
+        else:
+            return self._forward_kernels(x, out)
+
+    @torch.jit.unused
+    def _forward_kernels(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         rows = None if (x.requires_grad and torch.is_grad_enabled()) or torch.jit.is_tracing() else self._rows(x)
         if rows is None:
             y = (x - self._mean) / (self._std + self.eps)

@@ -389,7 +389,7 @@ def _golden_stream(g, meta):
     return obs, cat("rewards"), cat("dones"), cat("time_outs")
 
 
-def _drive_golden(g, meta, runner, iters, on_iter=None):
+def _drive_golden(g, meta, runner, iters, on_iter=None, DEV=DEV):
     alg = runner.alg
     for it in range(iters):
         p = f"it{it}."
@@ -407,11 +407,18 @@ def test_observation_normalisers_match_reference_golden(use_graph):
     """actor/critic_obs_normalization=True (EmpiricalNormalization, reference normalization.py:44-66) over four
     iterations: the running statistics change every env step while act() launch plans and -- with use_graph -- the
     captured update() graph hold the buffers' addresses (eager -> capture -> replay)."""
+    alg = check_normaliser_golden(DEV, use_graph).alg
+    assert (alg._graph is not None) == use_graph
+
+
+def check_normaliser_golden(DEV, use_graph, **alg_extra):
+    """(also driven by tests/test_host_logic_engine.py above the emulated ABI, without graphs)"""
     g = load("ppo_mlp_norm")
     meta = meta_of(g)
     obs, rewards, dones, time_outs = _golden_stream(g, meta)
     init = OrderedDict((k[len("init."):], g[k]) for k in g.files if k.startswith("init."))
-    runner, env = _make_runner(meta, obs, rewards, dones, time_outs, init, use_cuda_graph=use_graph)
+    runner, env = _make_runner(meta, obs, rewards, dones, time_outs, init, device=DEV, use_cuda_graph=use_graph,
+                               **alg_extra)
     alg = runner.alg
     names = meta["param_names"]
 
@@ -428,8 +435,8 @@ def test_observation_normalisers_match_reference_golden(use_graph):
         assert abs(alg.learning_rate - float(g[p + "learning_rate"])) < 1e-15, it
         assert rel_err(mine, g[p + "mb.params_after"][-1]) < 5e-5, it
 
-    _drive_golden(g, meta, runner, meta["iterations"], check)
-    assert (alg._graph is not None) == use_graph
+    _drive_golden(g, meta, runner, meta["iterations"], check, DEV=DEV)
+    return runner
 
 
 def test_logging_path_matches_reference_buffers(tmp_path):

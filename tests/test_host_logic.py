@@ -134,3 +134,63 @@ def test_fp16_storage_has_the_operand_precision_of_tf32():
     S = np.float32(2.0 ** 15)
     g = (rng.standard_normal(1000) * 1e-5).astype(np.float32)
     assert np.array_equal((g * S) / S, g)                                  # scaling by a power of two is exact
+
+
+def test_policy_modules_export_with_torchscript_and_tracing():
+    """Deployment surface: downstream play / export scripts deep-copy `policy.actor` (and the observation
+    normaliser, and `memory_a.rnn` of a recurrent policy), move them to the CPU and `torch.jit.script` or trace them
+    (ONNX export traces).  The kernel-backed modules script / trace to the plain layer chain; calling them eagerly on
+    host tensors still raises (there is no CPU compute path)."""
+    import copy
+
+    import pytest
+    import torch
+
+    from rsl_rl_b200.modules import ActorCritic, ActorCriticRecurrent, StudentTeacher
+    from rsl_rl_b200.utils import TensorDictLite
+
+    obs = TensorDictLite({"policy": torch.randn(4, 10)}, batch_size=[4])
+    groups = {"policy": ["policy"], "critic": ["policy"], "teacher": ["policy"]}
+    torch.manual_seed(0)
+    pol = ActorCritic(obs, groups, 3, actor_hidden_dims=[16, 8], critic_hidden_dims=[16, 8], actor_obs_normalization=True)
+    with torch.no_grad():
+        pol.actor_obs_normalizer._mean.normal_()
+        pol.actor_obs_normalizer._std.uniform_(0.5, 2.0)
+
+    class Exporter(torch.nn.Module):   # the shape of Isaac Lab's _TorchPolicyExporter
+        def __init__(self, actor, normalizer):
+            super().__init__()
+            self.actor = copy.deepcopy(actor)
+            self.normalizer = copy.deepcopy(normalizer)
+
+        def forward(self, x):
+            return self.actor(self.normalizer(x))
+
+    x = torch.randn(5, 10)
+    nrm = pol.actor_obs_normalizer
+
+    def plain(mlp, inp):   # (iterating the Sequential, not .children(): one activation module serves every layer)
+        for m in mlp:
+            inp = m(inp)
+        return inp
+
+    want = plain(pol.actor, (x - nrm._mean) / (nrm._std + nrm.eps))
+    exporter = Exporter(pol.actor, nrm).to("cpu")
+    scripted = torch.jit.script(exporter)
+    assert torch.equal(scripted(x), want)
+    traced = torch.jit.trace(exporter, x, check_trace=False)   # (the check would re-run the module eagerly on the host)
+    assert torch.equal(traced(x), want)
+    with pytest.raises(RuntimeError, match="no CPU"):
+        exporter(x)
+
+    # a state-dependent std head (Unflatten at the end) and a student network export the same way
+    sd = ActorCritic(obs, groups, 3, actor_hidden_dims=[8], critic_hidden_dims=[8], state_dependent_std=True)
+    assert torch.jit.script(copy.deepcopy(sd.actor))(x).shape == (5, 2, 3)
+    st = StudentTeacher(obs, groups, 3, student_hidden_dims=[8], teacher_hidden_dims=[8])
+    assert torch.equal(torch.jit.script(copy.deepcopy(st.student))(x), plain(st.student, x))
+    # recurrent policy: the memory's parameter container is a stock nn.LSTM
+    rec = ActorCriticRecurrent(obs, groups, 3, actor_hidden_dims=[8], critic_hidden_dims=[8], rnn_hidden_dim=12)
+    rnn = copy.deepcopy(rec.memory_a.rnn)
+    assert type(rnn) is torch.nn.LSTM
+    out, _ = rnn(x.unsqueeze(0))
+    assert torch.equal(torch.jit.script(copy.deepcopy(rec.actor))(out.squeeze(0)), plain(rec.actor, out.squeeze(0)))

@@ -38,3 +38,14 @@ def test_composite_paths_host_logic_replays_the_reference_golden(name, monkeypat
     if "rnd" in name:
         assert runner.alg._composite_fusable() and {"rnd_reward", "ppo_loss_fwd_bwd", "permute_gather"} <= calls
         assert lib.calls.count("allreduce_clip_adam") == 2 * lib.calls.count("ppo_loss_fwd_bwd")   # policy + RND predictor
+
+
+def test_observation_normalisers_on_the_engine_path_replay_the_reference_golden(monkeypatch):
+    """actor / critic observation normalisers over four iterations: the running statistics change every env step while the
+    rollout launch plans hold the buffers' addresses; the update normalises the gathered minibatch observations straight
+    into the padded input buffers (`normalizer(x, out=...)`)."""
+    from tests import host_emulation
+    from tests.test_gpu_ppo_parity import check_normaliser_golden
+    lib = host_emulation.install(monkeypatch)
+    runner = check_normaliser_golden("cpu", False, rng_compat=False)
+    assert runner.alg.fused and {"empirical_norm_update", "empirical_normalize"} <= set(lib.calls)
