@@ -478,6 +478,49 @@ class EmulatedLibrary:
         return self._launch("allreduce_clip_adam")
 
 
+def _two_launch_optimiser(cls):
+    """csrc/optim.cu: the NCCL-path optimiser step as two launches (norm / clip scale / KL rule, then Adam)."""
+
+    def rslrl_grad_norm_lr(self, g, P, kl_sum, state, workspace, world_size, max_grad_norm, adaptive, desired_kl,
+                           round_lr_fp32, beta1, beta2, stream):
+        st = ctypes.cast(int(state), ctypes.POINTER(nat.OptState)).contents
+        w = float(world_size)
+        norm = math.sqrt(float(np.sum(_view(g, P).astype(np.float64) ** 2))) / w      # || mean over ranks of g ||
+        coef = min(max_grad_norm / (norm + 1e-6), 1.0) if max_grad_norm > 0 else 1.0
+        lr = st.lr
+        if adaptive:
+            kl = np.float32(_view(kl_sum, 1)[0] / np.float32(w)) if kl_sum else np.float32(0)
+            if kl > np.float32(desired_kl * 2.0):
+                lr = max(1e-5, lr / 1.5)
+            elif np.float32(0) < kl < np.float32(desired_kl / 2.0):
+                lr = min(1e-2, lr * 1.5)
+            if round_lr_fp32:
+                lr = float(np.float32(lr))
+            st.kl_mean = float(kl)
+        t = st.step + 1
+        bc1, bc2 = 1.0 - beta1 ** t, 1.0 - beta2 ** t
+        st.lr, st.clip_scale, st.total_norm, st.step_size, st.bc2_sqrt, st.step = lr, coef / w, norm, lr / bc1, math.sqrt(bc2), t
+        return self._launch("grad_norm_lr")
+
+    def rslrl_adam_step(self, p, g, m, v, P, state, beta1, beta2, eps, zero_grad, stream):
+        st = ctypes.cast(int(state), ctypes.POINTER(nat.OptState)).contents
+        f = np.float32
+        pp, gg, mm, vv = _view(p, P), _view(g, P), _view(m, P), _view(v, P)
+        gc = gg * f(st.clip_scale)
+        mm[:] = mm + (gc - mm) * f(1.0 - beta1)
+        vv[:] = vv * f(beta2) + f(1.0 - beta2) * gc * gc
+        pp[:] = pp + f(-st.step_size) * (mm / (np.sqrt(vv) / f(st.bc2_sqrt) + f(eps)))
+        if zero_grad:
+            gg[:] = 0
+        return self._launch("adam_step")
+
+    cls.rslrl_grad_norm_lr, cls.rslrl_adam_step = rslrl_grad_norm_lr, rslrl_adam_step
+    return cls
+
+
+_two_launch_optimiser(EmulatedLibrary)
+
+
 def install(monkeypatch) -> EmulatedLibrary:
     """Routes `rsl_rl_b200._native` to the emulation for the duration of one test (pytest's monkeypatch undoes it)."""
     lib = EmulatedLibrary()

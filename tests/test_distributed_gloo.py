@@ -142,3 +142,88 @@ def test_two_rank_distillation_equals_one_rank_on_all_envs(tmp_path, monkeypatch
     single, loss = _distill_run(0, 1, 16, seed=100)     # rank 0's initial weights, all 32 envs
     assert np.abs(a[:-1] - single).max() < 2e-6 * np.abs(single).max()
     assert abs(0.5 * (a[-1] + b[-1]) - loss) < 1e-6 * max(1.0, abs(loss))   # mean of the ranks' losses = loss on the union
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# PPO.update on two ranks, NCCL-path host logic (reference ppo.py:272-290, 428-469) against the oracle's world hook
+# ---------------------------------------------------------------------------------------------------------------------
+
+def _ppo_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RSLRL_ALLREDUCE="nccl")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tests import host_emulation
+    host_emulation.install(_Setattr())
+    from oracle import ppo_oracle as O
+    from rsl_rl_b200.algorithms import PPO
+    from rsl_rl_b200.modules import ActorCritic
+    from rsl_rl_b200.utils import TensorDictLite
+
+    N, T, D, A, hidden = 48, 6, 10, 3, [24, 12]
+    cfg = dict(learning_rate=1e-3, num_learning_epochs=2, num_mini_batches=3, schedule="adaptive", value_loss_coef=1.0,
+               clip_param=0.2, use_clipped_value_loss=True, desired_kl=0.01, entropy_coef=0.01, gamma=0.99, lam=0.95,
+               max_grad_norm=0.5)
+    rng = np.random.default_rng(50 + rank)                       # every rank owns its own envs, noise and permutation
+    f = lambda *s: rng.standard_normal(s).astype(np.float32)
+    obs, rewards, z = f(T + 1, N, D), f(T, N), f(T, N, A)
+    dones = (rng.random((T, N)) < 0.1).astype(np.int64)
+    time_outs = (rng.random((T, N)) < 0.5) & (dones > 0)
+    perm = rng.permutation(N * T).astype(np.int64)
+    td = lambda t: TensorDictLite({"policy": torch.from_numpy(obs[t])}, batch_size=[N])
+
+    torch.manual_seed(200 + rank)                                # different initial weights before the broadcast
+    policy = ActorCritic(td(0), {"policy": ["policy"], "critic": ["policy"]}, A, actor_hidden_dims=hidden,
+                         critic_hidden_dims=hidden, activation="elu")
+    alg = PPO(policy, device="cpu", multi_gpu_cfg=dict(global_rank=rank, world_size=world), gemm_precision="fp32",
+              use_cuda_graph=False, rng_compat=False, **cfg)
+    assert not alg.optimizer.peer_allreduce                      # the NCCL path: in-place all-reduce + two launches
+    alg.init_storage("rl", N, T, td(0), [A])
+    alg.broadcast_parameters()
+    init = OrderedDict((k, v.detach().numpy().copy()) for k, v in policy.named_parameters())
+    zq = [torch.from_numpy(z[t]) for t in range(T)]
+    policy._noise_fn = lambda like: zq.pop(0)
+    alg.storage._randperm = lambda n: torch.from_numpy(perm)
+    with torch.inference_mode():
+        for t in range(T):
+            alg.act(td(t))
+            alg.process_env_step(td(t + 1), torch.from_numpy(rewards[t]), torch.from_numpy(dones[t]),
+                                 {"time_outs": torch.from_numpy(time_outs[t])})
+        alg.compute_returns(td(T))
+    alg.update()
+    mine = np.concatenate([p.detach().numpy().reshape(-1) for p in policy.parameters()])
+
+    # the oracle on this rank's rollout, gradients and KL averaged over the ranks where the reference does it
+    def world_hook(grads, kl):
+        flat = torch.from_numpy(np.concatenate([g.reshape(-1) for g in grads.values()] + [[np.float32(kl)]]))
+        dist.all_reduce(flat)
+        flat = (flat / world).numpy()
+        out, off = OrderedDict(), 0
+        for k, g in grads.items():
+            out[k] = flat[off:off + g.size].reshape(g.shape).astype(np.float32)
+            off += g.size
+        return out, float(flat[-1])
+
+    ocfg = dict(cfg, activation="elu", noise_std_type="scalar")
+    params = OrderedDict((k, v.copy()) for k, v in init.items())
+    st, last_values = O.rollout(params, obs, obs, rewards, dones, time_outs, z, ocfg)
+    st["returns"], st["advantages"] = O.compute_returns(st["rewards"], st["values"], st["dones"], last_values, 0.99, 0.95)
+    _, lr, trace = O.update(params, O.adam_init(params), 1e-3, st, perm, ocfg, world_hook=world_hook)
+    want = np.concatenate([v.reshape(-1) for v in params.values()])
+    err = float(np.abs(mine - want).max() / np.abs(want).max())
+    np.save(os.path.join(out_dir, f"ppo_rank{rank}.npy"), np.concatenate([mine, [alg.learning_rate, lr, err]]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_ppo_update_matches_the_oracle_on_rank_averaged_gradients(tmp_path):
+    """PPO.update with `multi_gpu_cfg` on two gloo ranks above the emulated ABI: per minibatch ONE in-place all-reduce of
+    [gradients | KL], then norm / clip / KL-adaptive LR (fp32-rounded, as the reference's broadcast makes it) / Adam on
+    the rank-averaged values.  Every rank keeps its own envs, advantage statistics and permutation.  Checked:
+    replicas bit-identical, same LR, and each rank equal to the numpy oracle run on its own rollout with the world hook."""
+    port = 29700 + os.getpid() % 150
+    mp.spawn(_ppo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a, b = np.load(tmp_path / "ppo_rank0.npy"), np.load(tmp_path / "ppo_rank1.npy")
+    assert np.array_equal(a[:-3], b[:-3]) and a[-3] == b[-3], "replicas disagree after update()"
+    for r in (a, b):
+        assert r[-1] < 1e-5, r[-1]                                  # product vs oracle, max-abs / max-abs
+        assert abs(r[-3] / r[-2] - 1.0) < 1e-6 and r[-3] != 1e-3    # same LR trajectory (the rule fired at least once)
