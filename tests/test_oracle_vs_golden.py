@@ -117,3 +117,43 @@ def test_torch_cpu_port_matches_numpy_oracle():
     a = np.concatenate([v.numpy().reshape(-1) for v in params.values()])
     b = np.concatenate([v.reshape(-1) for v in np_params.values()])
     assert rel_err(a, b) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["distill_mlp_small", "distill_mlp_adamw"])
+def test_distillation_oracle_matches_reference(name):
+    """oracle/distill_oracle.py (feed-forward student: rollout with both normalisers, windows of `gradient_length` steps
+    that carry across the epoch boundary, student-only clipping, Adam / AdamW) against the reference's recorded trace:
+    rollout buffer, the student's parameters after EVERY optimiser step, the reported loss, the normaliser statistics."""
+    from oracle import distill_oracle as D
+    g = load(name)
+    meta = meta_of(g)
+    cfg = dict(meta["alg"], activation=meta["activation"])
+    state = {k[len("init."):]: g[k].copy() for k in g.files if k.startswith("init.")}
+    student = [k for k in meta["param_names"] if k.startswith("student.")]
+    adam = O.adam_init({k: state[k] for k in student})
+    step = None
+    if cfg["optimizer"] == "adamw":
+        step = lambda params, grads: D.adamw_step(params, grads, adam, cfg["learning_rate"])
+    # where the student sits inside the reference's flat parameter trace (policy.parameters() order)
+    sizes = [int(np.prod(g["init." + k].shape)) for k in meta["param_names"]]
+    first = sum(s for k, s in zip(meta["param_names"], sizes) if meta["param_names"].index(k) < meta["param_names"].index(student[0]))
+    span = slice(first, first + sum(s for k, s in zip(meta["param_names"], sizes) if k in student))
+    cat = lambda p, groups: np.concatenate([g[f"{p}stream.obs.{k}"] for k in groups], axis=-1)
+    parts = [f"it{i}." for i in range(meta["iterations"])] + (["resume."] if "resume.z_rollout" in g.files else [])
+    for p in parts:
+        st = D.rollout(state, cat(p, meta["obs_groups"]["policy"]), cat(p, meta["obs_groups"]["teacher"]), g[p + "z_rollout"],
+                       g[p + "stream.rewards"], g[p + "stream.dones"], cfg)
+        assert rel_err(st["actions"], g[p + "storage.actions"]) < 1e-5
+        assert rel_err(st["privileged_actions"], g[p + "storage.privileged_actions"]) < 1e-5
+        assert np.array_equal(st["dones"], g[p + "storage.dones"]) and np.array_equal(st["rewards"], g[p + "storage.rewards"])
+        loss, trace = D.update(state, adam, st, cfg, optimizer_step=step)
+        ref = g[p + "mb.params_after"]
+        assert len(trace) == len(ref)
+        for i, (mine, want) in enumerate(zip(trace, ref)):
+            assert rel_err(mine, want[span]) < 1e-5, (p, i)
+        assert abs(loss - float(g[p + "loss.behavior"])) < 1e-6 * max(1.0, abs(loss))
+        for k in state:
+            if "normalizer" in k and not k.endswith("count"):
+                assert rel_err(np.asarray(state[k]).reshape(-1), g[p + "final." + k].reshape(-1)) < 1e-5, k
+    if "mb.total_norm" in " ".join(g.files):   # the clip saw the student's gradient only
+        assert g["it0.mb.raw_grads"].shape[1] == span.stop - span.start
