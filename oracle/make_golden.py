@@ -182,11 +182,13 @@ def scenario_ppo_mlp(out_dir, name, *, num_envs, num_steps, group_dims, obs_grou
     alg_run = dict(alg)
     if rnd_cfg is not None:
         alg_run["rnd_cfg"] = dict(rnd_cfg)
+    symmetry_flags = dict(use_data_augmentation=True, use_mirror_loss=True, mirror_loss_coeff=0.5)
+    if isinstance(symmetry, dict):   # other combinations of the two switches (ppo.py:226-244, 318-348)
+        symmetry_flags.update(symmetry)
     if symmetry:
         sys.path.insert(0, os.path.join(HERE, ".."))
         from oracle.symmetry_example import mirror_augmentation
-        alg_run["symmetry_cfg"] = dict(use_data_augmentation=True, use_mirror_loss=True, mirror_loss_coeff=0.5,
-                                       data_augmentation_func=mirror_augmentation)
+        alg_run["symmetry_cfg"] = dict(symmetry_flags, data_augmentation_func=mirror_augmentation)
     cfg = dict(num_steps_per_env=num_steps, save_interval=10 ** 9, obs_groups={k: list(v) for k, v in obs_groups.items()},
                policy=dict(class_name=policy_class, actor_hidden_dims=list(hidden), critic_hidden_dims=list(hidden),
                            activation=activation, init_noise_std=1.0, noise_std_type=noise_std_type,
@@ -198,7 +200,7 @@ def scenario_ppo_mlp(out_dir, name, *, num_envs, num_steps, group_dims, obs_grou
                 obs_groups={k: list(v) for k, v in obs_groups.items()}, group_dims=dict(group_dims),
                 alg={k: v for k, v in alg.items() if k != "class_name"}, policy_class=policy_class,
                 policy_extra=dict(policy_extra or {}), rnd_cfg=None if rnd_cfg is None else dict(rnd_cfg),
-                symmetry=bool(symmetry))
+                symmetry=bool(symmetry), symmetry_cfg=dict(symmetry_flags))
     with Recorder() as rec:
         runner = OnPolicyRunner(env, cfg, log_dir=tempfile.mkdtemp(prefix="golden_"), device="cpu")
         rec.watch_optimizer(runner.alg.optimizer, runner.alg.policy)
@@ -367,7 +369,9 @@ def scenario_distillation(out_dir, name, *, num_envs, num_steps, group_dims, obs
                 data[p + "mb.raw_grads"] = np.stack([c[0] for c in clips])     # student MLP gradients only
                 data[p + "mb.total_norm"] = np.array([c[1] for c in clips])
             data[p + "mb.lr"] = np.array([s[0] for s in steps])
-            data[p + "mb.params_after"] = np.stack([s[1] for s in steps])
+            n_params = sum(q.numel() for q in runner.alg.policy.parameters())
+            data[p + "mb.params_after"] = (np.stack([s[1] for s in steps]) if steps   # (no optimiser step when the
+                                           else np.zeros((0, n_params), np.float32))   #  window is longer than the update)
             data[p + "loss.behavior"] = np.array(losses[-1]["behavior"], dtype=np.float64)
             for k, v in _state_arrays(runner.alg.policy).items():
                 data[p + f"final.{k}"] = v

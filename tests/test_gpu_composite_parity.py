@@ -27,8 +27,8 @@ def _runner_from_golden(g, meta, DEV=DEV, **alg_extra):
     if meta["rnd_cfg"] is not None:
         alg["rnd_cfg"] = dict(meta["rnd_cfg"])
     if meta["symmetry"]:
-        alg["symmetry_cfg"] = dict(use_data_augmentation=True, use_mirror_loss=True, mirror_loss_coeff=0.5,
-                                   data_augmentation_func=mirror_augmentation)
+        flags = meta.get("symmetry_cfg", dict(use_data_augmentation=True, use_mirror_loss=True, mirror_loss_coeff=0.5))
+        alg["symmetry_cfg"] = dict(flags, data_augmentation_func=mirror_augmentation)
     cfg = dict(num_steps_per_env=T, save_interval=10 ** 9, obs_groups={k: list(v) for k, v in meta["obs_groups"].items()},
                policy=dict(class_name=meta["policy_class"], actor_hidden_dims=list(meta["hidden"]),
                            critic_hidden_dims=list(meta["hidden"]), activation=meta["activation"], init_noise_std=1.0,
