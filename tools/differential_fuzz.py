@@ -10,7 +10,7 @@ wiring, autograd wiring and configuration handling -- not the kernels (those are
 
     python tools/differential_fuzz.py [--ref /root/reference] [--only NAME ...]
 
-Matrix (47 runs): PPO feed-forward engine: 6 activations, per-minibatch advantage normalisation, fixed schedule, no KL
+Matrix: PPO feed-forward engine: 6 activations, per-minibatch advantage normalisation, fixed schedule, no KL
 target, env / minibatch counts that do not divide, observation groups, log-std + unclipped value loss, 1 and 4 hidden
 layers; recurrent: 2-layer LSTM (engine), 2-layer GRU (general path), LSTM + normalisers; RND / symmetry: every
 combination of the two symmetry switches, RND alone, step / linear weight schedules, reward normaliser, wide embedding
@@ -52,6 +52,11 @@ PPO_CASES = {
     "four_hidden_layers": dict(hidden=[32, 24, 16, 8]),
     "lstm_two_layers": dict(REC, policy_extra=dict(rnn_type="lstm", rnn_hidden_dim=12, rnn_num_layers=2)),
     "gru_two_layers": dict(REC, policy_extra=dict(rnn_type="gru", rnn_hidden_dim=12, rnn_num_layers=2)),
+    "state_dependent_std_lstm": dict(REC, noise_std_type="log", general=True,
+                                     policy_extra=dict(rnn_type="lstm", rnn_hidden_dim=12, state_dependent_std=True)),
+    "state_dependent_std_groups_relu": dict(activation="relu", general=True, policy_extra=dict(state_dependent_std=True),
+                                            group_dims={"policy": 7, "extra": 3},
+                                            obs_groups={"policy": ["policy", "extra"], "critic": ["policy"]}),
     "lstm_normalisers": dict(REC, policy_extra=dict(rnn_type="lstm", rnn_hidden_dim=12, rnn_num_layers=1,
                                                     actor_obs_normalization=True, critic_obs_normalization=True)),
 }
@@ -121,9 +126,11 @@ def main():
     from tests.test_gpu_ppo_parity import check_learn_iterations_against_golden
 
     def ppo(name, over, seed):
+        over = dict(over)
+        general = over.pop("general", False)     # configurations the engines do not take: modules + autograd functions
         mg.scenario_ppo_mlp(out, name, seed=seed, **dict(PPO_BASE, **over))
         host_emulation.install(_Setattr())
-        if "policy_class" in over:
+        if "policy_class" in over or general:
             r = test_zz_policy_variants._check_ppo_variant(name, "cpu", general_path=False, rng_compat=False)
         else:
             r = check_learn_iterations_against_golden(name, "cpu", rng_compat=False)
