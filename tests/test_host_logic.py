@@ -194,3 +194,79 @@ def test_policy_modules_export_with_torchscript_and_tracing():
     assert type(rnn) is torch.nn.LSTM
     out, _ = rnn(x.unsqueeze(0))
     assert torch.equal(torch.jit.script(copy.deepcopy(rec.actor))(out.squeeze(0)), plain(rec.actor, out.squeeze(0)))
+
+
+def test_error_behaviour_of_the_reference_surface(monkeypatch, tmp_path):
+    """SURVEY 8(b) "Errors": the exceptions a caller of the reference can rely on -- buffer overflow, generators of the
+    wrong training type, missing hidden states in batch mode, unknown noise parametrisation, a non-callable augmentation
+    function, a device that does not match the local rank, an unknown logger, `forward()` of the policy classes."""
+    import pytest
+    import torch
+
+    from tests import host_emulation
+    host_emulation.install(monkeypatch)
+    from rsl_rl_b200.algorithms import PPO
+    from rsl_rl_b200.env import ReplayVecEnv
+    from rsl_rl_b200.modules import ActorCritic, ActorCriticRecurrent, StudentTeacher
+    from rsl_rl_b200.networks import Memory
+    from rsl_rl_b200.runners import OnPolicyRunner
+    from rsl_rl_b200.storage import RolloutStorage
+    from rsl_rl_b200.utils import TensorDictLite
+
+    N, A = 8, 2
+    obs = TensorDictLite({"policy": torch.randn(N, 5)}, batch_size=[N])
+    groups = {"policy": ["policy"], "critic": ["policy"], "teacher": ["policy"]}
+    for cls in (ActorCritic, ActorCriticRecurrent, StudentTeacher):
+        with pytest.raises(ValueError, match="Unknown standard deviation type"):
+            cls(obs, groups, A, noise_std_type="softplus")
+    with pytest.raises(ValueError, match="Unknown standard deviation type"):
+        ActorCritic(obs, groups, A, noise_std_type="softplus", state_dependent_std=True)
+    policy = ActorCritic(obs, groups, A, actor_hidden_dims=[8], critic_hidden_dims=[8])
+    with pytest.raises(NotImplementedError):
+        policy.forward()
+    with pytest.raises(NotImplementedError):
+        ActorCriticRecurrent(obs, groups, A, actor_hidden_dims=[8], critic_hidden_dims=[8], rnn_hidden_dim=8).forward()
+    with pytest.raises(AssertionError, match="only supports 1D observations"):
+        ActorCritic(TensorDictLite({"policy": torch.zeros(N, 3, 3)}, batch_size=[N]), groups, A)
+    with pytest.raises(ValueError, match="Hidden states not passed"):
+        Memory(5, hidden_size=8)(torch.zeros(3, N, 5), masks=torch.ones(3, N, dtype=torch.bool), hidden_states=None)
+    with pytest.raises(ValueError, match="not callable"):
+        PPO(policy, device="cpu", symmetry_cfg=dict(use_data_augmentation=True, use_mirror_loss=False,
+                                                    data_augmentation_func=42))
+
+    st = RolloutStorage("rl", N, 1, obs, [A], "cpu")
+    alg = PPO(policy, device="cpu", use_cuda_graph=False, rng_compat=False, gemm_precision="fp32")
+    alg.init_storage("rl", N, 1, obs, [A])
+    with torch.inference_mode():
+        alg.act(obs)
+        alg.process_env_step(obs, torch.zeros(N), torch.zeros(N, dtype=torch.long), {})
+        with pytest.raises(OverflowError, match="Rollout buffer overflow"):
+            alg.act(obs)
+    with pytest.raises(ValueError, match="only available for distillation"):
+        next(st.generator())
+    with pytest.raises(ValueError, match="gemm_precision must be one of"):
+        PPO(policy, device="cpu", gemm_precision="bf16")
+
+    env = ReplayVecEnv({"policy": torch.zeros(2, N, 5)}, torch.zeros(1, N), torch.zeros(1, N, dtype=torch.long), None, A,
+                       device="cpu")
+    cfg = lambda **extra: dict(dict(num_steps_per_env=1, save_interval=1, obs_groups={"policy": ["policy"]},
+                                    policy=dict(class_name="ActorCritic", actor_hidden_dims=[8], critic_hidden_dims=[8]),
+                                    algorithm=dict(class_name="PPO", use_cuda_graph=False, rng_compat=False)), **extra)
+    with pytest.raises(ValueError, match="Logger type not found"):
+        OnPolicyRunner(env, cfg(logger="csv"), log_dir=str(tmp_path), device="cpu").learn(1)
+    with pytest.raises(NotImplementedError, match="W&B"):
+        OnPolicyRunner(env, cfg(logger="wandb"), log_dir=str(tmp_path), device="cpu").learn(1)
+    with pytest.raises(ValueError, match="Unknown class_name"):
+        OnPolicyRunner(env, cfg(policy=dict(class_name="Transformer")), device="cpu")
+    with pytest.raises(ValueError, match="must contain the 'policy' key"):
+        bad = ReplayVecEnv({"proprio": torch.zeros(2, N, 5)}, torch.zeros(1, N), torch.zeros(1, N), None, A, device="cpu")
+        OnPolicyRunner(bad, cfg(obs_groups={}), device="cpu")
+    # torchrun-style environment whose device does not match the local rank (reference on_policy_runner.py:378-390)
+    monkeypatch.setenv("WORLD_SIZE", "2")
+    monkeypatch.setenv("RANK", "1")
+    monkeypatch.setenv("LOCAL_RANK", "1")
+    with pytest.raises(ValueError, match="does not match expected device for local rank"):
+        OnPolicyRunner(env, cfg(), device="cuda:0")
+    monkeypatch.setenv("LOCAL_RANK", "3")
+    with pytest.raises(ValueError, match="greater than or equal to world size"):
+        OnPolicyRunner(env, cfg(), device="cuda:3")
