@@ -65,9 +65,10 @@ class GaussianHeadMixin:
     def entropy(self):
         return (_ENTROPY_CONST + torch.log(self._std)).sum(dim=-1)
 
-    def update_distribution(self, features):
+    def update_distribution(self, obs):
+        """`obs`: the (normalised, concatenated) network input -- the reference's parameter name (actor_critic.py:119)."""
         if self.state_dependent_std:
-            mean_and_std = self.actor(features)
+            mean_and_std = self.actor(obs)
             if self.noise_std_type == "scalar":
                 mean, std = torch.unbind(mean_and_std, dim=-2)
             elif self.noise_std_type == "log":
@@ -76,7 +77,7 @@ class GaussianHeadMixin:
             else:
                 raise ValueError(f"Unknown standard deviation type: {self.noise_std_type}. Should be 'scalar' or 'log'")
         else:
-            mean = self.actor(features)
+            mean = self.actor(obs)
             if self.noise_std_type == "scalar":
                 std = self.std.expand_as(mean)
             elif self.noise_std_type == "log":

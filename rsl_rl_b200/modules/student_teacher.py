@@ -59,8 +59,8 @@ class _StudentTeacherBase(nn.Module):
     def entropy(self):
         return self.distribution.entropy().sum(dim=-1)
 
-    def update_distribution(self, features):
-        self.set_distribution(self.student(features))
+    def update_distribution(self, obs):
+        self.set_distribution(self.student(obs))
 
     def set_distribution(self, mean):
         """The action distribution around a student output `mean` computed elsewhere (Distillation's grouped rollout)."""

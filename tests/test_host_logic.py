@@ -270,3 +270,59 @@ def test_error_behaviour_of_the_reference_surface(monkeypatch, tmp_path):
     monkeypatch.setenv("LOCAL_RANK", "3")
     with pytest.raises(ValueError, match="greater than or equal to world size"):
         OnPolicyRunner(env, cfg(), device="cuda:3")
+
+
+def test_public_api_surface_matches_the_reference_snapshot():
+    """The drop-in boundary: every public class / function of the reference's sub-packages exists here under
+    the same name, and every method of its surface takes the reference's parameters -- same names, same order, same
+    defaults (extra parameters here must be optional).  tests/golden/reference_api.json was recorded from the unmodified
+    reference by oracle/make_api_snapshot.py."""
+    import importlib
+    import inspect
+    import json
+    import os
+
+    from tests.golden_util import GOLDEN
+
+    snap = json.load(open(os.path.join(GOLDEN, "reference_api.json")))
+    assert sum(len(v) for v in snap.values()) >= 24
+
+    def sig(fn):
+        return [[p.name, p.kind.name, None if p.default is inspect.Parameter.empty else repr(p.default)]
+                for p in inspect.signature(fn).parameters.values()]
+
+    problems = []
+
+    def compare(where, ref, mine):
+        fixed = [r for r in ref if r[1] not in ("VAR_KEYWORD", "VAR_POSITIONAL")]
+        for r in ref:
+            if r[1] in ("VAR_KEYWORD", "VAR_POSITIONAL") and not any(m[1] == r[1] for m in mine):
+                problems.append(f"{where}: no {r[1]} parameter")
+        for i, r in enumerate(fixed):
+            if i >= len(mine) or mine[i][0] != r[0]:
+                problems.append(f"{where}: parameter {i} is {mine[i][0] if i < len(mine) else None!r}, reference {r[0]!r}")
+            elif mine[i][2] != r[2]:
+                problems.append(f"{where}: default of {r[0]!r} is {mine[i][2]}, reference {r[2]}")
+        for m in mine[len(fixed):]:
+            if m[1] not in ("VAR_KEYWORD", "VAR_POSITIONAL") and m[2] is None:
+                problems.append(f"{where}: extra required parameter {m[0]!r}")
+
+    def walk(prefix, cls, members):
+        for name, m in members.items():
+            if not hasattr(cls, name):
+                problems.append(f"{prefix}.{name}: missing")
+            elif isinstance(m, dict):
+                walk(f"{prefix}.{name}", getattr(cls, name), m["members"])
+            elif isinstance(m, list):
+                compare(f"{prefix}.{name}", m, sig(getattr(cls, name)))
+
+    for pkg, entries in snap.items():
+        mod = importlib.import_module(f"rsl_rl_b200.{pkg}")
+        for name, d in entries.items():
+            if not hasattr(mod, name):
+                problems.append(f"{pkg}.{name}: missing")
+            elif d["kind"] == "function":
+                compare(f"{pkg}.{name}", d["signature"], sig(getattr(mod, name)))
+            else:
+                walk(f"{pkg}.{name}", getattr(mod, name), d["members"])
+    assert not problems, "\n".join(problems)
