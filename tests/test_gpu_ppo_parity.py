@@ -442,11 +442,17 @@ def check_normaliser_golden(DEV, use_graph, **alg_extra):
 def test_logging_path_matches_reference_buffers(tmp_path):
     """log_dir set: the device-side episode statistics, flushed once per iteration, reproduce the
     reference's rewbuffer / lenbuffer contents (on_policy_runner.py:113-139) and the logged mean losses."""
+    check_logging_path(DEV, tmp_path)
+
+
+def check_logging_path(DEV, tmp_path, **alg_extra):
+    """(also driven by tests/test_host_logic_engine.py above the emulated ABI)"""
     g = load("ppo_mlp_small")
     meta = meta_of(g)
     obs, rewards, dones, time_outs = _golden_stream(g, meta)
     init = OrderedDict((k, g[f"init.{k}"]) for k in meta["param_names"])
-    runner, env = _make_runner(meta, obs, rewards, dones, time_outs, init, log_dir=str(tmp_path), use_cuda_graph=False)
+    runner, env = _make_runner(meta, obs, rewards, dones, time_outs, init, log_dir=str(tmp_path), device=DEV,
+                               use_cuda_graph=False, **alg_extra)
     seen = []
     orig_log = runner.log
 
@@ -467,7 +473,7 @@ def test_logging_path_matches_reference_buffers(tmp_path):
             ref = float(g[p + "log.loss." + k])
             assert abs(seen[-1]["loss"][k] - ref) < 1e-4 * max(1.0, abs(ref)), (it, k)
 
-    _drive_golden(g, meta, runner, meta["iterations"], check)
+    _drive_golden(g, meta, runner, meta["iterations"], check, DEV=DEV)
     import os
     assert any(f.startswith("events.out.tfevents") for f in os.listdir(tmp_path)), "no TensorBoard event file written"
     assert any(f.startswith("model_") for f in os.listdir(tmp_path)), "no checkpoint written at the end of learn()"
@@ -478,13 +484,19 @@ def test_reference_checkpoint_round_trip(tmp_path):
     oracle/make_golden.py after four iterations, on_policy_runner.py:289-305) loads into this runner (parameters,
     normaliser buffers, Adam moments / step / lr, iteration counter), training resumes from it, and a checkpoint written
     here has the reference's structure (and loads into the reference when its install travelled with the repo)."""
+    check_reference_checkpoint_round_trip(DEV, tmp_path)
+
+
+def check_reference_checkpoint_round_trip(DEV, tmp_path, **alg_extra):
+    """(also driven by tests/test_host_logic_engine.py above the emulated ABI)"""
     import os
     from tests.golden_util import GOLDEN
     g = load("ppo_mlp_norm")
     meta = meta_of(g)
     obs, rewards, dones, time_outs = _golden_stream(g, meta)
     init = OrderedDict((k[len("init."):], g[k]) for k in g.files if k.startswith("init."))
-    runner, env = _make_runner(meta, obs, rewards, dones, time_outs, init, log_dir=str(tmp_path), use_cuda_graph=False)
+    runner, env = _make_runner(meta, obs, rewards, dones, time_outs, init, log_dir=str(tmp_path), device=DEV,
+                               use_cuda_graph=False, **alg_extra)
     path = os.path.join(GOLDEN, "ppo_mlp_norm_ref_checkpoint.pt")
     ref_ckpt = torch.load(path, map_location="cpu", weights_only=False)
     runner.load(path)

@@ -49,3 +49,24 @@ def test_observation_normalisers_on_the_engine_path_replay_the_reference_golden(
     lib = host_emulation.install(monkeypatch)
     runner = check_normaliser_golden("cpu", False, rng_compat=False)
     assert runner.alg.fused and {"empirical_norm_update", "empirical_normalize"} <= set(lib.calls)
+
+
+def test_logging_path_reproduces_the_reference_buffers(monkeypatch, tmp_path):
+    """SURVEY 8 f1 above the emulated ABI: device-side episode statistics flushed once per iteration against the reference's
+    `rewbuffer` / `lenbuffer` and logged loss means, TensorBoard events, the final checkpoint."""
+    pytest.importorskip("tensorboard")
+    from tests import host_emulation
+    from tests.test_gpu_ppo_parity import check_logging_path
+    host_emulation.install(monkeypatch)
+    check_logging_path("cpu", tmp_path, rng_compat=False)
+
+
+def test_reference_written_checkpoint_round_trip(monkeypatch, tmp_path):
+    """SURVEY 8 f3 above the emulated ABI: the checkpoint the reference wrote loads (parameters, normaliser buffers, Adam
+    moments / step / lr, iteration), training resumes, the checkpoint written here has the reference's structure -- and the
+    reference loads it when its install is present."""
+    pytest.importorskip("tensorboard")
+    from tests import host_emulation
+    from tests.test_gpu_ppo_parity import check_reference_checkpoint_round_trip
+    host_emulation.install(monkeypatch)
+    check_reference_checkpoint_round_trip("cpu", tmp_path, rng_compat=False)
