@@ -478,6 +478,68 @@ class EmulatedLibrary:
         return self._launch("allreduce_clip_adam")
 
 
+def _fused_forward(cls):
+    """csrc/mlp_fused.cu: the whole 3-hidden-layer MLP of one or two nets in one launch (tf32 mode), optionally with the
+    Gaussian policy head in the output epilogue, and its rollout launch plans."""
+
+    def _run_nets(self, n, nets, xs=None):
+        for i in range(n):
+            q = nets[i]
+            x = int(xs[i]) if xs is not None else q.x
+            dims = [q.K0, q.N1, q.N2, q.N3, q.N4]
+            ok = (q.N1 % 128 == 0 and 128 <= q.N1 <= 512 and q.N2 in (128, 256) and q.N3 % 32 == 0 and 32 <= q.N3 <= 128
+                  and 1 <= q.N4 <= 16 and x % 16 == 0 and q.ldx % 4 == 0)
+            if not ok:
+                return 4
+            assert q.precision in (0, nat.PREC_TF32), "the emulation covers the tf32 variant"
+            h = _mat(x, q.M, q.K0, q.ldx).astype(np.float32)
+            for l in range(4):
+                ldw = q.ldw0 if l == 0 else dims[l]
+                z = h @ _mat(q.w[l], dims[l + 1], dims[l], ldw).T
+                if q.b[l]:
+                    z = z + _view(q.b[l], dims[l + 1])
+                h = _act(q.act, z.astype(np.float32)) if l < 3 else z.astype(np.float32)
+                if l < 3 and q.h[l]:
+                    _mat(q.h[l], q.M, dims[l + 1], q.ldh[l])[:] = h
+            _mat(q.y, q.M, q.N4, q.ldy)[:] = h
+            if q.head_z:
+                A = q.N4
+                assert q.ldy == A, "the head reads mu as a dense [M, A] matrix"
+                self.rslrl_gaussian_act(q.y, q.head_std, q.head_std_type, q.head_z, q.head_actions, q.head_logp,
+                                        q.head_sigma, q.M, A, 0)
+                self.calls.pop()            # (same launch: the head is the forward's epilogue)
+                self.launches -= 1
+                if q.head_actions_host:
+                    _view(q.head_actions_host, q.M * A)[:] = _view(q.head_actions, q.M * A)
+        return 0
+
+    def rslrl_mlp3_forward(self, n, nets, stream):
+        rc = _run_nets(self, n, nets)
+        return rc if rc else self._launch("mlp3_forward")
+
+    def rslrl_mlp3_plan_create(self, n, nets, plan_out):
+        copy = (nat.Mlp3Fwd * n)()
+        for i in range(n):
+            ctypes.memmove(ctypes.byref(copy[i]), ctypes.byref(nets[i]), ctypes.sizeof(nat.Mlp3Fwd))   # captured by value
+        self._plans = getattr(self, "_plans", {})
+        handle = len(self._plans) + 1
+        self._plans[handle] = (n, copy)
+        plan_out._obj.value = handle
+        return 0
+
+    def rslrl_mlp3_plan_run(self, plan, xs, stream):
+        n, nets = self._plans[plan.value if hasattr(plan, "value") else int(plan)]
+        rc = _run_nets(self, n, nets, xs)
+        return rc if rc else self._launch("mlp3_plan_run")
+
+    def rslrl_mlp3_plan_destroy(self, plan):
+        self._plans.pop(plan.value if hasattr(plan, "value") else int(plan), None)
+
+    cls.rslrl_mlp3_forward, cls.rslrl_mlp3_plan_create = rslrl_mlp3_forward, rslrl_mlp3_plan_create
+    cls.rslrl_mlp3_plan_run, cls.rslrl_mlp3_plan_destroy = rslrl_mlp3_plan_run, rslrl_mlp3_plan_destroy
+    return cls
+
+
 def _two_launch_optimiser(cls):
     """csrc/optim.cu: the NCCL-path optimiser step as two launches (norm / clip scale / KL rule, then Adam)."""
 
@@ -519,6 +581,7 @@ def _two_launch_optimiser(cls):
 
 
 _two_launch_optimiser(EmulatedLibrary)
+_fused_forward(EmulatedLibrary)
 
 
 def install(monkeypatch) -> EmulatedLibrary:

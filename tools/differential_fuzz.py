@@ -50,6 +50,13 @@ PPO_CASES = {
     "log_std_unclipped_value": dict(noise_std_type="log", alg_overrides=dict(use_clipped_value_loss=False, max_grad_norm=0.3)),
     "one_hidden_layer": dict(hidden=[16]),
     "four_hidden_layers": dict(hidden=[32, 24, 16, 8]),
+    # tf32 mode with shapes the one-launch fused forward covers: rollout launch plans with the Gaussian head in the
+    # epilogue (observation rows 16-byte aligned: read in place; 11 columns: zero-padded staging + padded first-layer
+    # weights), fused forward of the update storing the activations
+    "tf32_fused_forward_aligned": dict(hidden=[128, 128, 32], group_dims={"policy": 12}, alg_extra=dict(gemm_precision="tf32"),
+                                       alg_overrides=dict(num_learning_epochs=1, num_mini_batches=2)),
+    "tf32_fused_forward_unaligned": dict(hidden=[128, 128, 32], alg_extra=dict(gemm_precision="tf32"),
+                                         alg_overrides=dict(num_learning_epochs=1, num_mini_batches=2)),
     "lstm_two_layers": dict(REC, policy_extra=dict(rnn_type="lstm", rnn_hidden_dim=12, rnn_num_layers=2)),
     "gru_two_layers": dict(REC, policy_extra=dict(rnn_type="gru", rnn_hidden_dim=12, rnn_num_layers=2)),
     "state_dependent_std_lstm": dict(REC, noise_std_type="log", general=True,
@@ -128,13 +135,17 @@ def main():
     def ppo(name, over, seed):
         over = dict(over)
         general = over.pop("general", False)     # configurations the engines do not take: modules + autograd functions
+        alg_extra = over.pop("alg_extra", {})
         mg.scenario_ppo_mlp(out, name, seed=seed, **dict(PPO_BASE, **over))
-        host_emulation.install(_Setattr())
+        lib = host_emulation.install(_Setattr())
         if "policy_class" in over or general:
             r = test_zz_policy_variants._check_ppo_variant(name, "cpu", general_path=False, rng_compat=False)
         else:
-            r = check_learn_iterations_against_golden(name, "cpu", rng_compat=False)
-        return "engine" if r.alg.fused else ("recurrent engine" if r.alg._recurrent_fused else "general path")
+            r = check_learn_iterations_against_golden(name, "cpu", rng_compat=False, **alg_extra)
+        path = "engine" if r.alg.fused else ("recurrent engine" if r.alg._recurrent_fused else "general path")
+        if "mlp3_plan_run" in lib.calls:
+            path += f" (one-launch rollout plan x{lib.calls.count('mlp3_plan_run')}, fused forward x{lib.calls.count('mlp3_forward')})"
+        return path
 
     def composite(name, over, seed):
         mg.scenario_ppo_mlp(out, name, seed=seed, **dict(dict(PPO_BASE, alg_overrides=E2), **over))
