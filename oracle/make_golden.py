@@ -641,6 +641,13 @@ def main():
         teacher_class="ActorCriticRecurrent", teacher_extra=dict(rnn_type="lstm", rnn_hidden_dim=16, rnn_num_layers=1),
         alg_overrides=dict(num_learning_epochs=1, gradient_length=3, max_grad_norm=0.5, loss_type="huber"),
         iterations=2, seed=32, p_done=0.15)
+    # a shape the one-launch fused forward and the 16-bit storage chain cover (3 hidden layers, widths multiples of 64,
+    # 4 actions, 16-byte observation rows): drives the tf32 / fp16 host paths above the emulated ABI on the CPU
+    todo["ppo_mlp_fused_shape"] = lambda: scenario_ppo_mlp(
+        args.out, "ppo_mlp_fused_shape", num_envs=48, num_steps=6, group_dims={"policy": 12},
+        obs_groups={"policy": ["policy"], "critic": ["policy"]}, num_actions=4, hidden=[128, 128, 64],
+        activation="elu", noise_std_type="scalar", alg_overrides=dict(num_learning_epochs=2, num_mini_batches=2),
+        iterations=1, seed=41)
     # two LSTM layers, a feed-forward teacher, windows of 3 over two epochs of 8 steps: the third window crosses the epoch
     # boundary (where the reference re-installs the start-of-rollout hidden state), one trailing step
     todo["distill_lstm2_cross"] = lambda: scenario_distillation(

@@ -34,6 +34,49 @@ def _mat(ptr, rows, cols, ld):
     return np.lib.stride_tricks.as_strided(flat, shape=(rows, cols), strides=(4 * ld, 4))
 
 
+class _HalfStore:
+    """fp16 buffers of the 16-bit storage path, with an EXACT fp32 side copy of everything the emulation writes into them.
+    The memory itself holds the rounded fp16 values (what the kernels store); reads prefer the side copy wherever it still
+    agrees with memory after rounding (anything written by other means -- a torch op, a recycled allocation -- falls back to
+    memory).  Storage rounding is thereby taken out of the host-logic tests: the fp16 chain's pointer wiring and power-of-two
+    gradient scaling must reproduce the fp32 reference to fp32 accuracy, which a wiring mistake cannot do."""
+
+    def __init__(self):
+        self.regions = []      # [start address, element count, float32 array]
+
+    def _find(self, ptr, span):
+        for r in self.regions:
+            if r[0] <= ptr and ptr + 2 * span <= r[0] + 2 * r[1]:
+                return r, (ptr - r[0]) // 2
+        return None
+
+    @staticmethod
+    def _strided(flat, off, rows, cols, ld):
+        return np.lib.stride_tricks.as_strided(flat[off:], shape=(rows, cols), strides=(flat.itemsize * ld, flat.itemsize))
+
+    def write(self, ptr, rows, cols, ld, values):
+        ptr, span = int(ptr), (rows - 1) * ld + cols
+        mem = _view(ptr, span, np.float16)
+        self._strided(mem, 0, rows, cols, ld)[:] = np.clip(values, -65504.0, 65504.0).astype(np.float16)
+        hit = self._find(ptr, span)
+        if hit is None:
+            end = ptr + 2 * span
+            self.regions = [r for r in self.regions if r[0] + 2 * r[1] <= ptr or end <= r[0]]   # drop what it overlaps
+            hit = ([ptr, span, mem.astype(np.float32)], 0)
+            self.regions.append(hit[0])
+        self._strided(hit[0][2], hit[1], rows, cols, ld)[:] = values
+
+    def read(self, ptr, rows, cols, ld):
+        ptr, span = int(ptr), (rows - 1) * ld + cols
+        mem = self._strided(_view(ptr, span, np.float16), 0, rows, cols, ld)
+        hit = self._find(ptr, span)
+        if hit is None:
+            return mem.astype(np.float32)
+        exact = self._strided(hit[0][2], hit[1], rows, cols, ld)
+        agrees = np.clip(exact, -65504.0, 65504.0).astype(np.float16) == mem
+        return np.where(agrees, exact, mem.astype(np.float32)).astype(np.float32)
+
+
 def _act(code, z):
     if code == 0:
         return z
@@ -75,6 +118,7 @@ class EmulatedLibrary:
     def __init__(self):
         self.launches = 0
         self.calls = []
+        self.half = _HalfStore()
 
     def _launch(self, name):
         self.launches += 1
@@ -186,7 +230,7 @@ class EmulatedLibrary:
                                use_clipped, dmu16, dmu16_stride, dvalue16, dvalue16_stride, grad_scale16, scale_state,
                                head, stream):
         from oracle import ppo_oracle as O
-        assert not dmu16 and not head, "the emulation covers the fp32-class objective"
+        assert not head, "the (opt-in) output-layer data gradient inside the loss kernel is not emulated"
         f = np.float32
         m = _view(mu, rows * A).reshape(rows, A)
         std = _view(std_param, A)
@@ -216,6 +260,20 @@ class EmulatedLibrary:
                                             _view(old_sigma, mb_orig * A).reshape(mb_orig, A))
         if loss_sums:
             _view(loss_sums, 3, np.float64)[:] += (out["surrogate"], out["value_loss"], out["entropy"])
+        if dmu16:
+            # S * dL/dmu, S * dL/dV as fp16: S = scale_state[2] (dynamic, a power of two derived from the previous launch's
+            # largest gradient) or the static argument; [0] / [1] publish S and 1 / S for the weight-gradient launches
+            st = _view(scale_state, 8) if scale_state else None
+            S = np.float32(st[2]) if st is not None else np.float32(grad_scale16)
+            self.half.write(dmu16, rows, A, dmu16_stride, S * out["dmu"])
+            self.half.write(dvalue16, rows, 1, dvalue16_stride, S * out["dvalue"].reshape(rows, 1))
+            if st is not None:
+                mx = max(float(np.abs(out["dmu"]).max()), float(np.abs(out["dvalue"]).max()))
+                st[0], st[1] = S, np.float32(1.0) / S
+                if mx * S > 60000.0:
+                    _view(int(scale_state) + 16, 1, np.uint32)[0] += 1
+                if mx > 0 and math.isfinite(mx):
+                    st[2] = min(max(2.0 ** math.floor(math.log2(4096.0 / mx)), 2.0 ** -20), 2.0 ** 30)
         return self._launch("ppo_loss_fwd_bwd")
 
     # ---- csrc/rnd.cu: intrinsic reward in one launch
@@ -268,17 +326,43 @@ class EmulatedLibrary:
         return self._launch("linear_forward")
 
     def rslrl_linear_backward_data(self, n, probs, precision, stream):
+        f16 = precision == nat.PREC_FP16     # 16-bit storage: dy, w (shadow), h and dx are fp16 tensors
+        rd = (lambda ptr, r, c, ld: self.half.read(ptr, r, c, ld)) if f16 else _mat
         for i in range(n):
             p = probs[i]
-            dy, w = _mat(p.dy, p.M, p.N, p.ldy), _mat(p.w, p.N, p.K, p.K)
+            dy, w = rd(p.dy, p.M, p.N, p.ldy), rd(p.w, p.N, p.K, p.K)
             dx = dy @ w
             if p.act != 0:
-                dx = dx * _act_grad_from_output(p.act, _mat(p.h, p.M, p.K, p.ldh))
+                dx = dx * _act_grad_from_output(p.act, rd(p.h, p.M, p.K, p.ldh))
             dx = dx.astype(np.float32)
-            _mat(p.dx, p.M, p.K, p.ldx)[:] = dx
+            if f16:
+                self.half.write(p.dx, p.M, p.K, p.ldx, dx)
+            else:
+                _mat(p.dx, p.M, p.K, p.ldx)[:] = dx
             if p.db_prev:
                 _view(p.db_prev, p.K)[:] += dx.sum(0)
         return self._launch("linear_backward_data")
+
+    # ---- csrc/dgrad_fused.cu: data gradients of the two wide hidden layers of both nets in one launch (fp16 chain)
+    def rslrl_dgrad_chain16(self, n, nets, stream):
+        for i in range(n):
+            q = nets[i]
+            if not (q.N3 in (64, 128) and q.N2 in (128, 256) and q.N1 in (128, 256, 512)):
+                return 4
+            rd = self.half.read
+            dz3 = rd(q.dz3, q.M, q.N3, q.ld_dz3)
+            dz2 = (dz3 @ rd(q.w3, q.N3, q.N2, q.N2)) * _act_grad_from_output(q.act, rd(q.h2, q.M, q.N2, q.ldh2))
+            self.half.write(q.dz2, q.M, q.N2, q.ld_dz2, dz2.astype(np.float32))
+            dz1 = (dz2 @ rd(q.w2, q.N2, q.N1, q.N1)) * _act_grad_from_output(q.act, rd(q.h1, q.M, q.N1, q.ldh1))
+            self.half.write(q.dz1, q.M, q.N1, q.ld_dz1, dz1.astype(np.float32))
+        return self._launch("dgrad_chain16")
+
+    # ---- csrc/core.cu: fp16 shadows (flat weights, permuted minibatch observations)
+    def rslrl_convert_f32_f16(self, src, ld_src, dst, ld_dst, rows, cols, cols_pad, stream):
+        vals = np.zeros((rows, cols_pad), np.float32)
+        vals[:, :cols] = _mat(src, rows, cols, ld_src)
+        self.half.write(dst, rows, cols_pad, ld_dst, vals)
+        return self._launch("convert_f32_f16")
 
     def rslrl_linear_backward_head(self, n, probs, stream):
         """Narrow output layer: data gradient (x activation derivative of the previous layer), weight and bias gradient."""
@@ -294,9 +378,10 @@ class EmulatedLibrary:
         return self._launch("linear_backward_head")
 
     def rslrl_linear_backward_weight(self, n, probs, precision, stream):
+        rd = (lambda ptr, r, c, ld: self.half.read(ptr, r, c, ld)) if precision == nat.PREC_FP16 else _mat
         for i in range(n):
             p = probs[i]
-            dy, x = _mat(p.dy, p.M, p.N, p.ldy), _mat(p.x, p.M, p.K, p.ldx)
+            dy, x = rd(p.dy, p.M, p.N, p.ldy), rd(p.x, p.M, p.K, p.ldx)
             scale = np.float32(p.scale if p.scale != 0 else 1.0)
             if p.scale_dev:
                 scale = scale * _view(p.scale_dev, 1)[0]
@@ -474,7 +559,7 @@ class EmulatedLibrary:
         if zero_grad:
             g_ext[:] = 0
         if values16:
-            _view(values16, numel, np.float16)[:] = p.astype(np.float16)
+            self.half.write(values16, 1, numel, numel, p.reshape(1, -1))
         return self._launch("allreduce_clip_adam")
 
 
@@ -491,16 +576,22 @@ def _fused_forward(cls):
                   and 1 <= q.N4 <= 16 and x % 16 == 0 and q.ldx % 4 == 0)
             if not ok:
                 return 4
-            assert q.precision in (0, nat.PREC_TF32), "the emulation covers the tf32 variant"
+            f16 = q.precision == nat.PREC_FP16     # layers 2-4 read the fp16 weight shadow, activations are stored as fp16
             h = _mat(x, q.M, q.K0, q.ldx).astype(np.float32)
             for l in range(4):
-                ldw = q.ldw0 if l == 0 else dims[l]
-                z = h @ _mat(q.w[l], dims[l + 1], dims[l], ldw).T
+                if l == 0 or not f16:
+                    w = _mat(q.w[l], dims[l + 1], dims[l], q.ldw0 if l == 0 else dims[l])
+                else:
+                    w = self.half.read(q.w[l], dims[l + 1], dims[l], dims[l])
+                z = h @ w.T
                 if q.b[l]:
                     z = z + _view(q.b[l], dims[l + 1])
                 h = _act(q.act, z.astype(np.float32)) if l < 3 else z.astype(np.float32)
                 if l < 3 and q.h[l]:
-                    _mat(q.h[l], q.M, dims[l + 1], q.ldh[l])[:] = h
+                    if f16:
+                        self.half.write(q.h[l], q.M, dims[l + 1], q.ldh[l], h)
+                    else:
+                        _mat(q.h[l], q.M, dims[l + 1], q.ldh[l])[:] = h
             _mat(q.y, q.M, q.N4, q.ldy)[:] = h
             if q.head_z:
                 A = q.N4

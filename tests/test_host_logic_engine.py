@@ -70,3 +70,28 @@ def test_reference_written_checkpoint_round_trip(monkeypatch, tmp_path):
     from tests.test_gpu_ppo_parity import check_reference_checkpoint_round_trip
     host_emulation.install(monkeypatch)
     check_reference_checkpoint_round_trip("cpu", tmp_path, rng_compat=False)
+
+
+@pytest.mark.parametrize("precision", ["tf32", "fp16"])
+def test_fused_forward_and_16_bit_storage_chain_host_logic(precision, monkeypatch):
+    """The tensor-core modes' own host paths at a shape they cover (golden `ppo_mlp_fused_shape`: MLP [128, 128, 64]):
+    one-launch rollout plans with the Gaussian head in the epilogue and the fused forward (`tf32`), and on top of that the
+    16-bit storage chain of the bench default (`fp16`): fp16 weight shadow refreshed inside the optimiser step, fp16
+    observations / activations / layer gradients, the loss launch's dynamic power-of-two gradient scale and its inverse in
+    the weight-gradient launch, the fused data-gradient chain, all weight gradients in one grouped launch.  The emulation
+    computes in fp32 and keeps an exact side copy of every fp16 buffer (tests/host_emulation._HalfStore), so a correct wiring
+    lands on the fp32 reference at fp32 tolerances; what the storage rounding itself costs is the GPU tests' subject."""
+    from collections import Counter
+    from tests import host_emulation
+    from tests.test_gpu_ppo_parity import check_learn_iterations_against_golden
+    lib = host_emulation.install(monkeypatch)
+    runner = check_learn_iterations_against_golden("ppo_mlp_fused_shape", "cpu", gemm_precision=precision, rng_compat=False)
+    eng, n = runner.alg._engine, Counter(lib.calls)
+    assert eng.fused_fwd and n["mlp3_plan_run"] == 6 and n["gaussian_act"] == 0      # one launch per env step
+    assert n["mlp3_forward"] == 4 + 1                                               # 4 minibatches + the last values
+    if precision == "fp16":
+        assert eng.f16 and eng.head16 and eng.dgrad_chain and eng.scale_state is not None
+        assert n["dgrad_chain16"] == 4 and n["linear_backward_weight"] == 4 and n["linear_backward_head"] == 0
+        assert n["ppo_loss_fwd_bwd"] == 4 + 1                                       # + the one-off scale calibration
+        assert n["convert_f32_f16"] >= 2                                            # weight shadow, minibatch observations
+        assert float(eng.scale_state[0]) * float(eng.scale_state[1]) == 1.0 and float(eng.scale_state[0]) >= 1.0

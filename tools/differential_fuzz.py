@@ -57,6 +57,14 @@ PPO_CASES = {
                                        alg_overrides=dict(num_learning_epochs=1, num_mini_batches=2)),
     "tf32_fused_forward_unaligned": dict(hidden=[128, 128, 32], alg_extra=dict(gemm_precision="tf32"),
                                          alg_overrides=dict(num_learning_epochs=1, num_mini_batches=2)),
+    # the 16-bit storage chain (the bench default): fp16 weight shadow, activations, observations and layer gradients,
+    # fused forward, loss with the dynamic power-of-two gradient scale, fused data-gradient chain, grouped weight
+    # gradients, shadow refresh inside the optimiser step -- the emulation keeps an exact side copy of every fp16 buffer,
+    # so a correct wiring reproduces the fp32 reference to fp32 accuracy
+    "fp16_storage_chain": dict(hidden=[128, 128, 64], group_dims={"policy": 12}, alg_extra=dict(gemm_precision="fp16"),
+                               alg_overrides=dict(num_learning_epochs=2, num_mini_batches=2)),
+    "fp16_storage_chain_unaligned_obs": dict(hidden=[256, 128, 64], alg_extra=dict(gemm_precision="fp16"),
+                                             alg_overrides=dict(num_learning_epochs=1, num_mini_batches=2)),
     "lstm_two_layers": dict(REC, policy_extra=dict(rnn_type="lstm", rnn_hidden_dim=12, rnn_num_layers=2)),
     "gru_two_layers": dict(REC, policy_extra=dict(rnn_type="gru", rnn_hidden_dim=12, rnn_num_layers=2)),
     "state_dependent_std_lstm": dict(REC, noise_std_type="log", general=True,
