@@ -68,6 +68,56 @@ def snapshot(root_module_name):
     return out
 
 
+def instance_attributes():
+    """Public attribute names of live objects of the reference (what user code reads: `runner.alg.policy`,
+    `alg.learning_rate`, `storage.saved_hidden_states_a`, ...): an OnPolicyRunner with a recurrent policy, RND and
+    symmetry switched on, and a DistillationRunner, both on a tiny synthetic env on the CPU."""
+    import contextlib
+    import io
+
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    import make_golden as mg
+    from oracle.symmetry_example import mirror_augmentation
+    from rsl_rl.runners import DistillationRunner, OnPolicyRunner
+
+    Env = mg.make_env_class()
+    public = lambda obj: sorted(k for k in vars(obj) if not k.startswith("_"))
+    out = {}
+    with contextlib.redirect_stdout(io.StringIO()):
+        env = Env(8, {"policy": 11}, 4, seed=1)
+        cfg = dict(num_steps_per_env=4, save_interval=10, obs_groups={"policy": ["policy"], "critic": ["policy"]},
+                   policy=dict(class_name="ActorCriticRecurrent", actor_hidden_dims=[8], critic_hidden_dims=[8],
+                               rnn_hidden_dim=8),
+                   algorithm=dict(class_name="PPO",
+                                  rnd_cfg=dict(weight=1.0, weight_schedule=None, reward_normalization=False,
+                                               state_normalization=False, learning_rate=1e-3, num_outputs=1,
+                                               predictor_hidden_dims=[-1], target_hidden_dims=[-1]),
+                                  symmetry_cfg=dict(use_data_augmentation=True, use_mirror_loss=True, mirror_loss_coeff=0.5,
+                                                    data_augmentation_func=mirror_augmentation)))
+        runner = OnPolicyRunner(env, cfg, log_dir=None, device="cpu")
+        alg = runner.alg
+        alg.act(env.get_observations())          # fills the transition, creates the hidden states
+        out["OnPolicyRunner"] = public(runner)
+        out["PPO"] = public(alg)
+        out["ActorCriticRecurrent"] = public(alg.policy)
+        out["Memory"] = public(alg.policy.memory_a)
+        out["RolloutStorage[rl]"] = public(alg.storage)
+        out["Transition"] = public(alg.transition)
+        out["RandomNetworkDistillation"] = public(alg.rnd)
+        env = Env(8, {"policy": 6, "priv": 3}, 2, seed=2)
+        cfg = dict(num_steps_per_env=4, save_interval=10, obs_groups={"policy": ["policy"], "teacher": ["policy", "priv"]},
+                   policy=dict(class_name="StudentTeacher", student_hidden_dims=[8], teacher_hidden_dims=[8],
+                               student_obs_normalization=True),
+                   algorithm=dict(class_name="Distillation"))
+        runner = DistillationRunner(env, cfg, log_dir=None, device="cpu")
+        out["DistillationRunner"] = public(runner)
+        out["Distillation"] = public(runner.alg)
+        out["StudentTeacher"] = public(runner.alg.policy)
+        out["EmpiricalNormalization"] = public(runner.alg.policy.student_obs_normalizer)
+        out["RolloutStorage[distillation]"] = public(runner.alg.storage)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
@@ -76,9 +126,10 @@ def main():
     sys.path.insert(0, os.path.join(HERE, "_shim"))
     sys.path.insert(0, args.ref)
     snap = snapshot("rsl_rl")
+    snap["__instance_attributes__"] = instance_attributes()
     with open(args.out, "w") as f:
         json.dump(snap, f, indent=1, sort_keys=True)
-    n = sum(len(v) for v in snap.values())
+    n = sum(len(v) for k, v in snap.items() if not k.startswith("__"))
     print("wrote", args.out, n, "public names")
 
 

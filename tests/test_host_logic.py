@@ -326,3 +326,53 @@ def test_public_api_surface_matches_the_reference_snapshot():
             else:
                 walk(f"{pkg}.{name}", getattr(mod, name), d["members"])
     assert not problems, "\n".join(problems)
+
+
+def test_instance_attributes_of_the_reference_are_present(monkeypatch):
+    """What user code reads from live objects (`alg.policy`, `alg.learning_rate`, `alg.rnd_optimizer`,
+    `storage.saved_hidden_states_a`, `runner.current_learning_iteration`, ...): every public instance attribute the
+    reference's runner / algorithm / policy / storage / transition objects carry (recorded by oracle/make_api_snapshot.py
+    from live reference objects) exists on this library's objects built from the same configurations."""
+    import json
+    import os
+
+    import torch
+
+    from oracle.symmetry_example import mirror_augmentation
+    from tests import host_emulation
+    from tests.golden_util import GOLDEN
+    host_emulation.install(monkeypatch)
+    from rsl_rl_b200.env import ReplayVecEnv
+    from rsl_rl_b200.runners import DistillationRunner, OnPolicyRunner
+
+    want = json.load(open(os.path.join(GOLDEN, "reference_api.json")))["__instance_attributes__"]
+    N = 8
+    env = ReplayVecEnv({"policy": torch.randn(3, N, 11)}, torch.zeros(2, N), torch.zeros(2, N, dtype=torch.long), None, 4,
+                       device="cpu")
+    cfg = dict(num_steps_per_env=4, save_interval=10, obs_groups={"policy": ["policy"], "critic": ["policy"]},
+               policy=dict(class_name="ActorCriticRecurrent", actor_hidden_dims=[8], critic_hidden_dims=[8], rnn_hidden_dim=8),
+               algorithm=dict(class_name="PPO", use_cuda_graph=False, rng_compat=False,
+                              rnd_cfg=dict(weight=1.0, weight_schedule=None, reward_normalization=False,
+                                           state_normalization=False, learning_rate=1e-3, num_outputs=1,
+                                           predictor_hidden_dims=[-1], target_hidden_dims=[-1]),
+                              symmetry_cfg=dict(use_data_augmentation=True, use_mirror_loss=True, mirror_loss_coeff=0.5,
+                                                data_augmentation_func=mirror_augmentation)))
+    runner = OnPolicyRunner(env, cfg, log_dir=None, device="cpu")
+    alg = runner.alg
+    with torch.inference_mode():
+        alg.act(env.get_observations())
+    objects = {"OnPolicyRunner": runner, "PPO": alg, "ActorCriticRecurrent": alg.policy, "Memory": alg.policy.memory_a,
+               "RolloutStorage[rl]": alg.storage, "Transition": alg.transition, "RandomNetworkDistillation": alg.rnd}
+    env = ReplayVecEnv({"policy": torch.randn(3, N, 6), "priv": torch.randn(3, N, 3)}, torch.zeros(2, N),
+                       torch.zeros(2, N, dtype=torch.long), None, 2, device="cpu")
+    cfg = dict(num_steps_per_env=4, save_interval=10, obs_groups={"policy": ["policy"], "teacher": ["policy", "priv"]},
+               policy=dict(class_name="StudentTeacher", student_hidden_dims=[8], teacher_hidden_dims=[8],
+                           student_obs_normalization=True),
+               algorithm=dict(class_name="Distillation"))
+    drunner = DistillationRunner(env, cfg, log_dir=None, device="cpu")
+    objects.update({"DistillationRunner": drunner, "Distillation": drunner.alg, "StudentTeacher": drunner.alg.policy,
+                    "EmpiricalNormalization": drunner.alg.policy.student_obs_normalizer,
+                    "RolloutStorage[distillation]": drunner.alg.storage})
+    assert set(objects) == set(want)
+    missing = [f"{k}.{a}" for k, names in want.items() for a in names if not hasattr(objects[k], a)]
+    assert not missing, missing
