@@ -284,7 +284,7 @@ def test_public_api_surface_matches_the_reference_snapshot():
 
     from tests.golden_util import GOLDEN
 
-    snap = json.load(open(os.path.join(GOLDEN, "reference_api.json")))
+    snap = {k: v for k, v in json.load(open(os.path.join(GOLDEN, "reference_api.json"))).items() if not k.startswith("__")}
     assert sum(len(v) for v in snap.values()) >= 24
 
     def sig(fn):
