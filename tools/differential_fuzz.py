@@ -48,6 +48,9 @@ PPO_CASES = {
                                   group_dims={"policy": 7, "extra": 3},
                                   obs_groups={"policy": ["policy"], "critic": ["policy", "extra"]}),
     "log_std_unclipped_value": dict(noise_std_type="log", alg_overrides=dict(use_clipped_value_loss=False, max_grad_norm=0.3)),
+    "wide_action_head": dict(num_actions=17),            # beyond the narrow-head kernel (N <= 12): general wgrad / dgrad
+    "single_minibatch_single_epoch": dict(alg_overrides=dict(num_learning_epochs=1, num_mini_batches=1)),
+    "hidden_dim_minus_one": dict(hidden=[-1, 16]),       # -1 = the input width (mlp.py:58-60)
     "one_hidden_layer": dict(hidden=[16]),
     "four_hidden_layers": dict(hidden=[32, 24, 16, 8]),
     # tf32 mode with shapes the one-launch fused forward covers: rollout launch plans with the Gaussian head in the
